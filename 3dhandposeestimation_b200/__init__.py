@@ -1,0 +1,19 @@
+"""B200-native (sm_100a) implementation of the geometric hot path of
+hongrui16/3DHandPoseEstimation: the batched MANO layer, the RHD 21-joint
+forward-kinematics layer, the pinhole projection and the visible-joint
+MPJPE / L2 reductions — same ``nn.Module`` signatures as the reference's
+``network/sub_modules``, arithmetic in hand-written CUDA behind a C ABI
+(include/mano_b200.h).  No CPU fallback.
+
+The directory name is not a Python identifier; import it with
+``importlib.import_module("3dhandposeestimation_b200")`` or through the
+``handpose_b200`` alias module at the repository root.
+"""
+from . import assets  # noqa: F401
+from ._cabi import ManoB200Error, lib as load_library  # noqa: F401
+from .criterions import L2Loss, MPJPE, compute_regularization_loss  # noqa: F401
+from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv  # noqa: F401
+from .mano_layer import ManoLayer  # noqa: F401
+
+__all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "MPJPE", "L2Loss",
+           "compute_regularization_loss", "ManoB200Error", "assets", "load_library"]

@@ -1,0 +1,103 @@
+"""ctypes binding of libmano_b200.so (the C ABI declared in include/mano_b200.h).
+
+There is no fallback: if the shared library is missing, cannot be loaded or the
+device is not a B200, every entry point raises.  The library is built in-tree by
+``build.py`` (``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmano_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mano_b200.h")
+
+MODE_FP32, MODE_F16X3, MODE_F16 = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "f16x3": MODE_F16X3, "f16": MODE_F16}
+BWD_WORKSPACE_VALID = 1
+REDUCE_MPJPE_MM, REDUCE_L2 = 0, 1
+VIS_F32, VIS_U8 = 0, 1
+
+_p = C.c_void_p
+_i = C.c_int
+_ll = C.c_longlong
+_f = C.c_float
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/mano_b200.h declares
+SIGNATURES = {
+    "mb_abi_version": (_i, []),
+    "mb_error_string": (C.c_char_p, [_i]),
+    "mb_check_device": (_i, []),
+    "mb_mano_blob_bytes": (_sz, []),
+    "mb_mano_pack_constants": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "mb_mano_workspace_bytes": (_sz, [_i, _i]),
+    "mb_mano_forward": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "mb_mano_backward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "mb_lbs_forward": (_i, [_p, _p, _i, _p, _i, _p, _p, _p]),
+    "mb_fk_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "mb_fk_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "mb_project_uv_forward": (_i, [_p, _p, _i, _i, _p, _p]),
+    "mb_project_uv_backward": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "mb_masked_joint_reduce": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p]),
+    "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
+    "mb_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
+}
+
+
+class ManoB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def header_symbols() -> list:
+    """Function names declared (MB_API ...) in include/mano_b200.h."""
+    with open(HEADER_PATH) as fh:
+        text = fh.read()
+    return re.findall(r"MB_API\s+[\w\s\*]+?\b(mb_\w+)\s*\(", text)
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises ManoB200Error when it is absent —
+    the product has no CPU or PyTorch fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ManoB200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU/PyTorch fallback for this path.")
+    try:
+        handle = C.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise ManoB200Error(f"cannot load {LIB_PATH}: {exc}") from exc
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as exc:
+            raise ManoB200Error(f"{LIB_PATH} does not export {name}") from exc
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().mb_error_string(rc).decode()
+        raise ManoB200Error(f"{what} failed ({rc}): {msg}")
+
+
+def ptr(t):
+    """Raw device/host pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle(device=None):
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,224 @@
+// api.cu — extern "C" entry points of the MANO path (see include/mano_b200.h).
+#include <string.h>
+#include "common.cuh"
+
+using namespace mb;
+
+namespace mb {
+// blend_tc.cu (tcgen05 path); returns MB_E_RANGE when the mode is not built
+int launch_blend_tc_forward(const void* blob, const float* feat, float* v_posed, int B, int mode, cudaStream_t s);
+int launch_blend_tc_backward(const void* blob, const float* dv_posed, float* dfeat, int B, int mode, cudaStream_t s);
+size_t blend_tc_blob_bytes();
+void blend_tc_pack(const float* basis, void* host_blob_tc);
+}  // namespace mb
+
+extern "C" int mb_abi_version(void) { return MB_ABI_VERSION; }
+
+extern "C" const char* mb_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case MB_E_NULL: return "mano_b200: a required pointer is NULL";
+        case MB_E_RANGE: return "mano_b200: argument out of range (B < 0, pose_num outside [1,45], unknown mode/kind)";
+        case MB_E_WORKSPACE: return "mano_b200: workspace too small (see mb_mano_workspace_bytes)";
+        case MB_E_ALIGN: return "mano_b200: pointer must be 16-byte aligned";
+        case MB_E_MODEL: return "mano_b200: model outside supported limits (<= 8 bones per vertex, <= 3200 skin weights, parents before children)";
+        case MB_E_DEVICE: return "mano_b200: this library only runs on compute capability 10.x (B200, sm_100a)";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "mano_b200: unknown error";
+}
+
+extern "C" int mb_check_device(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return (int)e;
+    return major == 10 ? 0 : MB_E_DEVICE;
+}
+
+extern "C" size_t mb_mano_blob_bytes(void) { return blob_layout().total + blend_tc_blob_bytes(); }
+
+extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const float* jb, const float* pca, int nc,
+                                      const float* pose_mean, const float* skin_w, const int32_t* skin_b,
+                                      const int32_t* parents, void* host_blob) {
+    if (!basis || !j0 || !jb || !pca || !pose_mean || !skin_w || !skin_b || !parents || !host_blob) return MB_E_NULL;
+    if (nc < 1 || nc > NAA) return MB_E_RANGE;
+    const BlobLayout L = blob_layout();
+    char* out = reinterpret_cast<char*>(host_blob);
+    memset(out, 0, L.total);
+
+    BlobHeader* H = reinterpret_cast<BlobHeader*>(out + L.header);
+    H->magic = 0x4d423230;
+    H->abi = MB_ABI_VERSION;
+    H->nc = nc;
+    if (parents[0] >= 0) return MB_E_MODEL;
+    int maxd = 0;
+    for (int i = 0; i < NJ; ++i) {
+        H->parents[i] = parents[i];
+        if (i > 0 && (parents[i] < 0 || parents[i] >= i)) return MB_E_MODEL;
+        H->depth[i] = i == 0 ? 0 : H->depth[parents[i]] + 1;
+        if (H->depth[i] > maxd) maxd = H->depth[i];
+    }
+    H->max_depth = maxd;
+    for (int i = 1; i < NJ; ++i) {
+        const int p = parents[i];
+        H->children[p][H->n_children[p]++] = i;
+    }
+    for (int i = 0; i < NJ; ++i)
+        if (H->n_children[i] > H->max_children_at_depth[H->depth[i]]) H->max_children_at_depth[H->depth[i]] = H->n_children[i];
+
+    float* b = reinterpret_cast<float*>(out + L.basis);
+    float* bt = reinterpret_cast<float*>(out + L.basis_t);
+    for (int k = 0; k < FEAT_K; ++k)
+        for (int c = 0; c < NVC; ++c) {
+            const float v = basis[(size_t)k * NVC + c];
+            b[(size_t)k * VP_PITCH + c] = v;
+            bt[(size_t)c * FEAT_K + k] = v;
+        }
+    memcpy(out + L.j0, j0, sizeof(float) * NJ * 3);
+    memcpy(out + L.jb, jb, sizeof(float) * NJ * 3 * NB);
+    memcpy(out + L.pca, pca, sizeof(float) * nc * NAA);
+    memcpy(out + L.pose_mean, pose_mean, sizeof(float) * NAA);
+
+    float* sw = reinterpret_cast<float*>(out + L.skin_w);
+    uint8_t* sb = reinterpret_cast<uint8_t*>(out + L.skin_b);
+    uint8_t* sc = reinterpret_cast<uint8_t*>(out + L.skin_cnt);
+    int* cptr = reinterpret_cast<int*>(out + L.csc_ptr);
+    int* cv = reinterpret_cast<int*>(out + L.csc_v);
+    float* cw = reinterpret_cast<float*>(out + L.csc_w);
+    int per_bone[NJ] = {0};
+    int nnz = 0;
+    for (int v = 0; v < NV; ++v) {
+        int cnt = 0;
+        for (int s = 0; s < MAX_INFL; ++s) {
+            const float w = skin_w[v * MAX_INFL + s];
+            const int bi = skin_b[v * MAX_INFL + s];
+            if (w == 0.f) continue;
+            if (bi < 0 || bi >= NJ) return MB_E_MODEL;
+            sw[v * MAX_INFL + cnt] = w;
+            sb[v * MAX_INFL + cnt] = (uint8_t)bi;
+            ++cnt; ++per_bone[bi]; ++nnz;
+        }
+        sc[v] = (uint8_t)cnt;
+    }
+    if (nnz > 3200) return MB_E_MODEL;
+    cptr[0] = 0;
+    for (int k = 0; k < NJ; ++k) cptr[k + 1] = cptr[k] + per_bone[k];
+    int fill[NJ];
+    for (int k = 0; k < NJ; ++k) fill[k] = cptr[k];
+    for (int v = 0; v < NV; ++v)
+        for (int s = 0; s < sc[v]; ++s) {
+            const int bi = sb[v * MAX_INFL + s];
+            cv[fill[bi]] = v;
+            cw[fill[bi]] = sw[v * MAX_INFL + s];
+            ++fill[bi];
+        }
+    H->csc_nnz = nnz;
+    blend_tc_pack(basis, out + L.total);
+    return 0;
+}
+
+extern "C" size_t mb_mano_workspace_bytes(int B, int mode) {
+    (void)mode;
+    if (B < 0) return 0;
+    return work_layout(B).total;
+}
+
+static int check_common(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B, int mode,
+                        const void* workspace, size_t workspace_bytes) {
+    if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
+    if (mode != MB_MODE_FP32 && mode != MB_MODE_F16X3 && mode != MB_MODE_F16) return MB_E_RANGE;
+    if (B == 0) return 0;
+    if (!blob || !rot || !coeffs || !betas) return MB_E_NULL;
+    if (!workspace) return MB_E_NULL;
+    if (workspace_bytes < work_layout(B).total) return MB_E_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(blob) & 15)) return MB_E_ALIGN;
+    return 0;
+}
+
+static int blend_forward(const void* blob, const float* feat, float* v_posed, int B, int mode, cudaStream_t s) {
+    if (mode == MB_MODE_FP32) {
+        const BlobLayout L = blob_layout();
+        return launch_sgemm(feat, FEAT_K, blob_ptr<float>(blob, L.basis), VP_PITCH, v_posed, VP_PITCH, B, NVC, FEAT_K, s);
+    }
+    return launch_blend_tc_forward(blob, feat, v_posed, B, mode, s);
+}
+
+static int blend_backward(const void* blob, const float* dv_posed, float* dfeat, int B, int mode, cudaStream_t s) {
+    if (mode == MB_MODE_FP32) {
+        const BlobLayout L = blob_layout();
+        return launch_sgemm(dv_posed, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s);
+    }
+    return launch_blend_tc_backward(blob, dv_posed, dfeat, B, mode, s);
+}
+
+extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                               int B, int mode, float* verts, float* joints, void* workspace, size_t workspace_bytes,
+                               mb_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (verts == nullptr) {      // joints-only: no workspace needed
+        if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
+        if (B == 0) return 0;
+        if (!blob || !rot || !coeffs || !betas || !joints) return MB_E_NULL;
+        return launch_joints_only_forward(blob, nc, rot, coeffs, betas, B, joints, s);
+    }
+    int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
+    if (rc || B == 0) return rc;
+    if (!joints) return MB_E_NULL;
+    if (reinterpret_cast<uintptr_t>(verts) & 15) return MB_E_ALIGN;
+    const WorkLayout W = work_layout(B);
+    char* ws = reinterpret_cast<char*>(workspace);
+    float* feat = reinterpret_cast<float*>(ws + W.feat);
+    float* bone = reinterpret_cast<float*>(ws + W.bone);
+    float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
+    if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, feat, bone, joints, s))) return rc;
+    if ((rc = blend_forward(blob, feat, v_posed, B, mode, s))) return rc;
+    return launch_lbs_forward(blob, v_posed, VP_PITCH, bone, B, verts, joints, s);
+}
+
+extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                                const float* g_verts, const float* g_joints, int B, int mode, int flags,
+                                float* g_rot, float* g_coeffs, float* g_betas, void* workspace, size_t workspace_bytes,
+                                mb_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g_verts == nullptr) {    // the heads' case: only the 21 joints carry gradient
+        if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
+        if (B == 0) return 0;
+        if (!blob || !rot || !coeffs || !betas || !g_joints || !g_rot || !g_coeffs || !g_betas) return MB_E_NULL;
+        return launch_joints_only_backward(blob, nc, rot, coeffs, betas, g_joints, B, g_rot, g_coeffs, g_betas, s);
+    }
+    int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
+    if (rc || B == 0) return rc;
+    if (!g_joints || !g_rot || !g_coeffs || !g_betas) return MB_E_NULL;
+    const WorkLayout W = work_layout(B);
+    char* ws = reinterpret_cast<char*>(workspace);
+    float* feat = reinterpret_cast<float*>(ws + W.feat);
+    float* bone = reinterpret_cast<float*>(ws + W.bone);
+    float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
+    float* dv_posed = reinterpret_cast<float*>(ws + W.dv_posed);
+    float* dbone = reinterpret_cast<float*>(ws + W.dbone);
+    float* dfeat = reinterpret_cast<float*>(ws + W.dfeat);
+    if (!(flags & MB_BWD_WORKSPACE_VALID)) {
+        // recompute the forward intermediates; joints of the recompute go to scratch (dfeat is free until step 3)
+        float* scratch_joints = dfeat;      // B*63 floats <= B*148
+        if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, feat, bone, scratch_joints, s))) return rc;
+        if ((rc = blend_forward(blob, feat, v_posed, B, mode, s))) return rc;
+    }
+    if ((rc = launch_lbs_backward(blob, v_posed, VP_PITCH, bone, g_verts, g_joints, B, dv_posed, dbone, s))) return rc;
+    if ((rc = blend_backward(blob, dv_posed, dfeat, B, mode, s))) return rc;
+    return launch_pose_backward(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
+}
+
+extern "C" int mb_lbs_forward(const void* blob, const float* v_posed, int pitch, const float* bone, int B,
+                              float* verts, float* joints, mb_stream_t stream) {
+    if (B < 0 || pitch < NVC || (pitch & 3)) return MB_E_RANGE;
+    if (B == 0) return 0;
+    if (!blob || !v_posed || !bone || !verts) return MB_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(verts) & 15) || (reinterpret_cast<uintptr_t>(v_posed) & 15) ||
+        (reinterpret_cast<uintptr_t>(bone) & 15))
+        return MB_E_ALIGN;
+    return launch_lbs_forward(blob, v_posed, pitch, bone, B, verts, joints, (cudaStream_t)stream);
+}

@@ -1,0 +1,176 @@
+// fk_math.cuh — per-sample math of the RHD 21-joint forward-kinematics layer.
+// __host__ __device__ so tests can run the identical code on the CPU.
+//
+// Reference: ForwardKinematics.forward, forwardKinematicsLayer.py:147-330:
+//   R_root = Rx Ry Rz (root_angles)                                   :214-215, :59-96
+//   node i (A1..E4): parent = root if i%4==0 else node i-1            :225-230
+//   local angles from other_angles[23] through the DOF map            :239-274
+//   R_i = R_parent R_local ; p_i = p_parent + L_i R_i[:,2]            :286-308
+//   xyz = p * index_root_bone_length + kp_coord_xyz_root              :321, :333-358
+//   optional per-finger order swap                                    :324-327
+//   uv = (K xyz)_xy / (K xyz)_z, z==0 -> 1e-10                        utils/coordinate_trans.py:48-65
+#pragma once
+#include "hand_math.cuh"
+
+namespace mb {
+
+constexpr int FK_NODES = 20;
+constexpr int FK_OA = 23;
+
+// local Euler angles of segment `seg` (0..2) of finger f (0 = thumb)
+HD void fk_local_angles(const float* oa, int f, int seg, float& x, float& y, float& z) {
+    x = 0.f; y = 0.f; z = 0.f;
+    if (f == 0) {
+        if (seg == 0) { x = oa[0]; y = oa[1]; z = oa[2]; }
+        else if (seg == 1) { x = oa[3]; y = oa[4]; z = oa[5]; }
+        else { y = oa[6]; }
+    } else {
+        const int b = 7 + 4 * (f - 1);
+        if (seg == 0) { x = oa[b]; y = oa[b + 1]; }
+        else if (seg == 1) { x = oa[b + 2]; }
+        else { x = oa[b + 3]; }
+    }
+}
+// scatter (gx,gy,gz) of a segment's local angles back to other_angles
+HD void fk_scatter_angles(float* g_oa, int f, int seg, const V3& g) {
+    if (f == 0) {
+        if (seg == 0) { g_oa[0] += g.x; g_oa[1] += g.y; g_oa[2] += g.z; }
+        else if (seg == 1) { g_oa[3] += g.x; g_oa[4] += g.y; g_oa[5] += g.z; }
+        else { g_oa[6] += g.y; }
+    } else {
+        const int b = 7 + 4 * (f - 1);
+        if (seg == 0) { g_oa[b] += g.x; g_oa[b + 1] += g.y; }
+        else if (seg == 1) { g_oa[b + 2] += g.x; }
+        else { g_oa[b + 3] += g.x; }
+    }
+}
+// output slot of node n (1..20) — identity, or reversed inside its finger when swapping
+HD int fk_out_slot(int n, int swap) {
+    if (!swap) return n;
+    const int i = 1 + 4 * ((n - 1) / 4);
+    return 2 * i + 3 - n;
+}
+
+HD void project_point(const float* K, float x, float y, float z, float& u, float& v) {
+    const float px = fmaf(K[0], x, fmaf(K[1], y, K[2] * z));
+    const float py = fmaf(K[3], x, fmaf(K[4], y, K[5] * z));
+    float pz = fmaf(K[6], x, fmaf(K[7], y, K[8] * z));
+    if (pz == 0.f) pz = 1e-10f;
+    u = px / pz; v = py / pz;
+}
+// gradient of project_point w.r.t. (x,y,z); on the pz==0 branch the divisor is a constant
+HD V3 project_point_bwd(const float* K, float x, float y, float z, float gu, float gv) {
+    const float px = fmaf(K[0], x, fmaf(K[1], y, K[2] * z));
+    const float py = fmaf(K[3], x, fmaf(K[4], y, K[5] * z));
+    float pz = fmaf(K[6], x, fmaf(K[7], y, K[8] * z));
+    const bool zero = (pz == 0.f);
+    if (zero) pz = 1e-10f;
+    const float inv = 1.f / pz;
+    const float dpx = gu * inv, dpy = gv * inv;
+    const float dpz = zero ? 0.f : -(gu * px * inv + gv * py * inv) * inv;
+    return v3(fmaf(K[0], dpx, fmaf(K[3], dpy, K[6] * dpz)),
+              fmaf(K[1], dpx, fmaf(K[4], dpy, K[7] * dpz)),
+              fmaf(K[2], dpx, fmaf(K[5], dpy, K[8] * dpz)));
+}
+
+// One sample forward.  xyz[63], uv[42] may be strided (element stride 1, caller gives row base).
+HD void fk_forward_sample(const float* ra, const float* oa, const float* bl, const float* K, float s,
+                          const float* root, int swap, float* xyz, float* uv) {
+    const M3 Rroot = euler_xyz(ra[0], ra[1], ra[2]);
+    {
+        xyz[0] = root[0]; xyz[1] = root[1]; xyz[2] = root[2];      // wrist: p = 0
+        float u, v;
+        project_point(K, root[0], root[1], root[2], u, v);
+        uv[0] = u; uv[1] = v;
+    }
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+        M3 Rpar = Rroot;
+        V3 P = v3(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg) {
+            M3 Rg;
+            if (seg < 3) {
+                float x, y, z;
+                fk_local_angles(oa, f, seg, x, y, z);
+                Rg = m3_mul(Rpar, euler_xyz(x, y, z));
+            } else {
+                Rg = Rpar;                                          // tip: identity local rotation
+            }
+            const float L = bl[4 * f + seg];
+            P = v3(fmaf(L, Rg.m[2], P.x), fmaf(L, Rg.m[5], P.y), fmaf(L, Rg.m[8], P.z));
+            const int o = fk_out_slot(1 + 4 * f + seg, swap);
+            const float X = fmaf(P.x, s, root[0]), Y = fmaf(P.y, s, root[1]), Z = fmaf(P.z, s, root[2]);
+            xyz[o * 3] = X; xyz[o * 3 + 1] = Y; xyz[o * 3 + 2] = Z;
+            float u, v;
+            project_point(K, X, Y, Z, u, v);
+            uv[o * 2] = u; uv[o * 2 + 1] = v;
+            Rpar = Rg;
+        }
+    }
+}
+
+// One sample backward.  g_xyz / g_uv may be NULL.
+// g_ra[3], g_oa[23], g_bl[20] are overwritten.
+HD void fk_backward_sample(const float* ra, const float* oa, const float* bl, const float* K, float s,
+                           const float* root, int swap, const float* g_xyz, const float* g_uv,
+                           float* g_ra, float* g_oa, float* g_bl) {
+    const M3 Rroot = euler_xyz(ra[0], ra[1], ra[2]);
+    M3 dRroot = m3_zero();
+    for (int i = 0; i < FK_OA; ++i) g_oa[i] = 0.f;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+        M3 Rg[4], Rl[3];
+        V3 dP[4];
+        {
+            M3 Rpar = Rroot;
+            V3 P = v3(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int seg = 0; seg < 4; ++seg) {
+                if (seg < 3) {
+                    float x, y, z;
+                    fk_local_angles(oa, f, seg, x, y, z);
+                    Rl[seg] = euler_xyz(x, y, z);
+                    Rg[seg] = m3_mul(Rpar, Rl[seg]);
+                } else {
+                    Rg[seg] = Rpar;
+                }
+                const float L = bl[4 * f + seg];
+                P = v3(fmaf(L, Rg[seg].m[2], P.x), fmaf(L, Rg[seg].m[5], P.y), fmaf(L, Rg[seg].m[8], P.z));
+                const int o = fk_out_slot(1 + 4 * f + seg, swap);
+                V3 dx = v3(0.f, 0.f, 0.f);
+                if (g_xyz) dx = v3(g_xyz[o * 3], g_xyz[o * 3 + 1], g_xyz[o * 3 + 2]);
+                if (g_uv) {
+                    const float X = fmaf(P.x, s, root[0]), Y = fmaf(P.y, s, root[1]), Z = fmaf(P.z, s, root[2]);
+                    dx = v3_add(dx, project_point_bwd(K, X, Y, Z, g_uv[o * 2], g_uv[o * 2 + 1]));
+                }
+                dP[seg] = v3(dx.x * s, dx.y * s, dx.z * s);
+                Rpar = Rg[seg];
+            }
+        }
+        // reverse over the finger: node seg=3 (tip) .. 0
+        M3 dRg = m3_zero();        // gradient of the current node's global rotation
+        V3 dPacc = v3(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int seg = 3; seg >= 0; --seg) {
+            dPacc = v3_add(dPacc, dP[seg]);          // dP of this node including its descendants
+            const float L = bl[4 * f + seg];
+            g_bl[4 * f + seg] = fmaf(dPacc.x, Rg[seg].m[2], fmaf(dPacc.y, Rg[seg].m[5], dPacc.z * Rg[seg].m[8]));
+            dRg.m[2] = fmaf(L, dPacc.x, dRg.m[2]);
+            dRg.m[5] = fmaf(L, dPacc.y, dRg.m[5]);
+            dRg.m[8] = fmaf(L, dPacc.z, dRg.m[8]);
+            if (seg == 3) continue;                   // tip: R_tip = R_parent, dRg flows through unchanged
+            const M3& Rpar = (seg == 0) ? Rroot : Rg[seg - 1];
+            const M3 dRl = m3_tmul(Rpar, dRg);
+            float x, y, z;
+            fk_local_angles(oa, f, seg, x, y, z);
+            fk_scatter_angles(g_oa, f, seg, euler_xyz_bwd(x, y, z, dRl));
+            dRg = m3_mult(dRg, Rl[seg]);              // becomes the parent's dRg contribution
+        }
+        m3_acc(dRroot, dRg);
+    }
+    const V3 g = euler_xyz_bwd(ra[0], ra[1], ra[2], dRroot);
+    g_ra[0] = g.x; g_ra[1] = g.y; g_ra[2] = g.z;
+}
+
+}  // namespace mb

@@ -1,0 +1,188 @@
+// hand_math.cuh — small fixed-size rotation math shared by the MANO pose kernels and
+// the forward-kinematics kernels.  Everything is __host__ __device__ so the same code
+// is exercised on the CPU by tests/ (host harness) before it runs on the GPU.
+#pragma once
+#include <math.h>
+#include "common.cuh"
+
+namespace mb {
+
+struct M3 { float m[9]; };   // row-major 3x3
+struct V3 { float x, y, z; };
+
+HD M3 m3_identity() { M3 r; r.m[0]=1.f; r.m[1]=0.f; r.m[2]=0.f; r.m[3]=0.f; r.m[4]=1.f; r.m[5]=0.f; r.m[6]=0.f; r.m[7]=0.f; r.m[8]=1.f; return r; }
+HD M3 m3_zero() { M3 r; for (int i = 0; i < 9; ++i) r.m[i] = 0.f; return r; }
+
+HD M3 m3_mul(const M3& a, const M3& b) {
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r.m[i*3+j] = fmaf(a.m[i*3+0], b.m[0*3+j], fmaf(a.m[i*3+1], b.m[1*3+j], a.m[i*3+2] * b.m[2*3+j]));
+    return r;
+}
+// a^T b
+HD M3 m3_tmul(const M3& a, const M3& b) {
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r.m[i*3+j] = fmaf(a.m[0*3+i], b.m[0*3+j], fmaf(a.m[1*3+i], b.m[1*3+j], a.m[2*3+i] * b.m[2*3+j]));
+    return r;
+}
+// a b^T
+HD M3 m3_mult(const M3& a, const M3& b) {
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r.m[i*3+j] = fmaf(a.m[i*3+0], b.m[j*3+0], fmaf(a.m[i*3+1], b.m[j*3+1], a.m[i*3+2] * b.m[j*3+2]));
+    return r;
+}
+HD V3 m3_vec(const M3& a, const V3& v) {
+    V3 r;
+    r.x = fmaf(a.m[0], v.x, fmaf(a.m[1], v.y, a.m[2] * v.z));
+    r.y = fmaf(a.m[3], v.x, fmaf(a.m[4], v.y, a.m[5] * v.z));
+    r.z = fmaf(a.m[6], v.x, fmaf(a.m[7], v.y, a.m[8] * v.z));
+    return r;
+}
+// a^T v
+HD V3 m3_tvec(const M3& a, const V3& v) {
+    V3 r;
+    r.x = fmaf(a.m[0], v.x, fmaf(a.m[3], v.y, a.m[6] * v.z));
+    r.y = fmaf(a.m[1], v.x, fmaf(a.m[4], v.y, a.m[7] * v.z));
+    r.z = fmaf(a.m[2], v.x, fmaf(a.m[5], v.y, a.m[8] * v.z));
+    return r;
+}
+HD void m3_add_outer(M3& acc, const V3& a, const V3& b) {   // acc += a b^T
+    acc.m[0] = fmaf(a.x, b.x, acc.m[0]); acc.m[1] = fmaf(a.x, b.y, acc.m[1]); acc.m[2] = fmaf(a.x, b.z, acc.m[2]);
+    acc.m[3] = fmaf(a.y, b.x, acc.m[3]); acc.m[4] = fmaf(a.y, b.y, acc.m[4]); acc.m[5] = fmaf(a.y, b.z, acc.m[5]);
+    acc.m[6] = fmaf(a.z, b.x, acc.m[6]); acc.m[7] = fmaf(a.z, b.y, acc.m[7]); acc.m[8] = fmaf(a.z, b.z, acc.m[8]);
+}
+HD void m3_acc(M3& acc, const M3& a) { for (int i = 0; i < 9; ++i) acc.m[i] += a.m[i]; }
+HD float m3_dot(const M3& a, const M3& b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s = fmaf(a.m[i], b.m[i], s);
+    return s;
+}
+HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+HD V3 v3_add(const V3& a, const V3& b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+HD V3 v3_sub(const V3& a, const V3& b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+HD float v3_dot(const V3& a, const V3& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+
+HD void sincos_acc(float a, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+    sincosf(a, s, c);       // accurate path (no --use_fast_math): <= 2 ulp
+#else
+    *s = sinf(a); *c = cosf(a);
+#endif
+}
+
+// Axis-angle -> rotation.  Reference: ManoLayer.rodrigues, MANOLayer.py:82-112
+// R = I + sin(t) S(n) + (1 - cos t) S(n)^2, n = r / t; Taylor form below 1e-30 (:102-110).
+HD M3 rodrigues(const V3& r) {
+    float t2 = fmaf(r.x, r.x, fmaf(r.y, r.y, r.z * r.z));
+    float t = sqrtf(t2);
+    M3 R;
+    if (t < 1e-30f) {
+        float a = 1.f - t2 / 6.f, b = 0.5f - t2 / 24.f;
+        // S(r)^2 = r r^T - t2 I
+        R.m[0] = 1.f + b * (r.x * r.x - t2); R.m[1] = -a * r.z + b * r.x * r.y;   R.m[2] = a * r.y + b * r.x * r.z;
+        R.m[3] = a * r.z + b * r.x * r.y;    R.m[4] = 1.f + b * (r.y * r.y - t2); R.m[5] = -a * r.x + b * r.y * r.z;
+        R.m[6] = -a * r.y + b * r.x * r.z;   R.m[7] = a * r.x + b * r.y * r.z;    R.m[8] = 1.f + b * (r.z * r.z - t2);
+        return R;
+    }
+    float inv = 1.f / t;
+    float nx = r.x * inv, ny = r.y * inv, nz = r.z * inv;
+    float s, c;
+    sincos_acc(t, &s, &c);
+    float k = 1.f - c;
+    // S(n)^2 = n n^T - |n|^2 I ; |n|^2 is 1 up to rounding — keep the reference's form (S@S)
+    float nn = fmaf(nx, nx, fmaf(ny, ny, nz * nz));
+    R.m[0] = 1.f + k * (nx * nx - nn); R.m[1] = -s * nz + k * nx * ny;    R.m[2] = s * ny + k * nx * nz;
+    R.m[3] = s * nz + k * nx * ny;     R.m[4] = 1.f + k * (ny * ny - nn); R.m[5] = -s * nx + k * ny * nz;
+    R.m[6] = -s * ny + k * nx * nz;    R.m[7] = s * nx + k * ny * nz;     R.m[8] = 1.f + k * (nz * nz - nn);
+    return R;
+}
+
+// d<dR, rodrigues(r)>/dr.  SURVEY Appendix A.2 step 6.  R = I + a S + b S^2 with
+// a = sin t / t, b = (1 - cos t)/t^2 (S = skew(r)); analytic limits for small t where
+// the reference's autograd yields NaN (documented deviation).
+HD V3 rodrigues_bwd(const V3& r, const M3& dR) {
+    float t2 = fmaf(r.x, r.x, fmaf(r.y, r.y, r.z * r.z));
+    float a, b, a2, b2;
+    if (t2 < 1e-2f) {        // t < 0.1: three series terms are exact to fp32 rounding
+        a  = 1.f - t2 * (1.f / 6.f) + t2 * t2 * (1.f / 120.f);
+        b  = 0.5f - t2 * (1.f / 24.f) + t2 * t2 * (1.f / 720.f);
+        a2 = -1.f / 3.f + t2 * (1.f / 30.f) - t2 * t2 * (1.f / 840.f);
+        b2 = -1.f / 12.f + t2 * (1.f / 180.f) - t2 * t2 * (1.f / 6720.f);
+    } else {
+        float t = sqrtf(t2), s, c;
+        sincos_acc(t, &s, &c);
+        a = s / t;
+        // 1 - cos t = 2 sin^2(t/2): avoids cancellation for moderate t
+        float sh, ch;
+        sincos_acc(0.5f * t, &sh, &ch);
+        float omc = 2.f * sh * sh;
+        b = omc / t2;
+        a2 = (c - a) / t2;             // (t cos t - sin t)/t^3
+        b2 = (a - 2.f * b) / t2;       // (t sin t - 2(1 - cos t))/t^4
+    }
+    // <dR, S>     = x(d7 - d5) + y(d2 - d6) + z(d3 - d1)
+    // <dR, S^2>   = r^T dR r - t2 tr(dR)
+    // <dR, E_i S + S E_i> with S^2 = r r^T - t2 I : d(S^2)/dr_i = e_i r^T + r e_i^T - 2 r_i I
+    const float* d = dR.m;
+    float gS = r.x * (d[7] - d[5]) + r.y * (d[2] - d[6]) + r.z * (d[3] - d[1]);
+    float tr = d[0] + d[4] + d[8];
+    V3 dr = v3(fmaf(d[0], r.x, fmaf(d[1], r.y, d[2] * r.z)),
+               fmaf(d[3], r.x, fmaf(d[4], r.y, d[5] * r.z)),
+               fmaf(d[6], r.x, fmaf(d[7], r.y, d[8] * r.z)));        // dR r
+    V3 dtr = v3(fmaf(d[0], r.x, fmaf(d[3], r.y, d[6] * r.z)),
+                fmaf(d[1], r.x, fmaf(d[4], r.y, d[7] * r.z)),
+                fmaf(d[2], r.x, fmaf(d[5], r.y, d[8] * r.z)));       // dR^T r
+    float gS2 = v3_dot(r, dr) - t2 * tr;
+    float common = a2 * gS + b2 * gS2;
+    V3 g;
+    g.x = common * r.x + a * (d[7] - d[5]) + b * (dr.x + dtr.x - 2.f * r.x * tr);
+    g.y = common * r.y + a * (d[2] - d[6]) + b * (dr.y + dtr.y - 2.f * r.y * tr);
+    g.z = common * r.z + a * (d[3] - d[1]) + b * (dr.z + dtr.z - 2.f * r.z * tr);
+    return g;
+}
+
+// R = Rx(x) Ry(y) Rz(z).  Reference: get_right_hand_batch_rotation_matrix,
+// forwardKinematicsLayer.py:59-96.
+HD M3 euler_xyz(float x, float y, float z) {
+    float sx, cx, sy, cy, sz, cz;
+    sincos_acc(x, &sx, &cx); sincos_acc(y, &sy, &cy); sincos_acc(z, &sz, &cz);
+    M3 R;
+    R.m[0] = cy * cz;                 R.m[1] = -cy * sz;                R.m[2] = sy;
+    R.m[3] = cx * sz + sx * sy * cz;  R.m[4] = cx * cz - sx * sy * sz;  R.m[5] = -sx * cy;
+    R.m[6] = sx * sz - cx * sy * cz;  R.m[7] = sx * cz + cx * sy * sz;  R.m[8] = cx * cy;
+    return R;
+}
+
+// (d<dR,R>/dx, /dy, /dz) for R = Rx Ry Rz.  SURVEY Appendix A.3.
+HD V3 euler_xyz_bwd(float x, float y, float z, const M3& dR) {
+    float sx, cx, sy, cy, sz, cz;
+    sincos_acc(x, &sx, &cx); sincos_acc(y, &sy, &cy); sincos_acc(z, &sz, &cz);
+    const float* d = dR.m;
+    V3 g;
+    // dR/dx
+    g.x = d[3] * (-sx * sz + cx * sy * cz) + d[4] * (-sx * cz - cx * sy * sz) + d[5] * (-cx * cy)
+        + d[6] * (cx * sz + sx * sy * cz)  + d[7] * (cx * cz - sx * sy * sz)  + d[8] * (-sx * cy);
+    // dR/dy
+    g.y = d[0] * (-sy * cz) + d[1] * (sy * sz) + d[2] * cy
+        + d[3] * (sx * cy * cz) + d[4] * (-sx * cy * sz) + d[5] * (sx * sy)
+        + d[6] * (-cx * cy * cz) + d[7] * (cx * cy * sz) + d[8] * (-cx * sy);
+    // dR/dz
+    g.z = d[0] * (-cy * sz) + d[1] * (-cy * cz)
+        + d[3] * (cx * cz - sx * sy * sz) + d[4] * (-cx * sz - sx * sy * cz)
+        + d[6] * (sx * cz + cx * sy * sz) + d[7] * (-sx * sz + cx * sy * cz);
+    return g;
+}
+
+}  // namespace mb

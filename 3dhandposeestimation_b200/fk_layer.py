@@ -1,0 +1,138 @@
+"""ForwardKinematics and batch_project_xyz_to_uv — drop-ins for the reference's
+``network/sub_modules/forwardKinematicsLayer.py:ForwardKinematics`` (:142-358) and
+``utils/coordinate_trans.py:batch_project_xyz_to_uv`` (:29-73), backed by the sm_100a
+kernels of libmano_b200 (fk.cu).  No CPU path.
+"""
+from __future__ import annotations
+
+import sys
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .mano_layer import _as_f32_cuda
+
+
+def _reference_joint_order_switched(default=True) -> bool:
+    """The reference reads the mutable global ``config.joint_order_switched`` at call
+    time (forwardKinematicsLayer.py:324; the RHD loader sets it, dataloaderRHD.py:528).
+    When this layer is used as a drop-in inside the reference tree, honour the same global."""
+    cfg = sys.modules.get("config.config")
+    if cfg is not None and hasattr(cfg, "joint_order_switched"):
+        return bool(cfg.joint_order_switched)
+    return default
+
+
+class _FKFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, root_angles, other_angles, bone_lengths, K, scale, root, swap):
+        lib = _cabi.lib()
+        B = root_angles.shape[0]
+        dev = root_angles.device
+        xyz = torch.empty((B, 21, 3), dtype=torch.float32, device=dev)
+        uv = torch.empty((B, 21, 2), dtype=torch.float32, device=dev)
+        _cabi.check(lib.mb_fk_forward(root_angles.data_ptr(), other_angles.data_ptr(), bone_lengths.data_ptr(),
+                                      K.data_ptr(), scale.data_ptr(), root.data_ptr(), B, int(swap),
+                                      xyz.data_ptr(), uv.data_ptr(), _cabi.stream_handle(dev)), "mb_fk_forward")
+        ctx.save_for_backward(root_angles, other_angles, bone_lengths, K, scale, root)
+        ctx.swap = int(swap)
+        ctx.set_materialize_grads(False)
+        return xyz, uv
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_uv):
+        root_angles, other_angles, bone_lengths, K, scale, root = ctx.saved_tensors
+        lib = _cabi.lib()
+        B = root_angles.shape[0]
+        dev = root_angles.device
+        g_ra = torch.empty_like(root_angles)
+        g_oa = torch.empty_like(other_angles)
+        g_bl = torch.empty_like(bone_lengths)
+        if g_xyz is not None:
+            g_xyz = g_xyz.to(torch.float32).contiguous()
+        if g_uv is not None:
+            g_uv = g_uv.to(torch.float32).contiguous()
+        _cabi.check(lib.mb_fk_backward(root_angles.data_ptr(), other_angles.data_ptr(), bone_lengths.data_ptr(),
+                                       K.data_ptr(), scale.data_ptr(), root.data_ptr(), _cabi.ptr(g_xyz), _cabi.ptr(g_uv),
+                                       B, ctx.swap, g_ra.data_ptr(), g_oa.data_ptr(), g_bl.data_ptr(),
+                                       _cabi.stream_handle(dev)), "mb_fk_backward")
+        # K, index_root_bone_length and kp_coord_xyz_root come from the dataset in the
+        # reference (trainval.py:283-290) and never require grad.
+        return g_ra, g_oa, g_bl, None, None, None, None
+
+
+class ForwardKinematics(nn.Module):
+    """``ForwardKinematics(device='cpu')`` as in forwardKinematicsLayer.py:143-145.  The
+    ``device`` argument is kept for signature compatibility; the inputs' CUDA device is used.
+    ``joint_order_switched=None`` follows the reference's ``config.joint_order_switched``
+    global when that module is loaded, else True (config.py:68)."""
+
+    def __init__(self, device="cpu", joint_order_switched=None):
+        super().__init__()
+        self.device = device
+        self.joint_order_switched = joint_order_switched
+
+    def forward(self, root_angles, other_angles, bone_lengths, camera_intrinsic_matrix, index_root_bone_length,
+                kp_coord_xyz_root):
+        assert isinstance(camera_intrinsic_matrix, torch.Tensor)          # forwardKinematicsLayer.py:206
+        self.camera_intrinsic_matrix = camera_intrinsic_matrix
+        if not isinstance(root_angles, torch.Tensor) or root_angles.device.type != "cuda":
+            raise _cabi.ManoB200Error("ForwardKinematics only runs on CUDA tensors (sm_100a); there is no CPU fallback")
+        dev = root_angles.device
+        ra = _as_f32_cuda(root_angles, "root_angles", dev)
+        oa = _as_f32_cuda(other_angles, "other_angles", dev)
+        bl = _as_f32_cuda(bone_lengths, "bone_lengths", dev)
+        K = _as_f32_cuda(camera_intrinsic_matrix, "camera_intrinsic_matrix", dev)
+        sc = _as_f32_cuda(index_root_bone_length, "index_root_bone_length", dev)
+        root = _as_f32_cuda(kp_coord_xyz_root, "kp_coord_xyz_root", dev)
+        B = ra.shape[0]
+        if (ra.shape != (B, 3) or oa.shape != (B, 23) or bl.shape != (B, 20) or K.shape != (B, 3, 3)
+                or sc.numel() != B or root.shape != (B, 3)):
+            raise RuntimeError("expected root_angles[B,3], other_angles[B,23], bone_lengths[B,20], K[B,3,3], "
+                               "index_root_bone_length[B,1], kp_coord_xyz_root[B,3]")
+        switched = self.joint_order_switched
+        if switched is None:
+            switched = _reference_joint_order_switched()
+        xyz, uv = _FKFunction.apply(ra, oa, bl, K, sc.reshape(B), root, not switched)
+        return [xyz, uv, None]                                            # forwardKinematicsLayer.py:330
+
+    def convert_rel_normalized_to_absolute(self, kp_coord_xyz21_rel_normed, index_root_bone_length, kp_coord_xyz_root):
+        """forwardKinematicsLayer.py:333-358 (plain elementwise helper kept for API parity;
+        inside ``forward`` it is fused into the FK kernel)."""
+        return kp_coord_xyz21_rel_normed * index_root_bone_length.unsqueeze(-1) + kp_coord_xyz_root.unsqueeze(1)
+
+
+class _ProjectFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, K):
+        lib = _cabi.lib()
+        B, N = xyz.shape[0], xyz.shape[1]
+        uv = torch.empty((B, N, 2), dtype=torch.float32, device=xyz.device)
+        _cabi.check(lib.mb_project_uv_forward(xyz.data_ptr(), K.data_ptr(), B, N, uv.data_ptr(),
+                                              _cabi.stream_handle(xyz.device)), "mb_project_uv_forward")
+        ctx.save_for_backward(xyz, K)
+        return uv
+
+    @staticmethod
+    def backward(ctx, g_uv):
+        xyz, K = ctx.saved_tensors
+        lib = _cabi.lib()
+        B, N = xyz.shape[0], xyz.shape[1]
+        g_xyz = torch.empty_like(xyz)
+        g_uv = g_uv.to(torch.float32).contiguous()
+        _cabi.check(lib.mb_project_uv_backward(xyz.data_ptr(), K.data_ptr(), g_uv.data_ptr(), B, N, g_xyz.data_ptr(),
+                                               _cabi.stream_handle(xyz.device)), "mb_project_uv_backward")
+        return g_xyz, None
+
+
+def batch_project_xyz_to_uv(positions_xyz, camera_intrinsic_matrix):
+    """utils/coordinate_trans.py:29-73: uv[B,N,2] = (K xyz)_xy / (K xyz)_z with z==0 -> 1e-10."""
+    if not isinstance(positions_xyz, torch.Tensor) or positions_xyz.device.type != "cuda":
+        raise _cabi.ManoB200Error("batch_project_xyz_to_uv only runs on CUDA tensors (sm_100a); there is no CPU fallback")
+    dev = positions_xyz.device
+    xyz = _as_f32_cuda(positions_xyz, "positions_xyz", dev)
+    K = _as_f32_cuda(camera_intrinsic_matrix, "camera_intrinsic_matrix", dev)
+    if xyz.dim() != 3 or xyz.shape[2] != 3 or K.shape != (xyz.shape[0], 3, 3):
+        raise RuntimeError("expected positions_xyz[B,N,3] and camera_intrinsic_matrix[B,3,3]")
+    return _ProjectFunction.apply(xyz, K)

@@ -1,0 +1,165 @@
+/*
+ * mano_b200.h — C ABI of libmano_b200.so: the sm_100a (B200) implementation of the
+ * batched MANO layer, the RHD 21-joint forward-kinematics layer and the masked
+ * joint reductions of hongrui16/3DHandPoseEstimation.
+ *
+ * This is the drop-in boundary.  The reference is pure Python/PyTorch with no FFI
+ * of its own, so each entry point names the reference Python it replaces
+ * (paths relative to the reference checkout); INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every tensor pointer is a DEVICE pointer to contiguous row-major fp32 unless
+ *     stated otherwise; the library borrows it for the duration of the launch;
+ *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises;
+ *   - return value 0 = success, >0 = cudaError_t of the failed launch,
+ *     <0 = argument error (MB_E_*); the library never throws and never falls back
+ *     to a CPU path;
+ *   - B = number of hands / samples.  B == 0 is a successful no-op.
+ */
+#ifndef MANO_B200_H
+#define MANO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MB_API __attribute__((visibility("default")))
+#else
+#define MB_API
+#endif
+
+/* argument errors */
+#define MB_E_NULL      (-1)   /* required pointer is NULL                    */
+#define MB_E_RANGE     (-2)   /* B < 0, nc outside [1,45], bad mode/kind     */
+#define MB_E_WORKSPACE (-3)   /* workspace smaller than mb_mano_workspace_bytes */
+#define MB_E_ALIGN     (-4)   /* pointer not 16-byte aligned where required  */
+#define MB_E_MODEL     (-5)   /* model violates a supported-shape constraint */
+#define MB_E_DEVICE    (-6)   /* device is not compute capability 10.x       */
+
+/* blend-shape contraction precision (mb_mano_forward / mb_mano_backward `mode`) */
+#define MB_MODE_FP32    0     /* FFMA, fp32 end to end (correctness anchor)             */
+#define MB_MODE_F16X3   1     /* tcgen05 kind::f16, 2-way fp16 split, 3 products: fp32-accurate */
+#define MB_MODE_F16     2     /* tcgen05 kind::f16, single product: fast, ~1e-5 m error  */
+
+/* mb_mano_backward flags */
+#define MB_BWD_WORKSPACE_VALID 1  /* workspace still holds the forward's intermediates for these inputs */
+
+/* masked reductions */
+#define MB_REDUCE_MPJPE_MM 0  /* mean ||d|| * 1000  (criterions/metrics.py:10-27) */
+#define MB_REDUCE_L2       1  /* mean ||d||^2       (criterions/loss.py:10-25)    */
+#define MB_VIS_F32 0
+#define MB_VIS_U8  1
+
+typedef struct CUstream_st* mb_stream_t;
+
+MB_API int         mb_abi_version(void);
+MB_API const char* mb_error_string(int code);
+/* 0 if the current device can run this library (sm_100), else MB_E_DEVICE / cudaError. */
+MB_API int         mb_check_device(void);
+
+/* ------------------------------------------------------------------ MANO ---
+ * Constants.  Replaces ManoLayer.__init__ (network/sub_modules/MANOLayer.py:52-80):
+ * the eight fp32 constants are folded/laid out once into one blob.
+ *   basis      [148][2334]  rows 0-9 shapedirs, 10-144 posedirs, 145 v_template, 146-147 zero
+ *   j0 [16][3], jb [16][3][10]   J_regressor folded with v_template / shapedirs (MANOLayer.py:139)
+ *   pca [nc][45] = hands_components[:nc], pose_mean [45]
+ *   skin_w [778][8] / skin_b [778][8] ELL skinning weights and bone ids (zero padded)
+ *   parents [16] (parents[0] = -1, parents[i] < i)
+ * mb_mano_pack_constants writes `mb_mano_blob_bytes()` bytes of HOST memory; the
+ * caller copies them to the device once (16-byte aligned). */
+MB_API size_t mb_mano_blob_bytes(void);
+MB_API int    mb_mano_pack_constants(const float* basis, const float* j0, const float* jb,
+                              const float* pca, int nc, const float* pose_mean,
+                              const float* skin_w, const int32_t* skin_b,
+                              const int32_t* parents, void* host_blob);
+
+/* Bytes of device scratch mb_mano_forward / mb_mano_backward need for B hands. */
+MB_API size_t mb_mano_workspace_bytes(int B, int mode);
+
+/* Replaces ManoLayer.forward == rot_pose_beta_to_mesh (MANOLayer.py:122-208, :238-240).
+ *   rot[B][3] global axis-angle, coeffs[B][nc] PCA pose coefficients, betas[B][10]
+ *   -> verts[B][778][3], joints[B][21][3]   (metres; joints in the reference's 21-order)
+ * verts may be NULL: only the 21 joints are produced (what every head of the
+ * reference consumes, resnet50MANO.py:76,87) and the 778-vertex contraction is skipped. */
+MB_API int mb_mano_forward(const void* blob, int nc,
+                    const float* rot, const float* coeffs, const float* betas, int B, int mode,
+                    float* verts, float* joints,
+                    void* workspace, size_t workspace_bytes, mb_stream_t stream);
+
+/* Replaces the autograd tape of MANOLayer.py:122-208.
+ *   g_verts[B][778][3] (NULL = zero: the heads' joints-only case), g_joints[B][21][3]
+ *   -> g_rot[B][3], g_coeffs[B][nc], g_betas[B][10]
+ * Stateless: intermediates are recomputed from the inputs into `workspace` unless
+ * MB_BWD_WORKSPACE_VALID says the forward's are still there.
+ * Deviation (documented): at |axis-angle| -> 0 the analytic limit is returned where
+ * the reference's autograd yields NaN (r/theta at MANOLayer.py:91). */
+MB_API int mb_mano_backward(const void* blob, int nc,
+                     const float* rot, const float* coeffs, const float* betas,
+                     const float* g_verts, const float* g_joints, int B, int mode, int flags,
+                     float* g_rot, float* g_coeffs, float* g_betas,
+                     void* workspace, size_t workspace_bytes, mb_stream_t stream);
+
+/* Stand-alone linear-blend-skinning stage (MANOLayer.py:177-205) on caller-provided
+ * rest-pose vertices: v_posed[B][pitch] (pitch >= 2334 floats, multiple of 4),
+ * bone[B][16][12] (row-major 3x4 [R|t] per bone, global rotation already folded in)
+ * -> verts[B][778][3]; tips (verts 333,444,672,555,745) -> joints slots 4,8,12,16,20
+ * when joints != NULL.  Exposed so the LBS HBM throughput can be measured alone. */
+MB_API int mb_lbs_forward(const void* blob, const float* v_posed, int pitch, const float* bone, int B,
+                   float* verts, float* joints, mb_stream_t stream);
+
+/* -------------------------------------------------------------------- FK ---
+ * Replaces ForwardKinematics.forward (network/sub_modules/forwardKinematicsLayer.py:147-330)
+ * including convert_rel_normalized_to_absolute (:333-358) and the projection
+ * batch_project_xyz_to_uv (utils/coordinate_trans.py:29-73).
+ *   root_angles[B][3], other_angles[B][23], bone_lengths[B][20], K[B][3][3],
+ *   index_root_bone_length[B], kp_coord_xyz_root[B][3]
+ *   -> xyz[B][21][3], uv[B][21][2]
+ * swap_order != 0 applies the per-finger (i,i+3),(i+1,i+2) swap the reference does
+ * when config.joint_order_switched is False (:324-327). */
+MB_API int mb_fk_forward(const float* root_angles, const float* other_angles, const float* bone_lengths,
+                  const float* K, const float* index_root_bone_length, const float* kp_coord_xyz_root,
+                  int B, int swap_order, float* xyz, float* uv, mb_stream_t stream);
+
+/* Gradient w.r.t. the three tensors that require grad in the heads.
+ * g_xyz / g_uv may each be NULL (treated as zero). */
+MB_API int mb_fk_backward(const float* root_angles, const float* other_angles, const float* bone_lengths,
+                   const float* K, const float* index_root_bone_length, const float* kp_coord_xyz_root,
+                   const float* g_xyz, const float* g_uv, int B, int swap_order,
+                   float* g_root_angles, float* g_other_angles, float* g_bone_lengths, mb_stream_t stream);
+
+/* Replaces batch_project_xyz_to_uv (utils/coordinate_trans.py:29-73) for xyz[B][N][3]:
+ * p = K xyz; p_z == 0 -> 1e-10; uv = p_xy / p_z. */
+MB_API int mb_project_uv_forward(const float* xyz, const float* K, int B, int N, float* uv, mb_stream_t stream);
+MB_API int mb_project_uv_backward(const float* xyz, const float* K, const float* g_uv, int B, int N,
+                           float* g_xyz, mb_stream_t stream);
+
+/* ------------------------------------------------------------ reductions ---
+ * Replaces MPJPE.forward (criterions/metrics.py:10-27) and L2Loss.forward
+ * (criterions/loss.py:10-25): global mean over the visible joints of the batch,
+ * 0 when none is visible — decided on the device, no host sync.
+ *   pred[n_joints][3], gt[n_joints][3], vis[n_joints] (fp32 non-zero = visible, or u8)
+ *   accum: device double[2] scratch {sum, count} (overwritten);  out: device float[1] */
+MB_API int mb_masked_joint_reduce(const float* pred, const float* gt, const void* vis, int vis_kind,
+                           long long n_joints, int kind, double* accum, float* out, mb_stream_t stream);
+/* d(L2)/d(pred) = g_out * 2 (pred-gt) vis / count, with `accum` as left by the forward. */
+MB_API int mb_masked_l2_backward(const float* pred, const float* gt, const void* vis, int vis_kind,
+                          long long n_joints, const double* accum, const float* g_out,
+                          float* g_pred, mb_stream_t stream);
+
+/* ----------------------------------------------------------- fitting loop ---
+ * One Adam update on a flat fp32 parameter array (torch.optim.Adam semantics, no
+ * weight decay, no amsgrad): used by the batched MANO fitting loop (BASELINE config 5). */
+MB_API int mb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                 float lr, float beta1, float beta2, float eps, int step, mb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANO_B200_H */

@@ -1,0 +1,143 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_import.py) on CPU, fp32.
+
+Run in the authoring container only:  python tests/golden/make_golden.py
+The MANO model used is the seeded synthetic MANO-shaped model
+(assets.synthetic_mano) written to a temporary pkl that the reference's own
+ManoLayer constructor opens — so no MANO-licensed data enters the fixtures.
+Known-answer scalars from the real MANO_RIGHT.pkl go to kat_real_mano.json
+(a handful of sums/coordinates only).
+"""
+import importlib
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+assets = importlib.import_module("3dhandposeestimation_b200.assets")
+from oracle import ref_import  # noqa: E402
+
+ref = ref_import.load()
+torch.set_num_threads(1)
+
+
+def mano_case(pkl, nc, B, seed, scale_pose=np.pi):
+    layer = ref.ManoLayer("cpu", pkl, pose_num=nc)
+    g = torch.Generator().manual_seed(seed)
+    rot = ((torch.rand(B, 3, generator=g) - .5) * 2 * np.pi).requires_grad_()
+    pose = ((torch.rand(B, 45, generator=g) - .5) * scale_pose)[:, :nc].clone().requires_grad_()
+    beta = (torch.rand(B, 10, generator=g) - .5).requires_grad_()
+    v, j = layer(rot, pose, beta)
+    gv = torch.randn(v.shape, generator=g)
+    gj = torch.randn(j.shape, generator=g)
+    ((v * gv).sum() + (j * gj).sum()).backward()
+    full = [t.grad.clone() for t in (rot, pose, beta)]
+    for t in (rot, pose, beta):
+        t.grad = None
+    v2, j2 = layer(rot, pose, beta)
+    (j2 * gj).sum().backward()          # the heads' joints-only case
+    jo = [t.grad.clone() for t in (rot, pose, beta)]
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(rot=n(rot), pose=n(pose), beta=n(beta), verts=n(v), joints=n(j), g_verts=n(gv), g_joints=n(gj),
+                g_rot=n(full[0]), g_pose=n(full[1]), g_beta=n(full[2]),
+                gj_rot=n(jo[0]), gj_pose=n(jo[1]), gj_beta=n(jo[2]))
+
+
+def fk_case(B, seed, switched):
+    ref.config.joint_order_switched = switched
+    fk = ref.ForwardKinematics("cpu")
+    g = torch.Generator().manual_seed(seed)
+    ra = ((torch.rand(B, 3, generator=g) - .5) * 2 * np.pi).requires_grad_()
+    oa = ((torch.rand(B, 23, generator=g) - .5) * np.pi).requires_grad_()
+    bl = (torch.rand(B, 20, generator=g) + .1).requires_grad_()
+    K = torch.tensor([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1.]]).repeat(B, 1, 1)
+    K = K + torch.rand(B, 3, 3, generator=g) * torch.tensor([[1., 0, 1], [0, 1, 1], [0, 0, 0]])
+    sc = torch.rand(B, 1, generator=g) * .05 + .02
+    root = torch.randn(B, 3, generator=g) * .05 + torch.tensor([0, 0, .6])
+    xyz, uv, _ = fk(ra, oa, bl, K, sc, root)
+    gx = torch.randn(xyz.shape, generator=g)
+    gu = torch.randn(uv.shape, generator=g) * 1e-3
+    ((xyz * gx).sum() + (uv * gu).sum()).backward()
+    ref.config.joint_order_switched = True
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(root_angles=n(ra), other_angles=n(oa), bone_lengths=n(bl), K=n(K), scale=n(sc), root=n(root),
+                xyz=n(xyz), uv=n(uv), g_xyz=n(gx), g_uv=n(gu), g_root_angles=n(ra.grad),
+                g_other_angles=n(oa.grad), g_bone_lengths=n(bl.grad), switched=np.array(switched))
+
+
+def reduce_case(B, seed, p_vis):
+    g = torch.Generator().manual_seed(seed)
+    pre = (torch.randn(B, 21, 3, generator=g) * .05).requires_grad_()
+    gt = torch.randn(B, 21, 3, generator=g) * .05
+    vis = (torch.rand(B, 21, 1, generator=g) < p_vis).float()
+    m = ref.MPJPE()(pre.detach(), gt, vis)
+    l2 = ref.L2Loss()(pre, gt, vis)
+    if l2.requires_grad:
+        l2.backward()
+        gpre = pre.grad
+    else:
+        gpre = torch.zeros_like(pre)
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(pre=n(pre), gt=n(gt), vis=n(vis), mpjpe=np.float32(m.item()), l2=np.float32(l2.item()), g_pre=n(gpre))
+
+
+def proj_case():
+    g = torch.Generator().manual_seed(7)
+    B = 3
+    xyz = torch.randn(B, 21, 3, generator=g) * .1 + torch.tensor([0, 0, .5])
+    xyz[0, 0] = 0.0           # exercises the p_z == 0 -> 1e-10 branch (coordinate_trans.py:59)
+    xyz[1, 5, 2] = 0.0
+    xyz.requires_grad_()
+    K = torch.tensor([[600., 0, 300], [0, 600., 300], [0, 0, 1.]]).repeat(B, 1, 1)
+    uv = ref.batch_project_xyz_to_uv(xyz, K)
+    gu = torch.randn(uv.shape, generator=g)
+    (uv * gu).sum().backward()
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(xyz=n(xyz), K=n(K), uv=n(uv), g_uv=n(gu), g_xyz=n(xyz.grad))
+
+
+def main():
+    model = assets.synthetic_mano()
+    with tempfile.TemporaryDirectory() as td:
+        pkl = os.path.join(td, "synthetic_mano.pkl")
+        assets.write_reference_style_pkl(model, pkl)
+        np.savez_compressed(os.path.join(HERE, "mano_synth_nc45.npz"), **mano_case(pkl, 45, 4, 1234))
+        np.savez_compressed(os.path.join(HERE, "mano_synth_nc10.npz"), **mano_case(pkl, 10, 4, 1234))
+        np.savez_compressed(os.path.join(HERE, "mano_synth_nc6.npz"), **mano_case(pkl, 6, 3, 99, scale_pose=4.0))
+    np.savez_compressed(os.path.join(HERE, "fk_switched.npz"), **fk_case(8, 1234, True))
+    np.savez_compressed(os.path.join(HERE, "fk_unswitched.npz"), **fk_case(8, 4321, False))
+    np.savez_compressed(os.path.join(HERE, "reduce_vis80.npz"), **reduce_case(16, 5, .8))
+    np.savez_compressed(os.path.join(HERE, "reduce_none_visible.npz"), **reduce_case(4, 6, -1.0))
+    np.savez_compressed(os.path.join(HERE, "project_uv.npz"), **proj_case())
+
+    # model checksum pin + real-pkl known answers (scalars only)
+    chk = {k: float(np.asarray(v, dtype=np.float64).sum()) for k, v in model.items()}
+    kat = {"synthetic_model_field_sums": chk}
+    if os.path.isfile(ref_import.REAL_PKL):
+        layer = ref.ManoLayer("cpu", ref_import.REAL_PKL, pose_num=45)
+        z = lambda *s: torch.zeros(*s)
+        v, j = layer(z(1, 3), z(1, 45), z(1, 10))
+        kat["KAT-MANO-0"] = dict(verts_sum=v.sum().item(), joints_sum=j.sum().item(), verts_absmax=v.abs().max().item(),
+                                 joint0=j[0, 0].tolist(), joint4=j[0, 4].tolist(), joint20=j[0, 20].tolist())
+        g = torch.Generator().manual_seed(1234)
+        rot = (torch.rand(4, 3, generator=g) - .5) * 2 * np.pi
+        pose = (torch.rand(4, 45, generator=g) - .5) * np.pi
+        beta = torch.rand(4, 10, generator=g) - .5
+        v, j = layer(rot, pose, beta)
+        kat["KAT-MANO-1"] = dict(verts_sum=v.sum().item(), joints_sum=j.sum().item(), joint3_0=j[3, 0].tolist(),
+                                 joint3_8=j[3, 8].tolist(), joint3_17=j[3, 17].tolist())
+        layer10 = ref.ManoLayer("cpu", ref_import.REAL_PKL, pose_num=10)
+        v, j = layer10(rot, pose[:, :10], beta)
+        kat["KAT-MANO-2"] = dict(verts_sum=v.sum().item(), joints_sum=j.sum().item())
+    with open(os.path.join(HERE, "kat.json"), "w") as fh:
+        json.dump(kat, fh, indent=1)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

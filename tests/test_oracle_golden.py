@@ -1,0 +1,93 @@
+"""CPU: the numpy oracle against the golden vectors captured from the unmodified reference
+(tests/golden/make_golden.py) and the known answers recorded from the real MANO pkl."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+from oracle import fk_oracle as fo
+from oracle import mano_oracle as mo
+
+# tolerances: positions 2e-7 m vs the fp32 reference, gradients 1e-4 relative
+POS_TOL = 2e-7
+GRAD_TOL = 1e-4
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_synthetic_model_is_pinned(synth_model):
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))["synthetic_model_field_sums"]
+    for key, want in kat.items():
+        got = float(np.asarray(synth_model[key], dtype=np.float64).sum())
+        assert got == pytest.approx(want, rel=1e-9, abs=1e-9), key
+
+
+@pytest.mark.parametrize("name,nc", [("mano_synth_nc45.npz", 45), ("mano_synth_nc10.npz", 10), ("mano_synth_nc6.npz", 6)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_mano_oracle_matches_reference_golden(synth_model, name, nc, dtype):
+    g = load_golden(name)
+    v, j = mo.mano_forward(synth_model, g["rot"], g["pose"], g["beta"], dtype=dtype)
+    assert np.abs(v - g["verts"]).max() < POS_TOL
+    assert np.abs(j - g["joints"]).max() < POS_TOL
+    gr, gp, gb = mo.mano_backward(synth_model, g["rot"], g["pose"], g["beta"], g["g_verts"], g["g_joints"], dtype=dtype)
+    assert rel(gr, g["g_rot"]) < GRAD_TOL and rel(gp, g["g_pose"]) < GRAD_TOL and rel(gb, g["g_beta"]) < GRAD_TOL
+    gr, gp, gb = mo.mano_backward(synth_model, g["rot"], g["pose"], g["beta"], None, g["g_joints"], dtype=dtype)
+    assert rel(gr, g["gj_rot"]) < GRAD_TOL and rel(gp, g["gj_pose"]) < GRAD_TOL and rel(gb, g["gj_beta"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("name", ["fk_switched.npz", "fk_unswitched.npz"])
+def test_fk_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    sw = bool(g["switched"])
+    args = (g["root_angles"], g["other_angles"], g["bone_lengths"], g["K"], g["scale"], g["root"])
+    xyz, uv = fo.fk_forward(*args, joint_order_switched=sw)
+    assert np.abs(xyz - g["xyz"]).max() < POS_TOL
+    assert np.abs(uv - g["uv"]).max() < 1e-3            # pixels, |z| >= 0.1 m
+    gra, goa, gbl = fo.fk_backward(*args, g["g_xyz"], g["g_uv"], joint_order_switched=sw)
+    assert rel(gra, g["g_root_angles"]) < GRAD_TOL
+    assert rel(goa, g["g_other_angles"]) < GRAD_TOL
+    assert rel(gbl, g["g_bone_lengths"]) < GRAD_TOL
+
+
+def test_fk_kat0_hand_typed_pose():
+    """KAT-FK-0 (inputs of forwardKinematicsLayer.py:554-586)."""
+    oa = np.zeros((1, 23)); oa[0, 1] = np.pi / 2
+    K = np.array([[[600., 0, 300], [0, 600., 300], [0, 0, 1]]])
+    xyz, uv = fo.fk_forward(np.array([[0, 0, np.pi / 2]]), oa, np.ones((1, 20)), K, np.ones((1, 1)), np.zeros((1, 3)))
+    for k in range(1, 5):
+        assert np.allclose(xyz[0, k], [0, k, 0], atol=1e-12)
+    for f in range(1, 5):
+        for k in range(1, 5):
+            assert np.allclose(xyz[0, 4 * f + k], [0, 0, k], atol=1e-12)
+            assert np.allclose(uv[0, 4 * f + k], [300, 300], atol=1e-9)
+    assert np.allclose(uv[0, 0], [0, 0])                 # wrist: z == 0 -> 1e-10 branch
+
+
+@pytest.mark.parametrize("name", ["reduce_vis80.npz", "reduce_none_visible.npz"])
+def test_reductions_match_reference_golden(name):
+    g = load_golden(name)
+    assert fo.mpjpe(g["pre"], g["gt"], g["vis"]) == pytest.approx(float(g["mpjpe"]), rel=1e-5, abs=1e-12)
+    assert fo.l2loss(g["pre"], g["gt"], g["vis"]) == pytest.approx(float(g["l2"]), rel=1e-5, abs=1e-12)
+    gp = fo.l2loss_backward(g["pre"], g["gt"], g["vis"])
+    assert np.abs(gp - g["g_pre"]).max() <= 1e-6 * max(1e-12, np.abs(g["g_pre"]).max()) + 1e-12
+
+
+def test_projection_matches_reference_golden_including_z0_branch():
+    g = load_golden("project_uv.npz")
+    uv = fo.project_uv(g["xyz"].astype(np.float64), g["K"].astype(np.float64))
+    ok = np.abs(g["uv"]) < 1e6                           # the z==0 rows are +-inf/1e10-scale
+    assert np.abs(uv[ok] - g["uv"][ok]).max() < 2e-3
+    gx = fo.project_uv_backward(g["xyz"].astype(np.float64), g["K"].astype(np.float64), g["g_uv"].astype(np.float64))
+    fin = np.isfinite(g["g_xyz"]) & (np.abs(g["g_xyz"]) < 1e6)
+    assert rel(gx[fin], g["g_xyz"][fin]) < 1e-4
+
+
+def test_kat_real_mano_scalars_present():
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    assert kat["KAT-MANO-0"]["verts_sum"] == pytest.approx(45.808985, abs=2e-5)
+    assert kat["KAT-MANO-1"]["verts_sum"] == pytest.approx(-36.9227472, abs=2e-5)
+    assert kat["KAT-MANO-2"]["joints_sum"] == pytest.approx(-0.9595535, abs=2e-6)

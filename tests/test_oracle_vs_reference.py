@@ -1,0 +1,88 @@
+"""CPU, authoring container only: the oracle against the LIVE unmodified reference
+(imported from /root/reference).  Skipped where the reference is absent (GPU box)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import fk_oracle as fo
+from oracle import mano_oracle as mo
+from oracle import ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import torch
+
+    torch.set_num_threads(2)
+    return ref_import.load()
+
+
+@pytest.mark.parametrize("nc", [45, 10])
+def test_real_pkl_forward_backward(pkg, ref, nc):
+    import torch
+
+    model = pkg.assets.read_mano_pkl(ref_import.REAL_PKL)
+    layer = ref.ManoLayer("cpu", ref_import.REAL_PKL, pose_num=nc)
+    g = torch.Generator().manual_seed(1234)
+    B = 4
+    rot = ((torch.rand(B, 3, generator=g) - .5) * 2 * np.pi).requires_grad_()
+    pose = ((torch.rand(B, 45, generator=g) - .5) * np.pi)[:, :nc].clone().requires_grad_()
+    beta = (torch.rand(B, 10, generator=g) - .5).requires_grad_()
+    v, j = layer(rot, pose, beta)
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    key = "KAT-MANO-1" if nc == 45 else "KAT-MANO-2"
+    assert v.sum().item() == pytest.approx(kat[key]["verts_sum"], abs=1e-4)
+    gv, gj = torch.randn(v.shape, generator=g), torch.randn(j.shape, generator=g)
+    ((v * gv).sum() + (j * gj).sum()).backward()
+    n = lambda t: t.detach().numpy()
+    ov, oj = mo.mano_forward(model, n(rot), n(pose), n(beta))
+    assert np.abs(ov - n(v)).max() < 2e-7 and np.abs(oj - n(j)).max() < 2e-7
+    gr, gp, gb = mo.mano_backward(model, n(rot), n(pose), n(beta), n(gv), n(gj))
+    for got, want in ((gr, rot.grad), (gp, pose.grad), (gb, beta.grad)):
+        assert np.abs(got - n(want)).max() / np.abs(n(want)).max() < 1e-4
+
+
+def test_real_pkl_zero_pose_kat(pkg):
+    model = pkg.assets.read_mano_pkl(ref_import.REAL_PKL)
+    v, j = mo.mano_forward(model, np.zeros((1, 3)), np.zeros((1, 45)), np.zeros((1, 10)))
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))["KAT-MANO-0"]
+    assert v.sum() == pytest.approx(kat["verts_sum"], abs=2e-5)
+    assert np.abs(j[0, 0] - kat["joint0"]).max() < 2e-7
+    assert np.abs(j[0, 4] - kat["joint4"]).max() < 2e-7 and np.abs(v[0, 333] - kat["joint4"]).max() < 2e-7
+    assert np.abs(j[0, 20] - kat["joint20"]).max() < 2e-7
+
+
+def test_pkl_reader_equals_reference_constants(pkg, ref):
+    model = pkg.assets.read_mano_pkl(ref_import.REAL_PKL)
+    layer = ref.ManoLayer("cpu", ref_import.REAL_PKL, pose_num=45)
+    assert np.array_equal(model["shapedirs"].astype(np.float32), layer.mesh_pca[0].numpy())
+    assert np.array_equal(model["posedirs"].astype(np.float32), layer.posedirs[0].numpy())
+    assert np.array_equal(model["weights"].astype(np.float32), layer.weights[0].numpy())
+    assert np.array_equal(model["J_regressor"].astype(np.float32), layer.J_regressor[0].numpy())
+    assert layer.parent == {i: int(p) for i, p in enumerate(pkg.assets.parents_from_kintree(model["kintree_table"])) if i}
+
+
+def test_fk_live(ref):
+    import torch
+
+    fk = ref.ForwardKinematics("cpu")
+    g = torch.Generator().manual_seed(77)
+    B = 6
+    ra = (torch.rand(B, 3, generator=g) - .5) * 2 * np.pi
+    oa = (torch.rand(B, 23, generator=g) - .5) * np.pi
+    bl = torch.rand(B, 20, generator=g) + .1
+    K = torch.tensor([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1.]]).repeat(B, 1, 1)
+    sc = torch.rand(B, 1, generator=g) * .05 + .02
+    root = torch.randn(B, 3, generator=g) * .05 + torch.tensor([0, 0, .6])
+    for sw in (True, False):
+        ref.config.joint_order_switched = sw
+        xyz, uv, _ = fk(ra, oa, bl, K, sc, root)
+        oxyz, ouv = fo.fk_forward(*[t.numpy() for t in (ra, oa, bl, K, sc, root)], joint_order_switched=sw)
+        assert np.abs(oxyz - xyz.numpy()).max() < 2e-7
+        assert np.abs(ouv - uv.numpy()).max() < 1e-3
+    ref.config.joint_order_switched = True
