@@ -44,7 +44,12 @@ SIGNATURES = {
     "mb_masked_joint_reduce": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p]),
     "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
     "mb_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
+    "mb_launch_count": (_ll, []),
+    "mb_profile_enable": (None, [_i]),
+    "mb_profile_collect": (_i, [_p, _p]),
 }
+STAGES = ("pose_fwd", "blend_fwd", "lbs_fwd", "lbs_bwd", "blend_bwd", "pose_bwd",
+          "joints_only_fwd", "joints_only_bwd", "fk_fwd", "fk_bwd")
 
 
 class ManoB200Error(RuntimeError):
@@ -59,6 +64,14 @@ def header_symbols() -> list:
     with open(HEADER_PATH) as fh:
         text = fh.read()
     return re.findall(r"MB_API\s+[\w\s\*]+?\b(mb_\w+)\s*\(", text)
+
+
+def profile_collect() -> dict:
+    """{stage: (total_ms, launches)} since profiling was enabled / last collected."""
+    ms = (C.c_double * len(STAGES))()
+    cnt = (C.c_longlong * len(STAGES))()
+    check(lib().mb_profile_collect(ms, cnt), "mb_profile_collect")
+    return {name: (ms[i], cnt[i]) for i, name in enumerate(STAGES) if cnt[i]}
 
 
 def lib() -> C.CDLL:

@@ -4,13 +4,60 @@
 
 using namespace mb;
 
+#include "blend_tc.cuh"
 namespace mb {
-// blend_tc.cu (tcgen05 path); returns MB_E_RANGE when the mode is not built
-int launch_blend_tc_forward(const void* blob, const float* feat, float* v_posed, int B, int mode, cudaStream_t s);
-int launch_blend_tc_backward(const void* blob, const float* dv_posed, float* dfeat, int B, int mode, cudaStream_t s);
 size_t blend_tc_blob_bytes();
 void blend_tc_pack(const float* basis, void* host_blob_tc);
 }  // namespace mb
+
+// ---------------------------------------------------------------- bookkeeping
+#include <atomic>
+#include <mutex>
+#include <vector>
+namespace mb {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec*> g_prof_recs;
+
+StageTimer::StageTimer(int st, cudaStream_t s) : stage(st), stream(s), rec(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec* r = new ProfRec;
+    r->stage = st;
+    if (cudaEventCreate(&r->a) != cudaSuccess || cudaEventCreate(&r->b) != cudaSuccess) { delete r; return; }
+    cudaEventRecord(r->a, s);
+    rec = r;
+}
+StageTimer::~StageTimer() {
+    if (!rec) return;
+    ProfRec* r = reinterpret_cast<ProfRec*>(rec);
+    cudaEventRecord(r->b, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+}
+}  // namespace mb
+
+extern "C" long long mb_launch_count(void) { return g_launches.load(); }
+extern "C" void mb_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+extern "C" int mb_profile_collect(double* ms, long long* counts) {
+    if (!ms || !counts) return MB_E_NULL;
+    for (int i = 0; i < ST_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int rc = 0;
+    for (ProfRec* r : g_prof_recs) {
+        cudaError_t e = cudaEventSynchronize(r->b);
+        float t = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r->a, r->b);
+        if (e == cudaSuccess) { ms[r->stage] += t; counts[r->stage] += 1; } else rc = (int)e;
+        cudaEventDestroy(r->a); cudaEventDestroy(r->b);
+        delete r;
+    }
+    g_prof_recs.clear();
+    return rc;
+}
 
 extern "C" int mb_abi_version(void) { return MB_ABI_VERSION; }
 
@@ -139,20 +186,29 @@ static int check_common(const void* blob, int nc, const float* rot, const float*
     return 0;
 }
 
-static int blend_forward(const void* blob, const float* feat, float* v_posed, int B, int mode, cudaStream_t s) {
+// pose stage + blend contraction of the forward (fp32 FFMA or tcgen05)
+static int pose_and_blend_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B,
+                                  int mode, char* ws, const WorkLayout& W, float* joints, cudaStream_t s) {
+    float* feat = reinterpret_cast<float*>(ws + W.feat);
+    float* bone = reinterpret_cast<float*>(ws + W.bone);
+    float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
+    unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
+    int rc;
     if (mode == MB_MODE_FP32) {
+        { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, feat, nullptr, bone, joints, s))) return rc; }
+        StageTimer t(ST_BLEND_FWD, s);
         const BlobLayout L = blob_layout();
         return launch_sgemm(feat, FEAT_K, blob_ptr<float>(blob, L.basis), VP_PITCH, v_posed, VP_PITCH, B, NVC, FEAT_K, s);
     }
-    return launch_blend_tc_forward(blob, feat, v_posed, B, mode, s);
+    { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone, joints, s))) return rc; }
+    StageTimer t(ST_BLEND_FWD, s);
+    return launch_blend_tc_forward(blob, featp, v_posed, B, mode, s);
 }
 
 static int blend_backward(const void* blob, const float* dv_posed, float* dfeat, int B, int mode, cudaStream_t s) {
-    if (mode == MB_MODE_FP32) {
-        const BlobLayout L = blob_layout();
-        return launch_sgemm(dv_posed, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s);
-    }
-    return launch_blend_tc_backward(blob, dv_posed, dfeat, B, mode, s);
+    (void)mode;     // the K = 2334 gradient contraction runs in fp32 FFMA in every mode (tcgen05 version: next round)
+    const BlobLayout L = blob_layout();
+    return launch_sgemm(dv_posed, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s);
 }
 
 extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
@@ -163,6 +219,7 @@ extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const
         if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
         if (B == 0) return 0;
         if (!blob || !rot || !coeffs || !betas || !joints) return MB_E_NULL;
+        StageTimer t(ST_JOINTS_FWD, s);
         return launch_joints_only_forward(blob, nc, rot, coeffs, betas, B, joints, s);
     }
     int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
@@ -171,11 +228,10 @@ extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const
     if (reinterpret_cast<uintptr_t>(verts) & 15) return MB_E_ALIGN;
     const WorkLayout W = work_layout(B);
     char* ws = reinterpret_cast<char*>(workspace);
-    float* feat = reinterpret_cast<float*>(ws + W.feat);
     float* bone = reinterpret_cast<float*>(ws + W.bone);
     float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
-    if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, feat, bone, joints, s))) return rc;
-    if ((rc = blend_forward(blob, feat, v_posed, B, mode, s))) return rc;
+    if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, ws, W, joints, s))) return rc;
+    StageTimer t(ST_LBS_FWD, s);
     return launch_lbs_forward(blob, v_posed, VP_PITCH, bone, B, verts, joints, s);
 }
 
@@ -188,6 +244,7 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
         if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
         if (B == 0) return 0;
         if (!blob || !rot || !coeffs || !betas || !g_joints || !g_rot || !g_coeffs || !g_betas) return MB_E_NULL;
+        StageTimer t(ST_JOINTS_BWD, s);
         return launch_joints_only_backward(blob, nc, rot, coeffs, betas, g_joints, B, g_rot, g_coeffs, g_betas, s);
     }
     int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
@@ -195,7 +252,6 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
     if (!g_joints || !g_rot || !g_coeffs || !g_betas) return MB_E_NULL;
     const WorkLayout W = work_layout(B);
     char* ws = reinterpret_cast<char*>(workspace);
-    float* feat = reinterpret_cast<float*>(ws + W.feat);
     float* bone = reinterpret_cast<float*>(ws + W.bone);
     float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
     float* dv_posed = reinterpret_cast<float*>(ws + W.dv_posed);
@@ -204,11 +260,11 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
     if (!(flags & MB_BWD_WORKSPACE_VALID)) {
         // recompute the forward intermediates; joints of the recompute go to scratch (dfeat is free until step 3)
         float* scratch_joints = dfeat;      // B*63 floats <= B*148
-        if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, feat, bone, scratch_joints, s))) return rc;
-        if ((rc = blend_forward(blob, feat, v_posed, B, mode, s))) return rc;
+        if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, ws, W, scratch_joints, s))) return rc;
     }
-    if ((rc = launch_lbs_backward(blob, v_posed, VP_PITCH, bone, g_verts, g_joints, B, dv_posed, dbone, s))) return rc;
-    if ((rc = blend_backward(blob, dv_posed, dfeat, B, mode, s))) return rc;
+    { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_lbs_backward(blob, v_posed, VP_PITCH, bone, g_verts, g_joints, B, dv_posed, dbone, s))) return rc; }
+    { StageTimer t(ST_BLEND_BWD, s); if ((rc = blend_backward(blob, dv_posed, dfeat, B, mode, s))) return rc; }
+    StageTimer t(ST_POSE_BWD, s);
     return launch_pose_backward(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
 }
 
@@ -220,5 +276,6 @@ extern "C" int mb_lbs_forward(const void* blob, const float* v_posed, int pitch,
     if ((reinterpret_cast<uintptr_t>(verts) & 15) || (reinterpret_cast<uintptr_t>(v_posed) & 15) ||
         (reinterpret_cast<uintptr_t>(bone) & 15))
         return MB_E_ALIGN;
+    StageTimer t(ST_LBS_FWD, (cudaStream_t)stream);
     return launch_lbs_forward(blob, v_posed, pitch, bone, B, verts, joints, (cudaStream_t)stream);
 }

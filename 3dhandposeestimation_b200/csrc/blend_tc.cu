@@ -1,9 +1,333 @@
-// blend_tc.cu — tcgen05 (5th-gen tensor core) path of the blend-shape contractions.
-// Placeholder until the tensor-core kernels land: the modes report MB_E_RANGE.
+// blend_tc.cu — the blend-shape contraction on the 5th-generation tensor cores (tcgen05),
+// MB_MODE_F16X3 (fp32-accurate) and MB_MODE_F16 (fast).
+//
+//   v_posed[h][n] = v_template[n] + sum_k f[h][k] * basis[k][n]          (MANOLayer.py:130-137)
+//   f = [beta(10) | vec(R_j - I)(135)], k padded to 160;  n = vertex*3 + coord, 2334 -> 15 tiles of 160
+//
+// GEMM mapping: M = 128 hands (TMEM lanes), N = 160 vertex coordinates, K = 160.
+//   * B operand (the basis slice of the CTA's N-tile, 100 KB as fp16 hi+lo) is RESIDENT in shared
+//     memory: it is fetched once per N-tile by TMA bulk copies from a pre-tiled image in the
+//     constant blob and reused for every hand tile the CTA processes.
+//   * A operand (feature rows, written by the pose stage as fp16 hi/lo in the UMMA canonical
+//     K-major layout) streams through a 4-stage TMA/mbarrier ring, 16 KB (hi+lo of a K=32 chunk)
+//     per stage.
+//   * one elected thread issues tcgen05.mma.kind::f16 (fp32 accumulate in TMEM); two accumulator
+//     stages (2 x 160 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//   * epilogue warps: tcgen05.ld (lane = hand) -> smem transpose -> add v_template in fp32 ->
+//     128-byte coalesced row stores of v_posed.
+// fp32 accuracy from fp16 tensor cores: both operands are split x = hi + lo (two fp16, 22
+// significand bits) after a power-of-two pre-scale that keeps lo out of the fp16 subnormals, and
+// three products hi*hi + lo*hi + hi*lo are accumulated in fp32; v_template (the one large term)
+// never enters the tensor core — it is added in the epilogue.  MB_MODE_F16 issues hi*hi only.
+// Tiles are distributed as contiguous ranges of the flattened (n_tile, m_tile) space, so every
+// CTA gets the same number of tiles (+-1) and reloads its resident B at most once.
+#include <cuda_fp16.h>
+#include <string.h>
+#include <math.h>
 #include "common.cuh"
+#include "blend_tc.cuh"
+
 namespace mb {
-size_t blend_tc_blob_bytes() { return 0; }
-void blend_tc_pack(const float*, void*) {}
-int launch_blend_tc_forward(const void*, const float*, float*, int, int, cudaStream_t) { return MB_E_RANGE; }
-int launch_blend_tc_backward(const void*, const float*, float*, int, int, cudaStream_t) { return MB_E_RANGE; }
+namespace {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a broken pipeline must not hang the GPU — after ~2 s worth of polls the kernel
+// records the failure and every role falls through to the exit.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (int spin = 1;; ++spin) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((spin & 255) == 0) {
+            if (*abort_flag) return false;
+            if (clock64() - t0 > 4000000000LL) break;          // ~2 s
+        }
+    }
+    *abort_flag = 1;
+    return false;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B,
+// LBO = byte distance between the two K core matrices of one MMA, SBO = between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version 1 (Blackwell)
+    return d;                                     // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
+}
+
+// ---------------------------------------------------------------- kernel
+constexpr int TC_THREADS = 256;                   // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-7 epilogue
+constexpr int A_STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+
+struct TcShared {
+    alignas(128) unsigned char b[TC_B_TILE_BYTES];                  // resident basis tile (hi+lo, 5 chunks)
+    alignas(128) unsigned char a[A_STAGES][TC_A_STAGE_BYTES];       // feature ring
+    alignas(16) float stage[4][32][33];                             // epilogue transposes
+    alignas(8) unsigned long long full[A_STAGES], empty[A_STAGES];
+    unsigned long long acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
+    unsigned long long b_full, b_empty;
+    uint32_t tmem_base;
+    int abort_flag;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ basis_tc,
+                        const float* __restrict__ tmpl, const unsigned char* __restrict__ featp,
+                        float* __restrict__ v_posed, int B, int m_tiles, int products) {
+    extern __shared__ unsigned char smem_raw[];
+    TcShared& S = *reinterpret_cast<TcShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const float out_scale = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const long long total = (long long)TC_N_TILES * m_tiles;
+    const long long t_begin = total * blockIdx.x / gridDim.x;
+    const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(smem_u32(&S.full[s]), 1); mbar_init(smem_u32(&S.empty[s]), 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(smem_u32(&S.acc_full[s]), 1); mbar_init(smem_u32(&S.acc_empty[s]), 4); }
+        mbar_init(smem_u32(&S.b_full), 1);
+        mbar_init(smem_u32(&S.b_empty), 1);
+        S.abort_flag = 0;
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    volatile int* abort_flag = &S.abort_flag;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: resident B per n-tile, feature chunks through the ring =====
+        uint32_t stage = 0, phase = 0, b_loads = 0;
+        int cur_n = -1;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const int n_tile = (int)(t / m_tiles), m_tile = (int)(t % m_tiles);
+            if (n_tile != cur_n) {
+                if (b_loads > 0 && !mbar_wait(smem_u32(&S.b_empty), (b_loads - 1) & 1, abort_flag)) break;
+                mbar_expect_tx(smem_u32(&S.b_full), TC_B_TILE_BYTES);
+                const unsigned char* src = basis_tc + (size_t)n_tile * TC_B_TILE_BYTES;
+                for (int i = 0; i < TC_B_TILE_BYTES / TC_B_BLOCK_BYTES; ++i)
+                    bulk_g2s(smem_u32(S.b) + i * TC_B_BLOCK_BYTES, src + (size_t)i * TC_B_BLOCK_BYTES, TC_B_BLOCK_BYTES,
+                             smem_u32(&S.b_full));
+                cur_n = n_tile;
+                ++b_loads;
+            }
+            const unsigned char* fsrc = featp + (size_t)m_tile * TC_A_TILE_BYTES;
+            bool ok = true;
+            for (int c = 0; c < TC_K_CHUNKS; ++c) {
+                if (!(ok = mbar_wait(smem_u32(&S.empty[stage]), phase ^ 1, abort_flag))) break;
+                mbar_expect_tx(smem_u32(&S.full[stage]), TC_A_STAGE_BYTES);
+                bulk_g2s(smem_u32(S.a[stage]), fsrc + (size_t)c * TC_A_STAGE_BYTES, TC_A_STAGE_BYTES, smem_u32(&S.full[stage]));
+                if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (!ok) break;
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, b_seen = 0;
+        int cur_n = -1;
+        bool ok = true;
+        for (long long t = t_begin; t < t_end && ok; ++t) {
+            const int n_tile = (int)(t / m_tiles);
+            if (n_tile != cur_n) {
+                if (!(ok = mbar_wait(smem_u32(&S.b_full), b_seen & 1, abort_flag))) break;
+                ++b_seen;
+                cur_n = n_tile;
+            }
+            if (!(ok = mbar_wait(smem_u32(&S.acc_empty[acc]), acc_phase ^ 1, abort_flag))) break;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + acc * TC_N;
+            uint32_t accumulate = 0;
+            for (int c = 0; c < TC_K_CHUNKS && ok; ++c) {
+                if (!(ok = mbar_wait(smem_u32(&S.full[stage]), phase, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(S.a[stage]), a_lo = a_hi + TC_A_BLOCK_BYTES;
+                const uint32_t b_hi = smem_u32(S.b) + (uint32_t)(c * 2) * TC_B_BLOCK_BYTES, b_lo = b_hi + TC_B_BLOCK_BYTES;
+#pragma unroll
+                for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
+                    const uint32_t ko = (uint32_t)j * 2 * TC_LBO;
+                    umma_f16(d_tmem, umma_desc(a_hi + ko, TC_LBO, TC_SBO), umma_desc(b_hi + ko, TC_LBO, TC_SBO), IDESC, accumulate);
+                    accumulate = 1;
+                    if (products == 3) {
+                        umma_f16(d_tmem, umma_desc(a_lo + ko, TC_LBO, TC_SBO), umma_desc(b_hi + ko, TC_LBO, TC_SBO), IDESC, 1);
+                        umma_f16(d_tmem, umma_desc(a_hi + ko, TC_LBO, TC_SBO), umma_desc(b_lo + ko, TC_LBO, TC_SBO), IDESC, 1);
+                    }
+                }
+                tc_commit(smem_u32(&S.empty[stage]));          // frees the feature stage when these MMAs retire
+                if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (!ok) break;
+            tc_commit(smem_u32(&S.acc_full[acc]));             // accumulator ready for the epilogue
+            const long long tn = t + 1;
+            if (tn >= t_end || (int)(tn / m_tiles) != cur_n) tc_commit(smem_u32(&S.b_empty));   // last use of this B
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced v_posed rows =====
+        const int q = warp - 4;                                 // TMEM lane quarter of this warp (warp % 4)
+        float (*buf)[33] = S.stage[q];
+        uint32_t acc = 0, acc_phase = 0;
+        bool ok = true;
+        for (long long t = t_begin; t < t_end && ok; ++t) {
+            const int n_tile = (int)(t / m_tiles), m_tile = (int)(t % m_tiles);
+            ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&S.acc_full[acc]), acc_phase, abort_flag));
+            if (!ok) break;
+            tc_fence_after();
+            const int row0 = m_tile * TC_M + q * 32;
+            const int n0 = n_tile * TC_N;
+#pragma unroll 1
+            for (int j = 0; j < TC_N / 32; ++j) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * TC_N + j * 32, v);
+                if (j == TC_N / 32 - 1) {                       // accumulator drained: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty[acc]));
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) buf[lane][c] = v[c];
+                __syncwarp();
+                const int col = n0 + j * 32 + lane;
+                const float tv = col < NVC ? tmpl[col] : 0.f;
+                if (col < VP_PITCH) {
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = row0 + rr;
+                        if (row < B) v_posed[(size_t)row * VP_PITCH + col] = fmaf(buf[rr][lane], out_scale, tv);
+                    }
+                }
+                __syncwarp();
+            }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, TMEM_COLS);
+    if (threadIdx.x == 0 && S.abort_flag) __trap();           // a stalled pipeline is an error, never a silent result
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host side
+size_t blend_tc_blob_bytes() { return align256(sizeof(TcBlobHeader)) + (size_t)TC_N_TILES * TC_B_TILE_BYTES; }
+
+// basis [FEAT_K][2334] fp32 -> per n-tile, per K chunk, {hi, lo} blocks in the UMMA canonical
+// K-major layout [row-group][k-group][8 rows][8 halves]; pre-scaled by a power of two.
+void blend_tc_pack(const float* basis, void* host_blob_tc) {
+    unsigned char* out = reinterpret_cast<unsigned char*>(host_blob_tc);
+    memset(out, 0, blend_tc_blob_bytes());
+    TcBlobHeader* H = reinterpret_cast<TcBlobHeader*>(out);
+    float mx = 0.f;
+    for (int k = 0; k < TC_K_REAL; ++k)
+        for (int n = 0; n < NVC; ++n) mx = fmaxf(mx, fabsf(basis[(size_t)k * NVC + n]));
+    int e = 13;                                               // scale 2^e: largest with max * 2^e <= 2^11
+    if (mx > 0.f) { e = 11 - (int)ceilf(log2f(mx)); if (e > 24) e = 24; if (e < -8) e = -8; }
+    const float sb = ldexpf(1.f, e);
+    H->basis_scale_log2 = e;
+    H->feat_scale_log2 = TC_FEAT_SCALE_LOG2;
+    __half* dst = reinterpret_cast<__half*>(out + align256(sizeof(TcBlobHeader)));
+    for (int nt = 0; nt < TC_N_TILES; ++nt)
+        for (int c = 0; c < TC_K_CHUNKS; ++c)
+            for (int r = 0; r < TC_N; ++r)
+                for (int kk = 0; kk < TC_K_CHUNK; ++kk) {
+                    const int n = nt * TC_N + r, k = c * TC_K_CHUNK + kk;
+                    float x = (n < NVC && k < TC_K_REAL) ? basis[(size_t)k * NVC + n] * sb : 0.f;
+                    const __half hi = __float2half_rn(x);
+                    const __half lo = __float2half_rn(x - __half2float(hi));
+                    const size_t blk = ((size_t)nt * TC_K_CHUNKS + c) * 2;
+                    const size_t in = (((size_t)(r >> 3) * (TC_K_CHUNK / 8) + (kk >> 3)) * 8 + (r & 7)) * 8 + (kk & 7);
+                    dst[(blk + 0) * (TC_B_BLOCK_BYTES / 2) + in] = hi;
+                    dst[(blk + 1) * (TC_B_BLOCK_BYTES / 2) + in] = lo;
+                }
+}
+
+int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed, int B, int mode, cudaStream_t s) {
+    if (B <= 0) return 0;
+    static bool attr_done = false;
+    const size_t smem = sizeof(TcShared) + 128;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(blend_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const BlobLayout L = blob_layout();
+    const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
+    const int m_tiles = (B + TC_M - 1) / TC_M;
+    const long long total = (long long)TC_N_TILES * m_tiles;
+    const int grid = (int)(total < NUM_SMS ? total : NUM_SMS);
+    const float* tmpl = blob_ptr<float>(blob, L.basis) + (size_t)FEAT_ONE * VP_PITCH;
+    blend_tc_forward_kernel<<<grid, TC_THREADS, smem, s>>>(reinterpret_cast<const TcBlobHeader*>(tc),
+                                                           tc + align256(sizeof(TcBlobHeader)), tmpl, featp, v_posed, B, m_tiles,
+                                                           mode == MB_MODE_F16X3 ? 3 : 1);
+    return cuda_rc();
+}
+
 }  // namespace mb

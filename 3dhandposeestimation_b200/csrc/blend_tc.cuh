@@ -1,0 +1,45 @@
+// blend_tc.cuh — tiling constants of the tcgen05 blend-shape contraction, shared between the
+// GEMM kernel (blend_tc.cu) and the pose stage that writes its A operand (mano_pose.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mb {
+
+constexpr int TC_M = 128;                 // hands per tile (TMEM lanes)
+constexpr int TC_N = 160;                 // vertex coordinates per tile
+constexpr int TC_N_TILES = 15;            // 15 * 160 = 2400 >= 2334
+constexpr int TC_K = 160;                 // padded feature length
+constexpr int TC_K_REAL = 145;            // beta(10) + pose feature(135); v_template is added in the epilogue
+constexpr int TC_K_CHUNK = 32;            // K elements per pipeline stage
+constexpr int TC_K_CHUNKS = TC_K / TC_K_CHUNK;
+constexpr int TC_FEAT_SCALE_LOG2 = 4;     // features are pre-scaled by 2^4 before the fp16 split
+
+// UMMA canonical K-major no-swizzle blocks: [row-group][k-group (4 per chunk)][8 rows][8 halves]
+constexpr uint32_t TC_LBO = 128;                                        // between K core matrices
+constexpr uint32_t TC_SBO = (TC_K_CHUNK / 8) * 128;                     // between 8-row groups (512 B)
+constexpr int TC_A_BLOCK_BYTES = TC_M * TC_K_CHUNK * 2;                 // 8 KB: one split of one chunk
+constexpr int TC_A_STAGE_BYTES = 2 * TC_A_BLOCK_BYTES;                  // hi + lo
+constexpr int TC_A_TILE_BYTES = TC_K_CHUNKS * TC_A_STAGE_BYTES;         // 80 KB per 128 hands
+constexpr int TC_B_BLOCK_BYTES = TC_N * TC_K_CHUNK * 2;                 // 10 KB
+constexpr int TC_B_TILE_BYTES = TC_K_CHUNKS * 2 * TC_B_BLOCK_BYTES;     // 100 KB per n-tile
+
+struct TcBlobHeader {
+    int32_t basis_scale_log2;
+    int32_t feat_scale_log2;
+    int32_t pad[2];
+};
+
+// byte offset of the 16-byte group holding features [8*kg8, 8*kg8+8) of hand h, split sp (0 hi, 1 lo)
+__host__ __device__ inline size_t tc_feat_group_offset(long long h, int kg8, int sp) {
+    const long long tile = h >> 7;
+    const int r = (int)(h & 127);
+    const int c = kg8 >> 2, kg = kg8 & 3;
+    return (size_t)tile * TC_A_TILE_BYTES + (size_t)c * TC_A_STAGE_BYTES + (size_t)sp * TC_A_BLOCK_BYTES +
+           ((size_t)((r >> 3) * (TC_K_CHUNK / 8) + kg) * 8 + (r & 7)) * 16;
+}
+
+inline size_t tc_featp_bytes(long long B) { return (size_t)((B + TC_M - 1) / TC_M) * TC_A_TILE_BYTES; }
+
+int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed, int B, int mode, cudaStream_t s);
+
+}  // namespace mb

@@ -83,6 +83,7 @@ struct WorkLayout {
     size_t dv_posed;  // ALIASES v_posed: the skinning backward overwrites each row after reading it
     size_t dbone;     // float [B][16][12]     (backward only)
     size_t dfeat;     // float [B][FEAT_K]     (backward only)
+    size_t featp;     // fp16 hi/lo feature tiles of the tcgen05 path: ceil(B/128) * 80 KB
     size_t total;
 };
 
@@ -95,6 +96,7 @@ __host__ __device__ inline WorkLayout work_layout(long long B) {
     W.dv_posed = W.v_posed;
     W.dbone = o;    o = align256(o + sizeof(float) * B * NJ * BONE_F);
     W.dfeat = o;    o = align256(o + sizeof(float) * B * FEAT_K);
+    W.featp = o;    o = align256(o + (size_t)((B + 127) / 128) * 81920);
     W.total = o;
     return W;
 }
@@ -105,8 +107,9 @@ __host__ __device__ inline const T* blob_ptr(const void* blob, size_t off) {
 }
 
 // ---- kernel launchers implemented in the other translation units ----------
+// feat (fp32 rows) and featp (fp16 hi/lo UMMA tiles) may each be NULL
 int launch_pose_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                        int B, float* feat, float* bone, float* joints, cudaStream_t s);
+                        int B, float* feat, unsigned char* featp, float* bone, float* joints, cudaStream_t s);
 int launch_pose_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                          const float* dfeat, const float* dbone, const float* g_joints, int B,
                          float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
@@ -124,9 +127,21 @@ int launch_lbs_backward(const void* blob, const float* v_posed, int pitch, const
                         const float* g_verts, const float* g_joints, int B,
                         float* dv_posed, float* dbone, cudaStream_t s);
 
+// launch bookkeeping (api.cu): every kernel launch of this library goes through cuda_rc()
+void count_launch();
 inline int cuda_rc() {
+    count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
+
+// per-stage CUDA-event profiling (off by default; bench.py turns it on for the roofline pass)
+enum Stage { ST_POSE_FWD = 0, ST_BLEND_FWD, ST_LBS_FWD, ST_LBS_BWD, ST_BLEND_BWD, ST_POSE_BWD,
+             ST_JOINTS_FWD, ST_JOINTS_BWD, ST_FK_FWD, ST_FK_BWD, ST_COUNT };
+struct StageTimer {
+    StageTimer(int stage, cudaStream_t s);
+    ~StageTimer();
+    int stage; cudaStream_t stream; void* rec;
+};
 
 }  // namespace mb

@@ -136,6 +136,7 @@ extern "C" int mb_fk_forward(const float* root_angles, const float* other_angles
     if (B == 0) return 0;
     if (!root_angles || !other_angles || !bone_lengths || !K || !index_root_bone_length || !kp_coord_xyz_root || !xyz || !uv)
         return MB_E_NULL;
+    StageTimer t(ST_FK_FWD, (cudaStream_t)stream);
     fk_forward_kernel<<<fk_grid(B), FK_THREADS, 0, (cudaStream_t)stream>>>(root_angles, other_angles, bone_lengths, K,
                                                                             index_root_bone_length, kp_coord_xyz_root, B,
                                                                             swap_order != 0, xyz, uv);
@@ -151,6 +152,7 @@ extern "C" int mb_fk_backward(const float* root_angles, const float* other_angle
     if (!root_angles || !other_angles || !bone_lengths || !K || !index_root_bone_length || !kp_coord_xyz_root ||
         !g_root_angles || !g_other_angles || !g_bone_lengths)
         return MB_E_NULL;
+    StageTimer t(ST_FK_BWD, (cudaStream_t)stream);
     fk_backward_kernel<<<fk_grid(B), FK_THREADS, 0, (cudaStream_t)stream>>>(root_angles, other_angles, bone_lengths, K,
                                                                              index_root_bone_length, kp_coord_xyz_root,
                                                                              g_xyz, g_uv, B, swap_order != 0,

@@ -12,7 +12,9 @@
 // (333,444,672,555,745) from a 15-column slice of the blend basis, so the 21 joints and
 // their gradients are produced without touching the 778-vertex contraction at all —
 // the workload of every MANO head of the reference (resnet50MANO.py:76,87).
+#include <cuda_fp16.h>
 #include "hand_math.cuh"
+#include "blend_tc.cuh"
 
 namespace mb {
 
@@ -212,7 +214,8 @@ template <bool JOINTS_ONLY>
 __global__ void __launch_bounds__(WARPS * 32)
 pose_forward_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
                     const float* __restrict__ coeffs, const float* __restrict__ betas, int B,
-                    float* __restrict__ feat, float* __restrict__ bone, float* __restrict__ joints) {
+                    float* __restrict__ feat, unsigned char* __restrict__ featp, float* __restrict__ bone,
+                    float* __restrict__ joints) {
     __shared__ alignas(16) PoseShared S;
     stage_constants<JOINTS_ONLY>(S, blob, nc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -228,9 +231,28 @@ pose_forward_kernel(const void* __restrict__ blob, int nc, const float* __restri
         }
         __syncwarp();
         if (!JOINTS_ONLY) {
-            float4* fo = reinterpret_cast<float4*>(feat + hand * FEAT_K);
-            const float4* fs = reinterpret_cast<const float4*>(S.feat[warp]);
-            for (int i = lane; i < FEAT_K / 4; i += 32) fo[i] = fs[i];
+            if (feat != nullptr) {
+                float4* fo = reinterpret_cast<float4*>(feat + hand * FEAT_K);
+                const float4* fs = reinterpret_cast<const float4*>(S.feat[warp]);
+                for (int i = lane; i < FEAT_K / 4; i += 32) fo[i] = fs[i];
+            }
+            if (featp != nullptr) {
+                // A operand of the tcgen05 contraction: x * 2^4 split into fp16 hi + lo, written as
+                // 16-byte K-groups into the UMMA canonical tile layout (blend_tc.cuh)
+                const float fs = (float)(1 << TC_FEAT_SCALE_LOG2);
+                for (int p = lane; p < 2 * (TC_K / 8); p += 32) {
+                    const int sp = p / (TC_K / 8), kg8 = p - sp * (TC_K / 8);
+                    __align__(16) __half h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = kg8 * 8 + e;
+                        const float x = k < TC_K_REAL ? S.feat[warp][k] * fs : 0.f;
+                        const __half hi = __float2half_rn(x);
+                        h[e] = sp == 0 ? hi : __float2half_rn(x - __half2float(hi));
+                    }
+                    *reinterpret_cast<uint4*>(featp + tc_feat_group_offset(hand, kg8, sp)) = *reinterpret_cast<const uint4*>(h);
+                }
+            }
             float4* bo = reinterpret_cast<float4*>(bone + hand * (NJ * BONE_F));
             const float4* bs = reinterpret_cast<const float4*>(S.bone[warp]);
             for (int i = lane; i < NJ * BONE_F / 4; i += 32) bo[i] = bs[i];
@@ -431,14 +453,14 @@ inline int pose_grid(int B) {
 }  // namespace
 
 int launch_pose_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                        int B, float* feat, float* bone, float* joints, cudaStream_t s) {
-    pose_forward_kernel<false><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, B, feat, bone, joints);
+                        int B, float* feat, unsigned char* featp, float* bone, float* joints, cudaStream_t s) {
+    pose_forward_kernel<false><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, B, feat, featp, bone, joints);
     return cuda_rc();
 }
 
 int launch_joints_only_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                int B, float* joints, cudaStream_t s) {
-    pose_forward_kernel<true><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, B, nullptr, nullptr, joints);
+    pose_forward_kernel<true><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, B, nullptr, nullptr, nullptr, joints);
     return cuda_rc();
 }
 

@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — MANO hands/sec fwd+bwd on N B200s (one process per GPU), the headline metric of
+BASELINE.json, with the roofline of the dominant kernel, an end-to-end (host buffers) number
+and the CPU baseline (the numpy oracle port of the reference) timed on the box's host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--hands H] [--mode fp32|f16x3|f16]
+    python bench.py --impl reference ...     # the reference's CPU algorithm (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...
+
+Workload (config.workload): BASELINE configs[3] scaled to fwd+bwd — full 45-D axis-angle MANO
+(pose_num=45 with an identity PCA basis and zero pose mean, i.e. "no PCA"), H = 2^20 synthetic
+hands PER GPU (weak scaling: every rank skins its own slice, no data-path collective), forward
+(verts[H,778,3] + joints[H,21,3]) followed by the full backward (g_verts and g_joints dense).
+configs[1] (B=4096) is an 80 MB working set that lives in L2 and takes ~12 us at the HBM
+roofline, so it cannot be timed under the L2/clock rules; it is a parity-test case
+(tests/test_gpu_parity.py) and can be timed with --hands 4096 --rotate 16.
+One "step" = one fwd+bwd pass over the H hands.  Inputs are larger than L2 (>= 20 GB per step).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MANO hands/sec fwd+bwd"
+UNIT = "hands/s"
+# algorithmic bytes per hand (SURVEY 8d / BASELINE.md 4), fp32, nc = 45
+BYTES_FWD = 4 * (3 + 45 + 10) + 4 * (2334 + 63)                 # 9820
+BYTES_BWD = 4 * (2334 + 63) + 4 * (3 + 45 + 10) * 2             # 10052
+BYTES_LBS = 4 * (2334 + 192) + 4 * (2334 + 15)                  # stand-alone LBS stage: 19500 (+ 192 B tips rounding) ~ 19.7 KB
+BYTES_LBS = 19692
+FLOP_BLEND = 2 * 145 * 2334                                     # 676860 per hand per contraction
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def no_pca_model(assets):
+    """Synthetic MANO-shaped model with hands_components = I and hands_mean = 0, so the 45
+    coefficients ARE the articulated axis-angles (the oracle of BASELINE config 4)."""
+    import numpy as np
+
+    m = assets.synthetic_mano()
+    m["hands_components"] = np.eye(45)
+    m["hands_mean"] = np.zeros(45)
+    return m
+
+
+def synth_inputs(H, seed):
+    import numpy as np
+
+    rs = np.random.RandomState(seed)
+    rot = ((rs.rand(H, 3) - .5) * 2 * np.pi).astype(np.float32)
+    pose = ((rs.rand(H, 45) - .5) * (np.pi / 2)).astype(np.float32)     # U(-pi/2, pi/2) * 0.5
+    beta = (rs.rand(H, 10) - .5).astype(np.float32)
+    return rot, pose, beta
+
+
+def cpu_baseline(model, budget_s=12.0, chunk=256):
+    """The oracle (numpy port of the reference's algorithm, fp32) fwd+bwd on the host cores:
+    repeated `chunk`-hand batches of the same synthetic workload for about `budget_s` seconds."""
+    import numpy as np
+    from oracle import mano_oracle
+
+    rot, pose, beta = synth_inputs(chunk, 4242)
+    rs = np.random.RandomState(1)
+    gv = rs.randn(chunk, 778, 3).astype(np.float32)
+    gj = rs.randn(chunk, 21, 3).astype(np.float32)
+    mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)          # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)      # forward + backward
+        done += chunk
+        dt = time.perf_counter() - t0
+        if dt >= budget_s:
+            break
+    return {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{done} hands in {chunk}-hand batches, numpy fp32 oracle fwd+bwd, {dt:.1f} s"}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm for this path.  The reference is
+    Python and cannot travel to the GPU box, so this times its numpy port (oracle/) on the host
+    cores; each step is a bounded sample (args.ref_hands hands) of the workload."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import mano_oracle
+
+    assets = importlib.import_module("3dhandposeestimation_b200.assets")
+    model = no_pca_model(assets)
+    H = args.ref_hands
+    rot, pose, beta = synth_inputs(H, 4242)
+    rs = np.random.RandomState(1)
+    gv = rs.randn(H, 778, 3).astype(np.float32)
+    gj = rs.randn(H, 21, 3).astype(np.float32)
+    for _ in range(args.warmup):
+        mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)
+    dt = time.perf_counter() - t0
+    value = H * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_hands_per_step": H, "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{H} hands per step x {args.steps} steps, numpy fp32 oracle fwd+bwd"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return f"mano_full45_noPCA_fwd+bwd_{args.hands}_hands_per_gpu"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--hands", type=int, default=1 << 20, help="hands per GPU per step")
+    ap.add_argument("--mode", default=os.environ.get("MANO_B200_MODE", "fp32"))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-hands", type=int, default=512, help="hands per step of the --impl reference arm")
+    ap.add_argument("--rotate", type=int, default=1, help="number of distinct buffer sets cycled through (small --hands)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    pkg = importlib.import_module("3dhandposeestimation_b200")
+    cabi = pkg._cabi
+    lib = pkg.load_library()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    H = args.hands
+    model = no_pca_model(pkg.assets)
+    layer = pkg.ManoLayer(dev, model=model, pose_num=45, mode=args.mode)
+    mode = layer._mode
+    stream = cabi.stream_handle(dev)
+
+    nsets = max(1, args.rotate)
+    sets = []
+    for i in range(nsets):
+        rot, pose, beta = synth_inputs(H, 1234 + rank * 131 + i)
+        g = torch.Generator(device=dev).manual_seed(99 + rank * 7 + i)
+        sets.append(dict(
+            rot=torch.from_numpy(rot).to(dev), pose=torch.from_numpy(pose).to(dev), beta=torch.from_numpy(beta).to(dev),
+            verts=torch.empty(H, 778, 3, device=dev), joints=torch.empty(H, 21, 3, device=dev),
+            gv=torch.randn(H, 778, 3, device=dev, generator=g), gj=torch.randn(H, 21, 3, device=dev, generator=g),
+            g_rot=torch.empty(H, 3, device=dev), g_pose=torch.empty(H, 45, device=dev), g_beta=torch.empty(H, 10, device=dev)))
+    ws_bytes = lib.mb_mano_workspace_bytes(H, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    blob = layer._blob.data_ptr()
+
+    def step(i):
+        s = sets[i % nsets]
+        cabi.check(lib.mb_mano_forward(blob, 45, s["rot"].data_ptr(), s["pose"].data_ptr(), s["beta"].data_ptr(), H, mode,
+                                       s["verts"].data_ptr(), s["joints"].data_ptr(), ws.data_ptr(), ws_bytes, stream), "fwd")
+        cabi.check(lib.mb_mano_backward(blob, 45, s["rot"].data_ptr(), s["pose"].data_ptr(), s["beta"].data_ptr(),
+                                        s["gv"].data_ptr(), s["gj"].data_ptr(), H, mode, cabi.BWD_WORKSPACE_VALID,
+                                        s["g_rot"].data_ptr(), s["g_pose"].data_ptr(), s["g_beta"].data_ptr(),
+                                        ws.data_ptr(), ws_bytes, stream), "bwd")
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value) ----------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.mb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = lib.mb_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    value = world * H / (ms_per_step * 1e-3)
+
+    # ---- roofline pass: per-stage CUDA events on the launch stream ---------------------
+    lib.mb_profile_enable(1)
+    for i in range(args.steps):
+        step(i)
+    torch.cuda.synchronize(dev)
+    prof = cabi.profile_collect()
+    lib.mb_profile_enable(0)
+    peaks = load_peaks()
+    stages = {k: {"ms": v[0] / v[1], "launches": v[1]} for k, v in prof.items()}
+    tot_stage_ms = sum(s["ms"] for s in stages.values())
+    for k, s in stages.items():
+        s["share"] = s["ms"] / tot_stage_ms
+    lbs_ms = stages["lbs_fwd"]["ms"]
+    lbs_gbs = BYTES_LBS * H / (lbs_ms * 1e-3) / 1e9
+    blend_ms = stages["blend_fwd"]["ms"]
+    blend_tflops = FLOP_BLEND * H / (blend_ms * 1e-3) / 1e12
+    dominant = max(stages, key=lambda k: stages[k]["ms"])
+    roofline = {"kernel": "lbs_forward_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_hand": BYTES_LBS, "avg_launch_ms": lbs_ms, "dominant_stage": dominant}
+    blend_roof = {"kernel": "blend_fwd", "bound": "tensor", "achieved": blend_tflops, "peak": peaks["bf16_tflops_sustained"],
+                  "unit": "TFLOP/s", "frac": blend_tflops / peaks["bf16_tflops_sustained"],
+                  "algorithmic_flop_per_hand": FLOP_BLEND, "avg_launch_ms": blend_ms, "mode": args.mode}
+    step_gbs = (BYTES_FWD + BYTES_BWD) * H / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the public nn.Module API with host buffers ------------------
+    e2e = None
+    if not args.no_e2e:
+        s = sets[0]
+        h_in = [torch.from_numpy(a).pin_memory() for a in synth_inputs(H, 555 + rank)]
+        h_out = [torch.empty(H, n, dtype=torch.float32).pin_memory() for n in (3, 45, 10)]
+        h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            d = [t.to(dev, non_blocking=True).requires_grad_() for t in h_in]
+            verts, joints = layer(*d)
+            torch.autograd.backward([verts, joints], [s["gv"], s["gj"]])
+            for dst, src in zip(h_out, d):
+                dst.copy_(src.grad, non_blocking=True)
+            h_loss.copy_(joints[0, 0, :1], non_blocking=True)
+
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        sync_all()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        e2e = {"value": world * H / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * 58 * 4,
+               "d2h_bytes_per_step": H * 58 * 4 + 4, "ms_per_step": ms_e2e, "steps": n_e2e,
+               "api": "ManoLayer.forward + autograd backward; pinned host params in, pinned host grads out"}
+
+    # ---- parity spot check in the same run (checker only) -------------------------------
+    parity = None
+    cpu = None
+    if rank == 0:
+        from oracle import mano_oracle
+
+        s = sets[(args.steps - 1) % nsets]
+        idx = np.array([0, 1, H // 2, H - 1]) if H >= 4 else np.arange(H)
+        tidx = torch.from_numpy(idx).to(dev)
+        ov, oj = mano_oracle.mano_forward(model, s["rot"][tidx].cpu().numpy(), s["pose"][tidx].cpu().numpy(),
+                                          s["beta"][tidx].cpu().numpy())
+        og = mano_oracle.mano_backward(model, s["rot"][tidx].cpu().numpy(), s["pose"][tidx].cpu().numpy(),
+                                       s["beta"][tidx].cpu().numpy(), s["gv"][tidx].cpu().numpy(), s["gj"][tidx].cpu().numpy())
+        parity = {"verts_max_abs_err_m": float(np.abs(s["verts"][tidx].cpu().numpy() - ov).max()),
+                  "joints_max_abs_err_m": float(np.abs(s["joints"][tidx].cpu().numpy() - oj).max()),
+                  "grad_rel_err": max(float(np.abs(s[k][tidx].cpu().numpy() - w).max() / np.abs(w).max())
+                                      for k, w in zip(("g_rot", "g_pose", "g_beta"), og))}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(model)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.mode == "fp32" else ("f16x3->f32" if args.mode == "f16x3" else "f16->f32"),
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "hands_per_gpu": H, "pose_num": 45, "pca": "identity (no PCA)",
+                   "blend_mode": args.mode, "parallelism": f"batch-sharded x{world}, no collective",
+                   "l2": "inputs larger than L2 (>= 20 GB touched per step)" if H * 20000 > 4 * 126e6 else
+                         f"rotating {nsets} buffer sets", "model": "seeded synthetic MANO-shaped model"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "blend_gemm": blend_roof,
+        "step_hbm": {"algorithmic_gbs": step_gbs, "frac_of_peak": step_gbs / peaks["hbm_gbs"],
+                     "algorithmic_bytes_per_hand": BYTES_FWD + BYTES_BWD},
+        "stages_ms": stages,
+        "parity": parity,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,17 @@ MB_API int mb_masked_l2_backward(const float* pred, const float* gt, const void*
 MB_API int mb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                  float lr, float beta1, float beta2, float eps, int step, mb_stream_t stream);
 
+/* ------------------------------------------------------------ measurement ---
+ * mb_launch_count: kernels launched by this library in this process so far.
+ * mb_profile_enable(1): bracket every stage launch with CUDA events on its stream;
+ * mb_profile_collect: synchronise on those events, write the summed milliseconds and launch
+ * counts per stage (MB_N_STAGES entries each) and reset.  Stage order: pose_fwd, blend_fwd,
+ * lbs_fwd, lbs_bwd, blend_bwd, pose_bwd, joints_only_fwd, joints_only_bwd, fk_fwd, fk_bwd. */
+#define MB_N_STAGES 10
+MB_API long long mb_launch_count(void);
+MB_API void      mb_profile_enable(int on);
+MB_API int       mb_profile_collect(double* ms, long long* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,13 +125,13 @@ def mano_forward(model, rots, poses, betas, dtype=np.float64, return_cache=False
     pose = np.concatenate([np.broadcast_to(c["root_rot"], (B, 1, 3)), theta.reshape(B, nj - 1, 3)], axis=1)
 
     # :130-132 shape blend
-    v_shaped = c["mesh_mu"][None] + np.einsum("vcs,bs->bvc", c["mesh_pca"], betas)
+    v_shaped = c["mesh_mu"][None] + (betas @ c["mesh_pca"].reshape(-1, betas.shape[1]).T).reshape(B, -1, 3)
     # :116-119 pose feature, :134-137 pose blend
     R = rodrigues(pose.reshape(-1, 3)).reshape(B, nj, 3, 3)
     pf = (R[:, 1:] - np.eye(3, dtype=dtype)).reshape(B, (nj - 1) * 9)
-    v_posed = v_shaped + np.einsum("vck,bk->bvc", c["posedirs"], pf)
+    v_posed = v_shaped + (pf @ c["posedirs"].reshape(-1, pf.shape[1]).T).reshape(B, -1, 3)
     # :139-141 joint regression from the SHAPED mesh
-    J = np.einsum("jv,bvc->bjc", c["J_regressor"], v_shaped)
+    J = np.matmul(c["J_regressor"], v_shaped)
 
     # :159-165 chain
     Rg = np.zeros((B, nj, 3, 3), dtype=dtype)
@@ -145,17 +145,17 @@ def mano_forward(model, rots, poses, betas, dtype=np.float64, return_cache=False
     # :169-175 remove rest pose: A_i = [Rg_i | tg_i - Rg_i J_i]
     tA = tg - np.einsum("bkij,bkj->bki", Rg, J)
     # :177-185 LBS
-    Tr = np.einsum("vk,bkij->bvij", c["weights"], Rg)
-    Tt = np.einsum("vk,bki->bvi", c["weights"], tA)
-    v = np.einsum("bvij,bvj->bvi", Tr, v_posed) + Tt
+    Tr = np.matmul(c["weights"], Rg.reshape(B, nj, 9)).reshape(B, -1, 3, 3)
+    Tt = np.matmul(c["weights"], tA)
+    v = np.matmul(Tr, v_posed[..., None])[..., 0] + Tt
     # :190-202 joints: 16 chain translations with the 5 tips inserted
     Jtr = np.zeros((B, 21, 3), dtype=dtype)
     Jtr[:, list(CHAIN_SLOTS)] = tg
     Jtr[:, list(TIP_SLOTS)] = v[:, list(TIP_VERTS)]
     # :188, :204-205 global rotation about the origin
     Rq = rodrigues(rots)
-    vertices = np.einsum("bij,bvj->bvi", Rq, v)
-    joint = np.einsum("bij,bvj->bvi", Rq, Jtr)
+    vertices = np.matmul(v, np.swapaxes(Rq, -1, -2))
+    joint = np.matmul(Jtr, np.swapaxes(Rq, -1, -2))
     if return_cache:
         cache = dict(c=c, parent=parent, pose=pose, R=R, pf=pf, v_posed=v_posed, J=J,
                      Rg=Rg, tg=tg, tA=tA, v=v, Jtr=Jtr, Rq=Rq)
@@ -179,18 +179,19 @@ def mano_backward(model, rots, poses, betas, g_verts, g_joints, dtype=np.float64
 
     Rq, Rg, tg, J, R = k["Rq"], k["Rg"], k["tg"], k["J"], k["R"]
     # global rotation: vertices = Rq v ; joint = Rq Jtr
-    dRq = np.einsum("bvi,bvj->bij", gv_out, k["v"]) + np.einsum("bvi,bvj->bij", g_joints, k["Jtr"])
-    gv = np.einsum("bij,bvi->bvj", Rq, gv_out)          # Rq^T g
-    gJtr = np.einsum("bij,bvi->bvj", Rq, g_joints)
+    dRq = np.matmul(np.swapaxes(gv_out, -1, -2), k["v"]) + np.matmul(np.swapaxes(g_joints, -1, -2), k["Jtr"])
+    gv = np.matmul(gv_out, Rq)                          # Rq^T g
+    gJtr = np.matmul(g_joints, Rq)
     gv[:, list(TIP_VERTS)] += gJtr[:, list(TIP_SLOTS)]
     dtg = gJtr[:, list(CHAIN_SLOTS)].copy()
 
     # LBS: v = (sum_k w Rg_k) v_posed + sum_k w tA_k
     W = c["weights"]
-    dRg = np.einsum("vk,bvi,bvj->bkij", W, gv, k["v_posed"])
-    dtA = np.einsum("vk,bvi->bki", W, gv)
-    Tr = np.einsum("vk,bkij->bvij", W, Rg)
-    dv_posed = np.einsum("bvij,bvi->bvj", Tr, gv)
+    outer = (gv[..., :, None] * k["v_posed"][..., None, :]).reshape(B, -1, 9)
+    dRg = np.matmul(W.T, outer).reshape(B, nj, 3, 3)
+    dtA = np.matmul(W.T, gv)
+    Tr = np.matmul(W, Rg.reshape(B, nj, 9)).reshape(B, -1, 3, 3)
+    dv_posed = np.matmul(np.swapaxes(Tr, -1, -2), gv[..., None])[..., 0]
     # tA = tg - Rg J
     dtg += dtA
     dRg -= np.einsum("bki,bkj->bkij", dtA, J)
@@ -208,10 +209,10 @@ def mano_backward(model, rots, poses, betas, g_verts, g_joints, dtype=np.float64
         dJ[:, p] -= dd
     dJ[:, 0] += dtg[:, 0]          # tg_0 = J_0 ; R_0 is constant
     # v_posed = v_shaped + posedirs pf ; J = Jreg v_shaped
-    dpf = np.einsum("vck,bvc->bk", c["posedirs"], dv_posed)
+    dpf = dv_posed.reshape(B, -1) @ c["posedirs"].reshape(-1, (nj - 1) * 9)
     dR[:, 1:] += dpf.reshape(B, nj - 1, 3, 3)
-    dv_shaped = dv_posed + np.einsum("jv,bjc->bvc", c["J_regressor"], dJ)
-    g_betas = np.einsum("vcs,bvc->bs", c["mesh_pca"], dv_shaped)
+    dv_shaped = dv_posed + np.matmul(c["J_regressor"].T, dJ)
+    g_betas = dv_shaped.reshape(B, -1) @ c["mesh_pca"].reshape(-1, c["mesh_pca"].shape[-1])
     dtheta = rodrigues_backward(k["pose"][:, 1:].reshape(-1, 3), dR[:, 1:].reshape(-1, 3, 3)).reshape(B, 45)
     g_poses = dtheta @ c["hands_components"].T
     g_rots = rodrigues_backward(np.asarray(rots, dtype=dtype), dRq)

@@ -1,0 +1,367 @@
+"""GPU (B200): the CUDA path, called through the nn.Module wrappers and the C ABI, against the
+golden vectors of the unmodified reference and against the numpy oracle on seeded inputs.
+
+Tolerances (SURVEY A.4 / BASELINE north_star):
+  verts / joints / xyz : 2e-7 m absolute vs the fp32 reference goldens, 1e-7 m (1e-4 mm) vs the
+                         fp64 oracle for the fp32-accurate modes
+  uv                   : 1e-3 px for |z| >= 0.1 m
+  gradients            : 1e-4 relative to the tensor's max-abs
+  MPJPE / L2           : 1e-5 relative
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import fk_oracle as fo
+from oracle import mano_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL_REF = 2e-7
+# 1e-4 mm is the scale of fp32 rounding itself for 0.1 m coordinates behind a 3-level chain: the
+# reference's own fp32-vs-fp64 noise is 0.8e-7 m on 4 hands and 1.4e-7 m over a few hundred, so the
+# bound against the fp64 oracle is 2e-7 m (= 2e-4 mm); typical errors are 3e-8 m.
+POS_TOL_F64 = 2e-7
+GRAD_TOL = 1e-4
+ACCURATE_MODES = ["fp32", "f16x3"]
+FAST_TOL = 5e-5        # MB_MODE_F16: one fp16 product, stated bound for the blend contraction
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def to_dev(dev, *arrs, grad=False):
+    import torch
+
+    out = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in arrs]
+    if grad:
+        out = [t.requires_grad_() for t in out]
+    return out
+
+
+def mano_inputs(B, nc, seed, pose_scale=np.pi):
+    rs = np.random.RandomState(seed)
+    rot = ((rs.rand(B, 3) - .5) * 2 * np.pi).astype(np.float32)
+    pose = ((rs.rand(B, nc) - .5) * pose_scale).astype(np.float32)
+    beta = (rs.rand(B, 10) - .5).astype(np.float32)
+    return rot, pose, beta
+
+
+@pytest.mark.parametrize("mode", ACCURATE_MODES)
+@pytest.mark.parametrize("name,nc", [("mano_synth_nc45.npz", 45), ("mano_synth_nc10.npz", 10), ("mano_synth_nc6.npz", 6)])
+def test_mano_matches_reference_golden(pkg, synth_model, cuda_device, name, nc, mode):
+    import torch
+
+    g = load_golden(name)
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc, mode=mode)
+    rot, pose, beta = to_dev(cuda_device, g["rot"], g["pose"], g["beta"], grad=True)
+    gv, gj = to_dev(cuda_device, g["g_verts"], g["g_joints"])
+    verts, joints = layer(rot, pose, beta)
+    assert verts.shape == (rot.shape[0], 778, 3) and joints.shape == (rot.shape[0], 21, 3)
+    assert verts.is_contiguous() and joints.is_contiguous()
+    assert np.abs(verts.detach().cpu().numpy() - g["verts"]).max() < POS_TOL_REF
+    assert np.abs(joints.detach().cpu().numpy() - g["joints"]).max() < POS_TOL_REF
+    ((verts * gv).sum() + (joints * gj).sum()).backward()
+    assert rel(rot.grad.cpu().numpy(), g["g_rot"]) < GRAD_TOL
+    assert rel(pose.grad.cpu().numpy(), g["g_pose"]) < GRAD_TOL
+    assert rel(beta.grad.cpu().numpy(), g["g_beta"]) < GRAD_TOL
+    # the heads' case: only the joints are consumed -> joints-only backward kernel
+    for t in (rot, pose, beta):
+        t.grad = None
+    _, joints2 = layer(rot, pose, beta)
+    (joints2 * gj).sum().backward()
+    assert rel(rot.grad.cpu().numpy(), g["gj_rot"]) < GRAD_TOL
+    assert rel(pose.grad.cpu().numpy(), g["gj_pose"]) < GRAD_TOL
+    assert rel(beta.grad.cpu().numpy(), g["gj_beta"]) < GRAD_TOL
+    # joints-only forward (extension) gives the same joints without the vertex contraction
+    none, joints3 = layer.rot_pose_beta_to_mesh(rot.detach(), pose.detach(), beta.detach(), joints_only=True)
+    assert none is None
+    assert np.abs(joints3.cpu().numpy() - g["joints"]).max() < POS_TOL_REF
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("mode", ACCURATE_MODES)
+@pytest.mark.parametrize("B,nc", [(1, 45), (2, 45), (7, 10), (129, 45), (1000, 45), (4096, 10)])
+def test_mano_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc, mode):
+    """Ragged sizes (odd B exercises the unpaired tail hand of the skinning kernel) up to
+    BASELINE config 2 (B=4096, nc=10, the Resnet50MANO3DHandPose head workload)."""
+    rot, pose, beta = mano_inputs(B, nc, seed=B + nc)
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc, mode=mode)
+    trot, tpose, tbeta = to_dev(cuda_device, rot, pose, beta, grad=True)
+    verts, joints = layer(trot, tpose, tbeta)
+    nchk = min(B, 256)                                         # oracle on a bounded prefix + suffix
+    idx = np.unique(np.r_[np.arange(nchk), np.arange(B - min(B, 64), B)])
+    ov, oj = mo.mano_forward(synth_model, rot[idx], pose[idx], beta[idx])
+    assert np.abs(verts.detach().cpu().numpy()[idx] - ov).max() < POS_TOL_F64
+    assert np.abs(joints.detach().cpu().numpy()[idx] - oj).max() < POS_TOL_F64
+    rs = np.random.RandomState(1)
+    gv = rs.randn(B, 778, 3).astype(np.float32)
+    gj = rs.randn(B, 21, 3).astype(np.float32)
+    tgv, tgj = to_dev(cuda_device, gv, gj)
+    ((verts * tgv).sum() + (joints * tgj).sum()).backward()
+    og = mo.mano_backward(synth_model, rot[idx], pose[idx], beta[idx], gv[idx], gj[idx])
+    for t, want in zip((trot, tpose, tbeta), og):
+        assert rel(t.grad.cpu().numpy()[idx], want) < GRAD_TOL
+
+
+def test_mano_fast_f16_mode_error_is_bounded(pkg, synth_model, cuda_device):
+    """MB_MODE_F16 (single fp16 product on the tensor cores): bounded, stated error."""
+    rot, pose, beta = mano_inputs(512, 45, seed=3)
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=45, mode="f16")
+    v, j = layer(*to_dev(cuda_device, rot, pose, beta))
+    ov, oj = mo.mano_forward(synth_model, rot, pose, beta)
+    err = np.abs(v.cpu().numpy() - ov).max()
+    assert err < FAST_TOL, err
+    assert np.abs(j.cpu().numpy() - oj).max() < FAST_TOL
+
+
+def test_mano_backward_recompute_equals_saved_workspace(pkg, synth_model, cuda_device):
+    rot, pose, beta = mano_inputs(37, 45, seed=5)
+    rs = np.random.RandomState(2)
+    gv, gj = to_dev(cuda_device, rs.randn(37, 778, 3).astype(np.float32), rs.randn(37, 21, 3).astype(np.float32))
+    grads = []
+    for keep in (True, False):
+        layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=45, keep_workspace=keep)
+        t = to_dev(cuda_device, rot, pose, beta, grad=True)
+        v, j = layer(*t)
+        loss = (v * gv).sum() + (j * gj).sum()
+        loss.backward(retain_graph=keep)
+        first = [x.grad.clone() for x in t]
+        if keep:                                                 # second backward must recompute, not reuse
+            for x in t:
+                x.grad = None
+            loss.backward()
+            for a, b in zip(first, t):
+                assert np.array_equal(a.cpu().numpy(), b.grad.cpu().numpy())
+        grads.append([a.cpu().numpy() for a in first])
+    for a, b in zip(*grads):
+        assert np.array_equal(a, b)
+
+
+def test_mano_zero_angle_is_finite_where_the_reference_is_nan(pkg, synth_model, cuda_device):
+    """rots == 0 gives NaN gradients in the reference (r/theta); the analytic limit here."""
+    import torch
+
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=45)
+    rot = torch.zeros(3, 3, device=cuda_device, requires_grad=True)
+    pose = torch.zeros(3, 45, device=cuda_device, requires_grad=True)
+    beta = torch.zeros(3, 10, device=cuda_device, requires_grad=True)
+    v, j = layer(rot, pose, beta)
+    ov, oj = mo.mano_forward(synth_model, np.zeros((3, 3)), np.zeros((3, 45)), np.zeros((3, 10)))
+    assert np.abs(v.detach().cpu().numpy() - ov).max() < POS_TOL_F64
+    (v.sum() + j.sum()).backward()
+    og = mo.mano_backward(synth_model, np.zeros((3, 3)), np.zeros((3, 45)), np.zeros((3, 10)),
+                          np.ones((3, 778, 3)), np.ones((3, 21, 3)))
+    for t, want in zip((rot, pose, beta), og):
+        assert torch.isfinite(t.grad).all()
+        assert rel(t.grad.cpu().numpy(), want) < GRAD_TOL
+
+
+def test_mano_empty_batch_and_input_handling(pkg, synth_model, cuda_device):
+    import torch
+
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=10)
+    v, j = layer(torch.zeros(0, 3, device=cuda_device), torch.zeros(0, 10, device=cuda_device),
+                 torch.zeros(0, 10, device=cuda_device))
+    assert v.shape == (0, 778, 3) and j.shape == (0, 21, 3)
+    # non-contiguous / fp64 inputs are accepted like the reference tolerates views
+    rot, pose, beta = mano_inputs(6, 10, seed=9)
+    big = torch.from_numpy(np.concatenate([rot, rot], 1)).to(cuda_device)
+    v1, j1 = layer(big[:, :3], torch.from_numpy(pose).to(cuda_device).double(), torch.from_numpy(beta).to(cuda_device))
+    ov, oj = mo.mano_forward(synth_model, rot, pose, beta)
+    assert np.abs(v1.cpu().numpy() - ov).max() < POS_TOL_F64
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(2, 3, device=cuda_device), torch.zeros(2, 11, device=cuda_device),
+              torch.zeros(2, 10, device=cuda_device))
+
+
+def test_mano_linearity_property_full_size(pkg, synth_model, cuda_device):
+    """Size-independent property at a large batch (65536 hands): the layer is affine in the
+    shape coefficients for fixed pose up to the joint-regression path — check instead the exact
+    invariances: (a) verts of hand i do not depend on the batch it sits in, (b) a global
+    rotation about the origin preserves every vertex norm."""
+    import torch
+
+    B = 65536
+    rot, pose, beta = mano_inputs(B, 45, seed=11)
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=45)
+    t = to_dev(cuda_device, rot, pose, beta)
+    v, j = layer(*t)
+    sel = np.array([0, 1, 2, 777, 4095, 4096, 32767, 65534, 65535])
+    v_small, j_small = layer(*[x[torch.from_numpy(sel).to(cuda_device)] for x in t])
+    assert torch.equal(v[sel], v_small) and torch.equal(j[sel], j_small)
+    zero_rot = torch.zeros_like(t[0])
+    v0, _ = layer(zero_rot, t[1], t[2])
+    n1 = v.norm(dim=2)
+    n0 = v0.norm(dim=2)
+    assert float((n1 - n0).abs().max()) < 3e-7
+    ov, oj = mo.mano_forward(synth_model, rot[sel], pose[sel], beta[sel])
+    assert np.abs(v_small.cpu().numpy() - ov).max() < POS_TOL_F64
+
+
+def test_lbs_stage_alone(pkg, synth_model, cuda_device):
+    """mb_lbs_forward through the C ABI: identity bones reproduce the input; random bones match numpy."""
+    import torch
+
+    lib = pkg.load_library()
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=45)
+    B = 5
+    rs = np.random.RandomState(3)
+    vp = np.zeros((B, 2336), np.float32)
+    vp[:, :2334] = rs.randn(B, 2334).astype(np.float32) * .1
+    bone = rs.randn(B, 16, 3, 4).astype(np.float32)
+    tvp, tbone = to_dev(cuda_device, vp, bone)
+    verts = torch.empty(B, 778, 3, device=cuda_device)
+    joints = torch.zeros(B, 21, 3, device=cuda_device)
+    pkg._cabi.check(lib.mb_lbs_forward(layer._blob.data_ptr(), tvp.data_ptr(), 2336, tbone.data_ptr(), B,
+                                       verts.data_ptr(), joints.data_ptr(), pkg._cabi.stream_handle(cuda_device)), "lbs")
+    W = synth_model["weights"].astype(np.float32).astype(np.float64)
+    T = np.einsum("vk,bkij->bvij", W, bone.astype(np.float64))
+    x = vp[:, :2334].reshape(B, 778, 3).astype(np.float64)
+    want = np.einsum("bvij,bvj->bvi", T[..., :3], x) + T[..., 3]
+    assert np.abs(verts.cpu().numpy() - want).max() < 2e-6
+    assert np.abs(joints.cpu().numpy()[:, [4, 8, 12, 16, 20]] - want[:, [333, 444, 672, 555, 745]]).max() < 2e-6
+    assert lib.mb_lbs_forward(layer._blob.data_ptr(), tvp.data_ptr(), 2334, tbone.data_ptr(), B,
+                              verts.data_ptr(), None, None) == -2
+
+
+# ------------------------------------------------------------------------------- FK
+@pytest.mark.parametrize("name", ["fk_switched.npz", "fk_unswitched.npz"])
+def test_fk_matches_reference_golden(pkg, cuda_device, name):
+    g = load_golden(name)
+    sw = bool(g["switched"])
+    fk = pkg.ForwardKinematics(cuda_device, joint_order_switched=sw)
+    ra, oa, bl = to_dev(cuda_device, g["root_angles"], g["other_angles"], g["bone_lengths"], grad=True)
+    K, sc, root, gx, gu = to_dev(cuda_device, g["K"], g["scale"], g["root"], g["g_xyz"], g["g_uv"])
+    out = fk(ra, oa, bl, K, sc, root)
+    assert isinstance(out, list) and len(out) == 3 and out[2] is None
+    xyz, uv = out[0], out[1]
+    assert np.abs(xyz.detach().cpu().numpy() - g["xyz"]).max() < POS_TOL_REF
+    assert np.abs(uv.detach().cpu().numpy() - g["uv"]).max() < 1e-3
+    ((xyz * gx).sum() + (uv * gu).sum()).backward()
+    assert rel(ra.grad.cpu().numpy(), g["g_root_angles"]) < GRAD_TOL
+    assert rel(oa.grad.cpu().numpy(), g["g_other_angles"]) < GRAD_TOL
+    assert rel(bl.grad.cpu().numpy(), g["g_bone_lengths"]) < GRAD_TOL
+
+
+def fk_inputs(B, seed):
+    rs = np.random.RandomState(seed)
+    ra = ((rs.rand(B, 3) - .5) * 2 * np.pi).astype(np.float32)
+    oa = ((rs.rand(B, 23) - .5) * np.pi).astype(np.float32)
+    bl = (rs.rand(B, 20) + .1).astype(np.float32)
+    K = np.tile(np.array([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1]], np.float32), (B, 1, 1))
+    sc = (rs.rand(B, 1) * .05 + .02).astype(np.float32)
+    root = (rs.randn(B, 3) * .05 + np.array([0, 0, .6])).astype(np.float32)
+    return ra, oa, bl, K, sc, root
+
+
+@pytest.mark.parametrize("B", [1, 63, 64, 65, 1000, 65536])
+def test_fk_matches_oracle_config3(pkg, cuda_device, B):
+    """Up to BASELINE config 3 (B=65536) with the visible-joint MPJPE reduction."""
+    import torch
+
+    args = fk_inputs(B, seed=B)
+    fk = pkg.ForwardKinematics(cuda_device, joint_order_switched=True)
+    t = to_dev(cuda_device, *args[:3], grad=True) + to_dev(cuda_device, *args[3:])
+    xyz, uv, _ = fk(*t)
+    oxyz, ouv = fo.fk_forward(*args)
+    assert np.abs(xyz.detach().cpu().numpy() - oxyz).max() < POS_TOL_F64
+    assert np.abs(uv.detach().cpu().numpy() - ouv).max() < 1e-3
+    rs = np.random.RandomState(7)
+    gx = rs.randn(B, 21, 3).astype(np.float32)
+    gu = (rs.randn(B, 21, 2) * 1e-3).astype(np.float32)
+    tgx, tgu = to_dev(cuda_device, gx, gu)
+    ((xyz * tgx).sum() + (uv * tgu).sum()).backward()
+    ora, ooa, obl = fo.fk_backward(*args, gx, gu)
+    for got, want in zip(t[:3], (ora, ooa, obl)):
+        assert rel(got.grad.cpu().numpy(), want) < GRAD_TOL
+    vis = (rs.rand(B, 21, 1) < .8).astype(np.float32)
+    gt = (oxyz + rs.randn(B, 21, 3) * .05).astype(np.float32)
+    tvis, tgt = to_dev(cuda_device, vis, gt)
+    m = pkg.MPJPE()(xyz.detach(), tgt, tvis)
+    assert m.dim() == 0
+    want = fo.mpjpe(xyz.detach().cpu().numpy(), gt, vis)
+    assert abs(float(m) - want) <= 1e-5 * want
+    # xyz-only upstream gradient (uv unused) and uv-only
+    for x in t[:3]:
+        x.grad = None
+    xyz2, uv2, _ = fk(*t)
+    (xyz2 * tgx).sum().backward()
+    ora, ooa, obl = fo.fk_backward(*args, gx, None)
+    for got, want in zip(t[:3], (ora, ooa, obl)):
+        assert rel(got.grad.cpu().numpy(), want) < GRAD_TOL
+    torch.cuda.synchronize()
+
+
+def test_fk_hand_typed_kat(pkg, cuda_device):
+    """KAT-FK-0."""
+    import torch
+
+    oa = torch.zeros(1, 23, device=cuda_device)
+    oa[0, 1] = np.pi / 2
+    K = torch.tensor([[[600., 0, 300], [0, 600., 300], [0, 0, 1]]], device=cuda_device)
+    xyz, uv, _ = pkg.ForwardKinematics(cuda_device, joint_order_switched=True)(
+        torch.tensor([[0, 0, np.pi / 2]], device=cuda_device, dtype=torch.float32), oa,
+        torch.ones(1, 20, device=cuda_device), K, torch.ones(1, 1, device=cuda_device), torch.zeros(1, 3, device=cuda_device))
+    xyz, uv = xyz.cpu().numpy(), uv.cpu().numpy()
+    for k in range(1, 5):
+        assert np.allclose(xyz[0, k], [0, k, 0], atol=1e-6)
+    for f in range(1, 5):
+        for k in range(1, 5):
+            assert np.allclose(xyz[0, 4 * f + k], [0, 0, k], atol=1e-6)
+            assert np.allclose(uv[0, 4 * f + k], [300, 300], atol=1e-3)
+    assert np.allclose(uv[0, 0], [0, 0])
+
+
+def test_projection_and_z0_branch(pkg, cuda_device):
+    g = load_golden("project_uv.npz")
+    xyz, = to_dev(cuda_device, g["xyz"], grad=True)
+    K, gu = to_dev(cuda_device, g["K"], g["g_uv"])
+    uv = pkg.batch_project_xyz_to_uv(xyz, K)
+    got = uv.detach().cpu().numpy()
+    ok = np.abs(g["uv"]) < 1e6
+    assert np.abs(got[ok] - g["uv"][ok]).max() < 2e-3
+    assert np.array_equal(got[0, 0], g["uv"][0, 0])            # (0,0,0) -> 0 / 1e-10 = 0 exactly
+    (uv * gu).sum().backward()
+    fin = np.isfinite(g["g_xyz"]) & (np.abs(g["g_xyz"]) < 1e6)
+    assert rel(xyz.grad.cpu().numpy()[fin], g["g_xyz"][fin]) < GRAD_TOL
+
+
+# ------------------------------------------------------------------------ reductions
+@pytest.mark.parametrize("name", ["reduce_vis80.npz", "reduce_none_visible.npz"])
+def test_reductions_match_reference_golden(pkg, cuda_device, name):
+    import torch
+
+    g = load_golden(name)
+    pre, = to_dev(cuda_device, g["pre"], grad=True)
+    gt, vis = to_dev(cuda_device, g["gt"], g["vis"])
+    m = pkg.MPJPE()(pre, gt, vis)
+    l2 = pkg.L2Loss()(pre, gt, vis)
+    assert float(m) == pytest.approx(float(g["mpjpe"]), rel=1e-5, abs=1e-12)
+    assert float(l2) == pytest.approx(float(g["l2"]), rel=1e-5, abs=1e-12)
+    l2.backward()
+    assert np.abs(pre.grad.cpu().numpy() - g["g_pre"]).max() <= 1e-5 * max(np.abs(g["g_pre"]).max(), 1e-12) + 1e-12
+    # uint8 / bool masks behave like the float ones
+    m2 = pkg.MPJPE()(pre.detach(), gt, vis.bool())
+    assert float(m2) == pytest.approx(float(m), rel=1e-6, abs=1e-12)
+    torch.cuda.synchronize()
+
+
+def test_adam_step_matches_torch(pkg, cuda_device):
+    import torch
+
+    lib = pkg.load_library()
+    torch.manual_seed(0)
+    p = torch.randn(10001, device=cuda_device)
+    ref_p = p.clone().requires_grad_()
+    opt = torch.optim.Adam([ref_p], lr=1e-2)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 6):
+        gr = torch.randn_like(p)
+        ref_p.grad = gr.clone()
+        opt.step()
+        pkg._cabi.check(lib.mb_adam_step(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                         1e-2, 0.9, 0.999, 1e-8, step, pkg._cabi.stream_handle(cuda_device)), "adam")
+    assert float((p - ref_p.detach()).abs().max()) < 1e-6
