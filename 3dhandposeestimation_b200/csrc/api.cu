@@ -14,6 +14,7 @@ void blend_tc_pack(const float* basis, void* host_blob_tc);
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <algorithm>
 namespace mb {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -151,7 +152,7 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
         }
         sc[v] = (uint8_t)cnt;
     }
-    if (nnz > 3200) return MB_E_MODEL;
+    if (nnz > MAX_NNZ) return MB_E_MODEL;
     cptr[0] = 0;
     for (int k = 0; k < NJ; ++k) cptr[k + 1] = cptr[k] + per_bone[k];
     int fill[NJ];
@@ -164,6 +165,71 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
             ++fill[bi];
         }
     H->csc_nnz = nnz;
+
+    // ---- tables of the lane=hand skinning kernels ------------------------------------------
+    int* rptr = reinterpret_cast<int*>(out + L.csr_ptr);
+    float* rw = reinterpret_cast<float*>(out + L.csr_w);
+    uint8_t* rb = reinterpret_cast<uint8_t*>(out + L.csr_b);
+    rptr[0] = 0;
+    for (int v = 0; v < NV; ++v) {
+        int o = rptr[v];
+        for (int s = 0; s < sc[v]; ++s) { rw[o] = sw[v * MAX_INFL + s]; rb[o] = sb[v * MAX_INFL + s]; ++o; }
+        rptr[v + 1] = o;
+    }
+    // Ownership of the per-bone gradient sums: each of the 8 warps owns up to 3 "slots"; a slot is a
+    // bone or one half (even/odd entries) of a bone too long for one warp.  Longest-first greedy.
+    struct Part { int bone, half, len; };
+    std::vector<Part> parts;
+    const int target = (nnz + LBS_WARPS - 1) / LBS_WARPS;
+    for (int k = 0; k < NJ; ++k) {
+        if (per_bone[k] == 0) continue;
+        if (per_bone[k] > target && (int)parts.size() + 2 <= LBS_WARPS * LBS_SLOTS - (NJ - 1 - k)) {
+            parts.push_back({k, 1, (per_bone[k] + 1) / 2});
+            parts.push_back({k, 2, per_bone[k] / 2});
+        } else {
+            parts.push_back({k, 0, per_bone[k]});
+        }
+    }
+    if ((int)parts.size() > LBS_WARPS * LBS_SLOTS) return MB_E_MODEL;
+    std::sort(parts.begin(), parts.end(), [](const Part& a, const Part& b) { return a.len > b.len; });
+    int load[LBS_WARPS] = {0}, used[LBS_WARPS] = {0};
+    int* bslot = reinterpret_cast<int*>(out + L.bslot);          // bone | half << 8
+    for (int i = 0; i < LBS_WARPS * LBS_SLOTS; ++i) bslot[i] = -1;
+    for (const Part& p : parts) {
+        int best = -1;
+        for (int w = 0; w < LBS_WARPS; ++w)
+            if (used[w] < LBS_SLOTS && (best < 0 || load[w] < load[best])) best = w;
+        if (best < 0) return MB_E_MODEL;
+        bslot[best * LBS_SLOTS + used[best]] = p.bone | (p.half << 8);
+        ++used[best];
+        load[best] += p.len;
+    }
+    int* bseg = reinterpret_cast<int*>(out + L.bseg);
+    uint16_t* bidx = reinterpret_cast<uint16_t*>(out + L.bent_idx);
+    float* bw = reinterpret_cast<float*>(out + L.bent_w);
+    int e = 0;
+    for (int w = 0; w < LBS_WARPS; ++w)
+        for (int c = 0; c < LBS_CHUNKS; ++c)
+            for (int s = 0; s < LBS_SLOTS; ++s) {
+                int* seg = bseg + ((w * LBS_CHUNKS + c) * LBS_SLOTS + s) * 2;
+                seg[0] = e;
+                const int code = bslot[w * LBS_SLOTS + s];
+                if (code >= 0) {
+                    const int bone = code & 255, half = code >> 8;
+                    for (int i = cptr[bone]; i < cptr[bone + 1]; ++i) {
+                        const int ord = i - cptr[bone];
+                        if (half == 1 && (ord & 1)) continue;
+                        if (half == 2 && !(ord & 1)) continue;
+                        const int v = cv[i];
+                        if (v / LBS_CV != c) continue;
+                        bidx[e] = (uint16_t)((v - c * LBS_CV) * 3);
+                        bw[e] = cw[i];
+                        ++e;
+                    }
+                }
+                seg[1] = e;
+            }
+    if (e != nnz) return MB_E_MODEL;
     blend_tc_pack(basis, out + L.total);
     return 0;
 }

@@ -119,8 +119,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 // ---------------------------------------------------------------- kernel
-constexpr int TC_THREADS = 256;                   // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-7 epilogue
-constexpr int A_STAGES = 4;
+constexpr int TC_THREADS = 384;                   // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-11 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int A_STAGES = TC_K_CHUNKS;             // one ring slot per K chunk: slot index == chunk index (static descriptors)
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
@@ -128,10 +129,10 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_
 struct TcShared {
     alignas(128) unsigned char b[TC_B_TILE_BYTES];                  // resident basis tile (hi+lo, 5 chunks)
     alignas(128) unsigned char a[A_STAGES][TC_A_STAGE_BYTES];       // feature ring
-    alignas(16) float stage[4][32][33];                             // epilogue transposes
+    alignas(16) float stage[EPI_WARPS][32][33];                     // epilogue transposes
     alignas(8) unsigned long long full[A_STAGES], empty[A_STAGES];
     unsigned long long acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
-    unsigned long long b_full, b_empty;
+    unsigned long long b_full;
     uint32_t tmem_base;
     int abort_flag;
 };
@@ -145,15 +146,19 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
     const float out_scale = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const long long total = (long long)TC_N_TILES * m_tiles;
-    const long long t_begin = total * blockIdx.x / gridDim.x;
-    const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+    // Tile schedule: CTA c owns n-tile (c % 15) for its whole life (its basis slice stays resident in
+    // shared memory) and walks the hand tiles m = c/15, c/15 + G, ... where G is the number of CTAs
+    // on that n-tile.  All 15 groups sweep m upwards at the same pace, so a hand tile's feature rows
+    // are fetched from HBM once and served from L2 to the other 14 groups (round-1 ncu: the n-major
+    // order re-read them from DRAM 15 times).
+    const int n_tile = blockIdx.x % TC_N_TILES;
+    const int m_first = blockIdx.x / TC_N_TILES;
+    const int m_step = ((int)gridDim.x - n_tile + TC_N_TILES - 1) / TC_N_TILES;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(smem_u32(&S.full[s]), 1); mbar_init(smem_u32(&S.empty[s]), 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(smem_u32(&S.acc_full[s]), 1); mbar_init(smem_u32(&S.acc_empty[s]), 4); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(smem_u32(&S.acc_full[s]), 1); mbar_init(smem_u32(&S.acc_empty[s]), EPI_WARPS); }
         mbar_init(smem_u32(&S.b_full), 1);
-        mbar_init(smem_u32(&S.b_empty), 1);
         S.abort_flag = 0;
         fence_barrier_init();
     }
@@ -165,89 +170,76 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
     volatile int* abort_flag = &S.abort_flag;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer: resident B per n-tile, feature chunks through the ring =====
-        uint32_t stage = 0, phase = 0, b_loads = 0;
-        int cur_n = -1;
-        for (long long t = t_begin; t < t_end; ++t) {
-            const int n_tile = (int)(t / m_tiles), m_tile = (int)(t % m_tiles);
-            if (n_tile != cur_n) {
-                if (b_loads > 0 && !mbar_wait(smem_u32(&S.b_empty), (b_loads - 1) & 1, abort_flag)) break;
-                mbar_expect_tx(smem_u32(&S.b_full), TC_B_TILE_BYTES);
-                const unsigned char* src = basis_tc + (size_t)n_tile * TC_B_TILE_BYTES;
-                for (int i = 0; i < TC_B_TILE_BYTES / TC_B_BLOCK_BYTES; ++i)
-                    bulk_g2s(smem_u32(S.b) + i * TC_B_BLOCK_BYTES, src + (size_t)i * TC_B_BLOCK_BYTES, TC_B_BLOCK_BYTES,
-                             smem_u32(&S.b_full));
-                cur_n = n_tile;
-                ++b_loads;
-            }
+        // ===== TMA producer: resident B once, then feature chunks through the ring =====
+        mbar_expect_tx(smem_u32(&S.b_full), TC_B_TILE_BYTES);
+        const unsigned char* src = basis_tc + (size_t)n_tile * TC_B_TILE_BYTES;
+        for (int i = 0; i < TC_B_TILE_BYTES / TC_B_BLOCK_BYTES; ++i)
+            bulk_g2s(smem_u32(S.b) + i * TC_B_BLOCK_BYTES, src + (size_t)i * TC_B_BLOCK_BYTES, TC_B_BLOCK_BYTES, smem_u32(&S.b_full));
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int m_tile = m_first; m_tile < m_tiles && ok; m_tile += m_step) {
             const unsigned char* fsrc = featp + (size_t)m_tile * TC_A_TILE_BYTES;
-            bool ok = true;
+#pragma unroll
             for (int c = 0; c < TC_K_CHUNKS; ++c) {
-                if (!(ok = mbar_wait(smem_u32(&S.empty[stage]), phase ^ 1, abort_flag))) break;
-                mbar_expect_tx(smem_u32(&S.full[stage]), TC_A_STAGE_BYTES);
-                bulk_g2s(smem_u32(S.a[stage]), fsrc + (size_t)c * TC_A_STAGE_BYTES, TC_A_STAGE_BYTES, smem_u32(&S.full[stage]));
-                if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+                if (!(ok = mbar_wait(smem_u32(&S.empty[c]), phase ^ 1, abort_flag))) break;
+                mbar_expect_tx(smem_u32(&S.full[c]), TC_A_STAGE_BYTES);
+                bulk_g2s(smem_u32(S.a[c]), fsrc + (size_t)c * TC_A_STAGE_BYTES, TC_A_STAGE_BYTES, smem_u32(&S.full[c]));
             }
-            if (!ok) break;
+            phase ^= 1;
         }
     } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, b_seen = 0;
-        int cur_n = -1;
-        bool ok = true;
-        for (long long t = t_begin; t < t_end && ok; ++t) {
-            const int n_tile = (int)(t / m_tiles);
-            if (n_tile != cur_n) {
-                if (!(ok = mbar_wait(smem_u32(&S.b_full), b_seen & 1, abort_flag))) break;
-                ++b_seen;
-                cur_n = n_tile;
-            }
+        // ===== MMA issuer: 30 (or 10) fully unrolled tcgen05.mma per tile, descriptors are base + constant =====
+        uint32_t phase = 0, acc = 0, acc_phase = 0;
+        bool ok = mbar_wait(smem_u32(&S.b_full), 0, abort_flag);
+        const uint64_t a_base = umma_desc(smem_u32(S.a[0]), TC_LBO, TC_SBO);
+        const uint64_t b_base = umma_desc(smem_u32(S.b), TC_LBO, TC_SBO);
+        for (int m_tile = m_first; m_tile < m_tiles && ok; m_tile += m_step) {
             if (!(ok = mbar_wait(smem_u32(&S.acc_empty[acc]), acc_phase ^ 1, abort_flag))) break;
             tc_fence_after();
             const uint32_t d_tmem = tmem + acc * TC_N;
-            uint32_t accumulate = 0;
-            for (int c = 0; c < TC_K_CHUNKS && ok; ++c) {
-                if (!(ok = mbar_wait(smem_u32(&S.full[stage]), phase, abort_flag))) break;
+#pragma unroll
+            for (int c = 0; c < TC_K_CHUNKS; ++c) {
+                if (!(ok = mbar_wait(smem_u32(&S.full[c]), phase, abort_flag))) break;
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(S.a[stage]), a_lo = a_hi + TC_A_BLOCK_BYTES;
-                const uint32_t b_hi = smem_u32(S.b) + (uint32_t)(c * 2) * TC_B_BLOCK_BYTES, b_lo = b_hi + TC_B_BLOCK_BYTES;
 #pragma unroll
                 for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
-                    const uint32_t ko = (uint32_t)j * 2 * TC_LBO;
-                    umma_f16(d_tmem, umma_desc(a_hi + ko, TC_LBO, TC_SBO), umma_desc(b_hi + ko, TC_LBO, TC_SBO), IDESC, accumulate);
-                    accumulate = 1;
+                    const uint64_t a_hi = a_base + (uint64_t)((c * TC_A_STAGE_BYTES + j * 2 * (int)TC_LBO) >> 4);
+                    const uint64_t a_lo = a_hi + (uint64_t)(TC_A_BLOCK_BYTES >> 4);
+                    const uint64_t b_hi = b_base + (uint64_t)((c * 2 * TC_B_BLOCK_BYTES + j * 2 * (int)TC_LBO) >> 4);
+                    const uint64_t b_lo = b_hi + (uint64_t)(TC_B_BLOCK_BYTES >> 4);
+                    umma_f16(d_tmem, a_hi, b_hi, IDESC, (c | j) ? 1u : 0u);
                     if (products == 3) {
-                        umma_f16(d_tmem, umma_desc(a_lo + ko, TC_LBO, TC_SBO), umma_desc(b_hi + ko, TC_LBO, TC_SBO), IDESC, 1);
-                        umma_f16(d_tmem, umma_desc(a_hi + ko, TC_LBO, TC_SBO), umma_desc(b_lo + ko, TC_LBO, TC_SBO), IDESC, 1);
+                        umma_f16(d_tmem, a_lo, b_hi, IDESC, 1);
+                        umma_f16(d_tmem, a_hi, b_lo, IDESC, 1);
                     }
                 }
-                tc_commit(smem_u32(&S.empty[stage]));          // frees the feature stage when these MMAs retire
-                if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+                tc_commit(smem_u32(&S.empty[c]));              // frees the feature slot when these MMAs retire
             }
             if (!ok) break;
             tc_commit(smem_u32(&S.acc_full[acc]));             // accumulator ready for the epilogue
-            const long long tn = t + 1;
-            if (tn >= t_end || (int)(tn / m_tiles) != cur_n) tc_commit(smem_u32(&S.b_empty));   // last use of this B
+            phase ^= 1;
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced v_posed rows =====
-        const int q = warp - 4;                                 // TMEM lane quarter of this warp (warp % 4)
-        float (*buf)[33] = S.stage[q];
+        // warp % 4 selects the TMEM lane quarter; warps 4-7 take column chunks 0-2, warps 8-11 chunks 3-4
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int j_begin = half == 0 ? 0 : 3, j_end = half == 0 ? 3 : TC_N / 32;
+        float (*buf)[33] = S.stage[warp - 4];
         uint32_t acc = 0, acc_phase = 0;
         bool ok = true;
-        for (long long t = t_begin; t < t_end && ok; ++t) {
-            const int n_tile = (int)(t / m_tiles), m_tile = (int)(t % m_tiles);
+        const int n0 = n_tile * TC_N;
+        for (int m_tile = m_first; m_tile < m_tiles && ok; m_tile += m_step) {
             ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&S.acc_full[acc]), acc_phase, abort_flag));
             if (!ok) break;
             tc_fence_after();
             const int row0 = m_tile * TC_M + q * 32;
-            const int n0 = n_tile * TC_N;
 #pragma unroll 1
-            for (int j = 0; j < TC_N / 32; ++j) {
+            for (int j = j_begin; j < j_end; ++j) {
                 float v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * TC_N + j * 32, v);
-                if (j == TC_N / 32 - 1) {                       // accumulator drained: hand it back to the MMA warp
+                if (j == j_end - 1) {                           // this warp's share is drained: release the accumulator
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty[acc]));
@@ -258,11 +250,11 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
                 const int col = n0 + j * 32 + lane;
                 const float tv = col < NVC ? tmpl[col] : 0.f;
                 if (col < VP_PITCH) {
+                    float* dst = v_posed + (size_t)row0 * VP_PITCH + col;
+                    const int nrow = B - row0 < 32 ? B - row0 : 32;
 #pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = row0 + rr;
-                        if (row < B) v_posed[(size_t)row * VP_PITCH + col] = fmaf(buf[rr][lane], out_scale, tv);
-                    }
+                    for (int rr = 0; rr < 32; ++rr)
+                        if (rr < nrow) dst[(size_t)rr * VP_PITCH] = fmaf(buf[rr][lane], out_scale, tv);
                 }
                 __syncwarp();
             }
@@ -322,7 +314,7 @@ int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float*
     const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
     const int m_tiles = (B + TC_M - 1) / TC_M;
     const long long total = (long long)TC_N_TILES * m_tiles;
-    const int grid = (int)(total < NUM_SMS ? total : NUM_SMS);
+    const int grid = (int)(total < NUM_SMS ? total : NUM_SMS);      // >= 15: every n-tile has at least one CTA
     const float* tmpl = blob_ptr<float>(blob, L.basis) + (size_t)FEAT_ONE * VP_PITCH;
     blend_tc_forward_kernel<<<grid, TC_THREADS, smem, s>>>(reinterpret_cast<const TcBlobHeader*>(tc),
                                                            tc + align256(sizeof(TcBlobHeader)), tmpl, featp, v_posed, B, m_tiles,

@@ -21,6 +21,12 @@ constexpr int FEAT_ONE = 145;
 constexpr int MAX_INFL = 8;
 constexpr int BONE_F = 12;        // 3x4 [R|t] per bone
 constexpr int NUM_SMS = 148;
+constexpr int MAX_NNZ = 3200;      // total skinning weights supported
+constexpr int LBS_WARPS = 8;       // warps per CTA of the skinning kernels
+constexpr int LBS_CV = 64;         // vertices per chunk
+constexpr int LBS_CF = LBS_CV * 3; // floats per chunk row
+constexpr int LBS_CHUNKS = (NV + LBS_CV - 1) / LBS_CV;   // 13
+constexpr int LBS_SLOTS = 3;       // bones (or bone halves) owned by one warp in the backward reduction
 
 // Device blob layout (byte offsets, every section 256-byte aligned).
 struct BlobLayout {
@@ -37,6 +43,14 @@ struct BlobLayout {
     size_t csc_ptr;     // int32 [17]      bone -> range in csc_v / csc_w
     size_t csc_v;       // int32 [778*8]   vertex ids grouped by bone
     size_t csc_w;       // float [778*8]
+    // tables of the lane=hand skinning kernels (mano_lbs.cu)
+    size_t csr_ptr;     // int32 [779]     vertex -> range in csr_w / csr_b
+    size_t csr_w;       // float [MAX_NNZ]
+    size_t csr_b;       // uint8 [MAX_NNZ]
+    size_t bseg;        // int32 [LBS_WARPS][LBS_CHUNKS][LBS_SLOTS][2]  entry ranges per (warp, vertex chunk, owned slot)
+    size_t bent_idx;    // uint16 [MAX_NNZ] float index of the entry's vertex inside its chunk
+    size_t bent_w;      // float  [MAX_NNZ]
+    size_t bslot;       // int32 [LBS_WARPS][LBS_SLOTS] owned bone id (-1 = none)
     size_t total;
 };
 
@@ -71,6 +85,13 @@ __host__ __device__ inline BlobLayout blob_layout() {
     L.csc_ptr = o;   o = align256(o + sizeof(int32_t) * (NJ + 1));
     L.csc_v = o;     o = align256(o + sizeof(int32_t) * NV * MAX_INFL);
     L.csc_w = o;     o = align256(o + sizeof(float) * NV * MAX_INFL);
+    L.csr_ptr = o;   o = align256(o + sizeof(int32_t) * (NV + 1));
+    L.csr_w = o;     o = align256(o + sizeof(float) * MAX_NNZ);
+    L.csr_b = o;     o = align256(o + MAX_NNZ);
+    L.bseg = o;      o = align256(o + sizeof(int32_t) * LBS_WARPS * LBS_CHUNKS * LBS_SLOTS * 2);
+    L.bent_idx = o;  o = align256(o + sizeof(uint16_t) * MAX_NNZ);
+    L.bent_w = o;    o = align256(o + sizeof(float) * MAX_NNZ);
+    L.bslot = o;     o = align256(o + sizeof(int32_t) * LBS_WARPS * LBS_SLOTS);
     L.total = o;
     return L;
 }

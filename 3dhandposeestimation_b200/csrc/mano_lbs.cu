@@ -4,238 +4,344 @@
 // fingertip vertices become joints 4,8,12,16,20) and :188,:204-205 (global rotation — already
 // folded into the bone transforms by the pose stage, so it costs nothing here).
 //
-// The stage is HBM-bound: per hand it reads v_posed (9.3 KB) + 16 bone transforms (768 B) and
-// writes verts (9.3 KB) + 5 tip joints.  Rows are staged through shared memory so that every
-// global access is a coalesced 16-byte vector: hands are processed in PAIRS because one hand's
-// 2334 floats are only 8-byte aligned in the [B][778][3] output, two hands are 16-byte aligned.
-// Skinning weights live in shared memory slot-major ([slot][vertex]) so a warp's reads are
-// conflict-free; each thread owns fixed vertices (tid, tid+256, ...).
+// Mapping (round-1 ncu: the vertex-per-lane version spent 5.6 k warp-instructions per hand on
+// divergent per-vertex bone loops): LANE = HAND.  A CTA owns a group of 32 hands and sweeps the
+// 778 vertices in 13 chunks of 64.  A chunk is staged in shared memory TRANSPOSED — tile[f][hand]
+// with pitch 33 — so that
+//   * global traffic is coalesced: each hand row contributes contiguous 768-byte segments, read as
+//     16-byte (v_posed) / 8-byte (g_verts, whose rows are only 8-byte aligned) vectors and written
+//     back as 16-/8-byte vectors;
+//   * every shared-memory access of the compute phase is conflict-free (lane = hand = bank);
+//   * the skinning weights / bone ids of a vertex are WARP-UNIFORM: no divergence, weight loads
+//     are broadcasts, and the per-vertex bone loop costs exactly its nnz.
+// The 16 bone transforms of the 32 hands sit in shared memory with pitch 196 floats (49 x 16 B,
+// odd) so the three float4 rows of a bone are conflict-free LDS.128.
+// Loads of chunk i+1 are issued into registers before chunk i is computed (software pipeline).
+//
+// Backward:  dv_posed_v = sum_k w_vk R'_k^T g_v  and
+// dA'_k = sum_v w_vk g_v (x) [v_posed_v ; 1].  The second is a reduction over vertices: each warp
+// OWNS up to three bones (or halves of long bones; host-side greedy balance) and keeps their 3x4
+// accumulators in registers across the whole vertex sweep — no atomics, no shuffles.
 #include "common.cuh"
 
 namespace mb {
 namespace {
 
-constexpr int LBS_THREADS = 256;
-constexpr int VPAD = 784;                       // 778 rounded up (slot-major weight rows)
-constexpr int ROW4 = VP_PITCH / 4;              // 584 float4 per padded row
-constexpr int MAX_CSC = 3200;                   // >= total skin nnz supported by the backward kernel
+constexpr int LBS_THREADS = LBS_WARPS * 32;     // 256
+constexpr int TP = 33;                          // transposed tile pitch (floats)
+constexpr int BONE_PITCH = 196;                 // floats per hand in the bone tile (49 float4, odd)
+constexpr int HG = 32;                          // hands per group
 __constant__ int c_tip_vert[5] = {333, 444, 672, 555, 745};
 __constant__ int c_tip_slot[5] = {4, 8, 12, 16, 20};
 
-struct SkinShared {
-    float w[MAX_INFL][VPAD];
-    uint8_t b[MAX_INFL][VPAD];
-    uint8_t cnt[VPAD];
-};
-
-__device__ __forceinline__ void stage_skin(SkinShared& S, const void* blob) {
-    const BlobLayout L = blob_layout();
-    const float* sw = blob_ptr<float>(blob, L.skin_w);
-    const uint8_t* sb = blob_ptr<uint8_t>(blob, L.skin_b);
-    const uint8_t* sc = blob_ptr<uint8_t>(blob, L.skin_cnt);
-    for (int i = threadIdx.x; i < NV * MAX_INFL; i += blockDim.x) {
-        int v = i / MAX_INFL, s = i % MAX_INFL;
-        S.w[s][v] = sw[i];
-        S.b[s][v] = sb[i];
-    }
-    for (int i = threadIdx.x; i < NV; i += blockDim.x) S.cnt[i] = sc[i];
-}
-
-__device__ __forceinline__ float4 ld_stream(const float4* p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-// same without .nc: for rows that this kernel overwrites later (dv_posed aliases v_posed)
-__device__ __forceinline__ float4 ld_stream_rw(const float4* p) {
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
     float4 r;
     asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
     return r;
 }
-__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+__device__ __forceinline__ float2 ld_stream2(const float* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_stream2(float* p, const float2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+struct SkinCsr {            // per-vertex skinning lists, shared by forward and backward
+    int ptr[NV + 1];
+    float w[MAX_NNZ];
+    uint8_t b[MAX_NNZ];
+};
+
+__device__ __forceinline__ void stage_csr(SkinCsr& S, const void* blob) {
+    const BlobLayout L = blob_layout();
+    const int* p = blob_ptr<int>(blob, L.csr_ptr);
+    const float* w = blob_ptr<float>(blob, L.csr_w);
+    const uint8_t* b = blob_ptr<uint8_t>(blob, L.csr_b);
+    for (int i = threadIdx.x; i <= NV; i += blockDim.x) S.ptr[i] = p[i];
+    const int nnz = p[NV];
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) { S.w[i] = w[i]; S.b[i] = b[i]; }
+}
+
+// coalesced copy of the 16 bone transforms of `nh` hands into the padded bone tile
+__device__ __forceinline__ void stage_bones(float* s_bone, const float* __restrict__ bone, long long h0, int nh) {
+    const float4* src = reinterpret_cast<const float4*>(bone + h0 * (NJ * BONE_F));
+    for (int i = threadIdx.x; i < nh * (NJ * BONE_F / 4); i += blockDim.x) {
+        const int h = i / (NJ * BONE_F / 4), q = i - h * (NJ * BONE_F / 4);
+        reinterpret_cast<float4*>(s_bone + h * BONE_PITCH)[q] = src[i];
+    }
+}
+
+// Register-staged chunk I/O.  A chunk row holds PPR pieces of VEC floats (16- or 8-byte vectors).
+// One warp instruction covers LH rows x LQ pieces with LQ * VEC * 4 = 128 contiguous bytes per row:
+//   global side : LH fully used 128-byte lines per request;
+//   shared side : tile[(q*VEC + e) * 33 + h] -> bank (VEC*q + e + h) mod 32, distinct for the LQ x LH
+//                 lanes, so the transposing STS/LDS are conflict-free.
+// The (row, piece) of every thread and iteration is a compile-time function of (warp, lane, i).
+template <int VEC, int PPR>
+struct ChunkMap {
+    static constexpr int LQ = 32 / VEC;                 // pieces per row per instruction (8 or 16)
+    static constexpr int LH = 32 / LQ;                  // rows per instruction (4 or 2)
+    static constexpr int QB = (PPR + LQ - 1) / LQ;      // piece blocks per row
+    static constexpr int HB = HG / LH;                  // row blocks
+    static constexpr int ITERS = (QB * HB + LBS_WARPS - 1) / LBS_WARPS;
+    __device__ __forceinline__ static bool map(int i, int nh, int& h, int& q) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int t = warp + LBS_WARPS * i;
+        q = (t % QB) * LQ + (lane & (LQ - 1));
+        h = (t / QB) * LH + (lane / LQ);
+        return t < QB * HB && q < PPR && h < nh;
+    }
+};
+template <int VEC, int ITERS>
+struct ChunkRegs { float v[ITERS][VEC]; };
+
+template <int VEC, int PPR, int MAXI>
+__device__ __forceinline__ void chunk_load(ChunkRegs<VEC, MAXI>& R, const float* __restrict__ base, long long pitch,
+                                           long long h0, int nh, int f0) {
+    using M = ChunkMap<VEC, PPR>;
+#pragma unroll
+    for (int i = 0; i < M::ITERS; ++i) {
+        int h, q;
+        if (M::map(i, nh, h, q)) {
+            const float* src = base + (h0 + h) * pitch + f0 + q * VEC;
+            if (VEC == 4) { float4 t = ld_stream4(src); R.v[i][0] = t.x; R.v[i][1] = t.y; R.v[i][2] = t.z; R.v[i][3] = t.w; }
+            else          { float2 t = ld_stream2(src); R.v[i][0] = t.x; R.v[i][1] = t.y; }
+        }
+    }
+}
+template <int VEC, int PPR, int MAXI>
+__device__ __forceinline__ void chunk_to_tile(const ChunkRegs<VEC, MAXI>& R, float* tile, int nh) {
+    using M = ChunkMap<VEC, PPR>;
+#pragma unroll
+    for (int i = 0; i < M::ITERS; ++i) {
+        int h, q;
+        if (M::map(i, nh, h, q)) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) tile[(q * VEC + e) * TP + h] = R.v[i][e];
+        }
+    }
+}
+// coalesced store of a transposed tile back to rows (PPR pieces of VEC floats per row)
+template <int VEC, int PPR>
+__device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ base, long long pitch, long long h0,
+                                           int nh, int f0) {
+    using M = ChunkMap<VEC, PPR>;
+#pragma unroll
+    for (int i = 0; i < M::ITERS; ++i) {
+        int h, q;
+        if (M::map(i, nh, h, q)) {
+            float* dst = base + (h0 + h) * pitch + f0 + q * VEC;
+            if (VEC == 4) st_stream4(dst, make_float4(tile[(q * 4) * TP + h], tile[(q * 4 + 1) * TP + h],
+                                                      tile[(q * 4 + 2) * TP + h], tile[(q * 4 + 3) * TP + h]));
+            else          st_stream2(dst, make_float2(tile[(q * 2) * TP + h], tile[(q * 2 + 1) * TP + h]));
+        }
+    }
+}
+
+constexpr int TAIL_V = NV - (LBS_CHUNKS - 1) * LBS_CV;       // 10 vertices in the last chunk
+constexpr int TAIL_F4 = VP_PITCH - (LBS_CHUNKS - 1) * LBS_CF; // 32 floats of the padded v_posed row
+constexpr int TAIL_F2 = TAIL_V * 3;                          // 30 floats of the dense rows
+constexpr int I4 = ChunkMap<4, LBS_CF / 4>::ITERS;           // 6
+constexpr int I2 = ChunkMap<2, LBS_CF / 2>::ITERS;           // 12
 
 // ------------------------------------------------------------------ forward
+struct FwdShared {
+    SkinCsr csr;
+    alignas(16) float bone[HG * BONE_PITCH];
+    alignas(16) float tile[2][LBS_CF * TP];
+};
+
 __global__ void __launch_bounds__(LBS_THREADS)
 lbs_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed, int pitch,
                    const float* __restrict__ bone, int B, float* __restrict__ verts, float* __restrict__ joints) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkinShared& S = *reinterpret_cast<SkinShared*>(smem_raw);
-    float* s_vp = reinterpret_cast<float*>(smem_raw + ((sizeof(SkinShared) + 15) & ~size_t(15)));  // [2][VP_PITCH]
-    float* s_bone = s_vp + 2 * VP_PITCH;                                                            // [2][192]
-    stage_skin(S, blob);
-    const int tid = threadIdx.x;
-    const int npairs = (B + 1) / 2;
-    const int pitch4 = pitch / 4;
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        const long long h0 = 2LL * pair;
-        const int nh = (B - h0) >= 2 ? 2 : 1;
-        __syncthreads();                          // previous iteration's readers are done (also covers stage_skin)
-        for (int i = tid; i < nh * ROW4; i += LBS_THREADS) {
-            int hh = i / ROW4, q = i - hh * ROW4;
-            float4 v = (q < pitch4) ? ld_stream(reinterpret_cast<const float4*>(v_posed + (h0 + hh) * pitch) + q)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            reinterpret_cast<float4*>(s_vp)[hh * ROW4 + q] = v;
-        }
-        for (int i = tid; i < nh * (NJ * BONE_F / 4); i += LBS_THREADS)
-            reinterpret_cast<float4*>(s_bone)[i] = reinterpret_cast<const float4*>(bone + h0 * (NJ * BONE_F))[i];
-        __syncthreads();
-        for (int hh = 0; hh < nh; ++hh) {
-            float* vp = s_vp + hh * VP_PITCH;
-            const float* A0 = s_bone + hh * (NJ * BONE_F);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int v = tid + r * LBS_THREADS;
-                if (v < NV) {
-                    const float x = vp[v * 3], y = vp[v * 3 + 1], z = vp[v * 3 + 2];
-                    float ox = 0.f, oy = 0.f, oz = 0.f;
-                    const int cnt = S.cnt[v];
-                    for (int s = 0; s < cnt; ++s) {
-                        const float w = S.w[s][v];
-                        const float4* A = reinterpret_cast<const float4*>(A0 + S.b[s][v] * BONE_F);
-                        const float4 r0 = A[0], r1 = A[1], r2 = A[2];
-                        ox = fmaf(w, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), ox);
-                        oy = fmaf(w, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), oy);
-                        oz = fmaf(w, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), oz);
-                    }
-                    vp[v * 3] = ox; vp[v * 3 + 1] = oy; vp[v * 3 + 2] = oz;   // in place: this thread owns vertex v
+    FwdShared& S = *reinterpret_cast<FwdShared*>(smem_raw);
+    stage_csr(S.csr, blob);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = (B + HG - 1) / HG;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long h0 = (long long)grp * HG;
+        const int nh = (B - h0) < HG ? (int)(B - h0) : HG;
+        __syncthreads();                                   // previous group fully stored; csr staged
+        stage_bones(S.bone, bone, h0, nh);
+        ChunkRegs<4, I4> regs;
+        chunk_load<4, LBS_CF / 4, I4>(regs, v_posed, pitch, h0, nh, 0);
+        for (int c = 0; c < LBS_CHUNKS; ++c) {
+            float* tile = S.tile[c & 1];
+            const int f0 = c * LBS_CF;
+            const bool last = (c == LBS_CHUNKS - 1);
+            const int nv = last ? TAIL_V : LBS_CV;
+            if (!last) chunk_to_tile<4, LBS_CF / 4, I4>(regs, tile, nh);
+            else       chunk_to_tile<4, TAIL_F4 / 4, I4>(regs, tile, nh);
+            if (c + 2 < LBS_CHUNKS)       chunk_load<4, LBS_CF / 4, I4>(regs, v_posed, pitch, h0, nh, f0 + LBS_CF);
+            else if (c + 2 == LBS_CHUNKS) chunk_load<4, TAIL_F4 / 4, I4>(regs, v_posed, pitch, h0, nh, f0 + LBS_CF);
+            __syncthreads();                               // tile (and, for c == 0, bones) visible
+            const float* A0 = S.bone + lane * BONE_PITCH;
+            for (int vl = warp; vl < nv; vl += LBS_WARPS) {
+                const int v = c * LBS_CV + vl;
+                const float x = tile[(vl * 3) * TP + lane], y = tile[(vl * 3 + 1) * TP + lane], z = tile[(vl * 3 + 2) * TP + lane];
+                float ox = 0.f, oy = 0.f, oz = 0.f;
+                const int e1 = S.csr.ptr[v + 1];
+                for (int e = S.csr.ptr[v]; e < e1; ++e) {
+                    const float w = S.csr.w[e];
+                    const float4* A = reinterpret_cast<const float4*>(A0 + S.csr.b[e] * BONE_F);
+                    const float4 r0 = A[0], r1 = A[1], r2 = A[2];
+                    ox = fmaf(w, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), ox);
+                    oy = fmaf(w, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), oy);
+                    oz = fmaf(w, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), oz);
                 }
+                tile[(vl * 3) * TP + lane] = ox; tile[(vl * 3 + 1) * TP + lane] = oy; tile[(vl * 3 + 2) * TP + lane] = oz;
             }
-        }
-        __syncthreads();
-        // coalesced float4 stores of the pair's nh*2334 contiguous output floats
-        float* out = verts + h0 * NVC;
-        const int n = nh * NVC, nq = n >> 2;
-        for (int q = tid; q < nq; q += LBS_THREADS) {
-            float4 v;
-            int e = q * 4;
-            int a0 = e < NVC ? e : e + (VP_PITCH - NVC);            ++e;
-            int a1 = e < NVC ? e : e + (VP_PITCH - NVC);            ++e;
-            int a2 = e < NVC ? e : e + (VP_PITCH - NVC);            ++e;
-            int a3 = e < NVC ? e : e + (VP_PITCH - NVC);
-            v.x = s_vp[a0]; v.y = s_vp[a1]; v.z = s_vp[a2]; v.w = s_vp[a3];
-            st_stream(reinterpret_cast<float4*>(out) + q, v);
-        }
-        if (tid < (n & 3)) out[nq * 4 + tid] = s_vp[nq * 4 + tid];      // nh == 1: two tail floats (< NVC)
-        if (joints != nullptr && tid < nh * 15) {
-            int hh = tid / 15, tc = tid % 15;
-            joints[(h0 + hh) * (NOUTJ * 3) + c_tip_slot[tc / 3] * 3 + tc % 3] =
-                s_vp[hh * VP_PITCH + c_tip_vert[tc / 3] * 3 + tc % 3];
+            __syncthreads();                               // results complete
+            if (!last) tile_store<2, LBS_CF / 2>(tile, verts, NVC, h0, nh, f0);
+            else       tile_store<2, TAIL_F2 / 2>(tile, verts, NVC, h0, nh, f0);
+            if (joints != nullptr && warp < 5 && c_tip_vert[warp] / LBS_CV == c && lane < nh) {
+                const int vl = c_tip_vert[warp] - c * LBS_CV;
+                float* o = joints + (h0 + lane) * (NOUTJ * 3) + c_tip_slot[warp] * 3;
+                o[0] = tile[(vl * 3) * TP + lane]; o[1] = tile[(vl * 3 + 1) * TP + lane]; o[2] = tile[(vl * 3 + 2) * TP + lane];
+            }
+            // tile (c & 1) is rewritten at chunk c + 2, after the two barriers of chunk c + 1
         }
     }
 }
 
 // ----------------------------------------------------------------- backward
-// dv_posed_v = sum_k w_vk R'_k^T g_v ;  dA'_k = sum_v w_vk g_v (x) [v_posed_v ; 1]   (A.2 steps 1-2)
-struct CscShared {
-    int ptr[NJ + 1];
-    int v[MAX_CSC];
-    float w[MAX_CSC];
+struct BwdShared {
+    SkinCsr csr;
+    int seg[LBS_WARPS][LBS_CHUNKS][LBS_SLOTS][2];
+    int slot[LBS_WARPS][LBS_SLOTS];
+    unsigned short ent_idx[MAX_NNZ];
+    float ent_w[MAX_NNZ];
+    alignas(16) float bone[HG * BONE_PITCH];
+    alignas(16) float tile_g[2][LBS_CF * TP];
+    alignas(16) float tile_v[2][LBS_CF * TP];
+    alignas(16) float tile_o[LBS_CF * TP];          // dv chunk
 };
+static_assert(sizeof(float) * LBS_WARPS * LBS_SLOTS * BONE_F * (HG + 1) <= sizeof(float) * 2 * LBS_CF * TP,
+              "per-slot partial sums are staged in the (idle) g tiles at group end");
 
 __global__ void __launch_bounds__(LBS_THREADS)
 lbs_backward_kernel(const void* __restrict__ blob, const float* v_posed, int pitch,
                     const float* __restrict__ bone, const float* __restrict__ g_verts,
                     const float* __restrict__ g_joints, int B,
-                    float* dv_posed, float* __restrict__ dbone) {   // dv_posed may alias v_posed (row-wise read-then-write)
+                    float* dv_posed, float* __restrict__ dbone) {   // dv_posed may alias v_posed (chunk read before write)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SkinShared& S = *reinterpret_cast<SkinShared*>(smem_raw);
-    size_t off = (sizeof(SkinShared) + 15) & ~size_t(15);
-    CscShared& C = *reinterpret_cast<CscShared*>(smem_raw + off);
-    off = (off + sizeof(CscShared) + 15) & ~size_t(15);
-    float* s_vp = reinterpret_cast<float*>(smem_raw + off);     // [VP_PITCH]
-    float* s_g = s_vp + VP_PITCH;                               // [VP_PITCH]
-    float* s_dv = s_g + VP_PITCH;                               // [VP_PITCH]
-    float* s_bone = s_dv + VP_PITCH;                            // [192]
-    stage_skin(S, blob);
+    BwdShared& S = *reinterpret_cast<BwdShared*>(smem_raw);
+    stage_csr(S.csr, blob);
     {
         const BlobLayout L = blob_layout();
-        const int* cp = blob_ptr<int>(blob, L.csc_ptr);
-        const int* cv = blob_ptr<int>(blob, L.csc_v);
-        const float* cw = blob_ptr<float>(blob, L.csc_w);
-        for (int i = threadIdx.x; i <= NJ; i += blockDim.x) C.ptr[i] = cp[i];
-        const int nnz = cp[NJ];
-        for (int i = threadIdx.x; i < nnz && i < MAX_CSC; i += blockDim.x) { C.v[i] = cv[i]; C.w[i] = cw[i]; }
+        const int* seg = blob_ptr<int>(blob, L.bseg);
+        const int* slot = blob_ptr<int>(blob, L.bslot);
+        const unsigned short* ei = blob_ptr<unsigned short>(blob, L.bent_idx);
+        const float* ew = blob_ptr<float>(blob, L.bent_w);
+        for (int i = threadIdx.x; i < LBS_WARPS * LBS_CHUNKS * LBS_SLOTS * 2; i += blockDim.x) (&S.seg[0][0][0][0])[i] = seg[i];
+        for (int i = threadIdx.x; i < LBS_WARPS * LBS_SLOTS; i += blockDim.x) (&S.slot[0][0])[i] = slot[i];
+        const int nnz = blob_ptr<int>(blob, L.csr_ptr)[NV];
+        for (int i = threadIdx.x; i < nnz; i += blockDim.x) { S.ent_idx[i] = ei[i]; S.ent_w[i] = ew[i]; }
     }
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pitch4 = pitch / 4;
-    for (long long hand = blockIdx.x; hand < B; hand += gridDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = (B + HG - 1) / HG;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long h0 = (long long)grp * HG;
+        const int nh = (B - h0) < HG ? (int)(B - h0) : HG;
         __syncthreads();
-        for (int q = tid; q < ROW4; q += LBS_THREADS)
-            reinterpret_cast<float4*>(s_vp)[q] = (q < pitch4)
-                ? ld_stream_rw(reinterpret_cast<const float4*>(v_posed + hand * pitch) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        {   // g_verts rows are 8-byte aligned: float2 loads
-            const float2* g2 = reinterpret_cast<const float2*>(g_verts + hand * NVC);
-            for (int q = tid; q < NVC / 2; q += LBS_THREADS) reinterpret_cast<float2*>(s_g)[q] = g2[q];
-        }
-        if (tid < NJ * BONE_F / 4)
-            reinterpret_cast<float4*>(s_bone)[tid] = reinterpret_cast<const float4*>(bone + hand * (NJ * BONE_F))[tid];
-        __syncthreads();
-        if (tid < 15)   // fingertip joints are vertices: their upstream gradient joins g_verts (A.2 step 1)
-            s_g[c_tip_vert[tid / 3] * 3 + tid % 3] += g_joints[hand * (NOUTJ * 3) + c_tip_slot[tid / 3] * 3 + tid % 3];
-        __syncthreads();
-        // (a) per-vertex gather: dv = sum_s w R'^T g
+        stage_bones(S.bone, bone, h0, nh);
+        float acc[LBS_SLOTS][BONE_F];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int v = tid + r * LBS_THREADS;
-            if (v < NV) {
-                const float gx = s_g[v * 3], gy = s_g[v * 3 + 1], gz = s_g[v * 3 + 2];
+        for (int s = 0; s < LBS_SLOTS; ++s)
+#pragma unroll
+            for (int e = 0; e < BONE_F; ++e) acc[s][e] = 0.f;
+        ChunkRegs<4, I4> rv;
+        ChunkRegs<2, I2> rg;
+        chunk_load<4, LBS_CF / 4, I4>(rv, v_posed, pitch, h0, nh, 0);
+        chunk_load<2, LBS_CF / 2, I2>(rg, g_verts, NVC, h0, nh, 0);
+        for (int c = 0; c < LBS_CHUNKS; ++c) {
+            float* tg = S.tile_g[c & 1];
+            float* tv = S.tile_v[c & 1];
+            const int f0 = c * LBS_CF;
+            const bool last = (c == LBS_CHUNKS - 1);
+            const int nv = last ? TAIL_V : LBS_CV;
+            if (!last) { chunk_to_tile<4, LBS_CF / 4, I4>(rv, tv, nh); chunk_to_tile<2, LBS_CF / 2, I2>(rg, tg, nh); }
+            else       { chunk_to_tile<4, TAIL_F4 / 4, I4>(rv, tv, nh); chunk_to_tile<2, TAIL_F2 / 2, I2>(rg, tg, nh); }
+            __syncthreads();                               // tiles of chunk c complete (and dv of chunk c-1 stored)
+            // fingertip joints are vertices: their upstream gradient joins g_verts (A.2 step 1)
+            if (warp < 5 && c_tip_vert[warp] / LBS_CV == c && lane < nh) {
+                const int vl = c_tip_vert[warp] - c * LBS_CV;
+                const float* gj = g_joints + (h0 + lane) * (NOUTJ * 3) + c_tip_slot[warp] * 3;
+                tg[(vl * 3) * TP + lane] += gj[0]; tg[(vl * 3 + 1) * TP + lane] += gj[1]; tg[(vl * 3 + 2) * TP + lane] += gj[2];
+            }
+            // prefetch chunk c+1 into registers (its v_posed floats are read before dv chunk c+1 overwrites them)
+            if (c + 2 < LBS_CHUNKS) {
+                chunk_load<4, LBS_CF / 4, I4>(rv, v_posed, pitch, h0, nh, f0 + LBS_CF);
+                chunk_load<2, LBS_CF / 2, I2>(rg, g_verts, NVC, h0, nh, f0 + LBS_CF);
+            } else if (c + 2 == LBS_CHUNKS) {
+                chunk_load<4, TAIL_F4 / 4, I4>(rv, v_posed, pitch, h0, nh, f0 + LBS_CF);
+                chunk_load<2, TAIL_F2 / 2, I2>(rg, g_verts, NVC, h0, nh, f0 + LBS_CF);
+            }
+            __syncthreads();                               // tip fix-up visible
+            // (a) dv = sum_s w R'^T g  for this warp's vertices of the chunk
+            const float* A0 = S.bone + lane * BONE_PITCH;
+            for (int vl = warp; vl < nv; vl += LBS_WARPS) {
+                const int v = c * LBS_CV + vl;
+                const float gx = tg[(vl * 3) * TP + lane], gy = tg[(vl * 3 + 1) * TP + lane], gz = tg[(vl * 3 + 2) * TP + lane];
                 float dx = 0.f, dy = 0.f, dz = 0.f;
-                const int cnt = S.cnt[v];
-                for (int s = 0; s < cnt; ++s) {
-                    const float w = S.w[s][v];
-                    const float4* A = reinterpret_cast<const float4*>(s_bone + S.b[s][v] * BONE_F);
+                const int e1 = S.csr.ptr[v + 1];
+                for (int e = S.csr.ptr[v]; e < e1; ++e) {
+                    const float w = S.csr.w[e];
+                    const float4* A = reinterpret_cast<const float4*>(A0 + S.csr.b[e] * BONE_F);
                     const float4 r0 = A[0], r1 = A[1], r2 = A[2];
                     const float wx = w * gx, wy = w * gy, wz = w * gz;
                     dx = fmaf(r0.x, wx, fmaf(r1.x, wy, fmaf(r2.x, wz, dx)));
                     dy = fmaf(r0.y, wx, fmaf(r1.y, wy, fmaf(r2.y, wz, dy)));
                     dz = fmaf(r0.z, wx, fmaf(r1.z, wy, fmaf(r2.z, wz, dz)));
                 }
-                s_dv[v * 3] = dx; s_dv[v * 3 + 1] = dy; s_dv[v * 3 + 2] = dz;
+                S.tile_o[(vl * 3) * TP + lane] = dx; S.tile_o[(vl * 3 + 1) * TP + lane] = dy; S.tile_o[(vl * 3 + 2) * TP + lane] = dz;
             }
+            if (last && threadIdx.x < (VP_PITCH - NVC) * HG)    // zero the two pad floats of the row
+                S.tile_o[(TAIL_F2 + threadIdx.x / HG) * TP + (threadIdx.x % HG)] = 0.f;
+            // (b) per-bone sums for the slots this warp owns: registers across the whole sweep
+#pragma unroll
+            for (int s = 0; s < LBS_SLOTS; ++s) {
+                const int e1 = S.seg[warp][c][s][1];
+                for (int e = S.seg[warp][c][s][0]; e < e1; ++e) {
+                    const int fi = S.ent_idx[e];
+                    const float w = S.ent_w[e];
+                    const float wx = w * tg[fi * TP + lane], wy = w * tg[(fi + 1) * TP + lane], wz = w * tg[(fi + 2) * TP + lane];
+                    const float x = tv[fi * TP + lane], y = tv[(fi + 1) * TP + lane], z = tv[(fi + 2) * TP + lane];
+                    acc[s][0] = fmaf(wx, x, acc[s][0]); acc[s][1] = fmaf(wx, y, acc[s][1]); acc[s][2] = fmaf(wx, z, acc[s][2]);   acc[s][3] += wx;
+                    acc[s][4] = fmaf(wy, x, acc[s][4]); acc[s][5] = fmaf(wy, y, acc[s][5]); acc[s][6] = fmaf(wy, z, acc[s][6]);   acc[s][7] += wy;
+                    acc[s][8] = fmaf(wz, x, acc[s][8]); acc[s][9] = fmaf(wz, y, acc[s][9]); acc[s][10] = fmaf(wz, z, acc[s][10]); acc[s][11] += wz;
+                }
+            }
+            __syncthreads();                               // dv chunk complete
+            if (!last) tile_store<4, LBS_CF / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
+            else       tile_store<4, TAIL_F4 / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
         }
-        if (tid < VP_PITCH - NVC) s_dv[NVC + tid] = 0.f;
-        // (b) per-bone reduction over the bone's vertex list (CSC), one warp per bone
-        for (int k = warp; k < NJ; k += LBS_THREADS / 32) {
-            float acc[BONE_F];
+        // ---- group end: combine the per-slot sums into dbone[h][k][12] (staged in the now idle g tiles)
+        float (*part)[BONE_F][HG + 1] = reinterpret_cast<float (*)[BONE_F][HG + 1]>(&S.tile_g[0][0]);
 #pragma unroll
-            for (int e = 0; e < BONE_F; ++e) acc[e] = 0.f;
-            for (int i = C.ptr[k] + lane; i < C.ptr[k + 1]; i += 32) {
-                const int v = C.v[i];
-                const float w = C.w[i];
-                const float wx = w * s_g[v * 3], wy = w * s_g[v * 3 + 1], wz = w * s_g[v * 3 + 2];
-                const float x = s_vp[v * 3], y = s_vp[v * 3 + 1], z = s_vp[v * 3 + 2];
-                acc[0] = fmaf(wx, x, acc[0]); acc[1] = fmaf(wx, y, acc[1]); acc[2] = fmaf(wx, z, acc[2]);   acc[3] += wx;
-                acc[4] = fmaf(wy, x, acc[4]); acc[5] = fmaf(wy, y, acc[5]); acc[6] = fmaf(wy, z, acc[6]);   acc[7] += wy;
-                acc[8] = fmaf(wz, x, acc[8]); acc[9] = fmaf(wz, y, acc[9]); acc[10] = fmaf(wz, z, acc[10]); acc[11] += wz;
-            }
+        for (int s = 0; s < LBS_SLOTS; ++s)
 #pragma unroll
-            for (int e = 0; e < BONE_F; ++e) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
-            }
-            if (lane == 0) {
-                float4* d = reinterpret_cast<float4*>(dbone + hand * (NJ * BONE_F) + k * BONE_F);
-                d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                d[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
-            }
-        }
+            for (int e = 0; e < BONE_F; ++e) part[warp * LBS_SLOTS + s][e][lane] = acc[s][e];
         __syncthreads();
-        for (int q = tid; q < ROW4; q += LBS_THREADS)
-            st_stream(reinterpret_cast<float4*>(dv_posed + hand * pitch) + q, reinterpret_cast<const float4*>(s_dv)[q]);
+        for (int i = threadIdx.x; i < nh * NJ * BONE_F; i += LBS_THREADS) {
+            const int h = i / (NJ * BONE_F), r = i - h * (NJ * BONE_F), k = r / BONE_F, e = r - k * BONE_F;
+            float sum = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < LBS_WARPS * LBS_SLOTS; ++sl) {
+                const int code = (&S.slot[0][0])[sl];
+                if (code >= 0 && (code & 255) == k) sum += part[sl][e][h];
+            }
+            dbone[(h0 + h) * (NJ * BONE_F) + r] = sum;
+        }
     }
-}
-
-size_t lbs_fwd_smem() { return ((sizeof(SkinShared) + 15) & ~size_t(15)) + sizeof(float) * (2 * VP_PITCH + 2 * NJ * BONE_F); }
-size_t lbs_bwd_smem() {
-    size_t off = (sizeof(SkinShared) + 15) & ~size_t(15);
-    off = (off + sizeof(CscShared) + 15) & ~size_t(15);
-    return off + sizeof(float) * (3 * VP_PITCH + NJ * BONE_F);
 }
 
 }  // namespace
@@ -244,16 +350,15 @@ int launch_lbs_forward(const void* blob, const float* v_posed, int pitch, const 
                        float* verts, float* joints, cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
-    const size_t smem = lbs_fwd_smem();
+    const size_t smem = sizeof(FwdShared);
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(lbs_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    const int npairs = (B + 1) / 2;
-    const int cap = NUM_SMS * 4;
-    const int grid = npairs < cap ? npairs : cap;
-    lbs_forward_kernel<<<grid, LBS_THREADS, smem, s>>>(blob, v_posed, pitch, bone, B, verts, joints);
+    const int ngroups = (B + HG - 1) / HG;
+    const int cap = NUM_SMS * 2;
+    lbs_forward_kernel<<<ngroups < cap ? ngroups : cap, LBS_THREADS, smem, s>>>(blob, v_posed, pitch, bone, B, verts, joints);
     return cuda_rc();
 }
 
@@ -262,15 +367,16 @@ int launch_lbs_backward(const void* blob, const float* v_posed, int pitch, const
                         float* dv_posed, float* dbone, cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
-    const size_t smem = lbs_bwd_smem();
+    const size_t smem = sizeof(BwdShared);
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(lbs_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    const int cap = NUM_SMS * 2;
-    const int grid = B < cap ? B : cap;
-    lbs_backward_kernel<<<grid, LBS_THREADS, smem, s>>>(blob, v_posed, pitch, bone, g_verts, g_joints, B, dv_posed, dbone);
+    const int ngroups = (B + HG - 1) / HG;
+    const int cap = NUM_SMS;
+    lbs_backward_kernel<<<ngroups < cap ? ngroups : cap, LBS_THREADS, smem, s>>>(blob, v_posed, pitch, bone, g_verts, g_joints,
+                                                                                 B, dv_posed, dbone);
     return cuda_rc();
 }
 
