@@ -271,10 +271,13 @@ static int pose_and_blend_forward(const void* blob, int nc, const float* rot, co
     return launch_blend_tc_forward(blob, featp, v_posed, B, mode, s);
 }
 
-static int blend_backward(const void* blob, const float* dv_posed, float* dfeat, int B, int mode, cudaStream_t s) {
-    (void)mode;     // the K = 2334 gradient contraction runs in fp32 FFMA in every mode (tcgen05 version: next round)
-    const BlobLayout L = blob_layout();
-    return launch_sgemm(dv_posed, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s);
+static int blend_backward(const void* blob, const float* dv_posed, const unsigned char* dvp, float* dfeat, int B, int mode,
+                          cudaStream_t s) {
+    if (mode == MB_MODE_FP32) {
+        const BlobLayout L = blob_layout();
+        return launch_sgemm(dv_posed, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s);
+    }
+    return launch_blend_tc_backward(blob, dvp, dfeat, B, s);      // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
 }
 
 extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
@@ -328,8 +331,9 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
         float* scratch_joints = dfeat;      // B*63 floats <= B*148
         if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, ws, W, scratch_joints, s))) return rc;
     }
-    { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_lbs_backward(blob, v_posed, VP_PITCH, bone, g_verts, g_joints, B, dv_posed, dbone, s))) return rc; }
-    { StageTimer t(ST_BLEND_BWD, s); if ((rc = blend_backward(blob, dv_posed, dfeat, B, mode, s))) return rc; }
+    unsigned char* dvp = mode == MB_MODE_FP32 ? nullptr : reinterpret_cast<unsigned char*>(ws + W.dvp);
+    { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_lbs_backward(blob, v_posed, VP_PITCH, bone, g_verts, g_joints, B, dvp ? nullptr : dv_posed, dvp, dbone, s))) return rc; }
+    { StageTimer t(ST_BLEND_BWD, s); if ((rc = blend_backward(blob, dv_posed, dvp, dfeat, B, mode, s))) return rc; }
     StageTimer t(ST_POSE_BWD, s);
     return launch_pose_backward(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
 }

@@ -22,6 +22,7 @@
 // Tiles are distributed as contiguous ranges of the flattened (n_tile, m_tile) space, so every
 // CTA gets the same number of tiles (+-1) and reloads its resident B at most once.
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <string.h>
 #include <math.h>
 #include "common.cuh"
@@ -266,10 +267,155 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
     if (threadIdx.x == 0 && S.abort_flag) __trap();           // a stalled pipeline is an error, never a silent result
 }
 
+
+// ================================================================= backward contraction
+//   dfeat[h][n] = sum_k dv_posed[h][k] * basis[n][k],  n < 145 (+ pad to 160), K = 2336
+// M = 2 x 128 hands per CTA pass (two accumulators of 160 TMEM columns), both operands stream
+// through a 3-stage TMA/mbarrier ring (per K chunk of 32: 2 x 16 KB of dv tiles + 20 KB of basis),
+// bf16 hi + mid split on both sides, three products (hi*hi + mid*hi + hi*mid) in fp32 TMEM
+// accumulators: bf16 keeps fp32's exponent range, so upstream gradients of any magnitude need no
+// scaling, and 16 significand bits per operand bound the error at ~2e-5 relative.
+constexpr int BW_STAGES = 3;
+constexpr int BW_MT = 2;                                           // hand tiles per CTA pass
+constexpr int BW_STAGE_BYTES = BW_MT * TCB_A_CHUNK_BYTES + TCB_B_CHUNK_BYTES;   // 52 KB
+constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+struct TcBwdShared {
+    alignas(128) unsigned char st[BW_STAGES][BW_STAGE_BYTES];       // [A tile 0 (hi,mid)][A tile 1 (hi,mid)][B (hi,mid)]
+    alignas(16) float stage[EPI_WARPS][32][33];
+    alignas(8) unsigned long long full[BW_STAGES], empty[BW_STAGES];
+    unsigned long long acc_full, acc_empty;
+    uint32_t tmem_base;
+    int abort_flag;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsigned char* __restrict__ dvp,
+                         float* __restrict__ dfeat, int B, int m_tiles) {
+    extern __shared__ unsigned char smem_raw[];
+    TcBwdShared& S = *reinterpret_cast<TcBwdShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int passes = (m_tiles + BW_MT - 1) / BW_MT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BW_STAGES; ++s) { mbar_init(smem_u32(&S.full[s]), 1); mbar_init(smem_u32(&S.empty[s]), 1); }
+        mbar_init(smem_u32(&S.acc_full), 1);
+        mbar_init(smem_u32(&S.acc_empty), EPI_WARPS);
+        S.abort_flag = 0;
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    volatile int* abort_flag = &S.abort_flag;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        uint32_t stage = 0, phase = 0;
+        bool ok = true;
+        for (int p = blockIdx.x; p < passes && ok; p += gridDim.x) {
+            const int nmt = (m_tiles - p * BW_MT) < BW_MT ? (m_tiles - p * BW_MT) : BW_MT;
+            for (int kc = 0; kc < TCB_K_CHUNKS; ++kc) {
+                if (!(ok = mbar_wait(smem_u32(&S.empty[stage]), phase ^ 1, abort_flag))) break;
+                mbar_expect_tx(smem_u32(&S.full[stage]), nmt * TCB_A_CHUNK_BYTES + TCB_B_CHUNK_BYTES);
+                const uint32_t dst = smem_u32(S.st[stage]);
+                for (int mt = 0; mt < nmt; ++mt)
+                    bulk_g2s(dst + mt * TCB_A_CHUNK_BYTES,
+                             dvp + (size_t)(p * BW_MT + mt) * TCB_A_TILE_BYTES + (size_t)kc * TCB_A_CHUNK_BYTES,
+                             TCB_A_CHUNK_BYTES, smem_u32(&S.full[stage]));
+                bulk_g2s(dst + BW_MT * TCB_A_CHUNK_BYTES, basis_bw + (size_t)kc * TCB_B_CHUNK_BYTES, TCB_B_CHUNK_BYTES,
+                         smem_u32(&S.full[stage]));
+                if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        uint32_t stage = 0, phase = 0, pass_phase = 0;
+        bool ok = true;
+        const uint64_t base = umma_desc(smem_u32(S.st[0]), TC_LBO, TC_SBO);
+        for (int p = blockIdx.x; p < passes && ok; p += gridDim.x) {
+            const int nmt = (m_tiles - p * BW_MT) < BW_MT ? (m_tiles - p * BW_MT) : BW_MT;
+            if (!(ok = mbar_wait(smem_u32(&S.acc_empty), pass_phase ^ 1, abort_flag))) break;   // epilogue drained the accumulators
+            tc_fence_after();
+            for (int kc = 0; kc < TCB_K_CHUNKS && ok; ++kc) {
+                if (!(ok = mbar_wait(smem_u32(&S.full[stage]), phase, abort_flag))) break;
+                tc_fence_after();
+                const uint64_t sbase = base + (uint64_t)((stage * BW_STAGE_BYTES) >> 4);
+                const uint64_t b_hi0 = sbase + (uint64_t)((BW_MT * TCB_A_CHUNK_BYTES) >> 4);
+#pragma unroll
+                for (int mt = 0; mt < BW_MT; ++mt) {
+                    if (mt < nmt) {
+#pragma unroll
+                        for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
+                            const uint64_t a_hi = sbase + (uint64_t)((mt * TCB_A_CHUNK_BYTES + j * 2 * (int)TC_LBO) >> 4);
+                            const uint64_t a_mid = a_hi + (uint64_t)(TC_A_BLOCK_BYTES >> 4);
+                            const uint64_t b_hi = b_hi0 + (uint64_t)((j * 2 * (int)TC_LBO) >> 4);
+                            const uint64_t b_mid = b_hi + (uint64_t)(TC_B_BLOCK_BYTES >> 4);
+                            const uint32_t d = tmem + mt * TC_N;
+                            umma_f16(d, a_hi, b_hi, IDESC_BF16, (kc | j) ? 1u : 0u);
+                            umma_f16(d, a_mid, b_hi, IDESC_BF16, 1);
+                            umma_f16(d, a_hi, b_mid, IDESC_BF16, 1);
+                        }
+                    }
+                }
+                tc_commit(smem_u32(&S.empty[stage]));
+                if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (!ok) break;
+            tc_commit(smem_u32(&S.acc_full));
+            pass_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: warps 4-7 drain hand tile 0, warps 8-11 hand tile 1 =====
+        const int q = warp & 3;
+        const int mt = (warp - 4) >> 2;
+        float (*buf)[33] = S.stage[warp - 4];
+        uint32_t pass_phase = 0;
+        bool ok = true;
+        for (int p = blockIdx.x; p < passes && ok; p += gridDim.x) {
+            ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&S.acc_full), pass_phase, abort_flag));
+            if (!ok) break;
+            tc_fence_after();
+            const int m_tile = p * BW_MT + mt;
+            const int row0 = m_tile * TC_M + q * 32;
+            const bool active = m_tile < m_tiles;
+#pragma unroll 1
+            for (int j = 0; j < TC_N / 32; ++j) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mt * TC_N + j * 32, v);
+                if (j == TC_N / 32 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty));
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) buf[lane][c] = v[c];
+                __syncwarp();
+                const int col = j * 32 + lane;
+                if (active && col < FEAT_K) {
+                    float* dst = dfeat + (size_t)row0 * FEAT_K + col;
+                    const int nrow = B - row0 < 32 ? B - row0 : 32;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr)
+                        if (rr < nrow) dst[(size_t)rr * FEAT_K] = buf[rr][lane];
+                }
+                __syncwarp();
+            }
+            pass_phase ^= 1;
+        }
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, TMEM_COLS);
+    if (threadIdx.x == 0 && S.abort_flag) __trap();
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- host side
-size_t blend_tc_blob_bytes() { return align256(sizeof(TcBlobHeader)) + (size_t)TC_N_TILES * TC_B_TILE_BYTES; }
+static size_t tc_fwd_bytes() { return align256(sizeof(TcBlobHeader)) + align256((size_t)TC_N_TILES * TC_B_TILE_BYTES); }
+size_t blend_tc_blob_bytes() { return tc_fwd_bytes() + align256(TCB_B_BYTES); }
 
 // basis [FEAT_K][2334] fp32 -> per n-tile, per K chunk, {hi, lo} blocks in the UMMA canonical
 // K-major layout [row-group][k-group][8 rows][8 halves]; pre-scaled by a power of two.
@@ -299,6 +445,37 @@ void blend_tc_pack(const float* basis, void* host_blob_tc) {
                     dst[(blk + 0) * (TC_B_BLOCK_BYTES / 2) + in] = hi;
                     dst[(blk + 1) * (TC_B_BLOCK_BYTES / 2) + in] = lo;
                 }
+    // backward B operand: basis[n][k] as bf16 hi + mid (unscaled), rows n = feature (160, zero beyond 145),
+    // per K chunk of 32 vertex coordinates: [73][split 2][row-group 20][k-group 4][8 rows][8 bf16]
+    __nv_bfloat16* bw = reinterpret_cast<__nv_bfloat16*>(out + tc_fwd_bytes());
+    for (int kc = 0; kc < TCB_K_CHUNKS; ++kc)
+        for (int r = 0; r < TC_N; ++r)
+            for (int kk = 0; kk < TC_K_CHUNK; ++kk) {
+                const int k = kc * TC_K_CHUNK + kk;
+                const float x = (r < TC_K_REAL && k < NVC) ? basis[(size_t)r * NVC + k] : 0.f;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+                const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+                const size_t in = (((size_t)(r >> 3) * (TC_K_CHUNK / 8) + (kk >> 3)) * 8 + (r & 7)) * 8 + (kk & 7);
+                bw[((size_t)kc * 2 + 0) * (TC_B_BLOCK_BYTES / 2) + in] = hi;
+                bw[((size_t)kc * 2 + 1) * (TC_B_BLOCK_BYTES / 2) + in] = mid;
+            }
+}
+
+int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, cudaStream_t s) {
+    if (B <= 0) return 0;
+    static bool attr_done = false;
+    const size_t smem = sizeof(TcBwdShared) + 128;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(blend_tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const BlobLayout L = blob_layout();
+    const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
+    const int m_tiles = (B + TC_M - 1) / TC_M;
+    const int passes = (m_tiles + BW_MT - 1) / BW_MT;
+    blend_tc_backward_kernel<<<passes < NUM_SMS ? passes : NUM_SMS, TC_THREADS, smem, s>>>(tc + tc_fwd_bytes(), dvp, dfeat, B, m_tiles);
+    return cuda_rc();
 }
 
 int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed, int B, int mode, cudaStream_t s) {

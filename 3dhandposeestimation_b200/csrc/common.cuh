@@ -105,6 +105,7 @@ struct WorkLayout {
     size_t dbone;     // float [B][16][12]     (backward only)
     size_t dfeat;     // float [B][FEAT_K]     (backward only)
     size_t featp;     // fp16 hi/lo feature tiles of the tcgen05 path: ceil(B/128) * 80 KB
+    size_t dvp;       // bf16 hi/mid dv_posed tiles of the tcgen05 backward: ceil(B/128) * 73 * 16 KB
     size_t total;
 };
 
@@ -118,6 +119,7 @@ __host__ __device__ inline WorkLayout work_layout(long long B) {
     W.dbone = o;    o = align256(o + sizeof(float) * B * NJ * BONE_F);
     W.dfeat = o;    o = align256(o + sizeof(float) * B * FEAT_K);
     W.featp = o;    o = align256(o + (size_t)((B + 127) / 128) * 81920);
+    W.dvp = o;      o = align256(o + (size_t)((B + 127) / 128) * (73 * 16384));
     W.total = o;
     return W;
 }
@@ -144,9 +146,10 @@ int launch_sgemm(const float* A, int lda, const float* Bm, int ldb, float* C, in
                  long long M, int N, int K, cudaStream_t s);
 int launch_lbs_forward(const void* blob, const float* v_posed, int pitch, const float* bone, int B,
                        float* verts, float* joints, cudaStream_t s);
+// dv_posed (fp32 rows) or dvp (bf16 hi/mid UMMA tiles for the tcgen05 backward): exactly one is non-NULL
 int launch_lbs_backward(const void* blob, const float* v_posed, int pitch, const float* bone,
                         const float* g_verts, const float* g_joints, int B,
-                        float* dv_posed, float* dbone, cudaStream_t s);
+                        float* dv_posed, unsigned char* dvp, float* dbone, cudaStream_t s);
 
 // launch bookkeeping (api.cu): every kernel launch of this library goes through cuda_rc()
 void count_launch();

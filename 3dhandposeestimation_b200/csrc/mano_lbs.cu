@@ -22,7 +22,9 @@
 // dA'_k = sum_v w_vk g_v (x) [v_posed_v ; 1].  The second is a reduction over vertices: each warp
 // OWNS up to three bones (or halves of long bones; host-side greedy balance) and keeps their 3x4
 // accumulators in registers across the whole vertex sweep — no atomics, no shuffles.
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "blend_tc.cuh"
 
 namespace mb {
 namespace {
@@ -231,7 +233,8 @@ __global__ void __launch_bounds__(LBS_THREADS)
 lbs_backward_kernel(const void* __restrict__ blob, const float* v_posed, int pitch,
                     const float* __restrict__ bone, const float* __restrict__ g_verts,
                     const float* __restrict__ g_joints, int B,
-                    float* dv_posed, float* __restrict__ dbone) {   // dv_posed may alias v_posed (chunk read before write)
+                    float* dv_posed, unsigned char* __restrict__ dvp,
+                    float* __restrict__ dbone) {   // dv_posed may alias v_posed (chunk read before write)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdShared& S = *reinterpret_cast<BwdShared*>(smem_raw);
     stage_csr(S.csr, blob);
@@ -321,8 +324,34 @@ lbs_backward_kernel(const void* __restrict__ blob, const float* v_posed, int pit
                 }
             }
             __syncthreads();                               // dv chunk complete
-            if (!last) tile_store<4, LBS_CF / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
-            else       tile_store<4, TAIL_F4 / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
+            if (dvp == nullptr) {
+                if (!last) tile_store<4, LBS_CF / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
+                else       tile_store<4, TAIL_F4 / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
+            } else {
+                // A operand of the tcgen05 gradient contraction: bf16 hi + mid, UMMA canonical K-major
+                // blocks.  One warp store = 32 lanes x 16 B = one contiguous 512-byte piece
+                // (4 k-groups x 8 hands of one 8-row group); lane = (k-group, hand) is conflict-free
+                // on the transposed tile.
+                const int nblk = last ? 1 : LBS_CF / TC_K_CHUNK;           // K chunks of 32 in this vertex chunk
+                const int kg = lane >> 3, r = lane & 7;
+                unsigned char* tile_base = dvp + (size_t)(grp >> 2) * TCB_A_TILE_BYTES;
+                const int rg0 = (grp & 3) * 4;
+                for (int piece = warp; piece < nblk * 4; piece += LBS_WARPS) {
+                    const int blk = piece >> 2, rgl = piece & 3;
+                    const float* src = S.tile_o + ((blk * 4 + kg) * 8) * TP + rgl * 8 + r;
+                    __align__(16) __nv_bfloat16 hi[8], mid[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = src[e * TP];
+                        hi[e] = __float2bfloat16_rn(x);
+                        mid[e] = __float2bfloat16_rn(x - __bfloat162float(hi[e]));
+                    }
+                    unsigned char* dst = tile_base + (size_t)(c * (LBS_CF / TC_K_CHUNK) + blk) * TCB_A_CHUNK_BYTES +
+                                         (((rg0 + rgl) * 4 + kg) * 8 + r) * 16;
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+                    *reinterpret_cast<uint4*>(dst + TC_A_BLOCK_BYTES) = *reinterpret_cast<const uint4*>(mid);
+                }
+            }
         }
         // ---- group end: combine the per-slot sums into dbone[h][k][12] (staged in the now idle g tiles)
         float (*part)[BONE_F][HG + 1] = reinterpret_cast<float (*)[BONE_F][HG + 1]>(&S.tile_g[0][0]);
@@ -364,7 +393,7 @@ int launch_lbs_forward(const void* blob, const float* v_posed, int pitch, const 
 
 int launch_lbs_backward(const void* blob, const float* v_posed, int pitch, const float* bone,
                         const float* g_verts, const float* g_joints, int B,
-                        float* dv_posed, float* dbone, cudaStream_t s) {
+                        float* dv_posed, unsigned char* dvp, float* dbone, cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
     const size_t smem = sizeof(BwdShared);
@@ -376,7 +405,7 @@ int launch_lbs_backward(const void* blob, const float* v_posed, int pitch, const
     const int ngroups = (B + HG - 1) / HG;
     const int cap = NUM_SMS;
     lbs_backward_kernel<<<ngroups < cap ? ngroups : cap, LBS_THREADS, smem, s>>>(blob, v_posed, pitch, bone, g_verts, g_joints,
-                                                                                 B, dv_posed, dbone);
+                                                                                 B, dv_posed, dvp, dbone);
     return cuda_rc();
 }
 

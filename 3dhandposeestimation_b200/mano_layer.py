@@ -107,6 +107,8 @@ class _ManoFunction(torch.autograd.Function):
                                              layer._mode, flags, g_rot.data_ptr(), g_coeffs.data_ptr(),
                                              g_betas.data_ptr(), ws.data_ptr(), ws.numel(), stream),
                         "mb_mano_backward")
+            if not ctx.ws_valid:
+                ctx.ws = None                 # consumed: let the caching allocator reuse it (stream-ordered)
         return g_rot, g_coeffs, g_betas, None, None
 
 

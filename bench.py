@@ -313,36 +313,6 @@ def main():
                   "algorithmic_flop_per_hand": FLOP_BLEND, "avg_launch_ms": blend_ms, "mode": args.mode}
     step_gbs = (BYTES_FWD + BYTES_BWD) * H / (ms_per_step * 1e-3) / 1e9
 
-    # ---- end to end through the public nn.Module API with host buffers ------------------
-    e2e = None
-    if not args.no_e2e:
-        s = sets[0]
-        h_in = [torch.from_numpy(a).pin_memory() for a in synth_inputs(H, 555 + rank)]
-        h_out = [torch.empty(H, n, dtype=torch.float32).pin_memory() for n in (3, 45, 10)]
-        h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
-
-        def e2e_step():
-            d = [t.to(dev, non_blocking=True).requires_grad_() for t in h_in]
-            verts, joints = layer(*d)
-            torch.autograd.backward([verts, joints], [s["gv"], s["gj"]])
-            for dst, src in zip(h_out, d):
-                dst.copy_(src.grad, non_blocking=True)
-            h_loss.copy_(joints[0, 0, :1], non_blocking=True)
-
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(2):
-            e2e_step()
-        sync_all()
-        e0.record()
-        for _ in range(n_e2e):
-            e2e_step()
-        e1.record()
-        sync_all()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
-        e2e = {"value": world * H / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * 58 * 4,
-               "d2h_bytes_per_step": H * 58 * 4 + 4, "ms_per_step": ms_e2e, "steps": n_e2e,
-               "api": "ManoLayer.forward + autograd backward; pinned host params in, pinned host grads out"}
-
     # ---- parity spot check in the same run (checker only) -------------------------------
     parity = None
     cpu = None
@@ -360,8 +330,51 @@ def main():
                   "joints_max_abs_err_m": float(np.abs(s["joints"][tidx].cpu().numpy() - oj).max()),
                   "grad_rel_err": max(float(np.abs(s[k][tidx].cpu().numpy() - w).max() / np.abs(w).max())
                                       for k, w in zip(("g_rot", "g_pose", "g_beta"), og))}
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(model)
+    # ---- end to end through the public nn.Module API with host buffers ------------------
+    e2e = None
+    if not args.no_e2e:
+        s = sets[0]
+        # release the device-resident arm's big buffers before the module API allocates its own
+        gv_keep, gj_keep = s["gv"], s["gj"]
+        del ws
+        for st in sets:
+            st.clear()
+        sets.clear()
+        torch.cuda.empty_cache()
+        if os.environ.get("MANO_B200_BENCH_DEBUG"):
+            sys.stderr.write(f"before e2e: allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB\n")
+        h_in = [torch.from_numpy(a).pin_memory() for a in synth_inputs(H, 555 + rank)]
+        h_out = [torch.empty(H, n, dtype=torch.float32).pin_memory() for n in (3, 45, 10)]
+        h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            d = [t.to(dev, non_blocking=True).requires_grad_() for t in h_in]
+            verts, joints = layer(*d)
+            torch.autograd.backward([verts, joints], [gv_keep, gj_keep])
+            for dst, src in zip(h_out, d):
+                dst.copy_(src.grad, non_blocking=True)
+            h_loss.copy_(joints[0, 0, :1], non_blocking=True)
+            del verts, joints, d
+            if os.environ.get("MANO_B200_BENCH_DEBUG"):
+                sys.stderr.write(f"e2e step: allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB, "
+                                 f"reserved {torch.cuda.memory_reserved(dev) / 2**30:.1f} GiB\n")
+
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        sync_all()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        e2e = {"value": world * H / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * 58 * 4,
+               "d2h_bytes_per_step": H * 58 * 4 + 4, "ms_per_step": ms_e2e, "steps": n_e2e,
+               "api": "ManoLayer.forward + autograd backward; pinned host params in, pinned host grads out"}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(model)
 
     if world > 1:
         dist.barrier()
