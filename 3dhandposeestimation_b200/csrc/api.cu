@@ -178,29 +178,37 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
     }
     // Ownership of the per-bone gradient sums: each of the 8 warps owns up to 3 "slots"; a slot is a
     // bone or one half (even/odd entries) of a bone too long for one warp.  Longest-first greedy.
-    struct Part { int bone, half, len; };
+    struct Part { int bone, part, nparts, len; };
     std::vector<Part> parts;
-    const int target = (nnz + LBS_WARPS - 1) / LBS_WARPS;
-    for (int k = 0; k < NJ; ++k) {
-        if (per_bone[k] == 0) continue;
-        if (per_bone[k] > target && (int)parts.size() + 2 <= LBS_WARPS * LBS_SLOTS - (NJ - 1 - k)) {
-            parts.push_back({k, 1, (per_bone[k] + 1) / 2});
-            parts.push_back({k, 2, per_bone[k] / 2});
-        } else {
-            parts.push_back({k, 0, per_bone[k]});
+    {
+        int nb = 0;
+        for (int k = 0; k < NJ; ++k) nb += per_bone[k] > 0;
+        // split the longest lists into P parts (entries ord % P == part) until the slots are used up
+        int np[NJ];
+        for (int k = 0; k < NJ; ++k) np[k] = per_bone[k] > 0 ? 1 : 0;
+        int total_parts = nb;
+        while (total_parts < LBS_WARPS * LBS_SLOTS) {
+            int best = -1;
+            for (int k = 0; k < NJ; ++k)
+                if (np[k] > 0 && (best < 0 || per_bone[k] * np[best] > per_bone[best] * np[k])) best = k;
+            if (best < 0 || per_bone[best] / np[best] < 16) break;        // nothing worth splitting
+            ++np[best];
+            ++total_parts;
         }
+        for (int k = 0; k < NJ; ++k)
+            for (int q = 0; q < np[k]; ++q) parts.push_back({k, q, np[k], (per_bone[k] - q + np[k] - 1) / np[k]});
     }
     if ((int)parts.size() > LBS_WARPS * LBS_SLOTS) return MB_E_MODEL;
     std::sort(parts.begin(), parts.end(), [](const Part& a, const Part& b) { return a.len > b.len; });
     int load[LBS_WARPS] = {0}, used[LBS_WARPS] = {0};
-    int* bslot = reinterpret_cast<int*>(out + L.bslot);          // bone | half << 8
+    int* bslot = reinterpret_cast<int*>(out + L.bslot);          // bone | part << 8 | nparts << 16
     for (int i = 0; i < LBS_WARPS * LBS_SLOTS; ++i) bslot[i] = -1;
     for (const Part& p : parts) {
         int best = -1;
         for (int w = 0; w < LBS_WARPS; ++w)
             if (used[w] < LBS_SLOTS && (best < 0 || load[w] < load[best])) best = w;
         if (best < 0) return MB_E_MODEL;
-        bslot[best * LBS_SLOTS + used[best]] = p.bone | (p.half << 8);
+        bslot[best * LBS_SLOTS + used[best]] = p.bone | (p.part << 8) | (p.nparts << 16);
         ++used[best];
         load[best] += p.len;
     }
@@ -215,11 +223,10 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
                 seg[0] = e;
                 const int code = bslot[w * LBS_SLOTS + s];
                 if (code >= 0) {
-                    const int bone = code & 255, half = code >> 8;
+                    const int bone = code & 255, part = (code >> 8) & 255, nparts = code >> 16;
                     for (int i = cptr[bone]; i < cptr[bone + 1]; ++i) {
                         const int ord = i - cptr[bone];
-                        if (half == 1 && (ord & 1)) continue;
-                        if (half == 2 && !(ord & 1)) continue;
+                        if (ord % nparts != part) continue;
                         const int v = cv[i];
                         if (v / LBS_CV != c) continue;
                         bidx[e] = (uint16_t)((v - c * LBS_CV) * 3);

@@ -22,11 +22,11 @@ constexpr int MAX_INFL = 8;
 constexpr int BONE_F = 12;        // 3x4 [R|t] per bone
 constexpr int NUM_SMS = 148;
 constexpr int MAX_NNZ = 3200;      // total skinning weights supported
-constexpr int LBS_WARPS = 8;       // warps per CTA of the skinning kernels
+constexpr int LBS_WARPS = 16;      // warps per CTA of the skinning kernels
 constexpr int LBS_CV = 64;         // vertices per chunk
 constexpr int LBS_CF = LBS_CV * 3; // floats per chunk row
 constexpr int LBS_CHUNKS = (NV + LBS_CV - 1) / LBS_CV;   // 13
-constexpr int LBS_SLOTS = 3;       // bones (or bone halves) owned by one warp in the backward reduction
+constexpr int LBS_SLOTS = 2;       // bones (or parts of long bones) owned by one warp in the backward reduction
 
 // Device blob layout (byte offsets, every section 256-byte aligned).
 struct BlobLayout {

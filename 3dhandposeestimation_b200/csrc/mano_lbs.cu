@@ -29,7 +29,7 @@
 namespace mb {
 namespace {
 
-constexpr int LBS_THREADS = LBS_WARPS * 32;     // 256
+constexpr int LBS_THREADS = LBS_WARPS * 32;     // 512
 constexpr int TP = 33;                          // transposed tile pitch (floats)
 constexpr int BONE_PITCH = 196;                 // floats per hand in the bone tile (49 float4, odd)
 constexpr int HG = 32;                          // hands per group
@@ -160,7 +160,7 @@ struct FwdShared {
     alignas(16) float tile[2][LBS_CF * TP];
 };
 
-__global__ void __launch_bounds__(LBS_THREADS)
+__global__ void __launch_bounds__(LBS_THREADS, 2)
 lbs_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed, int pitch,
                    const float* __restrict__ bone, int B, float* __restrict__ verts, float* __restrict__ joints) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -222,8 +222,8 @@ struct BwdShared {
     unsigned short ent_idx[MAX_NNZ];
     float ent_w[MAX_NNZ];
     alignas(16) float bone[HG * BONE_PITCH];
-    alignas(16) float tile_g[2][LBS_CF * TP];
-    alignas(16) float tile_v[2][LBS_CF * TP];
+    alignas(16) float tile_g[LBS_CF * TP];          // single-buffered: chunk c+1 waits in registers
+    alignas(16) float tile_v[LBS_CF * TP];
     alignas(16) float tile_o[LBS_CF * TP];          // dv chunk
 };
 static_assert(sizeof(float) * LBS_WARPS * LBS_SLOTS * BONE_F * (HG + 1) <= sizeof(float) * 2 * LBS_CF * TP,
@@ -266,8 +266,8 @@ lbs_backward_kernel(const void* __restrict__ blob, const float* v_posed, int pit
         chunk_load<4, LBS_CF / 4, I4>(rv, v_posed, pitch, h0, nh, 0);
         chunk_load<2, LBS_CF / 2, I2>(rg, g_verts, NVC, h0, nh, 0);
         for (int c = 0; c < LBS_CHUNKS; ++c) {
-            float* tg = S.tile_g[c & 1];
-            float* tv = S.tile_v[c & 1];
+            float* tg = S.tile_g;
+            float* tv = S.tile_v;
             const int f0 = c * LBS_CF;
             const bool last = (c == LBS_CHUNKS - 1);
             const int nv = last ? TAIL_V : LBS_CV;
@@ -323,7 +323,7 @@ lbs_backward_kernel(const void* __restrict__ blob, const float* v_posed, int pit
                     acc[s][8] = fmaf(wz, x, acc[s][8]); acc[s][9] = fmaf(wz, y, acc[s][9]); acc[s][10] = fmaf(wz, z, acc[s][10]); acc[s][11] += wz;
                 }
             }
-            __syncthreads();                               // dv chunk complete
+            __syncthreads();                               // dv chunk complete; g / v tiles free for chunk c+1
             if (dvp == nullptr) {
                 if (!last) tile_store<4, LBS_CF / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
                 else       tile_store<4, TAIL_F4 / 4>(S.tile_o, dv_posed, pitch, h0, nh, f0);
@@ -354,7 +354,7 @@ lbs_backward_kernel(const void* __restrict__ blob, const float* v_posed, int pit
             }
         }
         // ---- group end: combine the per-slot sums into dbone[h][k][12] (staged in the now idle g tiles)
-        float (*part)[BONE_F][HG + 1] = reinterpret_cast<float (*)[BONE_F][HG + 1]>(&S.tile_g[0][0]);
+        float (*part)[BONE_F][HG + 1] = reinterpret_cast<float (*)[BONE_F][HG + 1]>(&S.tile_g[0]);
 #pragma unroll
         for (int s = 0; s < LBS_SLOTS; ++s)
 #pragma unroll

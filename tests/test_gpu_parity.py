@@ -8,6 +8,8 @@ Tolerances (SURVEY A.4 / BASELINE north_star):
   gradients            : 1e-4 relative to the tensor's max-abs
   MPJPE / L2           : 1e-5 relative
 """
+import importlib
+
 import numpy as np
 import pytest
 
@@ -365,3 +367,68 @@ def test_adam_step_matches_torch(pkg, cuda_device):
         pkg._cabi.check(lib.mb_adam_step(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
                                          1e-2, 0.9, 0.999, 1e-8, step, pkg._cabi.stream_handle(cuda_device)), "adam")
     assert float((p - ref_p.detach()).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------ fitting loop
+def test_fitting_loop_matches_oracle_adam(pkg, synth_model, cuda_device):
+    """BASELINE config 5 parity: 64 hands x 10 Adam iterations against the oracle's
+    objective (L2Loss + regulariser) and gradients with a numpy Adam (torch.optim.Adam semantics)."""
+    import torch
+
+    fitting = importlib.import_module("3dhandposeestimation_b200.fitting")
+    B, nc, iters = 64, 45, 10
+    rs = np.random.RandomState(5)
+    hidden = mano_inputs(B, nc, seed=77, pose_scale=1.0)
+    _, tj = mo.mano_forward(synth_model, *hidden)
+    target = (tj + rs.randn(B, 21, 3) * 1e-3).astype(np.float32)
+    vis = (rs.rand(B, 21, 1) < .8).astype(np.float32)
+    start = [a * 0.5 + 0.01 for a in hidden]
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc)
+    fit = fitting.ManoFitter(layer, B, lr=1e-2)
+    for dst, src in zip((fit.rot, fit.pose, fit.beta), start):
+        dst.copy_(torch.from_numpy(src.astype(np.float32)))
+    ttarget, tvis = to_dev(cuda_device, target, vis)
+    # numpy reference
+    p = [a.astype(np.float64) for a in start]
+    m = [np.zeros_like(a) for a in p]
+    v = [np.zeros_like(a) for a in p]
+    losses_ref, losses = [], []
+    for it in range(1, iters + 1):
+        losses.append(float(fit.step(ttarget, tvis)))
+        _, j = mo.mano_forward(synth_model, *p)
+        losses_ref.append(float(fo.l2loss(j, target, vis) + fo.regularizer(p[1], p[2])))
+        gj = fo.l2loss_backward(j, target, vis)
+        g = list(mo.mano_backward(synth_model, *p, None, gj))
+        g[1] = g[1] + p[1] / (100.0 * np.linalg.norm(p[1]))
+        g[2] = g[2] + 10.0 * p[2] / (100.0 * np.linalg.norm(p[2]))
+        for k in range(3):
+            m[k] = 0.9 * m[k] + 0.1 * g[k]
+            v[k] = 0.999 * v[k] + 0.001 * g[k] ** 2
+            p[k] = p[k] - 1e-2 / (1 - 0.9 ** it) * m[k] / (np.sqrt(v[k]) / np.sqrt(1 - 0.999 ** it) + 1e-8)
+    assert np.allclose(losses, losses_ref, rtol=2e-4, atol=1e-7), (losses, losses_ref)
+    assert losses[-1] < losses[0]
+    for got, want in zip((fit.rot, fit.pose, fit.beta), p):
+        assert np.abs(got.cpu().numpy() - want).max() < 2e-3      # Adam's sign-like first steps amplify fp32 noise
+
+
+def test_module_api_does_not_leak_device_memory(pkg, synth_model, cuda_device):
+    import torch
+
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=45, mode="f16x3")
+    rot, pose, beta = mano_inputs(2048, 45, seed=1)
+    gv = torch.randn(2048, 778, 3, device=cuda_device)
+    gj = torch.randn(2048, 21, 3, device=cuda_device)
+
+    def one():
+        t = to_dev(cuda_device, rot, pose, beta, grad=True)
+        v, j = layer(*t)
+        torch.autograd.backward([v, j], [gv, gj])
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated(cuda_device)
+    for _ in range(10):
+        one()
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated(cuda_device) - base < (1 << 20)
