@@ -36,7 +36,8 @@ SIGNATURES = {
     "mb_mano_workspace_bytes": (_sz, [_i, _i]),
     "mb_mano_forward": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "mb_mano_backward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
-    "mb_lbs_forward": (_i, [_p, _p, _i, _p, _i, _p, _p, _p]),
+    "mb_lbs_workspace_bytes": (_sz, [_i]),
+    "mb_lbs_forward": (_i, [_p, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "mb_fk_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "mb_fk_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "mb_project_uv_forward": (_i, [_p, _p, _i, _i, _p, _p]),

@@ -5,9 +5,10 @@
 using namespace mb;
 
 #include "blend_tc.cuh"
+#include "skin.cuh"
 namespace mb {
 size_t blend_tc_blob_bytes();
-void blend_tc_pack(const float* basis, void* host_blob_tc);
+void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob_tc);
 }  // namespace mb
 
 // ---------------------------------------------------------------- bookkeeping
@@ -166,85 +167,21 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
         }
     H->csc_nnz = nnz;
 
-    // ---- tables of the lane=hand skinning kernels ------------------------------------------
-    int* rptr = reinterpret_cast<int*>(out + L.csr_ptr);
-    float* rw = reinterpret_cast<float*>(out + L.csr_w);
-    uint8_t* rb = reinterpret_cast<uint8_t*>(out + L.csr_b);
-    rptr[0] = 0;
-    for (int v = 0; v < NV; ++v) {
-        int o = rptr[v];
-        for (int s = 0; s < sc[v]; ++s) { rw[o] = sw[v * MAX_INFL + s]; rb[o] = sb[v * MAX_INFL + s]; ++o; }
-        rptr[v + 1] = o;
-    }
-    // Ownership of the per-bone gradient sums: each of the 8 warps owns up to 3 "slots"; a slot is a
-    // bone or one half (even/odd entries) of a bone too long for one warp.  Longest-first greedy.
-    struct Part { int bone, part, nparts, len; };
-    std::vector<Part> parts;
+    // ---- skin program of the register-blocked skinning kernels + block-order v_template ----
+    std::vector<int32_t> coord_map(SK_TMPL_PAD);
     {
-        int nb = 0;
-        for (int k = 0; k < NJ; ++k) nb += per_bone[k] > 0;
-        // split the longest lists into P parts (entries ord % P == part) until the slots are used up
-        int np[NJ];
-        for (int k = 0; k < NJ; ++k) np[k] = per_bone[k] > 0 ? 1 : 0;
-        int total_parts = nb;
-        while (total_parts < LBS_WARPS * LBS_SLOTS) {
-            int best = -1;
-            for (int k = 0; k < NJ; ++k)
-                if (np[k] > 0 && (best < 0 || per_bone[k] * np[best] > per_bone[best] * np[k])) best = k;
-            if (best < 0 || per_bone[best] / np[best] < 16) break;        // nothing worth splitting
-            ++np[best];
-            ++total_parts;
-        }
-        for (int k = 0; k < NJ; ++k)
-            for (int q = 0; q < np[k]; ++q) parts.push_back({k, q, np[k], (per_bone[k] - q + np[k] - 1) / np[k]});
+        const int rc = skin_pack(skin_w, skin_b, host_blob, coord_map.data());
+        if (rc) return rc;
+        float* tm = reinterpret_cast<float*>(out + L.sk_tmpl);
+        for (int c = 0; c < SK_TMPL_PAD; ++c) tm[c] = coord_map[c] >= 0 ? basis[(size_t)FEAT_ONE * NVC + coord_map[c]] : 0.f;
     }
-    if ((int)parts.size() > LBS_WARPS * LBS_SLOTS) return MB_E_MODEL;
-    std::sort(parts.begin(), parts.end(), [](const Part& a, const Part& b) { return a.len > b.len; });
-    int load[LBS_WARPS] = {0}, used[LBS_WARPS] = {0};
-    int* bslot = reinterpret_cast<int*>(out + L.bslot);          // bone | part << 8 | nparts << 16
-    for (int i = 0; i < LBS_WARPS * LBS_SLOTS; ++i) bslot[i] = -1;
-    for (const Part& p : parts) {
-        int best = -1;
-        for (int w = 0; w < LBS_WARPS; ++w)
-            if (used[w] < LBS_SLOTS && (best < 0 || load[w] < load[best])) best = w;
-        if (best < 0) return MB_E_MODEL;
-        bslot[best * LBS_SLOTS + used[best]] = p.bone | (p.part << 8) | (p.nparts << 16);
-        ++used[best];
-        load[best] += p.len;
-    }
-    int* bseg = reinterpret_cast<int*>(out + L.bseg);
-    uint16_t* bidx = reinterpret_cast<uint16_t*>(out + L.bent_idx);
-    float* bw = reinterpret_cast<float*>(out + L.bent_w);
-    int e = 0;
-    for (int w = 0; w < LBS_WARPS; ++w)
-        for (int c = 0; c < LBS_CHUNKS; ++c)
-            for (int s = 0; s < LBS_SLOTS; ++s) {
-                int* seg = bseg + ((w * LBS_CHUNKS + c) * LBS_SLOTS + s) * 2;
-                seg[0] = e;
-                const int code = bslot[w * LBS_SLOTS + s];
-                if (code >= 0) {
-                    const int bone = code & 255, part = (code >> 8) & 255, nparts = code >> 16;
-                    for (int i = cptr[bone]; i < cptr[bone + 1]; ++i) {
-                        const int ord = i - cptr[bone];
-                        if (ord % nparts != part) continue;
-                        const int v = cv[i];
-                        if (v / LBS_CV != c) continue;
-                        bidx[e] = (uint16_t)((v - c * LBS_CV) * 3);
-                        bw[e] = cw[i];
-                        ++e;
-                    }
-                }
-                seg[1] = e;
-            }
-    if (e != nnz) return MB_E_MODEL;
-    blend_tc_pack(basis, out + L.total);
+    blend_tc_pack(basis, coord_map.data(), out + L.total);
     return 0;
 }
 
 extern "C" size_t mb_mano_workspace_bytes(int B, int mode) {
-    (void)mode;
     if (B < 0) return 0;
-    return work_layout(B).total;
+    return work_layout(B, mode).total;
 }
 
 static int check_common(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B, int mode,
@@ -254,37 +191,30 @@ static int check_common(const void* blob, int nc, const float* rot, const float*
     if (B == 0) return 0;
     if (!blob || !rot || !coeffs || !betas) return MB_E_NULL;
     if (!workspace) return MB_E_NULL;
-    if (workspace_bytes < work_layout(B).total) return MB_E_WORKSPACE;
+    if (workspace_bytes < work_layout(B, mode).total) return MB_E_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(blob) & 15)) return MB_E_ALIGN;
     return 0;
 }
 
-// pose stage + blend contraction of the forward (fp32 FFMA or tcgen05)
+// pose stage + blend contraction of the forward (fp32 FFMA or tcgen05): fills bone_t and v_posed_t
 static int pose_and_blend_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B,
                                   int mode, char* ws, const WorkLayout& W, float* joints, cudaStream_t s) {
-    float* feat = reinterpret_cast<float*>(ws + W.feat);
-    float* bone = reinterpret_cast<float*>(ws + W.bone);
-    float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
-    unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
+    float* bone_t = reinterpret_cast<float*>(ws + W.bone_t);
+    float* v_posed_t = reinterpret_cast<float*>(ws + W.v_posed_t);
     int rc;
     if (mode == MB_MODE_FP32) {
-        { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, feat, nullptr, bone, joints, s))) return rc; }
+        float* feat = reinterpret_cast<float*>(ws + W.feat);
+        float* rows = reinterpret_cast<float*>(ws + W.rows);
+        { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, feat, nullptr, bone_t, joints, s))) return rc; }
         StageTimer t(ST_BLEND_FWD, s);
         const BlobLayout L = blob_layout();
-        return launch_sgemm(feat, FEAT_K, blob_ptr<float>(blob, L.basis), VP_PITCH, v_posed, VP_PITCH, B, NVC, FEAT_K, s);
+        if ((rc = launch_sgemm(feat, FEAT_K, blob_ptr<float>(blob, L.basis), VP_PITCH, rows, VP_PITCH, B, NVC, FEAT_K, s))) return rc;
+        return launch_rows_to_t(blob, rows, VP_PITCH, B, v_posed_t, s);
     }
-    { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone, joints, s))) return rc; }
+    unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
+    { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s))) return rc; }
     StageTimer t(ST_BLEND_FWD, s);
-    return launch_blend_tc_forward(blob, featp, v_posed, B, mode, s);
-}
-
-static int blend_backward(const void* blob, const float* dv_posed, const unsigned char* dvp, float* dfeat, int B, int mode,
-                          cudaStream_t s) {
-    if (mode == MB_MODE_FP32) {
-        const BlobLayout L = blob_layout();
-        return launch_sgemm(dv_posed, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s);
-    }
-    return launch_blend_tc_backward(blob, dvp, dfeat, B, s);      // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
+    return launch_blend_tc_forward(blob, featp, v_posed_t, B, mode, s);
 }
 
 extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
@@ -302,13 +232,12 @@ extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const
     if (rc || B == 0) return rc;
     if (!joints) return MB_E_NULL;
     if (reinterpret_cast<uintptr_t>(verts) & 15) return MB_E_ALIGN;
-    const WorkLayout W = work_layout(B);
+    const WorkLayout W = work_layout(B, mode);
     char* ws = reinterpret_cast<char*>(workspace);
-    float* bone = reinterpret_cast<float*>(ws + W.bone);
-    float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
     if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, ws, W, joints, s))) return rc;
     StageTimer t(ST_LBS_FWD, s);
-    return launch_lbs_forward(blob, v_posed, VP_PITCH, bone, B, verts, joints, s);
+    return launch_skin_forward(blob, reinterpret_cast<float*>(ws + W.v_posed_t), reinterpret_cast<float*>(ws + W.bone_t), B,
+                               verts, joints, s);
 }
 
 extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
@@ -326,11 +255,10 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
     int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
     if (rc || B == 0) return rc;
     if (!g_joints || !g_rot || !g_coeffs || !g_betas) return MB_E_NULL;
-    const WorkLayout W = work_layout(B);
+    const WorkLayout W = work_layout(B, mode);
     char* ws = reinterpret_cast<char*>(workspace);
-    float* bone = reinterpret_cast<float*>(ws + W.bone);
-    float* v_posed = reinterpret_cast<float*>(ws + W.v_posed);
-    float* dv_posed = reinterpret_cast<float*>(ws + W.dv_posed);
+    float* bone_t = reinterpret_cast<float*>(ws + W.bone_t);
+    float* v_posed_t = reinterpret_cast<float*>(ws + W.v_posed_t);
     float* dbone = reinterpret_cast<float*>(ws + W.dbone);
     float* dfeat = reinterpret_cast<float*>(ws + W.dfeat);
     if (!(flags & MB_BWD_WORKSPACE_VALID)) {
@@ -338,21 +266,44 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
         float* scratch_joints = dfeat;      // B*63 floats <= B*148
         if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, ws, W, scratch_joints, s))) return rc;
     }
-    unsigned char* dvp = mode == MB_MODE_FP32 ? nullptr : reinterpret_cast<unsigned char*>(ws + W.dvp);
-    { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_lbs_backward(blob, v_posed, VP_PITCH, bone, g_verts, g_joints, B, dvp ? nullptr : dv_posed, dvp, dbone, s))) return rc; }
-    { StageTimer t(ST_BLEND_BWD, s); if ((rc = blend_backward(blob, dv_posed, dvp, dfeat, B, mode, s))) return rc; }
+    if (mode == MB_MODE_FP32) {
+        float* dv_t = reinterpret_cast<float*>(ws + W.dv_t);
+        float* rows = reinterpret_cast<float*>(ws + W.rows);
+        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, nullptr, dbone, s))) return rc; }
+        StageTimer t(ST_BLEND_BWD, s);
+        const BlobLayout L = blob_layout();
+        if ((rc = launch_t_to_rows(blob, dv_t, VP_PITCH, B, rows, s))) return rc;
+        if ((rc = launch_sgemm(rows, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s))) return rc;
+    } else {
+        unsigned char* dvp = reinterpret_cast<unsigned char*>(ws + W.dvp);
+        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, s))) return rc; }
+        StageTimer t(ST_BLEND_BWD, s);        // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
+        if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, s))) return rc;
+    }
     StageTimer t(ST_POSE_BWD, s);
     return launch_pose_backward(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
 }
 
+extern "C" size_t mb_lbs_workspace_bytes(int B) {
+    if (B < 0) return 0;
+    const size_t G = (size_t)((B + 31) / 32);
+    return align256(sizeof(float) * G * NJ * BONE_F * 32) + align256(sizeof(float) * G * SK_NCOORD * 32);
+}
+
 extern "C" int mb_lbs_forward(const void* blob, const float* v_posed, int pitch, const float* bone, int B,
-                              float* verts, float* joints, mb_stream_t stream) {
+                              float* verts, float* joints, void* workspace, size_t workspace_bytes, mb_stream_t stream) {
     if (B < 0 || pitch < NVC || (pitch & 3)) return MB_E_RANGE;
     if (B == 0) return 0;
-    if (!blob || !v_posed || !bone || !verts) return MB_E_NULL;
-    if ((reinterpret_cast<uintptr_t>(verts) & 15) || (reinterpret_cast<uintptr_t>(v_posed) & 15) ||
-        (reinterpret_cast<uintptr_t>(bone) & 15))
-        return MB_E_ALIGN;
-    StageTimer t(ST_LBS_FWD, (cudaStream_t)stream);
-    return launch_lbs_forward(blob, v_posed, pitch, bone, B, verts, joints, (cudaStream_t)stream);
+    if (!blob || !v_posed || !bone || !verts || !workspace) return MB_E_NULL;
+    if (workspace_bytes < mb_lbs_workspace_bytes(B)) return MB_E_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(verts) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15)) return MB_E_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t G = (size_t)((B + 31) / 32);
+    float* bone_t = reinterpret_cast<float*>(workspace);
+    float* v_posed_t = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256(sizeof(float) * G * NJ * BONE_F * 32));
+    int rc;
+    if ((rc = launch_bone_rows_to_t(bone, B, bone_t, s))) return rc;
+    if ((rc = launch_rows_to_t(blob, v_posed, pitch, B, v_posed_t, s))) return rc;
+    StageTimer t(ST_LBS_FWD, s);
+    return launch_skin_forward(blob, v_posed_t, bone_t, B, verts, joints, s);
 }

@@ -2,7 +2,7 @@
 // MB_MODE_F16X3 (fp32-accurate) and MB_MODE_F16 (fast).
 //
 //   v_posed[h][n] = v_template[n] + sum_k f[h][k] * basis[k][n]          (MANOLayer.py:130-137)
-//   f = [beta(10) | vec(R_j - I)(135)], k padded to 160;  n = vertex*3 + coord, 2334 -> 15 tiles of 160
+//   f = [beta(10) | vec(R_j - I)(135)], k padded to 160;  n = block-order coordinate, 2352 -> 15 tiles of 160
 //
 // GEMM mapping: M = 128 hands (TMEM lanes), N = 160 vertex coordinates, K = 160.
 //   * B operand (the basis slice of the CTA's N-tile, 100 KB as fp16 hi+lo) is RESIDENT in shared
@@ -13,8 +13,10 @@
 //     per stage.
 //   * one elected thread issues tcgen05.mma.kind::f16 (fp32 accumulate in TMEM); two accumulator
 //     stages (2 x 160 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
-//   * epilogue warps: tcgen05.ld (lane = hand) -> smem transpose -> add v_template in fp32 ->
-//     128-byte coalesced row stores of v_posed.
+//   * epilogue warps: tcgen05.ld (lane = hand) -> add v_template in fp32 -> straight from registers
+//     into the HAND-MINOR scratch v_posed_t[group][column][32]: a TMEM lane quarter is a hand group,
+//     so every column of a warp is one coalesced 128-byte store and no transposition is needed.
+//     Columns are in the skinning kernels' block order (the basis image is permuted at pack time).
 // fp32 accuracy from fp16 tensor cores: both operands are split x = hi + lo (two fp16, 22
 // significand bits) after a power-of-two pre-scale that keeps lo out of the fp16 subnormals, and
 // three products hi*hi + lo*hi + hi*lo are accumulated in fp32; v_template (the one large term)
@@ -130,7 +132,6 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_
 struct TcShared {
     alignas(128) unsigned char b[TC_B_TILE_BYTES];                  // resident basis tile (hi+lo, 5 chunks)
     alignas(128) unsigned char a[A_STAGES][TC_A_STAGE_BYTES];       // feature ring
-    alignas(16) float stage[EPI_WARPS][32][33];                     // epilogue transposes
     alignas(8) unsigned long long full[A_STAGES], empty[A_STAGES];
     unsigned long long acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
     unsigned long long b_full;
@@ -141,7 +142,7 @@ struct TcShared {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ basis_tc,
                         const float* __restrict__ tmpl, const unsigned char* __restrict__ featp,
-                        float* __restrict__ v_posed, int B, int m_tiles, int products) {
+                        float* __restrict__ v_posed_t, int B, int m_tiles, int products) {
     extern __shared__ unsigned char smem_raw[];
     TcShared& S = *reinterpret_cast<TcShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const float out_scale = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
@@ -222,12 +223,12 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced v_posed rows =====
-        // warp % 4 selects the TMEM lane quarter; warps 4-7 take column chunks 0-2, warps 8-11 chunks 3-4
+        // ===== epilogue: TMEM -> registers -> hand-minor v_posed_t =====
+        // warp % 4 selects the TMEM lane quarter (= one group of 32 hands); warps 4-7 take column
+        // chunks 0-2, warps 8-11 chunks 3-4
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int j_begin = half == 0 ? 0 : 3, j_end = half == 0 ? 3 : TC_N / 32;
-        float (*buf)[33] = S.stage[warp - 4];
         uint32_t acc = 0, acc_phase = 0;
         bool ok = true;
         const int n0 = n_tile * TC_N;
@@ -235,7 +236,8 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
             ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&S.acc_full[acc]), acc_phase, abort_flag));
             if (!ok) break;
             tc_fence_after();
-            const int row0 = m_tile * TC_M + q * 32;
+            const long long group = (long long)m_tile * (TC_M / 32) + q;
+            const bool live = group * 32 < B;                   // whole groups beyond the batch are skipped
 #pragma unroll 1
             for (int j = j_begin; j < j_end; ++j) {
                 float v[32];
@@ -245,19 +247,15 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty[acc]));
                 }
+                const int col0 = n0 + j * 32;
+                const float tv = tmpl[col0 + lane];             // v_template of this chunk's columns (block order, zero padded)
+                if (live) {
+                    float* dst = v_posed_t + ((size_t)group * SK_NCOORD + col0) * 32 + lane;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) buf[lane][c] = v[c];
-                __syncwarp();
-                const int col = n0 + j * 32 + lane;
-                const float tv = col < NVC ? tmpl[col] : 0.f;
-                if (col < VP_PITCH) {
-                    float* dst = v_posed + (size_t)row0 * VP_PITCH + col;
-                    const int nrow = B - row0 < 32 ? B - row0 : 32;
-#pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr)
-                        if (rr < nrow) dst[(size_t)rr * VP_PITCH] = fmaf(buf[rr][lane], out_scale, tv);
+                    for (int c = 0; c < 32; ++c)
+                        if (col0 + c < SK_NCOORD)
+                            __stcs(dst + c * 32, fmaf(v[c], out_scale, __shfl_sync(0xffffffffu, tv, c)));
                 }
-                __syncwarp();
             }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
@@ -418,8 +416,9 @@ static size_t tc_fwd_bytes() { return align256(sizeof(TcBlobHeader)) + align256(
 size_t blend_tc_blob_bytes() { return tc_fwd_bytes() + align256(TCB_B_BYTES); }
 
 // basis [FEAT_K][2334] fp32 -> per n-tile, per K chunk, {hi, lo} blocks in the UMMA canonical
-// K-major layout [row-group][k-group][8 rows][8 halves]; pre-scaled by a power of two.
-void blend_tc_pack(const float* basis, void* host_blob_tc) {
+// K-major layout [row-group][k-group][8 rows][8 halves]; pre-scaled by a power of two.  Columns are in
+// the skinning block order: coord_map[column] = original coordinate (vertex*3+c) or -1 (padding).
+void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob_tc) {
     unsigned char* out = reinterpret_cast<unsigned char*>(host_blob_tc);
     memset(out, 0, blend_tc_blob_bytes());
     TcBlobHeader* H = reinterpret_cast<TcBlobHeader*>(out);
@@ -436,8 +435,8 @@ void blend_tc_pack(const float* basis, void* host_blob_tc) {
         for (int c = 0; c < TC_K_CHUNKS; ++c)
             for (int r = 0; r < TC_N; ++r)
                 for (int kk = 0; kk < TC_K_CHUNK; ++kk) {
-                    const int n = nt * TC_N + r, k = c * TC_K_CHUNK + kk;
-                    float x = (n < NVC && k < TC_K_REAL) ? basis[(size_t)k * NVC + n] * sb : 0.f;
+                    const int n = coord_map[nt * TC_N + r], k = c * TC_K_CHUNK + kk;     // column -> original coordinate
+                    float x = (n >= 0 && k < TC_K_REAL) ? basis[(size_t)k * NVC + n] * sb : 0.f;
                     const __half hi = __float2half_rn(x);
                     const __half lo = __float2half_rn(x - __half2float(hi));
                     const size_t blk = ((size_t)nt * TC_K_CHUNKS + c) * 2;
@@ -446,13 +445,14 @@ void blend_tc_pack(const float* basis, void* host_blob_tc) {
                     dst[(blk + 1) * (TC_B_BLOCK_BYTES / 2) + in] = lo;
                 }
     // backward B operand: basis[n][k] as bf16 hi + mid (unscaled), rows n = feature (160, zero beyond 145),
-    // per K chunk of 32 vertex coordinates: [73][split 2][row-group 20][k-group 4][8 rows][8 bf16]
+    // per K chunk of 32 block-order coordinates: [74][split 2][row-group 20][k-group 4][8 rows][8 bf16]
     __nv_bfloat16* bw = reinterpret_cast<__nv_bfloat16*>(out + tc_fwd_bytes());
     for (int kc = 0; kc < TCB_K_CHUNKS; ++kc)
         for (int r = 0; r < TC_N; ++r)
             for (int kk = 0; kk < TC_K_CHUNK; ++kk) {
-                const int k = kc * TC_K_CHUNK + kk;
-                const float x = (r < TC_K_REAL && k < NVC) ? basis[(size_t)r * NVC + k] : 0.f;
+                const int kcol = kc * TC_K_CHUNK + kk;
+                const int k = kcol < SK_TMPL_PAD ? coord_map[kcol] : -1;
+                const float x = (r < TC_K_REAL && k >= 0) ? basis[(size_t)r * NVC + k] : 0.f;
                 const __nv_bfloat16 hi = __float2bfloat16_rn(x);
                 const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
                 const size_t in = (((size_t)(r >> 3) * (TC_K_CHUNK / 8) + (kk >> 3)) * 8 + (r & 7)) * 8 + (kk & 7);
@@ -478,7 +478,7 @@ int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* 
     return cuda_rc();
 }
 
-int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed, int B, int mode, cudaStream_t s) {
+int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed_t, int B, int mode, cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
     const size_t smem = sizeof(TcShared) + 128;
@@ -492,9 +492,9 @@ int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float*
     const int m_tiles = (B + TC_M - 1) / TC_M;
     const long long total = (long long)TC_N_TILES * m_tiles;
     const int grid = (int)(total < NUM_SMS ? total : NUM_SMS);      // >= 15: every n-tile has at least one CTA
-    const float* tmpl = blob_ptr<float>(blob, L.basis) + (size_t)FEAT_ONE * VP_PITCH;
+    const float* tmpl = blob_ptr<float>(blob, L.sk_tmpl);
     blend_tc_forward_kernel<<<grid, TC_THREADS, smem, s>>>(reinterpret_cast<const TcBlobHeader*>(tc),
-                                                           tc + align256(sizeof(TcBlobHeader)), tmpl, featp, v_posed, B, m_tiles,
+                                                           tc + align256(sizeof(TcBlobHeader)), tmpl, featp, v_posed_t, B, m_tiles,
                                                            mode == MB_MODE_F16X3 ? 3 : 1);
     return cuda_rc();
 }

@@ -40,10 +40,10 @@ __host__ __device__ inline size_t tc_feat_group_offset(long long h, int kg8, int
 
 inline size_t tc_featp_bytes(long long B) { return (size_t)((B + TC_M - 1) / TC_M) * TC_A_TILE_BYTES; }
 
-// ---- backward contraction  dfeat[h][n] = sum_k dv_posed[h][k] * basis[n][k]   (K = 2336 = 73 chunks of 32)
+// ---- backward contraction  dfeat[h][n] = sum_k dv_posed[h][k] * basis[n][k]   (K = 2368 = 74 chunks of 32, block order)
 // A operand: dv_posed as bf16 hi + mid tiles written by the skinning backward kernel, per 128-hand
-// tile [K chunk 73][split 2][8 KB canonical block]; B operand: basis as bf16 hi + mid, [73][2][10 KB].
-constexpr int TCB_K_CHUNKS = VP_PITCH / TC_K_CHUNK;                     // 73
+// tile [K chunk 74][split 2][8 KB canonical block]; B operand: basis as bf16 hi + mid, [74][2][10 KB].
+constexpr int TCB_K_CHUNKS = (SK_NCOORD + TC_K_CHUNK - 1) / TC_K_CHUNK; // 74 (2352 block-order coordinates + 16 zero columns)
 constexpr int TCB_A_CHUNK_BYTES = 2 * TC_A_BLOCK_BYTES;                 // 16 KB: hi + mid of one chunk of one hand tile
 constexpr size_t TCB_A_TILE_BYTES = (size_t)TCB_K_CHUNKS * TCB_A_CHUNK_BYTES;   // 1.17 MB per 128 hands
 constexpr int TCB_B_CHUNK_BYTES = 2 * TC_B_BLOCK_BYTES;                 // 20 KB
@@ -52,6 +52,6 @@ constexpr size_t TCB_B_BYTES = (size_t)TCB_K_CHUNKS * TCB_B_CHUNK_BYTES;
 inline size_t tc_dvp_bytes(long long B) { return (size_t)((B + TC_M - 1) / TC_M) * TCB_A_TILE_BYTES; }
 
 int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, cudaStream_t s);
-int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed, int B, int mode, cudaStream_t s);
+int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed_t, int B, int mode, cudaStream_t s);
 
 }  // namespace mb

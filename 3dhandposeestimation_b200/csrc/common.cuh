@@ -22,11 +22,23 @@ constexpr int MAX_INFL = 8;
 constexpr int BONE_F = 12;        // 3x4 [R|t] per bone
 constexpr int NUM_SMS = 148;
 constexpr int MAX_NNZ = 3200;      // total skinning weights supported
-constexpr int LBS_WARPS = 16;      // warps per CTA of the skinning kernels
-constexpr int LBS_CV = 64;         // vertices per chunk
-constexpr int LBS_CF = LBS_CV * 3; // floats per chunk row
-constexpr int LBS_CHUNKS = (NV + LBS_CV - 1) / LBS_CV;   // 13
-constexpr int LBS_SLOTS = 2;       // bones (or parts of long bones) owned by one warp in the backward reduction
+
+// ---- "skin program" of the register-blocked skinning kernels (skin.cu) -------------------------
+// Vertices are processed in blocks of 8 (24 coordinates held in registers by the lane that owns the
+// hand).  Blocks are formed INSIDE 32-vertex segments of the original order (so a warp's results
+// leave as contiguous 384-byte row pieces) by a host-side greedy that groups vertices with the same
+// bone set; per block the program lists the distinct bones and a dense 8-vector of weights each.
+// The rest-pose scratch v_posed_t is stored in this block order, hand-minor: [group][SK_NCOORD][32].
+constexpr int SK_BV = 8;                                   // vertices per block
+constexpr int SK_BC = SK_BV * 3;                           // coordinates per block
+constexpr int SK_SEG = 32;                                 // vertices per output segment
+constexpr int SK_SEG_BLKS = SK_SEG / SK_BV;                // 4
+constexpr int SK_NSEG = (NV + SK_SEG - 1) / SK_SEG;        // 25
+constexpr int SK_NBLK = (NV + SK_BV - 1) / SK_BV;          // 98 (the last segment has 2 blocks)
+constexpr int SK_NPOS = SK_NBLK * SK_BV;                   // 784 vertex positions (6 padding)
+constexpr int SK_NCOORD = SK_NPOS * 3;                     // 2352 coordinates per hand in block order
+constexpr int SK_MAX_ENT = 512;                            // (block, bone) pairs supported
+constexpr int SK_TMPL_PAD = 2400;                          // v_template in block order, padded to the GEMM's 15 x 160 columns
 
 // Device blob layout (byte offsets, every section 256-byte aligned).
 struct BlobLayout {
@@ -43,14 +55,13 @@ struct BlobLayout {
     size_t csc_ptr;     // int32 [17]      bone -> range in csc_v / csc_w
     size_t csc_v;       // int32 [778*8]   vertex ids grouped by bone
     size_t csc_w;       // float [778*8]
-    // tables of the lane=hand skinning kernels (mano_lbs.cu)
-    size_t csr_ptr;     // int32 [779]     vertex -> range in csr_w / csr_b
-    size_t csr_w;       // float [MAX_NNZ]
-    size_t csr_b;       // uint8 [MAX_NNZ]
-    size_t bseg;        // int32 [LBS_WARPS][LBS_CHUNKS][LBS_SLOTS][2]  entry ranges per (warp, vertex chunk, owned slot)
-    size_t bent_idx;    // uint16 [MAX_NNZ] float index of the entry's vertex inside its chunk
-    size_t bent_w;      // float  [MAX_NNZ]
-    size_t bslot;       // int32 [LBS_WARPS][LBS_SLOTS] owned bone id (-1 = none)
+    // skin program (skin.cu)
+    size_t sk_blk_ptr;  // int32 [SK_NBLK + 1]       block -> range of (block, bone) entries
+    size_t sk_ent_bone; // int32 [SK_MAX_ENT]
+    size_t sk_ent_w;    // float [SK_MAX_ENT][8]     dense weights of the block's 8 vertices for that bone
+    size_t sk_vloc;     // uint8 [SK_NPOS]           position -> vertex index inside its 32-segment (255 = padding)
+    size_t sk_perm;     // int32 [SK_NPOS]           position -> original vertex (-1 = padding)
+    size_t sk_tmpl;     // float [SK_TMPL_PAD]       v_template in block (position) order
     size_t total;
 };
 
@@ -85,41 +96,51 @@ __host__ __device__ inline BlobLayout blob_layout() {
     L.csc_ptr = o;   o = align256(o + sizeof(int32_t) * (NJ + 1));
     L.csc_v = o;     o = align256(o + sizeof(int32_t) * NV * MAX_INFL);
     L.csc_w = o;     o = align256(o + sizeof(float) * NV * MAX_INFL);
-    L.csr_ptr = o;   o = align256(o + sizeof(int32_t) * (NV + 1));
-    L.csr_w = o;     o = align256(o + sizeof(float) * MAX_NNZ);
-    L.csr_b = o;     o = align256(o + MAX_NNZ);
-    L.bseg = o;      o = align256(o + sizeof(int32_t) * LBS_WARPS * LBS_CHUNKS * LBS_SLOTS * 2);
-    L.bent_idx = o;  o = align256(o + sizeof(uint16_t) * MAX_NNZ);
-    L.bent_w = o;    o = align256(o + sizeof(float) * MAX_NNZ);
-    L.bslot = o;     o = align256(o + sizeof(int32_t) * LBS_WARPS * LBS_SLOTS);
+    L.sk_blk_ptr = o;  o = align256(o + sizeof(int32_t) * (SK_NBLK + 1));
+    L.sk_ent_bone = o; o = align256(o + sizeof(int32_t) * SK_MAX_ENT);
+    L.sk_ent_w = o;    o = align256(o + sizeof(float) * SK_MAX_ENT * SK_BV);
+    L.sk_vloc = o;     o = align256(o + SK_NPOS);
+    L.sk_perm = o;     o = align256(o + sizeof(int32_t) * SK_NPOS);
+    L.sk_tmpl = o;     o = align256(o + sizeof(float) * SK_TMPL_PAD);
     L.total = o;
     return L;
 }
 
-// Workspace layout for B hands (byte offsets, 256-byte aligned sections).
+// Workspace layout for B hands (byte offsets, 256-byte aligned sections).  "hand-minor" arrays hold
+// groups of 32 hands with the hand index fastest: x_t[group][element][32].
 struct WorkLayout {
+    size_t bone_t;    // float [G][16*12][32]      bone transforms, hand-minor
+    size_t v_posed_t; // float [G][SK_NCOORD][32]  rest-pose vertices, block order, hand-minor
+    size_t dbone;     // float [B][16][12]         (backward only)
+    size_t dfeat;     // float [B][FEAT_K]         (backward only)
+    // tensor-core modes
+    size_t featp;     // fp16 hi/lo feature tiles: ceil(B/128) * 80 KB
+    size_t dvp;       // bf16 hi/mid dv_posed tiles of the tcgen05 backward: ceil(B/128) * 74 * 16 KB
+    // fp32 anchor mode
     size_t feat;      // float [B][FEAT_K]
-    size_t bone;      // float [B][16][12]
-    size_t v_posed;   // float [B][VP_PITCH]
-    size_t dv_posed;  // ALIASES v_posed: the skinning backward overwrites each row after reading it
-    size_t dbone;     // float [B][16][12]     (backward only)
-    size_t dfeat;     // float [B][FEAT_K]     (backward only)
-    size_t featp;     // fp16 hi/lo feature tiles of the tcgen05 path: ceil(B/128) * 80 KB
-    size_t dvp;       // bf16 hi/mid dv_posed tiles of the tcgen05 backward: ceil(B/128) * 73 * 16 KB
+    size_t rows;      // float [B][VP_PITCH]       sgemm output (v_posed) / input (dv_posed), original vertex order
+    size_t dv_t;      // float [G][SK_NCOORD][32]
     size_t total;
 };
 
-__host__ __device__ inline WorkLayout work_layout(long long B) {
+__host__ __device__ inline WorkLayout work_layout(long long B, int mode) {
     WorkLayout W;
+    const size_t G = (size_t)((B + 31) / 32);
+    const size_t T = (size_t)((B + 127) / 128);
     size_t o = 0;
-    W.feat = o;     o = align256(o + sizeof(float) * B * FEAT_K);
-    W.bone = o;     o = align256(o + sizeof(float) * B * NJ * BONE_F);
-    W.v_posed = o;  o = align256(o + sizeof(float) * B * VP_PITCH);
-    W.dv_posed = W.v_posed;
-    W.dbone = o;    o = align256(o + sizeof(float) * B * NJ * BONE_F);
-    W.dfeat = o;    o = align256(o + sizeof(float) * B * FEAT_K);
-    W.featp = o;    o = align256(o + (size_t)((B + 127) / 128) * 81920);
-    W.dvp = o;      o = align256(o + (size_t)((B + 127) / 128) * (73 * 16384));
+    W.bone_t = o;    o = align256(o + sizeof(float) * G * NJ * BONE_F * 32);
+    W.v_posed_t = o; o = align256(o + sizeof(float) * G * SK_NCOORD * 32);
+    W.dbone = o;     o = align256(o + sizeof(float) * B * NJ * BONE_F);
+    W.dfeat = o;     o = align256(o + sizeof(float) * B * FEAT_K);
+    W.featp = W.dvp = W.feat = W.rows = W.dv_t = o;
+    if (mode == MB_MODE_FP32) {
+        W.feat = o;  o = align256(o + sizeof(float) * B * FEAT_K);
+        W.rows = o;  o = align256(o + sizeof(float) * B * VP_PITCH);
+        W.dv_t = o;  o = align256(o + sizeof(float) * G * SK_NCOORD * 32);
+    } else {
+        W.featp = o; o = align256(o + T * 81920);
+        W.dvp = o;   o = align256(o + T * (74 * 16384));
+    }
     W.total = o;
     return W;
 }
@@ -131,8 +152,9 @@ __host__ __device__ inline const T* blob_ptr(const void* blob, size_t off) {
 
 // ---- kernel launchers implemented in the other translation units ----------
 // feat (fp32 rows) and featp (fp16 hi/lo UMMA tiles) may each be NULL
+// bone_t is hand-minor: bone_t[group][16*12][32]
 int launch_pose_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                        int B, float* feat, unsigned char* featp, float* bone, float* joints, cudaStream_t s);
+                        int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s);
 int launch_pose_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                          const float* dfeat, const float* dbone, const float* g_joints, int B,
                          float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
@@ -144,13 +166,6 @@ int launch_joints_only_backward(const void* blob, int nc, const float* rot, cons
 // C[M][ldc] = A[M][lda] (K cols) * Bm[K][ldb] (N cols), fp32 FFMA
 int launch_sgemm(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc,
                  long long M, int N, int K, cudaStream_t s);
-int launch_lbs_forward(const void* blob, const float* v_posed, int pitch, const float* bone, int B,
-                       float* verts, float* joints, cudaStream_t s);
-// dv_posed (fp32 rows) or dvp (bf16 hi/mid UMMA tiles for the tcgen05 backward): exactly one is non-NULL
-int launch_lbs_backward(const void* blob, const float* v_posed, int pitch, const float* bone,
-                        const float* g_verts, const float* g_joints, int B,
-                        float* dv_posed, unsigned char* dvp, float* dbone, cudaStream_t s);
-
 // launch bookkeeping (api.cu): every kernel launch of this library goes through cuda_rc()
 void count_launch();
 inline int cuda_rc() {

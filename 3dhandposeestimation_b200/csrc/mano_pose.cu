@@ -5,7 +5,7 @@
 //              pose feature (:114-120), folded joint regression (:139-141),
 //              kinematic chain by tree level with parent state fetched by __shfl_sync
 //              (:159-165), rest-pose removal with the global rotation folded in
-//              (:169-175, :188, :204-205)  ->  feat[B][148], bone[B][16][12], joints (chain slots)
+//              (:169-175, :188, :204-205)  ->  feat[B][148], bone_t[B/32][16*12][32], joints (chain slots)
 //   backward:  SURVEY Appendix A.2 steps 3-7 (reverse chain, Rodrigues backward, PCA^T).
 //
 // JOINTS_ONLY variants additionally evaluate the five fingertip vertices
@@ -214,7 +214,7 @@ template <bool JOINTS_ONLY>
 __global__ void __launch_bounds__(WARPS * 32)
 pose_forward_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
                     const float* __restrict__ coeffs, const float* __restrict__ betas, int B,
-                    float* __restrict__ feat, unsigned char* __restrict__ featp, float* __restrict__ bone,
+                    float* __restrict__ feat, unsigned char* __restrict__ featp, float* __restrict__ bone_t,
                     float* __restrict__ joints) {
     __shared__ alignas(16) PoseShared S;
     stage_constants<JOINTS_ONLY>(S, blob, nc);
@@ -253,9 +253,10 @@ pose_forward_kernel(const void* __restrict__ blob, int nc, const float* __restri
                     *reinterpret_cast<uint4*>(featp + tc_feat_group_offset(hand, kg8, sp)) = *reinterpret_cast<const uint4*>(h);
                 }
             }
-            float4* bo = reinterpret_cast<float4*>(bone + hand * (NJ * BONE_F));
-            const float4* bs = reinterpret_cast<const float4*>(S.bone[warp]);
-            for (int i = lane; i < NJ * BONE_F / 4; i += 32) bo[i] = bs[i];
+            // bone transforms leave hand-minor: bone_t[hand / 32][element][hand % 32] (what the
+            // lane = hand skinning kernels load as coalesced 128-byte rows)
+            float* bo = bone_t + (hand >> 5) * (NJ * BONE_F * 32) + (hand & 31);
+            for (int i = lane; i < NJ * BONE_F; i += 32) bo[i * 32] = S.bone[warp][i];
         } else {
             tips_rest_pose(S, S.feat[warp], S.tipv[warp], lane);
             if (lane < NTIP) {

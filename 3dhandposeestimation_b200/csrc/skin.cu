@@ -1,0 +1,607 @@
+// skin.cu — linear blend skinning over 778 vertices x 16 bones, forward and backward,
+// register-blocked with LANE = HAND.
+//
+// Reference: MANOLayer.py:177-185 (T = sum_k w_vk A_k ; v' = T [v_posed;1]), :190-202 (the five
+// fingertip vertices become joints 4,8,12,16,20) and :188,:204-205 (global rotation — already
+// folded into the bone transforms by the pose stage, so it costs nothing here).
+//
+// Round-1 ncu of the previous lane=hand kernel (bones in shared memory, one vertex at a time):
+// l1tex data pipe 76 % busy, 1 321 shared-memory wavefronts per hand — three 16-byte bone rows per
+// (vertex, bone) pair per lane.  This version keeps the bone transform in REGISTERS and amortises
+// it over a block of 8 vertices:
+//   * a warp owns 32 hands (lane = hand) and sweeps all vertices on its own — no block barriers;
+//   * the rest-pose vertices arrive hand-minor (v_posed_t[group][coord][32], written that way by the
+//     blend GEMM's epilogue), so a coordinate of 32 hands is one coalesced 128-byte load and a block
+//     of 8 vertices is 24 registers per lane;
+//   * the host-built skin program lists, per block, its distinct bones and a dense 8-vector of
+//     weights per bone; a bone transform is fetched (12 coalesced loads from the hand-minor bone_t,
+//     L1/L2 hits) once per (block, bone) — 359 times per sweep for MANO instead of 2 028;
+//   * zero weights are skipped by a WARP-UNIFORM branch (weights are shared-memory broadcasts);
+//   * results are transposed through a 12 KB per-warp tile (XOR-swizzled, conflict-free both ways)
+//     and leave as 384-byte row pieces of verts[B][778][3] (8-byte vectors: rows are 8-byte aligned).
+//
+// Backward:  dv_posed_v = sum_k w_vk R'_k^T g_v  and
+// dA'_k = sum_v w_vk g_v (x) [v_posed_v ; 1].  Two warps share a hand group and a g_verts tile:
+// role 0 computes dv_posed (emitted as bf16 hi+mid UMMA tiles for the tcgen05 gradient contraction,
+// or fp32 hand-minor), role 1 accumulates the per-bone 3x4 sums in registers per (block, bone) and
+// folds them into a 24 KB shared accumulator that only it touches — no atomics.
+#include <cuda_bf16.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "blend_tc.cuh"
+#include "skin.cuh"
+
+namespace mb {
+namespace {
+
+constexpr int SEG_F = SK_SEG * 3;                 // 96 floats per segment row piece
+constexpr int TP = 33;                            // tile pitch (floats): element (float f, hand h) at f * 33 + h
+constexpr int TILE_FLOATS = SEG_F * TP;           // 3168 floats = 12.4 KB
+constexpr int GROUP_BONE_FLOATS = NJ * BONE_F * 32;
+constexpr size_t GROUP_V_FLOATS = (size_t)SK_NCOORD * 32;
+constexpr int N_TIP = 5;
+__constant__ int c_tip_vert[N_TIP] = {333, 444, 672, 555, 745};
+__constant__ int c_tip_slot[N_TIP] = {4, 8, 12, 16, 20};
+
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float r;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float2 ld_stream2(const float* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream2(float* p, const float2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream4u(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+
+// shared-memory copy of the skin program (22.7 KB), with the address arithmetic folded in
+struct SkinProg {
+    int blk_ptr[SK_NBLK + 1];
+    int ent_boff[SK_MAX_ENT];                    // bone * 12 * 32: float offset of the bone inside a group of bone_t
+    alignas(16) float ent_w[SK_MAX_ENT][SK_BV];
+    alignas(16) int voff[SK_NPOS];               // float offset of the vertex' x inside a tile: vl * 3 * TP
+};
+constexpr size_t PROG_BYTES = (sizeof(SkinProg) + 127) & ~size_t(127);
+
+__device__ __forceinline__ void stage_prog(SkinProg& P, const void* blob) {
+    const BlobLayout L = blob_layout();
+    const int* bp = blob_ptr<int>(blob, L.sk_blk_ptr);
+    const int* eb = blob_ptr<int>(blob, L.sk_ent_bone);
+    const float* ew = blob_ptr<float>(blob, L.sk_ent_w);
+    const uint8_t* vl = blob_ptr<uint8_t>(blob, L.sk_vloc);
+    for (int i = threadIdx.x; i <= SK_NBLK; i += blockDim.x) P.blk_ptr[i] = bp[i];
+    const int ne = bp[SK_NBLK];
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) P.ent_boff[i] = eb[i] * (BONE_F * 32);
+    for (int i = threadIdx.x; i < ne * SK_BV; i += blockDim.x) (&P.ent_w[0][0])[i] = ew[i];
+    // padding positions (only in the last block, whose segment uses 10 of its 32 vertex slots) are
+    // parked on slot 31 of the tile: written / read like any vertex, never stored, weights all zero
+    for (int i = threadIdx.x; i < SK_NPOS; i += blockDim.x) P.voff[i] = (vl[i] == 255 ? 31 : vl[i]) * (3 * TP);
+}
+
+__device__ __forceinline__ void load_w(const SkinProg& P, int e, float (&w)[SK_BV]) {
+    const float4 w0 = *reinterpret_cast<const float4*>(&P.ent_w[e][0]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&P.ent_w[e][4]);
+    w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+}
+__device__ __forceinline__ void load_voff(const SkinProg& P, int blk, int (&o)[SK_BV]) {
+    const int4 a = *reinterpret_cast<const int4*>(&P.voff[blk * SK_BV]);
+    const int4 b = *reinterpret_cast<const int4*>(&P.voff[blk * SK_BV + 4]);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// ------------------------------------------------------------------ forward
+__device__ __forceinline__ void load_bone(float (&A)[BONE_F], const float* __restrict__ bg, int boff) {
+    const float* bp = bg + boff;
+#pragma unroll
+    for (int i = 0; i < BONE_F; ++i) A[i] = __ldg(bp + i * 32);
+}
+// acc[3j+c] += w_j (A [x_j;1])_c for the vertices of the block with a non-zero weight (warp-uniform test)
+__device__ __forceinline__ void fma_entry(const float (&A)[BONE_F], const float (&w)[SK_BV],
+                                          const float (&x)[SK_BC], float (&acc)[SK_BC]) {
+#pragma unroll
+    for (int j = 0; j < SK_BV; ++j) {
+        if (w[j] != 0.f) {
+            const float X = x[3 * j], Y = x[3 * j + 1], Z = x[3 * j + 2];
+            acc[3 * j]     = fmaf(w[j], fmaf(A[0], X, fmaf(A[1], Y, fmaf(A[2], Z, A[3]))), acc[3 * j]);
+            acc[3 * j + 1] = fmaf(w[j], fmaf(A[4], X, fmaf(A[5], Y, fmaf(A[6], Z, A[7]))), acc[3 * j + 1]);
+            acc[3 * j + 2] = fmaf(w[j], fmaf(A[8], X, fmaf(A[9], Y, fmaf(A[10], Z, A[11]))), acc[3 * j + 2]);
+        }
+    }
+}
+// One block: acc[3j+c] = sum_k w_jk (A_k [x_j;1])_c for the 8 vertices held in x.  bg points at
+// bone_t[group][0][lane].  The bone of entry e+1 is fetched while entry e is computed (two register
+// sets, ping-pong: no copies).
+__device__ __forceinline__ void skin_block_fwd(const SkinProg& P, int blk, const float* __restrict__ bg,
+                                               const float (&x)[SK_BC], float (&acc)[SK_BC]) {
+    int e = P.blk_ptr[blk];
+    const int e1 = P.blk_ptr[blk + 1];
+    if (e >= e1) return;
+    float A0[BONE_F], A1[BONE_F], w[SK_BV];
+    load_bone(A0, bg, P.ent_boff[e]);
+    while (true) {
+        if (e + 1 < e1) load_bone(A1, bg, P.ent_boff[e + 1]);
+        load_w(P, e, w);
+        fma_entry(A0, w, x, acc);
+        if (++e >= e1) break;
+        if (e + 1 < e1) load_bone(A0, bg, P.ent_boff[e + 1]);
+        load_w(P, e, w);
+        fma_entry(A1, w, x, acc);
+        if (++e >= e1) break;
+    }
+}
+
+constexpr int SKF_WARPS = 16;                      // autonomous warps per CTA; 1 CTA per SM
+constexpr int SKF_THREADS = SKF_WARPS * 32;
+constexpr size_t SKF_SMEM = PROG_BYTES + (size_t)SKF_WARPS * TILE_FLOATS * sizeof(float);
+
+__global__ void __launch_bounds__(SKF_THREADS, 1)
+skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed_t,
+                    const float* __restrict__ bone_t, int B, float* __restrict__ verts, float* __restrict__ joints) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
+    stage_prog(P, blob);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = reinterpret_cast<float*>(smem_raw + PROG_BYTES) + warp * TILE_FLOATS;
+    float* tl = tile + lane;                                  // compute side: (f, lane)
+    const int hl = lane >> 4, l15 = lane & 15;
+    const float* ts = tile + (2 * l15) * TP + hl;             // store side: (f = 2*l15 + 32*qb + e, h = 2*rb + hl)
+    const int ngroups = (B + 31) >> 5;
+    for (int g = blockIdx.x + warp * gridDim.x; g < ngroups; g += gridDim.x * SKF_WARPS) {
+        const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
+        const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
+        const float* bg = bone_t + (size_t)g * GROUP_BONE_FLOATS + lane;
+        float* vrow = verts + (size_t)g * 32 * NVC + (size_t)hl * NVC + 2 * l15;
+        for (int seg = 0; seg < SK_NSEG; ++seg) {
+            const int nblk = (seg == SK_NSEG - 1) ? (SK_NBLK - seg * SK_SEG_BLKS) : SK_SEG_BLKS;
+            for (int bi = 0; bi < nblk; ++bi) {
+                const int blk = seg * SK_SEG_BLKS + bi;
+                float x[SK_BC], acc[SK_BC];
+#pragma unroll
+                for (int i = 0; i < SK_BC; ++i) { x[i] = ld_stream(vb + i * 32); acc[i] = 0.f; }
+                vb += SK_BC * 32;
+                skin_block_fwd(P, blk, bg, x, acc);
+                int vo[SK_BV];
+                load_voff(P, blk, vo);
+#pragma unroll
+                for (int j = 0; j < SK_BV; ++j) {
+                    float* t = tl + vo[j];
+                    t[0] = acc[3 * j]; t[TP] = acc[3 * j + 1]; t[2 * TP] = acc[3 * j + 2];
+                }
+            }
+            __syncwarp();
+            // the segment leaves as row pieces: one instruction = 2 rows x 16 float2 (128 B per row)
+            float* dst = vrow + seg * SEG_F;
+            if (nh == 32 && seg != SK_NSEG - 1) {
+#pragma unroll
+                for (int rb = 0; rb < 16; ++rb)
+#pragma unroll
+                    for (int qb = 0; qb < 3; ++qb)
+                        st_stream2(dst + (size_t)rb * 2 * NVC + qb * 32,
+                                   make_float2(ts[(qb * 32) * TP + rb * 2], ts[(qb * 32 + 1) * TP + rb * 2]));
+            } else {
+                const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
+                for (int rb = 0; rb < 16; ++rb)
+                    for (int qb = 0; qb < 3; ++qb)
+                        if (rb * 2 + hl < nh && qb * 32 + 2 * l15 < nf)
+                            st_stream2(dst + (size_t)rb * 2 * NVC + qb * 32,
+                                       make_float2(ts[(qb * 32) * TP + rb * 2], ts[(qb * 32 + 1) * TP + rb * 2]));
+            }
+            if (joints != nullptr && lane < nh) {
+#pragma unroll
+                for (int t = 0; t < N_TIP; ++t)
+                    if (c_tip_vert[t] / SK_SEG == seg) {
+                        const float* tv = tl + (c_tip_vert[t] % SK_SEG) * (3 * TP);
+                        float* o = joints + ((size_t)g * 32 + lane) * (NOUTJ * 3) + c_tip_slot[t] * 3;
+                        o[0] = tv[0]; o[1] = tv[TP]; o[2] = tv[2 * TP];
+                    }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ----------------------------------------------------------------- backward
+constexpr int SKB_PAIRS = 5;
+constexpr int SKB_THREADS = SKB_PAIRS * 64;
+constexpr int DACC_FLOATS = NJ * BONE_F * TP;      // 6336 floats = 24.8 KB: element (e, hand) at e * 33 + hand
+constexpr size_t SKB_SMEM = PROG_BYTES + (size_t)SKB_PAIRS * (TILE_FLOATS + DACC_FLOATS) * sizeof(float);
+
+// gather the upstream gradient of a block's 8 vertices from the segment tile
+__device__ __forceinline__ void gather_block(const SkinProg& P, const float* tl, int blk, float (&gg)[SK_BC]) {
+    int vo[SK_BV];
+    load_voff(P, blk, vo);
+#pragma unroll
+    for (int j = 0; j < SK_BV; ++j) {
+        const float* t = tl + vo[j];
+        gg[3 * j] = t[0]; gg[3 * j + 1] = t[TP]; gg[3 * j + 2] = t[2 * TP];
+    }
+}
+
+__device__ __forceinline__ void load_rot(float (&R)[9], const float* __restrict__ bg, int boff) {
+    const float* bp = bg + boff;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = __ldg(bp + ((i / 3) * 4 + (i % 3)) * 32);
+}
+__device__ __forceinline__ void dv_entry(const float (&R)[9], const float (&w)[SK_BV],
+                                         const float (&gg)[SK_BC], float (&dv)[SK_BC]) {
+#pragma unroll
+    for (int j = 0; j < SK_BV; ++j) {
+        if (w[j] != 0.f) {
+            const float wx = w[j] * gg[3 * j], wy = w[j] * gg[3 * j + 1], wz = w[j] * gg[3 * j + 2];
+            dv[3 * j]     = fmaf(R[0], wx, fmaf(R[3], wy, fmaf(R[6], wz, dv[3 * j])));
+            dv[3 * j + 1] = fmaf(R[1], wx, fmaf(R[4], wy, fmaf(R[7], wz, dv[3 * j + 1])));
+            dv[3 * j + 2] = fmaf(R[2], wx, fmaf(R[5], wy, fmaf(R[8], wz, dv[3 * j + 2])));
+        }
+    }
+}
+// role 0: dv[3j+c] = sum_k w_jk (R_k^T g_j)_c
+__device__ __forceinline__ void skin_block_dv(const SkinProg& P, int blk, const float* __restrict__ bg,
+                                              const float (&gg)[SK_BC], float (&dv)[SK_BC]) {
+    int e = P.blk_ptr[blk];
+    const int e1 = P.blk_ptr[blk + 1];
+    if (e >= e1) return;
+    float R0[9], R1[9], w[SK_BV];
+    load_rot(R0, bg, P.ent_boff[e]);
+    while (true) {
+        if (e + 1 < e1) load_rot(R1, bg, P.ent_boff[e + 1]);
+        load_w(P, e, w);
+        dv_entry(R0, w, gg, dv);
+        if (++e >= e1) break;
+        if (e + 1 < e1) load_rot(R0, bg, P.ent_boff[e + 1]);
+        load_w(P, e, w);
+        dv_entry(R1, w, gg, dv);
+        if (++e >= e1) break;
+    }
+}
+
+// role 1: dacc[k] += sum_j w_jk g_j (x) [v_j ; 1] for every bone k of the block (dl = dacc + lane)
+__device__ __forceinline__ void skin_block_da(const SkinProg& P, int blk, float* dl,
+                                              const float (&gg)[SK_BC], const float (&v)[SK_BC]) {
+    const int e1 = P.blk_ptr[blk + 1];
+    for (int e = P.blk_ptr[blk]; e < e1; ++e) {
+        float w[SK_BV];
+        load_w(P, e, w);
+        float* d = dl + (P.ent_boff[e] >> 5) * TP;
+        float a[BONE_F];
+#pragma unroll
+        for (int i = 0; i < BONE_F; ++i) a[i] = d[i * TP];
+#pragma unroll
+        for (int j = 0; j < SK_BV; ++j) {
+            if (w[j] != 0.f) {
+                const float wx = w[j] * gg[3 * j], wy = w[j] * gg[3 * j + 1], wz = w[j] * gg[3 * j + 2];
+                const float X = v[3 * j], Y = v[3 * j + 1], Z = v[3 * j + 2];
+                a[0] = fmaf(wx, X, a[0]); a[1] = fmaf(wx, Y, a[1]); a[2] = fmaf(wx, Z, a[2]);   a[3] += wx;
+                a[4] = fmaf(wy, X, a[4]); a[5] = fmaf(wy, Y, a[5]); a[6] = fmaf(wy, Z, a[6]);   a[7] += wy;
+                a[8] = fmaf(wz, X, a[8]); a[9] = fmaf(wz, Y, a[9]); a[10] = fmaf(wz, Z, a[10]); a[11] += wz;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BONE_F; ++i) d[i * TP] = a[i];
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+__global__ void __launch_bounds__(SKB_THREADS, 1)
+skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed_t,
+                     const float* __restrict__ bone_t, const float* __restrict__ g_verts,
+                     const float* __restrict__ g_joints, int B,
+                     float* __restrict__ dv_t, unsigned char* __restrict__ dvp, float* __restrict__ dbone) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
+    stage_prog(P, blob);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, role = warp & 1;
+    float* tile = reinterpret_cast<float*>(smem_raw + PROG_BYTES) + pair * (TILE_FLOATS + DACC_FLOATS);
+    float* dacc = tile + TILE_FLOATS;
+    float* tl = tile + lane;
+    const int hl = lane >> 4, l15 = lane & 15;
+    float* tsd = tile + (2 * l15) * TP + hl;                  // load side of the g tile (same mapping as the forward's store side)
+    const int bar = 1 + pair;
+    const int ngroups = (B + 31) >> 5;
+    for (int g = blockIdx.x + pair * gridDim.x; g < ngroups; g += gridDim.x * SKB_PAIRS) {
+        const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
+        const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
+        const float* bg = bone_t + (size_t)g * GROUP_BONE_FLOATS + lane;
+        const float* grow = g_verts + (size_t)g * 32 * NVC + (size_t)hl * NVC + 2 * l15;
+        if (role == 1) {
+#pragma unroll 8
+            for (int i = 0; i < NJ * BONE_F; ++i) dacc[i * TP + lane] = 0.f;
+        } else if (dvp != nullptr) {
+            // zero the 16 padding K columns (2352..2367) of the last chunk of the gradient tiles
+            unsigned char* tb = dvp + (size_t)(g >> 2) * TCB_A_TILE_BYTES + (size_t)(TCB_K_CHUNKS - 1) * TCB_A_CHUNK_BYTES;
+            const int rg = (g & 3) * 4 + (lane >> 3), r = lane & 7;
+#pragma unroll
+            for (int kg = 2; kg < 4; ++kg) {
+                unsigned char* d = tb + ((rg * 4 + kg) * 8 + r) * 16;
+                st_stream4u(d, make_uint4(0, 0, 0, 0));
+                st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(0, 0, 0, 0));
+            }
+        }
+        for (int seg = 0; seg < SK_NSEG; ++seg) {
+            const int nblk = (seg == SK_NSEG - 1) ? (SK_NBLK - seg * SK_SEG_BLKS) : SK_SEG_BLKS;
+            pair_barrier(bar);                                  // both warps are done with the previous tile
+            // each role loads half of the segment's row pieces: one instruction = 2 rows x 16 float2
+            const float* src = grow + seg * SEG_F;
+            if (nh == 32 && seg != SK_NSEG - 1) {
+#pragma unroll
+                for (int rb2 = 0; rb2 < 8; ++rb2) {
+                    const int rb = rb2 * 2 + role;
+                    float2 t[3];
+#pragma unroll
+                    for (int qb = 0; qb < 3; ++qb) t[qb] = ld_stream2(src + (size_t)rb * 2 * NVC + qb * 32);
+#pragma unroll
+                    for (int qb = 0; qb < 3; ++qb) { tsd[(qb * 32) * TP + rb * 2] = t[qb].x; tsd[(qb * 32 + 1) * TP + rb * 2] = t[qb].y; }
+                }
+            } else {
+                const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
+                for (int rb = role; rb < 16; rb += 2)
+                    for (int qb = 0; qb < 3; ++qb)
+                        if (rb * 2 + hl < nh && qb * 32 + 2 * l15 < nf) {
+                            const float2 t = ld_stream2(src + (size_t)rb * 2 * NVC + qb * 32);
+                            tsd[(qb * 32) * TP + rb * 2] = t.x; tsd[(qb * 32 + 1) * TP + rb * 2] = t.y;
+                        }
+            }
+            pair_barrier(bar);                                  // tile complete
+            bool has_tip = false;
+#pragma unroll
+            for (int t = 0; t < N_TIP; ++t) has_tip |= (c_tip_vert[t] / SK_SEG == seg);
+            if (has_tip) {
+                // fingertip joints are vertices: their upstream gradient joins g_verts (A.2 step 1)
+                if (role == 0 && lane < nh) {
+#pragma unroll
+                    for (int t = 0; t < N_TIP; ++t)
+                        if (c_tip_vert[t] / SK_SEG == seg) {
+                            float* tv = tl + (c_tip_vert[t] % SK_SEG) * (3 * TP);
+                            const float* gj = g_joints + ((size_t)g * 32 + lane) * (NOUTJ * 3) + c_tip_slot[t] * 3;
+                            tv[0] += gj[0]; tv[TP] += gj[1]; tv[2 * TP] += gj[2];
+                        }
+                }
+                pair_barrier(bar);
+            }
+            for (int bi = 0; bi < nblk; ++bi) {
+                const int blk = seg * SK_SEG_BLKS + bi;
+                if (role == 0) {
+                    float gg[SK_BC], dv[SK_BC];
+                    gather_block(P, tl, blk, gg);
+#pragma unroll
+                    for (int i = 0; i < SK_BC; ++i) dv[i] = 0.f;
+                    skin_block_dv(P, blk, bg, gg, dv);
+                    if (dvp != nullptr) {
+                        // A operand of the tcgen05 gradient contraction: bf16 hi + mid, UMMA canonical
+                        // K-major blocks; a lane owns a tile row, so 8 consecutive K values are one
+                        // 16-byte group and 8 lanes write one contiguous 128-byte core matrix.
+                        unsigned char* tb = dvp + (size_t)(g >> 2) * TCB_A_TILE_BYTES;
+                        const int rg = (g & 3) * 4 + (lane >> 3), r = lane & 7;
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            uint32_t hi[4], mid[4];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const float a = dv[t * 8 + 2 * p], b = dv[t * 8 + 2 * p + 1];
+                                hi[p] = pack_bf16x2(a, b);
+                                const float ah = __uint_as_float(hi[p] << 16), bh = __uint_as_float(hi[p] & 0xffff0000u);
+                                mid[p] = pack_bf16x2(a - ah, b - bh);
+                            }
+                            const int kg8 = blk * 3 + t;
+                            unsigned char* d = tb + (size_t)(kg8 >> 2) * TCB_A_CHUNK_BYTES + ((rg * 4 + (kg8 & 3)) * 8 + r) * 16;
+                            st_stream4u(d, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                            st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(mid[0], mid[1], mid[2], mid[3]));
+                        }
+                    } else {
+                        float* dg = dv_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * (SK_BC * 32) + lane;
+#pragma unroll
+                        for (int i = 0; i < SK_BC; ++i) st_stream(dg + i * 32, dv[i]);
+                    }
+                } else {
+                    float gg[SK_BC], v[SK_BC];
+#pragma unroll
+                    for (int i = 0; i < SK_BC; ++i) v[i] = ld_stream(vb + (size_t)blk * (SK_BC * 32) + i * 32);
+                    gather_block(P, tl, blk, gg);
+                    skin_block_da(P, blk, dacc + lane, gg, v);
+                }
+            }
+        }
+        if (role == 1) {
+            // per-bone sums of the group leave as dbone[h][16][12] rows (transposed out of the accumulator)
+            __syncwarp();
+            float* drow = dbone + (size_t)g * 32 * (NJ * BONE_F) + lane;
+            const float* da = dacc + lane * TP;
+            for (int h = 0; h < nh; ++h)
+#pragma unroll
+                for (int i = 0; i < NJ * BONE_F / 32; ++i) drow[(size_t)h * (NJ * BONE_F) + 32 * i] = da[(32 * i) * TP + h];
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------- layout conversions (fp32 anchor mode, mb_lbs_forward)
+// rows[B][pitch] (original vertex order) -> t[group][SK_NCOORD][32] (block order, hand-minor)
+__global__ void rows_to_t_kernel(const void* __restrict__ blob, const float* __restrict__ rows, int pitch, int B,
+                                 float* __restrict__ t) {
+    const int* perm = blob_ptr<int>(blob, blob_layout().sk_perm);
+    const long long n = (long long)((B + 31) >> 5) * SK_NCOORD * 32;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i & 31);
+        const long long gc = i >> 5;
+        const int c = (int)(gc % SK_NCOORD);
+        const long long h = (gc / SK_NCOORD) * 32 + lane;
+        const int v = perm[c / 3];
+        t[i] = (v >= 0 && h < B) ? rows[h * pitch + v * 3 + (c % 3)] : 0.f;
+    }
+}
+// inverse: t -> rows[B][pitch]; columns that are no vertex coordinate are zeroed
+__global__ void t_to_rows_kernel(const void* __restrict__ blob, const float* __restrict__ t, int pitch, int B,
+                                 float* __restrict__ rows) {
+    const int* perm = blob_ptr<int>(blob, blob_layout().sk_perm);
+    const long long n = (long long)((B + 31) >> 5) * SK_NCOORD * 32;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i & 31);
+        const long long gc = i >> 5;
+        const int c = (int)(gc % SK_NCOORD);
+        const long long h = (gc / SK_NCOORD) * 32 + lane;
+        const int v = perm[c / 3];
+        if (v >= 0 && h < B) rows[h * pitch + v * 3 + (c % 3)] = t[i];
+        if (c < pitch - NVC && h < B) rows[h * pitch + NVC + c] = 0.f;
+    }
+}
+// bone[B][192] -> bone_t[group][192][32]
+__global__ void bone_rows_to_t_kernel(const float* __restrict__ bone, int B, float* __restrict__ bone_t) {
+    const long long n = (long long)((B + 31) >> 5) * GROUP_BONE_FLOATS;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i & 31);
+        const long long ge = i >> 5;
+        const int e = (int)(ge % (NJ * BONE_F));
+        const long long h = (ge / (NJ * BONE_F)) * 32 + lane;
+        bone_t[i] = h < B ? bone[h * (NJ * BONE_F) + e] : 0.f;
+    }
+}
+
+inline int conv_grid(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = (long long)NUM_SMS * 16;
+    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host: skin program
+// Greedy grouping inside each 32-vertex segment: start a block with the vertex that has the most
+// bones, then keep adding the vertex that enlarges the block's bone set least.
+int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32_t* coord_map) {
+    const BlobLayout L = blob_layout();
+    char* out = reinterpret_cast<char*>(host_blob);
+    int* blk_ptr = reinterpret_cast<int*>(out + L.sk_blk_ptr);
+    int* ent_bone = reinterpret_cast<int*>(out + L.sk_ent_bone);
+    float* ent_w = reinterpret_cast<float*>(out + L.sk_ent_w);
+    uint8_t* vloc = reinterpret_cast<uint8_t*>(out + L.sk_vloc);
+    int* perm = reinterpret_cast<int*>(out + L.sk_perm);
+
+    std::vector<unsigned> mask(NV, 0u);
+    std::vector<float> dense((size_t)NV * NJ, 0.f);
+    for (int v = 0; v < NV; ++v)
+        for (int s = 0; s < MAX_INFL; ++s) {
+            const float w = skin_w[v * MAX_INFL + s];
+            const int b = skin_b[v * MAX_INFL + s];
+            if (w == 0.f) continue;
+            if (b < 0 || b >= NJ) return MB_E_MODEL;
+            mask[v] |= 1u << b;
+            dense[(size_t)v * NJ + b] += w;
+        }
+    auto pop = [](unsigned x) { return __builtin_popcount(x); };
+    int nblk = 0, ne = 0;
+    for (int seg = 0; seg < SK_NSEG; ++seg) {
+        std::vector<int> rem;
+        for (int v = seg * SK_SEG; v < NV && v < (seg + 1) * SK_SEG; ++v) rem.push_back(v);
+        while (!rem.empty()) {
+            size_t bi = 0;
+            for (size_t i = 1; i < rem.size(); ++i)
+                if (pop(mask[rem[i]]) > pop(mask[rem[bi]])) bi = i;
+            int grp[SK_BV];
+            int n = 0;
+            unsigned u = mask[rem[bi]];
+            grp[n++] = rem[bi];
+            rem.erase(rem.begin() + bi);
+            while (n < SK_BV && !rem.empty()) {
+                size_t best = 0;
+                for (size_t i = 1; i < rem.size(); ++i) {
+                    const int gi = pop(mask[rem[i]] & ~u), gb = pop(mask[rem[best]] & ~u);
+                    if (gi < gb || (gi == gb && pop(mask[rem[i]] & u) > pop(mask[rem[best]] & u))) best = i;
+                }
+                u |= mask[rem[best]];
+                grp[n++] = rem[best];
+                rem.erase(rem.begin() + best);
+            }
+            std::sort(grp, grp + n);
+            if (nblk >= SK_NBLK) return MB_E_MODEL;
+            blk_ptr[nblk] = ne;
+            for (int j = 0; j < SK_BV; ++j) {
+                perm[nblk * SK_BV + j] = j < n ? grp[j] : -1;
+                vloc[nblk * SK_BV + j] = j < n ? (uint8_t)(grp[j] - seg * SK_SEG) : (uint8_t)255;
+            }
+            for (int k = 0; k < NJ; ++k) {
+                if (!(u & (1u << k))) continue;
+                if (ne >= SK_MAX_ENT) return MB_E_MODEL;
+                ent_bone[ne] = k;
+                for (int j = 0; j < SK_BV; ++j) ent_w[ne * SK_BV + j] = j < n ? dense[(size_t)grp[j] * NJ + k] : 0.f;
+                ++ne;
+            }
+            ++nblk;
+        }
+    }
+    if (nblk != SK_NBLK) return MB_E_MODEL;
+    blk_ptr[SK_NBLK] = ne;
+    for (int c = 0; c < SK_TMPL_PAD; ++c) {
+        const int p = c / 3;
+        coord_map[c] = (p < SK_NPOS && perm[p] >= 0) ? perm[p] * 3 + c % 3 : -1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- launchers
+int launch_skin_forward(const void* blob, const float* v_posed_t, const float* bone_t, int B,
+                        float* verts, float* joints, cudaStream_t s) {
+    if (B <= 0) return 0;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(skin_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKF_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const int ngroups = (B + 31) >> 5;     // small batches spread one group per SM before warps double up
+    skin_forward_kernel<<<ngroups < NUM_SMS ? ngroups : NUM_SMS, SKF_THREADS, SKF_SMEM, s>>>(blob, v_posed_t, bone_t, B, verts, joints);
+    return cuda_rc();
+}
+
+int launch_skin_backward(const void* blob, const float* v_posed_t, const float* bone_t, const float* g_verts,
+                         const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, cudaStream_t s) {
+    if (B <= 0) return 0;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(skin_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKB_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const int ngroups = (B + 31) >> 5;
+    skin_backward_kernel<<<ngroups < NUM_SMS ? ngroups : NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(blob, v_posed_t, bone_t, g_verts, g_joints,
+                                                                                       B, dv_t, dvp, dbone);
+    return cuda_rc();
+}
+
+int launch_rows_to_t(const void* blob, const float* rows, int pitch, int B, float* t, cudaStream_t s) {
+    if (B <= 0) return 0;
+    const long long n = (long long)((B + 31) >> 5) * SK_NCOORD * 32;
+    rows_to_t_kernel<<<conv_grid(n), 256, 0, s>>>(blob, rows, pitch, B, t);
+    return cuda_rc();
+}
+int launch_t_to_rows(const void* blob, const float* t, int pitch, int B, float* rows, cudaStream_t s) {
+    if (B <= 0) return 0;
+    const long long n = (long long)((B + 31) >> 5) * SK_NCOORD * 32;
+    t_to_rows_kernel<<<conv_grid(n), 256, 0, s>>>(blob, t, pitch, B, rows);
+    return cuda_rc();
+}
+int launch_bone_rows_to_t(const float* bone, int B, float* bone_t, cudaStream_t s) {
+    if (B <= 0) return 0;
+    const long long n = (long long)((B + 31) >> 5) * GROUP_BONE_FLOATS;
+    bone_rows_to_t_kernel<<<conv_grid(n), 256, 0, s>>>(bone, B, bone_t);
+    return cuda_rc();
+}
+
+}  // namespace mb

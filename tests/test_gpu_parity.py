@@ -216,8 +216,10 @@ def test_lbs_stage_alone(pkg, synth_model, cuda_device):
     tvp, tbone = to_dev(cuda_device, vp, bone)
     verts = torch.empty(B, 778, 3, device=cuda_device)
     joints = torch.zeros(B, 21, 3, device=cuda_device)
+    ws = torch.empty(lib.mb_lbs_workspace_bytes(B), dtype=torch.uint8, device=cuda_device)
     pkg._cabi.check(lib.mb_lbs_forward(layer._blob.data_ptr(), tvp.data_ptr(), 2336, tbone.data_ptr(), B,
-                                       verts.data_ptr(), joints.data_ptr(), pkg._cabi.stream_handle(cuda_device)), "lbs")
+                                       verts.data_ptr(), joints.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       pkg._cabi.stream_handle(cuda_device)), "lbs")
     W = synth_model["weights"].astype(np.float32).astype(np.float64)
     T = np.einsum("vk,bkij->bvij", W, bone.astype(np.float64))
     x = vp[:, :2334].reshape(B, 778, 3).astype(np.float64)
@@ -225,7 +227,9 @@ def test_lbs_stage_alone(pkg, synth_model, cuda_device):
     assert np.abs(verts.cpu().numpy() - want).max() < 2e-6
     assert np.abs(joints.cpu().numpy()[:, [4, 8, 12, 16, 20]] - want[:, [333, 444, 672, 555, 745]]).max() < 2e-6
     assert lib.mb_lbs_forward(layer._blob.data_ptr(), tvp.data_ptr(), 2334, tbone.data_ptr(), B,
-                              verts.data_ptr(), None, None) == -2
+                              verts.data_ptr(), None, ws.data_ptr(), ws.numel(), None) == -2
+    assert lib.mb_lbs_forward(layer._blob.data_ptr(), tvp.data_ptr(), 2336, tbone.data_ptr(), B,
+                              verts.data_ptr(), None, ws.data_ptr(), 16, None) == -3
 
 
 # ------------------------------------------------------------------------------- FK
