@@ -25,15 +25,15 @@ constexpr int MAX_NNZ = 3200;      // total skinning weights supported
 
 // ---- "skin program" of the register-blocked skinning kernels (skin.cu) -------------------------
 // Vertices are processed in blocks of 8 (24 coordinates held in registers by the lane that owns the
-// hand).  Blocks are formed INSIDE 32-vertex segments of the original order (so a warp's results
-// leave as contiguous 384-byte row pieces) by a host-side greedy that groups vertices with the same
+// hand).  Blocks are formed INSIDE 16-vertex segments of the original order (so a warp's results
+// leave as contiguous 192-byte row pieces) by a host-side greedy that groups vertices with the same
 // bone set; per block the program lists the distinct bones and a dense 8-vector of weights each.
 // The rest-pose scratch v_posed_t is stored in this block order, hand-minor: [group][SK_NCOORD][32].
 constexpr int SK_BV = 8;                                   // vertices per block
 constexpr int SK_BC = SK_BV * 3;                           // coordinates per block
-constexpr int SK_SEG = 32;                                 // vertices per output segment
-constexpr int SK_SEG_BLKS = SK_SEG / SK_BV;                // 4
-constexpr int SK_NSEG = (NV + SK_SEG - 1) / SK_SEG;        // 25
+constexpr int SK_SEG = 16;                                 // vertices per output segment
+constexpr int SK_SEG_BLKS = SK_SEG / SK_BV;                // 2
+constexpr int SK_NSEG = (NV + SK_SEG - 1) / SK_SEG;        // 49
 constexpr int SK_NBLK = (NV + SK_BV - 1) / SK_BV;          // 98 (the last segment has 2 blocks)
 constexpr int SK_NPOS = SK_NBLK * SK_BV;                   // 784 vertex positions (6 padding)
 constexpr int SK_NCOORD = SK_NPOS * 3;                     // 2352 coordinates per hand in block order
@@ -59,7 +59,7 @@ struct BlobLayout {
     size_t sk_blk_ptr;  // int32 [SK_NBLK + 1]       block -> range of (block, bone) entries
     size_t sk_ent_bone; // int32 [SK_MAX_ENT]
     size_t sk_ent_w;    // float [SK_MAX_ENT][8]     dense weights of the block's 8 vertices for that bone
-    size_t sk_vloc;     // uint8 [SK_NPOS]           position -> vertex index inside its 32-segment (255 = padding)
+    size_t sk_vloc;     // uint8 [SK_NPOS]           position -> vertex index inside its 16-segment (255 = padding)
     size_t sk_perm;     // int32 [SK_NPOS]           position -> original vertex (-1 = padding)
     size_t sk_tmpl;     // float [SK_TMPL_PAD]       v_template in block (position) order
     size_t total;

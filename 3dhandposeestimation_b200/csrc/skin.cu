@@ -32,13 +32,16 @@
 #include "common.cuh"
 #include "blend_tc.cuh"
 #include "skin.cuh"
+#include "ptx.cuh"
 
 namespace mb {
 namespace {
 
-constexpr int SEG_F = SK_SEG * 3;                 // 96 floats per segment row piece
+constexpr int SEG_F = SK_SEG * 3;                 // 48 floats per segment row piece
 constexpr int TP = 33;                            // tile pitch (floats): element (float f, hand h) at f * 33 + h
-constexpr int TILE_FLOATS = SEG_F * TP;           // 3168 floats = 12.4 KB
+constexpr int TILE_FLOATS = SEG_F * TP;           // 1584 floats = 6.2 KB
+constexpr int XBLK_FLOATS = SK_BC * 32;           // one block of rest-pose coordinates of a hand group: 3 KB, contiguous
+constexpr int PAD_SLOT = SK_SEG - 1;
 constexpr int GROUP_BONE_FLOATS = NJ * BONE_F * 32;
 constexpr size_t GROUP_V_FLOATS = (size_t)SK_NCOORD * 32;
 constexpr int N_TIP = 5;
@@ -85,9 +88,9 @@ __device__ __forceinline__ void stage_prog(SkinProg& P, const void* blob) {
     const int ne = bp[SK_NBLK];
     for (int i = threadIdx.x; i < ne; i += blockDim.x) P.ent_boff[i] = eb[i] * (BONE_F * 32);
     for (int i = threadIdx.x; i < ne * SK_BV; i += blockDim.x) (&P.ent_w[0][0])[i] = ew[i];
-    // padding positions (only in the last block, whose segment uses 10 of its 32 vertex slots) are
-    // parked on slot 31 of the tile: written / read like any vertex, never stored, weights all zero
-    for (int i = threadIdx.x; i < SK_NPOS; i += blockDim.x) P.voff[i] = (vl[i] == 255 ? 31 : vl[i]) * (3 * TP);
+    // padding positions (only in the last block, whose segment uses 10 of its 16 vertex slots) are
+    // parked on the last slot of the tile: written / read like any vertex, never stored, weights all zero
+    for (int i = threadIdx.x; i < SK_NPOS; i += blockDim.x) P.voff[i] = (vl[i] == 255 ? PAD_SLOT : vl[i]) * (3 * TP);
 }
 
 __device__ __forceinline__ void load_w(const SkinProg& P, int e, float (&w)[SK_BV]) {
@@ -144,34 +147,85 @@ __device__ __forceinline__ void skin_block_fwd(const SkinProg& P, int blk, const
 
 constexpr int SKF_WARPS = 16;                      // autonomous warps per CTA; 1 CTA per SM
 constexpr int SKF_THREADS = SKF_WARPS * 32;
-constexpr size_t SKF_SMEM = PROG_BYTES + (size_t)SKF_WARPS * TILE_FLOATS * sizeof(float);
+constexpr int XSTAGES = 2;                         // per-warp ring of rest-pose blocks filled by the bulk-copy engine
+struct alignas(128) FwdWarpShared {
+    alignas(128) float xring[XSTAGES][XBLK_FLOATS];
+    alignas(16) float tile[TILE_FLOATS];
+    alignas(8) unsigned long long full[XSTAGES];
+};
+constexpr size_t SKF_SMEM = PROG_BYTES + (size_t)SKF_WARPS * sizeof(FwdWarpShared);
+
+// Row pieces of a 16-vertex segment <-> tile: one warp instruction covers 4 rows x 8 float2 (64 B per row).
+// lane -> (r = lane >> 3, p = lane & 7); piece block qb (0..2), row block rb (0..7):
+//   float f = 16 qb + 2 p + e, hand h = 4 rb + r   ->  tile[f * TP + h]
+struct RowMap {
+    int r, p;
+    __device__ __forceinline__ RowMap(int lane) : r(lane >> 3), p(lane & 7) {}
+    __device__ __forceinline__ int tile_base() const { return (2 * p) * TP + r; }
+    __device__ __forceinline__ size_t row_base() const { return (size_t)r * NVC + 2 * p; }
+};
 
 __global__ void __launch_bounds__(SKF_THREADS, 1)
 skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed_t,
                     const float* __restrict__ bone_t, int B, float* __restrict__ verts, float* __restrict__ joints) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FwdWarpShared& W = reinterpret_cast<FwdWarpShared*>(smem_raw + PROG_BYTES)[warp];
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < XSTAGES; ++s) mbar_init(smem_u32(&W.full[s]), 1);
+        fence_barrier_init();
+    }
     stage_prog(P, blob);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = reinterpret_cast<float*>(smem_raw + PROG_BYTES) + warp * TILE_FLOATS;
-    float* tl = tile + lane;                                  // compute side: (f, lane)
-    const int hl = lane >> 4, l15 = lane & 15;
-    const float* ts = tile + (2 * l15) * TP + hl;             // store side: (f = 2*l15 + 32*qb + e, h = 2*rb + hl)
+    float* tl = W.tile + lane;                                // compute side: (f, lane)
+    const RowMap rm(lane);
+    const float* ts = W.tile + rm.tile_base();                // store side
     const int ngroups = (B + 31) >> 5;
-    for (int g = blockIdx.x + warp * gridDim.x; g < ngroups; g += gridDim.x * SKF_WARPS) {
+    const int g0 = blockIdx.x + warp * gridDim.x, gstep = gridDim.x * SKF_WARPS;
+
+    // rest-pose blocks stream through the ring: the copy of block n+2 is issued as soon as block n
+    // has been read into registers, across group boundaries
+    int pg = g0, pblk = 0;                                    // next block to request
+    unsigned issued = 0, consumed = 0;
+    auto request = [&]() {
+        if (pg < ngroups) {
+            if (lane == 0) {
+                const uint32_t bar = smem_u32(&W.full[issued % XSTAGES]);
+                mbar_expect_tx(bar, XBLK_FLOATS * 4);
+                bulk_g2s(smem_u32(W.xring[issued % XSTAGES]), v_posed_t + (size_t)pg * GROUP_V_FLOATS + (size_t)pblk * XBLK_FLOATS,
+                         XBLK_FLOATS * 4, bar);
+            }
+            ++issued;
+            if (++pblk == SK_NBLK) { pblk = 0; pg += gstep; }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < XSTAGES; ++s) request();
+
+    for (int g = g0; g < ngroups; g += gstep) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
-        const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
         const float* bg = bone_t + (size_t)g * GROUP_BONE_FLOATS + lane;
-        float* vrow = verts + (size_t)g * 32 * NVC + (size_t)hl * NVC + 2 * l15;
+        float* vrow = verts + (size_t)g * 32 * NVC + rm.row_base();
         for (int seg = 0; seg < SK_NSEG; ++seg) {
             const int nblk = (seg == SK_NSEG - 1) ? (SK_NBLK - seg * SK_SEG_BLKS) : SK_SEG_BLKS;
             for (int bi = 0; bi < nblk; ++bi) {
                 const int blk = seg * SK_SEG_BLKS + bi;
                 float x[SK_BC], acc[SK_BC];
+                {
+                    const unsigned st = consumed % XSTAGES;
+                    const uint32_t bar = smem_u32(&W.full[st]);
+                    const uint32_t parity = (consumed / XSTAGES) & 1;
+                    long long spins = 0;
+                    while (!mbar_try_wait(bar, parity)) { if (++spins > (1LL << 26)) __trap(); }
+                    const float* xs = W.xring[st] + lane;
 #pragma unroll
-                for (int i = 0; i < SK_BC; ++i) { x[i] = ld_stream(vb + i * 32); acc[i] = 0.f; }
-                vb += SK_BC * 32;
+                    for (int i = 0; i < SK_BC; ++i) { x[i] = xs[i * 32]; acc[i] = 0.f; }
+                    ++consumed;
+                    __syncwarp();                             // every lane has its copy: the slot can be refilled
+                    request();
+                }
                 skin_block_fwd(P, blk, bg, x, acc);
                 int vo[SK_BV];
                 load_voff(P, blk, vo);
@@ -182,22 +236,22 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
                 }
             }
             __syncwarp();
-            // the segment leaves as row pieces: one instruction = 2 rows x 16 float2 (128 B per row)
+            // the segment leaves as 192-byte row pieces
             float* dst = vrow + seg * SEG_F;
             if (nh == 32 && seg != SK_NSEG - 1) {
 #pragma unroll
-                for (int rb = 0; rb < 16; ++rb)
+                for (int rb = 0; rb < 8; ++rb)
 #pragma unroll
                     for (int qb = 0; qb < 3; ++qb)
-                        st_stream2(dst + (size_t)rb * 2 * NVC + qb * 32,
-                                   make_float2(ts[(qb * 32) * TP + rb * 2], ts[(qb * 32 + 1) * TP + rb * 2]));
+                        st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
+                                   make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]));
             } else {
                 const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
-                for (int rb = 0; rb < 16; ++rb)
+                for (int rb = 0; rb < 8; ++rb)
                     for (int qb = 0; qb < 3; ++qb)
-                        if (rb * 2 + hl < nh && qb * 32 + 2 * l15 < nf)
-                            st_stream2(dst + (size_t)rb * 2 * NVC + qb * 32,
-                                       make_float2(ts[(qb * 32) * TP + rb * 2], ts[(qb * 32 + 1) * TP + rb * 2]));
+                        if (rb * 4 + rm.r < nh && qb * 16 + 2 * rm.p < nf)
+                            st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
+                                       make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]));
             }
             if (joints != nullptr && lane < nh) {
 #pragma unroll
@@ -214,7 +268,7 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
 }
 
 // ----------------------------------------------------------------- backward
-constexpr int SKB_PAIRS = 5;
+constexpr int SKB_PAIRS = 6;
 constexpr int SKB_THREADS = SKB_PAIRS * 64;
 constexpr int DACC_FLOATS = NJ * BONE_F * TP;      // 6336 floats = 24.8 KB: element (e, hand) at e * 33 + hand
 constexpr size_t SKB_SMEM = PROG_BYTES + (size_t)SKB_PAIRS * (TILE_FLOATS + DACC_FLOATS) * sizeof(float);
@@ -312,15 +366,15 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
     float* tile = reinterpret_cast<float*>(smem_raw + PROG_BYTES) + pair * (TILE_FLOATS + DACC_FLOATS);
     float* dacc = tile + TILE_FLOATS;
     float* tl = tile + lane;
-    const int hl = lane >> 4, l15 = lane & 15;
-    float* tsd = tile + (2 * l15) * TP + hl;                  // load side of the g tile (same mapping as the forward's store side)
+    const RowMap rm(lane);
+    float* tsd = tile + rm.tile_base();                       // load side of the g tile (same mapping as the forward's store side)
     const int bar = 1 + pair;
     const int ngroups = (B + 31) >> 5;
     for (int g = blockIdx.x + pair * gridDim.x; g < ngroups; g += gridDim.x * SKB_PAIRS) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
         const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
         const float* bg = bone_t + (size_t)g * GROUP_BONE_FLOATS + lane;
-        const float* grow = g_verts + (size_t)g * 32 * NVC + (size_t)hl * NVC + 2 * l15;
+        const float* grow = g_verts + (size_t)g * 32 * NVC + rm.row_base();
         if (role == 1) {
 #pragma unroll 8
             for (int i = 0; i < NJ * BONE_F; ++i) dacc[i * TP + lane] = 0.f;
@@ -338,25 +392,25 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
         for (int seg = 0; seg < SK_NSEG; ++seg) {
             const int nblk = (seg == SK_NSEG - 1) ? (SK_NBLK - seg * SK_SEG_BLKS) : SK_SEG_BLKS;
             pair_barrier(bar);                                  // both warps are done with the previous tile
-            // each role loads half of the segment's row pieces: one instruction = 2 rows x 16 float2
+            // each role loads half of the segment's row pieces: one instruction = 4 rows x 8 float2
             const float* src = grow + seg * SEG_F;
             if (nh == 32 && seg != SK_NSEG - 1) {
 #pragma unroll
-                for (int rb2 = 0; rb2 < 8; ++rb2) {
+                for (int rb2 = 0; rb2 < 4; ++rb2) {
                     const int rb = rb2 * 2 + role;
                     float2 t[3];
 #pragma unroll
-                    for (int qb = 0; qb < 3; ++qb) t[qb] = ld_stream2(src + (size_t)rb * 2 * NVC + qb * 32);
+                    for (int qb = 0; qb < 3; ++qb) t[qb] = ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16);
 #pragma unroll
-                    for (int qb = 0; qb < 3; ++qb) { tsd[(qb * 32) * TP + rb * 2] = t[qb].x; tsd[(qb * 32 + 1) * TP + rb * 2] = t[qb].y; }
+                    for (int qb = 0; qb < 3; ++qb) { tsd[(qb * 16) * TP + rb * 4] = t[qb].x; tsd[(qb * 16 + 1) * TP + rb * 4] = t[qb].y; }
                 }
             } else {
                 const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
-                for (int rb = role; rb < 16; rb += 2)
+                for (int rb = role; rb < 8; rb += 2)
                     for (int qb = 0; qb < 3; ++qb)
-                        if (rb * 2 + hl < nh && qb * 32 + 2 * l15 < nf) {
-                            const float2 t = ld_stream2(src + (size_t)rb * 2 * NVC + qb * 32);
-                            tsd[(qb * 32) * TP + rb * 2] = t.x; tsd[(qb * 32 + 1) * TP + rb * 2] = t.y;
+                        if (rb * 4 + rm.r < nh && qb * 16 + 2 * rm.p < nf) {
+                            const float2 t = ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16);
+                            tsd[(qb * 16) * TP + rb * 4] = t.x; tsd[(qb * 16 + 1) * TP + rb * 4] = t.y;
                         }
             }
             pair_barrier(bar);                                  // tile complete
