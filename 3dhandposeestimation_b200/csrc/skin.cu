@@ -38,8 +38,9 @@ namespace mb {
 namespace {
 
 constexpr int SEG_F = SK_SEG * 3;                 // 48 floats per segment row piece
-constexpr int TP = 33;                            // tile pitch (floats): element (float f, hand h) at f * 33 + h
-constexpr int TILE_FLOATS = SEG_F * TP;           // 1584 floats = 6.2 KB
+constexpr int TP = 34;                            // tile pitch (floats): element (float f, hand h) at f * 34 + h; conflict-free for
+                                                  // lane = hand (compute side) and for the 4 rows x 8 float2 row-piece mapping
+constexpr int TILE_FLOATS = SEG_F * TP;           // 1632 floats = 6.4 KB
 constexpr int XBLK_FLOATS = SK_BC * 32;           // one block of rest-pose coordinates of a hand group: 3 KB, contiguous
 constexpr int PAD_SLOT = SK_SEG - 1;
 constexpr int GROUP_BONE_FLOATS = NJ * BONE_F * 32;
@@ -72,7 +73,8 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 // shared-memory copy of the skin program (22.7 KB), with the address arithmetic folded in
 struct SkinProg {
     int blk_ptr[SK_NBLK + 1];
-    int ent_boff[SK_MAX_ENT];                    // bone * 12 * 32: float offset of the bone inside a group of bone_t
+    int ent_code[SK_MAX_ENT];                    // bits 0-15: bone * 12 * 32 = float offset of the bone inside a group of
+                                                 // bone_t; bits 16-23: which of the block's 8 vertices have a non-zero weight
     alignas(16) float ent_w[SK_MAX_ENT][SK_BV];
     alignas(16) int voff[SK_NPOS];               // float offset of the vertex' x inside a tile: vl * 3 * TP
 };
@@ -86,7 +88,11 @@ __device__ __forceinline__ void stage_prog(SkinProg& P, const void* blob) {
     const uint8_t* vl = blob_ptr<uint8_t>(blob, L.sk_vloc);
     for (int i = threadIdx.x; i <= SK_NBLK; i += blockDim.x) P.blk_ptr[i] = bp[i];
     const int ne = bp[SK_NBLK];
-    for (int i = threadIdx.x; i < ne; i += blockDim.x) P.ent_boff[i] = eb[i] * (BONE_F * 32);
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+        int mask = 0;
+        for (int j = 0; j < SK_BV; ++j) mask |= (ew[i * SK_BV + j] != 0.f) << j;
+        P.ent_code[i] = eb[i] * (BONE_F * 32) | (mask << 16);
+    }
     for (int i = threadIdx.x; i < ne * SK_BV; i += blockDim.x) (&P.ent_w[0][0])[i] = ew[i];
     // padding positions (only in the last block, whose segment uses 10 of its 16 vertex slots) are
     // parked on the last slot of the tile: written / read like any vertex, never stored, weights all zero
@@ -104,54 +110,85 @@ __device__ __forceinline__ void load_voff(const SkinProg& P, int blk, int (&o)[S
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
-// ------------------------------------------------------------------ forward
-__device__ __forceinline__ void load_bone(float (&A)[BONE_F], const float* __restrict__ bg, int boff) {
-    const float* bp = bg + boff;
+// ------------------------------------------------------------------ bulk-copy rings
+// Everything a sweep reads is contiguous per item and its order is static: a block of rest-pose
+// coordinates of a hand group is 24 rows x 128 B = 3 KB of v_posed_t, the bone transform of an entry is
+// 12 rows x 128 B = 1.5 KB of bone_t, and the entry list is the program.  Each warp therefore lets the
+// bulk-copy (TMA) engine stream both into small shared-memory rings, several items ahead of their
+// use and across block and group boundaries, completing on per-slot mbarriers: global-memory and L2
+// latency (there is no L1 to speak of — shared memory takes the whole carve-out) never reaches the
+// register scoreboard.  [round-1 ncu: with register prefetch one entry ahead half of all stall
+// samples were long-scoreboard waits on the first use of a bone or coordinate]
+template <int STAGES, int SLOT_FLOATS>
+struct alignas(128) Ring {
+    alignas(128) float slot[STAGES][SLOT_FLOATS];
+    alignas(8) unsigned long long full[STAGES];
+    __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int i = 0; i < BONE_F; ++i) A[i] = __ldg(bp + i * 32);
+        for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&full[s]), 1);
+    }
+};
+struct Cursor {               // per-warp stream position; every lane keeps an identical copy
+    int g, i;                 // next item to request: group g, item i of n
+    unsigned issued, consumed;
+};
+// request the next item of the stream (no-op once the warp's groups are exhausted); src(g, i) is its address
+template <int STAGES, int SLOT_FLOATS, class SrcFn>
+__device__ __forceinline__ void ring_request(Ring<STAGES, SLOT_FLOATS>& R, Cursor& C, int ngroups, int gstep, int n, int lane,
+                                             SrcFn src) {
+    if (C.g >= ngroups) return;
+    if (lane == 0) {
+        const unsigned st = C.issued % STAGES;
+        const uint32_t bar = smem_u32(&R.full[st]);
+        mbar_expect_tx(bar, SLOT_FLOATS * 4);
+        bulk_g2s(smem_u32(R.slot[st]), src(C.g, C.i), SLOT_FLOATS * 4, bar);
+    }
+    ++C.issued;
+    if (++C.i == n) { C.i = 0; C.g += gstep; }
 }
-// acc[3j+c] += w_j (A [x_j;1])_c for the vertices of the block with a non-zero weight (warp-uniform test)
-__device__ __forceinline__ void fma_entry(const float (&A)[BONE_F], const float (&w)[SK_BV],
-                                          const float (&x)[SK_BC], float (&acc)[SK_BC]) {
+// wait for the oldest outstanding item; returns its slot
+template <int STAGES, int SLOT_FLOATS>
+__device__ __forceinline__ const float* ring_wait(Ring<STAGES, SLOT_FLOATS>& R, const Cursor& C) {
+    const unsigned st = C.consumed % STAGES;
+    const uint32_t bar = smem_u32(&R.full[st]);
+    const uint32_t parity = (C.consumed / STAGES) & 1;
+    while (!mbar_try_wait(bar, parity)) {}
+    return R.slot[st];
+}
+
+constexpr int BSTAGES = 4;
+constexpr int XSTAGES = 2;
+constexpr int BONE_SLOT_FLOATS = BONE_F * 32;
+typedef Ring<BSTAGES, BONE_SLOT_FLOATS> BoneRing;
+typedef Ring<XSTAGES, XBLK_FLOATS> XRing;
+
+// ------------------------------------------------------------------ forward
+// Packed fp32 (FFMA2, sm_100): two vertices of the block per instruction, the bone element is the
+// broadcast scalar operand.  X[c][m] = coordinate c of vertices (2m, 2m+1).  Every entry is
+// computed DENSE over the block's 8 vertices (zero weights contribute exact zeros): with the packed
+// instruction that is 48 FFMA2 per entry, fewer issue slots than the skip-if-zero variant spent on
+// tests, branches and reconvergence barriers alone, and it is straight-line code.
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+__device__ __forceinline__ void fma_entry2(const float (&A)[BONE_F], const float (&w)[SK_BV],
+                                           const float2 (&X)[3][4], float2 (&ACC)[3][4]) {
 #pragma unroll
-    for (int j = 0; j < SK_BV; ++j) {
-        if (w[j] != 0.f) {
-            const float X = x[3 * j], Y = x[3 * j + 1], Z = x[3 * j + 2];
-            acc[3 * j]     = fmaf(w[j], fmaf(A[0], X, fmaf(A[1], Y, fmaf(A[2], Z, A[3]))), acc[3 * j]);
-            acc[3 * j + 1] = fmaf(w[j], fmaf(A[4], X, fmaf(A[5], Y, fmaf(A[6], Z, A[7]))), acc[3 * j + 1]);
-            acc[3 * j + 2] = fmaf(w[j], fmaf(A[8], X, fmaf(A[9], Y, fmaf(A[10], Z, A[11]))), acc[3 * j + 2]);
+    for (int m = 0; m < 4; ++m) {
+        const float2 wp = make_float2(w[2 * m], w[2 * m + 1]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float2 t = __ffma2_rn(X[2][m], bc(A[4 * c + 2]), bc(A[4 * c + 3]));
+            t = __ffma2_rn(X[1][m], bc(A[4 * c + 1]), t);
+            t = __ffma2_rn(X[0][m], bc(A[4 * c]), t);
+            ACC[c][m] = __ffma2_rn(wp, t, ACC[c][m]);
         }
     }
 }
-// One block: acc[3j+c] = sum_k w_jk (A_k [x_j;1])_c for the 8 vertices held in x.  bg points at
-// bone_t[group][0][lane].  The bone of entry e+1 is fetched while entry e is computed (two register
-// sets, ping-pong: no copies).
-__device__ __forceinline__ void skin_block_fwd(const SkinProg& P, int blk, const float* __restrict__ bg,
-                                               const float (&x)[SK_BC], float (&acc)[SK_BC]) {
-    int e = P.blk_ptr[blk];
-    const int e1 = P.blk_ptr[blk + 1];
-    if (e >= e1) return;
-    float A0[BONE_F], A1[BONE_F], w[SK_BV];
-    load_bone(A0, bg, P.ent_boff[e]);
-    while (true) {
-        if (e + 1 < e1) load_bone(A1, bg, P.ent_boff[e + 1]);
-        load_w(P, e, w);
-        fma_entry(A0, w, x, acc);
-        if (++e >= e1) break;
-        if (e + 1 < e1) load_bone(A0, bg, P.ent_boff[e + 1]);
-        load_w(P, e, w);
-        fma_entry(A1, w, x, acc);
-        if (++e >= e1) break;
-    }
-}
-
-constexpr int SKF_WARPS = 16;                      // autonomous warps per CTA; 1 CTA per SM
+constexpr int SKF_WARPS = 10;                      // autonomous warps per CTA; 1 CTA per SM
 constexpr int SKF_THREADS = SKF_WARPS * 32;
-constexpr int XSTAGES = 2;                         // per-warp ring of rest-pose blocks filled by the bulk-copy engine
 struct alignas(128) FwdWarpShared {
-    alignas(128) float xring[XSTAGES][XBLK_FLOATS];
+    BoneRing bones;
+    XRing xs;
     alignas(16) float tile[TILE_FLOATS];
-    alignas(8) unsigned long long full[XSTAGES];
 };
 constexpr size_t SKF_SMEM = PROG_BYTES + (size_t)SKF_WARPS * sizeof(FwdWarpShared);
 
@@ -165,6 +202,26 @@ struct RowMap {
     __device__ __forceinline__ size_t row_base() const { return (size_t)r * NVC + 2 * p; }
 };
 
+__device__ __forceinline__ void load_xblock(float (&x)[SK_BC], const float* __restrict__ vb) {
+#pragma unroll
+    for (int i = 0; i < SK_BC; ++i) x[i] = ld_stream(vb + i * 32);
+}
+// block of 8 vertices as packed pairs: X[c][m] = (x_{2m,c}, x_{2m+1,c}), straight from global memory ...
+__device__ __forceinline__ void load_xpairs(float2 (&X)[3][4], const float* __restrict__ vb) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            X[c][m] = make_float2(ld_stream(vb + (6 * m + c) * 32), ld_stream(vb + (6 * m + 3 + c) * 32));
+}
+// ... or out of a ring slot
+__device__ __forceinline__ void slot_to_pairs(float2 (&X)[3][4], const float* sl) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) X[c][m] = make_float2(sl[(6 * m + c) * 32], sl[(6 * m + 3 + c) * 32]);
+}
+
 __global__ void __launch_bounds__(SKF_THREADS, 1)
 skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed_t,
                     const float* __restrict__ bone_t, int B, float* __restrict__ verts, float* __restrict__ joints) {
@@ -173,8 +230,8 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FwdWarpShared& W = reinterpret_cast<FwdWarpShared*>(smem_raw + PROG_BYTES)[warp];
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < XSTAGES; ++s) mbar_init(smem_u32(&W.full[s]), 1);
+        W.bones.init();
+        W.xs.init();
         fence_barrier_init();
     }
     stage_prog(P, blob);
@@ -184,55 +241,52 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
     const float* ts = W.tile + rm.tile_base();                // store side
     const int ngroups = (B + 31) >> 5;
     const int g0 = blockIdx.x + warp * gridDim.x, gstep = gridDim.x * SKF_WARPS;
-
-    // rest-pose blocks stream through the ring: the copy of block n+2 is issued as soon as block n
-    // has been read into registers, across group boundaries
-    int pg = g0, pblk = 0;                                    // next block to request
-    unsigned issued = 0, consumed = 0;
-    auto request = [&]() {
-        if (pg < ngroups) {
-            if (lane == 0) {
-                const uint32_t bar = smem_u32(&W.full[issued % XSTAGES]);
-                mbar_expect_tx(bar, XBLK_FLOATS * 4);
-                bulk_g2s(smem_u32(W.xring[issued % XSTAGES]), v_posed_t + (size_t)pg * GROUP_V_FLOATS + (size_t)pblk * XBLK_FLOATS,
-                         XBLK_FLOATS * 4, bar);
-            }
-            ++issued;
-            if (++pblk == SK_NBLK) { pblk = 0; pg += gstep; }
-        }
-    };
+    const int ne = P.blk_ptr[SK_NBLK];
+    auto bone_src = [&](int g, int e) { return bone_t + (size_t)g * GROUP_BONE_FLOATS + (P.ent_code[e] & 0xffff); };
+    auto x_src = [&](int g, int blk) { return v_posed_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * XBLK_FLOATS; };
+    Cursor CB = {g0, 0, 0u, 0u}, CX = {g0, 0, 0u, 0u};
 #pragma unroll
-    for (int s = 0; s < XSTAGES; ++s) request();
+    for (int s = 0; s < BSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
+#pragma unroll
+    for (int s = 0; s < XSTAGES; ++s) ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src);
 
     for (int g = g0; g < ngroups; g += gstep) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
-        const float* bg = bone_t + (size_t)g * GROUP_BONE_FLOATS + lane;
         float* vrow = verts + (size_t)g * 32 * NVC + rm.row_base();
         for (int seg = 0; seg < SK_NSEG; ++seg) {
-            const int nblk = (seg == SK_NSEG - 1) ? (SK_NBLK - seg * SK_SEG_BLKS) : SK_SEG_BLKS;
-            for (int bi = 0; bi < nblk; ++bi) {
+#pragma unroll 1
+            for (int bi = 0; bi < SK_SEG_BLKS; ++bi) {
                 const int blk = seg * SK_SEG_BLKS + bi;
-                float x[SK_BC], acc[SK_BC];
-                {
-                    const unsigned st = consumed % XSTAGES;
-                    const uint32_t bar = smem_u32(&W.full[st]);
-                    const uint32_t parity = (consumed / XSTAGES) & 1;
-                    long long spins = 0;
-                    while (!mbar_try_wait(bar, parity)) { if (++spins > (1LL << 26)) __trap(); }
-                    const float* xs = W.xring[st] + lane;
+                float2 X[3][4], ACC[3][4];
+                slot_to_pairs(X, ring_wait(W.xs, CX) + lane);
+                ++CX.consumed;
+                __syncwarp();                                 // every lane has its copy: the slot can be refilled
+                ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src);
 #pragma unroll
-                    for (int i = 0; i < SK_BC; ++i) { x[i] = xs[i * 32]; acc[i] = 0.f; }
-                    ++consumed;
-                    __syncwarp();                             // every lane has its copy: the slot can be refilled
-                    request();
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) ACC[c][m] = make_float2(0.f, 0.f);
+                const int e1 = P.blk_ptr[blk + 1];
+#pragma unroll 1
+                for (int e = P.blk_ptr[blk]; e < e1; ++e) {
+                    float A[BONE_F], w[SK_BV];
+                    load_w(P, e, w);
+                    const float* sl = ring_wait(W.bones, CB) + lane;
+#pragma unroll
+                    for (int i = 0; i < BONE_F; ++i) A[i] = sl[i * 32];
+                    ++CB.consumed;
+                    __syncwarp();
+                    ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
+                    fma_entry2(A, w, X, ACC);
                 }
-                skin_block_fwd(P, blk, bg, x, acc);
                 int vo[SK_BV];
                 load_voff(P, blk, vo);
 #pragma unroll
-                for (int j = 0; j < SK_BV; ++j) {
-                    float* t = tl + vo[j];
-                    t[0] = acc[3 * j]; t[TP] = acc[3 * j + 1]; t[2 * TP] = acc[3 * j + 2];
+                for (int m = 0; m < 4; ++m) {
+                    float* t0 = tl + vo[2 * m];
+                    float* t1 = tl + vo[2 * m + 1];
+                    t0[0] = ACC[0][m].x; t0[TP] = ACC[1][m].x; t0[2 * TP] = ACC[2][m].x;
+                    t1[0] = ACC[0][m].y; t1[TP] = ACC[1][m].y; t1[2 * TP] = ACC[2][m].y;
                 }
             }
             __syncwarp();
@@ -268,82 +322,71 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
 }
 
 // ----------------------------------------------------------------- backward
-constexpr int SKB_PAIRS = 6;
+constexpr int SKB_PAIRS = 5;
 constexpr int SKB_THREADS = SKB_PAIRS * 64;
-constexpr int DACC_FLOATS = NJ * BONE_F * TP;      // 6336 floats = 24.8 KB: element (e, hand) at e * 33 + hand
-constexpr size_t SKB_SMEM = PROG_BYTES + (size_t)SKB_PAIRS * (TILE_FLOATS + DACC_FLOATS) * sizeof(float);
+constexpr int DP = 33;                             // accumulator pitch: element (e, hand) at e * 33 + hand
+struct alignas(128) BwdPairShared {
+    BoneRing bones;                                          // role 0
+    alignas(16) float tile[TILE_FLOATS];                     // upstream gradient of one 16-vertex segment, transposed
+    alignas(16) float dacc[NJ * BONE_F * DP];                // per-bone 3x4 sums of the group (role 1 only)
+};
+constexpr size_t SKB_SMEM = PROG_BYTES + (size_t)SKB_PAIRS * sizeof(BwdPairShared);
 
-// gather the upstream gradient of a block's 8 vertices from the segment tile
-__device__ __forceinline__ void gather_block(const SkinProg& P, const float* tl, int blk, float (&gg)[SK_BC]) {
+// gather the upstream gradient of a block's 8 vertices from the segment tile as packed pairs:
+// G[c][m] = (g_{2m,c}, g_{2m+1,c})
+__device__ __forceinline__ void gather_block(const SkinProg& P, const float* tl, int blk, float2 (&G)[3][4]) {
     int vo[SK_BV];
     load_voff(P, blk, vo);
 #pragma unroll
-    for (int j = 0; j < SK_BV; ++j) {
-        const float* t = tl + vo[j];
-        gg[3 * j] = t[0]; gg[3 * j + 1] = t[TP]; gg[3 * j + 2] = t[2 * TP];
+    for (int m = 0; m < 4; ++m) {
+        const float* t0 = tl + vo[2 * m];
+        const float* t1 = tl + vo[2 * m + 1];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) G[c][m] = make_float2(t0[c * TP], t1[c * TP]);
     }
 }
 
-__device__ __forceinline__ void load_rot(float (&R)[9], const float* __restrict__ bg, int boff) {
-    const float* bp = bg + boff;
+// role 0: DV[c][m] += w (R^T g)_c for the vertex pairs of the block, dense (FFMA2); A holds the first
+// 11 elements of the 3x4 transform (R = A[0..2], A[4..6], A[8..10])
+__device__ __forceinline__ void dv_entry2(const float (&A)[11], const float (&w)[SK_BV],
+                                          const float2 (&G)[3][4], float2 (&DV)[3][4]) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = __ldg(bp + ((i / 3) * 4 + (i % 3)) * 32);
-}
-__device__ __forceinline__ void dv_entry(const float (&R)[9], const float (&w)[SK_BV],
-                                         const float (&gg)[SK_BC], float (&dv)[SK_BC]) {
+    for (int m = 0; m < 4; ++m) {
+        const float2 wp = make_float2(w[2 * m], w[2 * m + 1]);
+        const float2 wx = __fmul2_rn(wp, G[0][m]), wy = __fmul2_rn(wp, G[1][m]), wz = __fmul2_rn(wp, G[2][m]);
 #pragma unroll
-    for (int j = 0; j < SK_BV; ++j) {
-        if (w[j] != 0.f) {
-            const float wx = w[j] * gg[3 * j], wy = w[j] * gg[3 * j + 1], wz = w[j] * gg[3 * j + 2];
-            dv[3 * j]     = fmaf(R[0], wx, fmaf(R[3], wy, fmaf(R[6], wz, dv[3 * j])));
-            dv[3 * j + 1] = fmaf(R[1], wx, fmaf(R[4], wy, fmaf(R[7], wz, dv[3 * j + 1])));
-            dv[3 * j + 2] = fmaf(R[2], wx, fmaf(R[5], wy, fmaf(R[8], wz, dv[3 * j + 2])));
-        }
-    }
-}
-// role 0: dv[3j+c] = sum_k w_jk (R_k^T g_j)_c
-__device__ __forceinline__ void skin_block_dv(const SkinProg& P, int blk, const float* __restrict__ bg,
-                                              const float (&gg)[SK_BC], float (&dv)[SK_BC]) {
-    int e = P.blk_ptr[blk];
-    const int e1 = P.blk_ptr[blk + 1];
-    if (e >= e1) return;
-    float R0[9], R1[9], w[SK_BV];
-    load_rot(R0, bg, P.ent_boff[e]);
-    while (true) {
-        if (e + 1 < e1) load_rot(R1, bg, P.ent_boff[e + 1]);
-        load_w(P, e, w);
-        dv_entry(R0, w, gg, dv);
-        if (++e >= e1) break;
-        if (e + 1 < e1) load_rot(R0, bg, P.ent_boff[e + 1]);
-        load_w(P, e, w);
-        dv_entry(R1, w, gg, dv);
-        if (++e >= e1) break;
+        for (int c = 0; c < 3; ++c)
+            DV[c][m] = __ffma2_rn(wx, bc(A[c]), __ffma2_rn(wy, bc(A[4 + c]), __ffma2_rn(wz, bc(A[8 + c]), DV[c][m])));
     }
 }
 
-// role 1: dacc[k] += sum_j w_jk g_j (x) [v_j ; 1] for every bone k of the block (dl = dacc + lane)
+// role 1: dacc[k] += sum_j w_jk g_j (x) [v_j ; 1] for every bone k of the block (dl = dacc + lane);
+// even / odd vertices accumulate in the two halves of packed registers and are added at the end
 __device__ __forceinline__ void skin_block_da(const SkinProg& P, int blk, float* dl,
-                                              const float (&gg)[SK_BC], const float (&v)[SK_BC]) {
+                                              const float2 (&G)[3][4], const float2 (&V)[3][4]) {
     const int e1 = P.blk_ptr[blk + 1];
+#pragma unroll 1
     for (int e = P.blk_ptr[blk]; e < e1; ++e) {
         float w[SK_BV];
         load_w(P, e, w);
-        float* d = dl + (P.ent_boff[e] >> 5) * TP;
-        float a[BONE_F];
+        float* d = dl + ((P.ent_code[e] & 0xffff) >> 5) * DP;
+        float2 a[BONE_F];
 #pragma unroll
-        for (int i = 0; i < BONE_F; ++i) a[i] = d[i * TP];
+        for (int i = 0; i < BONE_F; ++i) a[i] = make_float2(d[i * DP], 0.f);
 #pragma unroll
-        for (int j = 0; j < SK_BV; ++j) {
-            if (w[j] != 0.f) {
-                const float wx = w[j] * gg[3 * j], wy = w[j] * gg[3 * j + 1], wz = w[j] * gg[3 * j + 2];
-                const float X = v[3 * j], Y = v[3 * j + 1], Z = v[3 * j + 2];
-                a[0] = fmaf(wx, X, a[0]); a[1] = fmaf(wx, Y, a[1]); a[2] = fmaf(wx, Z, a[2]);   a[3] += wx;
-                a[4] = fmaf(wy, X, a[4]); a[5] = fmaf(wy, Y, a[5]); a[6] = fmaf(wy, Z, a[6]);   a[7] += wy;
-                a[8] = fmaf(wz, X, a[8]); a[9] = fmaf(wz, Y, a[9]); a[10] = fmaf(wz, Z, a[10]); a[11] += wz;
+        for (int m = 0; m < 4; ++m) {
+            const float2 wp = make_float2(w[2 * m], w[2 * m + 1]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float2 wg = __fmul2_rn(wp, G[r][m]);
+                a[4 * r]     = __ffma2_rn(wg, V[0][m], a[4 * r]);
+                a[4 * r + 1] = __ffma2_rn(wg, V[1][m], a[4 * r + 1]);
+                a[4 * r + 2] = __ffma2_rn(wg, V[2][m], a[4 * r + 2]);
+                a[4 * r + 3] = __fadd2_rn(a[4 * r + 3], wg);
             }
         }
 #pragma unroll
-        for (int i = 0; i < BONE_F; ++i) d[i * TP] = a[i];
+        for (int i = 0; i < BONE_F; ++i) d[i * DP] = a[i].x + a[i].y;
     }
 }
 
@@ -359,59 +402,141 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                      float* __restrict__ dv_t, unsigned char* __restrict__ dvp, float* __restrict__ dbone) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
-    stage_prog(P, blob);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = warp >> 1, role = warp & 1;
-    float* tile = reinterpret_cast<float*>(smem_raw + PROG_BYTES) + pair * (TILE_FLOATS + DACC_FLOATS);
-    float* dacc = tile + TILE_FLOATS;
-    float* tl = tile + lane;
+    BwdPairShared& W = reinterpret_cast<BwdPairShared*>(smem_raw + PROG_BYTES)[pair];
+    if (role == 0 && lane == 0) {
+        W.bones.init();
+        fence_barrier_init();
+    }
+    stage_prog(P, blob);
+    __syncthreads();
+    float* tl = W.tile + lane;
     const RowMap rm(lane);
-    float* tsd = tile + rm.tile_base();                       // load side of the g tile (same mapping as the forward's store side)
+    float* tsd = W.tile + rm.tile_base();                     // load side of the g tile (same mapping as the forward's store side)
     const int bar = 1 + pair;
     const int ngroups = (B + 31) >> 5;
-    for (int g = blockIdx.x + pair * gridDim.x; g < ngroups; g += gridDim.x * SKB_PAIRS) {
+    const int g0 = blockIdx.x + pair * gridDim.x, gstep = gridDim.x * SKB_PAIRS;
+    const int ne = P.blk_ptr[SK_NBLK];
+    auto bone_src = [&](int g, int e) { return bone_t + (size_t)g * GROUP_BONE_FLOATS + (P.ent_code[e] & 0xffff); };
+    Cursor CB = {g0, 0, 0u, 0u};
+    if (role == 0) {
+#pragma unroll
+        for (int s = 0; s < BSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
+    }
+
+    for (int g = g0; g < ngroups; g += gstep) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
         const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
-        const float* bg = bone_t + (size_t)g * GROUP_BONE_FLOATS + lane;
         const float* grow = g_verts + (size_t)g * 32 * NVC + rm.row_base();
-        if (role == 1) {
-#pragma unroll 8
-            for (int i = 0; i < NJ * BONE_F; ++i) dacc[i * TP + lane] = 0.f;
-        } else if (dvp != nullptr) {
-            // zero the 16 padding K columns (2352..2367) of the last chunk of the gradient tiles
-            unsigned char* tb = dvp + (size_t)(g >> 2) * TCB_A_TILE_BYTES + (size_t)(TCB_K_CHUNKS - 1) * TCB_A_CHUNK_BYTES;
-            const int rg = (g & 3) * 4 + (lane >> 3), r = lane & 7;
-#pragma unroll
-            for (int kg = 2; kg < 4; ++kg) {
-                unsigned char* d = tb + ((rg * 4 + kg) * 8 + r) * 16;
-                st_stream4u(d, make_uint4(0, 0, 0, 0));
-                st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(0, 0, 0, 0));
-            }
-        }
-        for (int seg = 0; seg < SK_NSEG; ++seg) {
-            const int nblk = (seg == SK_NSEG - 1) ? (SK_NBLK - seg * SK_SEG_BLKS) : SK_SEG_BLKS;
-            pair_barrier(bar);                                  // both warps are done with the previous tile
-            // each role loads half of the segment's row pieces: one instruction = 4 rows x 8 float2
+        // each role loads half of a segment's row pieces (one instruction = 4 rows x 8 float2) into
+        // registers one segment ahead of its use
+        float2 pre[4][3];
+        auto prefetch_g = [&](int seg) {
+            const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
             const float* src = grow + seg * SEG_F;
-            if (nh == 32 && seg != SK_NSEG - 1) {
 #pragma unroll
-                for (int rb2 = 0; rb2 < 4; ++rb2) {
-                    const int rb = rb2 * 2 + role;
-                    float2 t[3];
+            for (int rb2 = 0; rb2 < 4; ++rb2) {
+                const int rb = rb2 * 2 + role;
 #pragma unroll
-                    for (int qb = 0; qb < 3; ++qb) t[qb] = ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16);
+                for (int qb = 0; qb < 3; ++qb) {
+                    const bool ok = (rb * 4 + rm.r < nh) && (qb * 16 + 2 * rm.p < nf);
+                    pre[rb2][qb] = ok ? ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16) : make_float2(0.f, 0.f);
+                }
+            }
+        };
+        prefetch_g(0);
+        float2 va[3][4], vbk[3][4];                           // role 1: rest-pose blocks (packed pairs), loaded one block ahead
+        if (role == 0) {
+            if (dvp != nullptr) {
+                // zero the 16 padding K columns (2352..2367) of the last chunk of the gradient tiles
+                unsigned char* tb = dvp + (size_t)(g >> 2) * TCB_A_TILE_BYTES + (size_t)(TCB_K_CHUNKS - 1) * TCB_A_CHUNK_BYTES;
+                const int rg = (g & 3) * 4 + (lane >> 3), r = lane & 7;
 #pragma unroll
-                    for (int qb = 0; qb < 3; ++qb) { tsd[(qb * 16) * TP + rb * 4] = t[qb].x; tsd[(qb * 16 + 1) * TP + rb * 4] = t[qb].y; }
+                for (int kg = 2; kg < 4; ++kg) {
+                    unsigned char* d = tb + ((rg * 4 + kg) * 8 + r) * 16;
+                    st_stream4u(d, make_uint4(0, 0, 0, 0));
+                    st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(0, 0, 0, 0));
+                }
+            }
+        } else {
+            load_xpairs(va, vb);
+#pragma unroll 8
+            for (int i = 0; i < NJ * BONE_F; ++i) W.dacc[i * DP + lane] = 0.f;
+        }
+
+        // role 0, one block: dv_posed of its 8 vertices -> gradient tiles (or fp32 hand-minor)
+        auto dv_block = [&](int blk) {
+            float2 G[3][4], DV[3][4];
+            gather_block(P, tl, blk, G);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) DV[c][m] = make_float2(0.f, 0.f);
+            const int e1 = P.blk_ptr[blk + 1];
+#pragma unroll 1
+            for (int e = P.blk_ptr[blk]; e < e1; ++e) {
+                float A[11], w[SK_BV];
+                load_w(P, e, w);
+                {
+                    const float* sl = ring_wait(W.bones, CB) + lane;
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) A[i] = sl[i * 32];
+                    ++CB.consumed;
+                    __syncwarp();
+                    ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
+                }
+                dv_entry2(A, w, G, DV);
+            }
+            float dv[SK_BC];                                    // block order: dv[3j + c]
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { dv[6 * m + c] = DV[c][m].x; dv[6 * m + 3 + c] = DV[c][m].y; }
+            if (dvp != nullptr) {
+                // A operand of the tcgen05 gradient contraction: bf16 hi + mid, UMMA canonical K-major
+                // blocks; a lane owns a tile row, so 8 consecutive K values are one 16-byte group and
+                // 8 lanes write one contiguous 128-byte core matrix.
+                unsigned char* tb = dvp + (size_t)(g >> 2) * TCB_A_TILE_BYTES;
+                const int rg = (g & 3) * 4 + (lane >> 3), r = lane & 7;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    uint32_t hi[4], mid[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float a = dv[t * 8 + 2 * p], b = dv[t * 8 + 2 * p + 1];
+                        hi[p] = pack_bf16x2(a, b);
+                        const float ah = __uint_as_float(hi[p] << 16), bh = __uint_as_float(hi[p] & 0xffff0000u);
+                        mid[p] = pack_bf16x2(a - ah, b - bh);
+                    }
+                    const int kg8 = blk * 3 + t;
+                    unsigned char* d = tb + (size_t)(kg8 >> 2) * TCB_A_CHUNK_BYTES + ((rg * 4 + (kg8 & 3)) * 8 + r) * 16;
+                    st_stream4u(d, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                    st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(mid[0], mid[1], mid[2], mid[3]));
                 }
             } else {
-                const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
-                for (int rb = role; rb < 8; rb += 2)
-                    for (int qb = 0; qb < 3; ++qb)
-                        if (rb * 4 + rm.r < nh && qb * 16 + 2 * rm.p < nf) {
-                            const float2 t = ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16);
-                            tsd[(qb * 16) * TP + rb * 4] = t.x; tsd[(qb * 16 + 1) * TP + rb * 4] = t.y;
-                        }
+                float* dg = dv_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * XBLK_FLOATS + lane;
+#pragma unroll
+                for (int i = 0; i < SK_BC; ++i) st_stream(dg + i * 32, dv[i]);
+            }
+        };
+        // role 1, one block: per-bone sums
+        auto da_block = [&](int blk, const float2 (&V)[3][4]) {
+            float2 G[3][4];
+            gather_block(P, tl, blk, G);
+            skin_block_da(P, blk, W.dacc + lane, G, V);
+        };
+
+        for (int seg = 0; seg < SK_NSEG; ++seg) {
+            pair_barrier(bar);                                  // both warps are done with the previous tile
+#pragma unroll
+            for (int rb2 = 0; rb2 < 4; ++rb2) {
+                const int rb = rb2 * 2 + role;
+#pragma unroll
+                for (int qb = 0; qb < 3; ++qb) {
+                    tsd[(qb * 16) * TP + rb * 4] = pre[rb2][qb].x;
+                    tsd[(qb * 16 + 1) * TP + rb * 4] = pre[rb2][qb].y;
+                }
             }
             pair_barrier(bar);                                  // tile complete
             bool has_tip = false;
@@ -430,57 +555,25 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                 }
                 pair_barrier(bar);
             }
-            for (int bi = 0; bi < nblk; ++bi) {
-                const int blk = seg * SK_SEG_BLKS + bi;
-                if (role == 0) {
-                    float gg[SK_BC], dv[SK_BC];
-                    gather_block(P, tl, blk, gg);
-#pragma unroll
-                    for (int i = 0; i < SK_BC; ++i) dv[i] = 0.f;
-                    skin_block_dv(P, blk, bg, gg, dv);
-                    if (dvp != nullptr) {
-                        // A operand of the tcgen05 gradient contraction: bf16 hi + mid, UMMA canonical
-                        // K-major blocks; a lane owns a tile row, so 8 consecutive K values are one
-                        // 16-byte group and 8 lanes write one contiguous 128-byte core matrix.
-                        unsigned char* tb = dvp + (size_t)(g >> 2) * TCB_A_TILE_BYTES;
-                        const int rg = (g & 3) * 4 + (lane >> 3), r = lane & 7;
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            uint32_t hi[4], mid[4];
-#pragma unroll
-                            for (int p = 0; p < 4; ++p) {
-                                const float a = dv[t * 8 + 2 * p], b = dv[t * 8 + 2 * p + 1];
-                                hi[p] = pack_bf16x2(a, b);
-                                const float ah = __uint_as_float(hi[p] << 16), bh = __uint_as_float(hi[p] & 0xffff0000u);
-                                mid[p] = pack_bf16x2(a - ah, b - bh);
-                            }
-                            const int kg8 = blk * 3 + t;
-                            unsigned char* d = tb + (size_t)(kg8 >> 2) * TCB_A_CHUNK_BYTES + ((rg * 4 + (kg8 & 3)) * 8 + r) * 16;
-                            st_stream4u(d, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-                            st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(mid[0], mid[1], mid[2], mid[3]));
-                        }
-                    } else {
-                        float* dg = dv_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * (SK_BC * 32) + lane;
-#pragma unroll
-                        for (int i = 0; i < SK_BC; ++i) st_stream(dg + i * 32, dv[i]);
-                    }
-                } else {
-                    float gg[SK_BC], v[SK_BC];
-#pragma unroll
-                    for (int i = 0; i < SK_BC; ++i) v[i] = ld_stream(vb + (size_t)blk * (SK_BC * 32) + i * 32);
-                    gather_block(P, tl, blk, gg);
-                    skin_block_da(P, blk, dacc + lane, gg, v);
-                }
+            if (seg + 1 < SK_NSEG) prefetch_g(seg + 1);
+            if (role == 0) {
+                dv_block(2 * seg);
+                dv_block(2 * seg + 1);
+            } else {
+                load_xpairs(vbk, vb + (size_t)(2 * seg + 1) * XBLK_FLOATS);
+                da_block(2 * seg, va);
+                if (seg + 1 < SK_NSEG) load_xpairs(va, vb + (size_t)(2 * seg + 2) * XBLK_FLOATS);
+                da_block(2 * seg + 1, vbk);
             }
         }
         if (role == 1) {
             // per-bone sums of the group leave as dbone[h][16][12] rows (transposed out of the accumulator)
             __syncwarp();
             float* drow = dbone + (size_t)g * 32 * (NJ * BONE_F) + lane;
-            const float* da = dacc + lane * TP;
+            const float* da = W.dacc + lane * DP;
             for (int h = 0; h < nh; ++h)
 #pragma unroll
-                for (int i = 0; i < NJ * BONE_F / 32; ++i) drow[(size_t)h * (NJ * BONE_F) + 32 * i] = da[(32 * i) * TP + h];
+                for (int i = 0; i < NJ * BONE_F / 32; ++i) drow[(size_t)h * (NJ * BONE_F) + 32 * i] = da[(32 * i) * DP + h];
             __syncwarp();
         }
     }
