@@ -179,14 +179,30 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
     return 0;
 }
 
+extern "C" int mb_mano_model_flags(const int32_t* parents) {
+    if (!parents) return 0;
+    static const int32_t mano[NJ] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14};
+    for (int i = 0; i < NJ; ++i)
+        if (parents[i] != mano[i]) return 0;
+    return MB_MODEL_CHAINS_5X3;
+}
+
+// one thread per hand (mano_pose_lh.cu) once a batch fills the machine; one warp per hand below that
+static constexpr int LH_MIN_HANDS = 4096;
+static inline bool use_lane_hand(int model_flags, int mode, int B) {
+    return (model_flags & MB_MODEL_CHAINS_5X3) && mode != MB_MODE_FP32 && B >= LH_MIN_HANDS;
+}
+
 extern "C" size_t mb_mano_workspace_bytes(int B, int mode) {
     if (B < 0) return 0;
-    return work_layout(B, mode).total;
+    return work_layout(B, mode & 0xff).total;
 }
 
 static int check_common(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B, int mode,
                         const void* workspace, size_t workspace_bytes) {
     if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
+    if (mode & ~(0xff | MB_MODEL_CHAINS_5X3)) return MB_E_RANGE;
+    mode &= 0xff;
     if (mode != MB_MODE_FP32 && mode != MB_MODE_F16X3 && mode != MB_MODE_F16) return MB_E_RANGE;
     if (B == 0) return 0;
     if (!blob || !rot || !coeffs || !betas) return MB_E_NULL;
@@ -198,7 +214,7 @@ static int check_common(const void* blob, int nc, const float* rot, const float*
 
 // pose stage + blend contraction of the forward (fp32 FFMA or tcgen05): fills bone_t and v_posed_t
 static int pose_and_blend_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B,
-                                  int mode, char* ws, const WorkLayout& W, float* joints, cudaStream_t s) {
+                                  int mode, int model_flags, char* ws, const WorkLayout& W, float* joints, cudaStream_t s) {
     float* bone_t = reinterpret_cast<float*>(ws + W.bone_t);
     float* v_posed_t = reinterpret_cast<float*>(ws + W.v_posed_t);
     int rc;
@@ -212,7 +228,12 @@ static int pose_and_blend_forward(const void* blob, int nc, const float* rot, co
         return launch_rows_to_t(blob, rows, VP_PITCH, B, v_posed_t, s);
     }
     unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
-    { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s))) return rc; }
+    {
+        StageTimer t(ST_POSE_FWD, s);
+        rc = use_lane_hand(model_flags, mode, B) ? launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s)
+                                                 : launch_pose_forward(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s);
+        if (rc) return rc;
+    }
     StageTimer t(ST_BLEND_FWD, s);
     return launch_blend_tc_forward(blob, featp, v_posed_t, B, mode, s);
 }
@@ -232,9 +253,11 @@ extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const
     if (rc || B == 0) return rc;
     if (!joints) return MB_E_NULL;
     if (reinterpret_cast<uintptr_t>(verts) & 15) return MB_E_ALIGN;
+    const int model_flags = mode & ~0xff;
+    mode &= 0xff;
     const WorkLayout W = work_layout(B, mode);
     char* ws = reinterpret_cast<char*>(workspace);
-    if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, ws, W, joints, s))) return rc;
+    if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, model_flags, ws, W, joints, s))) return rc;
     StageTimer t(ST_LBS_FWD, s);
     return launch_skin_forward(blob, reinterpret_cast<float*>(ws + W.v_posed_t), reinterpret_cast<float*>(ws + W.bone_t), B,
                                verts, joints, s);
@@ -255,6 +278,9 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
     int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
     if (rc || B == 0) return rc;
     if (!g_joints || !g_rot || !g_coeffs || !g_betas) return MB_E_NULL;
+    const int model_flags = mode & ~0xff;
+    mode &= 0xff;
+    const bool lh = use_lane_hand(model_flags, mode, B);
     const WorkLayout W = work_layout(B, mode);
     char* ws = reinterpret_cast<char*>(workspace);
     float* bone_t = reinterpret_cast<float*>(ws + W.bone_t);
@@ -264,23 +290,24 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
     if (!(flags & MB_BWD_WORKSPACE_VALID)) {
         // recompute the forward intermediates; joints of the recompute go to scratch (dfeat is free until step 3)
         float* scratch_joints = dfeat;      // B*63 floats <= B*148
-        if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, ws, W, scratch_joints, s))) return rc;
+        if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, model_flags, ws, W, scratch_joints, s))) return rc;
     }
     if (mode == MB_MODE_FP32) {
         float* dv_t = reinterpret_cast<float*>(ws + W.dv_t);
         float* rows = reinterpret_cast<float*>(ws + W.rows);
-        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, nullptr, dbone, s))) return rc; }
+        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, nullptr, dbone, 0, s))) return rc; }
         StageTimer t(ST_BLEND_BWD, s);
         const BlobLayout L = blob_layout();
         if ((rc = launch_t_to_rows(blob, dv_t, VP_PITCH, B, rows, s))) return rc;
         if ((rc = launch_sgemm(rows, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s))) return rc;
     } else {
         unsigned char* dvp = reinterpret_cast<unsigned char*>(ws + W.dvp);
-        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, s))) return rc; }
+        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, lh ? 1 : 0, s))) return rc; }
         StageTimer t(ST_BLEND_BWD, s);        // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
-        if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, s))) return rc;
+        if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, lh ? 1 : 0, s))) return rc;
     }
     StageTimer t(ST_POSE_BWD, s);
+    if (lh) return launch_pose_backward_lh(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
     return launch_pose_backward(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
 }
 

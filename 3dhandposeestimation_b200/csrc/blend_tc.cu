@@ -248,7 +248,7 @@ struct TcBwdShared {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsigned char* __restrict__ dvp,
-                         float* __restrict__ dfeat, int B, int m_tiles) {
+                         float* __restrict__ dfeat, int B, int m_tiles, int hand_minor) {
     extern __shared__ unsigned char smem_raw[];
     TcBwdShared& S = *reinterpret_cast<TcBwdShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,18 +347,27 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty));
                 }
+                if (hand_minor) {                               // dfeat_t[group][column][32]: a lane quarter is a hand group
+                    const long long group = (long long)m_tile * (TC_M / 32) + q;
+                    if (active && group * 32 < B) {
+                        float* dst = dfeat + ((size_t)group * TC_N + j * 32) * 32 + lane;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) buf[lane][c] = v[c];
-                __syncwarp();
-                const int col = j * 32 + lane;
-                if (active && col < FEAT_K) {
-                    float* dst = dfeat + (size_t)row0 * FEAT_K + col;
-                    const int nrow = B - row0 < 32 ? B - row0 : 32;
+                        for (int c = 0; c < 32; ++c) dst[c * 32] = v[c];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) buf[lane][c] = v[c];
+                    __syncwarp();
+                    const int col = j * 32 + lane;
+                    if (active && col < FEAT_K) {
+                        float* dst = dfeat + (size_t)row0 * FEAT_K + col;
+                        const int nrow = B - row0 < 32 ? B - row0 : 32;
 #pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr)
-                        if (rr < nrow) dst[(size_t)rr * FEAT_K] = buf[rr][lane];
+                        for (int rr = 0; rr < 32; ++rr)
+                            if (rr < nrow) dst[(size_t)rr * FEAT_K] = buf[rr][lane];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             pass_phase ^= 1;
         }
@@ -420,7 +429,7 @@ void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob
             }
 }
 
-int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, cudaStream_t s) {
+int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, int hand_minor, cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
     const size_t smem = sizeof(TcBwdShared) + 128;
@@ -433,7 +442,7 @@ int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* 
     const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
     const int m_tiles = (B + TC_M - 1) / TC_M;
     const int passes = (m_tiles + BW_MT - 1) / BW_MT;
-    blend_tc_backward_kernel<<<passes < NUM_SMS ? passes : NUM_SMS, TC_THREADS, smem, s>>>(tc + tc_fwd_bytes(), dvp, dfeat, B, m_tiles);
+    blend_tc_backward_kernel<<<passes < NUM_SMS ? passes : NUM_SMS, TC_THREADS, smem, s>>>(tc + tc_fwd_bytes(), dvp, dfeat, B, m_tiles, hand_minor);
     return cuda_rc();
 }
 

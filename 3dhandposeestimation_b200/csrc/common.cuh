@@ -111,8 +111,8 @@ __host__ __device__ inline BlobLayout blob_layout() {
 struct WorkLayout {
     size_t bone_t;    // float [G][16*12][32]      bone transforms, hand-minor
     size_t v_posed_t; // float [G][SK_NCOORD][32]  rest-pose vertices, block order, hand-minor
-    size_t dbone;     // float [B][16][12]         (backward only)
-    size_t dfeat;     // float [B][FEAT_K]         (backward only)
+    size_t dbone;     // float [B][16][12] rows or [G][16*12][32] hand-minor   (backward only)
+    size_t dfeat;     // float [B][FEAT_K] rows or [G][160][32] hand-minor     (backward only)
     // tensor-core modes
     size_t featp;     // fp16 hi/lo feature tiles: ceil(B/128) * 80 KB
     size_t dvp;       // bf16 hi/mid dv_posed tiles of the tcgen05 backward: ceil(B/128) * 74 * 16 KB
@@ -130,8 +130,8 @@ __host__ __device__ inline WorkLayout work_layout(long long B, int mode) {
     size_t o = 0;
     W.bone_t = o;    o = align256(o + sizeof(float) * G * NJ * BONE_F * 32);
     W.v_posed_t = o; o = align256(o + sizeof(float) * G * SK_NCOORD * 32);
-    W.dbone = o;     o = align256(o + sizeof(float) * B * NJ * BONE_F);
-    W.dfeat = o;     o = align256(o + sizeof(float) * B * FEAT_K);
+    W.dbone = o;     o = align256(o + sizeof(float) * G * NJ * BONE_F * 32);
+    W.dfeat = o;     o = align256(o + sizeof(float) * G * 160 * 32);
     W.featp = W.dvp = W.feat = W.rows = W.dv_t = o;
     if (mode == MB_MODE_FP32) {
         W.feat = o;  o = align256(o + sizeof(float) * B * FEAT_K);
@@ -155,6 +155,12 @@ __host__ __device__ inline const T* blob_ptr(const void* blob, size_t off) {
 // bone_t is hand-minor: bone_t[group][16*12][32]
 int launch_pose_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                         int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s);
+// one-thread-per-hand variants (mano_pose_lh.cu): MANO tree only; dfeat_t [G][160][32], dbone_t [G][192][32] hand-minor
+int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                           int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s);
+int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                            const float* dfeat_t, const float* dbone_t, const float* g_joints, int B,
+                            float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
 int launch_pose_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                          const float* dfeat, const float* dbone, const float* g_joints, int B,
                          float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);

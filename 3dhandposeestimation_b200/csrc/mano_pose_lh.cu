@@ -1,0 +1,435 @@
+// mano_pose_lh.cu — the per-hand "pose stage" of the MANO layer with LANE = HAND (large batches).
+//
+//   forward :  PCA coefficients -> axis-angle (MANOLayer.py:126-128), 17 Rodrigues (:82-112), pose
+//              feature (:114-120), folded joint regression (:139-141), kinematic chain (:159-165),
+//              rest-pose removal with the global rotation folded in (:169-175, :188, :204-205)
+//   backward:  SURVEY Appendix A.2 steps 3-7 (reverse chain, Rodrigues backward, PCA^T).
+//
+// The one-warp-per-hand kernels of mano_pose.cu (the mapping north_star names) spend 1.5 k / 2.9 k
+// warp-instructions per hand [round-1 ncu: issue-bound at 58-69 %] because 16 of 32 lanes idle through
+// a chain that is serial in tree depth and every matrix moves between lanes by shuffles.  For batches
+// that fill the machine anyway the same arithmetic is done here by ONE THREAD per hand: the whole
+// chain stays in registers, all global traffic is coalesced through hand-minor layouts (bone_t,
+// dbone_t, dfeat_t written / read as 128-byte rows) or staged through a per-warp shared-memory tile,
+// and a hand costs ~150 / ~300 warp-instructions.  It requires MANO's tree — a wrist with five
+// chains of three joints (MB_MODEL_CHAINS_5X3) — which is what every MANO pickle has; other trees
+// and small batches keep the warp-per-hand kernels.
+#include <cuda_fp16.h>
+#include "hand_math.cuh"
+#include "blend_tc.cuh"
+
+namespace mb {
+namespace {
+
+constexpr int LH_WARPS = 4;
+constexpr int BP = 33;                               // staging pitch: element (row i, hand r) at i * 33 + r
+constexpr int BUF_ROWS = FEAT_K;                     // 148 rows
+constexpr int BUF_FLOATS = BUF_ROWS * BP;            // 4884 floats = 19.1 KB per warp
+constexpr int THETA_ROW = 100;                       // theta[45] lives in rows 100..144 until its joint is processed
+constexpr int PCA_PITCH = 48;
+
+struct LhConsts {
+    alignas(16) float pca[NAA * PCA_PITCH];          // [nc][48]
+    float mean[NAA + 3];
+    float j0[NJ * 3];
+    alignas(16) float jb[NJ * 3 * 12];               // [48][12] (10 used)
+};
+
+__device__ void lh_stage_constants(LhConsts& C, const void* blob, int nc) {
+    const BlobLayout L = blob_layout();
+    const float* pca = blob_ptr<float>(blob, L.pca);
+    const float* mean = blob_ptr<float>(blob, L.pose_mean);
+    const float* j0 = blob_ptr<float>(blob, L.j0);
+    const float* jb = blob_ptr<float>(blob, L.jb);
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < NAA * PCA_PITCH; i += nt) {
+        const int r = i / PCA_PITCH, c = i % PCA_PITCH;
+        C.pca[i] = (r < nc && c < NAA) ? pca[r * NAA + c] : 0.f;
+    }
+    for (int i = t; i < NAA; i += nt) C.mean[i] = mean[i];
+    for (int i = t; i < NJ * 3; i += nt) C.j0[i] = j0[i];
+    for (int i = t; i < NJ * 3 * 12; i += nt) {
+        const int r = i / 12, c = i % 12;
+        C.jb[i] = c < NB ? jb[r * NB + c] : 0.f;
+    }
+    __syncthreads();
+}
+
+// coalesced copy of `n` consecutive floats (rows of up to 32 hands) into the warp's staging buffer
+__device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ src, int n, int lane) {
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__device__ __forceinline__ V3 rest_joint(const LhConsts& C, int k, const float (&beta)[NB]) {
+    float j[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* row = &C.jb[(k * 3 + c) * 12];
+        float acc = C.j0[k * 3 + c];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) acc = fmaf(row[s], beta[s], acc);
+        j[c] = acc;
+    }
+    return v3(j[0], j[1], j[2]);
+}
+
+// theta = mean + coeffs . pca  -> rows THETA_ROW.. of the staging buffer (column = this lane)
+__device__ __forceinline__ void lh_theta(const LhConsts& C, const float* s_coef, int nc, float* bl) {
+    float th[NAA];
+#pragma unroll
+    for (int j = 0; j < NAA; ++j) th[j] = C.mean[j];
+    for (int i = 0; i < nc; ++i) {
+        const float ci = s_coef[i];
+        const float4* row = reinterpret_cast<const float4*>(&C.pca[i * PCA_PITCH]);
+#pragma unroll
+        for (int q = 0; q < 11; ++q) {
+            const float4 p = row[q];
+            th[4 * q] = fmaf(ci, p.x, th[4 * q]); th[4 * q + 1] = fmaf(ci, p.y, th[4 * q + 1]);
+            th[4 * q + 2] = fmaf(ci, p.z, th[4 * q + 2]); th[4 * q + 3] = fmaf(ci, p.w, th[4 * q + 3]);
+        }
+        th[44] = fmaf(ci, C.pca[i * PCA_PITCH + 44], th[44]);
+    }
+#pragma unroll
+    for (int j = 0; j < NAA; ++j) bl[(THETA_ROW + j) * BP] = th[j];
+}
+
+// bone transform with the global rotation folded in: A' = [Rq Rg | Rq (tg - Rg J)]  -> bone_t rows (hand-minor)
+__device__ __forceinline__ void emit_bone(float* __restrict__ bt, int k, const M3& Rq, const M3& Rg, const V3& tg, const V3& J) {
+    const M3 Rp = m3_mul(Rq, Rg);
+    const V3 tp = m3_vec(Rq, v3_sub(tg, m3_vec(Rg, J)));
+    float* o = bt + k * (BONE_F * 32);
+    o[0 * 32] = Rp.m[0]; o[1 * 32] = Rp.m[1]; o[2 * 32] = Rp.m[2];  o[3 * 32] = tp.x;
+    o[4 * 32] = Rp.m[3]; o[5 * 32] = Rp.m[4]; o[6 * 32] = Rp.m[5];  o[7 * 32] = tp.y;
+    o[8 * 32] = Rp.m[6]; o[9 * 32] = Rp.m[7]; o[10 * 32] = Rp.m[8]; o[11 * 32] = tp.z;
+}
+__device__ __forceinline__ void emit_joint(float* __restrict__ jrow, int slot, const M3& Rq, const V3& tg) {
+    const V3 j = m3_vec(Rq, tg);
+    jrow[slot * 3] = j.x; jrow[slot * 3 + 1] = j.y; jrow[slot * 3 + 2] = j.z;
+}
+
+__global__ void __launch_bounds__(LH_WARPS * 32)
+pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
+                       const float* __restrict__ coeffs, const float* __restrict__ betas, int B,
+                       float* __restrict__ feat, unsigned char* __restrict__ featp, float* __restrict__ bone_t,
+                       float* __restrict__ joints) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LhConsts& C = *reinterpret_cast<LhConsts*>(smem_raw);
+    lh_stage_constants(C, blob, nc);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts)) + warp * BUF_FLOATS;
+    float* bl = buf + lane;                                    // (row i, this hand) at bl[i * BP]
+    const int ngroups = (B + 31) >> 5;
+    for (int g = blockIdx.x * LH_WARPS + warp; g < ngroups; g += gridDim.x * LH_WARPS) {
+        const long long h0 = (long long)g * 32;
+        const int nh = (B - h0) < 32 ? (int)(B - h0) : 32;
+        const long long hand = h0 + (lane < nh ? lane : nh - 1);      // idle lanes of a ragged group redo the last hand
+        const bool live = lane < nh;
+        __syncwarp();
+        // ---- inputs: coalesced rows -> staging (coeffs at [0, 32 nc), betas behind, rot behind)
+        float* s_coef = buf;
+        float* s_beta = buf + 32 * NAA;
+        float* s_rot = s_beta + 32 * NB;
+        stage_in(s_coef, coeffs + h0 * nc, nh * nc, lane);
+        stage_in(s_beta, betas + h0 * NB, nh * NB, lane);
+        stage_in(s_rot, rot + h0 * 3, nh * 3, lane);
+        __syncwarp();
+        const int r = (int)(hand - h0);
+        float beta[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) beta[s] = s_beta[r * NB + s];
+        const M3 Rq = rodrigues(v3(s_rot[r * 3], s_rot[r * 3 + 1], s_rot[r * 3 + 2]));
+        // theta needs this lane's coefficients: copy them out of the row-major staging first
+        // (the theta rows alias nothing below float 32*NAA + 32*NB + 96 = 1856 < THETA_ROW * BP)
+        lh_theta(C, s_coef + r * nc, nc, bl);
+        __syncwarp();                                          // every lane is done with the input staging
+
+        float* bt = bone_t + (size_t)g * (NJ * BONE_F * 32) + lane;
+        float* jrow = joints + hand * (NOUTJ * 3);
+        // ---- wrist: constant root rotation [pi, 0, 0] (:76, :128)
+        const M3 R0 = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));
+        const V3 J0 = rest_joint(C, 0, beta);
+        if (live) { emit_bone(bt, 0, Rq, R0, J0, J0); emit_joint(jrow, 0, Rq, J0); }
+#pragma unroll
+        for (int s = 0; s < NB; ++s) bl[s * BP] = beta[s];
+        bl[FEAT_ONE * BP] = 1.f; bl[(FEAT_ONE + 1) * BP] = 0.f; bl[(FEAT_ONE + 2) * BP] = 0.f;
+        // ---- five chains of three joints
+#pragma unroll 1
+        for (int f = 0; f < 5; ++f) {
+            M3 Rgp = R0;
+            V3 tgp = J0, Jp = J0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int k = 1 + 3 * f + i;
+                const float* th = bl + (THETA_ROW + 3 * (k - 1)) * BP;
+                const M3 R = rodrigues(v3(th[0], th[BP], th[2 * BP]));
+                float* fr = bl + (NB + 9 * (k - 1)) * BP;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) fr[e * BP] = R.m[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+                const V3 J = rest_joint(C, k, beta);
+                const M3 Rg = m3_mul(Rgp, R);
+                const V3 tg = v3_add(tgp, m3_vec(Rgp, v3_sub(J, Jp)));
+                if (live) { emit_bone(bt, k, Rq, Rg, tg, J); emit_joint(jrow, 1 + 4 * f + i, Rq, tg); }
+                Rgp = Rg; tgp = tg; Jp = J;
+            }
+        }
+        // ---- blend features leave as fp32 rows (fp32 mode) or fp16 hi/lo UMMA K-groups (tensor-core modes)
+        if (feat != nullptr) {
+            __syncwarp();
+            for (int rr = 0; rr < nh; ++rr) {
+                float* o = feat + (h0 + rr) * FEAT_K;
+                for (int i = lane; i < FEAT_K; i += 32) o[i] = buf[i * BP + rr];
+            }
+        }
+        if (featp != nullptr && live) {
+            const float fs = (float)(1 << TC_FEAT_SCALE_LOG2);
+#pragma unroll 1
+            for (int kg8 = 0; kg8 < TC_K / 8; ++kg8) {
+                __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k = kg8 * 8 + e;
+                    const float x = k < TC_K_REAL ? bl[k * BP] * fs : 0.f;
+                    hi[e] = __float2half_rn(x);
+                    lo[e] = __float2half_rn(x - __half2float(hi[e]));
+                }
+                *reinterpret_cast<uint4*>(featp + tc_feat_group_offset(hand, kg8, 0)) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(featp + tc_feat_group_offset(hand, kg8, 1)) = *reinterpret_cast<const uint4*>(lo);
+            }
+        }
+    }
+}
+
+// ================================================================= backward
+// Staging rows of the backward (per warp, pitch BP): dfeat rows 0..147 are loaded first; the chain
+// joints' upstream gradients (48 floats) and the axis-angle gradients (45 floats) reuse rows that
+// have been consumed.
+__global__ void __launch_bounds__(LH_WARPS * 32)
+pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
+                        const float* __restrict__ coeffs, const float* __restrict__ betas,
+                        const float* __restrict__ dfeat_t, const float* __restrict__ dbone_t,
+                        const float* __restrict__ g_joints, int B,
+                        float* __restrict__ g_rot, float* __restrict__ g_coeffs, float* __restrict__ g_betas) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LhConsts& C = *reinterpret_cast<LhConsts*>(smem_raw);
+    lh_stage_constants(C, blob, nc);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts)) + warp * BUF_FLOATS;
+    float* bl = buf + lane;
+    const int ngroups = (B + 31) >> 5;
+    for (int g = blockIdx.x * LH_WARPS + warp; g < ngroups; g += gridDim.x * LH_WARPS) {
+        const long long h0 = (long long)g * 32;
+        const int nh = (B - h0) < 32 ? (int)(B - h0) : 32;
+        const long long hand = h0 + (lane < nh ? lane : nh - 1);
+        const bool live = lane < nh;
+        const int r = (int)(hand - h0);
+        __syncwarp();
+        float* s_coef = buf;
+        float* s_beta = buf + 32 * NAA;
+        float* s_rot = s_beta + 32 * NB;
+        float* s_gj = s_rot + 96;                              // [32][63] upstream joint gradients, row-major
+        stage_in(s_coef, coeffs + h0 * nc, nh * nc, lane);
+        stage_in(s_beta, betas + h0 * NB, nh * NB, lane);
+        stage_in(s_rot, rot + h0 * 3, nh * 3, lane);
+        stage_in(s_gj, g_joints + h0 * (NOUTJ * 3), nh * NOUTJ * 3, lane);   // 1856 + 2016 = 3872 floats < BUF_FLOATS
+        __syncwarp();
+        float beta[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) beta[s] = s_beta[r * NB + s];
+        const V3 rq = v3(s_rot[r * 3], s_rot[r * 3 + 1], s_rot[r * 3 + 2]);
+        const M3 Rq = rodrigues(rq);
+        // upstream gradients of the 16 chain joints -> registers (slot of chain joint k: 0, 1+4f+i)
+        V3 gj[NJ];
+        gj[0] = v3(s_gj[r * 63], s_gj[r * 63 + 1], s_gj[r * 63 + 2]);
+#pragma unroll
+        for (int f = 0; f < 5; ++f)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float* p = s_gj + r * 63 + (1 + 4 * f + i) * 3;
+                gj[1 + 3 * f + i] = v3(p[0], p[1], p[2]);
+            }
+        float th[NAA];
+        {
+            // theta in registers (the staging buffer is about to be overwritten by dfeat)
+#pragma unroll
+            for (int j = 0; j < NAA; ++j) th[j] = C.mean[j];
+            const float* sc = s_coef + r * nc;
+            for (int i = 0; i < nc; ++i) {
+                const float ci = sc[i];
+                const float4* row = reinterpret_cast<const float4*>(&C.pca[i * PCA_PITCH]);
+#pragma unroll
+                for (int q = 0; q < 11; ++q) {
+                    const float4 p = row[q];
+                    th[4 * q] = fmaf(ci, p.x, th[4 * q]); th[4 * q + 1] = fmaf(ci, p.y, th[4 * q + 1]);
+                    th[4 * q + 2] = fmaf(ci, p.z, th[4 * q + 2]); th[4 * q + 3] = fmaf(ci, p.w, th[4 * q + 3]);
+                }
+                th[44] = fmaf(ci, C.pca[i * PCA_PITCH + 44], th[44]);
+            }
+        }
+        __syncwarp();                                          // input staging consumed by every lane
+        // theta and the joint gradients move to staging rows (dynamic joint index inside the chain loop);
+        // dfeat is read straight from its hand-minor global rows
+#pragma unroll
+        for (int j = 0; j < NAA; ++j) bl[j * BP] = th[j];                      // rows 0..44: theta, later dtheta
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) { bl[(48 + 3 * k) * BP] = gj[k].x; bl[(49 + 3 * k) * BP] = gj[k].y; bl[(50 + 3 * k) * BP] = gj[k].z; }
+        const float* df = dfeat_t + (size_t)g * (TC_K * 32) + lane;             // dfeat_t[g][k][lane], k < 160
+        const float* db = dbone_t + (size_t)g * (NJ * BONE_F * 32) + lane;      // dbone_t[g][bone*12+e][lane]
+
+        float gbeta[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) gbeta[s] = df[s * 32];
+        M3 dRq = m3_zero();
+        // d beta += Jb^T dJ for one joint
+        auto add_dJ = [&](int k, const V3& dJ) {
+            const float d3[3] = {dJ.x, dJ.y, dJ.z};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* row = &C.jb[(k * 3 + c) * 12];
+#pragma unroll
+                for (int s = 0; s < NB; ++s) gbeta[s] = fmaf(row[s], d3[c], gbeta[s]);
+            }
+        };
+        // A.2 step 3 for one bone: split dA'_k = d[Rq Rg | Rq tA], joint_k = Rq tg
+        auto split_bone = [&](int k, const M3& Rg, const V3& tg, const V3& J, const V3& gjk, M3& dRg, V3& dtg, V3& dJ) {
+            float dA[BONE_F];
+#pragma unroll
+            for (int e = 0; e < BONE_F; ++e) dA[e] = db[(k * BONE_F + e) * 32];
+            const V3 tA = v3_sub(tg, m3_vec(Rg, J));
+            M3 dApR;
+            dApR.m[0] = dA[0]; dApR.m[1] = dA[1]; dApR.m[2] = dA[2];
+            dApR.m[3] = dA[4]; dApR.m[4] = dA[5]; dApR.m[5] = dA[6];
+            dApR.m[6] = dA[8]; dApR.m[7] = dA[9]; dApR.m[8] = dA[10];
+            const V3 dApt = v3(dA[3], dA[7], dA[11]);
+            // dRq += dA'R Rg^T + dA't tA^T + gj tg^T
+            m3_acc(dRq, m3_mult(dApR, Rg));
+            m3_add_outer(dRq, dApt, tA);
+            m3_add_outer(dRq, gjk, tg);
+            dRg = m3_tmul(Rq, dApR);
+            const V3 dAt = m3_tvec(Rq, dApt);
+            m3_add_outer(dRg, v3(-dAt.x, -dAt.y, -dAt.z), J);
+            dtg = v3_add(dAt, m3_tvec(Rq, gjk));
+            dJ = m3_tvec(Rg, v3(-dAt.x, -dAt.y, -dAt.z));
+        };
+
+        const M3 R0 = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));
+        const V3 J0 = rest_joint(C, 0, beta);
+        M3 dRg0; V3 dtg0, dJ0;
+        split_bone(0, R0, J0, J0, v3(bl[48 * BP], bl[49 * BP], bl[50 * BP]), dRg0, dtg0, dJ0);
+#pragma unroll 1
+        for (int f = 0; f < 5; ++f) {
+            // forward through the chain (state of the three joints stays in registers)
+            M3 R[3], Rg[3];
+            V3 tg[3], J[3], rr[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int k = 1 + 3 * f + i;
+                const float* tp = bl + (3 * (k - 1)) * BP;
+                rr[i] = v3(tp[0], tp[BP], tp[2 * BP]);
+                R[i] = rodrigues(rr[i]);
+                J[i] = rest_joint(C, k, beta);
+                const M3& Rgp = i == 0 ? R0 : Rg[i - 1];
+                const V3& tgp = i == 0 ? J0 : tg[i - 1];
+                const V3& Jp = i == 0 ? J0 : J[i - 1];
+                Rg[i] = m3_mul(Rgp, R[i]);
+                tg[i] = v3_add(tgp, m3_vec(Rgp, v3_sub(J[i], Jp)));
+            }
+            // reverse: tip of the chain first
+            M3 dRg_c = m3_zero();                              // gradient arriving from the child
+            V3 dtg_c = v3(0.f, 0.f, 0.f), dJ_c = v3(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 2; i >= 0; --i) {
+                const int k = 1 + 3 * f + i;
+                const float* gp = bl + (48 + 3 * k) * BP;
+                M3 dRg; V3 dtg, dJ;
+                split_bone(k, Rg[i], tg[i], J[i], v3(gp[0], gp[BP], gp[2 * BP]), dRg, dtg, dJ);
+                m3_acc(dRg, dRg_c); dtg = v3_add(dtg, dtg_c); dJ = v3_add(dJ, dJ_c);
+                const M3& Rgp = i == 0 ? R0 : Rg[i - 1];
+                const V3& Jp = i == 0 ? J0 : J[i - 1];
+                // A.2 step 4: Rg = Rgp R ; tg = tgp + Rgp (J - Jp)
+                M3 dRl = m3_tmul(Rgp, dRg);
+                M3 up = m3_mult(dRg, R[i]);
+                m3_add_outer(up, dtg, v3_sub(J[i], Jp));
+                const V3 dd = m3_tvec(Rgp, dtg);
+                dJ = v3_add(dJ, dd);
+                add_dJ(k, dJ);
+                // A.2 steps 5-6: pose-feature gradient joins dR_k ; Rodrigues backward
+#pragma unroll
+                for (int e = 0; e < 9; ++e) dRl.m[e] += df[(NB + 9 * (k - 1) + e) * 32];
+                const V3 dth = rodrigues_bwd(rr[i], dRl);
+                float* tp = bl + (3 * (k - 1)) * BP;
+                tp[0] = dth.x; tp[BP] = dth.y; tp[2 * BP] = dth.z;     // theta row -> dtheta row
+                dRg_c = up; dtg_c = dtg; dJ_c = v3(-dd.x, -dd.y, -dd.z);
+            }
+            m3_acc(dRg0, dRg_c); dtg0 = v3_add(dtg0, dtg_c); dJ0 = v3_add(dJ0, dJ_c);
+        }
+        dJ0 = v3_add(dJ0, dtg0);                               // tg_0 = J_0 ; R_0 is a constant
+        add_dJ(0, dJ0);
+        const V3 drq = rodrigues_bwd(rq, dRq);
+
+        // ---- A.2 step 7: d_coeffs = C[:nc] dtheta
+        float dth[NAA];
+#pragma unroll
+        for (int j = 0; j < NAA; ++j) dth[j] = bl[j * BP];
+        __syncwarp();
+        float* s_gc = buf + 64 * BP;                           // [32][nc | 1] row-major, rows 64.. (theta rows are consumed)
+        const int gp = nc | 1;
+        for (int i = 0; i < nc; ++i) {
+            const float4* row = reinterpret_cast<const float4*>(&C.pca[i * PCA_PITCH]);
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 11; ++q) {
+                const float4 p = row[q];
+                acc = fmaf(p.x, dth[4 * q], acc); acc = fmaf(p.y, dth[4 * q + 1], acc);
+                acc = fmaf(p.z, dth[4 * q + 2], acc); acc = fmaf(p.w, dth[4 * q + 3], acc);
+            }
+            acc = fmaf(C.pca[i * PCA_PITCH + 44], dth[44], acc);
+            s_gc[lane * gp + i] = acc;
+        }
+        __syncwarp();
+        for (int i = lane; i < nh * nc; i += 32) g_coeffs[h0 * nc + i] = s_gc[(i / nc) * gp + (i % nc)];
+        if (live) {
+            g_rot[hand * 3] = drq.x; g_rot[hand * 3 + 1] = drq.y; g_rot[hand * 3 + 2] = drq.z;
+#pragma unroll
+            for (int s = 0; s < NB; ++s) g_betas[hand * NB + s] = gbeta[s];
+        }
+    }
+}
+
+constexpr size_t LH_SMEM = sizeof(LhConsts) + (size_t)LH_WARPS * BUF_FLOATS * sizeof(float);
+
+inline int lh_grid(int B) {
+    const long long groups = ((long long)B + 31) / 32;
+    const long long blocks = (groups + LH_WARPS - 1) / LH_WARPS;
+    const long long cap = (long long)NUM_SMS * 2;
+    return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+}  // namespace
+
+int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                           int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pose_forward_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    pose_forward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, B, feat, featp, bone_t, joints);
+    return cuda_rc();
+}
+
+int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                            const float* dfeat_t, const float* dbone_t, const float* g_joints, int B,
+                            float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    pose_backward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, dfeat_t, dbone_t, g_joints, B,
+                                                                      g_rot, g_coeffs, g_betas);
+    return cuda_rc();
+}
+
+}  // namespace mb

@@ -202,10 +202,6 @@ struct RowMap {
     __device__ __forceinline__ size_t row_base() const { return (size_t)r * NVC + 2 * p; }
 };
 
-__device__ __forceinline__ void load_xblock(float (&x)[SK_BC], const float* __restrict__ vb) {
-#pragma unroll
-    for (int i = 0; i < SK_BC; ++i) x[i] = ld_stream(vb + i * 32);
-}
 // block of 8 vertices as packed pairs: X[c][m] = (x_{2m,c}, x_{2m+1,c}), straight from global memory ...
 __device__ __forceinline__ void load_xpairs(float2 (&X)[3][4], const float* __restrict__ vb) {
 #pragma unroll
@@ -399,7 +395,8 @@ __global__ void __launch_bounds__(SKB_THREADS, 1)
 skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed_t,
                      const float* __restrict__ bone_t, const float* __restrict__ g_verts,
                      const float* __restrict__ g_joints, int B,
-                     float* __restrict__ dv_t, unsigned char* __restrict__ dvp, float* __restrict__ dbone) {
+                     float* __restrict__ dv_t, unsigned char* __restrict__ dvp, float* __restrict__ dbone,
+                     int dbone_hand_minor) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -569,11 +566,17 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
         if (role == 1) {
             // per-bone sums of the group leave as dbone[h][16][12] rows (transposed out of the accumulator)
             __syncwarp();
-            float* drow = dbone + (size_t)g * 32 * (NJ * BONE_F) + lane;
-            const float* da = W.dacc + lane * DP;
-            for (int h = 0; h < nh; ++h)
+            if (dbone_hand_minor) {                            // the lane = hand pose backward reads them as they are
+                float* dt = dbone + (size_t)g * GROUP_BONE_FLOATS + lane;
+#pragma unroll 8
+                for (int i = 0; i < NJ * BONE_F; ++i) dt[i * 32] = W.dacc[i * DP + lane];
+            } else {
+                float* drow = dbone + (size_t)g * 32 * (NJ * BONE_F) + lane;
+                const float* da = W.dacc + lane * DP;
+                for (int h = 0; h < nh; ++h)
 #pragma unroll
-                for (int i = 0; i < NJ * BONE_F / 32; ++i) drow[(size_t)h * (NJ * BONE_F) + 32 * i] = da[(32 * i) * DP + h];
+                    for (int i = 0; i < NJ * BONE_F / 32; ++i) drow[(size_t)h * (NJ * BONE_F) + 32 * i] = da[(32 * i) * DP + h];
+            }
             __syncwarp();
         }
     }
@@ -718,7 +721,8 @@ int launch_skin_forward(const void* blob, const float* v_posed_t, const float* b
 }
 
 int launch_skin_backward(const void* blob, const float* v_posed_t, const float* bone_t, const float* g_verts,
-                         const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, cudaStream_t s) {
+                         const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, int dbone_hand_minor,
+                         cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
     if (!attr_done) {
@@ -728,7 +732,7 @@ int launch_skin_backward(const void* blob, const float* v_posed_t, const float* 
     }
     const int ngroups = (B + 31) >> 5;
     skin_backward_kernel<<<ngroups < NUM_SMS ? ngroups : NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(blob, v_posed_t, bone_t, g_verts, g_joints,
-                                                                                       B, dv_t, dvp, dbone);
+                                                                                       B, dv_t, dvp, dbone, dbone_hand_minor);
     return cuda_rc();
 }
 

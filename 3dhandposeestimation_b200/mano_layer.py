@@ -123,7 +123,7 @@ class ManoLayer(nn.Module):
     memory for not recomputing the forward in the backward.
     """
 
-    def __init__(self, device, MANO_RIGHT_pkl=None, bases_num=10, pose_num=6, *, model=None, mode="fp32",
+    def __init__(self, device, MANO_RIGHT_pkl=None, bases_num=10, pose_num=6, *, model=None, mode="f16x3",
                  keep_workspace=True):
         super().__init__()
         self.device = device
@@ -133,7 +133,7 @@ class ManoLayer(nn.Module):
         self.keypoints_num = 16
         if mode not in _cabi.MODES:
             raise ValueError(f"mode must be one of {sorted(_cabi.MODES)}, got {mode!r}")
-        self._mode = _cabi.MODES[mode]
+        self._mode = _cabi.MODES[mode]      # model property bits (mb_mano_model_flags) are OR-ed in below
         self.mode = mode
         self.keep_workspace = bool(keep_workspace)
 
@@ -157,6 +157,7 @@ class ManoLayer(nn.Module):
         _cabi.check(lib.mb_mano_pack_constants(args[0], args[1], args[2], args[3], self.pose_num, args[4], args[5],
                                                args[6], args[7], host.ctypes.data_as(C.c_void_p)),
                     "mb_mano_pack_constants")
+        self._mode |= int(lib.mb_mano_model_flags(args[7]))
         self._blob_host = torch.from_numpy(host)
         self._blob = None
         dev = torch.device(device)

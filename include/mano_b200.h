@@ -48,6 +48,11 @@ extern "C" {
 #define MB_MODE_F16X3   1     /* tcgen05 kind::f16, 2-way fp16 split, 3 products: fp32-accurate */
 #define MB_MODE_F16     2     /* tcgen05 kind::f16, single product: fast, ~1e-5 m error  */
 
+/* Model property, OR-ed into `mode` by the caller: the kinematic tree is MANO's wrist with five
+ * chains of three joints (parents = -1,0,1,2,0,4,5,0,7,8,0,10,11,0,13,14 — every MANO pickle).
+ * It lets large batches run the one-thread-per-hand pose kernels; mb_mano_model_flags computes it. */
+#define MB_MODEL_CHAINS_5X3 0x100
+
 /* mb_mano_backward flags */
 #define MB_BWD_WORKSPACE_VALID 1  /* workspace still holds the forward's intermediates for these inputs */
 
@@ -79,6 +84,9 @@ MB_API int    mb_mano_pack_constants(const float* basis, const float* j0, const 
                               const float* pca, int nc, const float* pose_mean,
                               const float* skin_w, const int32_t* skin_b,
                               const int32_t* parents, void* host_blob);
+
+/* Model property bits (MB_MODEL_*) of a kinematic tree, to be OR-ed into `mode`. */
+MB_API int    mb_mano_model_flags(const int32_t* parents);
 
 /* Bytes of device scratch mb_mano_forward / mb_mano_backward need for B hands. */
 MB_API size_t mb_mano_workspace_bytes(int B, int mode);
