@@ -109,7 +109,7 @@ __host__ __device__ inline BlobLayout blob_layout() {
 // Workspace layout for B hands (byte offsets, 256-byte aligned sections).  "hand-minor" arrays hold
 // groups of 32 hands with the hand index fastest: x_t[group][element][32].
 struct WorkLayout {
-    size_t bone_t;    // float [G][16*12][32]      bone transforms, hand-minor
+    size_t bone_t;    // float [G][16][32][12]     bone transforms grouped by 32 hands: [group][bone][hand % 32][3x4]
     size_t v_posed_t; // float [G][SK_NCOORD][32]  rest-pose vertices, block order, hand-minor
     size_t dbone;     // float [B][16][12] rows or [G][16*12][32] hand-minor   (backward only)
     size_t dfeat;     // float [B][FEAT_K] rows or [G][160][32] hand-minor     (backward only)
@@ -152,7 +152,7 @@ __host__ __device__ inline const T* blob_ptr(const void* blob, size_t off) {
 
 // ---- kernel launchers implemented in the other translation units ----------
 // feat (fp32 rows) and featp (fp16 hi/lo UMMA tiles) may each be NULL
-// bone_t is hand-minor: bone_t[group][16*12][32]
+// bone_t[group][bone][hand % 32][12]
 int launch_pose_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                         int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s);
 // one-thread-per-hand variants (mano_pose_lh.cu): MANO tree only; dfeat_t [G][160][32], dbone_t [G][192][32] hand-minor

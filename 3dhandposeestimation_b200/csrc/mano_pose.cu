@@ -5,7 +5,7 @@
 //              pose feature (:114-120), folded joint regression (:139-141),
 //              kinematic chain by tree level with parent state fetched by __shfl_sync
 //              (:159-165), rest-pose removal with the global rotation folded in
-//              (:169-175, :188, :204-205)  ->  feat[B][148], bone_t[B/32][16*12][32], joints (chain slots)
+//              (:169-175, :188, :204-205)  ->  feat[B][148], bone_t[B/32][16][32][12], joints (chain slots)
 //   backward:  SURVEY Appendix A.2 steps 3-7 (reverse chain, Rodrigues backward, PCA^T).
 //
 // JOINTS_ONLY variants additionally evaluate the five fingertip vertices
@@ -253,10 +253,11 @@ pose_forward_kernel(const void* __restrict__ blob, int nc, const float* __restri
                     *reinterpret_cast<uint4*>(featp + tc_feat_group_offset(hand, kg8, sp)) = *reinterpret_cast<const uint4*>(h);
                 }
             }
-            // bone transforms leave hand-minor: bone_t[hand / 32][element][hand % 32] (what the
-            // lane = hand skinning kernels load as coalesced 128-byte rows)
-            float* bo = bone_t + (hand >> 5) * (NJ * BONE_F * 32) + (hand & 31);
-            for (int i = lane; i < NJ * BONE_F; i += 32) bo[i * 32] = S.bone[warp][i];
+            // bone transforms leave grouped by 32 hands: bone_t[hand / 32][bone][hand % 32][12] — one bone
+            // of a hand group is 1.5 KB contiguous, one hand's transform 48 B (what the lane = hand
+            // skinning kernels fetch with three 16-byte async copies per lane)
+            float* bo = bone_t + (hand >> 5) * (NJ * BONE_F * 32) + (hand & 31) * BONE_F;
+            for (int i = lane; i < NJ * BONE_F; i += 32) bo[(i / BONE_F) * (BONE_F * 32) + (i % BONE_F)] = S.bone[warp][i];
         } else {
             tips_rest_pose(S, S.feat[warp], S.tipv[warp], lane);
             if (lane < NTIP) {

@@ -93,14 +93,14 @@ __device__ __forceinline__ void lh_theta(const LhConsts& C, const float* s_coef,
     for (int j = 0; j < NAA; ++j) bl[(THETA_ROW + j) * BP] = th[j];
 }
 
-// bone transform with the global rotation folded in: A' = [Rq Rg | Rq (tg - Rg J)]  -> bone_t rows (hand-minor)
+// bone transform with the global rotation folded in: A' = [Rq Rg | Rq (tg - Rg J)]  -> bone_t[group][k][lane][12]
 __device__ __forceinline__ void emit_bone(float* __restrict__ bt, int k, const M3& Rq, const M3& Rg, const V3& tg, const V3& J) {
     const M3 Rp = m3_mul(Rq, Rg);
     const V3 tp = m3_vec(Rq, v3_sub(tg, m3_vec(Rg, J)));
-    float* o = bt + k * (BONE_F * 32);
-    o[0 * 32] = Rp.m[0]; o[1 * 32] = Rp.m[1]; o[2 * 32] = Rp.m[2];  o[3 * 32] = tp.x;
-    o[4 * 32] = Rp.m[3]; o[5 * 32] = Rp.m[4]; o[6 * 32] = Rp.m[5];  o[7 * 32] = tp.y;
-    o[8 * 32] = Rp.m[6]; o[9 * 32] = Rp.m[7]; o[10 * 32] = Rp.m[8]; o[11 * 32] = tp.z;
+    float4* o = reinterpret_cast<float4*>(bt + k * (BONE_F * 32));      // bone_t[group][k][lane][12]
+    o[0] = make_float4(Rp.m[0], Rp.m[1], Rp.m[2], tp.x);
+    o[1] = make_float4(Rp.m[3], Rp.m[4], Rp.m[5], tp.y);
+    o[2] = make_float4(Rp.m[6], Rp.m[7], Rp.m[8], tp.z);
 }
 __device__ __forceinline__ void emit_joint(float* __restrict__ jrow, int slot, const M3& Rq, const V3& tg) {
     const V3 j = m3_vec(Rq, tg);
@@ -143,7 +143,7 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
         lh_theta(C, s_coef + r * nc, nc, bl);
         __syncwarp();                                          // every lane is done with the input staging
 
-        float* bt = bone_t + (size_t)g * (NJ * BONE_F * 32) + lane;
+        float* bt = bone_t + (size_t)g * (NJ * BONE_F * 32) + lane * BONE_F;
         float* jrow = joints + hand * (NOUTJ * 3);
         // ---- wrist: constant root rotation [pi, 0, 0] (:76, :128)
         const M3 R0 = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));

@@ -49,24 +49,37 @@ constexpr int N_TIP = 5;
 __constant__ int c_tip_vert[N_TIP] = {333, 444, 672, 555, 745};
 __constant__ int c_tip_slot[N_TIP] = {4, 8, 12, 16, 20};
 
-__device__ __forceinline__ float ld_stream(const float* p) {
+// Streamed data (rest-pose blocks, upstream gradients, vertices, gradient tiles) passes through L2
+// with evict-first priority; the bone transforms — re-read ~29 times per sweep, 100 MB for 131 072
+// hands — are loaded evict-last.  [round-1 ncu: without the hints the streams pushed the bones out of
+// L2 between uses: DRAM reads 31 % above the algorithmic bytes, half of all stalls on bone loads]
+struct L2Policies { uint64_t stream, keep; };
+__device__ __forceinline__ L2Policies make_policies() { return {l2_policy_evict_first(), l2_policy_evict_last()}; }
+
+__device__ __forceinline__ float ld_stream(const float* p, uint64_t pol) {
     float r;
-    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol) : "memory");
     return r;
 }
-__device__ __forceinline__ float2 ld_stream2(const float* p) {
+__device__ __forceinline__ float2 ld_stream2(const float* p, uint64_t pol) {
     float2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
     return r;
 }
-__device__ __forceinline__ void st_stream(float* p, float v) {
-    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+__device__ __forceinline__ float ld_keep(const float* p, uint64_t pol) {
+    float r;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
 }
-__device__ __forceinline__ void st_stream2(float* p, const float2& v) {
-    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+__device__ __forceinline__ void st_stream(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void st_stream4u(void* p, const uint4& v) {
-    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void st_stream2(float* p, const float2& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream4u(void* p, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
 
@@ -119,6 +132,14 @@ __device__ __forceinline__ void load_voff(const SkinProg& P, int blk, int (&o)[S
 // latency (there is no L1 to speak of — shared memory takes the whole carve-out) never reaches the
 // register scoreboard.  [round-1 ncu: with register prefetch one entry ahead half of all stall
 // samples were long-scoreboard waits on the first use of a bone or coordinate]
+// one lane of the (converged) warp, chosen by the hardware: lets ptxas keep the bulk-copy operands in
+// uniform registers without a vote loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int STAGES, int SLOT_FLOATS>
 struct alignas(128) Ring {
     alignas(128) float slot[STAGES][SLOT_FLOATS];
@@ -135,13 +156,13 @@ struct Cursor {               // per-warp stream position; every lane keeps an i
 // request the next item of the stream (no-op once the warp's groups are exhausted); src(g, i) is its address
 template <int STAGES, int SLOT_FLOATS, class SrcFn>
 __device__ __forceinline__ void ring_request(Ring<STAGES, SLOT_FLOATS>& R, Cursor& C, int ngroups, int gstep, int n, int lane,
-                                             SrcFn src) {
+                                             SrcFn src, uint64_t policy) {
     if (C.g >= ngroups) return;
-    if (lane == 0) {
+    if (elect_one()) {
         const unsigned st = C.issued % STAGES;
         const uint32_t bar = smem_u32(&R.full[st]);
         mbar_expect_tx(bar, SLOT_FLOATS * 4);
-        bulk_g2s(smem_u32(R.slot[st]), src(C.g, C.i), SLOT_FLOATS * 4, bar);
+        bulk_g2s_hint(smem_u32(R.slot[st]), src(C.g, C.i), SLOT_FLOATS * 4, bar, policy);
     }
     ++C.issued;
     if (++C.i == n) { C.i = 0; C.g += gstep; }
@@ -156,9 +177,11 @@ __device__ __forceinline__ const float* ring_wait(Ring<STAGES, SLOT_FLOATS>& R, 
     return R.slot[st];
 }
 
-constexpr int BSTAGES = 4;
+constexpr int FSTAGES = 4;                         // bone slots per warp, forward
+constexpr int BSTAGES = 2;                         // bone slots per pair, backward (measured: 2 beats 4 by 20 %)
 constexpr int XSTAGES = 2;
 constexpr int BONE_SLOT_FLOATS = BONE_F * 32;
+typedef Ring<FSTAGES, BONE_SLOT_FLOATS> FwdBoneRing;
 typedef Ring<BSTAGES, BONE_SLOT_FLOATS> BoneRing;
 typedef Ring<XSTAGES, XBLK_FLOATS> XRing;
 
@@ -186,7 +209,7 @@ __device__ __forceinline__ void fma_entry2(const float (&A)[BONE_F], const float
 constexpr int SKF_WARPS = 10;                      // autonomous warps per CTA; 1 CTA per SM
 constexpr int SKF_THREADS = SKF_WARPS * 32;
 struct alignas(128) FwdWarpShared {
-    BoneRing bones;
+    FwdBoneRing bones;                                       // slots are [lane][12]
     XRing xs;
     alignas(16) float tile[TILE_FLOATS];
 };
@@ -203,12 +226,12 @@ struct RowMap {
 };
 
 // block of 8 vertices as packed pairs: X[c][m] = (x_{2m,c}, x_{2m+1,c}), straight from global memory ...
-__device__ __forceinline__ void load_xpairs(float2 (&X)[3][4], const float* __restrict__ vb) {
+__device__ __forceinline__ void load_xpairs(float2 (&X)[3][4], const float* __restrict__ vb, uint64_t pol) {
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            X[c][m] = make_float2(ld_stream(vb + (6 * m + c) * 32), ld_stream(vb + (6 * m + 3 + c) * 32));
+            X[c][m] = make_float2(ld_stream(vb + (6 * m + c) * 32, pol), ld_stream(vb + (6 * m + 3 + c) * 32, pol));
 }
 // ... or out of a ring slot
 __device__ __forceinline__ void slot_to_pairs(float2 (&X)[3][4], const float* sl) {
@@ -216,6 +239,24 @@ __device__ __forceinline__ void slot_to_pairs(float2 (&X)[3][4], const float* sl
     for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int c = 0; c < 3; ++c) X[c][m] = make_float2(sl[(6 * m + c) * 32], sl[(6 * m + 3 + c) * 32]);
+}
+
+// a finished 16-vertex segment leaves the tile as 192-byte row pieces (kept out of line: once per segment)
+__device__ __noinline__ void store_segment(const float* ts, float* dst, int nh, int nf, int r, int p, uint64_t pol) {
+    if (nh == 32 && nf == SEG_F) {
+#pragma unroll
+        for (int rb = 0; rb < 8; ++rb)
+#pragma unroll
+            for (int qb = 0; qb < 3; ++qb)
+                st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
+                           make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]), pol);
+    } else {
+        for (int rb = 0; rb < 8; ++rb)
+            for (int qb = 0; qb < 3; ++qb)
+                if (rb * 4 + r < nh && qb * 16 + 2 * p < nf)
+                    st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
+                               make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]), pol);
+    }
 }
 
 __global__ void __launch_bounds__(SKF_THREADS, 1)
@@ -240,79 +281,64 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
     const int ne = P.blk_ptr[SK_NBLK];
     auto bone_src = [&](int g, int e) { return bone_t + (size_t)g * GROUP_BONE_FLOATS + (P.ent_code[e] & 0xffff); };
     auto x_src = [&](int g, int blk) { return v_posed_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * XBLK_FLOATS; };
+    const L2Policies pol = make_policies();
     Cursor CB = {g0, 0, 0u, 0u}, CX = {g0, 0, 0u, 0u};
 #pragma unroll
-    for (int s = 0; s < BSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
+    for (int s = 0; s < FSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
 #pragma unroll
-    for (int s = 0; s < XSTAGES; ++s) ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src);
+    for (int s = 0; s < XSTAGES; ++s) ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src, pol.stream);
 
     for (int g = g0; g < ngroups; g += gstep) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
         float* vrow = verts + (size_t)g * 32 * NVC + rm.row_base();
-        for (int seg = 0; seg < SK_NSEG; ++seg) {
 #pragma unroll 1
-            for (int bi = 0; bi < SK_SEG_BLKS; ++bi) {
-                const int blk = seg * SK_SEG_BLKS + bi;
-                float2 X[3][4], ACC[3][4];
-                slot_to_pairs(X, ring_wait(W.xs, CX) + lane);
-                ++CX.consumed;
-                __syncwarp();                                 // every lane has its copy: the slot can be refilled
-                ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src);
+        for (int blk = 0; blk < SK_NBLK; ++blk) {
+            float2 X[3][4], ACC[3][4];
+            slot_to_pairs(X, ring_wait(W.xs, CX) + lane);
+            ++CX.consumed;
+            __syncwarp();                                     // every lane has its copy: the slot can be refilled
+            ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src, pol.stream);
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) ACC[c][m] = make_float2(0.f, 0.f);
-                const int e1 = P.blk_ptr[blk + 1];
+                for (int m = 0; m < 4; ++m) ACC[c][m] = make_float2(0.f, 0.f);
+            const int e1 = P.blk_ptr[blk + 1];
 #pragma unroll 1
-                for (int e = P.blk_ptr[blk]; e < e1; ++e) {
-                    float A[BONE_F], w[SK_BV];
-                    load_w(P, e, w);
-                    const float* sl = ring_wait(W.bones, CB) + lane;
+            for (int e = P.blk_ptr[blk]; e < e1; ++e) {
+                float w[SK_BV];
+                load_w(P, e, w);
+                const float4* sl = reinterpret_cast<const float4*>(ring_wait(W.bones, CB) + lane * BONE_F);
+                const float4 a0 = sl[0], a1 = sl[1], a2 = sl[2];
+                ++CB.consumed;
+                __syncwarp();
+                ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
+                const float A[BONE_F] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+                fma_entry2(A, w, X, ACC);
+            }
+            int vo[SK_BV];
+            load_voff(P, blk, vo);
 #pragma unroll
-                    for (int i = 0; i < BONE_F; ++i) A[i] = sl[i * 32];
-                    ++CB.consumed;
-                    __syncwarp();
-                    ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
-                    fma_entry2(A, w, X, ACC);
+            for (int m = 0; m < 4; ++m) {
+                float* t0 = tl + vo[2 * m];
+                float* t1 = tl + vo[2 * m + 1];
+                t0[0] = ACC[0][m].x; t0[TP] = ACC[1][m].x; t0[2 * TP] = ACC[2][m].x;
+                t1[0] = ACC[0][m].y; t1[TP] = ACC[1][m].y; t1[2 * TP] = ACC[2][m].y;
+            }
+            if (blk & 1) {                                    // second block of a segment: the segment is complete
+                const int seg = blk >> 1;
+                __syncwarp();
+                store_segment(ts, vrow + seg * SEG_F, nh, (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F, rm.r, rm.p, pol.stream);
+                if (joints != nullptr && lane < nh) {
+#pragma unroll
+                    for (int t = 0; t < N_TIP; ++t)
+                        if (c_tip_vert[t] / SK_SEG == seg) {
+                            const float* tv = tl + (c_tip_vert[t] % SK_SEG) * (3 * TP);
+                            float* o = joints + ((size_t)g * 32 + lane) * (NOUTJ * 3) + c_tip_slot[t] * 3;
+                            o[0] = tv[0]; o[1] = tv[TP]; o[2] = tv[2 * TP];
+                        }
                 }
-                int vo[SK_BV];
-                load_voff(P, blk, vo);
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    float* t0 = tl + vo[2 * m];
-                    float* t1 = tl + vo[2 * m + 1];
-                    t0[0] = ACC[0][m].x; t0[TP] = ACC[1][m].x; t0[2 * TP] = ACC[2][m].x;
-                    t1[0] = ACC[0][m].y; t1[TP] = ACC[1][m].y; t1[2 * TP] = ACC[2][m].y;
-                }
+                __syncwarp();
             }
-            __syncwarp();
-            // the segment leaves as 192-byte row pieces
-            float* dst = vrow + seg * SEG_F;
-            if (nh == 32 && seg != SK_NSEG - 1) {
-#pragma unroll
-                for (int rb = 0; rb < 8; ++rb)
-#pragma unroll
-                    for (int qb = 0; qb < 3; ++qb)
-                        st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
-                                   make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]));
-            } else {
-                const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
-                for (int rb = 0; rb < 8; ++rb)
-                    for (int qb = 0; qb < 3; ++qb)
-                        if (rb * 4 + rm.r < nh && qb * 16 + 2 * rm.p < nf)
-                            st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
-                                       make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]));
-            }
-            if (joints != nullptr && lane < nh) {
-#pragma unroll
-                for (int t = 0; t < N_TIP; ++t)
-                    if (c_tip_vert[t] / SK_SEG == seg) {
-                        const float* tv = tl + (c_tip_vert[t] % SK_SEG) * (3 * TP);
-                        float* o = joints + ((size_t)g * 32 + lane) * (NOUTJ * 3) + c_tip_slot[t] * 3;
-                        o[0] = tv[0]; o[1] = tv[TP]; o[2] = tv[2 * TP];
-                    }
-            }
-            __syncwarp();
         }
     }
 }
@@ -416,10 +442,11 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
     const int g0 = blockIdx.x + pair * gridDim.x, gstep = gridDim.x * SKB_PAIRS;
     const int ne = P.blk_ptr[SK_NBLK];
     auto bone_src = [&](int g, int e) { return bone_t + (size_t)g * GROUP_BONE_FLOATS + (P.ent_code[e] & 0xffff); };
+    const L2Policies pol = make_policies();
     Cursor CB = {g0, 0, 0u, 0u};
     if (role == 0) {
 #pragma unroll
-        for (int s = 0; s < BSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
+        for (int s = 0; s < BSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
     }
 
     for (int g = g0; g < ngroups; g += gstep) {
@@ -438,7 +465,7 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
 #pragma unroll
                 for (int qb = 0; qb < 3; ++qb) {
                     const bool ok = (rb * 4 + rm.r < nh) && (qb * 16 + 2 * rm.p < nf);
-                    pre[rb2][qb] = ok ? ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16) : make_float2(0.f, 0.f);
+                    pre[rb2][qb] = ok ? ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16, pol.stream) : make_float2(0.f, 0.f);
                 }
             }
         };
@@ -452,12 +479,12 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
 #pragma unroll
                 for (int kg = 2; kg < 4; ++kg) {
                     unsigned char* d = tb + ((rg * 4 + kg) * 8 + r) * 16;
-                    st_stream4u(d, make_uint4(0, 0, 0, 0));
-                    st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(0, 0, 0, 0));
+                    st_stream4u(d, make_uint4(0, 0, 0, 0), pol.stream);
+                    st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(0, 0, 0, 0), pol.stream);
                 }
             }
         } else {
-            load_xpairs(va, vb);
+            load_xpairs(va, vb, pol.stream);
 #pragma unroll 8
             for (int i = 0; i < NJ * BONE_F; ++i) W.dacc[i * DP + lane] = 0.f;
         }
@@ -476,12 +503,13 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                 float A[11], w[SK_BV];
                 load_w(P, e, w);
                 {
-                    const float* sl = ring_wait(W.bones, CB) + lane;
-#pragma unroll
-                    for (int i = 0; i < 11; ++i) A[i] = sl[i * 32];
+                    const float4* sl = reinterpret_cast<const float4*>(ring_wait(W.bones, CB) + lane * BONE_F);   // [lane][12]
+                    const float4 a0 = sl[0], a1 = sl[1], a2 = sl[2];
+                    A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
+                    A[8] = a2.x; A[9] = a2.y; A[10] = a2.z;
                     ++CB.consumed;
                     __syncwarp();
-                    ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src);
+                    ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
                 }
                 dv_entry2(A, w, G, DV);
             }
@@ -508,13 +536,13 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                     }
                     const int kg8 = blk * 3 + t;
                     unsigned char* d = tb + (size_t)(kg8 >> 2) * TCB_A_CHUNK_BYTES + ((rg * 4 + (kg8 & 3)) * 8 + r) * 16;
-                    st_stream4u(d, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-                    st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(mid[0], mid[1], mid[2], mid[3]));
+                    st_stream4u(d, make_uint4(hi[0], hi[1], hi[2], hi[3]), pol.stream);
+                    st_stream4u(d + TC_A_BLOCK_BYTES, make_uint4(mid[0], mid[1], mid[2], mid[3]), pol.stream);
                 }
             } else {
                 float* dg = dv_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * XBLK_FLOATS + lane;
 #pragma unroll
-                for (int i = 0; i < SK_BC; ++i) st_stream(dg + i * 32, dv[i]);
+                for (int i = 0; i < SK_BC; ++i) st_stream(dg + i * 32, dv[i], pol.stream);
             }
         };
         // role 1, one block: per-bone sums
@@ -557,9 +585,9 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                 dv_block(2 * seg);
                 dv_block(2 * seg + 1);
             } else {
-                load_xpairs(vbk, vb + (size_t)(2 * seg + 1) * XBLK_FLOATS);
+                load_xpairs(vbk, vb + (size_t)(2 * seg + 1) * XBLK_FLOATS, pol.stream);
                 da_block(2 * seg, va);
-                if (seg + 1 < SK_NSEG) load_xpairs(va, vb + (size_t)(2 * seg + 2) * XBLK_FLOATS);
+                if (seg + 1 < SK_NSEG) load_xpairs(va, vb + (size_t)(2 * seg + 2) * XBLK_FLOATS, pol.stream);
                 da_block(2 * seg + 1, vbk);
             }
         }
@@ -612,15 +640,15 @@ __global__ void t_to_rows_kernel(const void* __restrict__ blob, const float* __r
         if (c < pitch - NVC && h < B) rows[h * pitch + NVC + c] = 0.f;
     }
 }
-// bone[B][192] -> bone_t[group][192][32]
+// bone[B][16][12] -> bone_t[group][16][32][12]
 __global__ void bone_rows_to_t_kernel(const float* __restrict__ bone, int B, float* __restrict__ bone_t) {
     const long long n = (long long)((B + 31) >> 5) * GROUP_BONE_FLOATS;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int lane = (int)(i & 31);
-        const long long ge = i >> 5;
-        const int e = (int)(ge % (NJ * BONE_F));
-        const long long h = (ge / (NJ * BONE_F)) * 32 + lane;
-        bone_t[i] = h < B ? bone[h * (NJ * BONE_F) + e] : 0.f;
+        const int e = (int)(i % BONE_F);                       // bone_t[group][bone][lane][12]
+        const int lane = (int)((i / BONE_F) & 31);
+        const int k = (int)((i / (BONE_F * 32)) % NJ);
+        const long long h = (i / GROUP_BONE_FLOATS) * 32 + lane;
+        bone_t[i] = h < B ? bone[h * (NJ * BONE_F) + k * BONE_F + e] : 0.f;
     }
 }
 

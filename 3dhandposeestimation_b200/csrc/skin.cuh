@@ -8,7 +8,7 @@ namespace mb {
 // original coordinate (vertex*3 + c), -1 for padding.  Returns 0 or MB_E_MODEL.
 int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32_t* coord_map);
 
-// v_posed_t [groups][SK_NCOORD][32], bone_t [groups][192][32] (hand-minor) -> verts[B][778][3], tips -> joints
+// v_posed_t [groups][SK_NCOORD][32], bone_t [groups][16][32][12] -> verts[B][778][3], tips -> joints
 int launch_skin_forward(const void* blob, const float* v_posed_t, const float* bone_t, int B,
                         float* verts, float* joints, cudaStream_t s);
 // exactly one of dv_t (fp32, hand-minor block order) / dvp (bf16 hi+mid UMMA tiles) is non-NULL
