@@ -38,6 +38,8 @@ constexpr int SK_NBLK = (NV + SK_BV - 1) / SK_BV;          // 98 (the last segme
 constexpr int SK_NPOS = SK_NBLK * SK_BV;                   // 784 vertex positions (6 padding)
 constexpr int SK_NCOORD = SK_NPOS * 3;                     // 2352 coordinates per hand in block order
 constexpr int SK_MAX_ENT = 512;                            // (block, bone) pairs supported
+constexpr int SK_SLOTS = 6;                                // bone transforms a warp keeps resident in shared memory
+constexpr int SK_MAX_CMD = 256;                            // slot (re)load commands per sweep
 constexpr int SK_TMPL_PAD = 2400;                          // v_template in block order, padded to the GEMM's 15 x 160 columns
 
 // Device blob layout (byte offsets, every section 256-byte aligned).
@@ -57,7 +59,8 @@ struct BlobLayout {
     size_t csc_w;       // float [778*8]
     // skin program (skin.cu)
     size_t sk_blk_ptr;  // int32 [SK_NBLK + 1]       block -> range of (block, bone) entries
-    size_t sk_ent_bone; // int32 [SK_MAX_ENT]
+    size_t sk_ent_bone; // int32 [SK_MAX_ENT]        bone | slot << 4 | wait << 7 (slot schedule, see skin.cu)
+    size_t sk_cmd;      // int32 [SK_MAX_CMD + 1]    [0] = count; then (after_entry + 1) | slot << 10 | bone << 13 | next_group << 17
     size_t sk_ent_w;    // float [SK_MAX_ENT][8]     dense weights of the block's 8 vertices for that bone
     size_t sk_vloc;     // uint8 [SK_NPOS]           position -> vertex index inside its 16-segment (255 = padding)
     size_t sk_perm;     // int32 [SK_NPOS]           position -> original vertex (-1 = padding)
@@ -98,6 +101,7 @@ __host__ __device__ inline BlobLayout blob_layout() {
     L.csc_w = o;     o = align256(o + sizeof(float) * NV * MAX_INFL);
     L.sk_blk_ptr = o;  o = align256(o + sizeof(int32_t) * (SK_NBLK + 1));
     L.sk_ent_bone = o; o = align256(o + sizeof(int32_t) * SK_MAX_ENT);
+    L.sk_cmd = o;      o = align256(o + sizeof(int32_t) * (SK_MAX_CMD + 1));
     L.sk_ent_w = o;    o = align256(o + sizeof(float) * SK_MAX_ENT * SK_BV);
     L.sk_vloc = o;     o = align256(o + SK_NPOS);
     L.sk_perm = o;     o = align256(o + sizeof(int32_t) * SK_NPOS);

@@ -83,11 +83,11 @@ __device__ __forceinline__ void st_stream4u(void* p, const uint4& v, uint64_t po
 }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
 
-// shared-memory copy of the skin program (22.7 KB), with the address arithmetic folded in
+// shared-memory copy of the skin program (23.7 KB), with the address arithmetic folded in
 struct SkinProg {
     int blk_ptr[SK_NBLK + 1];
-    int ent_code[SK_MAX_ENT];                    // bits 0-15: bone * 12 * 32 = float offset of the bone inside a group of
-                                                 // bone_t; bits 16-23: which of the block's 8 vertices have a non-zero weight
+    int ent_code[SK_MAX_ENT];                    // bone | slot << 4 | wait << 7 (slot schedule of skin_pack)
+    int cmd[SK_MAX_CMD + 1];                     // [0] = count, then slot (re)load commands sorted by `after`
     alignas(16) float ent_w[SK_MAX_ENT][SK_BV];
     alignas(16) int voff[SK_NPOS];               // float offset of the vertex' x inside a tile: vl * 3 * TP
 };
@@ -101,11 +101,10 @@ __device__ __forceinline__ void stage_prog(SkinProg& P, const void* blob) {
     const uint8_t* vl = blob_ptr<uint8_t>(blob, L.sk_vloc);
     for (int i = threadIdx.x; i <= SK_NBLK; i += blockDim.x) P.blk_ptr[i] = bp[i];
     const int ne = bp[SK_NBLK];
-    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
-        int mask = 0;
-        for (int j = 0; j < SK_BV; ++j) mask |= (ew[i * SK_BV + j] != 0.f) << j;
-        P.ent_code[i] = eb[i] * (BONE_F * 32) | (mask << 16);
-    }
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) P.ent_code[i] = eb[i];
+    const int* cm = blob_ptr<int>(blob, L.sk_cmd);
+    const int ncmd = cm[0];
+    for (int i = threadIdx.x; i <= ncmd; i += blockDim.x) P.cmd[i] = cm[i];
     for (int i = threadIdx.x; i < ne * SK_BV; i += blockDim.x) (&P.ent_w[0][0])[i] = ew[i];
     // padding positions (only in the last block, whose segment uses 10 of its 16 vertex slots) are
     // parked on the last slot of the tile: written / read like any vertex, never stored, weights all zero
@@ -177,13 +176,68 @@ __device__ __forceinline__ const float* ring_wait(Ring<STAGES, SLOT_FLOATS>& R, 
     return R.slot[st];
 }
 
-constexpr int FSTAGES = 4;                         // bone slots per warp, forward
-constexpr int BSTAGES = 2;                         // bone slots per pair, backward (measured: 2 beats 4 by 20 %)
 constexpr int XSTAGES = 2;
-constexpr int BONE_SLOT_FLOATS = BONE_F * 32;
-typedef Ring<FSTAGES, BONE_SLOT_FLOATS> FwdBoneRing;
-typedef Ring<BSTAGES, BONE_SLOT_FLOATS> BoneRing;
+constexpr int BONE_SLOT_FLOATS = BONE_F * 32;      // one bone of a hand group: [lane][12], 1.5 KB contiguous in bone_t
 typedef Ring<XSTAGES, XBLK_FLOATS> XRing;
+
+// ------------------------------------------------------------------ resident bones
+// SK_SLOTS bone transforms of the warp's hand group stay in shared memory; skin_pack's static
+// schedule says which slot an entry reads, when that is the first read after a (re)load (wait on the
+// slot's mbarrier) and after which entry a slot is refilled (bulk copy issued by an elected lane).
+struct alignas(128) BoneCache {
+    alignas(128) float slot[SK_SLOTS][BONE_SLOT_FLOATS];
+    alignas(8) unsigned long long full[SK_SLOTS];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < SK_SLOTS; ++s) mbar_init(smem_u32(&full[s]), 1);
+    }
+};
+struct CacheState { int ci, next_after; unsigned parity; };    // identical in every lane
+__device__ __forceinline__ void cache_issue(BoneCache& K, int c, const float* __restrict__ group_base, uint64_t pol) {
+    const int slot = (c >> 10) & 7, bone = (c >> 13) & 15;
+    __syncwarp();                                             // every lane is done reading the slot's previous occupant
+    if (elect_one()) {
+        const uint32_t bar = smem_u32(&K.full[slot]);
+        mbar_expect_tx(bar, BONE_SLOT_FLOATS * 4);
+        bulk_g2s_hint(smem_u32(K.slot[slot]), group_base + bone * BONE_SLOT_FLOATS, BONE_SLOT_FLOATS * 4, bar, pol);
+    }
+}
+// a warp's first group: nothing was prefetched by a previous sweep
+__device__ __forceinline__ void cache_prologue(BoneCache& K, const SkinProg& P, const float* __restrict__ group_base, uint64_t pol) {
+    const int ncmd = P.cmd[0];
+    for (int i = 0; i < ncmd; ++i) {
+        const int c = P.cmd[1 + i];
+        if ((c >> 17) & 1) cache_issue(K, c, group_base, pol);
+    }
+}
+__device__ __forceinline__ void cache_begin_group(CacheState& S, const SkinProg& P) {
+    S.ci = 0;
+    S.next_after = P.cmd[0] > 0 ? (P.cmd[1] & 1023) : (1 << 30);
+}
+// after entry e has been consumed: issue the loads scheduled behind it (group_base = this group's
+// bones; the next group's are next_off floats further when it exists)
+__device__ __forceinline__ void cache_after_entry(BoneCache& K, CacheState& S, const SkinProg& P, int e,
+                                                  const float* __restrict__ group_base, bool has_next, size_t next_off,
+                                                  uint64_t pol) {
+    while (S.next_after == e + 1) {
+        const int c = P.cmd[1 + S.ci];
+        if ((c >> 17) & 1) { if (has_next) cache_issue(K, c, group_base + next_off, pol); }
+        else cache_issue(K, c, group_base, pol);
+        ++S.ci;
+        S.next_after = S.ci < P.cmd[0] ? (P.cmd[1 + S.ci] & 1023) : (1 << 30);
+    }
+}
+// the slot of an entry, ready to read (lane = hand: 48 bytes at lane * 12)
+__device__ __forceinline__ const float4* cache_entry(BoneCache& K, CacheState& S, int code, int lane) {
+    const int slot = (code >> 4) & 7;
+    if (code & 128) {
+        const uint32_t bar = smem_u32(&K.full[slot]);
+        const uint32_t par = (S.parity >> slot) & 1;
+        while (!mbar_try_wait(bar, par)) {}
+        S.parity ^= 1u << slot;
+    }
+    return reinterpret_cast<const float4*>(K.slot[slot] + lane * BONE_F);
+}
 
 // ------------------------------------------------------------------ forward
 // Packed fp32 (FFMA2, sm_100): two vertices of the block per instruction, the bone element is the
@@ -206,10 +260,10 @@ __device__ __forceinline__ void fma_entry2(const float (&A)[BONE_F], const float
         }
     }
 }
-constexpr int SKF_WARPS = 10;                      // autonomous warps per CTA; 1 CTA per SM
+constexpr int SKF_WARPS = 9;                       // autonomous warps per CTA; 1 CTA per SM
 constexpr int SKF_THREADS = SKF_WARPS * 32;
 struct alignas(128) FwdWarpShared {
-    FwdBoneRing bones;                                       // slots are [lane][12]
+    BoneCache bones;
     XRing xs;
     alignas(16) float tile[TILE_FLOATS];
 };
@@ -278,19 +332,21 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
     const float* ts = W.tile + rm.tile_base();                // store side
     const int ngroups = (B + 31) >> 5;
     const int g0 = blockIdx.x + warp * gridDim.x, gstep = gridDim.x * SKF_WARPS;
-    const int ne = P.blk_ptr[SK_NBLK];
-    auto bone_src = [&](int g, int e) { return bone_t + (size_t)g * GROUP_BONE_FLOATS + (P.ent_code[e] & 0xffff); };
     auto x_src = [&](int g, int blk) { return v_posed_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * XBLK_FLOATS; };
     const L2Policies pol = make_policies();
-    Cursor CB = {g0, 0, 0u, 0u}, CX = {g0, 0, 0u, 0u};
-#pragma unroll
-    for (int s = 0; s < FSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
+    Cursor CX = {g0, 0, 0u, 0u};
 #pragma unroll
     for (int s = 0; s < XSTAGES; ++s) ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src, pol.stream);
+    CacheState CS = {0, 0, 0u};
+    if (g0 < ngroups) cache_prologue(W.bones, P, bone_t + (size_t)g0 * GROUP_BONE_FLOATS, pol.keep);
+    const size_t next_off = (size_t)gstep * GROUP_BONE_FLOATS;
 
     for (int g = g0; g < ngroups; g += gstep) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
         float* vrow = verts + (size_t)g * 32 * NVC + rm.row_base();
+        const float* bgrp = bone_t + (size_t)g * GROUP_BONE_FLOATS;
+        const bool has_next = g + gstep < ngroups;
+        cache_begin_group(CS, P);
 #pragma unroll 1
         for (int blk = 0; blk < SK_NBLK; ++blk) {
             float2 X[3][4], ACC[3][4];
@@ -307,11 +363,9 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
             for (int e = P.blk_ptr[blk]; e < e1; ++e) {
                 float w[SK_BV];
                 load_w(P, e, w);
-                const float4* sl = reinterpret_cast<const float4*>(ring_wait(W.bones, CB) + lane * BONE_F);
+                const float4* sl = cache_entry(W.bones, CS, P.ent_code[e], lane);
                 const float4 a0 = sl[0], a1 = sl[1], a2 = sl[2];
-                ++CB.consumed;
-                __syncwarp();
-                ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
+                cache_after_entry(W.bones, CS, P, e, bgrp, has_next, next_off, pol.keep);
                 const float A[BONE_F] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
                 fma_entry2(A, w, X, ACC);
             }
@@ -344,11 +398,11 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
 }
 
 // ----------------------------------------------------------------- backward
-constexpr int SKB_PAIRS = 5;
+constexpr int SKB_PAIRS = 4;
 constexpr int SKB_THREADS = SKB_PAIRS * 64;
 constexpr int DP = 33;                             // accumulator pitch: element (e, hand) at e * 33 + hand
 struct alignas(128) BwdPairShared {
-    BoneRing bones;                                          // role 0
+    BoneCache bones;                                         // role 0
     alignas(16) float tile[TILE_FLOATS];                     // upstream gradient of one 16-vertex segment, transposed
     alignas(16) float dacc[NJ * BONE_F * DP];                // per-bone 3x4 sums of the group (role 1 only)
 };
@@ -391,7 +445,7 @@ __device__ __forceinline__ void skin_block_da(const SkinProg& P, int blk, float*
     for (int e = P.blk_ptr[blk]; e < e1; ++e) {
         float w[SK_BV];
         load_w(P, e, w);
-        float* d = dl + ((P.ent_code[e] & 0xffff) >> 5) * DP;
+        float* d = dl + (P.ent_code[e] & 15) * (BONE_F * DP);
         float2 a[BONE_F];
 #pragma unroll
         for (int i = 0; i < BONE_F; ++i) a[i] = make_float2(d[i * DP], 0.f);
@@ -440,18 +494,17 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
     const int bar = 1 + pair;
     const int ngroups = (B + 31) >> 5;
     const int g0 = blockIdx.x + pair * gridDim.x, gstep = gridDim.x * SKB_PAIRS;
-    const int ne = P.blk_ptr[SK_NBLK];
-    auto bone_src = [&](int g, int e) { return bone_t + (size_t)g * GROUP_BONE_FLOATS + (P.ent_code[e] & 0xffff); };
     const L2Policies pol = make_policies();
-    Cursor CB = {g0, 0, 0u, 0u};
-    if (role == 0) {
-#pragma unroll
-        for (int s = 0; s < BSTAGES; ++s) ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
-    }
+    CacheState CS = {0, 0, 0u};
+    if (role == 0 && g0 < ngroups) cache_prologue(W.bones, P, bone_t + (size_t)g0 * GROUP_BONE_FLOATS, pol.keep);
+    const size_t next_off = (size_t)gstep * GROUP_BONE_FLOATS;
 
     for (int g = g0; g < ngroups; g += gstep) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
         const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
+        const float* bgrp = bone_t + (size_t)g * GROUP_BONE_FLOATS;
+        const bool has_next = g + gstep < ngroups;
+        cache_begin_group(CS, P);
         const float* grow = g_verts + (size_t)g * 32 * NVC + rm.row_base();
         // each role loads half of a segment's row pieces (one instruction = 4 rows x 8 float2) into
         // registers one segment ahead of its use
@@ -503,13 +556,11 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                 float A[11], w[SK_BV];
                 load_w(P, e, w);
                 {
-                    const float4* sl = reinterpret_cast<const float4*>(ring_wait(W.bones, CB) + lane * BONE_F);   // [lane][12]
+                    const float4* sl = cache_entry(W.bones, CS, P.ent_code[e], lane);
                     const float4 a0 = sl[0], a1 = sl[1], a2 = sl[2];
                     A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
                     A[8] = a2.x; A[9] = a2.y; A[10] = a2.z;
-                    ++CB.consumed;
-                    __syncwarp();
-                    ring_request(W.bones, CB, ngroups, gstep, ne, lane, bone_src, pol.keep);
+                    cache_after_entry(W.bones, CS, P, e, bgrp, has_next, next_off, pol.keep);
                 }
                 dv_entry2(A, w, G, DV);
             }
@@ -661,8 +712,20 @@ inline int conv_grid(long long n) {
 }  // namespace
 
 // ---------------------------------------------------------------- host: skin program
-// Greedy grouping inside each 32-vertex segment: start a block with the vertex that has the most
-// bones, then keep adding the vertex that enlarges the block's bone set least.
+// 1. Blocks: every 16-vertex segment is split into two blocks of 8 so that the two blocks' bone sets
+//    are as small as possible (exhaustive over the C(16,8)/2 splits: 6 435 per segment).
+// 2. Slot schedule: a warp keeps SK_SLOTS bone transforms of its hand group resident in shared
+//    memory.  The order in which a sweep touches bones is static, so the replacement policy is
+//    Belady's (evict the bone whose next use is farthest) computed here, and every (re)load is issued
+//    right after the LAST use of the bone it replaces — typically dozens of entries before its own
+//    first use, so the bulk copy's latency is hidden without a deep ring, and a bone is fetched
+//    ~5 times per sweep instead of once per (block, bone) entry (~29 times).  [round-1 ncu: the
+//    per-entry ring ran the skinning kernels at the L2 bandwidth limit — 58 KB of L2 sector
+//    traffic per hand, 21.6 KB of it bone re-reads]
+//    Per entry: bone | slot << 4 | wait << 7 (wait = first use after a load: wait on the slot's mbarrier).
+//    Commands, sorted by `after`: issue "slot <- bone" once entry `after` has been consumed;
+//    next_group marks the loads of the following group's first occupants, issued during this
+//    group's tail (and by the prologue for a warp's first group).
 int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32_t* coord_map) {
     const BlobLayout L = blob_layout();
     char* out = reinterpret_cast<char*>(host_blob);
@@ -671,6 +734,7 @@ int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32
     float* ent_w = reinterpret_cast<float*>(out + L.sk_ent_w);
     uint8_t* vloc = reinterpret_cast<uint8_t*>(out + L.sk_vloc);
     int* perm = reinterpret_cast<int*>(out + L.sk_perm);
+    int* cmd = reinterpret_cast<int*>(out + L.sk_cmd);
 
     std::vector<unsigned> mask(NV, 0u);
     std::vector<float> dense((size_t)NV * NJ, 0.f);
@@ -686,46 +750,87 @@ int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32
     auto pop = [](unsigned x) { return __builtin_popcount(x); };
     int nblk = 0, ne = 0;
     for (int seg = 0; seg < SK_NSEG; ++seg) {
-        std::vector<int> rem;
-        for (int v = seg * SK_SEG; v < NV && v < (seg + 1) * SK_SEG; ++v) rem.push_back(v);
-        while (!rem.empty()) {
-            size_t bi = 0;
-            for (size_t i = 1; i < rem.size(); ++i)
-                if (pop(mask[rem[i]]) > pop(mask[rem[bi]])) bi = i;
-            int grp[SK_BV];
-            int n = 0;
-            unsigned u = mask[rem[bi]];
-            grp[n++] = rem[bi];
-            rem.erase(rem.begin() + bi);
-            while (n < SK_BV && !rem.empty()) {
-                size_t best = 0;
-                for (size_t i = 1; i < rem.size(); ++i) {
-                    const int gi = pop(mask[rem[i]] & ~u), gb = pop(mask[rem[best]] & ~u);
-                    if (gi < gb || (gi == gb && pop(mask[rem[i]] & u) > pop(mask[rem[best]] & u))) best = i;
-                }
-                u |= mask[rem[best]];
-                grp[n++] = rem[best];
-                rem.erase(rem.begin() + best);
+        const int v0 = seg * SK_SEG;
+        const int n = (NV - v0) < SK_SEG ? (NV - v0) : SK_SEG;
+        unsigned best_sel = 0;
+        if (n > SK_BV) {
+            // choose which n - 8 (or 8) vertices go to the second block; vertex 0 stays in the first
+            int best_cost = 1 << 30;
+            const int n1 = SK_BV;                              // first block is full, the second takes the rest
+            for (unsigned sel = 1; sel < (1u << n); sel += 2) {   // bit i = vertex i in the first block; bit 0 fixed
+                if (pop(sel) != n1) continue;
+                unsigned ua = 0, ub = 0;
+                for (int i = 0; i < n; ++i) ((sel >> i) & 1 ? ua : ub) |= mask[v0 + i];
+                const int cost = pop(ua) + pop(ub);
+                if (cost < best_cost) { best_cost = cost; best_sel = sel; }
             }
-            std::sort(grp, grp + n);
-            if (nblk >= SK_NBLK) return MB_E_MODEL;
+        } else {
+            best_sel = (1u << n) - 1;
+        }
+        for (int half = 0; half < 2; ++half) {
+            int grp[SK_BV];
+            int m = 0;
+            unsigned u = 0;
+            for (int i = 0; i < n; ++i)
+                if ((int)((best_sel >> i) & 1) == (half == 0 ? 1 : 0)) { grp[m++] = v0 + i; u |= mask[v0 + i]; }
+            if (m > SK_BV || nblk >= SK_NBLK) return MB_E_MODEL;
             blk_ptr[nblk] = ne;
             for (int j = 0; j < SK_BV; ++j) {
-                perm[nblk * SK_BV + j] = j < n ? grp[j] : -1;
-                vloc[nblk * SK_BV + j] = j < n ? (uint8_t)(grp[j] - seg * SK_SEG) : (uint8_t)255;
+                perm[nblk * SK_BV + j] = j < m ? grp[j] : -1;
+                vloc[nblk * SK_BV + j] = j < m ? (uint8_t)(grp[j] - v0) : (uint8_t)255;
             }
             for (int k = 0; k < NJ; ++k) {
                 if (!(u & (1u << k))) continue;
                 if (ne >= SK_MAX_ENT) return MB_E_MODEL;
                 ent_bone[ne] = k;
-                for (int j = 0; j < SK_BV; ++j) ent_w[ne * SK_BV + j] = j < n ? dense[(size_t)grp[j] * NJ + k] : 0.f;
+                for (int j = 0; j < SK_BV; ++j) ent_w[ne * SK_BV + j] = j < m ? dense[(size_t)grp[j] * NJ + k] : 0.f;
                 ++ne;
             }
+            if (ne == blk_ptr[nblk]) return MB_E_MODEL;       // a block without any bone (vertex without weights)
             ++nblk;
         }
     }
     if (nblk != SK_NBLK) return MB_E_MODEL;
     blk_ptr[SK_NBLK] = ne;
+
+    // ---- slot schedule (Belady) ----
+    {
+        std::vector<int> next_use(ne), last_seen(NJ, 1 << 30);
+        for (int e = ne - 1; e >= 0; --e) { next_use[e] = last_seen[ent_bone[e]]; last_seen[ent_bone[e]] = e; }
+        int slot_bone[SK_SLOTS], slot_next[SK_SLOTS], slot_last[SK_SLOTS];   // occupant, its next use, its last use so far
+        for (int s = 0; s < SK_SLOTS; ++s) { slot_bone[s] = -1; slot_next[s] = 1 << 30; slot_last[s] = -1; }
+        struct Cmd { int after, slot, bone, next_group; };
+        std::vector<Cmd> cmds;
+        std::vector<int> first_load_of_slot(SK_SLOTS, -1);
+        for (int e = 0; e < ne; ++e) {
+            const int k = ent_bone[e];
+            int s = -1;
+            for (int t = 0; t < SK_SLOTS; ++t) if (slot_bone[t] == k) s = t;
+            int wait = 0;
+            if (s < 0) {
+                for (int t = 0; t < SK_SLOTS && s < 0; ++t) if (slot_bone[t] < 0) s = t;      // an empty slot first
+                if (s < 0) { s = 0; for (int t = 1; t < SK_SLOTS; ++t) if (slot_next[t] > slot_next[s]) s = t; }
+                Cmd c = {slot_last[s], s, k, 0};
+                if (slot_bone[s] < 0) { c.after = -2; c.next_group = 1; first_load_of_slot[s] = (int)cmds.size(); }
+                cmds.push_back(c);
+                slot_bone[s] = k;
+                wait = 1;
+            }
+            slot_next[s] = next_use[e];
+            slot_last[s] = e;
+            ent_bone[e] = k | (s << 4) | (wait << 7);
+        }
+        // the first occupant of a slot is loaded for the NEXT group once this group is done with the slot
+        for (int s = 0; s < SK_SLOTS; ++s)
+            if (first_load_of_slot[s] >= 0) cmds[first_load_of_slot[s]].after = slot_last[s];
+        std::stable_sort(cmds.begin(), cmds.end(), [](const Cmd& a, const Cmd& b) { return a.after < b.after; });
+        if ((int)cmds.size() > SK_MAX_CMD) return MB_E_MODEL;
+        cmd[0] = (int)cmds.size();
+        for (size_t i = 0; i < cmds.size(); ++i) {
+            if (cmds[i].after < 0 || cmds[i].after >= 1023) return MB_E_MODEL;
+            cmd[1 + i] = (cmds[i].after + 1) | (cmds[i].slot << 10) | (cmds[i].bone << 13) | (cmds[i].next_group << 17);
+        }
+    }
     for (int c = 0; c < SK_TMPL_PAD; ++c) {
         const int p = c / 3;
         coord_map[c] = (p < SK_NPOS && perm[p] >= 0) ? perm[p] * 3 + c % 3 : -1;
