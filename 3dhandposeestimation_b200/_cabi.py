@@ -34,6 +34,7 @@ SIGNATURES = {
     "mb_mano_blob_bytes": (_sz, []),
     "mb_mano_pack_constants": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "mb_mano_model_flags": (_i, [_p]),
+    "mb_mano_skin_program_stats": (_i, [_p, _p]),
     "mb_mano_workspace_bytes": (_sz, [_i, _i]),
     "mb_mano_forward": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "mb_mano_backward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),

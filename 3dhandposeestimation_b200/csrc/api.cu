@@ -176,7 +176,12 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
         for (int c = 0; c < SK_TMPL_PAD; ++c) tm[c] = coord_map[c] >= 0 ? basis[(size_t)FEAT_ONE * NVC + coord_map[c]] : 0.f;
     }
     blend_tc_pack(basis, coord_map.data(), out + L.total);
-    return 0;
+    return skin_program_check(host_blob, nullptr);
+}
+
+extern "C" int mb_mano_skin_program_stats(const void* host_blob, int32_t* stats4) {
+    if (!host_blob || !stats4) return MB_E_NULL;
+    return skin_program_check(host_blob, stats4);
 }
 
 extern "C" int mb_mano_model_flags(const int32_t* parents) {

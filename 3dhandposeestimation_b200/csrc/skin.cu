@@ -838,6 +838,69 @@ int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32
     return 0;
 }
 
+// Host-side verification of a packed skin program (used by tests/ and by mb_mano_pack_constants itself):
+// replays the slot schedule and checks that every entry reads the bone it expects from a slot whose
+// load was issued earlier, that loads only replace occupants that are not used again before, and
+// that the blocks partition the vertices.  stats[0..3] = entries, commands (loads per sweep), blocks, max bones per block.
+int skin_program_check(const void* host_blob, int32_t* stats) {
+    const BlobLayout L = blob_layout();
+    const char* in = reinterpret_cast<const char*>(host_blob);
+    const int* blk_ptr = reinterpret_cast<const int*>(in + L.sk_blk_ptr);
+    const int* ent = reinterpret_cast<const int*>(in + L.sk_ent_bone);
+    const float* ent_w = reinterpret_cast<const float*>(in + L.sk_ent_w);
+    const uint8_t* vloc = reinterpret_cast<const uint8_t*>(in + L.sk_vloc);
+    const int* perm = reinterpret_cast<const int*>(in + L.sk_perm);
+    const int* cmd = reinterpret_cast<const int*>(in + L.sk_cmd);
+    const int ne = blk_ptr[SK_NBLK], ncmd = cmd[0];
+    if (ne <= 0 || ne > SK_MAX_ENT || ncmd <= 0 || ncmd > SK_MAX_CMD) return MB_E_MODEL;
+    // blocks: a permutation of the vertices, 8 per block, inside their 16-vertex segment
+    std::vector<int> seen(NV, 0);
+    int max_bones = 0;
+    for (int b = 0; b < SK_NBLK; ++b) {
+        if (blk_ptr[b + 1] <= blk_ptr[b]) return MB_E_MODEL;
+        max_bones = std::max(max_bones, blk_ptr[b + 1] - blk_ptr[b]);
+        for (int j = 0; j < SK_BV; ++j) {
+            const int v = perm[b * SK_BV + j];
+            if (v < 0) { if (vloc[b * SK_BV + j] != 255) return MB_E_MODEL; continue; }
+            if (v >= NV || seen[v]++ || v / SK_SEG != b / SK_SEG_BLKS || vloc[b * SK_BV + j] != v % SK_SEG) return MB_E_MODEL;
+        }
+        for (int e = blk_ptr[b]; e < blk_ptr[b + 1]; ++e)
+            for (int j = 0; j < SK_BV; ++j)
+                if (perm[b * SK_BV + j] < 0 && ent_w[e * SK_BV + j] != 0.f) return MB_E_MODEL;
+    }
+    for (int v = 0; v < NV; ++v) if (!seen[v]) return MB_E_MODEL;
+    // slot schedule: replay two consecutive groups (the second one starts from the prefetched state)
+    int slot_bone[SK_SLOTS], slot_group[SK_SLOTS];
+    bool slot_waited[SK_SLOTS];
+    for (int s = 0; s < SK_SLOTS; ++s) { slot_bone[s] = -1; slot_group[s] = -1; slot_waited[s] = true; }
+    auto issue = [&](int c, int group) -> bool {
+        const int s = (c >> 10) & 7, k = (c >> 13) & 15;
+        if (s >= SK_SLOTS || !slot_waited[s]) return false;    // previous load of the slot never consumed
+        slot_bone[s] = k; slot_group[s] = group; slot_waited[s] = false;
+        return true;
+    };
+    for (int i = 0; i < ncmd; ++i)
+        if ((cmd[1 + i] >> 17) & 1) { if (!issue(cmd[1 + i], 0)) return MB_E_MODEL; }
+    for (int group = 0; group < 2; ++group) {
+        int ci = 0;
+        for (int e = 0; e < ne; ++e) {
+            const int k = ent[e] & 15, s = (ent[e] >> 4) & 7, wait = (ent[e] >> 7) & 1;
+            if (s >= SK_SLOTS || slot_bone[s] != k || slot_group[s] != group) return MB_E_MODEL;
+            if (wait) { if (slot_waited[s]) return MB_E_MODEL; slot_waited[s] = true; }
+            else if (!slot_waited[s]) return MB_E_MODEL;       // reading a slot whose load was never waited for
+            while (ci < ncmd && (cmd[1 + ci] & 1023) == e + 1) {
+                const int c = cmd[1 + ci];
+                if (!issue(c, group + ((c >> 17) & 1))) return MB_E_MODEL;
+                ++ci;
+            }
+            if (ci < ncmd && (cmd[1 + ci] & 1023) < e + 1) return MB_E_MODEL;   // commands must be sorted
+        }
+        if (ci != ncmd) return MB_E_MODEL;
+    }
+    if (stats) { stats[0] = ne; stats[1] = ncmd; stats[2] = SK_NBLK; stats[3] = max_bones; }
+    return 0;
+}
+
 // ---------------------------------------------------------------- launchers
 int launch_skin_forward(const void* blob, const float* v_posed_t, const float* bone_t, int B,
                         float* verts, float* joints, cudaStream_t s) {

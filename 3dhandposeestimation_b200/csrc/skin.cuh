@@ -8,6 +8,9 @@ namespace mb {
 // original coordinate (vertex*3 + c), -1 for padding.  Returns 0 or MB_E_MODEL.
 int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32_t* coord_map);
 
+// replays the packed program's slot schedule on the host; stats[4] = entries, loads per sweep, blocks, max bones per block
+int skin_program_check(const void* host_blob, int32_t* stats);
+
 // v_posed_t [groups][SK_NCOORD][32], bone_t [groups][16][32][12] -> verts[B][778][3], tips -> joints
 int launch_skin_forward(const void* blob, const float* v_posed_t, const float* bone_t, int B,
                         float* verts, float* joints, cudaStream_t s);

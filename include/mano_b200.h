@@ -85,6 +85,10 @@ MB_API int    mb_mano_pack_constants(const float* basis, const float* j0, const 
                               const float* skin_w, const int32_t* skin_b,
                               const int32_t* parents, void* host_blob);
 
+/* Re-validates the skinning program inside a packed HOST blob (block partition + shared-memory slot
+ * schedule) and reports stats4 = {(block, bone) entries, bone loads per sweep, blocks, max bones per block}. */
+MB_API int    mb_mano_skin_program_stats(const void* host_blob, int32_t* stats4);
+
 /* Model property bits (MB_MODEL_*) of a kinematic tree, to be OR-ed into `mode`. */
 MB_API int    mb_mano_model_flags(const int32_t* parents);
 

@@ -175,3 +175,48 @@ def test_device_fk_math_on_host(hostlib, swap):
         ora, ooa, obl = fo.fk_backward(ra, oa, bl, K, s, root, a, b, joint_order_switched=not swap)
         for got, want in ((gra, ora), (goa, ooa), (gbl, obl)):
             assert np.abs(got - want).max() / np.abs(want).max() < 1e-4
+
+
+def _pack_host_blob(pkg, model, nc=45):
+    lib = pkg.load_library()
+    packed = pkg.assets.pack_mano(model, nc)
+    host = np.zeros(lib.mb_mano_blob_bytes(), dtype=np.uint8)
+    keep = [np.ascontiguousarray(a) for a in (packed.basis, packed.j0, packed.jb, packed.pca, packed.pose_mean,
+                                              packed.skin_w, packed.skin_b.astype(np.int32), packed.parents.astype(np.int32))]
+    args = [a.ctypes.data_as(C.c_void_p) for a in keep]
+    rc = lib.mb_mano_pack_constants(args[0], args[1], args[2], args[3], nc, args[4], args[5], args[6], args[7],
+                                    host.ctypes.data_as(C.c_void_p))
+    return rc, host, keep
+
+
+def test_skin_program_schedule_is_valid(pkg, synth_model):
+    """The skinning kernels trust a host-built program: blocks of 8 vertices inside 16-vertex segments
+    and a static (Belady) schedule of which shared-memory slot holds which bone when.  The library
+    replays the schedule on the host over two consecutive hand groups; here the replay must accept the
+    synthetic model (and the real MANO pickle when the reference checkout is present) and the bone
+    loads per sweep must stay far below one per (block, bone) entry."""
+    lib = pkg.load_library()
+    models = [("synthetic", synth_model)]
+    real = "/root/reference/config/mano/models/MANO_RIGHT.pkl"
+    if os.path.isfile(real):
+        models.append(("real", pkg.assets.read_mano_pkl(real)))
+    for name, model in models:
+        rc, host, _ = _pack_host_blob(pkg, model)
+        assert rc == 0, name
+        stats = (C.c_int32 * 4)()
+        assert lib.mb_mano_skin_program_stats(host.ctypes.data_as(C.c_void_p), stats) == 0, name
+        entries, loads, blocks, max_bones = list(stats)
+        assert blocks == 98 and 98 <= entries <= 512 and max_bones <= 12, (name, list(stats))
+        assert loads < entries // 2, (name, list(stats))
+    # an empty (all-zero) blob is rejected
+    bad = np.zeros_like(host)
+    assert lib.mb_mano_skin_program_stats(bad.ctypes.data_as(C.c_void_p), stats) == -5
+
+
+def test_model_flags(pkg, synth_model):
+    lib = pkg.load_library()
+    parents = pkg.assets.pack_mano(synth_model, 45).parents.astype(np.int32)
+    assert lib.mb_mano_model_flags(parents.ctypes.data_as(C.c_void_p)) == 0x100
+    other = parents.copy()
+    other[5] = 1
+    assert lib.mb_mano_model_flags(other.ctypes.data_as(C.c_void_p)) == 0
