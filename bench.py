@@ -36,9 +36,22 @@ UNIT = "hands/s"
 # algorithmic bytes per hand (SURVEY 8d / BASELINE.md 4), fp32, nc = 45
 BYTES_FWD = 4 * (3 + 45 + 10) + 4 * (2334 + 63)                 # 9820
 BYTES_BWD = 4 * (2334 + 63) + 4 * (3 + 45 + 10) * 2             # 10052
-BYTES_LBS = 4 * (2334 + 192) + 4 * (2334 + 15)                  # stand-alone LBS stage: 19500 (+ 192 B tips rounding) ~ 19.7 KB
-BYTES_LBS = 19692
+BYTES_LBS = 19692                                               # stand-alone LBS forward: v_posed 9336 + bones 768 in, verts 9336 + tips 252 out
+# stand-alone LBS backward: g_verts 9336 + tip grads 60 + v_posed_t 9408 + bones 768 in,
+# dv_posed tiles (bf16 hi+mid, 4 B per coordinate) 9408 + per-bone sums 768 out
+BYTES_LBS_BWD = 9336 + 60 + 9408 + 768 + 9408 + 768             # 29748
 FLOP_BLEND = 2 * 145 * 2334                                     # 676860 per hand per contraction
+STAGE_KERNEL = {"pose_fwd": "pose_forward_lh_kernel", "blend_fwd": "blend_tc_forward_kernel", "lbs_fwd": "skin_forward_kernel",
+                "lbs_bwd": "skin_backward_kernel", "blend_bwd": "blend_tc_backward_kernel", "pose_bwd": "pose_backward_lh_kernel"}
+
+
+def ncu_traffic_per_hand():
+    """DRAM bytes per hand per kernel from the committed `ncu --set full` capture (profiles/r1/traffic_final.json)."""
+    path = os.path.join(ROOT, "profiles", "r1", "traffic_final.json")
+    if not os.path.isfile(path):
+        return {}
+    d = json.load(open(path))["kernels"]
+    return {k: (v["dram_read_bytes"] + v["dram_write_bytes"]) / v["hands"] for k, v in d.items()}
 
 
 def load_peaks():
@@ -301,17 +314,30 @@ def main():
     tot_stage_ms = sum(s["ms"] for s in stages.values())
     for k, s in stages.items():
         s["share"] = s["ms"] / tot_stage_ms
-    lbs_ms = stages["lbs_fwd"]["ms"]
-    lbs_gbs = BYTES_LBS * H / (lbs_ms * 1e-3) / 1e9
+    traffic = ncu_traffic_per_hand()
+
+    def hbm_roofline(stage, bytes_per_hand):
+        ms = stages[stage]["ms"]
+        gbs = bytes_per_hand * H / (ms * 1e-3) / 1e9
+        kern = STAGE_KERNEL[stage]
+        return {"kernel": kern, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"], "traffic": traffic[kern] * H if kern in traffic else None,
+                "traffic_source": "ncu dram__bytes_read+write per hand (profiles/r1/traffic_final.json) x hands" if kern in traffic else None,
+                "peak_source": peaks["source"], "algorithmic_bytes_per_hand": bytes_per_hand, "avg_launch_ms": ms,
+                "share_of_step": stages[stage]["share"]}
+
+    dominant = max(stages, key=lambda k: stages[k]["ms"])
+    lbs_fwd_roof = hbm_roofline("lbs_fwd", BYTES_LBS)
+    lbs_bwd_roof = hbm_roofline("lbs_bwd", BYTES_LBS_BWD)
+    # `roofline` is the dominant kernel of the step (the skinning backward); the north star's named
+    # "LBS GB/s" figure — the skinning forward — is reported next to it
+    roofline = dict(lbs_bwd_roof if dominant == "lbs_bwd" else lbs_fwd_roof, dominant_stage=dominant)
     blend_ms = stages["blend_fwd"]["ms"]
     blend_tflops = FLOP_BLEND * H / (blend_ms * 1e-3) / 1e12
-    dominant = max(stages, key=lambda k: stages[k]["ms"])
-    roofline = {"kernel": "skin_forward_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                "algorithmic_bytes_per_hand": BYTES_LBS, "avg_launch_ms": lbs_ms, "dominant_stage": dominant}
-    blend_roof = {"kernel": "blend_fwd", "bound": "tensor", "achieved": blend_tflops, "peak": peaks["bf16_tflops_sustained"],
+    blend_roof = {"kernel": "blend_tc_forward_kernel", "bound": "tensor", "achieved": blend_tflops, "peak": peaks["bf16_tflops_sustained"],
                   "unit": "TFLOP/s", "frac": blend_tflops / peaks["bf16_tflops_sustained"],
-                  "algorithmic_flop_per_hand": FLOP_BLEND, "avg_launch_ms": blend_ms, "mode": args.mode}
+                  "algorithmic_flop_per_hand": FLOP_BLEND, "avg_launch_ms": blend_ms, "mode": args.mode,
+                  "note": "3 fp16 products per algorithmic FLOP are executed; the kernel is bound by L2->SM operand traffic, not the tensor pipe"}
     step_gbs = (BYTES_FWD + BYTES_BWD) * H / (ms_per_step * 1e-3) / 1e9
 
     # ---- parity spot check in the same run (checker only) -------------------------------
@@ -414,6 +440,7 @@ def main():
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "roofline_lbs_forward": lbs_fwd_roof,
         "blend_gemm": blend_roof,
         "step_hbm": {"algorithmic_gbs": step_gbs, "frac_of_peak": step_gbs / peaks["hbm_gbs"],
                      "algorithmic_bytes_per_hand": BYTES_FWD + BYTES_BWD},
