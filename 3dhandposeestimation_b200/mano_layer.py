@@ -112,6 +112,10 @@ class _ManoFunction(torch.autograd.Function):
         return g_rot, g_coeffs, g_betas, None, None
 
 
+BLOB_SUFFIX = ".mb20.npz"
+BLOB_MAGIC = b"MB20BLOB"
+
+
 class ManoLayer(nn.Module):
     """B200-native MANO layer with the reference's interface.
 
@@ -140,6 +144,9 @@ class ManoLayer(nn.Module):
         if model is None:
             if MANO_RIGHT_pkl is None:
                 raise TypeError("MANO_RIGHT_pkl (path to MANO_RIGHT.pkl) or model= is required")
+            if str(MANO_RIGHT_pkl).endswith(BLOB_SUFFIX):     # packed constants written by save_blob()
+                self._init_from_blob_file(MANO_RIGHT_pkl, device)
+                return
             model = assets.read_mano_pkl(MANO_RIGHT_pkl)      # FileNotFoundError like MANOLayer.py:63
         self.kintree_table = model["kintree_table"]
         self.id_to_col = {int(self.kintree_table[1, i]): i for i in range(self.kintree_table.shape[1])}
@@ -159,6 +166,43 @@ class ManoLayer(nn.Module):
                     "mb_mano_pack_constants")
         self._mode |= int(lib.mb_mano_model_flags(args[7]))
         self._blob_host = torch.from_numpy(host)
+        self._blob = None
+        dev = torch.device(device)
+        if dev.type == "cuda" and torch.cuda.is_available():
+            self._upload(dev)
+
+    # ---- packed constants on disk: no pickle / chumpy at run time ----------------
+    def save_blob(self, path) -> None:
+        """Write the packed constant blob plus the few host attributes of the layer to ``path``
+        (must end in ``.mb20.npz``); ``ManoLayer(device, path)`` loads it back without unpickling."""
+        if not str(path).endswith(BLOB_SUFFIX):
+            raise ValueError(f"blob files end in {BLOB_SUFFIX}")
+        with open(path, "wb") as fh:
+            np.savez(fh, magic=np.frombuffer(BLOB_MAGIC, dtype=np.uint8), abi=np.int32(_cabi.lib().mb_abi_version()),
+                     pose_num=np.int32(self.pose_num), model_flags=np.int32(self._mode & ~0xff),
+                     blob=self._blob_host.numpy(), kintree_table=np.asarray(self.kintree_table), faces=np.asarray(self.faces))
+
+    def _init_from_blob_file(self, path, device) -> None:
+        lib = _cabi.lib()
+        with np.load(path, allow_pickle=False) as z:
+            if bytes(z["magic"].tobytes()) != BLOB_MAGIC:
+                raise _cabi.ManoB200Error(f"{path}: not a packed MANO blob")
+            if int(z["abi"]) != lib.mb_abi_version():
+                raise _cabi.ManoB200Error(f"{path}: packed for ABI {int(z['abi'])}, library is ABI {lib.mb_abi_version()}; re-pack it")
+            if int(z["pose_num"]) != self.pose_num:
+                raise _cabi.ManoB200Error(f"{path}: packed for pose_num={int(z['pose_num'])}, layer asks for {self.pose_num}")
+            host = np.ascontiguousarray(z["blob"], dtype=np.uint8)
+            self.kintree_table = z["kintree_table"]
+            self.faces = z["faces"]
+            flags = int(z["model_flags"])
+        if host.size != lib.mb_mano_blob_bytes():
+            raise _cabi.ManoB200Error(f"{path}: blob has {host.size} bytes, library expects {lib.mb_mano_blob_bytes()}")
+        stats = (C.c_int32 * 4)()
+        _cabi.check(lib.mb_mano_skin_program_stats(host.ctypes.data_as(C.c_void_p), stats), f"{path}: skin program")
+        self.id_to_col = {int(self.kintree_table[1, i]): i for i in range(self.kintree_table.shape[1])}
+        self.parent = {i: self.id_to_col[int(self.kintree_table[0, i])] for i in range(1, self.kintree_table.shape[1])}
+        self._mode |= flags
+        self._blob_host = torch.from_numpy(host.copy())
         self._blob = None
         dev = torch.device(device)
         if dev.type == "cuda" and torch.cuda.is_available():

@@ -220,3 +220,25 @@ def test_model_flags(pkg, synth_model):
     other = parents.copy()
     other[5] = 1
     assert lib.mb_mano_model_flags(other.ctypes.data_as(C.c_void_p)) == 0
+
+
+def test_blob_file_round_trip(pkg, synth_model, tmp_path):
+    """Packed constants on disk: save_blob() / ManoLayer(device, '*.mb20.npz') reproduce the blob byte for byte
+    and refuse files of another ABI, pose_num or size (no pickle is involved in loading)."""
+    layer = pkg.ManoLayer("cpu", model=synth_model, pose_num=10)
+    path = str(tmp_path / "synthetic.mb20.npz")
+    layer.save_blob(path)
+    again = pkg.ManoLayer("cpu", path, pose_num=10)
+    assert np.array_equal(again._blob_host.numpy(), layer._blob_host.numpy())
+    assert again._mode == layer._mode and again.parent == layer.parent
+    assert np.array_equal(np.asarray(again.faces), np.asarray(layer.faces))
+    with pytest.raises(pkg._cabi.ManoB200Error):
+        pkg.ManoLayer("cpu", path, pose_num=45)
+    with pytest.raises(ValueError):
+        layer.save_blob(str(tmp_path / "x.bin"))
+    z = dict(np.load(path))
+    z["abi"] = np.int32(1)
+    bad = str(tmp_path / "old.mb20.npz")
+    np.savez(bad, **z)
+    with pytest.raises(pkg._cabi.ManoB200Error):
+        pkg.ManoLayer("cpu", bad, pose_num=10)
