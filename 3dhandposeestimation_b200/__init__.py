@@ -9,7 +9,7 @@ The directory name is not a Python identifier; import it with
 ``importlib.import_module("3dhandposeestimation_b200")`` or through the
 ``handpose_b200`` alias module at the repository root.
 """
-from . import assets  # noqa: F401
+from . import assets, fitting  # noqa: F401
 from ._cabi import ManoB200Error, lib as load_library  # noqa: F401
 from .criterions import L2Loss, MPJPE, compute_regularization_loss  # noqa: F401
 from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv  # noqa: F401

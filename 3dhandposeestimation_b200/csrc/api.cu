@@ -252,6 +252,7 @@ extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const
         if (B == 0) return 0;
         if (!blob || !rot || !coeffs || !betas || !joints) return MB_E_NULL;
         StageTimer t(ST_JOINTS_FWD, s);
+        if (use_lane_hand(mode & ~0xff, mode & 0xff, B)) return launch_joints_only_forward_lh(blob, nc, rot, coeffs, betas, B, joints, s);
         return launch_joints_only_forward(blob, nc, rot, coeffs, betas, B, joints, s);
     }
     int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
@@ -278,6 +279,8 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
         if (B == 0) return 0;
         if (!blob || !rot || !coeffs || !betas || !g_joints || !g_rot || !g_coeffs || !g_betas) return MB_E_NULL;
         StageTimer t(ST_JOINTS_BWD, s);
+        if (use_lane_hand(mode & ~0xff, mode & 0xff, B))
+            return launch_joints_only_backward_lh(blob, nc, rot, coeffs, betas, g_joints, B, g_rot, g_coeffs, g_betas, s);
         return launch_joints_only_backward(blob, nc, rot, coeffs, betas, g_joints, B, g_rot, g_coeffs, g_betas, s);
     }
     int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);

@@ -165,6 +165,10 @@ int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const flo
 int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                             const float* dfeat_t, const float* dbone_t, const float* g_joints, int B,
                             float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
+int launch_joints_only_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                                  int B, float* joints, cudaStream_t s);
+int launch_joints_only_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                                   const float* g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
 int launch_pose_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                          const float* dfeat, const float* dbone, const float* g_joints, int B,
                          float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);

@@ -34,6 +34,14 @@ struct LhConsts {
     float j0[NJ * 3];
     alignas(16) float jb[NJ * 3 * 12];               // [48][12] (10 used)
 };
+// joints-only extras: the five fingertip vertices (333,444,672,555,745 -> joints 4,8,12,16,20) are evaluated from a
+// 15-column slice of the blend basis and their dense skinning weights, without the 778-vertex contraction
+constexpr int NTIP = 5;
+__constant__ int c_tip_vert_lh[NTIP] = {333, 444, 672, 555, 745};
+struct LhTips {
+    alignas(16) float basis[FEAT_K][16];             // basis[f][tip*3 + c], column 15 = 0; row FEAT_ONE = v_template
+    float w[NTIP][NJ];                               // dense skinning weights of the tip vertices
+};
 
 __device__ void lh_stage_constants(LhConsts& C, const void* blob, int nc) {
     const BlobLayout L = blob_layout();
@@ -53,6 +61,61 @@ __device__ void lh_stage_constants(LhConsts& C, const void* blob, int nc) {
         C.jb[i] = c < NB ? jb[r * NB + c] : 0.f;
     }
     __syncthreads();
+}
+
+__device__ void lh_stage_tips(LhTips& T, const void* blob) {
+    const BlobLayout L = blob_layout();
+    const float* basis = blob_ptr<float>(blob, L.basis);
+    const float* sw = blob_ptr<float>(blob, L.skin_w);
+    const uint8_t* sb = blob_ptr<uint8_t>(blob, L.skin_b);
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < FEAT_K * 16; i += nt) {
+        const int k = i / 16, tc = i % 16;
+        T.basis[k][tc] = tc < 15 ? basis[(size_t)k * VP_PITCH + c_tip_vert_lh[tc / 3] * 3 + tc % 3] : 0.f;
+    }
+    for (int i = t; i < NTIP * NJ; i += nt) {
+        const int tp = i / NJ, b = i % NJ;
+        float acc = 0.f;
+        for (int sl = 0; sl < MAX_INFL; ++sl)
+            if (sb[c_tip_vert_lh[tp] * MAX_INFL + sl] == b) acc += sw[c_tip_vert_lh[tp] * MAX_INFL + sl];
+        T.w[tp][b] = acc;
+    }
+    __syncthreads();
+}
+// x * basis row f accumulated into the 15 tip coordinates
+__device__ __forceinline__ void tip_axpy(const LhTips& T, int f, float x, float (&tv)[15]) {
+    const float4* row = reinterpret_cast<const float4*>(T.basis[f]);
+    const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+    tv[0] = fmaf(x, a.x, tv[0]); tv[1] = fmaf(x, a.y, tv[1]); tv[2] = fmaf(x, a.z, tv[2]); tv[3] = fmaf(x, a.w, tv[3]);
+    tv[4] = fmaf(x, b.x, tv[4]); tv[5] = fmaf(x, b.y, tv[5]); tv[6] = fmaf(x, b.z, tv[6]); tv[7] = fmaf(x, b.w, tv[7]);
+    tv[8] = fmaf(x, c.x, tv[8]); tv[9] = fmaf(x, c.y, tv[9]); tv[10] = fmaf(x, c.z, tv[10]); tv[11] = fmaf(x, c.w, tv[11]);
+    tv[12] = fmaf(x, d.x, tv[12]); tv[13] = fmaf(x, d.y, tv[13]); tv[14] = fmaf(x, d.z, tv[14]);
+}
+// <basis row f, dtv> : the gradient of feature f that arrives through the tips
+__device__ __forceinline__ float tip_dot(const LhTips& T, int f, const float (&dtv)[15]) {
+    const float4* row = reinterpret_cast<const float4*>(T.basis[f]);
+    const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+    float acc = a.x * dtv[0];
+    acc = fmaf(a.y, dtv[1], acc); acc = fmaf(a.z, dtv[2], acc); acc = fmaf(a.w, dtv[3], acc);
+    acc = fmaf(b.x, dtv[4], acc); acc = fmaf(b.y, dtv[5], acc); acc = fmaf(b.z, dtv[6], acc); acc = fmaf(b.w, dtv[7], acc);
+    acc = fmaf(c.x, dtv[8], acc); acc = fmaf(c.y, dtv[9], acc); acc = fmaf(c.z, dtv[10], acc); acc = fmaf(c.w, dtv[11], acc);
+    acc = fmaf(d.x, dtv[12], acc); acc = fmaf(d.y, dtv[13], acc); acc = fmaf(d.z, dtv[14], acc);
+    return acc;
+}
+// rest-pose tip vertices: tv = v_template + S beta + P vec(R_j - I), theta read from staging rows th0..
+__device__ __forceinline__ void tips_rest_pose(const LhTips& T, const float (&beta)[NB], const float* bl, int theta_row,
+                                               float (&tv)[15]) {
+#pragma unroll
+    for (int c = 0; c < 15; ++c) tv[c] = T.basis[FEAT_ONE][c];
+#pragma unroll
+    for (int sft = 0; sft < NB; ++sft) tip_axpy(T, sft, beta[sft], tv);
+#pragma unroll 1
+    for (int k = 1; k < NJ; ++k) {
+        const float* th = bl + (theta_row + 3 * (k - 1)) * BP;
+        const M3 R = rodrigues(v3(th[0], th[BP], th[2 * BP]));
+#pragma unroll
+        for (int e = 0; e < 9; ++e) tip_axpy(T, NB + 9 * (k - 1) + e, R.m[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f), tv);
+    }
 }
 
 // coalesced copy of `n` consecutive floats (rows of up to 32 hands) into the warp's staging buffer
@@ -199,10 +262,96 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
     }
 }
 
+// ---- joints only (verts == NULL): the 21 joints without the 778-vertex contraction -------------------
+__global__ void __launch_bounds__(LH_WARPS * 32)
+pose_forward_lh_jo_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
+                          const float* __restrict__ coeffs, const float* __restrict__ betas, int B,
+                          float* __restrict__ joints) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LhConsts& C = *reinterpret_cast<LhConsts*>(smem_raw);
+    LhTips& T = *reinterpret_cast<LhTips*>(smem_raw + sizeof(LhConsts));
+    lh_stage_constants(C, blob, nc);
+    lh_stage_tips(T, blob);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts) + sizeof(LhTips)) + warp * BUF_FLOATS;
+    float* bl = buf + lane;
+    const int ngroups = (B + 31) >> 5;
+    for (int g = blockIdx.x * LH_WARPS + warp; g < ngroups; g += gridDim.x * LH_WARPS) {
+        const long long h0 = (long long)g * 32;
+        const int nh = (B - h0) < 32 ? (int)(B - h0) : 32;
+        const long long hand = h0 + (lane < nh ? lane : nh - 1);
+        const bool live = lane < nh;
+        __syncwarp();
+        float* s_coef = buf;
+        float* s_beta = buf + 32 * NAA;
+        float* s_rot = s_beta + 32 * NB;
+        stage_in(s_coef, coeffs + h0 * nc, nh * nc, lane);
+        stage_in(s_beta, betas + h0 * NB, nh * NB, lane);
+        stage_in(s_rot, rot + h0 * 3, nh * 3, lane);
+        __syncwarp();
+        const int r = (int)(hand - h0);
+        float beta[NB];
+#pragma unroll
+        for (int sft = 0; sft < NB; ++sft) beta[sft] = s_beta[r * NB + sft];
+        const M3 Rq = rodrigues(v3(s_rot[r * 3], s_rot[r * 3 + 1], s_rot[r * 3 + 2]));
+        lh_theta(C, s_coef + r * nc, nc, bl);
+        __syncwarp();
+        float tv[15];
+        tips_rest_pose(T, beta, bl, THETA_ROW, tv);
+        float out[15];
+#pragma unroll
+        for (int c = 0; c < 15; ++c) out[c] = 0.f;
+        float* jrow = joints + hand * (NOUTJ * 3);
+        // bone k is known: its joint, and its share of the five tips
+        auto bone = [&](int k, int slot, const M3& Rg, const V3& tg, const V3& J) {
+            const M3 Rp = m3_mul(Rq, Rg);
+            const V3 tp = m3_vec(Rq, v3_sub(tg, m3_vec(Rg, J)));
+            if (live) emit_joint(jrow, slot, Rq, tg);
+#pragma unroll
+            for (int t = 0; t < NTIP; ++t) {
+                const float w = T.w[t][k];
+                if (w != 0.f) {
+                    const V3 p = m3_vec(Rp, v3(tv[3 * t], tv[3 * t + 1], tv[3 * t + 2]));
+                    out[3 * t] = fmaf(w, p.x + tp.x, out[3 * t]);
+                    out[3 * t + 1] = fmaf(w, p.y + tp.y, out[3 * t + 1]);
+                    out[3 * t + 2] = fmaf(w, p.z + tp.z, out[3 * t + 2]);
+                }
+            }
+        };
+        const M3 R0 = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));
+        const V3 J0 = rest_joint(C, 0, beta);
+        bone(0, 0, R0, J0, J0);
+#pragma unroll 1
+        for (int f = 0; f < 5; ++f) {
+            M3 Rgp = R0;
+            V3 tgp = J0, Jp = J0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int k = 1 + 3 * f + i;
+                const float* th = bl + (THETA_ROW + 3 * (k - 1)) * BP;
+                const M3 R = rodrigues(v3(th[0], th[BP], th[2 * BP]));
+                const V3 J = rest_joint(C, k, beta);
+                const M3 Rg = m3_mul(Rgp, R);
+                const V3 tg = v3_add(tgp, m3_vec(Rgp, v3_sub(J, Jp)));
+                bone(k, 1 + 4 * f + i, Rg, tg, J);
+                Rgp = Rg; tgp = tg; Jp = J;
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int t = 0; t < NTIP; ++t) {
+                float* o = jrow + (4 + 4 * t) * 3;
+                o[0] = out[3 * t]; o[1] = out[3 * t + 1]; o[2] = out[3 * t + 2];
+            }
+        }
+    }
+}
+
 // ================================================================= backward
 // Staging rows of the backward (per warp, pitch BP): dfeat rows 0..147 are loaded first; the chain
 // joints' upstream gradients (48 floats) and the axis-angle gradients (45 floats) reuse rows that
 // have been consumed.
+template <bool JO>
 __global__ void __launch_bounds__(LH_WARPS * 32)
 pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
                         const float* __restrict__ coeffs, const float* __restrict__ betas,
@@ -211,9 +360,11 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
                         float* __restrict__ g_rot, float* __restrict__ g_coeffs, float* __restrict__ g_betas) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LhConsts& C = *reinterpret_cast<LhConsts*>(smem_raw);
+    LhTips& T = *reinterpret_cast<LhTips*>(smem_raw + sizeof(LhConsts));      // joints-only variant
     lh_stage_constants(C, blob, nc);
+    if (JO) lh_stage_tips(T, blob);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts)) + warp * BUF_FLOATS;
+    float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts) + (JO ? sizeof(LhTips) : 0)) + warp * BUF_FLOATS;
     float* bl = buf + lane;
     const int ngroups = (B + 31) >> 5;
     for (int g = blockIdx.x * LH_WARPS + warp; g < ngroups; g += gridDim.x * LH_WARPS) {
@@ -247,6 +398,11 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
                 const float* p = s_gj + r * 63 + (1 + 4 * f + i) * 3;
                 gj[1 + 3 * f + i] = v3(p[0], p[1], p[2]);
             }
+        float gt[15];                                          // upstream gradients of the five tip joints (joints-only)
+#pragma unroll
+        for (int t = 0; t < NTIP; ++t)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gt[3 * t + c] = JO ? s_gj[r * 63 + (4 + 4 * t) * 3 + c] : 0.f;
         float th[NAA];
         {
             // theta in registers (the staging buffer is about to be overwritten by dfeat)
@@ -272,12 +428,48 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
         for (int j = 0; j < NAA; ++j) bl[j * BP] = th[j];                      // rows 0..44: theta, later dtheta
 #pragma unroll
         for (int k = 0; k < NJ; ++k) { bl[(48 + 3 * k) * BP] = gj[k].x; bl[(49 + 3 * k) * BP] = gj[k].y; bl[(50 + 3 * k) * BP] = gj[k].z; }
-        const float* df = dfeat_t + (size_t)g * (TC_K * 32) + lane;             // dfeat_t[g][k][lane], k < 160
-        const float* db = dbone_t + (size_t)g * (NJ * BONE_F * 32) + lane;      // dbone_t[g][bone*12+e][lane]
+        const float* df = JO ? nullptr : dfeat_t + (size_t)g * (TC_K * 32) + lane;             // dfeat_t[g][k][lane], k < 160
+        const float* db = JO ? nullptr : dbone_t + (size_t)g * (NJ * BONE_F * 32) + lane;      // dbone_t[g][bone*12+e][lane]
 
+        // joints only: the five tips stand in for the 778 vertices — rest-pose tips tv, and (pre-pass over
+        // the chain) d tv = sum_k w_tk R'_k^T g_t, from which every feature gradient follows
+        float tv[15], dtv[15];
+#pragma unroll
+        for (int c = 0; c < 15; ++c) { tv[c] = 0.f; dtv[c] = 0.f; }
+        if (JO) {
+            float beta_[NB];
+#pragma unroll
+            for (int sft = 0; sft < NB; ++sft) beta_[sft] = beta[sft];
+            tips_rest_pose(T, beta_, bl, 0, tv);
+            auto tip_back = [&](int k, const M3& Rg) {
+                const M3 Rp = m3_mul(Rq, Rg);
+#pragma unroll
+                for (int t = 0; t < NTIP; ++t) {
+                    const float w = T.w[t][k];
+                    if (w != 0.f) {
+                        const V3 d = m3_tvec(Rp, v3(gt[3 * t], gt[3 * t + 1], gt[3 * t + 2]));
+                        dtv[3 * t] = fmaf(w, d.x, dtv[3 * t]); dtv[3 * t + 1] = fmaf(w, d.y, dtv[3 * t + 1]); dtv[3 * t + 2] = fmaf(w, d.z, dtv[3 * t + 2]);
+                    }
+                }
+            };
+            const M3 R0p = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));
+            tip_back(0, R0p);
+#pragma unroll 1
+            for (int f = 0; f < 5; ++f) {
+                M3 Rgp = R0p;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int k = 1 + 3 * f + i;
+                    const float* tp = bl + (3 * (k - 1)) * BP;
+                    const M3 Rg = m3_mul(Rgp, rodrigues(v3(tp[0], tp[BP], tp[2 * BP])));
+                    tip_back(k, Rg);
+                    Rgp = Rg;
+                }
+            }
+        }
         float gbeta[NB];
 #pragma unroll
-        for (int s = 0; s < NB; ++s) gbeta[s] = df[s * 32];
+        for (int s = 0; s < NB; ++s) gbeta[s] = JO ? tip_dot(T, s, dtv) : df[s * 32];
         M3 dRq = m3_zero();
         // d beta += Jb^T dJ for one joint
         auto add_dJ = [&](int k, const V3& dJ) {
@@ -292,8 +484,26 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
         // A.2 step 3 for one bone: split dA'_k = d[Rq Rg | Rq tA], joint_k = Rq tg
         auto split_bone = [&](int k, const M3& Rg, const V3& tg, const V3& J, const V3& gjk, M3& dRg, V3& dtg, V3& dJ) {
             float dA[BONE_F];
+            if (JO) {
+                // dA'_k = sum_t w_tk g_t (x) [tv_t ; 1]
 #pragma unroll
-            for (int e = 0; e < BONE_F; ++e) dA[e] = db[(k * BONE_F + e) * 32];
+                for (int e = 0; e < BONE_F; ++e) dA[e] = 0.f;
+#pragma unroll
+                for (int t = 0; t < NTIP; ++t) {
+                    const float w = T.w[t][k];
+                    if (w != 0.f) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const float wg = w * gt[3 * t + i];
+                            dA[4 * i] = fmaf(wg, tv[3 * t], dA[4 * i]); dA[4 * i + 1] = fmaf(wg, tv[3 * t + 1], dA[4 * i + 1]);
+                            dA[4 * i + 2] = fmaf(wg, tv[3 * t + 2], dA[4 * i + 2]); dA[4 * i + 3] += wg;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < BONE_F; ++e) dA[e] = db[(k * BONE_F + e) * 32];
+            }
             const V3 tA = v3_sub(tg, m3_vec(Rg, J));
             M3 dApR;
             dApR.m[0] = dA[0]; dApR.m[1] = dA[1]; dApR.m[2] = dA[2];
@@ -354,7 +564,7 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
                 add_dJ(k, dJ);
                 // A.2 steps 5-6: pose-feature gradient joins dR_k ; Rodrigues backward
 #pragma unroll
-                for (int e = 0; e < 9; ++e) dRl.m[e] += df[(NB + 9 * (k - 1) + e) * 32];
+                for (int e = 0; e < 9; ++e) dRl.m[e] += JO ? tip_dot(T, NB + 9 * (k - 1) + e, dtv) : df[(NB + 9 * (k - 1) + e) * 32];
                 const V3 dth = rodrigues_bwd(rr[i], dRl);
                 float* tp = bl + (3 * (k - 1)) * BP;
                 tp[0] = dth.x; tp[BP] = dth.y; tp[2 * BP] = dth.z;     // theta row -> dtheta row
@@ -396,6 +606,7 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
 }
 
 constexpr size_t LH_SMEM = sizeof(LhConsts) + (size_t)LH_WARPS * BUF_FLOATS * sizeof(float);
+constexpr size_t LH_SMEM_JO = LH_SMEM + sizeof(LhTips);
 
 inline int lh_grid(int B) {
     const long long groups = ((long long)B + 31) / 32;
@@ -423,12 +634,37 @@ int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const fl
                             float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    pose_backward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, dfeat_t, dbone_t, g_joints, B,
-                                                                      g_rot, g_coeffs, g_betas);
+    pose_backward_lh_kernel<false><<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, dfeat_t, dbone_t, g_joints, B,
+                                                                             g_rot, g_coeffs, g_betas);
+    return cuda_rc();
+}
+
+int launch_joints_only_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                                  int B, float* joints, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pose_forward_lh_jo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    pose_forward_lh_jo_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM_JO, s>>>(blob, nc, rot, coeffs, betas, B, joints);
+    return cuda_rc();
+}
+
+int launch_joints_only_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                                   const float* g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    pose_backward_lh_kernel<true><<<lh_grid(B), LH_WARPS * 32, LH_SMEM_JO, s>>>(blob, nc, rot, coeffs, betas, nullptr, nullptr, g_joints, B,
+                                                                               g_rot, g_coeffs, g_betas);
     return cuda_rc();
 }
 

@@ -196,6 +196,90 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_secondary(args, pkg, layer, dev, rank, world, dist):
+    """The other measured BASELINE configs (not the contract line): config 5 fitting loop, config 3 FK."""
+    import numpy as np
+    import torch
+
+    H = args.hands
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / n
+
+    if args.workload == "fit":
+        # config 5: Adam on (rot, pose, beta) of H hands per GPU against target keypoints; one NCCL all-reduce of
+        # 4 doubles per iteration when world > 1
+        rot, pose, beta = synth_inputs(H, 777 + rank)
+        with torch.no_grad():
+            _, tgt = layer.rot_pose_beta_to_mesh(*[torch.from_numpy(a).to(dev) for a in (rot, pose, beta)], joints_only=True)
+            tgt = tgt + 1e-3 * torch.randn_like(tgt)
+        vis = (torch.rand(H, 21, 1, device=dev) < 0.8).float()
+        fitter = pkg.fitting.ManoFitter(layer, H)
+        loss0 = float(fitter.step(tgt, vis))
+        l2_0 = float(fitter.partials[0] / fitter.partials[1].clamp(min=1))
+        ms = timed(lambda: fitter.step(tgt, vis), args.steps)
+        loss1 = float(fitter.loss)
+        l2_1 = float(fitter.partials[0] / fitter.partials[1].clamp(min=1))
+        return {"metric": "MANO fitting-loop hand-iterations/sec (config 5)", "value": world * H / (ms * 1e-3), "unit": "hand-iterations/s",
+                "n_gpus": world, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "config": {"workload": f"mano_fit_adam_{H}_hands_per_gpu", "collective": "all-reduce of 4 doubles per iteration" if world > 1 else "none"},
+                "loss_first": loss0, "loss_last": loss1, "l2_term_first_m2": l2_0, "l2_term_last_m2": l2_1,
+                "note": "loss = masked L2 + the reference's batch-global Frobenius regulariser (loss.py:113-117), which grows with "
+                        "sqrt(batch) and dominates at 2^20 hands; the L2 term is reported separately", "data": "synthetic"}
+    # config 3: RHD 21-joint FK forward + backward + visible-joint MPJPE, rotating buffer sets (the working set of one
+    # 65 536-sample call fits in L2)
+    B = 65536 if args.hands == (1 << 20) else args.hands
+    nsets = 16
+    fk = pkg.ForwardKinematics(dev)
+    mp = pkg.MPJPE()
+    sets = []
+    for i in range(nsets):
+        rs = np.random.RandomState(31 + i + 100 * rank)
+        a = [((rs.rand(B, 3) - .5) * 2 * np.pi), ((rs.rand(B, 23) - .5) * np.pi), rs.rand(B, 20) + .1]
+        K = np.tile(np.array([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1]]), (B, 1, 1))
+        sc = rs.rand(B, 1) * .05 + .02
+        root = rs.randn(B, 3) * .05 + np.array([0, 0, .6])
+        t = [torch.from_numpy(x.astype(np.float32)).to(dev) for x in (*a, K, sc, root)]
+        for x in t[:3]:
+            x.requires_grad_()
+        gt = torch.from_numpy((rs.randn(B, 21, 3) * .05 + np.array([0, 0, .6])).astype(np.float32)).to(dev)
+        vis = torch.from_numpy((rs.rand(B, 21, 1) < .8).astype(np.float32)).to(dev)
+        sets.append((t, gt, vis))
+    it = [0]
+
+    def step():
+        t, gt, vis = sets[it[0] % nsets]
+        it[0] += 1
+        xyz, uv, _ = fk(*t)
+        loss = mp(xyz, gt, vis) + 1e-3 * uv.sum()
+        loss.backward()
+        for x in t[:3]:
+            x.grad = None
+
+    ms = timed(step, args.steps)
+    return {"metric": "RHD FK fwd+bwd+MPJPE samples/sec (config 3)", "value": world * B / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "config": {"workload": f"fk_fwd+bwd+mpjpe_{B}_samples_per_gpu", "l2": f"rotating {nsets} buffer sets",
+                       "note": "through the nn.Module API: includes torch's autograd glue for the uv.sum() term"},
+            "data": "synthetic"}
+
+
 def workload_name(args):
     return f"mano_full45_noPCA_fwd+bwd_{args.hands}_hands_per_gpu"
 
@@ -208,6 +292,8 @@ def main():
     ap.add_argument("--hands", type=int, default=1 << 20, help="hands per GPU per step")
     ap.add_argument("--mode", default=os.environ.get("MANO_B200_MODE", "f16x3"))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mano", choices=["mano", "fit", "fk"],
+                    help="mano (default, the contract line) | fit = BASELINE config 5 fitting loop | fk = config 3 FK fwd+bwd+MPJPE")
     ap.add_argument("--ref-hands", type=int, default=512, help="hands per step of the --impl reference arm")
     ap.add_argument("--rotate", type=int, default=1, help="number of distinct buffer sets cycled through (small --hands)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -246,6 +332,15 @@ def main():
     layer = pkg.ManoLayer(dev, model=model, pose_num=45, mode=args.mode)
     mode = layer._mode
     stream = cabi.stream_handle(dev)
+
+    if args.workload != "mano":
+        line = run_secondary(args, pkg, layer, dev, rank, world, dist)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
 
     nsets = max(1, args.rotate)
     sets = []

@@ -108,6 +108,30 @@ def test_mano_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc, mode):
         assert rel(t.grad.cpu().numpy()[idx], want) < GRAD_TOL
 
 
+@pytest.mark.parametrize("B,nc", [(4099, 45), (6000, 10)])
+def test_mano_joints_only_large_batch_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc):
+    """The heads' / fitting loop's case at a batch that runs the one-thread-per-hand joints-only kernels
+    (>= 4096 hands): 21 joints and their gradients without the 778-vertex contraction."""
+    import torch
+
+    rot, pose, beta = mano_inputs(B, nc, seed=B + nc)
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc)
+    trot, tpose, tbeta = to_dev(cuda_device, rot, pose, beta, grad=True)
+    none, joints = layer.rot_pose_beta_to_mesh(trot, tpose, tbeta, joints_only=True)
+    assert none is None
+    idx = np.unique(np.r_[np.arange(96), np.arange(B - 40, B)])
+    _, oj = mo.mano_forward(synth_model, rot[idx], pose[idx], beta[idx])
+    assert np.abs(joints.detach().cpu().numpy()[idx] - oj).max() < POS_TOL_F64
+    # the full layer gives the same joints
+    _, joints_full = layer(trot.detach(), tpose.detach(), tbeta.detach())
+    assert float((joints_full - joints.detach()).abs().max()) < 2e-7
+    gj = np.random.RandomState(2).randn(B, 21, 3).astype(np.float32)
+    (joints * torch.from_numpy(gj).to(cuda_device)).sum().backward()
+    og = mo.mano_backward(synth_model, rot[idx], pose[idx], beta[idx], np.zeros((idx.size, 778, 3), np.float32), gj[idx])
+    for t, want in zip((trot, tpose, tbeta), og):
+        assert rel(t.grad.cpu().numpy()[idx], want) < GRAD_TOL
+
+
 def test_mano_fast_f16_mode_error_is_bounded(pkg, synth_model, cuda_device):
     """MB_MODE_F16 (single fp16 product on the tensor cores): bounded, stated error."""
     rot, pose, beta = mano_inputs(512, 45, seed=3)
