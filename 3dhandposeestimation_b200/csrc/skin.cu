@@ -139,6 +139,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// A wait that cannot hang the GPU: a broken schedule / pipeline traps after ~2 s instead of spinning forever.
+__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
 template <int STAGES, int SLOT_FLOATS>
 struct alignas(128) Ring {
     alignas(128) float slot[STAGES][SLOT_FLOATS];
@@ -172,7 +181,7 @@ __device__ __forceinline__ const float* ring_wait(Ring<STAGES, SLOT_FLOATS>& R, 
     const unsigned st = C.consumed % STAGES;
     const uint32_t bar = smem_u32(&R.full[st]);
     const uint32_t parity = (C.consumed / STAGES) & 1;
-    while (!mbar_try_wait(bar, parity)) {}
+    mbar_wait_or_trap(bar, parity);
     return R.slot[st];
 }
 
@@ -233,7 +242,7 @@ __device__ __forceinline__ const float4* cache_entry(BoneCache& K, CacheState& S
     if (code & 128) {
         const uint32_t bar = smem_u32(&K.full[slot]);
         const uint32_t par = (S.parity >> slot) & 1;
-        while (!mbar_try_wait(bar, par)) {}
+        mbar_wait_or_trap(bar, par);
         S.parity ^= 1u << slot;
     }
     return reinterpret_cast<const float4*>(K.slot[slot] + lane * BONE_F);
@@ -365,7 +374,7 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
                 load_w(P, e, w);
                 const float4* sl = cache_entry(W.bones, CS, P.ent_code[e], lane);
                 const float4 a0 = sl[0], a1 = sl[1], a2 = sl[2];
-                cache_after_entry(W.bones, CS, P, e, bgrp, has_next, next_off, pol.keep);
+                cache_after_entry(W.bones, CS, P, e, bgrp, has_next, next_off, pol.keep);   // may refill the slot just read
                 const float A[BONE_F] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
                 fma_entry2(A, w, X, ACC);
             }
