@@ -269,12 +269,14 @@ __device__ __forceinline__ void fma_entry2(const float (&A)[BONE_F], const float
         }
     }
 }
-constexpr int SKF_WARPS = 9;                       // autonomous warps per CTA; 1 CTA per SM
+constexpr int SKF_WARPS = 8;                       // autonomous warps per CTA; 1 CTA per SM (the kernel is bound by the
+                                                   // memory system, not by warp count: 7..20 warps measured the same)
+constexpr int CARRY_F = 8;                         // floats of the previous segment kept in front of the tile
 constexpr int SKF_THREADS = SKF_WARPS * 32;
 struct alignas(128) FwdWarpShared {
     BoneCache bones;
     XRing xs;
-    alignas(16) float tile[TILE_FLOATS];
+    alignas(16) float tile[(CARRY_F + SEG_F) * TP];          // slots 0..7: tail of the previous segment, 8..55: this segment
 };
 constexpr size_t SKF_SMEM = PROG_BYTES + (size_t)SKF_WARPS * sizeof(FwdWarpShared);
 
@@ -305,20 +307,31 @@ __device__ __forceinline__ void slot_to_pairs(float2 (&X)[3][4], const float* sl
 }
 
 // a finished 16-vertex segment leaves the tile as 192-byte row pieces (kept out of line: once per segment)
-__device__ __noinline__ void store_segment(const float* ts, float* dst, int nh, int nf, int r, int p, uint64_t pol) {
-    if (nh == 32 && nf == SEG_F) {
+// A finished segment leaves the tile as one contiguous run per row (24 lanes x 8 B; four rows take three
+// instructions, flat index i = lane + 32 it -> (row i / 24, float2 i % 24)), and every run is SECTOR-ALIGNED:
+// rows of verts[B][778][3] are 9 336 B = 24 mod 32 apart, so row h's 32-byte boundaries sit at floats
+// f = 2h mod 8.  Row h therefore stores the window [48 seg - d, 48 seg + 48 - d), d = (0, 6, 4, 2)[h % 4] floats
+// — the last d floats of the previous segment (kept in the tile's carry slots) instead of the last d of this
+// one — except at the two ends of the row.  [measured: a 32-byte-aligned row pitch alone was worth 12 %:
+// partial-sector writes cost L2 a read-modify-write and DRAM 1.1 GB of fill reads per 2^20 hands]
+__device__ __noinline__ void store_segment(const float* tile, float* row0 /* verts row 0 of the group */, int seg,
+                                           int nh, int lane, uint64_t pol) {
+    const bool last = seg == SK_NSEG - 1;
+#pragma unroll 1
+    for (int rb = 0; rb < 8; ++rb) {
 #pragma unroll
-        for (int rb = 0; rb < 8; ++rb)
-#pragma unroll
-            for (int qb = 0; qb < 3; ++qb)
-                st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
-                           make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]), pol);
-    } else {
-        for (int rb = 0; rb < 8; ++rb)
-            for (int qb = 0; qb < 3; ++qb)
-                if (rb * 4 + r < nh && qb * 16 + 2 * p < nf)
-                    st_stream2(dst + (size_t)rb * 4 * NVC + qb * 16,
-                               make_float2(ts[(qb * 16) * TP + rb * 4], ts[(qb * 16 + 1) * TP + rb * 4]), pol);
+        for (int it = 0; it < 3; ++it) {
+            const int i = lane + 32 * it;
+            const int rr = i / 24, pp = i - rr * 24;
+            const int h = rb * 4 + rr;
+            const int d2 = (4 - rr) & 3;                       // d / 2 = (0, 3, 2, 1)[h % 4]; h % 4 == rr
+            const int f2 = 24 * seg - d2 + pp;                 // float2 index inside the row
+            const int np = last ? (NV * 3 / 2 - 24 * seg + d2) : 24;
+            if (h < nh && pp < np && f2 >= 0) {
+                const float* t = tile + (CARRY_F - 2 * d2 + 2 * pp) * TP + h;
+                st_stream2(row0 + (size_t)h * NVC + 2 * f2, make_float2(t[0], t[TP]), pol);
+            }
+        }
     }
 }
 
@@ -336,9 +349,7 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
     }
     stage_prog(P, blob);
     __syncthreads();
-    float* tl = W.tile + lane;                                // compute side: (f, lane)
-    const RowMap rm(lane);
-    const float* ts = W.tile + rm.tile_base();                // store side
+    float* tl = W.tile + CARRY_F * TP + lane;                 // compute side: (float f of the segment, lane)
     const int ngroups = (B + 31) >> 5;
     const int g0 = blockIdx.x + warp * gridDim.x, gstep = gridDim.x * SKF_WARPS;
     auto x_src = [&](int g, int blk) { return v_posed_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * XBLK_FLOATS; };
@@ -352,7 +363,6 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
 
     for (int g = g0; g < ngroups; g += gstep) {
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
-        float* vrow = verts + (size_t)g * 32 * NVC + rm.row_base();
         const float* bgrp = bone_t + (size_t)g * GROUP_BONE_FLOATS;
         const bool has_next = g + gstep < ngroups;
         cache_begin_group(CS, P);
@@ -390,7 +400,7 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
             if (blk & 1) {                                    // second block of a segment: the segment is complete
                 const int seg = blk >> 1;
                 __syncwarp();
-                store_segment(ts, vrow + seg * SEG_F, nh, (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F, rm.r, rm.p, pol.stream);
+                store_segment(W.tile, verts + (size_t)g * 32 * NVC, seg, nh, lane, pol.stream);
                 if (joints != nullptr && lane < nh) {
 #pragma unroll
                     for (int t = 0; t < N_TIP; ++t)
@@ -400,6 +410,10 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
                             o[0] = tv[0]; o[1] = tv[TP]; o[2] = tv[2 * TP];
                         }
                 }
+                __syncwarp();
+                // keep the segment's last 8 floats of this lane's hand for the next segment's shifted windows
+#pragma unroll
+                for (int c = 0; c < CARRY_F; ++c) tl[(c - CARRY_F) * TP] = tl[(SEG_F - CARRY_F + c) * TP];
                 __syncwarp();
             }
         }
