@@ -193,7 +193,7 @@ extern "C" int mb_mano_model_flags(const int32_t* parents) {
 }
 
 // one thread per hand (mano_pose_lh.cu) once a batch fills the machine; one warp per hand below that
-static constexpr int LH_MIN_HANDS = 4096;
+// [measured, pose forward + backward: B = 4096 54 us vs 82 us lane = hand; 8192 90 vs 93; 16384 136 vs 94]
 static inline bool use_lane_hand(int model_flags, int mode, int B) {
     return (model_flags & MB_MODEL_CHAINS_5X3) && mode != MB_MODE_FP32 && B >= LH_MIN_HANDS;
 }
@@ -294,7 +294,10 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
     float* bone_t = reinterpret_cast<float*>(ws + W.bone_t);
     float* v_posed_t = reinterpret_cast<float*>(ws + W.v_posed_t);
     float* dbone = reinterpret_cast<float*>(ws + W.dbone);
+    float* dparts = reinterpret_cast<float*>(ws + W.dparts);
     float* dfeat = reinterpret_cast<float*>(ws + W.dfeat);
+    const int dfeat_parts = (mode == MB_MODE_FP32) ? 1 : blend_bwd_splits(B);
+    const size_t dfeat_stride = (size_t)((B + 31) / 32) * 160 * 32;
     if (!(flags & MB_BWD_WORKSPACE_VALID)) {
         // recompute the forward intermediates; joints of the recompute go to scratch (dfeat is free until step 3)
         float* scratch_joints = dfeat;      // B*63 floats <= B*148
@@ -303,20 +306,20 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
     if (mode == MB_MODE_FP32) {
         float* dv_t = reinterpret_cast<float*>(ws + W.dv_t);
         float* rows = reinterpret_cast<float*>(ws + W.rows);
-        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, nullptr, dbone, 0, s))) return rc; }
+        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, nullptr, dbone, 0, dparts, s))) return rc; }
         StageTimer t(ST_BLEND_BWD, s);
         const BlobLayout L = blob_layout();
         if ((rc = launch_t_to_rows(blob, dv_t, VP_PITCH, B, rows, s))) return rc;
         if ((rc = launch_sgemm(rows, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s))) return rc;
     } else {
         unsigned char* dvp = reinterpret_cast<unsigned char*>(ws + W.dvp);
-        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, lh ? 1 : 0, s))) return rc; }
+        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, lh ? 1 : 0, dparts, s))) return rc; }
         StageTimer t(ST_BLEND_BWD, s);        // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
-        if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, lh ? 1 : 0, s))) return rc;
+        if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, lh ? 1 : 0, dfeat_parts, dfeat_stride, s))) return rc;
     }
     StageTimer t(ST_POSE_BWD, s);
     if (lh) return launch_pose_backward_lh(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
-    return launch_pose_backward(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
+    return launch_pose_backward(blob, nc, rot, coeffs, betas, dfeat, dfeat_parts, dfeat_stride, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);
 }
 
 extern "C" size_t mb_lbs_workspace_bytes(int B) {

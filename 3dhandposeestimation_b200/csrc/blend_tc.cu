@@ -248,11 +248,14 @@ struct TcBwdShared {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsigned char* __restrict__ dvp,
-                         float* __restrict__ dfeat, int B, int m_tiles, int hand_minor) {
+                         float* __restrict__ dfeat, int B, int m_tiles, int hand_minor, int ksplit, size_t part_stride) {
     extern __shared__ unsigned char smem_raw[];
     TcBwdShared& S = *reinterpret_cast<TcBwdShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // work item w = (pass p = w / ksplit, K range w % ksplit): small batches cut the K loop so that every SM has a
+    // range; range r accumulates chunks [74 r / ksplit, 74 (r + 1) / ksplit) into its own dfeat copy
     const int passes = (m_tiles + BW_MT - 1) / BW_MT;
+    const int nwork = passes * ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < BW_STAGES; ++s) { mbar_init(smem_u32(&S.full[s]), 1); mbar_init(smem_u32(&S.empty[s]), 1); }
@@ -272,9 +275,10 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
         // ===== TMA producer =====
         uint32_t stage = 0, phase = 0;
         bool ok = true;
-        for (int p = blockIdx.x; p < passes && ok; p += gridDim.x) {
+        for (int w = blockIdx.x; w < nwork && ok; w += gridDim.x) {
+            const int p = w / ksplit, r = w - p * ksplit;
             const int nmt = (m_tiles - p * BW_MT) < BW_MT ? (m_tiles - p * BW_MT) : BW_MT;
-            for (int kc = 0; kc < TCB_K_CHUNKS; ++kc) {
+            for (int kc = TCB_K_CHUNKS * r / ksplit; kc < TCB_K_CHUNKS * (r + 1) / ksplit; ++kc) {
                 if (!(ok = mbar_wait(smem_u32(&S.empty[stage]), phase ^ 1, abort_flag))) break;
                 mbar_expect_tx(smem_u32(&S.full[stage]), nmt * TCB_A_CHUNK_BYTES + TCB_B_CHUNK_BYTES);
                 const uint32_t dst = smem_u32(S.st[stage]);
@@ -292,11 +296,13 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
         uint32_t stage = 0, phase = 0, pass_phase = 0;
         bool ok = true;
         const uint64_t base = umma_desc(smem_u32(S.st[0]), TC_LBO, TC_SBO);
-        for (int p = blockIdx.x; p < passes && ok; p += gridDim.x) {
+        for (int w = blockIdx.x; w < nwork && ok; w += gridDim.x) {
+            const int p = w / ksplit, r = w - p * ksplit;
             const int nmt = (m_tiles - p * BW_MT) < BW_MT ? (m_tiles - p * BW_MT) : BW_MT;
+            const int kc0 = TCB_K_CHUNKS * r / ksplit, kc1 = TCB_K_CHUNKS * (r + 1) / ksplit;
             if (!(ok = mbar_wait(smem_u32(&S.acc_empty), pass_phase ^ 1, abort_flag))) break;   // epilogue drained the accumulators
             tc_fence_after();
-            for (int kc = 0; kc < TCB_K_CHUNKS && ok; ++kc) {
+            for (int kc = kc0; kc < kc1 && ok; ++kc) {
                 if (!(ok = mbar_wait(smem_u32(&S.full[stage]), phase, abort_flag))) break;
                 tc_fence_after();
                 const uint64_t sbase = base + (uint64_t)((stage * BW_STAGE_BYTES) >> 4);
@@ -311,7 +317,7 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
                             const uint64_t b_hi = b_hi0 + (uint64_t)((j * 2 * (int)TC_LBO) >> 4);
                             const uint64_t b_mid = b_hi + (uint64_t)(TC_B_BLOCK_BYTES >> 4);
                             const uint32_t d = tmem + mt * TC_N;
-                            umma_f16(d, a_hi, b_hi, IDESC_BF16, (kc | j) ? 1u : 0u);
+                            umma_f16(d, a_hi, b_hi, IDESC_BF16, (kc != kc0 || j) ? 1u : 0u);
                             umma_f16(d, a_mid, b_hi, IDESC_BF16, 1);
                             umma_f16(d, a_hi, b_mid, IDESC_BF16, 1);
                         }
@@ -331,7 +337,9 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
         float (*buf)[33] = S.stage[warp - 4];
         uint32_t pass_phase = 0;
         bool ok = true;
-        for (int p = blockIdx.x; p < passes && ok; p += gridDim.x) {
+        for (int w = blockIdx.x; w < nwork && ok; w += gridDim.x) {
+            const int p = w / ksplit;
+            float* dfeat_r = dfeat + (size_t)(w - p * ksplit) * part_stride;
             ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&S.acc_full), pass_phase, abort_flag));
             if (!ok) break;
             tc_fence_after();
@@ -350,7 +358,7 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
                 if (hand_minor) {                               // dfeat_t[group][column][32]: a lane quarter is a hand group
                     const long long group = (long long)m_tile * (TC_M / 32) + q;
                     if (active && group * 32 < B) {
-                        float* dst = dfeat + ((size_t)group * TC_N + j * 32) * 32 + lane;
+                        float* dst = dfeat_r + ((size_t)group * TC_N + j * 32) * 32 + lane;
 #pragma unroll
                         for (int c = 0; c < 32; ++c) dst[c * 32] = v[c];
                     }
@@ -360,7 +368,7 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
                     __syncwarp();
                     const int col = j * 32 + lane;
                     if (active && col < FEAT_K) {
-                        float* dst = dfeat + (size_t)row0 * FEAT_K + col;
+                        float* dst = dfeat_r + (size_t)row0 * FEAT_K + col;
                         const int nrow = B - row0 < 32 ? B - row0 : 32;
 #pragma unroll 8
                         for (int rr = 0; rr < 32; ++rr)
@@ -429,7 +437,8 @@ void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob
             }
 }
 
-int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, int hand_minor, cudaStream_t s) {
+int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, int hand_minor, int ksplit,
+                             size_t part_stride, cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
     const size_t smem = sizeof(TcBwdShared) + 128;
@@ -442,7 +451,10 @@ int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* 
     const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
     const int m_tiles = (B + TC_M - 1) / TC_M;
     const int passes = (m_tiles + BW_MT - 1) / BW_MT;
-    blend_tc_backward_kernel<<<passes < NUM_SMS ? passes : NUM_SMS, TC_THREADS, smem, s>>>(tc + tc_fwd_bytes(), dvp, dfeat, B, m_tiles, hand_minor);
+    if (ksplit < 1 || ksplit > TCB_K_CHUNKS) return MB_E_RANGE;
+    const long long nwork = (long long)passes * ksplit;
+    blend_tc_backward_kernel<<<nwork < NUM_SMS ? (int)nwork : NUM_SMS, TC_THREADS, smem, s>>>(tc + tc_fwd_bytes(), dvp, dfeat, B, m_tiles,
+                                                                                          hand_minor, ksplit, part_stride);
     return cuda_rc();
 }
 

@@ -52,7 +52,9 @@ constexpr size_t TCB_B_BYTES = (size_t)TCB_K_CHUNKS * TCB_B_CHUNK_BYTES;
 inline size_t tc_dvp_bytes(long long B) { return (size_t)((B + TC_M - 1) / TC_M) * TCB_A_TILE_BYTES; }
 
 // dfeat: [B][148] rows, or hand-minor [groups][160][32] when hand_minor != 0
-int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, int hand_minor, cudaStream_t s);
+// ksplit K ranges, each into its own dfeat copy part_stride floats apart (the pose backward adds them)
+int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, int hand_minor, int ksplit,
+                             size_t part_stride, cudaStream_t s);
 int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed_t, int B, int mode, cudaStream_t s);
 
 }  // namespace mb

@@ -61,6 +61,7 @@ struct BlobLayout {
     size_t sk_blk_ptr;  // int32 [SK_NBLK + 1]       block -> range of (block, bone) entries
     size_t sk_ent_bone; // int32 [SK_MAX_ENT]        bone | slot << 4 | wait << 7 (slot schedule, see skin.cu)
     size_t sk_cmd;      // int32 [SK_MAX_CMD + 1]    [0] = count; then (after_entry + 1) | slot << 10 | bone << 13 | next_group << 17
+    size_t sk_split;    // int32 [SK_NSEG][8]        resident bones (6 slots, -1 = empty), command cursor, bones-touched mask at the start of each segment
     size_t sk_ent_w;    // float [SK_MAX_ENT][8]     dense weights of the block's 8 vertices for that bone
     size_t sk_vloc;     // uint8 [SK_NPOS]           position -> vertex index inside its 16-segment (255 = padding)
     size_t sk_perm;     // int32 [SK_NPOS]           position -> original vertex (-1 = padding)
@@ -102,6 +103,7 @@ __host__ __device__ inline BlobLayout blob_layout() {
     L.sk_blk_ptr = o;  o = align256(o + sizeof(int32_t) * (SK_NBLK + 1));
     L.sk_ent_bone = o; o = align256(o + sizeof(int32_t) * SK_MAX_ENT);
     L.sk_cmd = o;      o = align256(o + sizeof(int32_t) * (SK_MAX_CMD + 1));
+    L.sk_split = o;    o = align256(o + sizeof(int32_t) * SK_NSEG * 8);
     L.sk_ent_w = o;    o = align256(o + sizeof(float) * SK_MAX_ENT * SK_BV);
     L.sk_vloc = o;     o = align256(o + SK_NPOS);
     L.sk_perm = o;     o = align256(o + sizeof(int32_t) * SK_NPOS);
@@ -116,7 +118,8 @@ struct WorkLayout {
     size_t bone_t;    // float [G][16][32][12]     bone transforms grouped by 32 hands: [group][bone][hand % 32][3x4]
     size_t v_posed_t; // float [G][SK_NCOORD][32]  rest-pose vertices, block order, hand-minor
     size_t dbone;     // float [B][16][12] rows or [G][16*12][32] hand-minor   (backward only)
-    size_t dfeat;     // float [B][FEAT_K] rows or [G][160][32] hand-minor     (backward only)
+    size_t dfeat;     // float [B][FEAT_K] rows or [G][160][32] hand-minor, x blend_bwd_splits(B) copies G*160*32 floats apart
+    size_t dparts;    // float [G][units per group][16*12][32]   bone sums of split backward sweeps (small batches only)
     // tensor-core modes
     size_t featp;     // fp16 hi/lo feature tiles: ceil(B/128) * 80 KB
     size_t dvp;       // bf16 hi/mid dv_posed tiles of the tcgen05 backward: ceil(B/128) * 74 * 16 KB
@@ -127,6 +130,34 @@ struct WorkLayout {
     size_t total;
 };
 
+// Fewer hand groups than resident sweepers (forward: 148 x 8 warps, backward: 148 x 4 warp pairs): every
+// 49-segment sweep is cut into units of 7 segments, or of 1 when even that leaves most sweepers idle.
+constexpr int SKF_SWEEPERS = NUM_SMS * 8, SKB_SWEEPERS = NUM_SMS * 4;
+__host__ __device__ inline int skin_segments_per_unit(long long ngroups, int sweepers) {
+    // static unit -> sweeper assignment: rounds x (segments per unit + ~3 segment-times of per-unit start-up
+    // [measured: B = 16384 backward, 7 units of 7 segments per pair took 224 us against 138 us unsplit]);
+    // a group has ceil(49 / spu) units, the last one short
+    int best = SK_NSEG;
+    long long best_cost = ((ngroups + sweepers - 1) / sweepers) * SK_NSEG;
+    for (int spu = SK_NSEG - 1; spu >= 1; --spu) {
+        const int parts = (SK_NSEG + spu - 1) / spu;
+        const long long rounds = (ngroups * parts + sweepers - 1) / sweepers;
+        const long long cost = rounds * (spu + 3);
+        if (cost < best_cost) { best_cost = cost; best = spu; }
+    }
+    return best;
+}
+__host__ __device__ inline int skin_units_per_group(int spu) { return (SK_NSEG + spu - 1) / spu; }
+// Backward contraction at small batches: fewer CTA passes (2 x 128 hands) than SMs, so the K = 2368 loop is cut
+// into up to 8 ranges; each range writes its own dfeat copy and the pose backward adds them in order.
+// Only below LH_MIN_HANDS: the lane = hand pose backward reads one dfeat copy.
+constexpr int LH_MIN_HANDS = 8192;   // one thread per hand pose kernels from here on, one warp per hand below
+__host__ __device__ inline int blend_bwd_splits(long long B) {
+    const long long passes = ((B + 127) / 128 + 1) / 2;
+    if (passes <= 0 || B >= LH_MIN_HANDS) return 1;
+    const long long s = NUM_SMS / passes;
+    return s < 1 ? 1 : (s > 8 ? 8 : (int)s);
+}
 __host__ __device__ inline WorkLayout work_layout(long long B, int mode) {
     WorkLayout W;
     const size_t G = (size_t)((B + 31) / 32);
@@ -135,7 +166,10 @@ __host__ __device__ inline WorkLayout work_layout(long long B, int mode) {
     W.bone_t = o;    o = align256(o + sizeof(float) * G * NJ * BONE_F * 32);
     W.v_posed_t = o; o = align256(o + sizeof(float) * G * SK_NCOORD * 32);
     W.dbone = o;     o = align256(o + sizeof(float) * G * NJ * BONE_F * 32);
-    W.dfeat = o;     o = align256(o + sizeof(float) * G * 160 * 32);
+    W.dfeat = o;     o = align256(o + sizeof(float) * G * 160 * 32 * blend_bwd_splits(B));   // one copy per K range
+    W.dparts = o;                                              // split backward sweeps: per-unit bone sums
+    const int spu = skin_segments_per_unit((long long)G, SKB_SWEEPERS);
+    if (spu < SK_NSEG) o = align256(o + sizeof(float) * G * skin_units_per_group(spu) * NJ * BONE_F * 32);
     W.featp = W.dvp = W.feat = W.rows = W.dv_t = o;
     if (mode == MB_MODE_FP32) {
         W.feat = o;  o = align256(o + sizeof(float) * B * FEAT_K);
@@ -169,9 +203,10 @@ int launch_joints_only_forward_lh(const void* blob, int nc, const float* rot, co
                                   int B, float* joints, cudaStream_t s);
 int launch_joints_only_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                    const float* g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
+// dfeat: dfeat_parts partial copies, dfeat_stride floats apart, added in order
 int launch_pose_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                         const float* dfeat, const float* dbone, const float* g_joints, int B,
-                         float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
+                         const float* dfeat, int dfeat_parts, size_t dfeat_stride, const float* dbone, const float* g_joints,
+                         int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
 int launch_joints_only_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                int B, float* joints, cudaStream_t s);
 int launch_joints_only_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,

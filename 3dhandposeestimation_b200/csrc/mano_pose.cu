@@ -282,8 +282,8 @@ template <bool JOINTS_ONLY>
 __global__ void __launch_bounds__(WARPS * 32)
 pose_backward_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
                      const float* __restrict__ coeffs, const float* __restrict__ betas,
-                     const float* __restrict__ dfeat_g, const float* __restrict__ dbone_g,
-                     const float* __restrict__ g_joints, int B,
+                     const float* __restrict__ dfeat_g, int dfeat_parts, size_t dfeat_stride,
+                     const float* __restrict__ dbone_g, const float* __restrict__ g_joints, int B,
                      float* __restrict__ g_rot, float* __restrict__ g_coeffs, float* __restrict__ g_betas) {
     __shared__ alignas(16) PoseShared S;
     stage_constants<JOINTS_ONLY>(S, blob, nc);
@@ -303,7 +303,14 @@ pose_backward_kernel(const void* __restrict__ blob, int nc, const float* __restr
             for (int i = lane; i < NJ * BONE_F / 4; i += 32) dst[i] = src[i];
             const float4* fsrc = reinterpret_cast<const float4*>(dfeat_g + hand * FEAT_K);
             float4* fdst = reinterpret_cast<float4*>(s_dfeat);
-            for (int i = lane; i < FEAT_K / 4; i += 32) fdst[i] = fsrc[i];
+            for (int i = lane; i < FEAT_K / 4; i += 32) {
+                float4 a = fsrc[i];
+                for (int part = 1; part < dfeat_parts; ++part) {     // K ranges of a split backward contraction
+                    const float4 b = reinterpret_cast<const float4*>(dfeat_g + part * dfeat_stride + hand * FEAT_K)[i];
+                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                }
+                fdst[i] = a;
+            }
             __syncwarp();
         } else {
             // skinning backward restricted to the five tip vertices (A.2 steps 1-2)
@@ -467,9 +474,9 @@ int launch_joints_only_forward(const void* blob, int nc, const float* rot, const
 }
 
 int launch_pose_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                         const float* dfeat, const float* dbone, const float* g_joints, int B,
-                         float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
-    pose_backward_kernel<false><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B,
+                         const float* dfeat, int dfeat_parts, size_t dfeat_stride, const float* dbone, const float* g_joints,
+                         int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
+    pose_backward_kernel<false><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, dfeat, dfeat_parts, dfeat_stride, dbone, g_joints, B,
                                                                      g_rot, g_coeffs, g_betas);
     return cuda_rc();
 }
@@ -477,7 +484,7 @@ int launch_pose_backward(const void* blob, int nc, const float* rot, const float
 int launch_joints_only_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                 const float* g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas,
                                 cudaStream_t s) {
-    pose_backward_kernel<true><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, nullptr, nullptr, g_joints, B,
+    pose_backward_kernel<true><<<pose_grid(B), WARPS * 32, 0, s>>>(blob, nc, rot, coeffs, betas, nullptr, 0, 0, nullptr, g_joints, B,
                                                                     g_rot, g_coeffs, g_betas);
     return cuda_rc();
 }

@@ -88,6 +88,7 @@ struct SkinProg {
     int blk_ptr[SK_NBLK + 1];
     int ent_code[SK_MAX_ENT];                    // bone | slot << 4 | wait << 7 (slot schedule of skin_pack)
     int cmd[SK_MAX_CMD + 1];                     // [0] = count, then slot (re)load commands sorted by `after`
+    int split[SK_NSEG][8];                       // split sweeps: 6 slot bones, command cursor, bones-touched mask per segment
     alignas(16) float ent_w[SK_MAX_ENT][SK_BV];
     alignas(16) int voff[SK_NPOS];               // float offset of the vertex' x inside a tile: vl * 3 * TP
 };
@@ -105,6 +106,8 @@ __device__ __forceinline__ void stage_prog(SkinProg& P, const void* blob) {
     const int* cm = blob_ptr<int>(blob, L.sk_cmd);
     const int ncmd = cm[0];
     for (int i = threadIdx.x; i <= ncmd; i += blockDim.x) P.cmd[i] = cm[i];
+    const int* sp = blob_ptr<int>(blob, L.sk_split);
+    for (int i = threadIdx.x; i < SK_NSEG * 8; i += blockDim.x) (&P.split[0][0])[i] = sp[i];
     for (int i = threadIdx.x; i < ne * SK_BV; i += blockDim.x) (&P.ent_w[0][0])[i] = ew[i];
     // padding positions (only in the last block, whose segment uses 10 of its 16 vertex slots) are
     // parked on the last slot of the tile: written / read like any vertex, never stored, weights all zero
@@ -201,9 +204,12 @@ struct alignas(128) BoneCache {
         for (int s = 0; s < SK_SLOTS; ++s) mbar_init(smem_u32(&full[s]), 1);
     }
 };
-struct CacheState { int ci, next_after; unsigned parity; };    // identical in every lane
-__device__ __forceinline__ void cache_issue(BoneCache& K, int c, const float* __restrict__ group_base, uint64_t pol) {
+// ci / next_after: cursor into the command list; parity: mbarrier phase per slot; pending: slots whose
+// latest load has not been waited for yet (set at issue, cleared by the first read)
+struct CacheState { int ci, next_after; unsigned parity, pending; };    // identical in every lane
+__device__ __forceinline__ void cache_issue(BoneCache& K, CacheState& S, int c, const float* __restrict__ group_base, uint64_t pol) {
     const int slot = (c >> 10) & 7, bone = (c >> 13) & 15;
+    S.pending |= 1u << slot;
     __syncwarp();                                             // every lane is done reading the slot's previous occupant
     if (elect_one()) {
         const uint32_t bar = smem_u32(&K.full[slot]);
@@ -212,12 +218,34 @@ __device__ __forceinline__ void cache_issue(BoneCache& K, int c, const float* __
     }
 }
 // a warp's first group: nothing was prefetched by a previous sweep
-__device__ __forceinline__ void cache_prologue(BoneCache& K, const SkinProg& P, const float* __restrict__ group_base, uint64_t pol) {
+__device__ __forceinline__ void cache_prologue(BoneCache& K, CacheState& S, const SkinProg& P, const float* __restrict__ group_base,
+                                               uint64_t pol) {
     const int ncmd = P.cmd[0];
     for (int i = 0; i < ncmd; ++i) {
         const int c = P.cmd[1 + i];
-        if ((c >> 17) & 1) cache_issue(K, c, group_base, pol);
+        if ((c >> 17) & 1) cache_issue(K, S, c, group_base, pol);
     }
+}
+// split sweeps: start at segment `part` of a group from its snapshot — load what the schedule has resident there
+__device__ __forceinline__ void cache_begin_part(BoneCache& K, CacheState& S, const SkinProg& P, int part,
+                                                 const float* __restrict__ group_base, uint64_t pol) {
+#pragma unroll
+    for (int sl = 0; sl < SK_SLOTS; ++sl) {
+        const int b = P.split[part][sl];
+        if (b >= 0) cache_issue(K, S, (sl << 10) | (b << 13), group_base, pol);
+    }
+    S.ci = P.split[part][6];
+    S.next_after = S.ci < P.cmd[0] ? (P.cmd[1 + S.ci] & 1023) : (1 << 30);
+}
+// split sweeps: nothing may stay in flight when the warp moves on to another unit
+__device__ __forceinline__ void cache_drain(BoneCache& K, CacheState& S) {
+#pragma unroll
+    for (int sl = 0; sl < SK_SLOTS; ++sl)
+        if (S.pending & (1u << sl)) {
+            mbar_wait_or_trap(smem_u32(&K.full[sl]), (S.parity >> sl) & 1);
+            S.parity ^= 1u << sl;
+        }
+    S.pending = 0;
 }
 __device__ __forceinline__ void cache_begin_group(CacheState& S, const SkinProg& P) {
     S.ci = 0;
@@ -230,8 +258,8 @@ __device__ __forceinline__ void cache_after_entry(BoneCache& K, CacheState& S, c
                                                   uint64_t pol) {
     while (S.next_after == e + 1) {
         const int c = P.cmd[1 + S.ci];
-        if ((c >> 17) & 1) { if (has_next) cache_issue(K, c, group_base + next_off, pol); }
-        else cache_issue(K, c, group_base, pol);
+        if ((c >> 17) & 1) { if (has_next) cache_issue(K, S, c, group_base + next_off, pol); }
+        else cache_issue(K, S, c, group_base, pol);
         ++S.ci;
         S.next_after = S.ci < P.cmd[0] ? (P.cmd[1 + S.ci] & 1023) : (1 << 30);
     }
@@ -239,11 +267,12 @@ __device__ __forceinline__ void cache_after_entry(BoneCache& K, CacheState& S, c
 // the slot of an entry, ready to read (lane = hand: 48 bytes at lane * 12)
 __device__ __forceinline__ const float4* cache_entry(BoneCache& K, CacheState& S, int code, int lane) {
     const int slot = (code >> 4) & 7;
-    if (code & 128) {
+    if (S.pending & (1u << slot)) {                           // first read since the slot's last (re)load
         const uint32_t bar = smem_u32(&K.full[slot]);
         const uint32_t par = (S.parity >> slot) & 1;
         mbar_wait_or_trap(bar, par);
         S.parity ^= 1u << slot;
+        S.pending &= ~(1u << slot);
     }
     return reinterpret_cast<const float4*>(K.slot[slot] + lane * BONE_F);
 }
@@ -314,9 +343,19 @@ __device__ __forceinline__ void slot_to_pairs(float2 (&X)[3][4], const float* sl
 // — the last d floats of the previous segment (kept in the tile's carry slots) instead of the last d of this
 // one — except at the two ends of the row.  [measured: a 32-byte-aligned row pitch alone was worth 12 %:
 // partial-sector writes cost L2 a read-modify-write and DRAM 1.1 GB of fill reads per 2^20 hands]
+// A split sweep (part_first / part_last) has no carry at its first segment — the window starts at the
+// segment — and writes the d floats the next part will not at its last one.
+template <bool SPLIT>
 __device__ __noinline__ void store_segment(const float* tile, float* row0 /* verts row 0 of the group */, int seg,
-                                           int nh, int lane, uint64_t pol) {
+                                           int nh, int lane, uint64_t pol, bool part_first = false, bool part_last = false) {
     const bool last = seg == SK_NSEG - 1;
+    if (SPLIT && part_last && !last && lane < nh) {
+        const int d2 = (4 - lane) & 3;
+        for (int q = 0; q < d2; ++q) {
+            const float* t = tile + (CARRY_F + SEG_F - 2 * d2 + 2 * q) * TP + lane;
+            st_stream2(row0 + (size_t)lane * NVC + SEG_F * seg + SEG_F - 2 * d2 + 2 * q, make_float2(t[0], t[TP]), pol);
+        }
+    }
 #pragma unroll 1
     for (int rb = 0; rb < 8; ++rb) {
 #pragma unroll
@@ -327,7 +366,7 @@ __device__ __noinline__ void store_segment(const float* tile, float* row0 /* ver
             const int d2 = (4 - rr) & 3;                       // d / 2 = (0, 3, 2, 1)[h % 4]; h % 4 == rr
             const int f2 = 24 * seg - d2 + pp;                 // float2 index inside the row
             const int np = last ? (NV * 3 / 2 - 24 * seg + d2) : 24;
-            if (h < nh && pp < np && f2 >= 0) {
+            if (h < nh && pp < np && f2 >= (SPLIT && part_first ? 24 * seg : 0)) {
                 const float* t = tile + (CARRY_F - 2 * d2 + 2 * pp) * TP + h;
                 st_stream2(row0 + (size_t)h * NVC + 2 * f2, make_float2(t[0], t[TP]), pol);
             }
@@ -335,9 +374,13 @@ __device__ __noinline__ void store_segment(const float* tile, float* row0 /* ver
     }
 }
 
+// SPLIT: a work unit is `spu` segments of a group's sweep (spu divides 49) instead of the whole sweep, so a
+// batch of fewer groups than resident warps still fills the machine [B = 4096: 158 us -> see ncu_history];
+// the resident bones of a part come from skin_pack's snapshot of the slot schedule at its first segment.
+template <bool SPLIT>
 __global__ void __launch_bounds__(SKF_THREADS, 1)
 skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed_t,
-                    const float* __restrict__ bone_t, int B, float* __restrict__ verts, float* __restrict__ joints) {
+                    const float* __restrict__ bone_t, int B, float* __restrict__ verts, float* __restrict__ joints, int spu) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -350,29 +393,41 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
     stage_prog(P, blob);
     __syncthreads();
     float* tl = W.tile + CARRY_F * TP + lane;                 // compute side: (float f of the segment, lane)
-    const int ngroups = (B + 31) >> 5;
-    const int g0 = blockIdx.x + warp * gridDim.x, gstep = gridDim.x * SKF_WARPS;
-    auto x_src = [&](int g, int blk) { return v_posed_t + (size_t)g * GROUP_V_FLOATS + (size_t)blk * XBLK_FLOATS; };
+    const int PARTS = SPLIT ? skin_units_per_group(spu) : 1;  // work units per group (the last one may be short)
+    const int UBLK = SPLIT ? spu * SK_SEG_BLKS : SK_NBLK;     // blocks per full unit
+    const int nunits = ((B + 31) >> 5) * PARTS;
+    const int u0 = blockIdx.x + warp * gridDim.x, ustep = gridDim.x * SKF_WARPS;
+    auto x_src = [&](int u, int i) {
+        return v_posed_t + (size_t)(u / PARTS) * GROUP_V_FLOATS + (size_t)((u % PARTS) * UBLK + i) * XBLK_FLOATS;
+    };
+    auto unit_blocks = [&](int u) {                           // of the unit the ring's request cursor is in
+        if (!SPLIT) return SK_NBLK;
+        const int b0 = (u % PARTS) * UBLK;
+        return (b0 + UBLK < SK_NBLK ? b0 + UBLK : SK_NBLK) - b0;
+    };
     const L2Policies pol = make_policies();
-    Cursor CX = {g0, 0, 0u, 0u};
+    Cursor CX = {u0, 0, 0u, 0u};
 #pragma unroll
-    for (int s = 0; s < XSTAGES; ++s) ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src, pol.stream);
-    CacheState CS = {0, 0, 0u};
-    if (g0 < ngroups) cache_prologue(W.bones, P, bone_t + (size_t)g0 * GROUP_BONE_FLOATS, pol.keep);
-    const size_t next_off = (size_t)gstep * GROUP_BONE_FLOATS;
+    for (int s = 0; s < XSTAGES; ++s) ring_request(W.xs, CX, nunits, ustep, unit_blocks(CX.g), lane, x_src, pol.stream);
+    CacheState CS = {0, 0, 0u, 0u};
+    if (!SPLIT && u0 < nunits) cache_prologue(W.bones, CS, P, bone_t + (size_t)u0 * GROUP_BONE_FLOATS, pol.keep);
+    const size_t next_off = (size_t)ustep * GROUP_BONE_FLOATS;
 
-    for (int g = g0; g < ngroups; g += gstep) {
+    for (int u = u0; u < nunits; u += ustep) {
+        const int g = u / PARTS, part = u % PARTS;
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
         const float* bgrp = bone_t + (size_t)g * GROUP_BONE_FLOATS;
-        const bool has_next = g + gstep < ngroups;
-        cache_begin_group(CS, P);
+        const bool has_next = !SPLIT && u + ustep < nunits;
+        if (SPLIT) cache_begin_part(W.bones, CS, P, part * spu, bgrp, pol.keep);
+        else cache_begin_group(CS, P);
+        const int blk1 = (part + 1) * UBLK < SK_NBLK ? (part + 1) * UBLK : SK_NBLK;
 #pragma unroll 1
-        for (int blk = 0; blk < SK_NBLK; ++blk) {
+        for (int blk = part * UBLK; blk < blk1; ++blk) {
             float2 X[3][4], ACC[3][4];
             slot_to_pairs(X, ring_wait(W.xs, CX) + lane);
             ++CX.consumed;
             __syncwarp();                                     // every lane has its copy: the slot can be refilled
-            ring_request(W.xs, CX, ngroups, gstep, SK_NBLK, lane, x_src, pol.stream);
+            ring_request(W.xs, CX, nunits, ustep, unit_blocks(CX.g), lane, x_src, pol.stream);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -400,7 +455,11 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
             if (blk & 1) {                                    // second block of a segment: the segment is complete
                 const int seg = blk >> 1;
                 __syncwarp();
-                store_segment(W.tile, verts + (size_t)g * 32 * NVC, seg, nh, lane, pol.stream);
+                if (SPLIT)
+                    store_segment<true>(W.tile, verts + (size_t)g * 32 * NVC, seg, nh, lane, pol.stream,
+                                  blk == part * UBLK + 1, blk == blk1 - 1);
+                else
+                    store_segment<false>(W.tile, verts + (size_t)g * 32 * NVC, seg, nh, lane, pol.stream);
                 if (joints != nullptr && lane < nh) {
 #pragma unroll
                     for (int t = 0; t < N_TIP; ++t)
@@ -417,6 +476,7 @@ skin_forward_kernel(const void* __restrict__ blob, const float* __restrict__ v_p
                 __syncwarp();
             }
         }
+        if (SPLIT) cache_drain(W.bones, CS);
     }
 }
 
@@ -494,12 +554,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&p);
 }
 
+// SPLIT: a work unit is `spu` segments of a group's sweep; the unit's bone sums go to dparts[unit][192][32]
+// (touched bones only) and dbone_reduce_kernel adds the units of a group in a fixed order.
+template <bool SPLIT>
 __global__ void __launch_bounds__(SKB_THREADS, 1)
 skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_posed_t,
                      const float* __restrict__ bone_t, const float* __restrict__ g_verts,
                      const float* __restrict__ g_joints, int B,
                      float* __restrict__ dv_t, unsigned char* __restrict__ dvp, float* __restrict__ dbone,
-                     int dbone_hand_minor) {
+                     int dbone_hand_minor, float* __restrict__ dparts, int spu) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -515,19 +578,25 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
     const RowMap rm(lane);
     float* tsd = W.tile + rm.tile_base();                     // load side of the g tile (same mapping as the forward's store side)
     const int bar = 1 + pair;
-    const int ngroups = (B + 31) >> 5;
-    const int g0 = blockIdx.x + pair * gridDim.x, gstep = gridDim.x * SKB_PAIRS;
+    const int PARTS = SPLIT ? skin_units_per_group(spu) : 1;  // work units per group (the last one may be short)
+    const int nunits = ((B + 31) >> 5) * PARTS;
+    const int u0 = blockIdx.x + pair * gridDim.x, ustep = gridDim.x * SKB_PAIRS;
     const L2Policies pol = make_policies();
-    CacheState CS = {0, 0, 0u};
-    if (role == 0 && g0 < ngroups) cache_prologue(W.bones, P, bone_t + (size_t)g0 * GROUP_BONE_FLOATS, pol.keep);
-    const size_t next_off = (size_t)gstep * GROUP_BONE_FLOATS;
+    CacheState CS = {0, 0, 0u, 0u};
+    if (!SPLIT && role == 0 && u0 < nunits) cache_prologue(W.bones, CS, P, bone_t + (size_t)u0 * GROUP_BONE_FLOATS, pol.keep);
+    const size_t next_off = (size_t)ustep * GROUP_BONE_FLOATS;
 
-    for (int g = g0; g < ngroups; g += gstep) {
+    for (int u = u0; u < nunits; u += ustep) {
+        const int g = u / PARTS;
+        const int seg0 = SPLIT ? (u % PARTS) * spu : 0, seg1 = SPLIT && seg0 + spu < SK_NSEG ? seg0 + spu : SK_NSEG;
         const int nh = (B - g * 32) < 32 ? (B - g * 32) : 32;
         const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
         const float* bgrp = bone_t + (size_t)g * GROUP_BONE_FLOATS;
-        const bool has_next = g + gstep < ngroups;
-        cache_begin_group(CS, P);
+        const bool has_next = !SPLIT && u + ustep < nunits;
+        if (role == 0) {
+            if (SPLIT) cache_begin_part(W.bones, CS, P, seg0, bgrp, pol.keep);
+            else cache_begin_group(CS, P);
+        }
         const float* grow = g_verts + (size_t)g * 32 * NVC + rm.row_base();
         // each role loads half of a segment's row pieces (one instruction = 4 rows x 8 float2) into
         // registers one segment ahead of its use
@@ -545,10 +614,10 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                 }
             }
         };
-        prefetch_g(0);
+        prefetch_g(seg0);
         float2 va[3][4], vbk[3][4];                           // role 1: rest-pose blocks (packed pairs), loaded one block ahead
         if (role == 0) {
-            if (dvp != nullptr) {
+            if (dvp != nullptr && seg1 == SK_NSEG) {
                 // zero the 16 padding K columns (2352..2367) of the last chunk of the gradient tiles
                 unsigned char* tb = dvp + (size_t)(g >> 2) * TCB_A_TILE_BYTES + (size_t)(TCB_K_CHUNKS - 1) * TCB_A_CHUNK_BYTES;
                 const int rg = (g & 3) * 4 + (lane >> 3), r = lane & 7;
@@ -560,7 +629,7 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                 }
             }
         } else {
-            load_xpairs(va, vb, pol.stream);
+            load_xpairs(va, vb + (size_t)(2 * seg0) * XBLK_FLOATS, pol.stream);
 #pragma unroll 8
             for (int i = 0; i < NJ * BONE_F; ++i) W.dacc[i * DP + lane] = 0.f;
         }
@@ -626,7 +695,7 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
             skin_block_da(P, blk, W.dacc + lane, G, V);
         };
 
-        for (int seg = 0; seg < SK_NSEG; ++seg) {
+        for (int seg = seg0; seg < seg1; ++seg) {
             pair_barrier(bar);                                  // both warps are done with the previous tile
 #pragma unroll
             for (int rb2 = 0; rb2 < 4; ++rb2) {
@@ -654,18 +723,33 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                 }
                 pair_barrier(bar);
             }
-            if (seg + 1 < SK_NSEG) prefetch_g(seg + 1);
+            if (seg + 1 < seg1) prefetch_g(seg + 1);
             if (role == 0) {
                 dv_block(2 * seg);
                 dv_block(2 * seg + 1);
             } else {
                 load_xpairs(vbk, vb + (size_t)(2 * seg + 1) * XBLK_FLOATS, pol.stream);
                 da_block(2 * seg, va);
-                if (seg + 1 < SK_NSEG) load_xpairs(va, vb + (size_t)(2 * seg + 2) * XBLK_FLOATS, pol.stream);
+                if (seg + 1 < seg1) load_xpairs(va, vb + (size_t)(2 * seg + 2) * XBLK_FLOATS, pol.stream);
                 da_block(2 * seg + 1, vbk);
             }
         }
-        if (role == 1) {
+        if (SPLIT) {
+            if (role == 0) {
+                cache_drain(W.bones, CS);
+            } else {
+                __syncwarp();
+                int touched = 0;
+                for (int seg = seg0; seg < seg1; ++seg) touched |= P.split[seg][7];
+                float* dt = dparts + (size_t)u * GROUP_BONE_FLOATS + lane;
+                for (int k = 0; k < NJ; ++k)
+                    if ((touched >> k) & 1) {
+#pragma unroll
+                        for (int i = 0; i < BONE_F; ++i) dt[(k * BONE_F + i) * 32] = W.dacc[(k * BONE_F + i) * DP + lane];
+                    }
+                __syncwarp();
+            }
+        } else if (role == 1) {
             // per-bone sums of the group leave as dbone[h][16][12] rows (transposed out of the accumulator)
             __syncwarp();
             if (dbone_hand_minor) {                            // the lane = hand pose backward reads them as they are
@@ -682,6 +766,42 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
             __syncwarp();
         }
     }
+}
+
+// split backward sweeps: dbone[g] = sum over the group's units (ascending, touched bones only) of dparts.
+// One CTA per (group, bone): thread -> (element i = t / 32, hand = t % 32).
+__global__ void __launch_bounds__(BONE_F * 32)
+dbone_reduce_kernel(const void* __restrict__ blob, const float* __restrict__ dparts, int B, int spu,
+                    float* __restrict__ dbone, int dbone_hand_minor) {
+    __shared__ int touched[SK_NSEG], plist[SK_NSEG], np_s;
+    const int* split = blob_ptr<int>(blob, blob_layout().sk_split);
+    const int g = blockIdx.x / NJ, k = blockIdx.x % NJ;
+    const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int parts = skin_units_per_group(spu);
+    if (threadIdx.x < SK_NSEG) touched[threadIdx.x] = split[threadIdx.x * 8 + 7];
+    __syncthreads();
+    if (threadIdx.x == 0) {                                    // the units that hold a sum for bone k, ascending
+        int n = 0;
+        for (int p = 0; p < parts; ++p) {
+            int m = 0;
+            for (int seg = p * spu; seg < (p + 1) * spu && seg < SK_NSEG; ++seg) m |= touched[seg];
+            if ((m >> k) & 1) plist[n++] = p;
+        }
+        np_s = n;
+    }
+    __syncthreads();
+    const int n = np_s;
+    const float* src = dparts + (size_t)g * parts * GROUP_BONE_FLOATS + (k * BONE_F + i) * 32 + lane;
+    float acc = 0.f;
+    for (int j = 0; j < n; j += 4) {                           // four independent loads in flight, added in order
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = j + q < n ? src[(size_t)plist[j + q] * GROUP_BONE_FLOATS] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc += v[q];
+    }
+    if (dbone_hand_minor) dbone[(size_t)g * GROUP_BONE_FLOATS + (k * BONE_F + i) * 32 + lane] = acc;
+    else if (g * 32 + lane < B) dbone[((size_t)g * 32 + lane) * (NJ * BONE_F) + k * BONE_F + i] = acc;
 }
 
 // ------------------------------------------------- layout conversions (fp32 anchor mode, mb_lbs_forward)
@@ -853,6 +973,27 @@ int skin_pack(const float* skin_w, const int32_t* skin_b, void* host_blob, int32
             if (cmds[i].after < 0 || cmds[i].after >= 1023) return MB_E_MODEL;
             cmd[1 + i] = (cmds[i].after + 1) | (cmds[i].slot << 10) | (cmds[i].bone << 13) | (cmds[i].next_group << 17);
         }
+        // slot contents and command cursor at the start of every segment: a split sweep (small batches) can
+        // start there; [7] = the bones the segment's entries read
+        int* split = reinterpret_cast<int*>(out + L.sk_split);
+        static_assert(SK_SLOTS <= 6, "6 slots + cursor + mask per row");
+        for (int p = 0; p < SK_NSEG; ++p) {
+            const int e0 = blk_ptr[p * SK_SEG_BLKS];
+            int state[SK_SLOTS];
+            for (int sl = 0; sl < SK_SLOTS; ++sl) state[sl] = -1;
+            for (const Cmd& c : cmds) if (c.next_group) state[c.slot] = c.bone;
+            int ci0 = 0;
+            for (const Cmd& c : cmds) {
+                if (c.after >= e0) break;
+                if (!c.next_group) state[c.slot] = c.bone;
+                ++ci0;
+            }
+            for (int sl = 0; sl < 6; ++sl) split[p * 8 + sl] = sl < SK_SLOTS ? state[sl] : -1;
+            split[p * 8 + 6] = ci0;
+            int touched = 0;
+            for (int e = e0; e < blk_ptr[(p + 1) * SK_SEG_BLKS]; ++e) touched |= 1 << (ent_bone[e] & 15);
+            split[p * 8 + 7] = touched;
+        }
     }
     for (int c = 0; c < SK_TMPL_PAD; ++c) {
         const int p = c / 3;
@@ -920,6 +1061,26 @@ int skin_program_check(const void* host_blob, int32_t* stats) {
         }
         if (ci != ncmd) return MB_E_MODEL;
     }
+    // split sweeps: a sweep started at any segment from its snapshot, without any next-group load, finds its bones
+    const int* split = reinterpret_cast<const int*>(in + L.sk_split);
+    for (int p = 0; p < SK_NSEG; ++p) {
+        const int e0 = blk_ptr[p * SK_SEG_BLKS], e1 = ne;
+        int touched = 0;
+        for (int e = e0; e < blk_ptr[(p + 1) * SK_SEG_BLKS]; ++e) touched |= 1 << (ent[e] & 15);
+        if (split[p * 8 + 7] != touched) return MB_E_MODEL;
+        int state[SK_SLOTS];
+        for (int s = 0; s < SK_SLOTS; ++s) state[s] = split[p * 8 + s];
+        int ci = split[p * 8 + 6];
+        for (int e = e0; e < e1; ++e) {
+            const int k = ent[e] & 15, s = (ent[e] >> 4) & 7;
+            if (state[s] != k) return MB_E_MODEL;
+            while (ci < ncmd && (cmd[1 + ci] & 1023) == e + 1) {
+                const int c = cmd[1 + ci];
+                if (!((c >> 17) & 1)) state[(c >> 10) & 7] = (c >> 13) & 15;
+                ++ci;
+            }
+        }
+    }
     if (stats) { stats[0] = ne; stats[1] = ncmd; stats[2] = SK_NBLK; stats[3] = max_bones; }
     return 0;
 }
@@ -930,28 +1091,49 @@ int launch_skin_forward(const void* blob, const float* v_posed_t, const float* b
     if (B <= 0) return 0;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(skin_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKF_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(skin_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKF_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(skin_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKF_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    const int ngroups = (B + 31) >> 5;     // small batches spread one group per SM before warps double up
-    skin_forward_kernel<<<ngroups < NUM_SMS ? ngroups : NUM_SMS, SKF_THREADS, SKF_SMEM, s>>>(blob, v_posed_t, bone_t, B, verts, joints);
+    const int ngroups = (B + 31) >> 5;
+    const int spu = skin_segments_per_unit(ngroups, SKF_SWEEPERS);
+    if (spu < SK_NSEG) {
+        const int nunits = ngroups * skin_units_per_group(spu);
+        skin_forward_kernel<true><<<nunits < NUM_SMS ? nunits : NUM_SMS, SKF_THREADS, SKF_SMEM, s>>>(blob, v_posed_t, bone_t, B, verts, joints, spu);
+    } else {
+        skin_forward_kernel<false><<<NUM_SMS, SKF_THREADS, SKF_SMEM, s>>>(blob, v_posed_t, bone_t, B, verts, joints, SK_NSEG);
+    }
     return cuda_rc();
 }
 
 int launch_skin_backward(const void* blob, const float* v_posed_t, const float* bone_t, const float* g_verts,
                          const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, int dbone_hand_minor,
-                         cudaStream_t s) {
+                         float* dparts, cudaStream_t s) {
     if (B <= 0) return 0;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(skin_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKB_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(skin_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKB_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(skin_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKB_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
     const int ngroups = (B + 31) >> 5;
-    skin_backward_kernel<<<ngroups < NUM_SMS ? ngroups : NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(blob, v_posed_t, bone_t, g_verts, g_joints,
-                                                                                       B, dv_t, dvp, dbone, dbone_hand_minor);
+    const int spu = skin_segments_per_unit(ngroups, SKB_SWEEPERS);
+    if (spu < SK_NSEG) {
+        if (dparts == nullptr) return MB_E_NULL;
+        const int nunits = ngroups * skin_units_per_group(spu);
+        skin_backward_kernel<true><<<nunits < NUM_SMS ? nunits : NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(
+            blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp, dbone, dbone_hand_minor, dparts, spu);
+        int rc = cuda_rc();
+        if (rc) return rc;
+        dbone_reduce_kernel<<<ngroups * NJ, BONE_F * 32, 0, s>>>(blob, dparts, B, spu, dbone, dbone_hand_minor);
+    } else {
+        skin_backward_kernel<false><<<NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp,
+                                                                          dbone, dbone_hand_minor, nullptr, SK_NSEG);
+    }
     return cuda_rc();
 }
 

@@ -16,9 +16,10 @@ int launch_skin_forward(const void* blob, const float* v_posed_t, const float* b
                         float* verts, float* joints, cudaStream_t s);
 // exactly one of dv_t (fp32, hand-minor block order) / dvp (bf16 hi+mid UMMA tiles) is non-NULL
 // dbone: [B][16][12] rows, or hand-minor [groups][192][32] when dbone_hand_minor != 0
+// dparts: WorkLayout::dparts scratch, needed when skin_segments_per_unit(groups, SKB_SWEEPERS) < SK_NSEG
 int launch_skin_backward(const void* blob, const float* v_posed_t, const float* bone_t, const float* g_verts,
                          const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, int dbone_hand_minor,
-                         cudaStream_t s);
+                         float* dparts, cudaStream_t s);
 // layout conversions used by the fp32 anchor mode and the stand-alone mb_lbs_forward
 int launch_rows_to_t(const void* blob, const float* rows, int pitch, int B, float* t, cudaStream_t s);
 int launch_t_to_rows(const void* blob, const float* t, int pitch, int B, float* rows, cudaStream_t s);

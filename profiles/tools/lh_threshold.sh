@@ -1,0 +1,8 @@
+#!/bin/bash
+for T in 4096 1000000; do for B in 4096 8192 16384 32768 65536; do
+  MB_TUNE_LH_MIN=$T python bench.py --hands $B --rotate 8 --steps 100 --warmup 10 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('lh_min', $T, 'B', $B, 'ms/step', round(d['ms_per_step'],4), {k: round(v['ms']*1e3,1) for k,v in d['stages_ms'].items()})"
+done; done

@@ -84,10 +84,11 @@ def test_mano_matches_reference_golden(pkg, synth_model, cuda_device, name, nc, 
 
 
 @pytest.mark.parametrize("mode", ACCURATE_MODES)
-@pytest.mark.parametrize("B,nc", [(1, 45), (2, 45), (7, 10), (129, 45), (1000, 45), (4096, 10), (4133, 45), (5000, 6)])
+@pytest.mark.parametrize("B,nc", [(1, 45), (2, 45), (7, 10), (129, 45), (1000, 45), (1344, 45), (2720, 10), (4096, 10), (4133, 45), (5000, 6), (8192, 10), (9001, 45),
+                                  (20001, 45)])
 def test_mano_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc, mode):
     """Ragged sizes (partial hand groups, partial tcgen05 tiles) up to BASELINE config 2 (B=4096,
-    nc=10, the Resnet50MANO3DHandPose head workload).  B >= 4096 in the tensor-core modes runs the
+    nc=10, the Resnet50MANO3DHandPose head workload).  B >= 8192 in the tensor-core modes runs the
     one-thread-per-hand pose kernels, below that the one-warp-per-hand kernels."""
     rot, pose, beta = mano_inputs(B, nc, seed=B + nc)
     layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc, mode=mode)
@@ -108,10 +109,10 @@ def test_mano_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc, mode):
         assert rel(t.grad.cpu().numpy()[idx], want) < GRAD_TOL
 
 
-@pytest.mark.parametrize("B,nc", [(4099, 45), (6000, 10)])
+@pytest.mark.parametrize("B,nc", [(4099, 45), (8195, 45), (12000, 10)])
 def test_mano_joints_only_large_batch_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc):
     """The heads' / fitting loop's case at a batch that runs the one-thread-per-hand joints-only kernels
-    (>= 4096 hands): 21 joints and their gradients without the 778-vertex contraction."""
+    (>= 8192 hands): 21 joints and their gradients without the 778-vertex contraction."""
     import torch
 
     rot, pose, beta = mano_inputs(B, nc, seed=B + nc)
@@ -216,7 +217,7 @@ def test_mano_linearity_property_full_size(pkg, synth_model, cuda_device):
     t = to_dev(cuda_device, rot, pose, beta)
     v, j = layer(*t)
     sel = np.array([0, 1, 2, 777, 4095, 4096, 32767, 65534, 65535])
-    # (a) bit-exact in another batch served by the same kernels (>= 4096 hands: one thread per hand),
+    # (a) bit-exact in another batch served by the same kernels (>= 8192 hands: one thread per hand),
     #     at other positions of a hand group / tcgen05 tile ...
     order = torch.from_numpy(np.r_[np.arange(5000, 5003), sel, np.arange(7000, 7000 + 8192 - 12)]).to(cuda_device)
     v_mid, j_mid = layer(*[x[order] for x in t])
