@@ -12,8 +12,8 @@ The directory name is not a Python identifier; import it with
 from . import assets, fitting  # noqa: F401
 from ._cabi import ManoB200Error, lib as load_library  # noqa: F401
 from .criterions import L2Loss, MPJPE, compute_regularization_loss  # noqa: F401
-from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv  # noqa: F401
+from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv, mano_joints_to_rhd_uv, match_mano_to_RHD  # noqa: F401
 from .mano_layer import ManoLayer  # noqa: F401
 
-__all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "MPJPE", "L2Loss",
+__all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "match_mano_to_RHD", "mano_joints_to_rhd_uv", "MPJPE", "L2Loss",
            "compute_regularization_loss", "ManoB200Error", "assets", "load_library"]

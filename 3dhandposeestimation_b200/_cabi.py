@@ -44,6 +44,8 @@ SIGNATURES = {
     "mb_fk_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "mb_project_uv_forward": (_i, [_p, _p, _i, _i, _p, _p]),
     "mb_project_uv_backward": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "mb_joint_epilogue_forward": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "mb_joint_epilogue_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "mb_masked_joint_reduce": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p]),
     "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
     "mb_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),

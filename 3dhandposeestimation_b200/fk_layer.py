@@ -136,3 +136,79 @@ def batch_project_xyz_to_uv(positions_xyz, camera_intrinsic_matrix):
     if xyz.dim() != 3 or xyz.shape[2] != 3 or K.shape != (xyz.shape[0], 3, 3):
         raise RuntimeError("expected positions_xyz[B,N,3] and camera_intrinsic_matrix[B,3,3]")
     return _ProjectFunction.apply(xyz, K)
+
+
+class _JointEpilogueFunction(torch.autograd.Function):
+    """joints -> (rel_normalized, joint_xyz21[, uv21]) in one kernel (joint_epilogue.cu)."""
+
+    @staticmethod
+    def forward(ctx, joints, scale, root, K, swap):
+        lib = _cabi.lib()
+        B = joints.shape[0]
+        rel = torch.empty_like(joints)
+        xyz = torch.empty_like(joints)
+        uv = torch.empty((B, 21, 2), dtype=torch.float32, device=joints.device) if K is not None else None
+        _cabi.check(lib.mb_joint_epilogue_forward(joints.data_ptr(), scale.data_ptr(), root.data_ptr(),
+                                                  K.data_ptr() if K is not None else 0, B, int(swap), rel.data_ptr(),
+                                                  xyz.data_ptr(), uv.data_ptr() if uv is not None else 0,
+                                                  _cabi.stream_handle(joints.device)), "mb_joint_epilogue_forward")
+        ctx.save_for_backward(joints, scale, root, K)
+        ctx.swap = int(swap)
+        return rel, xyz, uv                  # uv is None when no intrinsics were given
+
+    @staticmethod
+    def backward(ctx, g_rel, g_xyz, g_uv):
+        joints, scale, root, K = ctx.saved_tensors
+        lib = _cabi.lib()
+        B = joints.shape[0]
+        prep = lambda g: None if g is None else g.to(torch.float32).contiguous()
+        g_rel, g_xyz = prep(g_rel), prep(g_xyz)
+        g_uv = prep(g_uv) if K is not None else None
+        ptr = lambda t: t.data_ptr() if t is not None else 0
+        g_joints = torch.empty_like(joints)
+        g_scale = torch.empty_like(scale) if ctx.needs_input_grad[1] else None
+        g_root = torch.empty_like(root) if ctx.needs_input_grad[2] else None
+        _cabi.check(lib.mb_joint_epilogue_backward(joints.data_ptr(), scale.data_ptr(), root.data_ptr(), ptr(K), ptr(g_rel),
+                                                   ptr(g_xyz), ptr(g_uv), B, ctx.swap, g_joints.data_ptr(), ptr(g_scale),
+                                                   ptr(g_root), _cabi.stream_handle(joints.device)),
+                    "mb_joint_epilogue_backward")
+        return g_joints, g_scale, g_root, None, None
+
+
+def _joint_epilogue(mano_joints, index_root_bone_length, kp_coord_xyz_root, K, joint_order_switched):
+    if not isinstance(mano_joints, torch.Tensor) or mano_joints.device.type != "cuda":
+        raise _cabi.ManoB200Error("match_mano_to_RHD only runs on CUDA tensors (sm_100a); there is no CPU fallback")
+    dev = mano_joints.device
+    joints = _as_f32_cuda(mano_joints, "mano_joints", dev)
+    B = joints.shape[0]
+    if joints.dim() != 3 or joints.shape[1:] != (21, 3):
+        raise RuntimeError("expected mano_joints[B,21,3]")
+    scale = _as_f32_cuda(index_root_bone_length, "index_root_bone_length", dev)
+    root = _as_f32_cuda(kp_coord_xyz_root, "kp_coord_xyz_root", dev)
+    if scale.numel() != B or root.shape != (B, 3):
+        raise RuntimeError("expected index_root_bone_length[B,1] and kp_coord_xyz_root[B,3]")
+    if K is not None:
+        K = _as_f32_cuda(K, "camera_intrinsic_matrix", dev)
+        if K.shape != (B, 3, 3):
+            raise RuntimeError("expected camera_intrinsic_matrix[B,3,3]")
+    if joint_order_switched is None:
+        joint_order_switched = _reference_joint_order_switched()
+    return _JointEpilogueFunction.apply(joints, scale, root, K, not joint_order_switched)
+
+
+def match_mano_to_RHD(mano_joints, index_root_bone_length, kp_coord_xyz_root, joint_order_switched=None):
+    """``match_mano_to_RHD`` of the MANO heads (network/Resnet50MANO3DHandPose.py:35-60,
+    network/MANO3DHandPose.py:30-55) -> ``(mano_joints_rel_normalized, joint_xyz21)``.
+    ``joint_order_switched`` defaults to the reference's global ``config.joint_order_switched``
+    (True when the reference tree is not loaded).  Unlike the reference, ``mano_joints`` is not
+    permuted in place."""
+    rel, xyz, _ = _joint_epilogue(mano_joints, index_root_bone_length, kp_coord_xyz_root, None, joint_order_switched)
+    return rel, xyz
+
+
+def mano_joints_to_rhd_uv(mano_joints, index_root_bone_length, kp_coord_xyz_root, camera_intrinsic_matrix,
+                          joint_order_switched=None):
+    """``match_mano_to_RHD`` followed by ``batch_project_xyz_to_uv`` (Resnet50MANO3DHandPose.py:71-73)
+    as one kernel -> ``(rel_normalized, joint_xyz21, uv21)``."""
+    return _joint_epilogue(mano_joints, index_root_bone_length, kp_coord_xyz_root, camera_intrinsic_matrix,
+                           joint_order_switched)

@@ -155,6 +155,23 @@ MB_API int mb_project_uv_forward(const float* xyz, const float* K, int B, int N,
 MB_API int mb_project_uv_backward(const float* xyz, const float* K, const float* g_uv, int B, int N,
                            float* g_xyz, mb_stream_t stream);
 
+/* Replaces match_mano_to_RHD (network/Resnet50MANO3DHandPose.py:35-60; the same body at
+ * network/MANO3DHandPose.py:30-55) followed by batch_project_xyz_to_uv (Resnet50MANO3DHandPose.py:73)
+ * in one pass over joints[B][21][3]:
+ *   per-finger joint reversal when swap_order != 0 (the reference's `not config.joint_order_switched`),
+ *   r = p - p_0, n = r / ||r_12||, x = n * index_root_bone_length + kp_coord_xyz_root, uv = project(K, x).
+ * rel_normalized and uv may be NULL (not wanted); K may be NULL when uv is.  Unlike the reference the
+ * input is not permuted in place.  ||r_12|| == 0 divides by zero exactly as the reference does. */
+MB_API int mb_joint_epilogue_forward(const float* joints, const float* index_root_bone_length,
+                              const float* kp_coord_xyz_root, const float* K, int B, int swap_order,
+                              float* rel_normalized, float* xyz, float* uv, mb_stream_t stream);
+/* Gradients w.r.t. joints (required), index_root_bone_length and kp_coord_xyz_root (each may be NULL);
+ * g_rel / g_xyz / g_uv may each be NULL (treated as zero). */
+MB_API int mb_joint_epilogue_backward(const float* joints, const float* index_root_bone_length,
+                               const float* kp_coord_xyz_root, const float* K, const float* g_rel,
+                               const float* g_xyz, const float* g_uv, int B, int swap_order,
+                               float* g_joints, float* g_scale, float* g_root, mb_stream_t stream);
+
 /* ------------------------------------------------------------ reductions ---
  * Replaces MPJPE.forward (criterions/metrics.py:10-27) and L2Loss.forward
  * (criterions/loss.py:10-25): global mean over the visible joints of the batch,

@@ -196,3 +196,46 @@ def l2loss_backward(pre_xyz, gt_xyz, keypoint_vis, dtype=np.float64):
 def regularizer(theta, beta, dtype=np.float64):
     """criterions/loss.py:113-117: (||theta||_F + 10 ||beta||_F) / 100 over the batch."""
     return dtype((np.linalg.norm(np.asarray(theta, dtype)) + 10.0 * np.linalg.norm(np.asarray(beta, dtype))) / 100.0)
+
+
+def match_mano_to_rhd(mano_joints, index_root_bone_length, kp_coord_xyz_root, joint_order_switched=True, dtype=np.float64):
+    """``match_mano_to_RHD`` (network/Resnet50MANO3DHandPose.py:35-60, the same body at
+    network/MANO3DHandPose.py:30-55): optional per-finger joint reversal, root-relative
+    coordinates, division by ||joint 12 - root||, then * index_root_bone_length + root.
+    Returns (rel_normalized[B,21,3], joint_xyz21[B,21,3]).  The reference permutes its argument
+    in place; this restatement (and the product) leave the input alone."""
+    j = np.asarray(mano_joints, dtype=dtype)
+    if not joint_order_switched:
+        j = swap_joint_order(j)
+    rel = j - j[:, :1]
+    s = np.sqrt(np.sum(rel[:, 12] ** 2, axis=-1))[:, None, None]
+    reln = rel / s
+    L = np.asarray(index_root_bone_length, dtype=dtype).reshape(-1, 1, 1)
+    root = np.asarray(kp_coord_xyz_root, dtype=dtype).reshape(-1, 1, 3)
+    return reln, reln * L + root
+
+
+def match_mano_to_rhd_backward(mano_joints, index_root_bone_length, kp_coord_xyz_root, g_rel, g_xyz,
+                               joint_order_switched=True, dtype=np.float64):
+    """Gradients of ``match_mano_to_rhd`` w.r.t. (mano_joints, index_root_bone_length,
+    kp_coord_xyz_root) for upstream gradients of both outputs."""
+    j = np.asarray(mano_joints, dtype=dtype)
+    if not joint_order_switched:
+        j = swap_joint_order(j)
+    L = np.asarray(index_root_bone_length, dtype=dtype).reshape(-1, 1, 1)
+    g_rel = np.asarray(g_rel, dtype=dtype)
+    g_xyz = np.asarray(g_xyz, dtype=dtype)
+    rel = j - j[:, :1]
+    s = np.sqrt(np.sum(rel[:, 12] ** 2, axis=-1))[:, None, None]
+    reln = rel / s
+    g_L = np.sum(reln * g_xyz, axis=(1, 2)).reshape(-1, 1)
+    g_root = g_xyz.sum(axis=1)
+    gn = g_rel + L * g_xyz
+    g_s = -np.sum(gn * rel, axis=(1, 2), keepdims=True) / (s * s)
+    gr = gn / s
+    gr[:, 12] += (g_s * rel[:, 12:13] / s)[:, 0]
+    gj = gr.copy()
+    gj[:, 0] -= gr.sum(axis=1)
+    if not joint_order_switched:
+        gj = swap_joint_order(gj)          # the reversal is its own inverse
+    return gj, g_L, g_root

@@ -101,6 +101,28 @@ def proj_case():
     return dict(xyz=n(xyz), K=n(K), uv=n(uv), g_uv=n(gu), g_xyz=n(xyz.grad))
 
 
+def match_case(B, seed, switched):
+    """match_mano_to_RHD -> batch_project_xyz_to_uv, the heads' joint epilogue
+    (network/Resnet50MANO3DHandPose.py:35-60,73)."""
+    from network.Resnet50MANO3DHandPose import Resnet50MANO3DHandPose
+    ref.config.joint_order_switched = switched
+    g = torch.Generator().manual_seed(seed)
+    j = (torch.randn(B, 21, 3, generator=g) * .04).requires_grad_()
+    L = (torch.rand(B, 1, generator=g) * .05 + .02).requires_grad_()
+    root = (torch.randn(B, 3, generator=g) * .05 + torch.tensor([0, 0, .6])).requires_grad_()
+    K = torch.tensor([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1.]]).repeat(B, 1, 1)
+    rel, xyz = Resnet50MANO3DHandPose.match_mano_to_RHD(None, j.clone(), L, root)   # the reference permutes its argument in place
+    uv = ref.batch_project_xyz_to_uv(xyz, K)
+    gr = torch.randn(rel.shape, generator=g)
+    gx = torch.randn(xyz.shape, generator=g)
+    gu = torch.randn(uv.shape, generator=g) * 1e-3
+    ((rel * gr).sum() + (xyz * gx).sum() + (uv * gu).sum()).backward()
+    ref.config.joint_order_switched = True
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(joints=n(j), scale=n(L), root=n(root), K=n(K), rel=n(rel), xyz=n(xyz), uv=n(uv), g_rel=n(gr), g_xyz=n(gx),
+                g_uv=n(gu), g_joints=n(j.grad), g_scale=n(L.grad), g_root=n(root.grad), switched=np.array(switched))
+
+
 def main():
     model = assets.synthetic_mano()
     with tempfile.TemporaryDirectory() as td:
@@ -114,6 +136,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "reduce_vis80.npz"), **reduce_case(16, 5, .8))
     np.savez_compressed(os.path.join(HERE, "reduce_none_visible.npz"), **reduce_case(4, 6, -1.0))
     np.savez_compressed(os.path.join(HERE, "project_uv.npz"), **proj_case())
+    np.savez_compressed(os.path.join(HERE, "match_switched.npz"), **match_case(6, 77, True))
+    np.savez_compressed(os.path.join(HERE, "match_unswitched.npz"), **match_case(6, 78, False))
 
     # model checksum pin + real-pkl known answers (scalars only)
     chk = {k: float(np.asarray(v, dtype=np.float64).sum()) for k, v in model.items()}

@@ -366,6 +366,68 @@ def test_projection_and_z0_branch(pkg, cuda_device):
     assert rel(xyz.grad.cpu().numpy()[fin], g["g_xyz"][fin]) < GRAD_TOL
 
 
+# ---------------------------------------------------------------- joint epilogue
+@pytest.mark.parametrize("name", ["match_switched.npz", "match_unswitched.npz"])
+def test_match_mano_to_rhd_matches_reference_golden(pkg, cuda_device, name):
+    """match_mano_to_RHD -> batch_project_xyz_to_uv of the reference heads, forward and the three input
+    gradients, against fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+    g = load_golden(name)
+    switched = bool(g["switched"])
+    j, L, root = to_dev(cuda_device, g["joints"], g["scale"], g["root"], grad=True)
+    K, gr, gx, gu = to_dev(cuda_device, g["K"], g["g_rel"], g["g_xyz"], g["g_uv"])
+    keep = j.detach().clone()
+    rel_n, xyz, uv = pkg.mano_joints_to_rhd_uv(j, L, root, K, joint_order_switched=switched)
+    assert bool((j.detach() == keep).all())                    # the input is not permuted in place
+    assert np.abs(rel_n.detach().cpu().numpy() - g["rel"]).max() < 2e-6 * np.abs(g["rel"]).max()
+    assert np.abs(xyz.detach().cpu().numpy() - g["xyz"]).max() < 2e-7
+    assert np.abs(uv.detach().cpu().numpy() - g["uv"]).max() < 2e-4          # pixels, |uv| ~ 160
+    ((rel_n * gr).sum() + (xyz * gx).sum() + (uv * gu).sum()).backward()
+    for t, key in ((j, "g_joints"), (L, "g_scale"), (root, "g_root")):
+        assert rel(t.grad.cpu().numpy(), g[key]) < GRAD_TOL, key
+    # the two-output form (no projection) gives the same tensors
+    rel2, xyz2 = pkg.match_mano_to_RHD(j.detach(), L.detach(), root.detach(), joint_order_switched=switched)
+    import torch
+    assert torch.equal(rel2, rel_n.detach()) and torch.equal(xyz2, xyz.detach())
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 4096, 100003])
+def test_match_mano_to_rhd_matches_fp64_oracle(pkg, cuda_device, B):
+    """Ragged batches up to beyond config 2, both joint orders, optional outputs / gradients."""
+    rs = np.random.RandomState(B)
+    # hand-like joints: every joint a few centimetres from the wrist, so ||r_12|| (either joint order) stays away from 0
+    spread = np.arange(21)[:, None] * np.array([.006, .004, .002]) + np.array([0, 0, 0.])
+    joints = (spread[None] + rs.randn(B, 21, 3) * .01).astype(np.float32)
+    L = (rs.rand(B, 1) * .05 + .02).astype(np.float32)
+    root = (rs.randn(B, 3) * .05 + np.array([0, 0, .6])).astype(np.float32)
+    K = np.tile(np.array([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1]], np.float32), (B, 1, 1))
+    gr, gx = rs.randn(B, 21, 3).astype(np.float32), rs.randn(B, 21, 3).astype(np.float32)
+    gu = (rs.randn(B, 21, 2) * 1e-3).astype(np.float32)
+    for switched in (True, False):
+        tj, tL, troot = to_dev(cuda_device, joints, L, root, grad=True)
+        tK, tgr, tgx, tgu = to_dev(cuda_device, K, gr, gx, gu)
+        rel_n, xyz, uv = pkg.mano_joints_to_rhd_uv(tj, tL, troot, tK, joint_order_switched=switched)
+        orel, oxyz = fo.match_mano_to_rhd(joints, L, root, switched)
+        ouv = fo.project_uv(oxyz, K.astype(np.float64))
+        # a hand whose ||r_12|| happens to be tiny has huge normalised coordinates: tolerances are relative,
+        # and the projection is checked where it is well conditioned (z away from 0)
+        assert (np.abs(rel_n.detach().cpu().numpy() - orel) <= 1e-6 * (1 + np.abs(orel))).all()
+        assert (np.abs(xyz.detach().cpu().numpy() - oxyz) <= 2e-7 + 1e-6 * np.abs(oxyz)).all()
+        okz = oxyz[..., 2] > 0.1
+        assert okz.mean() > 0.9
+        assert (np.abs(uv.detach().cpu().numpy() - ouv)[okz] <= 2e-4 + 1e-5 * np.abs(ouv)[okz]).all()
+        ((rel_n * tgr).sum() + (xyz * tgx).sum() + (uv * tgu).sum()).backward()
+        gx_tot = gx.astype(np.float64) + fo.project_uv_backward(oxyz, K.astype(np.float64), gu.astype(np.float64))
+        want = fo.match_mano_to_rhd_backward(joints, L, root, gr, gx_tot, switched)
+        for t, w in zip((tj, tL, troot), want):
+            assert rel(t.grad.cpu().numpy(), w) < GRAD_TOL
+        # xyz-only upstream gradient, no scale / root gradient wanted
+        tj2, = to_dev(cuda_device, joints, grad=True)
+        _, xyz2 = pkg.match_mano_to_RHD(tj2, tL.detach(), troot.detach(), joint_order_switched=switched)
+        (xyz2 * tgx).sum().backward()
+        want2 = fo.match_mano_to_rhd_backward(joints, L, root, np.zeros_like(gr), gx, switched)[0]
+        assert rel(tj2.grad.cpu().numpy(), want2) < GRAD_TOL
+
+
 # ------------------------------------------------------------------------ reductions
 @pytest.mark.parametrize("name", ["reduce_vis80.npz", "reduce_none_visible.npz"])
 def test_reductions_match_reference_golden(pkg, cuda_device, name):

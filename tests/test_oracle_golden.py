@@ -86,6 +86,20 @@ def test_projection_matches_reference_golden_including_z0_branch():
     assert rel(gx[fin], g["g_xyz"][fin]) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["match_switched.npz", "match_unswitched.npz"])
+def test_match_mano_to_rhd_oracle_matches_reference_golden(name):
+    """oracle restatement of match_mano_to_RHD (+ projection) against the unmodified reference's outputs and autograd."""
+    g = load_golden(name)
+    sw = bool(g["switched"])
+    K = g["K"].astype(np.float64)
+    reln, xyz = fo.match_mano_to_rhd(g["joints"], g["scale"], g["root"], sw)
+    uv = fo.project_uv(xyz, K)
+    assert rel(reln, g["rel"]) < 1e-6 and rel(xyz, g["xyz"]) < 1e-6 and rel(uv, g["uv"]) < 1e-6
+    gx = g["g_xyz"].astype(np.float64) + fo.project_uv_backward(xyz, K, g["g_uv"].astype(np.float64))
+    gj, gL, groot = fo.match_mano_to_rhd_backward(g["joints"], g["scale"], g["root"], g["g_rel"], gx, sw)
+    assert rel(gj, g["g_joints"]) < 1e-5 and rel(gL, g["g_scale"]) < 1e-5 and rel(groot, g["g_root"]) < 1e-5
+
+
 def test_kat_real_mano_scalars_present():
     kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
     assert kat["KAT-MANO-0"]["verts_sum"] == pytest.approx(45.808985, abs=2e-5)      # SURVEY 8c

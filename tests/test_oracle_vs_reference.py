@@ -86,3 +86,29 @@ def test_fk_live(ref):
         assert np.abs(oxyz - xyz.numpy()).max() < 2e-7
         assert np.abs(ouv - uv.numpy()).max() < 1e-3
     ref.config.joint_order_switched = True
+
+
+def test_match_mano_to_rhd_live(ref):
+    """Both copies of match_mano_to_RHD in the reference (the two MANO heads) against the oracle,
+    including the in-place permutation of the argument that the product does not reproduce."""
+    import torch
+    from network.MANO3DHandPose import MANO3DHandPose
+    from network.Resnet50MANO3DHandPose import Resnet50MANO3DHandPose
+
+    g = torch.Generator().manual_seed(5)
+    B = 9
+    j = torch.randn(B, 21, 3, generator=g) * .04
+    L = torch.rand(B, 1, generator=g) * .05 + .02
+    root = torch.randn(B, 3, generator=g) * .05 + torch.tensor([0, 0, .6])
+    try:
+        for head in (MANO3DHandPose, Resnet50MANO3DHandPose):
+            for sw in (True, False):
+                ref.config.joint_order_switched = sw
+                arg = j.clone()
+                reln, xyz = head.match_mano_to_RHD(None, arg, L, root)
+                orel, oxyz = fo.match_mano_to_rhd(j.numpy(), L.numpy(), root.numpy(), sw)
+                assert np.abs(orel - reln.numpy()).max() < 2e-6 * np.abs(orel).max()
+                assert np.abs(oxyz - xyz.numpy()).max() < 2e-7
+                assert torch.equal(arg, j) == sw                   # permuted in place when not switched
+    finally:
+        ref.config.joint_order_switched = True
