@@ -13,7 +13,9 @@ from . import assets, fitting  # noqa: F401
 from ._cabi import ManoB200Error, lib as load_library  # noqa: F401
 from .criterions import L2Loss, MPJPE, compute_regularization_loss  # noqa: F401
 from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv, mano_joints_to_rhd_uv, match_mano_to_RHD  # noqa: F401
+from .keypoint_trafo import bone_rel_trafo, bone_rel_trafo_inv, canonical_trafo, flip_right_hand  # noqa: F401
 from .mano_layer import ManoLayer  # noqa: F401
 
-__all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "match_mano_to_RHD", "mano_joints_to_rhd_uv", "MPJPE", "L2Loss",
+__all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "match_mano_to_RHD", "mano_joints_to_rhd_uv",
+           "bone_rel_trafo", "bone_rel_trafo_inv", "canonical_trafo", "flip_right_hand", "MPJPE", "L2Loss",
            "compute_regularization_loss", "ManoB200Error", "assets", "load_library"]

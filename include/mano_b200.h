@@ -172,6 +172,23 @@ MB_API int mb_joint_epilogue_backward(const float* joints, const float* index_ro
                                const float* g_xyz, const float* g_uv, int B, int swap_order,
                                float* g_joints, float* g_scale, float* g_root, mb_stream_t stream);
 
+/* ------------------------------------------------ keypoint re-parameterisations ---
+ * Batched, forward-only replacements of the transforms the reference applies per sample in its
+ * dataloaders (dataloaderRHD.py:242-250); all tensors [B][21][3] fp32.
+ * mb_bone_rel_trafo      utils/relative_trafo.py:167-216  xyz -> (length, angle_x, angle_y) per bone
+ * mb_bone_rel_trafo_inv  utils/relative_trafo.py:219-270  the inverse
+ * mb_canonical_trafo     utils/canonical_trafo.py:93-159  root at the origin, joint 12 on the y axis, joint 20 in
+ *                        the xy-plane; total_rot_mat[B][3][3] may be NULL; cond_right[B] (bytes, may be NULL)
+ *                        additionally applies flip_right_hand (:163-184) to the flagged hands
+ * mb_flip_right_hand     utils/canonical_trafo.py:163-184 for xyz[B][N][3]; cond_right is [B] or, with
+ *                        cond_per_joint != 0, [B][N] */
+MB_API int mb_bone_rel_trafo(const float* coords_xyz, int B, float* coords_rel, mb_stream_t stream);
+MB_API int mb_bone_rel_trafo_inv(const float* coords_rel, int B, float* coords_xyz, mb_stream_t stream);
+MB_API int mb_canonical_trafo(const float* coords_xyz, const unsigned char* cond_right, int B, float* coords_can,
+                       float* total_rot_mat, mb_stream_t stream);
+MB_API int mb_flip_right_hand(const float* coords_xyz, const unsigned char* cond_right, int B, int N, int cond_per_joint,
+                       float* out, mb_stream_t stream);
+
 /* ------------------------------------------------------------ reductions ---
  * Replaces MPJPE.forward (criterions/metrics.py:10-27) and L2Loss.forward
  * (criterions/loss.py:10-25): global mean over the visible joints of the batch,

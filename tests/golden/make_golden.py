@@ -123,6 +123,25 @@ def match_case(B, seed, switched):
                 g_uv=n(gu), g_joints=n(j.grad), g_scale=n(L.grad), g_root=n(root.grad), switched=np.array(switched))
 
 
+def trafo_case(B, seed):
+    """bone_rel_trafo / bone_rel_trafo_inv / canonical_trafo / flip_right_hand on hand-like keypoints
+    (root-relative, normalised: joint 0 at the origin, bones ~0.3-1 long)."""
+    from utils.canonical_trafo import canonical_trafo, flip_right_hand
+    from utils.relative_trafo import bone_rel_trafo, bone_rel_trafo_inv
+    g = torch.Generator().manual_seed(seed)
+    spread = torch.arange(21)[:, None] * torch.tensor([.09, .06, .03])
+    xyz = torch.randn(B, 21, 3, generator=g) * .5 + spread
+    xyz[:, 0] = 0
+    xyz[1] += torch.tensor([.3, -.2, .1])                    # one hand whose root is not at the origin
+    rel = bone_rel_trafo(xyz)
+    inv = bone_rel_trafo_inv(rel)
+    can, rot = canonical_trafo(xyz)
+    cond = torch.rand(B, generator=g) < .5
+    flipped = flip_right_hand(can, cond[:, None].expand(B, 21))
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(xyz=n(xyz), rel=n(rel), inv=n(inv), can=n(can), rot=n(rot), cond_right=n(cond), flipped=n(flipped))
+
+
 def main():
     model = assets.synthetic_mano()
     with tempfile.TemporaryDirectory() as td:
@@ -136,6 +155,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "reduce_vis80.npz"), **reduce_case(16, 5, .8))
     np.savez_compressed(os.path.join(HERE, "reduce_none_visible.npz"), **reduce_case(4, 6, -1.0))
     np.savez_compressed(os.path.join(HERE, "project_uv.npz"), **proj_case())
+    np.savez_compressed(os.path.join(HERE, "trafo.npz"), **trafo_case(12, 31))
     np.savez_compressed(os.path.join(HERE, "match_switched.npz"), **match_case(6, 77, True))
     np.savez_compressed(os.path.join(HERE, "match_unswitched.npz"), **match_case(6, 78, False))
 

@@ -428,6 +428,61 @@ def test_match_mano_to_rhd_matches_fp64_oracle(pkg, cuda_device, B):
         assert rel(tj2.grad.cpu().numpy(), want2) < GRAD_TOL
 
 
+# ------------------------------------------------------- keypoint re-parameterisations
+def test_keypoint_trafos_match_reference_golden(pkg, cuda_device):
+    import torch
+
+    g = load_golden("trafo.npz")
+    xyz, rel_in = to_dev(cuda_device, g["xyz"], g["rel"])
+    assert np.abs(pkg.bone_rel_trafo(xyz).cpu().numpy() - g["rel"]).max() < 5e-6
+    assert np.abs(pkg.bone_rel_trafo_inv(rel_in).cpu().numpy() - g["inv"]).max() < 5e-6
+    can, rot = pkg.canonical_trafo(xyz)
+    assert np.abs(can.cpu().numpy() - g["can"]).max() < 1e-5 and np.abs(rot.cpu().numpy() - g["rot"]).max() < 1e-5
+    cond = torch.from_numpy(g["cond_right"]).to(cuda_device)
+    can_in, = to_dev(cuda_device, g["can"])
+    assert np.array_equal(pkg.flip_right_hand(can_in, cond).cpu().numpy(), g["flipped"])
+    assert np.array_equal(pkg.flip_right_hand(can_in, cond[:, None].expand(-1, 21)).cpu().numpy(), g["flipped"])
+    assert np.array_equal(pkg.flip_right_hand(can_in[3], cond[3]).cpu().numpy(), g["flipped"][3])       # [21,3] form
+    # canonical_trafo + flip in one pass
+    can_f, _ = pkg.canonical_trafo(xyz, cond_right=cond)
+    assert torch.equal(can_f, pkg.flip_right_hand(can, cond))
+    # single-sample form of the dataloaders
+    assert np.abs(pkg.bone_rel_trafo(xyz[2]).cpu().numpy()[0] - g["rel"][2]).max() < 5e-6
+
+
+@pytest.mark.parametrize("B", [1, 33, 1000, 262147])
+def test_keypoint_trafos_match_fp64_oracle_and_round_trip(pkg, cuda_device, B):
+    """Ragged batches; size-independent properties at the large size: bone_rel_trafo_inv o bone_rel_trafo = id,
+    the canonical frame puts joint 12 on the y axis and joint 20 in the xy-plane, and keeps every distance."""
+    from oracle import trafo_oracle as tro
+
+    rs = np.random.RandomState(B % 1000)
+    xyz = (rs.randn(B, 21, 3) * .5 + np.arange(21)[:, None] * np.array([.09, .06, .03])).astype(np.float32)
+    xyz[:, 0] = 0
+    t, = to_dev(cuda_device, xyz)
+    rel_n = pkg.bone_rel_trafo(t)
+    back = pkg.bone_rel_trafo_inv(rel_n)
+    assert float((back - t).abs().max()) < 2e-5
+    can, rot = pkg.canonical_trafo(t)
+    c = can.cpu().numpy()
+    assert np.abs(c[:, 0]).max() == 0 and np.abs(c[:, 12, [0, 2]]).max() < 2e-5 and np.abs(c[:, 20, 2]).max() < 2e-5
+    assert np.abs(np.linalg.norm(c, axis=2) - np.linalg.norm(xyz, axis=2)).max() < 2e-5
+    r = rot.cpu().numpy().astype(np.float64)
+    assert np.abs(r @ np.swapaxes(r, 1, 2) - np.eye(3)).max() < 1e-5
+    idx = np.unique(np.r_[np.arange(min(B, 512)), np.arange(max(B - 64, 0), B)])
+    orel = tro.bone_rel_trafo(xyz[idx])
+    got = rel_n.cpu().numpy()[idx]
+    # angles of a bone nearly parallel to the local y axis are ill-conditioned: compare where the projected length is sane
+    d = np.abs(got - orel)
+    d[..., 1:] = np.minimum(d[..., 1:], 2 * np.pi - d[..., 1:])
+    well = orel[..., 0] * np.abs(np.cos(orel[..., 1])) > 0.05
+    assert np.abs(d[..., 0]).max() < 2e-6 and d[..., 1:][well].max() < 2e-5
+    assert np.abs(pkg.bone_rel_trafo_inv(to_dev(cuda_device, orel.astype(np.float32))[0]).cpu().numpy()
+                  - tro.bone_rel_trafo_inv(orel.astype(np.float32))).max() < 5e-6
+    ocan, orot = tro.canonical_trafo(xyz[idx])
+    assert np.abs(c[idx] - ocan).max() < 2e-5 and np.abs(r[idx] - orot).max() < 2e-5
+
+
 # ------------------------------------------------------------------------ reductions
 @pytest.mark.parametrize("name", ["reduce_vis80.npz", "reduce_none_visible.npz"])
 def test_reductions_match_reference_golden(pkg, cuda_device, name):

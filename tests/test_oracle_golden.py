@@ -100,6 +100,25 @@ def test_match_mano_to_rhd_oracle_matches_reference_golden(name):
     assert rel(gj, g["g_joints"]) < 1e-5 and rel(gL, g["g_scale"]) < 1e-5 and rel(groot, g["g_root"]) < 1e-5
 
 
+def test_keypoint_trafo_oracle_matches_reference_golden():
+    """bone_rel_trafo / inverse / canonical_trafo / flip_right_hand restatements against the unmodified reference."""
+    from oracle import trafo_oracle as tro
+
+    g = load_golden("trafo.npz")
+    assert np.abs(tro.bone_rel_trafo(g["xyz"]) - g["rel"]).max() < 5e-6
+    assert np.abs(tro.bone_rel_trafo_inv(g["rel"]) - g["inv"]).max() < 5e-6
+    can, rot = tro.canonical_trafo(g["xyz"])
+    assert np.abs(can - g["can"]).max() < 1e-5 and np.abs(rot - g["rot"]).max() < 1e-5
+    assert np.array_equal(tro.flip_right_hand(g["can"], g["cond_right"]), g["flipped"])
+    # the two bone transforms are inverses up to the reference's atan2 epsilon, for a root at the origin
+    keep = np.abs(g["xyz"][:, 0]).max(axis=1) == 0
+    assert np.abs(tro.bone_rel_trafo_inv(tro.bone_rel_trafo(g["xyz"]))[keep] - g["xyz"][keep]).max() < 1e-6
+    # canonical frame: root at 0, joint 12 on the y axis, joint 20 in the xy-plane with x > 0, a pure rotation
+    assert np.abs(can[:, 0]).max() < 1e-12 and np.abs(can[:, 12, [0, 2]]).max() < 1e-6
+    assert np.abs(can[:, 20, 2]).max() < 1e-6 and (can[:, 20, 0] > 0).all()
+    assert np.abs(rot @ np.swapaxes(rot, 1, 2) - np.eye(3)).max() < 1e-12
+
+
 def test_kat_real_mano_scalars_present():
     kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
     assert kat["KAT-MANO-0"]["verts_sum"] == pytest.approx(45.808985, abs=2e-5)      # SURVEY 8c

@@ -112,3 +112,27 @@ def test_match_mano_to_rhd_live(ref):
                 assert torch.equal(arg, j) == sw                   # permuted in place when not switched
     finally:
         ref.config.joint_order_switched = True
+
+
+def test_keypoint_trafos_live(ref):
+    """utils/relative_trafo.py and utils/canonical_trafo.py run live against the oracle restatement."""
+    import torch
+    from oracle import trafo_oracle as tro
+    from utils.canonical_trafo import canonical_trafo, flip_right_hand
+    from utils.relative_trafo import bone_rel_trafo, bone_rel_trafo_inv
+
+    g = torch.Generator().manual_seed(8)
+    B = 10
+    xyz = torch.randn(B, 21, 3, generator=g) * .5 + torch.arange(21)[:, None] * torch.tensor([.09, .06, .03])
+    xyz[:, 0] = 0
+    rel = bone_rel_trafo(xyz)
+    assert np.abs(tro.bone_rel_trafo(xyz.numpy()) - rel.numpy()).max() < 5e-6
+    assert np.abs(tro.bone_rel_trafo_inv(rel.numpy()) - bone_rel_trafo_inv(rel).numpy()).max() < 5e-6
+    can, rot = canonical_trafo(xyz)
+    ocan, orot = tro.canonical_trafo(xyz.numpy())
+    assert np.abs(ocan - can.numpy()).max() < 1e-5 and np.abs(orot - rot.numpy()).max() < 1e-5
+    cond = torch.rand(B, generator=g) < .5
+    assert np.array_equal(tro.flip_right_hand(can.numpy(), cond.numpy()),
+                          flip_right_hand(can, cond[:, None].expand(B, 21)).numpy())
+    # single-sample form of the dataloaders ([21,3] in, leading batch dimension of 1 out)
+    assert np.abs(tro.bone_rel_trafo(xyz[0].numpy())[0] - bone_rel_trafo(xyz[0]).numpy()[0]).max() < 5e-6
