@@ -15,7 +15,8 @@ from .criterions import L2Loss, MPJPE, compute_regularization_loss  # noqa: F401
 from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv, mano_joints_to_rhd_uv, match_mano_to_RHD  # noqa: F401
 from .keypoint_trafo import bone_rel_trafo, bone_rel_trafo_inv, canonical_trafo, flip_right_hand  # noqa: F401
 from .mano_layer import ManoLayer  # noqa: F401
+from .viewpoint import _get_rot_mat, viewpoint_transform  # noqa: F401
 
 __all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "match_mano_to_RHD", "mano_joints_to_rhd_uv",
-           "bone_rel_trafo", "bone_rel_trafo_inv", "canonical_trafo", "flip_right_hand", "MPJPE", "L2Loss",
+           "bone_rel_trafo", "bone_rel_trafo_inv", "canonical_trafo", "flip_right_hand", "_get_rot_mat", "viewpoint_transform", "MPJPE", "L2Loss",
            "compute_regularization_loss", "ManoB200Error", "assets", "load_library"]

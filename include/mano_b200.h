@@ -189,6 +189,23 @@ MB_API int mb_canonical_trafo(const float* coords_xyz, const unsigned char* cond
 MB_API int mb_flip_right_hand(const float* coords_xyz, const unsigned char* cond_right, int B, int N, int cond_per_joint,
                        float* out, mb_stream_t stream);
 
+/* ------------------------------------------------------------ viewpoint epilogue ---
+ * Replaces _get_rot_mat (utils/general.py:191-226) and its consumer in the canonical-pose heads
+ * (network/Hand3DPoseNet.py:41-50, network/Hand3DPosePriorNetwork.py:38-40):
+ *   theta = sqrt(ux^2 + uy^2 + uz^2 + 1e-8), n = u * (1 / theta), R = cos I + (1 - cos) n n^T + sin [n]x
+ *   rel_normed[B][21][3] = can_xyz[B][21][3] @ R            (row vectors times R)
+ *   xyz = rel_normed * index_root_bone_length + kp_coord_xyz_root,  uv = project(K, xyz)   (inference branch)
+ * ux, uy, uz are [B] (the reference's [B,1]).  Every output may be NULL (not wanted); can_xyz may be NULL when
+ * only rot_mat is wanted; uv needs xyz. */
+MB_API int mb_viewpoint_forward(const float* can_xyz, const float* ux, const float* uy, const float* uz,
+                         const float* index_root_bone_length, const float* kp_coord_xyz_root, const float* K, int B,
+                         float* rot_mat, float* rel_normed, float* xyz, float* uv, mb_stream_t stream);
+/* Gradients of (rot_mat, rel_normed) w.r.t. (can_xyz, ux, uy, uz); g_rot / g_rel may be NULL (zero);
+ * g_can may be NULL; g_ux, g_uy, g_uz are all NULL or all given. */
+MB_API int mb_viewpoint_backward(const float* can_xyz, const float* ux, const float* uy, const float* uz,
+                          const float* g_rot, const float* g_rel, int B, float* g_can, float* g_ux, float* g_uy,
+                          float* g_uz, mb_stream_t stream);
+
 /* ------------------------------------------------------------ reductions ---
  * Replaces MPJPE.forward (criterions/metrics.py:10-27) and L2Loss.forward
  * (criterions/loss.py:10-25): global mean over the visible joints of the batch,

@@ -116,3 +116,44 @@ def flip_right_hand(coords_xyz_canonical, cond_right):
     cond = np.asarray(cond_right).astype(bool)
     m = c * np.array([1, 1, -1], dtype=c.dtype)
     return np.where(cond.reshape(cond.shape + (1,) * (c.ndim - cond.ndim)), m, c)
+
+
+def get_rot_mat(ux, uy, uz, dtype=np.float64):
+    """utils/general.py:191-226 ``_get_rot_mat``: theta = sqrt(|u|^2 + 1e-8), axis = u * (1 / theta),
+    Rodrigues -> [B,3,3].  Inputs [B,1] or [B]."""
+    ux, uy, uz = (np.asarray(a, dtype=dtype).reshape(-1) for a in (ux, uy, uz))
+    th = np.sqrt(ux ** 2 + uy ** 2 + uz ** 2 + dtype(1e-8))
+    st, ct, oc = np.sin(th), np.cos(th), 1.0 - np.cos(th)
+    nx, ny, nz = ux / th, uy / th, uz / th
+    top = np.stack([ct + nx * nx * oc, nx * ny * oc - nz * st, nx * nz * oc + ny * st], 1)
+    mid = np.stack([ny * nx * oc + nz * st, ct + ny * ny * oc, ny * nz * oc - nx * st], 1)
+    bot = np.stack([nz * nx * oc - ny * st, nz * ny * oc + nx * st, ct + nz * nz * oc], 1)
+    return np.stack([top, mid, bot], 1)
+
+
+def viewpoint_forward(can_xyz, ux, uy, uz, dtype=np.float64):
+    """network/Hand3DPoseNet.py:41-43: (rot_mat, coord_xyz_rel_normed = can_xyz_kps21 @ rot_mat)."""
+    R = get_rot_mat(ux, uy, uz, dtype)
+    return R, np.asarray(can_xyz, dtype=dtype) @ R
+
+
+def viewpoint_backward(can_xyz, ux, uy, uz, g_rot, g_rel, dtype=np.float64, h=1e-6):
+    """Gradients of ``viewpoint_forward`` w.r.t. (can_xyz, ux, uy, uz): g_can analytically, the three
+    axis-angle gradients by central differences in float64 of <g_rot, R> + <g_rel, can @ R> (a check that is
+    independent of the kernel's closed form)."""
+    can = np.asarray(can_xyz, dtype=dtype)
+    g_rot = np.asarray(g_rot, dtype=dtype)
+    g_rel = np.asarray(g_rel, dtype=dtype)
+    u = [np.asarray(a, dtype=dtype).reshape(-1) for a in (ux, uy, uz)]
+    R = get_rot_mat(*u, dtype=dtype)
+    g_can = g_rel @ np.swapaxes(R, 1, 2)
+    G = g_rot + np.swapaxes(can, 1, 2) @ g_rel                  # dL/dR
+    gu = []
+    for k in range(3):
+        up = [a.copy() for a in u]
+        um = [a.copy() for a in u]
+        up[k] += h
+        um[k] -= h
+        dR = (get_rot_mat(*up, dtype=dtype) - get_rot_mat(*um, dtype=dtype)) / (2 * h)
+        gu.append(np.sum(G * dR, axis=(1, 2)))
+    return g_can, gu[0], gu[1], gu[2]

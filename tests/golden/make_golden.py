@@ -142,6 +142,30 @@ def trafo_case(B, seed):
     return dict(xyz=n(xyz), rel=n(rel), inv=n(inv), can=n(can), rot=n(rot), cond_right=n(cond), flipped=n(flipped))
 
 
+def viewpoint_case(B, seed):
+    """_get_rot_mat -> can @ R -> * scale + root -> projection (network/Hand3DPoseNet.py:41-50) with autograd."""
+    from utils.general import _get_rot_mat
+    g = torch.Generator().manual_seed(seed)
+    can = (torch.randn(B, 21, 3, generator=g) * .5).requires_grad_()
+    u = [((torch.rand(B, 1, generator=g) - .5) * 4).requires_grad_() for _ in range(3)]
+    with torch.no_grad():
+        u[0][0] = u[1][0] = u[2][0] = 0.0                     # theta = 1e-4: the epsilon branch
+    L = torch.rand(B, 1, generator=g) * .05 + .02
+    root = torch.randn(B, 3, generator=g) * .05 + torch.tensor([0, 0, .6])
+    K = torch.tensor([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1.]]).repeat(B, 1, 1)
+    R = _get_rot_mat(*u)
+    rel = torch.matmul(can, R)
+    xyz = rel * L.unsqueeze(-1) + root.unsqueeze(1)
+    uv = ref.batch_project_xyz_to_uv(xyz, K)
+    gR = torch.randn(R.shape, generator=g)
+    gr = torch.randn(rel.shape, generator=g)
+    ((R * gR).sum() + (rel * gr).sum()).backward()
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(can=n(can), ux=n(u[0]), uy=n(u[1]), uz=n(u[2]), scale=n(L), root=n(root), K=n(K), rot=n(R), rel=n(rel),
+                xyz=n(xyz), uv=n(uv), g_rot=n(gR), g_rel=n(gr), g_can=n(can.grad), g_ux=n(u[0].grad), g_uy=n(u[1].grad),
+                g_uz=n(u[2].grad))
+
+
 def main():
     model = assets.synthetic_mano()
     with tempfile.TemporaryDirectory() as td:
@@ -156,6 +180,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "reduce_none_visible.npz"), **reduce_case(4, 6, -1.0))
     np.savez_compressed(os.path.join(HERE, "project_uv.npz"), **proj_case())
     np.savez_compressed(os.path.join(HERE, "trafo.npz"), **trafo_case(12, 31))
+    np.savez_compressed(os.path.join(HERE, "viewpoint.npz"), **viewpoint_case(7, 41))
     np.savez_compressed(os.path.join(HERE, "match_switched.npz"), **match_case(6, 77, True))
     np.savez_compressed(os.path.join(HERE, "match_unswitched.npz"), **match_case(6, 78, False))
 

@@ -483,6 +483,66 @@ def test_keypoint_trafos_match_fp64_oracle_and_round_trip(pkg, cuda_device, B):
     assert np.abs(c[idx] - ocan).max() < 2e-5 and np.abs(r[idx] - orot).max() < 2e-5
 
 
+# --------------------------------------------------------------------- viewpoint epilogue
+def test_viewpoint_matches_reference_golden(pkg, cuda_device):
+    """_get_rot_mat -> can @ R (-> * scale + root -> projection) and its gradients against the reference's autograd."""
+    g = load_golden("viewpoint.npz")
+    can, ux, uy, uz = to_dev(cuda_device, g["can"], g["ux"], g["uy"], g["uz"], grad=True)
+    gR, gr = to_dev(cuda_device, g["g_rot"], g["g_rel"])
+    rel_n, R = pkg.viewpoint_transform(can, ux, uy, uz)
+    assert np.abs(R.detach().cpu().numpy() - g["rot"]).max() < 5e-7
+    assert np.abs(rel_n.detach().cpu().numpy() - g["rel"]).max() < 1e-6
+    ((R * gR).sum() + (rel_n * gr).sum()).backward()
+    assert rel(can.grad.cpu().numpy(), g["g_can"]) < GRAD_TOL
+    for t, name in ((ux, "g_ux"), (uy, "g_uy"), (uz, "g_uz")):
+        assert t.grad.shape == g[name].shape and rel(t.grad.cpu().numpy(), g[name]) < GRAD_TOL
+    # stand-alone _get_rot_mat with its own gradient
+    u2 = to_dev(cuda_device, g["ux"], g["uy"], g["uz"], grad=True)
+    R2 = pkg._get_rot_mat(*u2)
+    assert np.array_equal(R2.detach().cpu().numpy(), R.detach().cpu().numpy())
+    (R2 * gR).sum().backward()
+    from oracle import trafo_oracle as tro
+    want = tro.viewpoint_backward(np.zeros_like(g["can"]), g["ux"], g["uy"], g["uz"], g["g_rot"], np.zeros_like(g["g_rel"]))
+    for t, w in zip(u2, want[1:]):
+        assert rel(t.grad.cpu().numpy()[:, 0], w) < GRAD_TOL
+    # inference branch
+    L, root, K = to_dev(cuda_device, g["scale"], g["root"], g["K"])
+    xyz, uv = pkg.viewpoint_transform(can.detach().reshape(-1, 63), ux.detach(), uy.detach(), uz.detach(), L, root, K)
+    assert np.abs(xyz.cpu().numpy() - g["xyz"]).max() < 1e-6
+    assert np.abs(uv.cpu().numpy() - g["uv"]).max() < 5e-3
+
+
+@pytest.mark.parametrize("B", [1, 31, 129, 4096, 300007])
+def test_viewpoint_matches_fp64_oracle_and_properties(pkg, cuda_device, B):
+    """Ragged batches against the fp64 restatement (subsample at the large size) plus size-independent properties:
+    R is a rotation (up to the reference's 1e-8 epsilon), it keeps every norm, and R(-u) = R(u)^T."""
+    import torch
+    from oracle import trafo_oracle as tro
+
+    rs = np.random.RandomState(B % 977)
+    can = (rs.randn(B, 21, 3) * .5).astype(np.float32)
+    u = [((rs.rand(B, 1) - .5) * 6).astype(np.float32) for _ in range(3)]
+    gR = rs.randn(B, 3, 3).astype(np.float32)
+    gr = rs.randn(B, 21, 3).astype(np.float32)
+    tc, tx, ty, tz = to_dev(cuda_device, can, *u, grad=True)
+    tgR, tgr = to_dev(cuda_device, gR, gr)
+    rel_n, R = pkg.viewpoint_transform(tc, tx, ty, tz)
+    ((R * tgR).sum() + (rel_n * tgr).sum()).backward()
+    r = R.detach().cpu().numpy().astype(np.float64)
+    assert np.abs(r @ np.swapaxes(r, 1, 2) - np.eye(3)).max() < 2e-6
+    assert np.abs(np.linalg.norm(rel_n.detach().cpu().numpy(), axis=2) - np.linalg.norm(can, axis=2)).max() < 2e-6
+    Rm = pkg._get_rot_mat(-tx.detach(), -ty.detach(), -tz.detach())
+    assert float((Rm - R.detach().transpose(1, 2)).abs().max()) < 1e-6
+    idx = np.unique(np.r_[np.arange(min(B, 512)), np.arange(max(B - 64, 0), B)])
+    oR, orel = tro.viewpoint_forward(can[idx], u[0][idx], u[1][idx], u[2][idx])
+    assert np.abs(r[idx] - oR).max() < 5e-7 and np.abs(rel_n.detach().cpu().numpy()[idx] - orel).max() < 2e-6
+    ogc, ogx, ogy, ogz = tro.viewpoint_backward(can[idx], u[0][idx], u[1][idx], u[2][idx], gR[idx], gr[idx])
+    assert rel(tc.grad.cpu().numpy()[idx], ogc) < GRAD_TOL
+    for t, w in ((tx, ogx), (ty, ogy), (tz, ogz)):
+        assert rel(t.grad.cpu().numpy()[idx, 0], w) < GRAD_TOL
+    assert pkg.viewpoint_transform(tc.detach()[:0], tx.detach()[:0], ty.detach()[:0], tz.detach()[:0])[0].shape == (0, 21, 3)
+
+
 # ------------------------------------------------------------------------ reductions
 @pytest.mark.parametrize("name", ["reduce_vis80.npz", "reduce_none_visible.npz"])
 def test_reductions_match_reference_golden(pkg, cuda_device, name):

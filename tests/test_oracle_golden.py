@@ -119,6 +119,25 @@ def test_keypoint_trafo_oracle_matches_reference_golden():
     assert np.abs(rot @ np.swapaxes(rot, 1, 2) - np.eye(3)).max() < 1e-12
 
 
+def test_viewpoint_oracle_matches_reference_golden():
+    """_get_rot_mat and the can @ R epilogue (utils/general.py:191-226, network/Hand3DPoseNet.py:41-50) restated,
+    against the unmodified reference and its autograd."""
+    from oracle import fk_oracle as fo
+    from oracle import trafo_oracle as tro
+
+    g = load_golden("viewpoint.npz")
+    R, rel_n = tro.viewpoint_forward(g["can"], g["ux"], g["uy"], g["uz"])
+    assert np.abs(R - g["rot"]).max() < 1e-6 and np.abs(rel_n - g["rel"]).max() < 1e-6
+    assert np.abs(R[0] - np.eye(3)).max() < 1e-7                                       # u = 0: theta = 1e-4, R ~ I
+    xyz = rel_n * g["scale"][:, :, None] + g["root"][:, None, :]
+    assert np.abs(xyz - g["xyz"]).max() < 1e-6
+    assert np.abs(fo.project_uv(xyz, g["K"]) - g["uv"]).max() < 2e-3
+    gc, gx, gy, gz = tro.viewpoint_backward(g["can"], g["ux"], g["uy"], g["uz"], g["g_rot"], g["g_rel"])
+    assert np.abs(gc - g["g_can"]).max() < 5e-6
+    for got, name in ((gx, "g_ux"), (gy, "g_uy"), (gz, "g_uz")):
+        assert np.abs(got - g[name][:, 0]).max() < 1e-5 * max(1.0, np.abs(g[name]).max())
+
+
 def test_kat_real_mano_scalars_present():
     kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
     assert kat["KAT-MANO-0"]["verts_sum"] == pytest.approx(45.808985, abs=2e-5)      # SURVEY 8c

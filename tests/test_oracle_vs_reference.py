@@ -136,3 +136,19 @@ def test_keypoint_trafos_live(ref):
                           flip_right_hand(can, cond[:, None].expand(B, 21)).numpy())
     # single-sample form of the dataloaders ([21,3] in, leading batch dimension of 1 out)
     assert np.abs(tro.bone_rel_trafo(xyz[0].numpy())[0] - bone_rel_trafo(xyz[0]).numpy()[0]).max() < 5e-6
+
+
+def test_viewpoint_live(ref):
+    """utils/general.py _get_rot_mat and the matmul of network/Hand3DPoseNet.py:41-43 live against the oracle."""
+    import torch
+    from oracle import trafo_oracle as tro
+    from utils.general import _get_rot_mat
+
+    g = torch.Generator().manual_seed(9)
+    B = 16
+    can = torch.randn(B, 21, 3, generator=g)
+    u = [(torch.rand(B, 1, generator=g) - .5) * 6 for _ in range(3)]
+    R = _get_rot_mat(*u)
+    oR, orel = tro.viewpoint_forward(can.numpy(), *[t.numpy() for t in u])
+    assert np.abs(oR - R.numpy()).max() < 1e-6
+    assert np.abs(orel - torch.matmul(can, R).numpy()).max() < 2e-6
