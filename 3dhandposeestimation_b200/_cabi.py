@@ -50,10 +50,12 @@ SIGNATURES = {
     "mb_bone_rel_trafo_inv": (_i, [_p, _i, _p, _p]),
     "mb_canonical_trafo": (_i, [_p, _p, _i, _p, _p, _p]),
     "mb_flip_right_hand": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "mb_mirror_hand": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "mb_viewpoint_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "mb_viewpoint_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "mb_masked_joint_reduce": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p]),
     "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
+    "mb_hand_mask_loss": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mb_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
     "mb_launch_count": (_ll, []),
     "mb_profile_enable": (None, [_i]),

@@ -1,6 +1,6 @@
-"""MPJPE / L2Loss / MANO regulariser — drop-ins for ``criterions/metrics.py:MPJPE`` (:6-27),
-``criterions/loss.py:L2Loss`` (:6-25) and ``LossCalculation.compute_regularization_loss``
-(:113-117).  The two masked reductions run in one fused sm_100a kernel each (reduce.cu):
+"""MPJPE / L2Loss / MANO regulariser / hand-mask loss — drop-ins for ``criterions/metrics.py:MPJPE`` (:6-27),
+``criterions/loss.py:L2Loss`` (:6-25), ``LossCalculation.compute_regularization_loss`` (:113-117) and
+``LossCalculation.compute_hand_mask_loss`` (:92-111).  The two masked reductions run in one fused sm_100a kernel each (reduce.cu):
 no masked_select, no host sync on numel(); the all-invisible case returns 0 from the device.
 """
 from __future__ import annotations
@@ -84,3 +84,31 @@ def compute_regularization_loss(theta, beta):
     """criterions/loss.py:113-117: (||theta||_F + 10 ||beta||_F) / 100 over the whole batch."""
     alpha_beta = 10
     return (torch.norm(theta) + alpha_beta * torch.norm(beta)) / 100
+
+
+def compute_hand_mask_loss(pred_uv, gt_uv, hand_mask):
+    """criterions/loss.py:92-111: 1 - (mask samples at the predicted keypoints) / (mask samples at the ground-truth
+    keypoints + 1e-8); uv[B,N,2] are truncated to integers and clamped to [0, W-1], ``hand_mask`` is [B,H,W].
+    One gather-reduce kernel, no host sync; the result carries no gradient (neither does the reference's)."""
+    if not isinstance(pred_uv, torch.Tensor) or pred_uv.device.type != "cuda":
+        raise _cabi.ManoB200Error("compute_hand_mask_loss only runs on CUDA tensors (sm_100a); no CPU fallback")
+    dev = pred_uv.device
+    pred = _as_f32_cuda(pred_uv.detach(), "pred_uv", dev)
+    gt = _as_f32_cuda(gt_uv.detach(), "gt_uv", dev)
+    if pred.shape != gt.shape or pred.dim() != 3 or pred.shape[2] != 2:
+        raise RuntimeError("expected pred_uv and gt_uv of shape [B, N, 2]")
+    if hand_mask.device != dev or hand_mask.dim() != 3 or hand_mask.shape[0] != pred.shape[0]:
+        raise RuntimeError("expected hand_mask[B, H, W] on the device of pred_uv")
+    B, N = pred.shape[0], pred.shape[1]
+    H, W = hand_mask.shape[1], hand_mask.shape[2]
+    if W > H:
+        raise IndexError("hand_mask rows are clamped with the last dimension (loss.py:94-95): needs W <= H")
+    if hand_mask.dtype in (torch.uint8, torch.bool):
+        mask, kind = hand_mask.contiguous().view(torch.uint8), _cabi.VIS_U8
+    else:
+        mask, kind = hand_mask.to(torch.float32).contiguous(), _cabi.VIS_F32
+    accum = torch.empty((2,), dtype=torch.float64, device=dev)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    _cabi.check(_cabi.lib().mb_hand_mask_loss(pred.data_ptr(), gt.data_ptr(), mask.data_ptr(), kind, B, N, H, W,
+                                              accum.data_ptr(), out.data_ptr(), _cabi.stream_handle(dev)), "mb_hand_mask_loss")
+    return out

@@ -221,10 +221,10 @@ canonical_trafo_kernel(const float* __restrict__ xyz, const unsigned char* __res
 }
 
 __global__ void flip_right_hand_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ cond, long long total,
-                                       int cond_per_joint, int N, float* __restrict__ out) {
+                                       int cond_per_joint, int N, int axis, float* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long joint = i / 3;
-        const bool flip = (i - joint * 3 == 2) && cond[cond_per_joint ? joint : joint / N];
+        const bool flip = (i - joint * 3 == axis) && cond[cond_per_joint ? joint : joint / N];
         out[i] = flip ? -xyz[i] : xyz[i];
     }
 }
@@ -266,12 +266,17 @@ extern "C" int mb_canonical_trafo(const float* coords_xyz, const unsigned char* 
 
 extern "C" int mb_flip_right_hand(const float* coords_xyz, const unsigned char* cond_right, int B, int N, int cond_per_joint,
                                   float* out, mb_stream_t stream) {
-    if (B < 0 || N < 0) return MB_E_RANGE;
+    return mb_mirror_hand(coords_xyz, cond_right, B, N, cond_per_joint, 2, out, stream);
+}
+
+extern "C" int mb_mirror_hand(const float* coords_xyz, const unsigned char* cond_right, int B, int N, int cond_per_joint, int axis,
+                              float* out, mb_stream_t stream) {
+    if (B < 0 || N < 0 || axis < 0 || axis > 2) return MB_E_RANGE;
     if (B == 0 || N == 0) return 0;
     if (!coords_xyz || !cond_right || !out) return MB_E_NULL;
     const long long total = (long long)B * N * 3;
     const long long blocks = (total + 255) / 256;
     flip_right_hand_kernel<<<(unsigned)(blocks < NUM_SMS * 16 ? blocks : NUM_SMS * 16), 256, 0, (cudaStream_t)stream>>>(
-        coords_xyz, cond_right, total, cond_per_joint != 0, N, out);
+        coords_xyz, cond_right, total, cond_per_joint != 0, N, axis, out);
     return cuda_rc();
 }

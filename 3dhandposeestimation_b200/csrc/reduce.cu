@@ -68,6 +68,49 @@ masked_l2_backward_kernel(const float* __restrict__ pred, const float* __restric
     }
 }
 
+// LossCalculation.compute_hand_mask_loss (criterions/loss.py:92-111): uv -> int64 (truncation), clamp to
+// [0, W-1] on both axes (the reference clamps rows with the last dimension too), sample hand_mask[b][v][u] at the
+// predicted and the ground-truth keypoints; accum = {sum of predicted samples, sum of ground-truth samples}.
+__device__ __forceinline__ double mask_at(const void* mask, int kind, long long b, long long HW, int W, float u, float v) {
+    long long x = __float2ll_rz(u), y = __float2ll_rz(v);
+    x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+    y = y < 0 ? 0 : (y > W - 1 ? W - 1 : y);
+    const long long i = b * HW + y * W + x;
+    return kind == MB_VIS_U8 ? (double)reinterpret_cast<const uint8_t*>(mask)[i] : (double)reinterpret_cast<const float*>(mask)[i];
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+hand_mask_kernel(const float2* __restrict__ pred_uv, const float2* __restrict__ gt_uv, const void* __restrict__ mask, int mask_kind,
+                 long long n, int N, int H, int W, double* __restrict__ accum) {
+    double sp = 0.0, sg = 0.0;
+    const long long HW = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / N;
+        const float2 p = pred_uv[i], g = gt_uv[i];
+        sp += mask_at(mask, mask_kind, b, HW, W, p.x, p.y);
+        sg += mask_at(mask, mask_kind, b, HW, W, g.x, g.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sp += __shfl_xor_sync(0xffffffffu, sp, o);
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    }
+    __shared__ double s_p[RED_THREADS / 32], s_g[RED_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_p[warp] = sp; s_g[warp] = sg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < RED_THREADS / 32; ++w) { a += s_p[w]; c += s_g[w]; }
+        if (a != 0.0) atomicAdd(&accum[0], a);
+        if (c != 0.0) atomicAdd(&accum[1], c);
+    }
+}
+
+__global__ void hand_mask_finalize_kernel(const double* __restrict__ accum, float* __restrict__ out) {
+    out[0] = 1.f - (float)accum[0] / ((float)accum[1] + 1e-8f);      // fp32 like the reference (epsilon :108)
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad):
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void __launch_bounds__(RED_THREADS)
@@ -120,6 +163,26 @@ extern "C" int mb_masked_l2_backward(const float* pred, const float* gt, const v
     if (!pred || !gt || !vis || !accum || !g_out || !g_pred) return MB_E_NULL;
     masked_l2_backward_kernel<<<red_grid(n_joints), RED_THREADS, 0, (cudaStream_t)stream>>>(pred, gt, vis, vis_kind, n_joints,
                                                                                               accum, g_out, g_pred);
+    return cuda_rc();
+}
+
+extern "C" int mb_hand_mask_loss(const float* pred_uv, const float* gt_uv, const void* hand_mask, int mask_kind, int B, int N,
+                                 int H, int W, double* accum, float* out, mb_stream_t stream) {
+    if (B < 0 || N < 0 || H < 1 || W < 1 || W > H || (mask_kind != MB_VIS_F32 && mask_kind != MB_VIS_U8)) return MB_E_RANGE;
+    if (!accum || !out) return MB_E_NULL;
+    const long long n = (long long)B * N;
+    if (n > 0 && (!pred_uv || !gt_uv || !hand_mask)) return MB_E_NULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(accum, 0, 2 * sizeof(double), s);
+    if (e != cudaSuccess) return (int)e;
+    if (n > 0) {
+        hand_mask_kernel<<<red_grid(n), RED_THREADS, 0, s>>>(reinterpret_cast<const float2*>(pred_uv),
+                                                             reinterpret_cast<const float2*>(gt_uv), hand_mask, mask_kind, n, N, H,
+                                                             W, accum);
+        int rc = cuda_rc();
+        if (rc) return rc;
+    }
+    hand_mask_finalize_kernel<<<1, 1, 0, s>>>(accum, out);
     return cuda_rc();
 }
 

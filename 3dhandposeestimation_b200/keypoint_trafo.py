@@ -63,6 +63,17 @@ def canonical_trafo(coords_xyz, cond_right=None):
 def flip_right_hand(coords_xyz_canonical, cond_right):
     """utils/canonical_trafo.py:163-184: z -> -z where ``cond_right``; [N,3] or [B,N,3] coordinates,
     ``cond_right`` broadcastable to [B,N] (the reference broadcasts ``cond_right.unsqueeze(-1)``)."""
+    return _mirror(coords_xyz_canonical, cond_right, 2)
+
+
+def mirror_left_hand(keypoint_xyz21, hand_side):
+    """dataloader/RHD/dataloaderRHD.py:224-225, batched: x -> -x for the hands with ``hand_side == 0`` (left), so
+    every sample reaches the right-hand MANO / FK layers as a right hand.  ``hand_side``: one integer per hand."""
+    side = torch.as_tensor(hand_side, device=keypoint_xyz21.device if isinstance(keypoint_xyz21, torch.Tensor) else None)
+    return _mirror(keypoint_xyz21, side == 0, 0)
+
+
+def _mirror(coords_xyz_canonical, cond_right, axis):
     if not isinstance(coords_xyz_canonical, torch.Tensor) or coords_xyz_canonical.device.type != "cuda":
         raise _cabi.ManoB200Error("coords_xyz_canonical must be a CUDA tensor (sm_100a); there is no CPU fallback")
     dev = coords_xyz_canonical.device
@@ -80,6 +91,6 @@ def flip_right_hand(coords_xyz_canonical, cond_right):
         c = c.unsqueeze(-1) if c.shape[0] == B else c.unsqueeze(0)
     cond = _cond_bytes(c, (B, N), dev)
     out = torch.empty_like(x)
-    _cabi.check(_cabi.lib().mb_flip_right_hand(x.data_ptr(), cond.data_ptr(), B, N, 1, out.data_ptr(), _cabi.stream_handle(dev)),
-                "mb_flip_right_hand")
+    _cabi.check(_cabi.lib().mb_mirror_hand(x.data_ptr(), cond.data_ptr(), B, N, 1, axis, out.data_ptr(), _cabi.stream_handle(dev)),
+                "mb_mirror_hand")
     return out.squeeze(0) if expanded else out

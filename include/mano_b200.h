@@ -181,13 +181,17 @@ MB_API int mb_joint_epilogue_backward(const float* joints, const float* index_ro
  *                        the xy-plane; total_rot_mat[B][3][3] may be NULL; cond_right[B] (bytes, may be NULL)
  *                        additionally applies flip_right_hand (:163-184) to the flagged hands
  * mb_flip_right_hand     utils/canonical_trafo.py:163-184 for xyz[B][N][3]; cond_right is [B] or, with
- *                        cond_per_joint != 0, [B][N] */
+ *                        cond_per_joint != 0, [B][N]
+ * mb_mirror_hand         the same sign flip on a chosen axis (0 = x, 1 = y, 2 = z): axis 0 with cond = "is a left
+ *                        hand" is the left -> right mirroring of dataloader/RHD/dataloaderRHD.py:224-225 */
 MB_API int mb_bone_rel_trafo(const float* coords_xyz, int B, float* coords_rel, mb_stream_t stream);
 MB_API int mb_bone_rel_trafo_inv(const float* coords_rel, int B, float* coords_xyz, mb_stream_t stream);
 MB_API int mb_canonical_trafo(const float* coords_xyz, const unsigned char* cond_right, int B, float* coords_can,
                        float* total_rot_mat, mb_stream_t stream);
 MB_API int mb_flip_right_hand(const float* coords_xyz, const unsigned char* cond_right, int B, int N, int cond_per_joint,
                        float* out, mb_stream_t stream);
+MB_API int mb_mirror_hand(const float* coords_xyz, const unsigned char* cond, int B, int N, int cond_per_joint, int axis,
+                   float* out, mb_stream_t stream);
 
 /* ------------------------------------------------------------ viewpoint epilogue ---
  * Replaces _get_rot_mat (utils/general.py:191-226) and its consumer in the canonical-pose heads
@@ -218,6 +222,14 @@ MB_API int mb_masked_joint_reduce(const float* pred, const float* gt, const void
 MB_API int mb_masked_l2_backward(const float* pred, const float* gt, const void* vis, int vis_kind,
                           long long n_joints, const double* accum, const float* g_out,
                           float* g_pred, mb_stream_t stream);
+
+/* Replaces LossCalculation.compute_hand_mask_loss (criterions/loss.py:92-111):
+ *   uv -> int64 by truncation, clamped to [0, W-1] on both axes (as the reference does), samples of
+ *   hand_mask[B][H][W] (fp32 or u8, MB_VIS_*) at pred_uv[B][N][2] and gt_uv[B][N][2] (u = column, v = row);
+ *   out = 1 - sum(pred samples) / (sum(gt samples) + 1e-8).  No gradient exists (integer indexing).
+ *   Needs W <= H (the reference would raise an IndexError for a clamped row >= H); accum: device double[2]. */
+MB_API int mb_hand_mask_loss(const float* pred_uv, const float* gt_uv, const void* hand_mask, int mask_kind, int B, int N,
+                      int H, int W, double* accum, float* out, mb_stream_t stream);
 
 /* ----------------------------------------------------------- fitting loop ---
  * One Adam update on a flat fp32 parameter array (torch.optim.Adam semantics, no

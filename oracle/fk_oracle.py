@@ -193,6 +193,18 @@ def l2loss_backward(pre_xyz, gt_xyz, keypoint_vis, dtype=np.float64):
     return 2.0 * diff * m[..., None] / n
 
 
+def hand_mask_loss(pred_uv, gt_uv, hand_mask):
+    """criterions/loss.py:92-111: uv truncated to int64 and clamped to [0, W-1] on both axes, mask sampled at
+    [b, v, u]; 1 - sum(pred samples) / (sum(gt samples) + 1e-8), the last step in fp32 like the reference."""
+    mask = np.asarray(hand_mask)
+    hi = mask.shape[-1] - 1
+    b = np.arange(mask.shape[0]).reshape(-1, 1)
+    def samples(uv):
+        q = np.clip(np.trunc(np.asarray(uv, np.float64)).astype(np.int64), 0, hi)
+        return mask[b, q[..., 1], q[..., 0]].astype(np.float64).sum()
+    return np.float32(1.0) - np.float32(samples(pred_uv)) / (np.float32(samples(gt_uv)) + np.float32(1e-8))
+
+
 def regularizer(theta, beta, dtype=np.float64):
     """criterions/loss.py:113-117: (||theta||_F + 10 ||beta||_F) / 100 over the batch."""
     return dtype((np.linalg.norm(np.asarray(theta, dtype)) + 10.0 * np.linalg.norm(np.asarray(beta, dtype))) / 100.0)

@@ -166,6 +166,25 @@ def viewpoint_case(B, seed):
                 g_uz=n(u[2].grad))
 
 
+def hand_mask_case(B, seed, empty_gt=False):
+    """LossCalculation.compute_hand_mask_loss (criterions/loss.py:92-111) on a blob mask; some uv outside the image."""
+    from criterions.loss import LossCalculation
+    g = torch.Generator().manual_seed(seed)
+    H = W = 64
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    c = torch.rand(B, 2, generator=g) * 24 + 20
+    mask = (((xx[None] - c[:, 0, None, None]) ** 2 + (yy[None] - c[:, 1, None, None]) ** 2) < 15 ** 2).float()
+    gt_uv = c[:, None, :] + torch.randn(B, 21, 2, generator=g) * 9
+    pred_uv = gt_uv + torch.randn(B, 21, 2, generator=g) * 8
+    pred_uv[0, 0] = torch.tensor([-7.5, 300.25])               # clamped on both sides
+    pred_uv[1, 3] = torch.tensor([-0.9, 63.999])               # truncation toward zero
+    if empty_gt:
+        mask[:] = 0
+    loss = LossCalculation("cpu", comp_hand_mask_loss=True).compute_hand_mask_loss(pred_uv, gt_uv, mask)
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(pred_uv=n(pred_uv), gt_uv=n(gt_uv), hand_mask=n(mask), loss=np.float32(loss.item()))
+
+
 def main():
     model = assets.synthetic_mano()
     with tempfile.TemporaryDirectory() as td:
@@ -181,6 +200,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "project_uv.npz"), **proj_case())
     np.savez_compressed(os.path.join(HERE, "trafo.npz"), **trafo_case(12, 31))
     np.savez_compressed(os.path.join(HERE, "viewpoint.npz"), **viewpoint_case(7, 41))
+    np.savez_compressed(os.path.join(HERE, "hand_mask.npz"), **hand_mask_case(5, 51))
+    np.savez_compressed(os.path.join(HERE, "hand_mask_empty.npz"), **hand_mask_case(3, 52, True))
     np.savez_compressed(os.path.join(HERE, "match_switched.npz"), **match_case(6, 77, True))
     np.savez_compressed(os.path.join(HERE, "match_unswitched.npz"), **match_case(6, 78, False))
 

@@ -443,6 +443,11 @@ def test_keypoint_trafos_match_reference_golden(pkg, cuda_device):
     assert np.array_equal(pkg.flip_right_hand(can_in, cond).cpu().numpy(), g["flipped"])
     assert np.array_equal(pkg.flip_right_hand(can_in, cond[:, None].expand(-1, 21)).cpu().numpy(), g["flipped"])
     assert np.array_equal(pkg.flip_right_hand(can_in[3], cond[3]).cpu().numpy(), g["flipped"][3])       # [21,3] form
+    # left -> right mirroring of the RHD dataloader (dataloaderRHD.py:224-225): x -> -x where hand_side == 0
+    side = torch.tensor([0, 1] * 6, device=cuda_device)
+    want = torch.where((side == 0)[:, None, None], torch.cat([-xyz[..., :1], xyz[..., 1:]], dim=-1), xyz)
+    assert torch.equal(pkg.mirror_left_hand(xyz, side), want)
+    assert torch.equal(pkg.mirror_left_hand(xyz[0], side[0]), want[0])
     # canonical_trafo + flip in one pass
     can_f, _ = pkg.canonical_trafo(xyz, cond_right=cond)
     assert torch.equal(can_f, pkg.flip_right_hand(can, cond))
@@ -561,6 +566,32 @@ def test_reductions_match_reference_golden(pkg, cuda_device, name):
     m2 = pkg.MPJPE()(pre.detach(), gt, vis.bool())
     assert float(m2) == pytest.approx(float(m), rel=1e-6, abs=1e-12)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("name", ["hand_mask.npz", "hand_mask_empty.npz"])
+def test_hand_mask_loss_matches_reference_golden(pkg, cuda_device, name):
+    import torch
+
+    g = load_golden(name)
+    p, q, m = to_dev(cuda_device, g["pred_uv"], g["gt_uv"], g["hand_mask"])
+    assert float(pkg.compute_hand_mask_loss(p, q, m)) == float(g["loss"])
+    assert float(pkg.compute_hand_mask_loss(p, q, m.to(torch.uint8))) == float(g["loss"])       # byte masks too
+    assert float(pkg.compute_hand_mask_loss(p, q, m > 0)) == float(g["loss"])
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 8), (37, 40, 32), (4096, 64, 64)])
+def test_hand_mask_loss_matches_oracle(pkg, cuda_device, B, H, W):
+    """Bit-exact (integer gather + exactly representable sums) against the oracle, uv far outside the image,
+    non-finite uv (NaN -> 0 like the reference's float -> int64 cast of this platform is not relied on: excluded)."""
+    rs = np.random.RandomState(B)
+    mask = (rs.rand(B, H, W) < .4).astype(np.float32)
+    gt = (rs.rand(B, 21, 2) * (W + 20) - 10).astype(np.float32)
+    pred = (gt + rs.randn(B, 21, 2) * 6).astype(np.float32)
+    pred[0, 0] = [-1e9, 1e9]
+    p, q, m = to_dev(cuda_device, pred, gt, mask)
+    assert float(pkg.compute_hand_mask_loss(p, q, m)) == float(fo.hand_mask_loss(pred, gt, mask))
+    with pytest.raises(IndexError):
+        pkg.compute_hand_mask_loss(p, q, m[:, : W // 2, :])
 
 
 def test_adam_step_matches_torch(pkg, cuda_device):

@@ -138,6 +138,15 @@ def test_viewpoint_oracle_matches_reference_golden():
         assert np.abs(got - g[name][:, 0]).max() < 1e-5 * max(1.0, np.abs(g[name]).max())
 
 
+@pytest.mark.parametrize("name", ["hand_mask.npz", "hand_mask_empty.npz"])
+def test_hand_mask_loss_oracle_matches_reference_golden(name):
+    """compute_hand_mask_loss (criterions/loss.py:92-111) restated: truncation, the clamp to W-1, the epsilon."""
+    from oracle import fk_oracle as fo
+
+    g = load_golden(name)
+    assert fo.hand_mask_loss(g["pred_uv"], g["gt_uv"], g["hand_mask"]) == g["loss"]
+
+
 def test_kat_real_mano_scalars_present():
     kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
     assert kat["KAT-MANO-0"]["verts_sum"] == pytest.approx(45.808985, abs=2e-5)      # SURVEY 8c
