@@ -225,6 +225,168 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
 }
 
 
+// ----------------------------------------------------------------- large batches: hand tile resident, basis streamed
+// ncu on the kernel above at 2^20 hands (profiles/r1): tensor pipe 27 %, DRAM 33 %, and the time does not change
+// when two of the three products are dropped — its feature ring holds exactly ONE hand tile, so every tile waits
+// a full bulk-copy latency (the next tile's chunk can only be requested when this tile's MMAs on that slot retire).
+// Here the roles are swapped: the CTA keeps the 80 KB feature rows of its hand tile resident for all 15 n-tiles,
+// and the basis (1.5 MB, always an L2 hit, the same stream for every CTA and every hand tile) flows through a
+// BS-stage ring of 20 KB K-chunks that never drains at a tile boundary: the producer runs up to BS chunks
+// (> one n-tile) ahead.  Feature rows are read once from HBM instead of 15 times from L2.  A second producer
+// thread requests the next hand tile's chunk c as soon as the last n-tile's MMAs on it retire.
+constexpr int BS = 6;                                              // basis ring stages (20 KB each)
+struct TcSharedM {
+    alignas(128) unsigned char a[TC_K_CHUNKS][TC_A_STAGE_BYTES];    // resident feature rows of the hand tile (hi+lo)
+    alignas(128) unsigned char b[BS][2 * TC_B_BLOCK_BYTES];         // basis ring: (n-tile, K-chunk) hi+lo
+    alignas(16) float tmpl[SK_TMPL_PAD];                            // v_template, block order
+    alignas(8) unsigned long long a_full[TC_K_CHUNKS], a_empty[TC_K_CHUNKS];
+    unsigned long long b_full[BS], b_empty[BS];
+    unsigned long long acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
+    uint32_t tmem_base;
+    int abort_flag;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+blend_tc_forward_mres_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ basis_tc,
+                             const float* __restrict__ tmpl, const unsigned char* __restrict__ featp,
+                             float* __restrict__ v_posed_t, int B, int m_tiles, int products) {
+    extern __shared__ unsigned char smem_raw[];
+    TcSharedM& S = *reinterpret_cast<TcSharedM*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const float out_scale = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < TC_K_CHUNKS; ++c) { mbar_init(smem_u32(&S.a_full[c]), 1); mbar_init(smem_u32(&S.a_empty[c]), 1); }
+        for (int st = 0; st < BS; ++st) { mbar_init(smem_u32(&S.b_full[st]), 1); mbar_init(smem_u32(&S.b_empty[st]), 1); }
+        for (int st = 0; st < ACC_STAGES; ++st) { mbar_init(smem_u32(&S.acc_full[st]), 1); mbar_init(smem_u32(&S.acc_empty[st]), EPI_WARPS); }
+        S.abort_flag = 0;
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < SK_TMPL_PAD; i += TC_THREADS) S.tmpl[i] = tmpl[i];
+    if (warp == 2) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    volatile int* abort_flag = &S.abort_flag;
+
+    if (warp == 0 && lane == 0) {
+        // ===== basis producer: the same 75-chunk stream for every hand tile, kept in L2 =====
+        const uint64_t keep = l2_policy_evict_last();
+        uint32_t stage = 0, phase = 0;
+        bool ok = true;
+        for (int m_tile = blockIdx.x; m_tile < m_tiles && ok; m_tile += gridDim.x) {
+            for (int i = 0; i < TC_N_TILES * TC_K_CHUNKS; ++i) {
+                if (!(ok = mbar_wait(smem_u32(&S.b_empty[stage]), phase ^ 1, abort_flag))) break;
+                mbar_expect_tx(smem_u32(&S.b_full[stage]), 2 * TC_B_BLOCK_BYTES);
+                bulk_g2s_hint(smem_u32(S.b[stage]), basis_tc + (size_t)i * 2 * TC_B_BLOCK_BYTES, 2 * TC_B_BLOCK_BYTES,
+                              smem_u32(&S.b_full[stage]), keep);
+                if (++stage == BS) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 3 && lane == 0) {
+        // ===== feature producer: one hand tile, read once =====
+        const uint64_t once = l2_policy_evict_first();
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int m_tile = blockIdx.x; m_tile < m_tiles && ok; m_tile += gridDim.x) {
+            const unsigned char* fsrc = featp + (size_t)m_tile * TC_A_TILE_BYTES;
+            for (int c = 0; c < TC_K_CHUNKS; ++c) {
+                if (!(ok = mbar_wait(smem_u32(&S.a_empty[c]), phase ^ 1, abort_flag))) break;
+                mbar_expect_tx(smem_u32(&S.a_full[c]), TC_A_STAGE_BYTES);
+                bulk_g2s_hint(smem_u32(S.a[c]), fsrc + (size_t)c * TC_A_STAGE_BYTES, TC_A_STAGE_BYTES, smem_u32(&S.a_full[c]), once);
+            }
+            phase ^= 1;
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+        bool ok = true;
+        const uint64_t a_base = umma_desc(smem_u32(S.a[0]), TC_LBO, TC_SBO);
+        const uint64_t b_base = umma_desc(smem_u32(S.b[0]), TC_LBO, TC_SBO);
+        for (int m_tile = blockIdx.x; m_tile < m_tiles && ok; m_tile += gridDim.x) {
+            for (int n_tile = 0; n_tile < TC_N_TILES && ok; ++n_tile) {
+                if (!(ok = mbar_wait(smem_u32(&S.acc_empty[acc]), acc_phase ^ 1, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + acc * TC_N;
+#pragma unroll
+                for (int c = 0; c < TC_K_CHUNKS; ++c) {
+                    if (n_tile == 0 && !(ok = mbar_wait(smem_u32(&S.a_full[c]), a_phase, abort_flag))) break;
+                    if (!(ok = mbar_wait(smem_u32(&S.b_full[stage]), phase, abort_flag))) break;
+                    tc_fence_after();
+                    const uint64_t b_st = b_base + (uint64_t)((stage * 2 * TC_B_BLOCK_BYTES) >> 4);
+#pragma unroll
+                    for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
+                        const uint64_t a_hi = a_base + (uint64_t)((c * TC_A_STAGE_BYTES + j * 2 * (int)TC_LBO) >> 4);
+                        const uint64_t a_lo = a_hi + (uint64_t)(TC_A_BLOCK_BYTES >> 4);
+                        const uint64_t b_hi = b_st + (uint64_t)((j * 2 * (int)TC_LBO) >> 4);
+                        const uint64_t b_lo = b_hi + (uint64_t)(TC_B_BLOCK_BYTES >> 4);
+                        umma_f16(d_tmem, a_hi, b_hi, IDESC, (c | j) ? 1u : 0u);
+                        if (products == 3) {
+                            umma_f16(d_tmem, a_lo, b_hi, IDESC, 1);
+                            umma_f16(d_tmem, a_hi, b_lo, IDESC, 1);
+                        }
+                    }
+                    tc_commit(smem_u32(&S.b_empty[stage]));            // frees the basis slot when these MMAs retire
+                    if (n_tile == TC_N_TILES - 1) tc_commit(smem_u32(&S.a_empty[c]));   // ... and the feature chunk after its last use
+                    if (++stage == BS) { stage = 0; phase ^= 1; }
+                }
+                if (!ok) break;
+                tc_commit(smem_u32(&S.acc_full[acc]));
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+            a_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (as above; v_template from shared memory, one broadcast read per column) =====
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int j_begin = half == 0 ? 0 : 3, j_end = half == 0 ? 3 : TC_N / 32;
+        uint32_t acc = 0, acc_phase = 0;
+        bool ok = true;
+        for (int m_tile = blockIdx.x; m_tile < m_tiles && ok; m_tile += gridDim.x) {
+            const long long group = (long long)m_tile * (TC_M / 32) + q;
+            const bool live = group * 32 < B;
+            for (int n_tile = 0; n_tile < TC_N_TILES; ++n_tile) {
+                ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&S.acc_full[acc]), acc_phase, abort_flag));
+                if (!ok) break;
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = j_begin; j < j_end; ++j) {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * TC_N + j * 32, v);
+                    if (j == j_end - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty[acc]));
+                    }
+                    const int col0 = n_tile * TC_N + j * 32;
+                    if (live) {
+                        float* dst = v_posed_t + ((size_t)group * SK_NCOORD + col0) * 32 + lane;
+                        const float4* tp = reinterpret_cast<const float4*>(S.tmpl + col0);
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 t4 = tp[c4];
+                            const int c = c4 * 4;
+                            if (col0 + c < SK_NCOORD) {               // SK_NCOORD is a multiple of 4
+                                __stcs(dst + (c + 0) * 32, fmaf(v[c + 0], out_scale, t4.x));
+                                __stcs(dst + (c + 1) * 32, fmaf(v[c + 1], out_scale, t4.y));
+                                __stcs(dst + (c + 2) * 32, fmaf(v[c + 2], out_scale, t4.z));
+                                __stcs(dst + (c + 3) * 32, fmaf(v[c + 3], out_scale, t4.w));
+                            }
+                        }
+                    }
+                }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, TMEM_COLS);
+    if (threadIdx.x == 0 && S.abort_flag) __trap();
+}
+
+
 // ================================================================= backward contraction
 //   dfeat[h][n] = sum_k dv_posed[h][k] * basis[n][k],  n < 145 (+ pad to 160), K = 2336
 // M = 2 x 128 hands per CTA pass (two accumulators of 160 TMEM columns), both operands stream
@@ -473,6 +635,19 @@ int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float*
     const long long total = (long long)TC_N_TILES * m_tiles;
     const int grid = (int)(total < NUM_SMS ? total : NUM_SMS);      // >= 15: every n-tile has at least one CTA
     const float* tmpl = blob_ptr<float>(blob, L.sk_tmpl);
+    if (m_tiles >= TC_MRES_MIN_TILES) {             // large batch: hand tile resident, basis streamed (one CTA per hand tile)
+        static bool attr2_done = false;
+        const size_t smem2 = sizeof(TcSharedM) + 128;
+        if (!attr2_done) {
+            cudaError_t e = cudaFuncSetAttribute(blend_tc_forward_mres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return (int)e;
+            attr2_done = true;
+        }
+        blend_tc_forward_mres_kernel<<<m_tiles < NUM_SMS ? m_tiles : NUM_SMS, TC_THREADS, smem2, s>>>(
+            reinterpret_cast<const TcBlobHeader*>(tc), tc + align256(sizeof(TcBlobHeader)), tmpl, featp, v_posed_t, B, m_tiles,
+            mode == MB_MODE_F16X3 ? 3 : 1);
+        return cuda_rc();
+    }
     blend_tc_forward_kernel<<<grid, TC_THREADS, smem, s>>>(reinterpret_cast<const TcBlobHeader*>(tc),
                                                            tc + align256(sizeof(TcBlobHeader)), tmpl, featp, v_posed_t, B, m_tiles,
                                                            mode == MB_MODE_F16X3 ? 3 : 1);

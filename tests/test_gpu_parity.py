@@ -85,17 +85,19 @@ def test_mano_matches_reference_golden(pkg, synth_model, cuda_device, name, nc, 
 
 @pytest.mark.parametrize("mode", ACCURATE_MODES)
 @pytest.mark.parametrize("B,nc", [(1, 45), (2, 45), (7, 10), (129, 45), (1000, 45), (1344, 45), (2720, 10), (4096, 10), (4133, 45), (5000, 6), (8192, 10), (9001, 45),
-                                  (20001, 45)])
+                                  (20001, 45), (40001, 45), (77777, 10)])
 def test_mano_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc, mode):
     """Ragged sizes (partial hand groups, partial tcgen05 tiles) up to BASELINE config 2 (B=4096,
     nc=10, the Resnet50MANO3DHandPose head workload).  B >= 8192 in the tensor-core modes runs the
-    one-thread-per-hand pose kernels, below that the one-warp-per-hand kernels."""
+    one-thread-per-hand pose kernels, below that the one-warp-per-hand kernels; from 37 888 hands (296 hand
+    tiles) the blend forward is the hand-tile-resident kernel (several hand tiles per CTA at 77 777)."""
     rot, pose, beta = mano_inputs(B, nc, seed=B + nc)
     layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc, mode=mode)
     trot, tpose, tbeta = to_dev(cuda_device, rot, pose, beta, grad=True)
     verts, joints = layer(trot, tpose, tbeta)
     nchk = min(B, 256)                                         # oracle on a bounded prefix + suffix
-    idx = np.unique(np.r_[np.arange(nchk), np.arange(B - min(B, 64), B)])
+    idx = np.unique(np.r_[np.arange(nchk), np.arange(B - min(B, 64), B),
+                          np.random.RandomState(B).choice(B, min(B, 192), replace=False)])     # + a sample of every region
     ov, oj = mo.mano_forward(synth_model, rot[idx], pose[idx], beta[idx])
     assert np.abs(verts.detach().cpu().numpy()[idx] - ov).max() < POS_TOL_F64
     assert np.abs(joints.detach().cpu().numpy()[idx] - oj).max() < POS_TOL_F64
