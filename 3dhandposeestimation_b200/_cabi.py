@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mano_b200.h")
 MODE_FP32, MODE_F16X3, MODE_F16 = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "f16x3": MODE_F16X3, "f16": MODE_F16}
 BWD_WORKSPACE_VALID = 1
+MODEL_CHAINS_5X3 = 0x100
 REDUCE_MPJPE_MM, REDUCE_L2 = 0, 1
 VIS_F32, VIS_U8 = 0, 1
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "mb_masked_joint_reduce": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p]),
     "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
     "mb_hand_mask_loss": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "mb_mano_fit_step": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _f, _f, _f, _f, _i, _i, _p]),
     "mb_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
     "mb_launch_count": (_ll, []),
     "mb_profile_enable": (None, [_i]),

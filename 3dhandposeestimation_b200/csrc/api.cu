@@ -269,6 +269,20 @@ extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const
                                verts, joints, s);
 }
 
+extern "C" int mb_mano_fit_step(const void* blob, int nc, float* params, float* exp_avg, float* exp_avg_sq,
+                                const float* target_joints, const float* keypoint_vis, int B, int mode, const double* globals,
+                                double* partials, float lr, float beta1, float beta2, float eps, int step, int regularize,
+                                mb_stream_t stream) {
+    if (B < 0 || nc < 1 || nc > NAA || step < 1) return MB_E_RANGE;
+    if (!(mode & MB_MODEL_CHAINS_5X3)) return MB_E_MODEL;       // one-thread-per-hand kernel: MANO's tree only
+    if (!partials) return MB_E_NULL;
+    if (B == 0) return (int)cudaMemsetAsync(partials, 0, 3 * sizeof(double), (cudaStream_t)stream);
+    if (!blob || !params || !exp_avg || !exp_avg_sq || !target_joints || !keypoint_vis || !globals) return MB_E_NULL;
+    StageTimer t(ST_JOINTS_BWD, (cudaStream_t)stream);
+    return launch_fit_step_lh(blob, nc, params, exp_avg, exp_avg_sq, target_joints, keypoint_vis, B, globals, partials, lr, beta1,
+                              beta2, eps, step, regularize, (cudaStream_t)stream);
+}
+
 extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                 const float* g_verts, const float* g_joints, int B, int mode, int flags,
                                 float* g_rot, float* g_coeffs, float* g_betas, void* workspace, size_t workspace_bytes,

@@ -234,6 +234,7 @@ blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned cha
 // BS-stage ring of 20 KB K-chunks that never drains at a tile boundary: the producer runs up to BS chunks
 // (> one n-tile) ahead.  Feature rows are read once from HBM instead of 15 times from L2.  A second producer
 // thread requests the next hand tile's chunk c as soon as the last n-tile's MMAs on it retire.
+constexpr int MRES_ACC = 3;                                        // accumulator stages (3 x 160 TMEM columns)
 constexpr int BS = 6;                                              // basis ring stages (20 KB each)
 struct TcSharedM {
     alignas(128) unsigned char a[TC_K_CHUNKS][TC_A_STAGE_BYTES];    // resident feature rows of the hand tile (hi+lo)
@@ -241,7 +242,7 @@ struct TcSharedM {
     alignas(16) float tmpl[SK_TMPL_PAD];                            // v_template, block order
     alignas(8) unsigned long long a_full[TC_K_CHUNKS], a_empty[TC_K_CHUNKS];
     unsigned long long b_full[BS], b_empty[BS];
-    unsigned long long acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
+    unsigned long long acc_full[MRES_ACC], acc_empty[MRES_ACC];
     uint32_t tmem_base;
     int abort_flag;
 };
@@ -258,7 +259,7 @@ blend_tc_forward_mres_kernel(const TcBlobHeader* __restrict__ hdr, const unsigne
     if (threadIdx.x == 0) {
         for (int c = 0; c < TC_K_CHUNKS; ++c) { mbar_init(smem_u32(&S.a_full[c]), 1); mbar_init(smem_u32(&S.a_empty[c]), 1); }
         for (int st = 0; st < BS; ++st) { mbar_init(smem_u32(&S.b_full[st]), 1); mbar_init(smem_u32(&S.b_empty[st]), 1); }
-        for (int st = 0; st < ACC_STAGES; ++st) { mbar_init(smem_u32(&S.acc_full[st]), 1); mbar_init(smem_u32(&S.acc_empty[st]), EPI_WARPS); }
+        for (int st = 0; st < MRES_ACC; ++st) { mbar_init(smem_u32(&S.acc_full[st]), 1); mbar_init(smem_u32(&S.acc_empty[st]), EPI_WARPS); }
         S.abort_flag = 0;
         fence_barrier_init();
     }
@@ -333,7 +334,7 @@ blend_tc_forward_mres_kernel(const TcBlobHeader* __restrict__ hdr, const unsigne
                 }
                 if (!ok) break;
                 tc_commit(smem_u32(&S.acc_full[acc]));
-                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                if (++acc == MRES_ACC) { acc = 0; acc_phase ^= 1; }
             }
             a_phase ^= 1;
         }
@@ -377,7 +378,7 @@ blend_tc_forward_mres_kernel(const TcBlobHeader* __restrict__ hdr, const unsigne
                         }
                     }
                 }
-                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                if (++acc == MRES_ACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     }

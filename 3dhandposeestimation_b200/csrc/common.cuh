@@ -203,6 +203,9 @@ int launch_joints_only_forward_lh(const void* blob, int nc, const float* rot, co
                                   int B, float* joints, cudaStream_t s);
 int launch_joints_only_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                    const float* g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);
+int launch_fit_step_lh(const void* blob, int nc, float* params, float* exp_avg, float* exp_avg_sq, const float* target_joints,
+                       const float* vis, int B, const double* globals, double* partials, float lr, float beta1, float beta2,
+                       float eps, int step, int regularize, cudaStream_t s);
 // dfeat: dfeat_parts partial copies, dfeat_stride floats apart, added in order
 int launch_pose_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                          const float* dfeat, int dfeat_parts, size_t dfeat_stride, const float* dbone, const float* g_joints,

@@ -182,7 +182,12 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
     float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts)) + warp * BUF_FLOATS;
     float* bl = buf + lane;                                    // (row i, this hand) at bl[i * BP]
     const int ngroups = (B + 31) >> 5;
-    for (int g = blockIdx.x * LH_WARPS + warp; g < ngroups; g += gridDim.x * LH_WARPS) {
+    // block-uniform trip count with a barrier per pass: the four warps of a block walk this long straight-line code
+    // (85-170 KB of SASS) together, so they share its instruction-cache lines instead of evicting each other's
+    for (int g0 = blockIdx.x * LH_WARPS; g0 < ngroups; g0 += gridDim.x * LH_WARPS) {
+        __syncthreads();
+        const int g = g0 + warp;
+        if (g >= ngroups) continue;
         const long long h0 = (long long)g * 32;
         const int nh = (B - h0) < 32 ? (int)(B - h0) : 32;
         const long long hand = h0 + (lane < nh ? lane : nh - 1);      // idle lanes of a ragged group redo the last hand
@@ -276,7 +281,12 @@ pose_forward_lh_jo_kernel(const void* __restrict__ blob, int nc, const float* __
     float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts) + sizeof(LhTips)) + warp * BUF_FLOATS;
     float* bl = buf + lane;
     const int ngroups = (B + 31) >> 5;
-    for (int g = blockIdx.x * LH_WARPS + warp; g < ngroups; g += gridDim.x * LH_WARPS) {
+    // block-uniform trip count with a barrier per pass: the four warps of a block walk this long straight-line code
+    // (85-170 KB of SASS) together, so they share its instruction-cache lines instead of evicting each other's
+    for (int g0 = blockIdx.x * LH_WARPS; g0 < ngroups; g0 += gridDim.x * LH_WARPS) {
+        __syncthreads();
+        const int g = g0 + warp;
+        if (g >= ngroups) continue;
         const long long h0 = (long long)g * 32;
         const int nh = (B - h0) < 32 ? (int)(B - h0) : 32;
         const long long hand = h0 + (lane < nh ? lane : nh - 1);
@@ -351,13 +361,64 @@ pose_forward_lh_jo_kernel(const void* __restrict__ blob, int nc, const float* __
 // Staging rows of the backward (per warp, pitch BP): dfeat rows 0..147 are loaded first; the chain
 // joints' upstream gradients (48 floats) and the axis-angle gradients (45 floats) reuse rows that
 // have been consumed.
-template <bool JO>
+// MODE 0: full backward (dfeat / dbone from the skinning and blend backward); MODE 1: joints only (the five tips stand
+// in for the 778 vertices); MODE 2: one iteration of the fitting loop in ONE kernel (BASELINE config 5) — joints-only
+// forward, gradient of the masked L2 objective against target keypoints (criterions/loss.py:10-25), joints-only
+// backward, the regulariser's gradient (:113-117) and the Adam update of this hand's 58 parameters, plus this
+// launch's partial sums {sum vis |d|^2, sum theta_new^2, sum beta_new^2}.  The batch-global quantities the gradient
+// needs (visible count, Frobenius norms of the CURRENT parameters) depend only on the mask and the parameters, not on
+// the forward pass, so they arrive reduced from the previous iteration (FitArgs::globals) and the iteration needs
+// no grid-wide dependency inside.  In MODE 2 rot/coeffs/betas alias g_rot/g_coeffs/g_betas (updated in place).
+struct FitArgs {
+    const float* tgt;          // [B][21][3] target keypoints
+    const float* vis;          // [B][21] visibility (non-zero = visible)
+    float* m;                  // Adam first moments, laid out like the parameters: rot[B][3] | coeffs[B][nc] | betas[B][10]
+    float* v;                  // Adam second moments
+    const double* globals;     // device {N_vis, sum theta^2, sum beta^2} over ALL ranks for the current parameters
+    double* partials;          // device {sum vis |d|^2, sum theta_new^2, sum beta_new^2} of this launch (zeroed by the launcher)
+    float step_size, b1, b2, eps, inv_sqrt_bc2;
+    int regularize;
+};
+
+// torch.optim.Adam on `n` consecutive parameters (rows of `w` values, gradients staged row-major with pitch `pitch`),
+// plus `reg` * parameter added to the gradient; loads of a batch of ADAM_U rows are issued before any arithmetic so
+// that one warp keeps 3 * ADAM_U coalesced requests in flight.  Returns this lane's sum of the updated squares.
+constexpr int ADAM_U = 9;
+__device__ __noinline__ float adam_rows(float* __restrict__ prm, float* __restrict__ m, float* __restrict__ v,
+                                           const float* __restrict__ s_grad, int w, int pitch, int n, float reg,
+                                           float b1, float b2, float step_size, float inv_sqrt_bc2, float eps, int lane) {
+    const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+    float sq = 0.f;
+    for (int base = lane; base < n; base += 32 * ADAM_U) {
+        float pv[ADAM_U], mv[ADAM_U], vv[ADAM_U];
+#pragma unroll
+        for (int u = 0; u < ADAM_U; ++u) {
+            const int i = base + 32 * u;
+            if (i < n) { pv[u] = prm[i]; mv[u] = m[i]; vv[u] = v[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < ADAM_U; ++u) {
+            const int i = base + 32 * u;
+            if (i < n) {
+                const float gr = fmaf(reg, pv[u], s_grad[(i / w) * pitch + (i % w)]);
+                const float mi = fmaf(b1, mv[u], omb1 * gr);
+                const float vi = fmaf(b2, vv[u], omb2 * gr * gr);
+                const float pn = pv[u] - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+                m[i] = mi; v[i] = vi; prm[i] = pn;
+                sq = fmaf(pn, pn, sq);
+            }
+        }
+    }
+    return sq;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(LH_WARPS * 32)
-pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
-                        const float* __restrict__ coeffs, const float* __restrict__ betas,
+pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* rot, const float* coeffs, const float* betas,
                         const float* __restrict__ dfeat_t, const float* __restrict__ dbone_t,
-                        const float* __restrict__ g_joints, int B,
-                        float* __restrict__ g_rot, float* __restrict__ g_coeffs, float* __restrict__ g_betas) {
+                        const float* __restrict__ g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas,
+                        const FitArgs F) {
+    constexpr bool JO = MODE >= 1, FIT = MODE == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LhConsts& C = *reinterpret_cast<LhConsts*>(smem_raw);
     LhTips& T = *reinterpret_cast<LhTips*>(smem_raw + sizeof(LhConsts));      // joints-only variant
@@ -367,21 +428,39 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
     float* buf = reinterpret_cast<float*>(smem_raw + sizeof(LhConsts) + (JO ? sizeof(LhTips) : 0)) + warp * BUF_FLOATS;
     float* bl = buf + lane;
     const int ngroups = (B + 31) >> 5;
-    for (int g = blockIdx.x * LH_WARPS + warp; g < ngroups; g += gridDim.x * LH_WARPS) {
+    // fitting step: batch-global scalars of the objective, this thread's partial sums
+    float l2_scale = 0.f, reg_t = 0.f, reg_b = 0.f;
+    double acc_s = 0.0, acc_t = 0.0, acc_b = 0.0;
+    if (FIT) {
+        const double nv = F.globals[0], tn = sqrt(F.globals[1]), bn = sqrt(F.globals[2]);
+        l2_scale = nv > 0.0 ? (float)(2.0 / nv) : 0.f;                       // d(mean over visible of |d|^2) / d joint
+        reg_t = (F.regularize && tn > 0.0) ? (float)(1.0 / (100.0 * tn)) : 0.f;   // d(|theta|_F / 100) = theta / (100 |theta|_F)
+        reg_b = (F.regularize && bn > 0.0) ? (float)(1.0 / (10.0 * bn)) : 0.f;    // d(10 |beta|_F / 100)
+    }
+    // block-uniform trip count with a barrier per pass: the four warps of a block walk this long straight-line code
+    // (85-170 KB of SASS) together, so they share its instruction-cache lines instead of evicting each other's
+    for (int g0 = blockIdx.x * LH_WARPS; g0 < ngroups; g0 += gridDim.x * LH_WARPS) {
+        __syncthreads();
+        // a warp beyond the last group walks the pass with zero hands (it reads group ngroups-1, writes nothing): the
+        // barriers inside the finger loops below need every warp of the block
+        const bool active = g0 + warp < ngroups;
+        const int g = active ? g0 + warp : ngroups - 1;
         const long long h0 = (long long)g * 32;
-        const int nh = (B - h0) < 32 ? (int)(B - h0) : 32;
-        const long long hand = h0 + (lane < nh ? lane : nh - 1);
+        const int nh = !active ? 0 : ((B - h0) < 32 ? (int)(B - h0) : 32);
+        const long long hand = h0 + (lane < nh ? lane : (nh > 0 ? nh - 1 : 0));
         const bool live = lane < nh;
         const int r = (int)(hand - h0);
         __syncwarp();
         float* s_coef = buf;
         float* s_beta = buf + 32 * NAA;
         float* s_rot = s_beta + 32 * NB;
-        float* s_gj = s_rot + 96;                              // [32][63] upstream joint gradients, row-major
+        float* s_gj = s_rot + 96;                              // [32][63] upstream joint gradients (fit: targets), row-major
+        float* s_vis = s_gj + 32 * NOUTJ * 3;                  // [32][21] fit only: 3872 + 672 = 4544 floats < BUF_FLOATS
         stage_in(s_coef, coeffs + h0 * nc, nh * nc, lane);
         stage_in(s_beta, betas + h0 * NB, nh * NB, lane);
         stage_in(s_rot, rot + h0 * 3, nh * 3, lane);
-        stage_in(s_gj, g_joints + h0 * (NOUTJ * 3), nh * NOUTJ * 3, lane);   // 1856 + 2016 = 3872 floats < BUF_FLOATS
+        stage_in(s_gj, (FIT ? F.tgt : g_joints) + h0 * (NOUTJ * 3), nh * NOUTJ * 3, lane);   // 1856 + 2016 = 3872 floats < BUF_FLOATS
+        if (FIT) stage_in(s_vis, F.vis + h0 * NOUTJ, nh * NOUTJ, lane);
         __syncwarp();
         float beta[NB];
 #pragma unroll
@@ -390,19 +469,22 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
         const M3 Rq = rodrigues(rq);
         // upstream gradients of the 16 chain joints -> registers (slot of chain joint k: 0, 1+4f+i)
         V3 gj[NJ];
-        gj[0] = v3(s_gj[r * 63], s_gj[r * 63 + 1], s_gj[r * 63 + 2]);
-#pragma unroll
-        for (int f = 0; f < 5; ++f)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float* p = s_gj + r * 63 + (1 + 4 * f + i) * 3;
-                gj[1 + 3 * f + i] = v3(p[0], p[1], p[2]);
-            }
         float gt[15];                                          // upstream gradients of the five tip joints (joints-only)
+        auto load_joint_grads = [&]() {
+            gj[0] = v3(s_gj[r * 63], s_gj[r * 63 + 1], s_gj[r * 63 + 2]);
 #pragma unroll
-        for (int t = 0; t < NTIP; ++t)
+            for (int f = 0; f < 5; ++f)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) gt[3 * t + c] = JO ? s_gj[r * 63 + (4 + 4 * t) * 3 + c] : 0.f;
+                for (int i = 0; i < 3; ++i) {
+                    const float* p = s_gj + r * 63 + (1 + 4 * f + i) * 3;
+                    gj[1 + 3 * f + i] = v3(p[0], p[1], p[2]);
+                }
+#pragma unroll
+            for (int t = 0; t < NTIP; ++t)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gt[3 * t + c] = JO ? s_gj[r * 63 + (4 + 4 * t) * 3 + c] : 0.f;
+        };
+        if (!FIT) load_joint_grads();
         float th[NAA];
         {
             // theta in registers (the staging buffer is about to be overwritten by dfeat)
@@ -426,6 +508,66 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
         // dfeat is read straight from its hand-minor global rows
 #pragma unroll
         for (int j = 0; j < NAA; ++j) bl[j * BP] = th[j];                      // rows 0..44: theta, later dtheta
+        float tv[15], dtv[15];
+#pragma unroll
+        for (int c = 0; c < 15; ++c) { tv[c] = 0.f; dtv[c] = 0.f; }
+        if (FIT) {
+            // ---- forward (as pose_forward_lh_jo_kernel): every joint turns its staged target into the objective's
+            // gradient in place — row r of s_gj belongs to this lane alone (idle lanes of a ragged group do not write)
+            tips_rest_pose(T, beta, bl, 0, tv);
+            float sres = 0.f;
+            auto resid = [&](int slot, const V3& j) {
+                float* p = s_gj + r * 63 + slot * 3;
+                const float dx = j.x - p[0], dy = j.y - p[1], dz = j.z - p[2];
+                const bool on = s_vis[r * NOUTJ + slot] != 0.f;
+                if (on) sres += dx * dx + dy * dy + dz * dz;
+                const float sc = on ? l2_scale : 0.f;
+                if (live) { p[0] = sc * dx; p[1] = sc * dy; p[2] = sc * dz; }
+            };
+            float out[15];
+#pragma unroll
+            for (int c = 0; c < 15; ++c) out[c] = 0.f;
+            auto bone = [&](int k, int slot, const M3& Rg, const V3& tg, const V3& J) {
+                const M3 Rp = m3_mul(Rq, Rg);
+                const V3 tp = m3_vec(Rq, v3_sub(tg, m3_vec(Rg, J)));
+                resid(slot, m3_vec(Rq, tg));
+#pragma unroll
+                for (int t = 0; t < NTIP; ++t) {
+                    const float w = T.w[t][k];
+                    if (w != 0.f) {
+                        const V3 p = m3_vec(Rp, v3(tv[3 * t], tv[3 * t + 1], tv[3 * t + 2]));
+                        out[3 * t] = fmaf(w, p.x + tp.x, out[3 * t]);
+                        out[3 * t + 1] = fmaf(w, p.y + tp.y, out[3 * t + 1]);
+                        out[3 * t + 2] = fmaf(w, p.z + tp.z, out[3 * t + 2]);
+                    }
+                }
+            };
+            const M3 R0f = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));
+            const V3 J0f = rest_joint(C, 0, beta);
+            bone(0, 0, R0f, J0f, J0f);
+#pragma unroll 1
+            for (int f = 0; f < 5; ++f) {
+                __syncthreads();                               // keep the block's warps on the same code
+                M3 Rgp = R0f;
+                V3 tgp = J0f, Jp = J0f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int k = 1 + 3 * f + i;
+                    const float* tp = bl + (3 * (k - 1)) * BP;
+                    const M3 R = rodrigues(v3(tp[0], tp[BP], tp[2 * BP]));
+                    const V3 J = rest_joint(C, k, beta);
+                    const M3 Rg = m3_mul(Rgp, R);
+                    const V3 tg = v3_add(tgp, m3_vec(Rgp, v3_sub(J, Jp)));
+                    bone(k, 1 + 4 * f + i, Rg, tg, J);
+                    Rgp = Rg; tgp = tg; Jp = J;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NTIP; ++t) resid(4 + 4 * t, v3(out[3 * t], out[3 * t + 1], out[3 * t + 2]));
+            if (live) acc_s += (double)sres;
+            load_joint_grads();
+            __syncwarp();                                      // targets / visibility consumed: rows 48.. may be overwritten
+        }
 #pragma unroll
         for (int k = 0; k < NJ; ++k) { bl[(48 + 3 * k) * BP] = gj[k].x; bl[(49 + 3 * k) * BP] = gj[k].y; bl[(50 + 3 * k) * BP] = gj[k].z; }
         const float* df = JO ? nullptr : dfeat_t + (size_t)g * (TC_K * 32) + lane;             // dfeat_t[g][k][lane], k < 160
@@ -433,14 +575,8 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
 
         // joints only: the five tips stand in for the 778 vertices — rest-pose tips tv, and (pre-pass over
         // the chain) d tv = sum_k w_tk R'_k^T g_t, from which every feature gradient follows
-        float tv[15], dtv[15];
-#pragma unroll
-        for (int c = 0; c < 15; ++c) { tv[c] = 0.f; dtv[c] = 0.f; }
         if (JO) {
-            float beta_[NB];
-#pragma unroll
-            for (int sft = 0; sft < NB; ++sft) beta_[sft] = beta[sft];
-            tips_rest_pose(T, beta_, bl, 0, tv);
+            if (!FIT) tips_rest_pose(T, beta, bl, 0, tv);
             auto tip_back = [&](int k, const M3& Rg) {
                 const M3 Rp = m3_mul(Rq, Rg);
 #pragma unroll
@@ -456,6 +592,7 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
             tip_back(0, R0p);
 #pragma unroll 1
             for (int f = 0; f < 5; ++f) {
+                __syncthreads();                               // keep the block's warps on the same code
                 M3 Rgp = R0p;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -527,6 +664,7 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
         split_bone(0, R0, J0, J0, v3(bl[48 * BP], bl[49 * BP], bl[50 * BP]), dRg0, dtg0, dJ0);
 #pragma unroll 1
         for (int f = 0; f < 5; ++f) {
+            __syncthreads();                                   // keep the block's warps on the same code
             // forward through the chain (state of the three joints stays in registers)
             M3 R[3], Rg[3];
             V3 tg[3], J[3], rr[3];
@@ -596,11 +734,42 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* __re
             s_gc[lane * gp + i] = acc;
         }
         __syncwarp();
-        for (int i = lane; i < nh * nc; i += 32) g_coeffs[h0 * nc + i] = s_gc[(i / nc) * gp + (i % nc)];
-        if (live) {
-            g_rot[hand * 3] = drq.x; g_rot[hand * 3 + 1] = drq.y; g_rot[hand * 3 + 2] = drq.z;
+        if (!FIT) {
+            for (int i = lane; i < nh * nc; i += 32) g_coeffs[h0 * nc + i] = s_gc[(i / nc) * gp + (i % nc)];
+            if (live) {
+                g_rot[hand * 3] = drq.x; g_rot[hand * 3 + 1] = drq.y; g_rot[hand * 3 + 2] = drq.z;
 #pragma unroll
-            for (int s = 0; s < NB; ++s) g_betas[hand * NB + s] = gbeta[s];
+                for (int s = 0; s < NB; ++s) g_betas[hand * NB + s] = gbeta[s];
+            }
+        } else {
+            // ---- regulariser gradient + torch.optim.Adam (as adam_kernel in reduce.cu), parameters updated in place
+            const size_t off_c = (size_t)B * 3, off_b = (size_t)B * (3 + nc);
+            // rot / beta gradients join the coefficient gradients in the row-major staging so that every parameter,
+            // moment and update moves as a coalesced row of the flat buffers
+            float* s_gb = s_gc + 32 * 46;                      // [32][11]
+            float* s_gr = s_gb + 32 * 11;                      // [32][3]   (ends at float 2112 + 1472 + 352 + 96 < BUF_FLOATS)
+#pragma unroll
+            for (int s = 0; s < NB; ++s) s_gb[lane * 11 + s] = fmaf(reg_b, beta[s], gbeta[s]);
+            s_gr[lane * 3] = drq.x; s_gr[lane * 3 + 1] = drq.y; s_gr[lane * 3 + 2] = drq.z;
+            __syncwarp();
+            const float st = adam_rows(g_coeffs + (size_t)h0 * nc, F.m + off_c + (size_t)h0 * nc, F.v + off_c + (size_t)h0 * nc,
+                                       s_gc, nc, gp, nh * nc, reg_t, F.b1, F.b2, F.step_size, F.inv_sqrt_bc2, F.eps, lane);
+            const float sb = adam_rows(g_betas + (size_t)h0 * NB, F.m + off_b + (size_t)h0 * NB, F.v + off_b + (size_t)h0 * NB,
+                                       s_gb, NB, 11, nh * NB, 0.f, F.b1, F.b2, F.step_size, F.inv_sqrt_bc2, F.eps, lane);
+            adam_rows(g_rot + (size_t)h0 * 3, F.m + (size_t)h0 * 3, F.v + (size_t)h0 * 3, s_gr, 3, 3, nh * 3, 0.f, F.b1, F.b2, F.step_size, F.inv_sqrt_bc2, F.eps, lane);
+            acc_t += (double)st;
+            acc_b += (double)sb;
+        }
+    }
+    if (FIT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+            acc_t += __shfl_xor_sync(0xffffffffu, acc_t, o);
+            acc_b += __shfl_xor_sync(0xffffffffu, acc_b, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&F.partials[0], acc_s); atomicAdd(&F.partials[1], acc_t); atomicAdd(&F.partials[2], acc_b);
         }
     }
 }
@@ -611,7 +780,7 @@ constexpr size_t LH_SMEM_JO = LH_SMEM + sizeof(LhTips);
 inline int lh_grid(int B) {
     const long long groups = ((long long)B + 31) / 32;
     const long long blocks = (groups + LH_WARPS - 1) / LH_WARPS;
-    const long long cap = (long long)NUM_SMS * 2;
+    const long long cap = (long long)NUM_SMS * (8 / LH_WARPS);
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
@@ -634,12 +803,12 @@ int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const fl
                             float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    pose_backward_lh_kernel<false><<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, dfeat_t, dbone_t, g_joints, B,
-                                                                             g_rot, g_coeffs, g_betas);
+    pose_backward_lh_kernel<0><<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, dfeat_t, dbone_t, g_joints, B,
+                                                                             g_rot, g_coeffs, g_betas, FitArgs{});
     return cuda_rc();
 }
 
@@ -659,12 +828,37 @@ int launch_joints_only_backward_lh(const void* blob, int nc, const float* rot, c
                                    const float* g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
+        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    pose_backward_lh_kernel<true><<<lh_grid(B), LH_WARPS * 32, LH_SMEM_JO, s>>>(blob, nc, rot, coeffs, betas, nullptr, nullptr, g_joints, B,
-                                                                               g_rot, g_coeffs, g_betas);
+    pose_backward_lh_kernel<1><<<lh_grid(B), LH_WARPS * 32, LH_SMEM_JO, s>>>(blob, nc, rot, coeffs, betas, nullptr, nullptr, g_joints, B,
+                                                                               g_rot, g_coeffs, g_betas, FitArgs{});
+    return cuda_rc();
+}
+
+// One fitting iteration (MODE 2 above).  params / exp_avg / exp_avg_sq: rot[B][3] | coeffs[B][nc] | betas[B][10].
+int launch_fit_step_lh(const void* blob, int nc, float* params, float* exp_avg, float* exp_avg_sq, const float* target_joints,
+                       const float* vis, int B, const double* globals, double* partials, float lr, float beta1, float beta2,
+                       float eps, int step, int regularize, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    cudaError_t e = cudaMemsetAsync(partials, 0, 3 * sizeof(double), s);
+    if (e != cudaSuccess) return (int)e;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    FitArgs F;
+    F.tgt = target_joints; F.vis = vis; F.m = exp_avg; F.v = exp_avg_sq; F.globals = globals; F.partials = partials;
+    F.step_size = (float)(lr / bc1); F.b1 = beta1; F.b2 = beta2; F.eps = eps; F.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    F.regularize = regularize;
+    float* rot = params;
+    float* coeffs = params + (size_t)B * 3;
+    float* betas = params + (size_t)B * (3 + nc);
+    pose_backward_lh_kernel<2><<<lh_grid(B), LH_WARPS * 32, LH_SMEM_JO, s>>>(blob, nc, rot, coeffs, betas, nullptr, nullptr, nullptr, B,
+                                                                            rot, coeffs, betas, F);
     return cuda_rc();
 }
 

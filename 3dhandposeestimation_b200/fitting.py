@@ -7,9 +7,14 @@ Objective = the reference's training terms for the MANO heads:
 Both are normalised by batch-global quantities (visible count, Frobenius norms), so with the batch
 sharded over ranks every iteration needs exactly one collective: an all-reduce (sum) of the four
 partials ``[sum ||d||^2, N_vis, sum theta^2, sum beta^2]`` — 32 bytes over NCCL/NVLink.  Everything
-else is rank-local: joints-only forward kernel, masked reduction kernel, joints-only backward kernel,
-fused Adam kernel (all sm_100a, through the C ABI; no autograd tape, no host synchronisation —
-the reduced scalars stay on the device).
+else is rank-local, and for MANO's kinematic tree it is ONE kernel per iteration (``mb_mano_fit_step``:
+joints-only forward, objective gradient, joints-only backward, regulariser gradient, Adam).  That is possible
+because the batch-global scalars the gradient needs — the visible count and the Frobenius norms of the current
+parameters — do not depend on the forward pass: the kernel of iteration i also emits the norms of the parameters it
+has just updated, and the all-reduce that follows it delivers them to iteration i+1 together with iteration i's
+L2 sum.  Other trees run the separate kernels (joints-only forward, masked reduction, joints-only backward, fused
+Adam).  All sm_100a, through the C ABI; no autograd tape, no host synchronisation — the reduced scalars stay on
+the device.
 
 The reference itself has no fitting loop (its only optimiser is Adam on network weights,
 trainval.py:119); the hyper-parameters here (lr 1e-2, betas (0.9, 0.999), eps 1e-8) are this
@@ -55,8 +60,13 @@ def objective_from_partials(p: torch.Tensor):
 class ManoFitter:
     """Fits `n_hands` MANO parameter sets (this rank's shard) to target 21-joint keypoints."""
 
-    def __init__(self, layer, n_hands: int, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, group=None, regularize=True):
+    def __init__(self, layer, n_hands: int, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, group=None, regularize=True, fused=None):
         self.layer = layer
+        # one-kernel iterations need MANO's tree (five chains of three joints below the wrist)
+        can_fuse = bool(layer._mode & _cabi.MODEL_CHAINS_5X3)
+        if fused and not can_fuse:
+            raise _cabi.ManoB200Error("fused fitting steps need a MANO-shaped kinematic tree (MB_MODEL_CHAINS_5X3)")
+        self.fused = can_fuse if fused is None else bool(fused)
         self.dev = layer._require_device()
         self.B = int(n_hands)
         self.nc = layer.pose_num
@@ -83,6 +93,46 @@ class ManoFitter:
         self.one = torch.ones((), device=self.dev)
         self.steps = 0
         self.loss = torch.zeros((), dtype=torch.float64, device=self.dev)
+        # fused path: {N_vis, sum theta^2, sum beta^2} of the current parameters (global), this rank's kernel partials
+        self.globals = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        self.kernel_partials = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        self._vis_key = None
+        self._param_version = None
+
+    def refresh(self, keypoint_vis: torch.Tensor) -> None:
+        """(Re)compute the batch-global scalars of the fused path from scratch: visible count and parameter norms,
+        all-reduced.  Called automatically on the first step, when another visibility mask is passed and when the
+        parameters were written from outside (``fit.pose.copy_(...)``); with a sharded batch every rank must do so
+        in the same iteration (it is a collective)."""
+        g = self.globals
+        g[0] = keypoint_vis.ne(0).sum(dtype=torch.float64)
+        g[1] = self.pose.double().square().sum()
+        g[2] = self.beta.double().square().sum()
+        reduce_partials(g, self.group)
+        self._vis_key = (keypoint_vis.data_ptr(), keypoint_vis._version, tuple(keypoint_vis.shape))
+        self._param_version = self.params._version
+
+    def _step_fused(self, tgt, vis, stream):
+        lib = _cabi.lib()
+        if (self._vis_key != (vis.data_ptr(), vis._version, tuple(vis.shape)) or self._param_version != self.params._version):
+            self.refresh(vis)
+        self.steps += 1
+        _cabi.check(lib.mb_mano_fit_step(self.layer._blob.data_ptr(), self.nc, self.params.data_ptr(), self.exp_avg.data_ptr(),
+                                         self.exp_avg_sq.data_ptr(), tgt.data_ptr(), vis.data_ptr(), self.B, self.layer._mode,
+                                         self.globals.data_ptr(), self.kernel_partials.data_ptr(), self.lr, self.b1, self.b2,
+                                         self.eps, self.steps, int(self.regularize), stream), "mb_mano_fit_step")
+        # the one collective of the iteration: {L2 sum of this iteration, norms of the updated parameters}
+        reduce_partials(self.kernel_partials, self.group)
+        p = self.partials                                     # [S, N, sum theta^2, sum beta^2] of the iteration just done
+        p[0] = self.kernel_partials[0]
+        p[1] = self.globals[0]
+        if self.regularize:
+            p[2:4] = self.globals[1:3]
+        else:
+            p[2:4] = 0
+        self.loss, _, _ = objective_from_partials(p)
+        self.globals[1:3] = self.kernel_partials[1:3]
+        return self.loss
 
     def step(self, target_joints: torch.Tensor, keypoint_vis: torch.Tensor) -> torch.Tensor:
         """One Adam iteration; returns the (global) loss as a 0-dim device tensor (no host sync)."""
@@ -92,7 +142,10 @@ class ManoFitter:
         blob = self.layer._blob.data_ptr()
         mode = self.layer._mode
         tgt = target_joints.contiguous()
-        vis = keypoint_vis.to(torch.float32).contiguous()
+        vis = keypoint_vis if (keypoint_vis.dtype == torch.float32 and keypoint_vis.is_contiguous()) else \
+            keypoint_vis.to(torch.float32).contiguous()
+        if self.fused:
+            return self._step_fused(tgt, vis, stream)
         # 1. joints-only forward (no 778-vertex contraction)
         _cabi.check(lib.mb_mano_forward(blob, nc, self.rot.data_ptr(), self.pose.data_ptr(), self.beta.data_ptr(), B, mode,
                                         None, self.joints.data_ptr(), None, 0, stream), "mb_mano_forward")

@@ -234,6 +234,20 @@ MB_API int mb_hand_mask_loss(const float* pred_uv, const float* gt_uv, const voi
 /* ----------------------------------------------------------- fitting loop ---
  * One Adam update on a flat fp32 parameter array (torch.optim.Adam semantics, no
  * weight decay, no amsgrad): used by the batched MANO fitting loop (BASELINE config 5). */
+/* One whole iteration of that loop in a single kernel (SURVEY 8b `mano_fit_step`): joints-only forward, gradient of
+ * L2Loss (criterions/loss.py:10-25) against target_joints[B][21][3] under keypoint_vis[B][21] (fp32, non-zero =
+ * visible), joints-only backward, gradient of the regulariser (:113-117, when regularize != 0) and the Adam update
+ * (step = 1, 2, ...) of params / exp_avg / exp_avg_sq, each laid out rot[B][3] | coeffs[B][nc] | betas[B][10].
+ *   globals  (device, in) : {N_vis, sum theta^2, sum beta^2} over ALL ranks for the parameters as they are on entry —
+ *                           they depend on the mask and the parameters only, so they come from the previous
+ *                           iteration's partials (all-reduced by the caller when the batch is sharded)
+ *   partials (device, out): {sum over this call's visible joints of |joint - target|^2, sum theta^2, sum beta^2 of
+ *                           the UPDATED parameters} of this rank
+ * `mode` must carry MB_MODEL_CHAINS_5X3 (MANO's tree), else MB_E_MODEL: use the separate calls above. */
+MB_API int mb_mano_fit_step(const void* blob, int nc, float* params, float* exp_avg, float* exp_avg_sq,
+                     const float* target_joints, const float* keypoint_vis, int B, int mode, const double* globals,
+                     double* partials, float lr, float beta1, float beta2, float eps, int step, int regularize,
+                     mb_stream_t stream);
 MB_API int mb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                  float lr, float beta1, float beta2, float eps, int step, mb_stream_t stream);
 

@@ -616,13 +616,16 @@ def test_adam_step_matches_torch(pkg, cuda_device):
 
 
 # ------------------------------------------------------------------------ fitting loop
-def test_fitting_loop_matches_oracle_adam(pkg, synth_model, cuda_device):
+@pytest.mark.parametrize("fused,B", [(True, 64), (False, 64), (True, 8231)])
+def test_fitting_loop_matches_oracle_adam(pkg, synth_model, cuda_device, fused, B):
     """BASELINE config 5 parity: 64 hands x 10 Adam iterations against the oracle's
-    objective (L2Loss + regulariser) and gradients with a numpy Adam (torch.optim.Adam semantics)."""
+    objective (L2Loss + regulariser) and gradients with a numpy Adam (torch.optim.Adam semantics) — as one
+    kernel per iteration (mb_mano_fit_step) and as the separate forward / reduce / backward / Adam kernels;
+    a ragged 8 231-hand batch for the fused kernel's multi-group path."""
     import torch
 
     fitting = importlib.import_module("3dhandposeestimation_b200.fitting")
-    B, nc, iters = 64, 45, 10
+    nc, iters = 45, 10
     rs = np.random.RandomState(5)
     hidden = mano_inputs(B, nc, seed=77, pose_scale=1.0)
     _, tj = mo.mano_forward(synth_model, *hidden)
@@ -630,7 +633,8 @@ def test_fitting_loop_matches_oracle_adam(pkg, synth_model, cuda_device):
     vis = (rs.rand(B, 21, 1) < .8).astype(np.float32)
     start = [a * 0.5 + 0.01 for a in hidden]
     layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc)
-    fit = fitting.ManoFitter(layer, B, lr=1e-2)
+    fit = fitting.ManoFitter(layer, B, lr=1e-2, fused=fused)
+    assert fit.fused == fused
     for dst, src in zip((fit.rot, fit.pose, fit.beta), start):
         dst.copy_(torch.from_numpy(src.astype(np.float32)))
     ttarget, tvis = to_dev(cuda_device, target, vis)
