@@ -31,6 +31,7 @@ constexpr int PCA_PITCH = 48;
 struct LhConsts {
     alignas(16) float pca[NAA * PCA_PITCH];          // [nc][48]
     float mean[NAA + 3];
+    int pca_identity;                                // hands_components[:nc] is the identity (full axis-angle input): theta = mean + coeffs
     float j0[NJ * 3];
     alignas(16) float jb[NJ * 3 * 12];               // [48][12] (10 used)
 };
@@ -50,10 +51,17 @@ __device__ void lh_stage_constants(LhConsts& C, const void* blob, int nc) {
     const float* j0 = blob_ptr<float>(blob, L.j0);
     const float* jb = blob_ptr<float>(blob, L.jb);
     const int t = threadIdx.x, nt = blockDim.x;
+    bool other = false;
     for (int i = t; i < NAA * PCA_PITCH; i += nt) {
         const int r = i / PCA_PITCH, c = i % PCA_PITCH;
-        C.pca[i] = (r < nc && c < NAA) ? pca[r * NAA + c] : 0.f;
+        const float x = (r < nc && c < NAA) ? pca[r * NAA + c] : 0.f;
+        C.pca[i] = x;
+        other |= r < nc && x != (r == c ? 1.f : 0.f);
     }
+    // "no PCA" models (BASELINE config 4: the 45 axis-angle values are the input) skip the 45 x 45 products;
+    // block-uniform, decided from the constants themselves
+    const int any_other = __syncthreads_or(other ? 1 : 0);
+    if (t == 0) C.pca_identity = !any_other;
     for (int i = t; i < NAA; i += nt) C.mean[i] = mean[i];
     for (int i = t; i < NJ * 3; i += nt) C.j0[i] = j0[i];
     for (int i = t; i < NJ * 3 * 12; i += nt) {
@@ -138,6 +146,10 @@ __device__ __forceinline__ V3 rest_joint(const LhConsts& C, int k, const float (
 
 // theta = mean + coeffs . pca  -> rows THETA_ROW.. of the staging buffer (column = this lane)
 __device__ __forceinline__ void lh_theta(const LhConsts& C, const float* s_coef, int nc, float* bl) {
+    if (C.pca_identity) {
+        for (int j = 0; j < NAA; ++j) bl[(THETA_ROW + j) * BP] = j < nc ? fmaf(s_coef[j], 1.f, C.mean[j]) : C.mean[j];
+        return;
+    }
     float th[NAA];
 #pragma unroll
     for (int j = 0; j < NAA; ++j) th[j] = C.mean[j];
@@ -491,6 +503,10 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* rot,
 #pragma unroll
             for (int j = 0; j < NAA; ++j) th[j] = C.mean[j];
             const float* sc = s_coef + r * nc;
+            if (C.pca_identity) {
+#pragma unroll
+                for (int j = 0; j < NAA; ++j) if (j < nc) th[j] = fmaf(sc[j], 1.f, th[j]);
+            } else
             for (int i = 0; i < nc; ++i) {
                 const float ci = sc[i];
                 const float4* row = reinterpret_cast<const float4*>(&C.pca[i * PCA_PITCH]);
@@ -721,6 +737,10 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* rot,
         __syncwarp();
         float* s_gc = buf + 64 * BP;                           // [32][nc | 1] row-major, rows 64.. (theta rows are consumed)
         const int gp = nc | 1;
+        if (C.pca_identity) {
+#pragma unroll
+            for (int j = 0; j < NAA; ++j) if (j < nc) s_gc[lane * gp + j] = dth[j];
+        } else
         for (int i = 0; i < nc; ++i) {
             const float4* row = reinterpret_cast<const float4*>(&C.pca[i * PCA_PITCH]);
             float acc = 0.f;

@@ -135,6 +135,40 @@ def test_mano_joints_only_large_batch_matches_fp64_oracle(pkg, synth_model, cuda
         assert rel(t.grad.cpu().numpy()[idx], want) < GRAD_TOL
 
 
+@pytest.mark.parametrize("B,nc", [(8200, 45), (9000, 20)])
+def test_mano_identity_pca_model_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc):
+    """BASELINE config 4 ("no PCA": hands_components = I, the coefficients are the axis-angles): the one-thread-per-hand
+    kernels detect the identity and skip the 45 x 45 products — full layer, joints-only path and gradients; with a
+    non-zero mean and nc < 45 the remaining angles stay at the mean."""
+    import torch
+
+    model = dict(synth_model)
+    model["hands_components"] = np.eye(45)
+    rot, pose, beta = mano_inputs(B, nc, seed=B, pose_scale=np.pi / 2)
+    layer = pkg.ManoLayer(cuda_device, model=model, pose_num=nc)
+    t = to_dev(cuda_device, rot, pose, beta, grad=True)
+    verts, joints = layer(*t)
+    idx = np.unique(np.r_[np.arange(64), np.arange(B - 40, B)])
+    ov, oj = mo.mano_forward(model, rot[idx], pose[idx], beta[idx])
+    assert np.abs(verts.detach().cpu().numpy()[idx] - ov).max() < POS_TOL_F64
+    assert np.abs(joints.detach().cpu().numpy()[idx] - oj).max() < POS_TOL_F64
+    rs = np.random.RandomState(4)
+    gv = rs.randn(B, 778, 3).astype(np.float32)
+    gj = rs.randn(B, 21, 3).astype(np.float32)
+    tgv, tgj = to_dev(cuda_device, gv, gj)
+    ((verts * tgv).sum() + (joints * tgj).sum()).backward()
+    og = mo.mano_backward(model, rot[idx], pose[idx], beta[idx], gv[idx], gj[idx])
+    for x, want in zip(t, og):
+        assert rel(x.grad.cpu().numpy()[idx], want) < GRAD_TOL
+    t2 = to_dev(cuda_device, rot, pose, beta, grad=True)
+    _, j2 = layer.rot_pose_beta_to_mesh(*t2, joints_only=True)
+    assert float((j2.detach() - joints.detach()).abs().max()) < 2e-7
+    (j2 * tgj).sum().backward()
+    og2 = mo.mano_backward(model, rot[idx], pose[idx], beta[idx], np.zeros((idx.size, 778, 3), np.float32), gj[idx])
+    for x, want in zip(t2, og2):
+        assert rel(x.grad.cpu().numpy()[idx], want) < GRAD_TOL
+
+
 def test_mano_fast_f16_mode_error_is_bounded(pkg, synth_model, cuda_device):
     """MB_MODE_F16 (single fp16 product on the tensor cores): bounded, stated error."""
     rot, pose, beta = mano_inputs(512, 45, seed=3)
