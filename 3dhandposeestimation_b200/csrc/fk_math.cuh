@@ -73,6 +73,93 @@ HD V3 project_point_bwd(const float* K, float x, float y, float z, float gu, flo
               fmaf(K[2], dpx, fmaf(K[5], dpy, K[8] * dpz)));
 }
 
+// ---- local rotations by their zero structure -----------------------------------------------------------------
+// Of the 16 Euler triples only the root and the first two thumb segments use all three angles
+// (forwardKinematicsLayer.py:239-274): the third thumb segment turns about y only, a finger's first segment about
+// x and y, its second and third about x only.  sin 0 = 0 and cos 0 = 1 are exact and a product with an exact zero
+// adds nothing in m3_mul's fmaf chains, so dropping those terms gives the SAME floats as euler_xyz + m3_mul with
+// 26 sincos instead of 48 and about a third of the multiplies.  kind: 0 = xyz, 1 = xy, 2 = x, 3 = y.
+HD int fk_angle_kind(int f, int seg) { return f == 0 ? (seg < 2 ? 0 : 3) : (seg == 0 ? 1 : 2); }
+
+struct FkSC { float sx, cx, sy, cy, sz, cz; };                    // unused pairs stay (0, 1)
+
+HD FkSC fk_sincos(int kind, float x, float y, float z) {
+    FkSC q = {0.f, 1.f, 0.f, 1.f, 0.f, 1.f};
+    if (kind != 3) sincos_acc(x, &q.sx, &q.cx);
+    if (kind == 0 || kind == 1 || kind == 3) sincos_acc(y, &q.sy, &q.cy);
+    if (kind == 0) sincos_acc(z, &q.sz, &q.cz);
+    return q;
+}
+// the local rotation itself (the backward needs it for dRg Rl^T)
+HD M3 fk_local_rot(int kind, const FkSC& q) {
+    M3 R;
+    if (kind == 0) {
+        R.m[0] = q.cy * q.cz;                       R.m[1] = -q.cy * q.sz;                      R.m[2] = q.sy;
+        R.m[3] = q.cx * q.sz + q.sx * q.sy * q.cz;  R.m[4] = q.cx * q.cz - q.sx * q.sy * q.sz;  R.m[5] = -q.sx * q.cy;
+        R.m[6] = q.sx * q.sz - q.cx * q.sy * q.cz;  R.m[7] = q.sx * q.cz + q.cx * q.sy * q.sz;  R.m[8] = q.cx * q.cy;
+    } else if (kind == 1) {
+        R.m[0] = q.cy;           R.m[1] = 0.f;   R.m[2] = q.sy;
+        R.m[3] = q.sx * q.sy;    R.m[4] = q.cx;  R.m[5] = -q.sx * q.cy;
+        R.m[6] = -(q.cx * q.sy); R.m[7] = q.sx;  R.m[8] = q.cx * q.cy;
+    } else if (kind == 2) {
+        R.m[0] = 1.f; R.m[1] = 0.f;  R.m[2] = 0.f;
+        R.m[3] = 0.f; R.m[4] = q.cx; R.m[5] = -q.sx;
+        R.m[6] = 0.f; R.m[7] = q.sx; R.m[8] = q.cx;
+    } else {
+        R.m[0] = q.cy;  R.m[1] = 0.f; R.m[2] = q.sy;
+        R.m[3] = 0.f;   R.m[4] = 1.f; R.m[5] = 0.f;
+        R.m[6] = -q.sy; R.m[7] = 0.f; R.m[8] = q.cy;
+    }
+    return R;
+}
+// Rg = A Rl with the zero terms of m3_mul dropped (same association for the terms that stay)
+HD M3 fk_chain_rot(int kind, const M3& A, const M3& Rl) {
+    if (kind == 0) return m3_mul(A, Rl);
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a0 = A.m[i * 3], a1 = A.m[i * 3 + 1], a2 = A.m[i * 3 + 2];
+        if (kind == 1) {
+            r.m[i * 3]     = fmaf(a0, Rl.m[0], fmaf(a1, Rl.m[3], a2 * Rl.m[6]));
+            r.m[i * 3 + 1] = fmaf(a1, Rl.m[4], a2 * Rl.m[7]);
+            r.m[i * 3 + 2] = fmaf(a0, Rl.m[2], fmaf(a1, Rl.m[5], a2 * Rl.m[8]));
+        } else if (kind == 2) {
+            r.m[i * 3]     = a0;
+            r.m[i * 3 + 1] = fmaf(a1, Rl.m[4], a2 * Rl.m[7]);
+            r.m[i * 3 + 2] = fmaf(a1, Rl.m[5], a2 * Rl.m[8]);
+        } else {
+            r.m[i * 3]     = fmaf(a0, Rl.m[0], a2 * Rl.m[6]);
+            r.m[i * 3 + 1] = a1;
+            r.m[i * 3 + 2] = fmaf(a0, Rl.m[2], a2 * Rl.m[8]);
+        }
+    }
+    return r;
+}
+// euler_xyz_bwd from the sines and cosines the forward sweep already has; only the angles of `kind` are meaningful
+HD V3 fk_angle_grad(int kind, const FkSC& q, const M3& dR) {
+    const float* d = dR.m;
+    const float sx = q.sx, cx = q.cx, sy = q.sy, cy = q.cy, sz = q.sz, cz = q.cz;
+    V3 g = v3(0.f, 0.f, 0.f);
+    if (kind == 0) {
+        g.x = d[3] * (-sx * sz + cx * sy * cz) + d[4] * (-sx * cz - cx * sy * sz) + d[5] * (-cx * cy)
+            + d[6] * (cx * sz + sx * sy * cz)  + d[7] * (cx * cz - sx * sy * sz)  + d[8] * (-sx * cy);
+        g.y = d[0] * (-sy * cz) + d[1] * (sy * sz) + d[2] * cy
+            + d[3] * (sx * cy * cz) + d[4] * (-sx * cy * sz) + d[5] * (sx * sy)
+            + d[6] * (-cx * cy * cz) + d[7] * (cx * cy * sz) + d[8] * (-cx * sy);
+        g.z = d[0] * (-cy * sz) + d[1] * (-cy * cz)
+            + d[3] * (cx * cz - sx * sy * sz) + d[4] * (-cx * sz - sx * sy * cz)
+            + d[6] * (sx * cz + cx * sy * sz) + d[7] * (-sx * sz + cx * sy * cz);
+    } else if (kind == 1) {
+        g.x = d[3] * (cx * sy) + d[4] * (-sx) + d[5] * (-cx * cy) + d[6] * (sx * sy) + d[7] * cx + d[8] * (-sx * cy);
+        g.y = d[0] * (-sy) + d[2] * cy + d[3] * (sx * cy) + d[5] * (sx * sy) + d[6] * (-cx * cy) + d[8] * (-cx * sy);
+    } else if (kind == 2) {
+        g.x = d[4] * (-sx) + d[5] * (-cx) + d[7] * cx + d[8] * (-sx);
+    } else {
+        g.y = d[0] * (-sy) + d[2] * cy + d[6] * (-cy) + d[8] * (-sy);
+    }
+    return g;
+}
+
 // One sample forward.  xyz[63], uv[42] may be strided (element stride 1, caller gives row base).
 HD void fk_forward_sample(const float* ra, const float* oa, const float* bl, const float* K, float s,
                           const float* root, int swap, float* xyz, float* uv) {
@@ -93,7 +180,8 @@ HD void fk_forward_sample(const float* ra, const float* oa, const float* bl, con
             if (seg < 3) {
                 float x, y, z;
                 fk_local_angles(oa, f, seg, x, y, z);
-                Rg = m3_mul(Rpar, euler_xyz(x, y, z));
+                const int kind = fk_angle_kind(f, seg);
+                Rg = fk_chain_rot(kind, Rpar, fk_local_rot(kind, fk_sincos(kind, x, y, z)));
             } else {
                 Rg = Rpar;                                          // tip: identity local rotation
             }
@@ -121,6 +209,7 @@ HD void fk_backward_sample(const float* ra, const float* oa, const float* bl, co
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
         M3 Rg[4], Rl[3];
+        FkSC sc[3];
         V3 dP[4];
         {
             M3 Rpar = Rroot;
@@ -130,8 +219,10 @@ HD void fk_backward_sample(const float* ra, const float* oa, const float* bl, co
                 if (seg < 3) {
                     float x, y, z;
                     fk_local_angles(oa, f, seg, x, y, z);
-                    Rl[seg] = euler_xyz(x, y, z);
-                    Rg[seg] = m3_mul(Rpar, Rl[seg]);
+                    const int kind = fk_angle_kind(f, seg);
+                    sc[seg] = fk_sincos(kind, x, y, z);
+                    Rl[seg] = fk_local_rot(kind, sc[seg]);
+                    Rg[seg] = fk_chain_rot(kind, Rpar, Rl[seg]);
                 } else {
                     Rg[seg] = Rpar;
                 }
@@ -162,9 +253,7 @@ HD void fk_backward_sample(const float* ra, const float* oa, const float* bl, co
             if (seg == 3) continue;                   // tip: R_tip = R_parent, dRg flows through unchanged
             const M3& Rpar = (seg == 0) ? Rroot : Rg[seg - 1];
             const M3 dRl = m3_tmul(Rpar, dRg);
-            float x, y, z;
-            fk_local_angles(oa, f, seg, x, y, z);
-            fk_scatter_angles(g_oa, f, seg, euler_xyz_bwd(x, y, z, dRl));
+            fk_scatter_angles(g_oa, f, seg, fk_angle_grad(fk_angle_kind(f, seg), sc[seg], dRl));
             dRg = m3_mult(dRg, Rl[seg]);              // becomes the parent's dRg contribution
         }
         m3_acc(dRroot, dRg);

@@ -10,6 +10,7 @@
 // HBM-bound: 252 B in, 252 (+36) B out per hand; rows move as flat 128-byte warp accesses through a
 // pitch-63 shared tile, as in joint_epilogue.cu.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "hand_math.cuh"
 #include "../../include/mano_b200.h"
 
@@ -20,8 +21,8 @@ constexpr int HT_WARPS = 4;
 constexpr int JN = NOUTJ * 3;
 
 __device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, long long base, int n, int w, int lane) {
-    const float* s = src + base * w;
-    for (int i = lane; i < n * w; i += 32) tile[i] = s[i];
+    warp_copy_async(tile, src + base * w, n * w, lane);       // asynchronous requests, one wait (ptx.cuh)
+    cp_async_wait_all();
     __syncwarp();
 }
 __device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, long long base, int n, int w, int lane) {
@@ -54,7 +55,7 @@ __device__ __forceinline__ R3 step_frame(const R3& R, float ax, float ay) {
 
 __global__ void __launch_bounds__(HT_WARPS * 32)
 bone_rel_trafo_kernel(const float* __restrict__ xyz, int B, float* __restrict__ rel) {
-    __shared__ float tiles[HT_WARPS][32 * JN];
+    __shared__ __align__(16) float tiles[HT_WARPS][32 * JN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
     float* mine = tile + lane * JN;
@@ -107,7 +108,7 @@ bone_rel_trafo_kernel(const float* __restrict__ xyz, int B, float* __restrict__ 
 
 __global__ void __launch_bounds__(HT_WARPS * 32)
 bone_rel_trafo_inv_kernel(const float* __restrict__ rel, int B, float* __restrict__ xyz) {
-    __shared__ float tiles[HT_WARPS][32 * JN];
+    __shared__ __align__(16) float tiles[HT_WARPS][32 * JN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
     float* mine = tile + lane * JN;
@@ -156,7 +157,7 @@ __device__ __forceinline__ float atan2_reference(float y, float x) {
 __global__ void __launch_bounds__(HT_WARPS * 32)
 canonical_trafo_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ cond_right, int B,
                        float* __restrict__ can, float* __restrict__ rot) {
-    __shared__ float tiles[HT_WARPS][32 * JN];
+    __shared__ __align__(16) float tiles[HT_WARPS][32 * JN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
     float* mine = tile + lane * JN;

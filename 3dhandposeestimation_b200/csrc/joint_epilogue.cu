@@ -11,6 +11,7 @@
 // HBM-bound and tiny (252 B in, <= 672 B out per hand): one thread per hand, every global row moved as
 // contiguous 128-byte warp accesses through a per-warp shared-memory tile (pitch 63 = -1 mod 32 banks).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "fk_math.cuh"
 #include "../../include/mano_b200.h"
 
@@ -22,8 +23,8 @@ constexpr int JN = NOUTJ * 3;                      // 63 floats per hand
 
 // joints[base .. base + n) rows <-> tile (row pitch `w`, contiguous, so the copy is flat)
 __device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, long long base, int n, int w, int lane) {
-    const float* s = src + base * w;
-    for (int i = lane; i < n * w; i += 32) tile[i] = s[i];
+    warp_copy_async(tile, src + base * w, n * w, lane);       // asynchronous requests, one wait (ptx.cuh)
+    cp_async_wait_all();
     __syncwarp();
 }
 __device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, long long base, int n, int w, int lane) {
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(JE_WARPS * 32)
 joint_epilogue_forward_kernel(const float* __restrict__ joints, const float* __restrict__ scale, const float* __restrict__ root,
                               const float* __restrict__ K, int B, int swap, float* __restrict__ rel, float* __restrict__ xyz,
                               float* __restrict__ uv) {
-    __shared__ float tiles[JE_WARPS][32 * JN];
+    __shared__ __align__(16) float tiles[JE_WARPS][32 * JN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
     float* mine = tile + lane * JN;
@@ -101,7 +102,7 @@ joint_epilogue_backward_kernel(const float* __restrict__ joints, const float* __
                                const float* __restrict__ K, const float* __restrict__ g_rel, const float* __restrict__ g_xyz,
                                const float* __restrict__ g_uv, int B, int swap, float* __restrict__ g_joints,
                                float* __restrict__ g_scale, float* __restrict__ g_root) {
-    __shared__ float tiles[JE_WARPS][32 * JN];
+    __shared__ __align__(16) float tiles[JE_WARPS][32 * JN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
     float* mine = tile + lane * JN;

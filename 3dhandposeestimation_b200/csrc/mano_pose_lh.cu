@@ -17,6 +17,7 @@
 #include <cuda_fp16.h>
 #include "hand_math.cuh"
 #include "blend_tc.cuh"
+#include "ptx.cuh"
 
 namespace mb {
 namespace {
@@ -128,7 +129,11 @@ __device__ __forceinline__ void tips_rest_pose(const LhTips& T, const float (&be
 
 // coalesced copy of `n` consecutive floats (rows of up to 32 hands) into the warp's staging buffer
 __device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ src, int n, int lane) {
-    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+    warp_copy_async(dst, src, n, lane);                       // asynchronous; stage_wait() before the first read
+}
+__device__ __forceinline__ void stage_wait() {
+    cp_async_wait_all();
+    __syncwarp();
 }
 
 __device__ __forceinline__ V3 rest_joint(const LhConsts& C, int k, const float (&beta)[NB]) {
@@ -212,7 +217,7 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
         stage_in(s_coef, coeffs + h0 * nc, nh * nc, lane);
         stage_in(s_beta, betas + h0 * NB, nh * NB, lane);
         stage_in(s_rot, rot + h0 * 3, nh * 3, lane);
-        __syncwarp();
+        stage_wait();
         const int r = (int)(hand - h0);
         float beta[NB];
 #pragma unroll
@@ -310,7 +315,7 @@ pose_forward_lh_jo_kernel(const void* __restrict__ blob, int nc, const float* __
         stage_in(s_coef, coeffs + h0 * nc, nh * nc, lane);
         stage_in(s_beta, betas + h0 * NB, nh * NB, lane);
         stage_in(s_rot, rot + h0 * 3, nh * 3, lane);
-        __syncwarp();
+        stage_wait();
         const int r = (int)(hand - h0);
         float beta[NB];
 #pragma unroll
@@ -473,7 +478,7 @@ pose_backward_lh_kernel(const void* __restrict__ blob, int nc, const float* rot,
         stage_in(s_rot, rot + h0 * 3, nh * 3, lane);
         stage_in(s_gj, (FIT ? F.tgt : g_joints) + h0 * (NOUTJ * 3), nh * NOUTJ * 3, lane);   // 1856 + 2016 = 3872 floats < BUF_FLOATS
         if (FIT) stage_in(s_vis, F.vis + h0 * NOUTJ, nh * NOUTJ, lane);
-        __syncwarp();
+        stage_wait();
         float beta[NB];
 #pragma unroll
         for (int s = 0; s < NB; ++s) beta[s] = s_beta[r * NB + s];

@@ -61,4 +61,27 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     return p;
 }
 
+// ---- asynchronous global -> shared copies by the threads themselves (cp.async, LDGSTS) ----------------------------
+// A staging loop `tile[i] = src[i]` is one dependent global-load round trip per element and thread; with the few
+// warps per SM of the one-thread-per-hand kernels that chain was up to 40 % of their time.  cp.async requests are
+// issued back to back and waited for once.
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// one warp copies n consecutive floats (16-byte requests when both sides are 16-byte aligned); the caller waits
+// (cp_async_wait_all + __syncwarp) before anyone reads dst
+__device__ __forceinline__ void warp_copy_async(float* dst_smem, const float* __restrict__ src, int n, int lane) {
+    if ((((uintptr_t)src | (uintptr_t)smem_u32(dst_smem)) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = lane; i < n4; i += 32) cp_async16(dst_smem + 4 * i, src + 4 * i);
+        for (int i = 4 * n4 + lane; i < n; i += 32) cp_async4(dst_smem + i, src + i);
+    } else {
+        for (int i = lane; i < n; i += 32) cp_async4(dst_smem + i, src + i);
+    }
+}
+
 }  // namespace mb

@@ -5,6 +5,7 @@
 // (the same lines in network/Hand3DPosePriorNetwork.py:38-40 and the ground-truth side trainval_hand3DPose.py:389).
 // One thread per hand; the 21 x 3 rows go through a pitch-63 shared tile as flat 128-byte warp accesses.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "fk_math.cuh"
 #include "../../include/mano_b200.h"
 
@@ -15,8 +16,8 @@ constexpr int VP_WARPS = 4;
 constexpr int JN = NOUTJ * 3;
 
 __device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, long long base, int n, int w, int lane) {
-    const float* s = src + base * w;
-    for (int i = lane; i < n * w; i += 32) tile[i] = s[i];
+    warp_copy_async(tile, src + base * w, n * w, lane);       // asynchronous requests, one wait (ptx.cuh)
+    cp_async_wait_all();
     __syncwarp();
 }
 __device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, long long base, int n, int w, int lane) {
@@ -47,7 +48,7 @@ viewpoint_forward_kernel(const float* __restrict__ can, const float* __restrict_
                          const float* __restrict__ uz, const float* __restrict__ scale, const float* __restrict__ root,
                          const float* __restrict__ K, int B, float* __restrict__ rot, float* __restrict__ rel,
                          float* __restrict__ xyz, float* __restrict__ uv) {
-    __shared__ float tiles[VP_WARPS][32 * JN];
+    __shared__ __align__(16) float tiles[VP_WARPS][32 * JN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
     float* mine = tile + lane * JN;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(VP_WARPS * 32)
 viewpoint_backward_kernel(const float* __restrict__ can, const float* __restrict__ ux, const float* __restrict__ uy,
                           const float* __restrict__ uz, const float* __restrict__ g_rot, const float* __restrict__ g_rel, int B,
                           float* __restrict__ g_can, float* __restrict__ g_ux, float* __restrict__ g_uy, float* __restrict__ g_uz) {
-    __shared__ float tiles[VP_WARPS][32 * JN];
+    __shared__ __align__(16) float tiles[VP_WARPS][32 * JN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = tiles[warp];
     float* mine = tile + lane * JN;
