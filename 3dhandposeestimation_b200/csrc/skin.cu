@@ -100,18 +100,24 @@ __device__ __forceinline__ void stage_prog(SkinProg& P, const void* blob) {
     const int* eb = blob_ptr<int>(blob, L.sk_ent_bone);
     const float* ew = blob_ptr<float>(blob, L.sk_ent_w);
     const uint8_t* vl = blob_ptr<uint8_t>(blob, L.sk_vloc);
-    for (int i = threadIdx.x; i <= SK_NBLK; i += blockDim.x) P.blk_ptr[i] = bp[i];
+    // asynchronous copies (cp.async): the ~6 000 words of the program arrive in one round trip instead of ~24
+    // dependent ones per thread — it matters for the small-batch launches, where the sweep itself is 40-80 us
+    auto acopy = [](void* dst, const void* src) {
+        cp_async4(reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(src));
+    };
+    for (int i = threadIdx.x; i <= SK_NBLK; i += blockDim.x) acopy(&P.blk_ptr[i], &bp[i]);
     const int ne = bp[SK_NBLK];
-    for (int i = threadIdx.x; i < ne; i += blockDim.x) P.ent_code[i] = eb[i];
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) acopy(&P.ent_code[i], &eb[i]);
     const int* cm = blob_ptr<int>(blob, L.sk_cmd);
     const int ncmd = cm[0];
-    for (int i = threadIdx.x; i <= ncmd; i += blockDim.x) P.cmd[i] = cm[i];
+    for (int i = threadIdx.x; i <= ncmd; i += blockDim.x) acopy(&P.cmd[i], &cm[i]);
     const int* sp = blob_ptr<int>(blob, L.sk_split);
-    for (int i = threadIdx.x; i < SK_NSEG * 8; i += blockDim.x) (&P.split[0][0])[i] = sp[i];
-    for (int i = threadIdx.x; i < ne * SK_BV; i += blockDim.x) (&P.ent_w[0][0])[i] = ew[i];
+    for (int i = threadIdx.x; i < SK_NSEG * 8; i += blockDim.x) acopy(&(&P.split[0][0])[i], &sp[i]);
+    for (int i = threadIdx.x; i < ne * SK_BV; i += blockDim.x) acopy(&(&P.ent_w[0][0])[i], &ew[i]);
     // padding positions (only in the last block, whose segment uses 10 of its 16 vertex slots) are
     // parked on the last slot of the tile: written / read like any vertex, never stored, weights all zero
     for (int i = threadIdx.x; i < SK_NPOS; i += blockDim.x) P.voff[i] = (vl[i] == 255 ? PAD_SLOT : vl[i]) * (3 * TP);
+    cp_async_wait_all();                                      // the callers' __syncthreads() follows
 }
 
 __device__ __forceinline__ void load_w(const SkinProg& P, int e, float (&w)[SK_BV]) {
