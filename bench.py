@@ -522,21 +522,28 @@ def main():
         if os.environ.get("MANO_B200_BENCH_DEBUG"):
             sys.stderr.write(f"before e2e: allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB\n")
         h_in = [torch.from_numpy(a).pin_memory() for a in synth_inputs(H, 555 + rank)]
-        h_out = [torch.empty(H, n, dtype=torch.float32).pin_memory() for n in (3, 45, 10)]
-        h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        h_out2 = [[torch.empty(H, n, dtype=torch.float32).pin_memory() for n in (3, 45, 10)] for _ in range(2)]
+        h_loss2 = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
 
         # The step is pipelined the way a host-fed training loop would be: the batch is cut into chunks,
         # each chunk's host->device copy, ManoLayer forward, autograd backward and device->host copy
-        # run on one of three CUDA streams, so the PCIe copies of one chunk overlap the kernels of another.
-        n_chunks = 8 if H >= 8 * 4096 else 1
+        # run on one of two CUDA streams, so the PCIe copies of one chunk overlap the kernels of another
+        # (measured: 4 chunks on 2 streams 50.0 M hands/s, 8 on 3 46.0 M — a third stream only makes the
+        # chunks' kernels compete for the SMs) —
+        # across step boundaries too (a loader that prefetches the next batch): consecutive steps are ordered
+        # per stream only and write their results to alternating pinned buffers; every step still copies all
+        # of its inputs in and all of its gradients out inside the timed region.
+        n_chunks = int(os.environ.get("MANO_B200_E2E_CHUNKS", "4")) if H >= 8 * 4096 else 1
         Hc = (H + n_chunks - 1) // n_chunks
-        side = [torch.cuda.Stream(device=dev) for _ in range(min(3, n_chunks))]
+        side = [torch.cuda.Stream(device=dev) for _ in range(min(int(os.environ.get("MANO_B200_E2E_STREAMS", "2")), n_chunks))]
+
+        step_no = [0]
 
         def e2e_step():
-            main = torch.cuda.current_stream(dev)
+            h_out, h_loss = h_out2[step_no[0] & 1], h_loss2[step_no[0] & 1]
+            step_no[0] += 1
             for c in range(n_chunks):
                 st = side[c % len(side)]
-                st.wait_stream(main)
                 with torch.cuda.stream(st):
                     sl = slice(c * Hc, min(H, (c + 1) * Hc))
                     d = [t[sl].to(dev, non_blocking=True).requires_grad_() for t in h_in]
@@ -549,26 +556,32 @@ def main():
                     for t in (verts, joints, gv_keep, gj_keep):
                         t.record_stream(st)
                     del verts, joints, d
-            for st in side:
-                main.wait_stream(st)
             if os.environ.get("MANO_B200_BENCH_DEBUG"):
                 sys.stderr.write(f"e2e step: allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB, "
                                  f"reserved {torch.cuda.memory_reserved(dev) / 2**30:.1f} GiB\n")
 
+        def join_side():
+            main = torch.cuda.current_stream(dev)
+            for st in side:
+                main.wait_stream(st)
+
         n_e2e = max(3, min(args.steps, 10))
+        sync_all()                                            # the side streams start after everything above
         for _ in range(2):
             e2e_step()
+        join_side()
         sync_all()
         e0.record()
         for _ in range(n_e2e):
             e2e_step()
+        join_side()                                           # the last step's copies are inside the timed region
         e1.record()
         sync_all()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
         e2e = {"value": world * H / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * 58 * 4,
                "d2h_bytes_per_step": H * 58 * 4 + 4, "ms_per_step": ms_e2e, "steps": n_e2e,
                "api": "ManoLayer.forward + autograd backward; pinned host params in, pinned host grads out; "
-                      f"{n_chunks} chunks over {len(side)} CUDA streams"}
+                      f"{n_chunks} chunks over {len(side)} CUDA streams, steps pipelined per stream (alternating pinned result buffers)"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(model)
