@@ -138,11 +138,21 @@ def synth_inputs(H, seed):
     return rot, pose, beta
 
 
-def cpu_baseline(model, budget_s=12.0, chunk=256):
+def cpu_baseline(model, kept=None, budget_s=12.0, chunk=256):
     """The oracle (numpy port of the reference's algorithm, fp32) fwd+bwd on the host cores:
-    repeated `chunk`-hand batches of the same synthetic workload for about `budget_s` seconds."""
+    repeated `chunk`-hand batches of the same synthetic workload for about `budget_s` seconds.  `kept`: four hands of
+    the GPU arm's last step (inputs, outputs, gradients) — checked against the fp64 oracle here, reported as `parity`."""
     import numpy as np
     from oracle import mano_oracle
+
+    parity = None
+    if kept is not None:
+        ov, oj = mano_oracle.mano_forward(model, kept["rot"], kept["pose"], kept["beta"])
+        og = mano_oracle.mano_backward(model, kept["rot"], kept["pose"], kept["beta"], kept["gv"], kept["gj"])
+        parity = {"verts_max_abs_err_m": float(np.abs(kept["verts"] - ov).max()),
+                  "joints_max_abs_err_m": float(np.abs(kept["joints"] - oj).max()),
+                  "grad_rel_err": max(float(np.abs(kept[k] - w).max() / np.abs(w).max())
+                                      for k, w in zip(("g_rot", "g_pose", "g_beta"), og))}
 
     rot, pose, beta = synth_inputs(chunk, 4242)
     rs = np.random.RandomState(1)
@@ -157,7 +167,7 @@ def cpu_baseline(model, budget_s=12.0, chunk=256):
         if dt >= budget_s:
             break
     return {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{done} hands in {chunk}-hand batches, numpy fp32 oracle fwd+bwd, {dt:.1f} s"}
+            "sample": f"{done} hands in {chunk}-hand batches, numpy fp32 oracle fwd+bwd, {dt:.1f} s"}, parity
 
 
 def run_reference_arm(args, rank, world):
@@ -491,23 +501,16 @@ def main():
                           "v_posed_t per hand and sits 1.2x above its HBM-write floor (the single-product mode reaches it)"}
     step_gbs = (BYTES_FWD + BYTES_BWD) * H / (ms_per_step * 1e-3) / 1e9
 
-    # ---- parity spot check in the same run (checker only) -------------------------------
+    # ---- parity spot check: four hands of the last timed step are kept (numpy) for the CPU-baseline leg, the one
+    # place this script runs oracle/ in the product arm — as the checker of those four hands and as the timed baseline
     parity = None
     cpu = None
-    if rank == 0:
-        from oracle import mano_oracle
-
+    kept = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         s = sets[(args.steps - 1) % nsets]
         idx = np.array([0, 1, H // 2, H - 1]) if H >= 4 else np.arange(H)
         tidx = torch.from_numpy(idx).to(dev)
-        ov, oj = mano_oracle.mano_forward(model, s["rot"][tidx].cpu().numpy(), s["pose"][tidx].cpu().numpy(),
-                                          s["beta"][tidx].cpu().numpy())
-        og = mano_oracle.mano_backward(model, s["rot"][tidx].cpu().numpy(), s["pose"][tidx].cpu().numpy(),
-                                       s["beta"][tidx].cpu().numpy(), s["gv"][tidx].cpu().numpy(), s["gj"][tidx].cpu().numpy())
-        parity = {"verts_max_abs_err_m": float(np.abs(s["verts"][tidx].cpu().numpy() - ov).max()),
-                  "joints_max_abs_err_m": float(np.abs(s["joints"][tidx].cpu().numpy() - oj).max()),
-                  "grad_rel_err": max(float(np.abs(s[k][tidx].cpu().numpy() - w).max() / np.abs(w).max())
-                                      for k, w in zip(("g_rot", "g_pose", "g_beta"), og))}
+        kept = {k: s[k][tidx].cpu().numpy() for k in ("rot", "pose", "beta", "gv", "gj", "verts", "joints", "g_rot", "g_pose", "g_beta")}
     # ---- end to end through the public nn.Module API with host buffers ------------------
     e2e = None
     if not args.no_e2e:
@@ -584,7 +587,7 @@ def main():
                       f"{n_chunks} chunks over {len(side)} CUDA streams, steps pipelined per stream (alternating pinned result buffers)"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(model)
+        cpu, parity = cpu_baseline(model, kept)
 
     if world > 1:
         dist.barrier()
