@@ -252,6 +252,66 @@ def run_secondary(args, pkg, layer, dev, rank, world, dist):
                 "loss_first": loss0, "loss_last": loss1, "l2_term_first_m2": l2_0, "l2_term_last_m2": l2_1,
                 "note": "loss = masked L2 + the reference's batch-global Frobenius regulariser (loss.py:113-117), which grows with "
                         "sqrt(batch) and dominates at 2^20 hands; the L2 term is reported separately", "data": "synthetic"}
+    if args.workload == "aux":
+        # the joint epilogue, keypoint re-parameterisations, viewpoint epilogue and hand-mask loss,
+        # each timed alone through the C ABI on H hands (every tensor is larger than L2) against the HBM roofline
+        cabi = pkg._cabi
+        lib = cabi.lib()
+        peaks = load_peaks()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        P = lambda t: t.data_ptr()
+        g = torch.Generator(device=dev).manual_seed(5 + rank)
+        R = lambda *shape: torch.randn(*shape, device=dev, generator=g)
+        joints = R(H, 21, 3) * .05
+        joints[:, 0] = 0
+        xyz_in = (R(H, 21, 3) * .5 + torch.arange(21, device=dev)[:, None] * torch.tensor([.09, .06, .03], device=dev)).contiguous()
+        scale = torch.rand(H, 1, device=dev, generator=g) * .05 + .02
+        root = R(H, 3) * .05 + torch.tensor([0, 0, .6], device=dev)
+        K = torch.tensor([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1.]], device=dev).repeat(H, 1, 1).contiguous()
+        o63 = [torch.empty(H, 21, 3, device=dev) for _ in range(3)]
+        o42 = torch.empty(H, 21, 2, device=dev)
+        g63 = [R(H, 21, 3) for _ in range(2)]
+        g42 = R(H, 21, 2) * 1e-3
+        o9 = torch.empty(H, 3, 3, device=dev)
+        g9 = R(H, 3, 3)
+        u = [R(H) for _ in range(3)]
+        gu = [torch.empty(H, device=dev) for _ in range(3)]
+        gs, gr = torch.empty(H, 1, device=dev), torch.empty(H, 3, device=dev)
+        Hm = min(H, 65536)                                       # hand-mask loss: [Hm][64][64] fp32 masks = 1 GB at 65 536
+        mask = (torch.rand(Hm, 64, 64, device=dev, generator=g) < .4).float()
+        uvp, uvg = torch.rand(Hm, 21, 2, device=dev, generator=g) * 70 - 3, torch.rand(Hm, 21, 2, device=dev, generator=g) * 70 - 3
+        acc, out1 = torch.zeros(2, dtype=torch.float64, device=dev), torch.zeros((), device=dev)
+        cases = [
+            ("joint_epilogue_forward", 252 + 4 + 12 + 36 + 252 + 252 + 168, H,
+             lambda: lib.mb_joint_epilogue_forward(P(joints), P(scale), P(root), P(K), H, 0, P(o63[0]), P(o63[1]), P(o42), st)),
+            ("joint_epilogue_backward", 252 + 52 + 252 + 252 + 168 + 252 + 16, H,
+             lambda: lib.mb_joint_epilogue_backward(P(joints), P(scale), P(root), P(K), P(g63[0]), P(g63[1]), P(g42), H, 0, P(o63[2]),
+                                                    P(gs), P(gr), st)),
+            ("bone_rel_trafo", 504, H, lambda: lib.mb_bone_rel_trafo(P(xyz_in), H, P(o63[0]), st)),
+            ("bone_rel_trafo_inv", 504, H, lambda: lib.mb_bone_rel_trafo_inv(P(o63[0]), H, P(o63[1]), st)),
+            ("canonical_trafo", 540, H, lambda: lib.mb_canonical_trafo(P(xyz_in), None, H, P(o63[2]), P(o9), st)),
+            ("viewpoint_forward", 252 + 12 + 36 + 252, H,
+             lambda: lib.mb_viewpoint_forward(P(xyz_in), P(u[0]), P(u[1]), P(u[2]), None, None, None, H, P(o9), P(o63[0]), None, None, st)),
+            ("viewpoint_backward", 252 + 12 + 36 + 252 + 252 + 12, H,
+             lambda: lib.mb_viewpoint_backward(P(xyz_in), P(u[0]), P(u[1]), P(u[2]), P(g9), P(g63[0]), H, P(o63[1]), P(gu[0]), P(gu[1]),
+                                               P(gu[2]), st)),
+            ("hand_mask_loss", 2 * 168 + 42 * 32, Hm,
+             lambda: lib.mb_hand_mask_loss(P(uvp), P(uvg), P(mask), cabi.VIS_F32, Hm, 21, 64, 64, P(acc), P(out1), st)),
+        ]
+        res = {}
+        for name, nbytes, n, fn in cases:
+            def call(fn=fn, name=name):
+                cabi.check(fn(), name)
+            ms = timed(call, args.steps)
+            gbs = nbytes * n / (ms * 1e-3) / 1e9
+            res[name] = {"ms": ms, "items": n, "bytes_per_item": nbytes, "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                         "frac": gbs / peaks["hbm_gbs"], "bound": "hbm"}
+        return {"metric": "SURVEY 8(f) kernels, each alone (hands/s of the joint epilogue forward + backward)",
+                "value": world * H / ((res["joint_epilogue_forward"]["ms"] + res["joint_epilogue_backward"]["ms"]) * 1e-3), "unit": "hands/s",
+                "n_gpus": world, "steps": args.steps, "ms_per_step": res["joint_epilogue_forward"]["ms"] + res["joint_epilogue_backward"]["ms"],
+                "higher_is_better": True, "scaling": "weak", "config": {"workload": f"aux_kernels_{H}_hands_per_gpu",
+                "note": "hand_mask_loss: bytes = 2 x 21 uv pairs + 42 sampled 32-byte sectors per hand (gather)"},
+                "roofline": res, "data": "synthetic"}
     # config 3: RHD 21-joint FK forward + backward + visible-joint MPJPE, rotating buffer sets (the working set of one
     # 65 536-sample call fits in L2)
     B = 65536 if args.hands == (1 << 20) else args.hands
@@ -355,7 +415,7 @@ def main():
     ap.add_argument("--hands", type=int, default=1 << 20, help="hands per GPU per step")
     ap.add_argument("--mode", default=os.environ.get("MANO_B200_MODE", "f16x3"))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mano", choices=["mano", "fit", "fk"],
+    ap.add_argument("--workload", default="mano", choices=["mano", "fit", "fk", "aux"],
                     help="mano (default, the contract line) | fit = BASELINE config 5 fitting loop | fk = config 3 FK fwd+bwd+MPJPE")
     ap.add_argument("--ref-hands", type=int, default=512, help="hands per step of the --impl reference arm")
     ap.add_argument("--rotate", type=int, default=1, help="number of distinct buffer sets cycled through (small --hands)")
