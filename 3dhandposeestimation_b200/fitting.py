@@ -109,13 +109,15 @@ class ManoFitter:
         g[1] = self.pose.double().square().sum()
         g[2] = self.beta.double().square().sum()
         reduce_partials(g, self.group)
-        self._vis_key = (keypoint_vis.data_ptr(), keypoint_vis._version, tuple(keypoint_vis.shape))
         self._param_version = self.params._version
 
-    def _step_fused(self, tgt, vis, stream):
+    def _step_fused(self, tgt, vis, vis_key, stream):
         lib = _cabi.lib()
-        if (self._vis_key != (vis.data_ptr(), vis._version, tuple(vis.shape)) or self._param_version != self.params._version):
+        # vis_key identifies the mask the CALLER passed (a bool / non-contiguous mask is converted to a fresh fp32
+        # tensor on every call, so the converted tensor's address says nothing)
+        if self._vis_key != vis_key or self._param_version != self.params._version:
             self.refresh(vis)
+            self._vis_key = vis_key
         self.steps += 1
         _cabi.check(lib.mb_mano_fit_step(self.layer._blob.data_ptr(), self.nc, self.params.data_ptr(), self.exp_avg.data_ptr(),
                                          self.exp_avg_sq.data_ptr(), tgt.data_ptr(), vis.data_ptr(), self.B, self.layer._mode,
@@ -145,7 +147,8 @@ class ManoFitter:
         vis = keypoint_vis if (keypoint_vis.dtype == torch.float32 and keypoint_vis.is_contiguous()) else \
             keypoint_vis.to(torch.float32).contiguous()
         if self.fused:
-            return self._step_fused(tgt, vis, stream)
+            key = (keypoint_vis.data_ptr(), keypoint_vis._version, tuple(keypoint_vis.shape), keypoint_vis.dtype)
+            return self._step_fused(tgt, vis, key, stream)
         # 1. joints-only forward (no 778-vertex contraction)
         _cabi.check(lib.mb_mano_forward(blob, nc, self.rot.data_ptr(), self.pose.data_ptr(), self.beta.data_ptr(), B, mode,
                                         None, self.joints.data_ptr(), None, 0, stream), "mb_mano_forward")

@@ -650,8 +650,8 @@ def test_adam_step_matches_torch(pkg, cuda_device):
 
 
 # ------------------------------------------------------------------------ fitting loop
-@pytest.mark.parametrize("fused,B", [(True, 64), (False, 64), (True, 8231)])
-def test_fitting_loop_matches_oracle_adam(pkg, synth_model, cuda_device, fused, B):
+@pytest.mark.parametrize("fused,B,nc", [(True, 64, 45), (False, 64, 45), (True, 8231, 45), (True, 100, 10)])
+def test_fitting_loop_matches_oracle_adam(pkg, synth_model, cuda_device, fused, B, nc):
     """BASELINE config 5 parity: 64 hands x 10 Adam iterations against the oracle's
     objective (L2Loss + regulariser) and gradients with a numpy Adam (torch.optim.Adam semantics) — as one
     kernel per iteration (mb_mano_fit_step) and as the separate forward / reduce / backward / Adam kernels;
@@ -659,7 +659,7 @@ def test_fitting_loop_matches_oracle_adam(pkg, synth_model, cuda_device, fused, 
     import torch
 
     fitting = importlib.import_module("3dhandposeestimation_b200.fitting")
-    nc, iters = 45, 10
+    iters = 10
     rs = np.random.RandomState(5)
     hidden = mano_inputs(B, nc, seed=77, pose_scale=1.0)
     _, tj = mo.mano_forward(synth_model, *hidden)
