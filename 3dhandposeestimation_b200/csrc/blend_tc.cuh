@@ -12,7 +12,10 @@ constexpr int TC_K = 160;                 // padded feature length
 constexpr int TC_K_REAL = 145;            // beta(10) + pose feature(135); v_template is added in the epilogue
 constexpr int TC_K_CHUNK = 32;            // K elements per pipeline stage
 constexpr int TC_K_CHUNKS = TC_K / TC_K_CHUNK;
-constexpr int TC_MRES_MIN_TILES = 2 * NUM_SMS;   // hand tiles from which the hand-tile-resident forward kernel is used
+// hand tiles from which the hand-tile-resident forward kernel is used — the measured crossover (blend_fwd in us, resident
+// hand tile vs resident basis): 4 096 hands 43.5 / 29.2, 6 144 43.6 / 37.4, 8 192 45.1 / 45.6, 12 288 45.5 / 59.9,
+// 18 944 48.0 / 86.5, 65 536 164 / 262
+constexpr int TC_MRES_MIN_TILES = 64;
 constexpr int TC_FEAT_SCALE_LOG2 = 4;     // features are pre-scaled by 2^4 before the fp16 split
 
 // UMMA canonical K-major no-swizzle blocks: [row-group][k-group (4 per chunk)][8 rows][8 halves]

@@ -552,7 +552,7 @@ def main():
     roofline = dict(lbs_bwd_roof if dominant == "lbs_bwd" else lbs_fwd_roof, dominant_stage=dominant)
     blend_ms = stages["blend_fwd"]["ms"]
     blend_tflops = FLOP_BLEND * H / (blend_ms * 1e-3) / 1e12
-    blend_kernel = "blend_tc_forward_mres_kernel" if (H + 127) // 128 >= 296 else "blend_tc_forward_kernel"
+    blend_kernel = "blend_tc_forward_mres_kernel" if (H + 127) // 128 >= 64 else "blend_tc_forward_kernel"
     blend_roof = {"kernel": blend_kernel, "bound": "tensor", "achieved": blend_tflops, "peak": peaks["bf16_tflops_sustained"],
                   "unit": "TFLOP/s", "frac": blend_tflops / peaks["bf16_tflops_sustained"],
                   "algorithmic_flop_per_hand": FLOP_BLEND, "avg_launch_ms": blend_ms, "mode": args.mode,

@@ -89,8 +89,8 @@ def test_mano_matches_reference_golden(pkg, synth_model, cuda_device, name, nc, 
 def test_mano_matches_fp64_oracle(pkg, synth_model, cuda_device, B, nc, mode):
     """Ragged sizes (partial hand groups, partial tcgen05 tiles) up to BASELINE config 2 (B=4096,
     nc=10, the Resnet50MANO3DHandPose head workload).  B >= 8192 in the tensor-core modes runs the
-    one-thread-per-hand pose kernels, below that the one-warp-per-hand kernels; from 37 888 hands (296 hand
-    tiles) the blend forward is the hand-tile-resident kernel (several hand tiles per CTA at 77 777)."""
+    one-thread-per-hand pose kernels, below that the one-warp-per-hand kernels; from 8 192 hands (64 hand
+    tiles) the blend forward is the hand-tile-resident kernel (several hand tiles per CTA from 18 945)."""
     rot, pose, beta = mano_inputs(B, nc, seed=B + nc)
     layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc, mode=mode)
     trot, tpose, tbeta = to_dev(cuda_device, rot, pose, beta, grad=True)
