@@ -37,4 +37,20 @@ __attribute__((visibility("default"))) void hc_fk_backward(int B, const float* r
                            g_xyz ? g_xyz + b * 63 : nullptr, g_uv ? g_uv + b * 42 : nullptr,
                            g_ra + b * 3, g_oa + b * 23, g_bl + b * 20);
 }
+// kind 0..3 (xyz / xy / x / y): the specialised chain step against euler_xyz + m3_mul on the same inputs
+__attribute__((visibility("default"))) void hc_fk_chain(int kind, const float* A, const float* ang, float* special, float* general) {
+    M3 a; for (int i = 0; i < 9; ++i) a.m[i] = A[i];
+    const float x = kind == 3 ? 0.f : ang[0], y = kind == 2 ? 0.f : ang[1], z = kind == 0 ? ang[2] : 0.f;
+    const M3 s = fk_chain_rot(kind, a, fk_local_rot(kind, fk_sincos(kind, x, y, z)));
+    const M3 g = m3_mul(a, euler_xyz(x, y, z));
+    for (int i = 0; i < 9; ++i) { special[i] = s.m[i]; general[i] = g.m[i]; }
+}
+__attribute__((visibility("default"))) void hc_fk_angle_grad(int kind, const float* ang, const float* dR, float* special, float* general) {
+    M3 d; for (int i = 0; i < 9; ++i) d.m[i] = dR[i];
+    const float x = kind == 3 ? 0.f : ang[0], y = kind == 2 ? 0.f : ang[1], z = kind == 0 ? ang[2] : 0.f;
+    const V3 s = fk_angle_grad(kind, fk_sincos(kind, x, y, z), d);
+    const V3 g = euler_xyz_bwd(x, y, z, d);
+    special[0] = s.x; special[1] = s.y; special[2] = s.z;
+    general[0] = g.x; general[1] = g.y; general[2] = g.z;
+}
 }

@@ -177,6 +177,25 @@ def test_device_fk_math_on_host(hostlib, swap):
             assert np.abs(got - want).max() / np.abs(want).max() < 1e-4
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_fk_specialised_rotations_equal_the_general_form(hostlib, kind):
+    """fk_math.cuh chains local rotations by their zero structure (xyz / xy / x / y angles): the result must be the
+    SAME floats as euler_xyz + m3_mul (sin 0, cos 0 exact; zero products add nothing in the fmaf chains), and the
+    specialised angle gradients must agree with euler_xyz_bwd on the angles that exist."""
+    rs = np.random.RandomState(10 + kind)
+    live = {0: [0, 1, 2], 1: [0, 1], 2: [0], 3: [1]}[kind]
+    for _ in range(200):
+        A = rs.randn(9).astype(np.float32)
+        ang = ((rs.rand(3) - .5) * 8).astype(np.float32)
+        sp, ge = np.zeros(9, np.float32), np.zeros(9, np.float32)
+        hostlib.hc_fk_chain(kind, P(A), P(ang), P(sp), P(ge))
+        assert np.array_equal(sp, ge), (kind, sp, ge)
+        dR = rs.randn(9).astype(np.float32)
+        gs, gg = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        hostlib.hc_fk_angle_grad(kind, P(ang), P(dR), P(gs), P(gg))
+        assert np.abs(gs[live] - gg[live]).max() <= 4e-6 * max(1.0, np.abs(gg[live]).max())
+
+
 def _pack_host_blob(pkg, model, nc=45):
     lib = pkg.load_library()
     packed = pkg.assets.pack_mano(model, nc)
