@@ -104,6 +104,18 @@ def test_mano_layer_interface_matches_reference(pkg, synth_model):
         pkg.MPJPE()(torch.zeros(1, 21, 3), torch.zeros(1, 21, 3), torch.ones(1, 21, 1))
     with pytest.raises(pkg.ManoB200Error):
         pkg.batch_project_xyz_to_uv(torch.zeros(1, 21, 3), torch.eye(3)[None])
+    # ... and so do the drop-ins of the rows either side of the path
+    z21 = torch.zeros(1, 21, 3)
+    for call in (lambda: pkg.match_mano_to_RHD(z21, torch.ones(1, 1), torch.zeros(1, 3)),
+                 lambda: pkg.mano_joints_to_rhd_uv(z21, torch.ones(1, 1), torch.zeros(1, 3), torch.eye(3)[None]),
+                 lambda: pkg.bone_rel_trafo(z21), lambda: pkg.bone_rel_trafo_inv(z21), lambda: pkg.canonical_trafo(z21),
+                 lambda: pkg.flip_right_hand(z21, torch.ones(1, dtype=torch.bool)),
+                 lambda: pkg._get_rot_mat(torch.zeros(1, 1), torch.zeros(1, 1), torch.zeros(1, 1)),
+                 lambda: pkg.viewpoint_transform(z21, torch.zeros(1, 1), torch.zeros(1, 1), torch.zeros(1, 1)),
+                 lambda: pkg.compute_hand_mask_loss(torch.zeros(1, 21, 2), torch.zeros(1, 21, 2), torch.zeros(1, 8, 8)),
+                 lambda: pkg.L2Loss()(z21, z21, torch.ones(1, 21, 1))):
+        with pytest.raises(pkg.ManoB200Error):
+            call()
 
 
 def test_missing_library_fails_loudly(pkg, monkeypatch):
