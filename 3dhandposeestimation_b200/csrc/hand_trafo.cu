@@ -20,17 +20,6 @@ namespace {
 constexpr int HT_WARPS = 4;
 constexpr int JN = NOUTJ * 3;
 
-__device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, long long base, int n, int w, int lane) {
-    warp_copy_async(tile, src + base * w, n * w, lane);       // asynchronous requests, one wait (ptx.cuh)
-    cp_async_wait_all();
-    __syncwarp();
-}
-__device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, long long base, int n, int w, int lane) {
-    __syncwarp();
-    float* d = dst + base * w;
-    for (int i = lane; i < n * w; i += 32) d[i] = tile[i];
-    __syncwarp();
-}
 
 struct R3 { float m[9]; };
 __device__ __forceinline__ R3 r3_identity() { return {{1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}}; }

@@ -22,17 +22,6 @@ constexpr int JE_WARPS = 4;
 constexpr int JN = NOUTJ * 3;                      // 63 floats per hand
 
 // joints[base .. base + n) rows <-> tile (row pitch `w`, contiguous, so the copy is flat)
-__device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, long long base, int n, int w, int lane) {
-    warp_copy_async(tile, src + base * w, n * w, lane);       // asynchronous requests, one wait (ptx.cuh)
-    cp_async_wait_all();
-    __syncwarp();
-}
-__device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, long long base, int n, int w, int lane) {
-    __syncwarp();
-    float* d = dst + base * w;
-    for (int i = lane; i < n * w; i += 32) d[i] = tile[i];
-    __syncwarp();
-}
 __device__ __forceinline__ int je_slot(int i, int swap) { return i == 0 ? 0 : fk_out_slot(i, swap); }
 
 __global__ void __launch_bounds__(JE_WARPS * 32)

@@ -84,4 +84,18 @@ __device__ __forceinline__ void warp_copy_async(float* dst_smem, const float* __
     }
 }
 
+// rows of up to 32 samples <-> a per-warp shared tile as flat coalesced accesses (n samples of w floats, dense pitch w):
+// used by the one-thread-per-sample epilogue kernels (joint_epilogue.cu, hand_trafo.cu, viewpoint.cu)
+__device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, long long base, int n, int w, int lane) {
+    warp_copy_async(tile, src + base * w, n * w, lane);       // asynchronous requests, one wait
+    cp_async_wait_all();
+    __syncwarp();
+}
+__device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, long long base, int n, int w, int lane) {
+    __syncwarp();
+    float* d = dst + base * w;
+    for (int i = lane; i < n * w; i += 32) d[i] = tile[i];
+    __syncwarp();
+}
+
 }  // namespace mb
