@@ -9,7 +9,8 @@ The directory name is not a Python identifier; import it with
 ``importlib.import_module("3dhandposeestimation_b200")`` or through the
 ``handpose_b200`` alias module at the repository root.
 """
-from . import assets, fitting  # noqa: F401
+from . import assets, dropin, fitting  # noqa: F401
+from .dropin import install_into_reference  # noqa: F401
 from ._cabi import ManoB200Error, lib as load_library  # noqa: F401
 from .criterions import L2Loss, MPJPE, compute_hand_mask_loss, compute_regularization_loss  # noqa: F401
 from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv, mano_joints_to_rhd_uv, match_mano_to_RHD  # noqa: F401
@@ -19,4 +20,4 @@ from .viewpoint import _get_rot_mat, viewpoint_transform  # noqa: F401
 
 __all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "match_mano_to_RHD", "mano_joints_to_rhd_uv",
            "bone_rel_trafo", "bone_rel_trafo_inv", "canonical_trafo", "flip_right_hand", "mirror_left_hand", "_get_rot_mat", "viewpoint_transform", "MPJPE", "L2Loss",
-           "compute_regularization_loss", "compute_hand_mask_loss", "ManoB200Error", "assets", "load_library"]
+           "compute_regularization_loss", "compute_hand_mask_loss", "install_into_reference", "ManoB200Error", "assets", "load_library"]

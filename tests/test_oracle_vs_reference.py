@@ -152,3 +152,35 @@ def test_viewpoint_live(ref):
     oR, orel = tro.viewpoint_forward(can.numpy(), *[t.numpy() for t in u])
     assert np.abs(oR - R.numpy()).max() < 1e-6
     assert np.abs(orel - torch.matmul(can, R).numpy()).max() < 2e-6
+
+
+def test_dropin_rebinds_the_reference_in_place(ref):
+    """dropin.install_into_reference(): the reference's own modules — and the heads that imported the symbols by name —
+    end up holding the B200 classes / functions; uninstall() restores the originals."""
+    import importlib
+    import sys
+
+    pkg = importlib.import_module("3dhandposeestimation_b200")
+    import network.sub_modules.MANOLayer as ML
+    import network.sub_modules.forwardKinematicsLayer as FKL
+    import network.sub_modules.resnetMANO as RM            # holds `ManoLayer` by `from ... import` (resnetMANO.py)
+    import utils.general as UG
+    import utils.relative_trafo as RT
+    import criterions.loss as CL
+    import criterions.metrics as CM
+    orig = (ML.ManoLayer, FKL.ForwardKinematics, UG._get_rot_mat, RT.bone_rel_trafo, CL.L2Loss, CM.MPJPE)
+    assert RM.ManoLayer is ML.ManoLayer
+    try:
+        done = pkg.install_into_reference()
+        assert ML.ManoLayer is pkg.ManoLayer and RM.ManoLayer is pkg.ManoLayer
+        assert FKL.ForwardKinematics is pkg.ForwardKinematics and UG._get_rot_mat is pkg._get_rot_mat
+        assert RT.bone_rel_trafo is pkg.bone_rel_trafo and CL.L2Loss is pkg.L2Loss and CM.MPJPE is pkg.MPJPE
+        assert CL.LossCalculation is not None                 # the rest of the reference module is untouched
+        assert "network.sub_modules.MANOLayer.ManoLayer" in done
+        assert pkg.install_into_reference() == []             # idempotent
+    finally:
+        assert pkg.dropin.uninstall() > 0
+    assert (ML.ManoLayer, FKL.ForwardKinematics, UG._get_rot_mat, RT.bone_rel_trafo, CL.L2Loss, CM.MPJPE) == orig
+    assert RM.ManoLayer is orig[0]
+    # the oracle helper's handle on the live reference was never touched
+    assert ref.ManoLayer is orig[0]
