@@ -54,8 +54,10 @@ SIGNATURES = {
     "mb_mirror_hand": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "mb_viewpoint_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "mb_viewpoint_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
-    "mb_masked_joint_reduce": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p]),
-    "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
+    "mb_masked_joint_reduce": (_i, [_p, _p, _p, _i, _ll, _i, _i, _p, _p, _p]),
+    "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p, _p]),
+    "mb_regulariser_forward": (_i, [_p, _ll, _p, _ll, _f, _p, _p, _p]),
+    "mb_regulariser_backward": (_i, [_p, _ll, _p, _ll, _f, _p, _p, _p, _p, _p]),
     "mb_hand_mask_loss": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mb_mano_fit_step": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _f, _f, _f, _f, _i, _i, _p]),
     "mb_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
@@ -118,6 +120,34 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().mb_error_string(rc).decode()
         raise ManoB200Error(f"{what} failed ({rc}): {msg}")
+
+
+def on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its first CUDA tensor argument (or of the autograd context's saved
+    tensors) current.  The C ABI launches on the CURRENT device and only receives a stream, so a layer built on
+    ``cuda:1`` while ``cuda:0`` is current would otherwise fail every launch (cudaErrorInvalidResourceHandle)."""
+    import functools
+
+    import torch
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None and args and hasattr(args[0], "saved_tensors"):
+            for a in args[0].saved_tensors:
+                if isinstance(a, torch.Tensor) and a.is_cuda:
+                    dev = a.device
+                    break
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 def ptr(t):

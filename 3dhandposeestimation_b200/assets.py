@@ -5,7 +5,7 @@ Reference behaviour being replaced: ``ManoLayer.__init__``
 (/root/reference/network/sub_modules/MANOLayer.py:52-80) unpickles
 ``MANO_RIGHT.pkl`` (python-2 pickle, latin1, chumpy objects inside) and casts
 eight constants to fp32.  This module reads the same file without chumpy (a
-restricted unpickler maps ``chumpy.*`` classes to inert stubs), and can build a
+allow-listing unpickler: ``chumpy.*`` classes become inert stubs, numpy / scipy.sparse array globals resolve, anything else is refused), and can build a
 synthetic model of identical keys/shapes/sparsity so that nothing
 MANO-licensed has to live in this repository.
 
@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import io
 import pickle
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -47,11 +48,32 @@ class _ChStub:
         self.__dict__.update(state)
 
 
+# The only globals a MANO pickle resolves (traced on MANO_RIGHT.pkl): numpy array reconstruction, a scipy CSC
+# matrix (J_regressor), a builtin set, and chumpy nodes (stubbed).  Anything else is refused, so a crafted pickle
+# cannot reach os.system & co. through this reader (the reference's plain pickle.load would).
+_ALLOWED_GLOBALS = {
+    ("numpy", "dtype"), ("numpy", "ndarray"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("scipy.sparse.csc", "csc_matrix"), ("scipy.sparse._csc", "csc_matrix"), ("scipy.sparse", "csc_matrix"),
+    ("scipy.sparse.csr", "csr_matrix"), ("scipy.sparse._csr", "csr_matrix"), ("scipy.sparse", "csr_matrix"),
+    ("__builtin__", "set"), ("builtins", "set"), ("__builtin__", "object"), ("builtins", "object"),
+    ("copy_reg", "_reconstructor"), ("copyreg", "_reconstructor"),
+}
+
+
 class _ManoUnpickler(pickle.Unpickler):
+    """Allow-listing unpickler: chumpy classes become inert stubs, the globals in ``_ALLOWED_GLOBALS`` resolve
+    normally, everything else raises ``pickle.UnpicklingError``."""
+
     def find_class(self, module, name):
         if module.split(".")[0] == "chumpy":
             return type(name, (_ChStub,), {})
-        return super().find_class(module, name)
+        if (module, name) not in _ALLOWED_GLOBALS:
+            raise pickle.UnpicklingError(f"MANO pickle asks for {module}.{name}, which a MANO model never needs")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)     # scipy.sparse.csc is a deprecated alias
+            return super().find_class(module, name)
 
 
 def _ch_to_numpy(obj) -> np.ndarray:

@@ -18,8 +18,8 @@ def _prep(pre_xyz, gt_xyz, keypoint_vis):
     dev = pre_xyz.device
     pre = _as_f32_cuda(pre_xyz, "pre_xyz", dev)
     gt = _as_f32_cuda(gt_xyz, "gt_xyz", dev)
-    if pre.shape != gt.shape or pre.dim() != 3 or pre.shape[2] != 3:
-        raise RuntimeError("expected pre_xyz and gt_xyz of shape [B, J, 3]")
+    if pre.shape != gt.shape or pre.dim() != 3 or not 1 <= pre.shape[2] <= 4:
+        raise RuntimeError("expected pre_xyz and gt_xyz of shape [B, J, D], D = 3 (xyz) or 2 (uv, loss.py:86-87)")
     n = pre.shape[0] * pre.shape[1]
     vis = keypoint_vis
     if vis.device != dev:
@@ -37,12 +37,13 @@ def _prep(pre_xyz, gt_xyz, keypoint_vis):
 
 class _MaskedReduce(torch.autograd.Function):
     @staticmethod
+    @_cabi.on_tensor_device
     def forward(ctx, pre, gt, vis, vis_kind, n, kind):
         lib = _cabi.lib()
         dev = pre.device
         accum = torch.empty((2,), dtype=torch.float64, device=dev)
         out = torch.empty((), dtype=torch.float32, device=dev)
-        _cabi.check(lib.mb_masked_joint_reduce(pre.data_ptr(), gt.data_ptr(), vis.data_ptr(), vis_kind, n, kind,
+        _cabi.check(lib.mb_masked_joint_reduce(pre.data_ptr(), gt.data_ptr(), vis.data_ptr(), vis_kind, n, pre.shape[2], kind,
                                                accum.data_ptr(), out.data_ptr(), _cabi.stream_handle(dev)),
                     "mb_masked_joint_reduce")
         ctx.save_for_backward(pre, gt, vis, accum)
@@ -50,6 +51,7 @@ class _MaskedReduce(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_cabi.on_tensor_device
     def backward(ctx, g_out):
         if ctx.kind != _cabi.REDUCE_L2:
             raise RuntimeError("MPJPE is a metric (used under no_grad, trainval.py:313-320); use L2Loss for training")
@@ -58,7 +60,7 @@ class _MaskedReduce(torch.autograd.Function):
         g_pre = torch.empty_like(pre)
         g_out = g_out.to(torch.float32).contiguous()
         _cabi.check(lib.mb_masked_l2_backward(pre.data_ptr(), gt.data_ptr(), vis.data_ptr(), ctx.vis_kind, ctx.n,
-                                              accum.data_ptr(), g_out.data_ptr(), g_pre.data_ptr(),
+                                              pre.shape[2], accum.data_ptr(), g_out.data_ptr(), g_pre.data_ptr(),
                                               _cabi.stream_handle(pre.device)), "mb_masked_l2_backward")
         return g_pre, None, None, None, None, None
 
@@ -80,12 +82,49 @@ class L2Loss(nn.Module):
         return _MaskedReduce.apply(pre, gt, vis, kind, n, _cabi.REDUCE_L2)
 
 
-def compute_regularization_loss(theta, beta):
-    """criterions/loss.py:113-117: (||theta||_F + 10 ||beta||_F) / 100 over the whole batch."""
-    alpha_beta = 10
-    return (torch.norm(theta) + alpha_beta * torch.norm(beta)) / 100
+class _Regulariser(torch.autograd.Function):
+    @staticmethod
+    @_cabi.on_tensor_device
+    def forward(ctx, theta, beta, alpha_beta):
+        lib = _cabi.lib()
+        dev = theta.device
+        accum = torch.empty((2,), dtype=torch.float64, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.mb_regulariser_forward(theta.data_ptr(), theta.numel(), beta.data_ptr(), beta.numel(), alpha_beta,
+                                                   accum.data_ptr(), out.data_ptr(), _cabi.stream_handle(dev)),
+                        "mb_regulariser_forward")
+        ctx.save_for_backward(theta, beta, accum)
+        ctx.alpha_beta = alpha_beta
+        return out
+
+    @staticmethod
+    @_cabi.on_tensor_device
+    def backward(ctx, g_out):
+        theta, beta, accum = ctx.saved_tensors
+        dev = theta.device
+        g_theta = torch.empty_like(theta)
+        g_beta = torch.empty_like(beta)
+        g_out = g_out.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().mb_regulariser_backward(theta.data_ptr(), theta.numel(), beta.data_ptr(), beta.numel(),
+                                                            ctx.alpha_beta, accum.data_ptr(), g_out.data_ptr(),
+                                                            g_theta.data_ptr(), g_beta.data_ptr(), _cabi.stream_handle(dev)),
+                        "mb_regulariser_backward")
+        return g_theta, g_beta, None
 
 
+def compute_regularization_loss(theta, beta, alpha_beta=10.0):
+    """criterions/loss.py:113-117 — the MANO regulariser over the whole batch, as two kernels (a fp64 sum-of-squares
+    reduction + finalise; an elementwise backward), differentiable in both arguments.  ``alpha_beta`` is the
+    reference's hard-coded weight of the shape term."""
+    if not isinstance(theta, torch.Tensor) or theta.device.type != "cuda":
+        raise _cabi.ManoB200Error("compute_regularization_loss only runs on CUDA tensors (sm_100a); no CPU fallback")
+    dev = theta.device
+    return _Regulariser.apply(_as_f32_cuda(theta, "theta", dev), _as_f32_cuda(beta, "beta", dev), float(alpha_beta))
+
+
+@_cabi.on_tensor_device
 def compute_hand_mask_loss(pred_uv, gt_uv, hand_mask):
     """criterions/loss.py:92-111: 1 - (mask samples at the predicted keypoints) / (mask samples at the ground-truth
     keypoints + 1e-8); uv[B,N,2] are truncated to integers and clamped to [0, W-1], ``hand_mask`` is [B,H,W].

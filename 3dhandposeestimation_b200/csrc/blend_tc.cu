@@ -603,13 +603,9 @@ void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob
 int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, int hand_minor, int ksplit,
                              size_t part_stride, cudaStream_t s) {
     if (B <= 0) return 0;
-    static bool attr_done = false;
+    static SmemAttrOnce once;
     const size_t smem = sizeof(TcBwdShared) + 128;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(blend_tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    if (int arc = ensure_dyn_smem(once, blend_tc_backward_kernel, smem)) return arc;
     const BlobLayout L = blob_layout();
     const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
     const int m_tiles = (B + TC_M - 1) / TC_M;
@@ -623,13 +619,9 @@ int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* 
 
 int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float* v_posed_t, int B, int mode, cudaStream_t s) {
     if (B <= 0) return 0;
-    static bool attr_done = false;
+    static SmemAttrOnce once;
     const size_t smem = sizeof(TcShared) + 128;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(blend_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    if (int arc = ensure_dyn_smem(once, blend_tc_forward_kernel, smem)) return arc;
     const BlobLayout L = blob_layout();
     const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
     const int m_tiles = (B + TC_M - 1) / TC_M;
@@ -637,13 +629,9 @@ int launch_blend_tc_forward(const void* blob, const unsigned char* featp, float*
     const int grid = (int)(total < NUM_SMS ? total : NUM_SMS);      // >= 15: every n-tile has at least one CTA
     const float* tmpl = blob_ptr<float>(blob, L.sk_tmpl);
     if (m_tiles >= TC_MRES_MIN_TILES) {             // large batch: hand tile resident, basis streamed (one CTA per hand tile)
-        static bool attr2_done = false;
+        static SmemAttrOnce once2;
         const size_t smem2 = sizeof(TcSharedM) + 128;
-        if (!attr2_done) {
-            cudaError_t e = cudaFuncSetAttribute(blend_tc_forward_mres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            if (e != cudaSuccess) return (int)e;
-            attr2_done = true;
-        }
+        if (int arc = ensure_dyn_smem(once2, blend_tc_forward_mres_kernel, smem2)) return arc;
         blend_tc_forward_mres_kernel<<<m_tiles < NUM_SMS ? m_tiles : NUM_SMS, TC_THREADS, smem2, s>>>(
             reinterpret_cast<const TcBlobHeader*>(tc), tc + align256(sizeof(TcBlobHeader)), tmpl, featp, v_posed_t, B, m_tiles,
             mode == MB_MODE_F16X3 ? 3 : 1);

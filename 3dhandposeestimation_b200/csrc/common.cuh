@@ -226,6 +226,24 @@ inline int cuda_rc() {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs must
+// set it on each of them (a process-wide "done" flag made the first launch on a second device fail with
+// invalid-value).  One bit per device ordinal, lock-free; setting it twice is harmless.
+struct SmemAttrOnce { unsigned long long mask[4]; };
+template <class Kernel>
+inline int ensure_dyn_smem(SmemAttrOnce& once, Kernel kernel, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long* word = &once.mask[(dev >> 6) & 3];
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(word, __ATOMIC_ACQUIRE) & bit) return 0;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    __atomic_fetch_or(word, bit, __ATOMIC_RELEASE);
+    return 0;
+}
+
 // per-stage CUDA-event profiling (off by default; bench.py turns it on for the roofline pass)
 enum Stage { ST_POSE_FWD = 0, ST_BLEND_FWD, ST_LBS_FWD, ST_LBS_BWD, ST_BLEND_BWD, ST_POSE_BWD,
              ST_JOINTS_FWD, ST_JOINTS_BWD, ST_FK_FWD, ST_FK_BWD, ST_COUNT };

@@ -813,12 +813,8 @@ inline int lh_grid(int B) {
 
 int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                            int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_forward_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemAttrOnce once;
+    if (int arc = ensure_dyn_smem(once, pose_forward_lh_kernel, LH_SMEM)) return arc;
     pose_forward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, B, feat, featp, bone_t, joints);
     return cuda_rc();
 }
@@ -826,12 +822,8 @@ int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const flo
 int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                             const float* dfeat_t, const float* dbone_t, const float* g_joints, int B,
                             float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemAttrOnce once;
+    if (int arc = ensure_dyn_smem(once, pose_backward_lh_kernel<0>, LH_SMEM)) return arc;
     pose_backward_lh_kernel<0><<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, dfeat_t, dbone_t, g_joints, B,
                                                                              g_rot, g_coeffs, g_betas, FitArgs{});
     return cuda_rc();
@@ -839,24 +831,16 @@ int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const fl
 
 int launch_joints_only_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                   int B, float* joints, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_forward_lh_jo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemAttrOnce once;
+    if (int arc = ensure_dyn_smem(once, pose_forward_lh_jo_kernel, LH_SMEM_JO)) return arc;
     pose_forward_lh_jo_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM_JO, s>>>(blob, nc, rot, coeffs, betas, B, joints);
     return cuda_rc();
 }
 
 int launch_joints_only_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                                    const float* g_joints, int B, float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemAttrOnce once;
+    if (int arc = ensure_dyn_smem(once, pose_backward_lh_kernel<1>, LH_SMEM_JO)) return arc;
     pose_backward_lh_kernel<1><<<lh_grid(B), LH_WARPS * 32, LH_SMEM_JO, s>>>(blob, nc, rot, coeffs, betas, nullptr, nullptr, g_joints, B,
                                                                                g_rot, g_coeffs, g_betas, FitArgs{});
     return cuda_rc();
@@ -866,12 +850,8 @@ int launch_joints_only_backward_lh(const void* blob, int nc, const float* rot, c
 int launch_fit_step_lh(const void* blob, int nc, float* params, float* exp_avg, float* exp_avg_sq, const float* target_joints,
                        const float* vis, int B, const double* globals, double* partials, float lr, float beta1, float beta2,
                        float eps, int step, int regularize, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pose_backward_lh_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LH_SMEM_JO);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemAttrOnce once;
+    if (int arc = ensure_dyn_smem(once, pose_backward_lh_kernel<2>, LH_SMEM_JO)) return arc;
     cudaError_t e = cudaMemsetAsync(partials, 0, 3 * sizeof(double), s);
     if (e != cudaSuccess) return (int)e;
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);

@@ -20,13 +20,17 @@ __device__ __forceinline__ bool visible(const void* vis, int kind, long long i) 
 
 __global__ void __launch_bounds__(RED_THREADS)
 masked_reduce_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const void* __restrict__ vis,
-                     int vis_kind, long long n, int kind, double* __restrict__ accum) {
+                     int vis_kind, long long n, int dim, int kind, double* __restrict__ accum) {
+    // dim = components per joint: 3 for xyz, 2 for the uv loss (loss.py:86-87 sends [B,21,2] through the same L2Loss)
     double sum = 0.0;
     double cnt = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         if (visible(vis, vis_kind, i)) {
-            const float dx = pred[i * 3] - gt[i * 3], dy = pred[i * 3 + 1] - gt[i * 3 + 1], dz = pred[i * 3 + 2] - gt[i * 3 + 2];
-            const float d2 = dx * dx + dy * dy + dz * dz;
+            float d2 = 0.f;
+            for (int c = 0; c < dim; ++c) {                     // same order as the reference's sum(dim=2)
+                const float d = pred[i * dim + c] - gt[i * dim + c];
+                d2 = c == 0 ? d * d : d2 + d * d;
+            }
             sum += (kind == MB_REDUCE_MPJPE_MM) ? (double)sqrtf(d2) : (double)d2;
             cnt += 1.0;
         }
@@ -56,16 +60,54 @@ __global__ void masked_finalize_kernel(const double* __restrict__ accum, int kin
 
 __global__ void __launch_bounds__(RED_THREADS)
 masked_l2_backward_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const void* __restrict__ vis,
-                          int vis_kind, long long n, const double* __restrict__ accum, const float* __restrict__ g_out,
+                          int vis_kind, long long n, int dim, const double* __restrict__ accum, const float* __restrict__ g_out,
                           float* __restrict__ g_pred) {
     const double c = accum[1];
     const float scale = c > 0.0 ? (float)(2.0 * (double)g_out[0] / c) : 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float m = visible(vis, vis_kind, i) ? scale : 0.f;
-        g_pred[i * 3] = m * (pred[i * 3] - gt[i * 3]);
-        g_pred[i * 3 + 1] = m * (pred[i * 3 + 1] - gt[i * 3 + 1]);
-        g_pred[i * 3 + 2] = m * (pred[i * 3 + 2] - gt[i * 3 + 2]);
+        for (int k = 0; k < dim; ++k) g_pred[i * dim + k] = m * (pred[i * dim + k] - gt[i * dim + k]);
     }
+}
+
+// LossCalculation.compute_regularization_loss (criterions/loss.py:113-117): (||theta||_F + alpha ||beta||_F) / 100
+// over the whole batch.  accum = {sum theta^2, sum beta^2} in fp64.
+__global__ void __launch_bounds__(RED_THREADS)
+sumsq2_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb, double* __restrict__ accum) {
+    double sa = 0.0, sb = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) { const float x = a[i]; sa += (double)x * x; }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) { const float x = b[i]; sb += (double)x * x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    __shared__ double s_a[RED_THREADS / 32], s_b[RED_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_a[warp] = sa; s_b[warp] = sb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < RED_THREADS / 32; ++w) { x += s_a[w]; y += s_b[w]; }
+        atomicAdd(&accum[0], x);
+        atomicAdd(&accum[1], y);
+    }
+}
+__global__ void regulariser_finalize_kernel(const double* __restrict__ accum, float alpha_beta, float* __restrict__ out) {
+    out[0] = (sqrtf((float)accum[0]) + alpha_beta * sqrtf((float)accum[1])) / 100.f;
+}
+// d/dtheta = g theta / (100 ||theta||), d/dbeta = g alpha beta / (100 ||beta||); 0 at a zero norm (torch.norm's subgradient)
+__global__ void __launch_bounds__(RED_THREADS)
+regulariser_backward_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
+                            const double* __restrict__ accum, float alpha_beta, const float* __restrict__ g_out,
+                            float* __restrict__ ga, float* __restrict__ gb) {
+    const float na2 = sqrtf((float)accum[0]), nb2 = sqrtf((float)accum[1]);
+    const float g = g_out[0] / 100.f;
+    const float ka = na2 > 0.f ? g / na2 : 0.f, kb = nb2 > 0.f ? g * alpha_beta / nb2 : 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) ga[i] = ka * a[i];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) gb[i] = kb * b[i];
 }
 
 // LossCalculation.compute_hand_mask_loss (criterions/loss.py:92-111): uv -> int64 (truncation), clamp to
@@ -137,8 +179,8 @@ inline unsigned red_grid(long long n) {
 using namespace mb;
 
 extern "C" int mb_masked_joint_reduce(const float* pred, const float* gt, const void* vis, int vis_kind,
-                                      long long n_joints, int kind, double* accum, float* out, mb_stream_t stream) {
-    if (n_joints < 0 || (kind != MB_REDUCE_MPJPE_MM && kind != MB_REDUCE_L2) ||
+                                      long long n_joints, int dim, int kind, double* accum, float* out, mb_stream_t stream) {
+    if (n_joints < 0 || dim < 1 || dim > 4 || (kind != MB_REDUCE_MPJPE_MM && kind != MB_REDUCE_L2) ||
         (vis_kind != MB_VIS_F32 && vis_kind != MB_VIS_U8))
         return MB_E_RANGE;
     if (!accum || !out) return MB_E_NULL;
@@ -147,7 +189,7 @@ extern "C" int mb_masked_joint_reduce(const float* pred, const float* gt, const 
     cudaError_t e = cudaMemsetAsync(accum, 0, 2 * sizeof(double), s);
     if (e != cudaSuccess) return (int)e;
     if (n_joints > 0) {
-        masked_reduce_kernel<<<red_grid(n_joints), RED_THREADS, 0, s>>>(pred, gt, vis, vis_kind, n_joints, kind, accum);
+        masked_reduce_kernel<<<red_grid(n_joints), RED_THREADS, 0, s>>>(pred, gt, vis, vis_kind, n_joints, dim, kind, accum);
         int rc = cuda_rc();
         if (rc) return rc;
     }
@@ -156,13 +198,41 @@ extern "C" int mb_masked_joint_reduce(const float* pred, const float* gt, const 
 }
 
 extern "C" int mb_masked_l2_backward(const float* pred, const float* gt, const void* vis, int vis_kind,
-                                     long long n_joints, const double* accum, const float* g_out,
+                                     long long n_joints, int dim, const double* accum, const float* g_out,
                                      float* g_pred, mb_stream_t stream) {
-    if (n_joints < 0 || (vis_kind != MB_VIS_F32 && vis_kind != MB_VIS_U8)) return MB_E_RANGE;
+    if (n_joints < 0 || dim < 1 || dim > 4 || (vis_kind != MB_VIS_F32 && vis_kind != MB_VIS_U8)) return MB_E_RANGE;
     if (n_joints == 0) return 0;
     if (!pred || !gt || !vis || !accum || !g_out || !g_pred) return MB_E_NULL;
     masked_l2_backward_kernel<<<red_grid(n_joints), RED_THREADS, 0, (cudaStream_t)stream>>>(pred, gt, vis, vis_kind, n_joints,
-                                                                                              accum, g_out, g_pred);
+                                                                                              dim, accum, g_out, g_pred);
+    return cuda_rc();
+}
+
+extern "C" int mb_regulariser_forward(const float* theta, long long n_theta, const float* beta, long long n_beta,
+                                      float alpha_beta, double* accum, float* out, mb_stream_t stream) {
+    if (n_theta < 0 || n_beta < 0) return MB_E_RANGE;
+    if (!accum || !out) return MB_E_NULL;
+    if ((n_theta > 0 && !theta) || (n_beta > 0 && !beta)) return MB_E_NULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(accum, 0, 2 * sizeof(double), s);
+    if (e != cudaSuccess) return (int)e;
+    if (n_theta + n_beta > 0) {
+        sumsq2_kernel<<<red_grid(n_theta > n_beta ? n_theta : n_beta), RED_THREADS, 0, s>>>(theta, n_theta, beta, n_beta, accum);
+        int rc = cuda_rc();
+        if (rc) return rc;
+    }
+    regulariser_finalize_kernel<<<1, 1, 0, s>>>(accum, alpha_beta, out);
+    return cuda_rc();
+}
+
+extern "C" int mb_regulariser_backward(const float* theta, long long n_theta, const float* beta, long long n_beta,
+                                       float alpha_beta, const double* accum, const float* g_out, float* g_theta,
+                                       float* g_beta, mb_stream_t stream) {
+    if (n_theta < 0 || n_beta < 0) return MB_E_RANGE;
+    if (n_theta + n_beta == 0) return 0;
+    if (!accum || !g_out || (n_theta > 0 && (!theta || !g_theta)) || (n_beta > 0 && (!beta || !g_beta))) return MB_E_NULL;
+    regulariser_backward_kernel<<<red_grid(n_theta > n_beta ? n_theta : n_beta), RED_THREADS, 0, (cudaStream_t)stream>>>(
+        theta, n_theta, beta, n_beta, accum, alpha_beta, g_out, g_theta, g_beta);
     return cuda_rc();
 }
 

@@ -1095,14 +1095,9 @@ int skin_program_check(const void* host_blob, int32_t* stats) {
 int launch_skin_forward(const void* blob, const float* v_posed_t, const float* bone_t, int B,
                         float* verts, float* joints, cudaStream_t s) {
     if (B <= 0) return 0;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(skin_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKF_SMEM);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(skin_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKF_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemAttrOnce once_a, once_b;
+    if (int arc = ensure_dyn_smem(once_a, skin_forward_kernel<false>, SKF_SMEM)) return arc;
+    if (int arc = ensure_dyn_smem(once_b, skin_forward_kernel<true>, SKF_SMEM)) return arc;
     const int ngroups = (B + 31) >> 5;
     const int spu = skin_segments_per_unit(ngroups, SKF_SWEEPERS);
     if (spu < SK_NSEG) {
@@ -1118,14 +1113,9 @@ int launch_skin_backward(const void* blob, const float* v_posed_t, const float* 
                          const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, int dbone_hand_minor,
                          float* dparts, cudaStream_t s) {
     if (B <= 0) return 0;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(skin_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKB_SMEM);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(skin_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKB_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemAttrOnce once_a, once_b;
+    if (int arc = ensure_dyn_smem(once_a, skin_backward_kernel<false>, SKB_SMEM)) return arc;
+    if (int arc = ensure_dyn_smem(once_b, skin_backward_kernel<true>, SKB_SMEM)) return arc;
     const int ngroups = (B + 31) >> 5;
     const int spu = skin_segments_per_unit(ngroups, SKB_SWEEPERS);
     if (spu < SK_NSEG) {

@@ -154,7 +154,7 @@ class ManoFitter:
                                         None, self.joints.data_ptr(), None, 0, stream), "mb_mano_forward")
         # 2. rank-local partials of the objective
         _cabi.check(lib.mb_masked_joint_reduce(self.joints.data_ptr(), tgt.data_ptr(), vis.data_ptr(), _cabi.VIS_F32,
-                                               B * 21, _cabi.REDUCE_L2, self.accum.data_ptr(), self.l2_out.data_ptr(),
+                                               B * 21, 3, _cabi.REDUCE_L2, self.accum.data_ptr(), self.l2_out.data_ptr(),
                                                stream), "mb_masked_joint_reduce")
         self.partials[0:2] = self.accum
         if self.regularize:
@@ -167,7 +167,7 @@ class ManoFitter:
         self.loss, inv_t, inv_b = objective_from_partials(self.partials)
         # 4. gradient of the global L2 term w.r.t. this rank's joints, with the GLOBAL visible count
         self.accum.copy_(self.partials[0:2])
-        _cabi.check(lib.mb_masked_l2_backward(self.joints.data_ptr(), tgt.data_ptr(), vis.data_ptr(), _cabi.VIS_F32, B * 21,
+        _cabi.check(lib.mb_masked_l2_backward(self.joints.data_ptr(), tgt.data_ptr(), vis.data_ptr(), _cabi.VIS_F32, B * 21, 3,
                                               self.accum.data_ptr(), self.one.data_ptr(), self.g_joints.data_ptr(), stream),
                     "mb_masked_l2_backward")
         # 5. joints-only backward

@@ -26,6 +26,7 @@ def _reference_joint_order_switched(default=True) -> bool:
 
 class _FKFunction(torch.autograd.Function):
     @staticmethod
+    @_cabi.on_tensor_device
     def forward(ctx, root_angles, other_angles, bone_lengths, K, scale, root, swap):
         lib = _cabi.lib()
         B = root_angles.shape[0]
@@ -41,6 +42,7 @@ class _FKFunction(torch.autograd.Function):
         return xyz, uv
 
     @staticmethod
+    @_cabi.on_tensor_device
     def backward(ctx, g_xyz, g_uv):
         root_angles, other_angles, bone_lengths, K, scale, root = ctx.saved_tensors
         lib = _cabi.lib()
@@ -105,6 +107,7 @@ class ForwardKinematics(nn.Module):
 
 class _ProjectFunction(torch.autograd.Function):
     @staticmethod
+    @_cabi.on_tensor_device
     def forward(ctx, xyz, K):
         lib = _cabi.lib()
         B, N = xyz.shape[0], xyz.shape[1]
@@ -115,6 +118,7 @@ class _ProjectFunction(torch.autograd.Function):
         return uv
 
     @staticmethod
+    @_cabi.on_tensor_device
     def backward(ctx, g_uv):
         xyz, K = ctx.saved_tensors
         lib = _cabi.lib()
@@ -142,6 +146,7 @@ class _JointEpilogueFunction(torch.autograd.Function):
     """joints -> (rel_normalized, joint_xyz21[, uv21]) in one kernel (joint_epilogue.cu)."""
 
     @staticmethod
+    @_cabi.on_tensor_device
     def forward(ctx, joints, scale, root, K, swap):
         lib = _cabi.lib()
         B = joints.shape[0]
@@ -157,6 +162,7 @@ class _JointEpilogueFunction(torch.autograd.Function):
         return rel, xyz, uv                  # uv is None when no intrinsics were given
 
     @staticmethod
+    @_cabi.on_tensor_device
     def backward(ctx, g_rel, g_xyz, g_uv):
         joints, scale, root, K = ctx.saved_tensors
         lib = _cabi.lib()

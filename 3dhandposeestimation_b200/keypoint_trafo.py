@@ -22,6 +22,7 @@ def _coords21(t, name):
     return x.contiguous()
 
 
+@_cabi.on_tensor_device
 def bone_rel_trafo(coords_xyz):
     """utils/relative_trafo.py:167-216: xyz[B,21,3] -> [B,21,3] = (bone length, angle_x, angle_y) in the
     frames of the kinematic chain."""
@@ -32,6 +33,7 @@ def bone_rel_trafo(coords_xyz):
     return out
 
 
+@_cabi.on_tensor_device
 def bone_rel_trafo_inv(coords_rel):
     """utils/relative_trafo.py:219-270: (length, angle_x, angle_y)[B,21,3] -> xyz[B,21,3]."""
     rel = _coords21(coords_rel, "coords_rel")
@@ -46,6 +48,7 @@ def _cond_bytes(cond, shape, dev):
     return c.to(torch.bool).expand(shape).contiguous().to(torch.uint8)
 
 
+@_cabi.on_tensor_device
 def canonical_trafo(coords_xyz, cond_right=None):
     """utils/canonical_trafo.py:93-159 -> ``(coords_xyz_normed[B,21,3], total_rot_mat[B,3,3])``.  With
     ``cond_right`` (bool, one per hand) the flagged hands are additionally mirrored as by
@@ -73,6 +76,7 @@ def mirror_left_hand(keypoint_xyz21, hand_side):
     return _mirror(keypoint_xyz21, side == 0, 0)
 
 
+@_cabi.on_tensor_device
 def _mirror(coords_xyz_canonical, cond_right, axis):
     if not isinstance(coords_xyz_canonical, torch.Tensor) or coords_xyz_canonical.device.type != "cuda":
         raise _cabi.ManoB200Error("coords_xyz_canonical must be a CUDA tensor (sm_100a); there is no CPU fallback")

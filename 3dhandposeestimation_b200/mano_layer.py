@@ -38,6 +38,7 @@ class _ManoFunction(torch.autograd.Function):
     backward re-uses that scratch once and recomputes it if called again."""
 
     @staticmethod
+    @_cabi.on_tensor_device
     def forward(ctx, rot, coeffs, betas, layer, want_verts):
         lib = _cabi.lib()
         B = rot.shape[0]
@@ -70,6 +71,7 @@ class _ManoFunction(torch.autograd.Function):
         return placeholder, joints
 
     @staticmethod
+    @_cabi.on_tensor_device
     def backward(ctx, g_verts, g_joints):
         rot, coeffs, betas = ctx.saved_tensors
         layer = ctx.layer

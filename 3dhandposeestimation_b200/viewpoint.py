@@ -19,6 +19,7 @@ class _ViewpointFunction(torch.autograd.Function):
     """(can, ux, uy, uz) -> (rot_mat, rel_normed); ``can`` may be None (rot_mat only)."""
 
     @staticmethod
+    @_cabi.on_tensor_device
     def forward(ctx, can, ux, uy, uz):
         B = ux.shape[0]
         dev = ux.device
@@ -31,6 +32,7 @@ class _ViewpointFunction(torch.autograd.Function):
         return rot, rel
 
     @staticmethod
+    @_cabi.on_tensor_device
     def backward(ctx, g_rot, g_rel):
         can, ux, uy, uz = ctx.saved_tensors
         B = ux.shape[0]
@@ -63,6 +65,7 @@ def _get_rot_mat(ux_b, uy_b, uz_b):
     return rot
 
 
+@_cabi.on_tensor_device
 def viewpoint_transform(can_xyz_kps21, ux, uy, uz, index_root_bone_length=None, kp_coord_xyz_root=None,
                         camera_intrinsic_matrix=None):
     """network/Hand3DPoseNet.py:41-50 in one kernel.  Training branch (no scale / root given) ->

@@ -360,13 +360,13 @@ def run_secondary(args, pkg, layer, dev, rank, world, dist):
         o = outs[i]
         ra, oa, bl, K, sc, root = t
         cabi.check(lib.mb_fk_forward(P(ra), P(oa), P(bl), P(K), P(sc), P(root), B, 0, P(o["xyz"]), P(o["uv"]), stream), "fk_forward")
-        cabi.check(lib.mb_masked_joint_reduce(P(o["xyz"]), P(gt), P(vis), cabi.VIS_F32, B * 21, cabi.REDUCE_L2, P(o["acc"]), P(o["l2"]),
+        cabi.check(lib.mb_masked_joint_reduce(P(o["xyz"]), P(gt), P(vis), cabi.VIS_F32, B * 21, 3, cabi.REDUCE_L2, P(o["acc"]), P(o["l2"]),
                                               stream), "reduce")
-        cabi.check(lib.mb_masked_l2_backward(P(o["xyz"]), P(gt), P(vis), cabi.VIS_F32, B * 21, P(o["acc"]), P(one), P(o["g_xyz"]),
+        cabi.check(lib.mb_masked_l2_backward(P(o["xyz"]), P(gt), P(vis), cabi.VIS_F32, B * 21, 3, P(o["acc"]), P(one), P(o["g_xyz"]),
                                              stream), "l2_backward")
         cabi.check(lib.mb_fk_backward(P(ra), P(oa), P(bl), P(K), P(sc), P(root), P(o["g_xyz"]), None, B, 0, P(o["g"][0]), P(o["g"][1]),
                                       P(o["g"][2]), stream), "fk_backward")
-        cabi.check(lib.mb_masked_joint_reduce(P(o["xyz"]), P(gt), P(vis), cabi.VIS_F32, B * 21, cabi.REDUCE_MPJPE_MM, P(o["acc2"]),
+        cabi.check(lib.mb_masked_joint_reduce(P(o["xyz"]), P(gt), P(vis), cabi.VIS_F32, B * 21, 3, cabi.REDUCE_MPJPE_MM, P(o["acc2"]),
                                               P(o["mp"]), stream), "mpjpe")
 
     side = torch.cuda.Stream(device=dev)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MB_ABI_VERSION 2
+#define MB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MB_API __attribute__((visibility("default")))
@@ -214,14 +214,27 @@ MB_API int mb_viewpoint_backward(const float* can_xyz, const float* ux, const fl
  * Replaces MPJPE.forward (criterions/metrics.py:10-27) and L2Loss.forward
  * (criterions/loss.py:10-25): global mean over the visible joints of the batch,
  * 0 when none is visible — decided on the device, no host sync.
- *   pred[n_joints][3], gt[n_joints][3], vis[n_joints] (fp32 non-zero = visible, or u8)
+ *   pred[n_joints][dim], gt[n_joints][dim], vis[n_joints] (fp32 non-zero = visible, or u8)
+ *   dim = components per joint, 1..4: 3 for the xyz loss / MPJPE, 2 for the uv loss
+ *         (LossCalculation.compute_uv_coord_loss, criterions/loss.py:86-87, sends [B,21,2] through L2Loss)
  *   accum: device double[2] scratch {sum, count} (overwritten);  out: device float[1] */
 MB_API int mb_masked_joint_reduce(const float* pred, const float* gt, const void* vis, int vis_kind,
-                           long long n_joints, int kind, double* accum, float* out, mb_stream_t stream);
+                           long long n_joints, int dim, int kind, double* accum, float* out, mb_stream_t stream);
 /* d(L2)/d(pred) = g_out * 2 (pred-gt) vis / count, with `accum` as left by the forward. */
 MB_API int mb_masked_l2_backward(const float* pred, const float* gt, const void* vis, int vis_kind,
-                          long long n_joints, const double* accum, const float* g_out,
+                          long long n_joints, int dim, const double* accum, const float* g_out,
                           float* g_pred, mb_stream_t stream);
+
+/* Replaces LossCalculation.compute_regularization_loss (criterions/loss.py:113-117):
+ *   out = (||theta||_F + alpha_beta * ||beta||_F) / 100 over ALL n_theta / n_beta elements (the reference's
+ *   torch.norm of the whole [B,nc] / [B,10] tensors; alpha_beta = 10 there).
+ *   accum: device double[2] scratch {sum theta^2, sum beta^2} (overwritten; the backward reads it).
+ * Backward: g_theta = g_out theta / (100 ||theta||), g_beta = g_out alpha_beta beta / (100 ||beta||), 0 at a zero norm. */
+MB_API int mb_regulariser_forward(const float* theta, long long n_theta, const float* beta, long long n_beta,
+                           float alpha_beta, double* accum, float* out, mb_stream_t stream);
+MB_API int mb_regulariser_backward(const float* theta, long long n_theta, const float* beta, long long n_beta,
+                            float alpha_beta, const double* accum, const float* g_out, float* g_theta,
+                            float* g_beta, mb_stream_t stream);
 
 /* Replaces LossCalculation.compute_hand_mask_loss (criterions/loss.py:92-111):
  *   uv -> int64 by truncation, clamped to [0, W-1] on both axes (as the reference does), samples of

@@ -210,6 +210,13 @@ def regularizer(theta, beta, dtype=np.float64):
     return dtype((np.linalg.norm(np.asarray(theta, dtype)) + 10.0 * np.linalg.norm(np.asarray(beta, dtype))) / 100.0)
 
 
+def regularizer_backward(theta, beta, dtype=np.float64):
+    """Gradient of ``regularizer`` (autograd of criterions/loss.py:113-117): theta / (100 ||theta||), 10 beta / (100 ||beta||)."""
+    t, b = np.asarray(theta, dtype), np.asarray(beta, dtype)
+    nt, nb = np.linalg.norm(t), np.linalg.norm(b)
+    return (t / (100.0 * nt) if nt > 0 else np.zeros_like(t)), (10.0 * b / (100.0 * nb) if nb > 0 else np.zeros_like(b))
+
+
 def match_mano_to_rhd(mano_joints, index_root_bone_length, kp_coord_xyz_root, joint_order_switched=True, dtype=np.float64):
     """``match_mano_to_RHD`` (network/Resnet50MANO3DHandPose.py:35-60, the same body at
     network/MANO3DHandPose.py:30-55): optional per-finger joint reversal, root-relative

@@ -1,8 +1,8 @@
-"""ORACLE helper — imports the UNMODIFIED reference from /root/reference in the
-authoring container (it does not exist on the GPU box; callers must skip when
-``available()`` is False).  Used to pin the numpy oracle and to generate
-``tests/golden``.  Nothing is copied: the reference modules are imported from
-where they lie, behind stub modules for its missing third-party imports
+"""ORACLE helper (test infrastructure) — imports the UNMODIFIED reference: from /root/reference in the authoring
+container, else from the byte-for-byte travelling copy ``oracle/_ref/`` that ``oracle/make_ref.py`` stages (git-ignored,
+shipped to the GPU box by gpurun); callers must skip when ``available()`` is False.  Used to pin the numpy oracle, to
+generate ``tests/golden``, as the live parity checker of the ``-m gpu`` tests and as the CPU baseline arm of
+``bench.py``.  The reference modules are imported as they are, behind stub modules for its missing third-party imports
 (``mano`` — mesh viewer only, ``chumpy`` — unpickling only, ``matplotlib``).
 """
 from __future__ import annotations
@@ -11,12 +11,17 @@ import os
 import sys
 import types
 
-REF_ROOT = "/root/reference"
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = "/root/reference" if os.path.isfile("/root/reference/network/sub_modules/MANOLayer.py") else _STAGED
 REAL_PKL = os.path.join(REF_ROOT, "config/mano/models/MANO_RIGHT.pkl")
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "network/sub_modules/MANOLayer.py"))
+
+
+def real_pkl_available() -> bool:
+    return os.path.isfile(REAL_PKL)
 
 
 def _install_stubs():

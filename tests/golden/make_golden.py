@@ -86,6 +86,31 @@ def reduce_case(B, seed, p_vis):
     return dict(pre=n(pre), gt=n(gt), vis=n(vis), mpjpe=np.float32(m.item()), l2=np.float32(l2.item()), g_pre=n(gpre))
 
 
+def reduce_uv_case(B, seed, p_vis):
+    """L2Loss on [B,21,2] — LossCalculation.compute_uv_coord_loss (criterions/loss.py:86-87) sends uv through the same class."""
+    g = torch.Generator().manual_seed(seed)
+    pre = (torch.rand(B, 21, 2, generator=g) * 320).requires_grad_()
+    gt = torch.rand(B, 21, 2, generator=g) * 320
+    vis = (torch.rand(B, 21, 1, generator=g) < p_vis).float()
+    l2 = ref.L2Loss()(pre, gt, vis)
+    l2.backward()
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(pre=n(pre), gt=n(gt), vis=n(vis), l2=np.float32(l2.item()), g_pre=n(pre.grad))
+
+
+def regulariser_case(B, nc, seed):
+    """LossCalculation.compute_regularization_loss (criterions/loss.py:113-117) and its autograd."""
+    from criterions.loss import LossCalculation
+    g = torch.Generator().manual_seed(seed)
+    theta = ((torch.rand(B, nc, generator=g) - .5) * 4).requires_grad_()
+    beta = ((torch.rand(B, 10, generator=g) - .5) * .1).requires_grad_()
+    loss = LossCalculation(comp_regularization_loss=True).compute_regularization_loss(theta, beta)
+    (loss * 3.0).backward()
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(theta=n(theta), beta=n(beta), loss=np.float32(loss.item()), g_theta=n(theta.grad), g_beta=n(beta.grad),
+                g_out=np.float32(3.0))
+
+
 def proj_case():
     g = torch.Generator().manual_seed(7)
     B = 3
@@ -197,6 +222,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "fk_unswitched.npz"), **fk_case(8, 4321, False))
     np.savez_compressed(os.path.join(HERE, "reduce_vis80.npz"), **reduce_case(16, 5, .8))
     np.savez_compressed(os.path.join(HERE, "reduce_none_visible.npz"), **reduce_case(4, 6, -1.0))
+    np.savez_compressed(os.path.join(HERE, "reduce_uv.npz"), **reduce_uv_case(9, 15, .7))
+    np.savez_compressed(os.path.join(HERE, "regulariser.npz"), **regulariser_case(13, 10, 21))
     np.savez_compressed(os.path.join(HERE, "project_uv.npz"), **proj_case())
     np.savez_compressed(os.path.join(HERE, "trafo.npz"), **trafo_case(12, 31))
     np.savez_compressed(os.path.join(HERE, "viewpoint.npz"), **viewpoint_case(7, 41))

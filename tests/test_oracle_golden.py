@@ -76,6 +76,19 @@ def test_reductions_match_reference_golden(name):
     assert np.abs(gp - g["g_pre"]).max() <= 1e-6 * max(1e-12, np.abs(g["g_pre"]).max()) + 1e-12
 
 
+def test_l2loss_on_uv_and_regulariser_match_reference_golden():
+    """[B,21,2] through L2Loss (loss.py:86-87) and the MANO regulariser with its gradient (loss.py:113-117)."""
+    g = load_golden("reduce_uv.npz")
+    assert fo.l2loss(g["pre"], g["gt"], g["vis"]) == pytest.approx(float(g["l2"]), rel=1e-5)
+    gp = fo.l2loss_backward(g["pre"], g["gt"], g["vis"])
+    assert np.abs(gp - g["g_pre"]).max() <= 1e-5 * np.abs(g["g_pre"]).max()
+    r = load_golden("regulariser.npz")
+    assert fo.regularizer(r["theta"], r["beta"]) == pytest.approx(float(r["loss"]), rel=1e-6)
+    gt_, gb_ = fo.regularizer_backward(r["theta"], r["beta"])
+    assert np.abs(gt_ * float(r["g_out"]) - r["g_theta"]).max() <= 1e-5 * np.abs(r["g_theta"]).max()
+    assert np.abs(gb_ * float(r["g_out"]) - r["g_beta"]).max() <= 1e-5 * np.abs(r["g_beta"]).max()
+
+
 def test_projection_matches_reference_golden_including_z0_branch():
     g = load_golden("project_uv.npz")
     uv = fo.project_uv(g["xyz"].astype(np.float64), g["K"].astype(np.float64))

@@ -171,15 +171,25 @@ def test_dropin_rebinds_the_reference_in_place(ref):
     orig = (ML.ManoLayer, FKL.ForwardKinematics, UG._get_rot_mat, RT.bone_rel_trafo, CL.L2Loss, CM.MPJPE)
     assert RM.ManoLayer is ML.ManoLayer
     try:
+        reg0 = CL.LossCalculation.__dict__["compute_regularization_loss"]
         done = pkg.install_into_reference()
         assert ML.ManoLayer is pkg.ManoLayer and RM.ManoLayer is pkg.ManoLayer
         assert FKL.ForwardKinematics is pkg.ForwardKinematics and UG._get_rot_mat is pkg._get_rot_mat
-        assert RT.bone_rel_trafo is pkg.bone_rel_trafo and CL.L2Loss is pkg.L2Loss and CM.MPJPE is pkg.MPJPE
-        assert CL.LossCalculation is not None                 # the rest of the reference module is untouched
+        assert CL.L2Loss is pkg.L2Loss and CM.MPJPE is pkg.MPJPE
+        # the per-sample CPU helpers of the reference's Dataset.__getitem__ are NOT swapped by default (the B200
+        # versions are batched GPU-side functions and would break the DataLoader workers) ...
+        assert RT.bone_rel_trafo is orig[3]
+        # ... the two LossCalculation methods are (the rest of the class is untouched)
+        assert CL.LossCalculation.__dict__["compute_regularization_loss"].__mb_replacement__ is pkg.compute_regularization_loss
+        assert CL.LossCalculation.__dict__["compute_hand_mask_loss"].__mb_replacement__ is pkg.compute_hand_mask_loss
         assert "network.sub_modules.MANOLayer.ManoLayer" in done
+        assert "criterions.loss.LossCalculation.compute_regularization_loss" in done
         assert pkg.install_into_reference() == []             # idempotent
+        more = pkg.install_into_reference(dataloader=True)    # opt-in
+        assert RT.bone_rel_trafo is pkg.bone_rel_trafo and "utils.relative_trafo.bone_rel_trafo" in more
     finally:
         assert pkg.dropin.uninstall() > 0
+    assert CL.LossCalculation.__dict__["compute_regularization_loss"] is reg0
     assert (ML.ManoLayer, FKL.ForwardKinematics, UG._get_rot_mat, RT.bone_rel_trafo, CL.L2Loss, CM.MPJPE) == orig
     assert RM.ManoLayer is orig[0]
     # the oracle helper's handle on the live reference was never touched
