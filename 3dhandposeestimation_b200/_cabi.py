@@ -18,6 +18,8 @@ MODE_FP32, MODE_F16X3, MODE_F16 = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "f16x3": MODE_F16X3, "f16": MODE_F16}
 BWD_WORKSPACE_VALID = 1
 MODEL_CHAINS_5X3 = 0x100
+FWD_INFERENCE = 0x200
+FWD_UNFUSED = 0x400
 REDUCE_MPJPE_MM, REDUCE_L2 = 0, 1
 VIS_F32, VIS_U8 = 0, 1
 
@@ -38,7 +40,10 @@ SIGNATURES = {
     "mb_mano_skin_program_stats": (_i, [_p, _p]),
     "mb_mano_workspace_bytes": (_sz, [_i, _i]),
     "mb_mano_forward": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "mb_mano_forward_debug": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _sz, _p, _i, _p]),
     "mb_mano_backward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "mb_affine_forward": (_i, [_p, _p, _p, _p, _i, _p]),
+    "mb_affine_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mb_lbs_workspace_bytes": (_sz, [_i]),
     "mb_lbs_forward": (_i, [_p, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "mb_fk_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
@@ -66,7 +71,7 @@ SIGNATURES = {
     "mb_profile_collect": (_i, [_p, _p]),
 }
 STAGES = ("pose_fwd", "blend_fwd", "lbs_fwd", "lbs_bwd", "blend_bwd", "pose_bwd",
-          "joints_only_fwd", "joints_only_bwd", "fk_fwd", "fk_bwd")
+          "joints_only_fwd", "joints_only_bwd", "fk_fwd", "fk_bwd", "fused_fwd")
 
 
 class ManoB200Error(RuntimeError):

@@ -6,10 +6,7 @@ using namespace mb;
 
 #include "blend_tc.cuh"
 #include "skin.cuh"
-namespace mb {
-size_t blend_tc_blob_bytes();
-void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob_tc);
-}  // namespace mb
+#include "vskin.cuh"
 
 // ---------------------------------------------------------------- bookkeeping
 #include <atomic>
@@ -88,7 +85,7 @@ extern "C" int mb_check_device(void) {
     return major == 10 ? 0 : MB_E_DEVICE;
 }
 
-extern "C" size_t mb_mano_blob_bytes(void) { return blob_layout().total + blend_tc_blob_bytes(); }
+extern "C" size_t mb_mano_blob_bytes(void) { return blob_layout().total + blend_tc_blob_bytes() + vskin_blob_bytes(); }
 
 extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const float* jb, const float* pca, int nc,
                                       const float* pose_mean, const float* skin_w, const int32_t* skin_b,
@@ -176,6 +173,9 @@ extern "C" int mb_mano_pack_constants(const float* basis, const float* j0, const
         for (int c = 0; c < SK_TMPL_PAD; ++c) tm[c] = coord_map[c] >= 0 ? basis[(size_t)FEAT_ONE * NVC + coord_map[c]] : 0.f;
     }
     blend_tc_pack(basis, coord_map.data(), out + L.total);
+    // operand images of the fused lane = vertex forward (vskin.cu): same power-of-two basis scale as the blend images
+    vskin_pack(basis, skin_w, skin_b, reinterpret_cast<const int32_t*>(out + L.sk_perm),
+               reinterpret_cast<const TcBlobHeader*>(out + L.total)->basis_scale_log2, out + L.total + blend_tc_blob_bytes());
     return skin_program_check(host_blob, nullptr);
 }
 
@@ -206,7 +206,7 @@ extern "C" size_t mb_mano_workspace_bytes(int B, int mode) {
 static int check_common(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B, int mode,
                         const void* workspace, size_t workspace_bytes) {
     if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
-    if (mode & ~(0xff | MB_MODEL_CHAINS_5X3)) return MB_E_RANGE;
+    if (mode & ~(0xff | MB_MODEL_CHAINS_5X3 | MB_FWD_INFERENCE | MB_FWD_UNFUSED)) return MB_E_RANGE;
     mode &= 0xff;
     if (mode != MB_MODE_FP32 && mode != MB_MODE_F16X3 && mode != MB_MODE_F16) return MB_E_RANGE;
     if (B == 0) return 0;
@@ -235,12 +235,44 @@ static int pose_and_blend_forward(const void* blob, int nc, const float* rot, co
     unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
     {
         StageTimer t(ST_POSE_FWD, s);
-        rc = use_lane_hand(model_flags, mode, B) ? launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s)
+        rc = use_lane_hand(model_flags, mode, B) ? launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, nullptr, joints, s)
                                                  : launch_pose_forward(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s);
         if (rc) return rc;
     }
     StageTimer t(ST_BLEND_FWD, s);
     return launch_blend_tc_forward(blob, featp, v_posed_t, B, mode, s);
+}
+
+// the fused lane = vertex forward (vskin.cu) serves the batches of the one-thread-per-hand pose kernels
+static inline bool use_fused_forward(int model_flags, int mode, int B) {
+    return use_lane_hand(model_flags, mode, B) && !(model_flags & MB_FWD_UNFUSED);
+}
+
+// pose stage -> fused blend + skinning: verts, fingertip joints; v_posed_t only when a backward will want the workspace
+static int fused_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B, int mode,
+                         int model_flags, char* ws, const WorkLayout& W, float* verts, float* joints, float* dbg, int variant,
+                         cudaStream_t s) {
+    float* bone_t = reinterpret_cast<float*>(ws + W.bone_t);
+    unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
+    unsigned char* bone16 = reinterpret_cast<unsigned char*>(ws + W.bone16);
+    float* v_posed_t = (model_flags & MB_FWD_INFERENCE) ? nullptr : reinterpret_cast<float*>(ws + W.v_posed_t);
+    int rc;
+    { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, bone16, joints, s))) return rc; }
+    StageTimer t(ST_FUSED_FWD, s);
+    return launch_vskin_forward(blob, featp, bone16, B, mode, verts, joints, v_posed_t, dbg, variant, s);
+}
+
+extern "C" int mb_mano_forward_debug(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                                     int B, int mode, float* verts, float* joints, void* workspace, size_t workspace_bytes,
+                                     float* dbg, int variant, mb_stream_t stream) {
+    int rc = check_common(blob, nc, rot, coeffs, betas, B, mode, workspace, workspace_bytes);
+    if (rc || B == 0) return rc;
+    if (!joints || !verts) return MB_E_NULL;
+    const int model_flags = mode & ~0xff;
+    mode &= 0xff;
+    if (!(model_flags & MB_MODEL_CHAINS_5X3) || mode == MB_MODE_FP32) return MB_E_MODEL;
+    return fused_forward(blob, nc, rot, coeffs, betas, B, mode, model_flags, reinterpret_cast<char*>(workspace), work_layout(B, mode),
+                         verts, joints, dbg, variant, (cudaStream_t)stream);
 }
 
 extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
@@ -263,6 +295,8 @@ extern "C" int mb_mano_forward(const void* blob, int nc, const float* rot, const
     mode &= 0xff;
     const WorkLayout W = work_layout(B, mode);
     char* ws = reinterpret_cast<char*>(workspace);
+    if (use_fused_forward(model_flags, mode, B))
+        return fused_forward(blob, nc, rot, coeffs, betas, B, mode, model_flags, ws, W, verts, joints, nullptr, 0, s);
     if ((rc = pose_and_blend_forward(blob, nc, rot, coeffs, betas, B, mode, model_flags, ws, W, joints, s))) return rc;
     StageTimer t(ST_LBS_FWD, s);
     return launch_skin_forward(blob, reinterpret_cast<float*>(ws + W.v_posed_t), reinterpret_cast<float*>(ws + W.bone_t), B,

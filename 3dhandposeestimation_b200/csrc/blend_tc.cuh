@@ -55,6 +55,9 @@ constexpr size_t TCB_B_BYTES = (size_t)TCB_K_CHUNKS * TCB_B_CHUNK_BYTES;
 
 inline size_t tc_dvp_bytes(long long B) { return (size_t)((B + TC_M - 1) / TC_M) * TCB_A_TILE_BYTES; }
 
+size_t blend_tc_blob_bytes();
+void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob_tc);
+
 // dfeat: [B][148] rows, or hand-minor [groups][160][32] when hand_minor != 0
 // ksplit K ranges, each into its own dfeat copy part_stride floats apart (the pose backward adds them)
 int launch_blend_tc_backward(const void* blob, const unsigned char* dvp, float* dfeat, int B, int hand_minor, int ksplit,

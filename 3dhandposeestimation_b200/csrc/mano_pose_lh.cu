@@ -17,6 +17,7 @@
 #include <cuda_fp16.h>
 #include "hand_math.cuh"
 #include "blend_tc.cuh"
+#include "vskin.cuh"
 #include "ptx.cuh"
 
 namespace mb {
@@ -174,13 +175,19 @@ __device__ __forceinline__ void lh_theta(const LhConsts& C, const float* s_coef,
 }
 
 // bone transform with the global rotation folded in: A' = [Rq Rg | Rq (tg - Rg J)]  -> bone_t[group][k][lane][12]
-__device__ __forceinline__ void emit_bone(float* __restrict__ bt, int k, const M3& Rq, const M3& Rg, const V3& tg, const V3& J) {
+// ... and, when bone16 is given, into the fp16 x3 MMA operand of the fused lane = vertex forward (vskin.cuh)
+__device__ __forceinline__ void emit_bone(float* __restrict__ bt, unsigned char* __restrict__ bone16, long long hand, int k,
+                                          const M3& Rq, const M3& Rg, const V3& tg, const V3& J) {
     const M3 Rp = m3_mul(Rq, Rg);
     const V3 tp = m3_vec(Rq, v3_sub(tg, m3_vec(Rg, J)));
     float4* o = reinterpret_cast<float4*>(bt + k * (BONE_F * 32));      // bone_t[group][k][lane][12]
     o[0] = make_float4(Rp.m[0], Rp.m[1], Rp.m[2], tp.x);
     o[1] = make_float4(Rp.m[3], Rp.m[4], Rp.m[5], tp.y);
     o[2] = make_float4(Rp.m[6], Rp.m[7], Rp.m[8], tp.z);
+    if (bone16 != nullptr) {
+        const float A[BONE_F] = {Rp.m[0], Rp.m[1], Rp.m[2], tp.x, Rp.m[3], Rp.m[4], Rp.m[5], tp.y, Rp.m[6], Rp.m[7], Rp.m[8], tp.z};
+        vs_emit_bone16(bone16, hand, k, A);
+    }
 }
 __device__ __forceinline__ void emit_joint(float* __restrict__ jrow, int slot, const M3& Rq, const V3& tg) {
     const V3 j = m3_vec(Rq, tg);
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(LH_WARPS * 32)
 pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
                        const float* __restrict__ coeffs, const float* __restrict__ betas, int B,
                        float* __restrict__ feat, unsigned char* __restrict__ featp, float* __restrict__ bone_t,
-                       float* __restrict__ joints) {
+                       unsigned char* __restrict__ bone16, float* __restrict__ joints) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LhConsts& C = *reinterpret_cast<LhConsts*>(smem_raw);
     lh_stage_constants(C, blob, nc);
@@ -233,7 +240,7 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
         // ---- wrist: constant root rotation [pi, 0, 0] (:76, :128)
         const M3 R0 = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));
         const V3 J0 = rest_joint(C, 0, beta);
-        if (live) { emit_bone(bt, 0, Rq, R0, J0, J0); emit_joint(jrow, 0, Rq, J0); }
+        if (live) { emit_bone(bt, bone16, hand, 0, Rq, R0, J0, J0); emit_joint(jrow, 0, Rq, J0); }
 #pragma unroll
         for (int s = 0; s < NB; ++s) bl[s * BP] = beta[s];
         bl[FEAT_ONE * BP] = 1.f; bl[(FEAT_ONE + 1) * BP] = 0.f; bl[(FEAT_ONE + 2) * BP] = 0.f;
@@ -253,7 +260,7 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
                 const V3 J = rest_joint(C, k, beta);
                 const M3 Rg = m3_mul(Rgp, R);
                 const V3 tg = v3_add(tgp, m3_vec(Rgp, v3_sub(J, Jp)));
-                if (live) { emit_bone(bt, k, Rq, Rg, tg, J); emit_joint(jrow, 1 + 4 * f + i, Rq, tg); }
+                if (live) { emit_bone(bt, bone16, hand, k, Rq, Rg, tg, J); emit_joint(jrow, 1 + 4 * f + i, Rq, tg); }
                 Rgp = Rg; tgp = tg; Jp = J;
             }
         }
@@ -812,10 +819,10 @@ inline int lh_grid(int B) {
 }  // namespace
 
 int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                           int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s) {
+                           int B, float* feat, unsigned char* featp, float* bone_t, unsigned char* bone16, float* joints, cudaStream_t s) {
     static SmemAttrOnce once;
     if (int arc = ensure_dyn_smem(once, pose_forward_lh_kernel, LH_SMEM)) return arc;
-    pose_forward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, B, feat, featp, bone_t, joints);
+    pose_forward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, B, feat, featp, bone_t, bone16, joints);
     return cuda_rc();
 }
 

@@ -1,0 +1,475 @@
+// vskin.cu — blend shapes + linear blend skinning of the forward pass in ONE kernel, LANE = VERTEX, both
+// contractions on the 5th-generation tensor cores (tcgen05), no rest-pose scratch in HBM.
+//
+// Reference: MANOLayer.py:130-137 (v_posed = v_template + S beta + P pf), :177-185 (T_v = sum_k w_vk A_k,
+// v' = T_v [v_posed; 1]), :190-202 (fingertip vertices -> joints 4, 8, 12, 16, 20), :188/:204-205 (global rotation,
+// folded into the bone transforms by the pose stage).
+//
+// Why another mapping (profiles/r1 -> r2): with lane = hand (skin.cu) the weight blend sum_k w_vk A_k costs
+// ~31 FMAs per (vertex, hand) on the CUDA cores plus a transposition of every result through shared memory —
+// 1 750 warp instructions per hand, issue-bound at ~5 ms per 2^20 hands — and the rest-pose vertices cross HBM
+// twice (written by the blend GEMM, read here).  Here both contractions are MMAs with M = 128 VERTICES:
+//   v_posed[v][h] = sum_f basis[v][f] feat[h][f]      three planes x, y, z;  N = 64 hands, K = 160, fp16 hi/lo x 3 products
+//   T[v][(h, e)]  = sum_k W[v][k] A[h][k][e]          N = 4 hands x 12 elements, K = 16 bones, fp16 3-way split, 4 products
+// Both land in TMEM with lane = vertex; the epilogue thread of vertex v reads its rest position (3 columns) and its
+// blended 3x4 transform (12 columns) of a hand, does 12 FMAs, and the warp's 32 consecutive vertices leave through a
+// shared-memory row as ONE contiguous, sector-aligned 1 536-byte bulk store per (hand, vertex tile) of
+// verts[B][778][3] in its natural layout — no transposition, no v_posed_t round trip.
+//
+// Roles (384 threads, 1 CTA per SM, persistent over 64-hand tiles):
+//   warp 0   basis producer: (tile, plane, K chunk) stages of 16 KB, always L2 hits, 4-stage ring
+//   warp 1   MMA issuer (one thread): blend products of vertex tile t+1 interleaved with the transform chunks of tile t
+//   warp 2   TMEM allocation; producer of the per-hand-tile operands (feature rows 40 KB, bone operand 72 KB) and of
+//            the weight tiles (12 KB per vertex tile, double buffered)
+//   warp 3   store warp: bulk stores shared -> global, row heads / tails that cannot be 16-byte aligned
+//   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices), warp / 8 = which two hands of a chunk
+// TMEM (512 columns): two rest-position stages of 3 x 64 columns, two transform stages of 48 columns.
+#include <cuda_fp16.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+#include "blend_tc.cuh"
+#include "vskin.cuh"
+#include "ptx.cuh"
+#include "tc_ptx.cuh"
+
+namespace mb {
+namespace {
+
+constexpr int VS_THREADS = 384;
+constexpr int VS_EPI_WARPS = 8;
+constexpr int VS_ASTAGES = 4;
+constexpr int VS_OSTAGES = 3;
+constexpr int VS_ROW = 392;                        // floats per staging row: up to 6 carried floats + 384 + slack
+constexpr uint32_t VS_TMEM_COLS = 512;
+constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns per rest-position stage
+constexpr uint32_t VS_T_COL0 = 2 * VS_VP_COLS;     // 384: first transform column
+// instruction descriptors: f16 x f16 -> f32, M = 128
+constexpr uint32_t VS_IDESC_BLEND = (1u << 4) | ((uint32_t)(VS_NH >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);                // A, B K-major
+constexpr uint32_t VS_IDESC_T = (1u << 4) | (1u << 16) | ((uint32_t)(VS_TN >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);       // B MN-major
+
+__constant__ int c_vs_tip_vert[5] = {333, 444, 672, 555, 745};
+__constant__ int c_vs_tip_slot[5] = {4, 8, 12, 16, 20};
+
+struct VsShared {
+    alignas(128) unsigned char feat[TC_K_CHUNKS][2][VS_NH * TC_K_CHUNK * 2];      // 40 KB: [K chunk][hi, lo][64 hands x 32]
+    alignas(128) unsigned char bones[VS_NCH][VS_BONE_SPLITS][VS_BONE_CHUNK_BYTES]; // 72 KB
+    alignas(128) unsigned char a[VS_ASTAGES][VS_A_STAGE_BYTES];                    // 64 KB basis ring
+    alignas(128) unsigned char w[2][VS_W_TILE_BYTES];                              // 24 KB weight tiles
+    alignas(128) float out[VS_OSTAGES][VS_HC][VS_ROW];                             // 18.4 KB result rows
+    alignas(16) float carry[2][VS_NH][8];                                          // tail of a hand's row piece, for the next vertex tile
+    alignas(8) unsigned long long a_full[VS_ASTAGES], a_empty[VS_ASTAGES];
+    unsigned long long w_full[2], w_empty[2];
+    unsigned long long feat_full, feat_empty, bones_full, bones_empty;
+    unsigned long long vp_full[2], vp_empty[2];
+    unsigned long long t_full[2], t_empty[2];
+    unsigned long long out_full[VS_OSTAGES], out_empty[VS_OSTAGES];
+    uint32_t tmem_base;
+};
+
+// A wait that cannot hang the GPU: a broken pipeline traps after ~1 s instead of spinning forever.
+__device__ __forceinline__ void vs_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t b = smem_u32(bar);
+    if (mbar_try_wait(b, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(b, parity)) {
+        if (clock64() - t0 > 2000000000LL) __trap();
+    }
+}
+
+// sector alignment of the row pieces: rows of verts[B][778][3] are 9 336 B = 24 (mod 32) apart, so the piece of
+// vertex tile t >= 1 of hand h covers floats [384 t - d, 384 t + 384 - d), d = (0, 6, 4, 2)[h % 4]: every piece starts on
+// a 32-byte boundary; the d floats in front are the tail of the previous tile's results (carry).  Tile 0 starts at the
+// row's first 32-byte boundary (float a = (8 - d) % 8) and its first a floats are plain stores; inside the shared row
+// the results sit S floats in so that the bulk copy's source is 16-byte aligned: S = d for t >= 1, (0, 2, 0, 2)[h % 4] for t = 0.
+__device__ __forceinline__ int vs_d(int hl) { return (8 - 2 * hl) & 7; }                 // hl = h % 4 -> 0, 6, 4, 2
+__device__ __forceinline__ int vs_shift(int t, int hl) { return t == 0 ? ((hl & 1) << 1) : vs_d(hl); }
+
+__global__ void __launch_bounds__(VS_THREADS, 1)
+vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ vs_basis,
+                     const unsigned char* __restrict__ vs_w, const float4* __restrict__ vs_tmpl,
+                     const unsigned char* __restrict__ featp, const unsigned char* __restrict__ bone16,
+                     int B, int ntiles, int blend_products, int t_products,
+                     float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ v_posed_t,
+                     float* __restrict__ dbg, int variant) {
+    extern __shared__ unsigned char smem_raw[];
+    VsShared& S = *reinterpret_cast<VsShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VS_ASTAGES; ++s) { mbar_init(smem_u32(&S.a_full[s]), 1); mbar_init(smem_u32(&S.a_empty[s]), 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&S.w_full[s]), 1); mbar_init(smem_u32(&S.w_empty[s]), 1);
+            mbar_init(smem_u32(&S.vp_full[s]), 1); mbar_init(smem_u32(&S.vp_empty[s]), VS_EPI_WARPS);
+            mbar_init(smem_u32(&S.t_full[s]), 1); mbar_init(smem_u32(&S.t_empty[s]), VS_EPI_WARPS);
+        }
+        mbar_init(smem_u32(&S.feat_full), 1); mbar_init(smem_u32(&S.feat_empty), 1);
+        mbar_init(smem_u32(&S.bones_full), 1); mbar_init(smem_u32(&S.bones_empty), 1);
+        for (int s = 0; s < VS_OSTAGES; ++s) { mbar_init(smem_u32(&S.out_full[s]), VS_EPI_WARPS); mbar_init(smem_u32(&S.out_empty[s]), 1); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&S.tmem_base), VS_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== basis producer: the same 105-stage stream for every hand tile, kept in L2 =====
+            const uint64_t keep = l2_policy_evict_last();
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int i = 0; i < VS_NT * VS_STAGES_PER_TILE; ++i) {
+                    vs_wait(&S.a_empty[stage], phase ^ 1);
+                    mbar_expect_tx(smem_u32(&S.a_full[stage]), VS_A_STAGE_BYTES);
+                    bulk_g2s_hint(smem_u32(S.a[stage]), vs_basis + (size_t)i * VS_A_STAGE_BYTES, VS_A_STAGE_BYTES,
+                                  smem_u32(&S.a_full[stage]), keep);
+                    if (++stage == VS_ASTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ===== per-hand-tile operands (features, bones) and the weight tiles =====
+            const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
+            uint32_t it = 0, gw = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                vs_wait(&S.feat_empty, (it & 1) ^ 1);
+                mbar_expect_tx(smem_u32(&S.feat_full), TC_K_CHUNKS * 2 * 4096);
+                const unsigned char* fsrc = featp + (size_t)(tile >> 1) * TC_A_TILE_BYTES + (size_t)(tile & 1) * 4096;
+                for (int c = 0; c < TC_K_CHUNKS; ++c)
+                    for (int sp = 0; sp < 2; ++sp)
+                        bulk_g2s_hint(smem_u32(S.feat[c][sp]), fsrc + (size_t)c * TC_A_STAGE_BYTES + (size_t)sp * TC_A_BLOCK_BYTES, 4096,
+                                      smem_u32(&S.feat_full), once);
+                vs_wait(&S.bones_empty, (it & 1) ^ 1);
+                mbar_expect_tx(smem_u32(&S.bones_full), VS_BONE_TILE_BYTES);
+                const unsigned char* bsrc = bone16 + (size_t)tile * VS_BONE_TILE_BYTES;
+                for (int q = 0; q < 4; ++q)
+                    bulk_g2s_hint(smem_u32(&S.bones[0][0][0]) + q * (VS_BONE_TILE_BYTES / 4), bsrc + (size_t)q * (VS_BONE_TILE_BYTES / 4),
+                                  VS_BONE_TILE_BYTES / 4, smem_u32(&S.bones_full), once);
+                for (int t = 0; t < VS_NT; ++t, ++gw) {
+                    vs_wait(&S.w_empty[gw & 1], ((gw >> 1) & 1) ^ 1);
+                    mbar_expect_tx(smem_u32(&S.w_full[gw & 1]), VS_W_TILE_BYTES);
+                    bulk_g2s_hint(smem_u32(S.w[gw & 1]), vs_w + (size_t)t * VS_W_TILE_BYTES, VS_W_TILE_BYTES, smem_u32(&S.w_full[gw & 1]), keep);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            uint32_t a_stage = 0, a_phase = 0, gt = 0, tc = 0, it = 0;
+            const uint64_t a_base = umma_desc(smem_u32(S.a[0]), TC_LBO, TC_SBO);
+            const uint64_t f_base = umma_desc(smem_u32(S.feat[0][0]), TC_LBO, TC_SBO);
+            // weights: K-major, K = 16 bones = 2 core matrices 128 B apart, 8-row groups 256 B apart
+            const uint64_t w_base = umma_desc(smem_u32(S.w[0]), 128, 256);
+            // bones: MN-major, n-groups 256 B apart (SBO), k-groups 128 B apart (LBO); variant 1 swaps the two fields
+            const uint64_t b_base = (variant & 1) ? umma_desc(smem_u32(&S.bones[0][0][0]), 256, 128)
+                                                  : umma_desc(smem_u32(&S.bones[0][0][0]), 128, 256);
+            // one (plane, K chunk) stage of the blend products of vertex-tile counter g
+            auto blend_stage = [&](uint32_t g, int k) {
+                const int p = k / TC_K_CHUNKS, c = k - p * TC_K_CHUNKS;
+                if (k == 0) { vs_wait(&S.vp_empty[g & 1], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
+                vs_wait(&S.a_full[a_stage], a_phase);
+                tc_fence_after();
+                const uint32_t d = tmem + (g & 1) * VS_VP_COLS + p * VS_NH;
+                const uint64_t a_st = a_base + (uint64_t)((a_stage * VS_A_STAGE_BYTES) >> 4);
+#pragma unroll
+                for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
+                    const uint64_t a_hi = a_st + (uint64_t)((j * 2 * (int)TC_LBO) >> 4);
+                    const uint64_t a_lo = a_hi + (uint64_t)((VS_A_STAGE_BYTES / 2) >> 4);
+                    const uint64_t b_hi = f_base + (uint64_t)((c * 2 * 4096 + j * 2 * (int)TC_LBO) >> 4);
+                    const uint64_t b_lo = b_hi + (uint64_t)(4096 >> 4);
+                    umma_f16(d, a_hi, b_hi, VS_IDESC_BLEND, (c | j) ? 1u : 0u);
+                    if (blend_products == 3) {
+                        umma_f16(d, a_lo, b_hi, VS_IDESC_BLEND, 1);
+                        umma_f16(d, a_hi, b_lo, VS_IDESC_BLEND, 1);
+                    }
+                }
+                tc_commit(smem_u32(&S.a_empty[a_stage]));
+                if (++a_stage == VS_ASTAGES) { a_stage = 0; a_phase ^= 1; }
+                if (k == VS_STAGES_PER_TILE - 1) tc_commit(smem_u32(&S.vp_full[g & 1]));
+            };
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                vs_wait(&S.feat_full, it & 1);
+                tc_fence_after();
+                for (int k = 0; k < VS_STAGES_PER_TILE; ++k) blend_stage(gt, k);
+                vs_wait(&S.bones_full, it & 1);
+                tc_fence_after();
+                for (int t = 0; t < VS_NT; ++t, ++gt) {
+                    vs_wait(&S.w_full[gt & 1], (gt >> 1) & 1);
+                    tc_fence_after();
+                    const uint64_t w1 = w_base + (uint64_t)(((gt & 1) * VS_W_TILE_BYTES) >> 4);
+                    const uint64_t w2 = w1 + (uint64_t)(4096 >> 4), w3 = w2 + (uint64_t)(4096 >> 4);
+                    for (int ch = 0; ch < VS_NCH; ++ch, ++tc) {
+                        const uint32_t ts = tc & 1;
+                        vs_wait(&S.t_empty[ts], ((tc >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem + VS_T_COL0 + ts * VS_TN;
+                        const uint64_t a1 = b_base + (uint64_t)((ch * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES) >> 4);
+                        const uint64_t a2 = a1 + (uint64_t)(VS_BONE_CHUNK_BYTES >> 4), a3 = a2 + (uint64_t)(VS_BONE_CHUNK_BYTES >> 4);
+                        umma_f16(d, w1, a1, VS_IDESC_T, 0);
+                        if (t_products >= 3) { umma_f16(d, w1, a2, VS_IDESC_T, 1); umma_f16(d, w2, a1, VS_IDESC_T, 1); }
+                        if (t_products >= 4) umma_f16(d, w1, a3, VS_IDESC_T, 1);
+                        if (t_products >= 5) umma_f16(d, w2, a2, VS_IDESC_T, 1);
+                        if (t_products >= 6) umma_f16(d, w3, a1, VS_IDESC_T, 1);
+                        tc_commit(smem_u32(&S.t_full[ts]));
+                        // the next vertex tile's blend products, one stage per chunk (15 stages over 16 chunks)
+                        if (t + 1 < VS_NT && ch < VS_STAGES_PER_TILE) blend_stage(gt + 1, ch);
+                    }
+                    tc_commit(smem_u32(&S.w_empty[gt & 1]));
+                    if (t == VS_NT - 2) tc_commit(smem_u32(&S.feat_empty));        // blend products of the last vertex tile are issued
+                }
+                tc_commit(smem_u32(&S.bones_empty));
+            }
+        }
+    } else if (warp == 3) {
+        // ===== store warp =====
+        uint32_t oc = 0, gt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long hand0 = (long long)tile * VS_NH;
+            for (int t = 0; t < VS_NT; ++t, ++gt) {
+                for (int ch = 0; ch < VS_NCH; ++ch, ++oc) {
+                    const uint32_t ob = oc % VS_OSTAGES;
+                    vs_wait(&S.out_full[ob], (oc / VS_OSTAGES) & 1);
+                    // carried floats of the previous vertex tile go in front of the results (generic writes, made visible to
+                    // the bulk-copy engine by the proxy fence below)
+                    if (t >= 1 && lane < 4 * 8) {
+                        const int hl = lane >> 3, i = lane & 7;
+                        if (i < vs_d(hl)) S.out[ob][hl][i] = S.carry[gt & 1][ch * VS_HC + hl][i];
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (t == 0 || t == VS_NT - 1) {
+                        // row heads (tile 0) and the short last tile: plain stores
+                        for (int hl = 0; hl < VS_HC; ++hl) {
+                            const long long hand = hand0 + ch * VS_HC + hl;
+                            if (hand >= B) break;
+                            const int d = vs_d(hl);
+                            float* grow = verts + (size_t)hand * NVC;
+                            const float* row = S.out[ob][hl];
+                            if (t == 0) {
+                                const int a = (8 - d) & 7, sh = vs_shift(0, hl);
+                                if (lane < a) grow[lane] = row[sh + lane];
+                            } else {
+                                const int n = NVC - (VS_NT - 1) * 3 * VS_M + d;          // 30 + d floats
+                                for (int i = lane; i < n; i += 32) grow[(VS_NT - 1) * 3 * VS_M - d + i] = row[i];
+                            }
+                        }
+                    }
+                    if (lane < VS_HC) {
+                        const int hl = lane;
+                        const long long hand = hand0 + ch * VS_HC + hl;
+                        if (hand < B && t < VS_NT - 1) {
+                            const int d = vs_d(hl);
+                            float* grow = verts + (size_t)hand * NVC;
+                            if (t == 0) {
+                                const int a = (8 - d) & 7, sh = vs_shift(0, hl);
+                                bulk_s2g(grow + a, smem_u32(&S.out[ob][hl][sh + a]), (uint32_t)(3 * VS_M - d - a) * 4u);
+                            } else {
+                                bulk_s2g(grow + 3 * VS_M * t - d, smem_u32(&S.out[ob][hl][0]), 3 * VS_M * 4u);
+                            }
+                        }
+                        bulk_commit();
+                        bulk_wait_read<1>();                                   // the previous chunk's rows have been read
+                    }
+                    __syncwarp();
+                    if (oc > 0 && lane == 0) mbar_arrive(smem_u32(&S.out_empty[(oc - 1) % VS_OSTAGES]));
+                }
+            }
+        }
+        if (lane < VS_HC) bulk_wait_all<0>();
+    } else {
+        // ===== epilogue: thread = vertex =====
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int vl = q * 32 + lane;                                  // vertex inside the tile
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const float osv = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
+        const float ost = exp2f(-(float)(VS_W_SCALE_LOG2 + VS_BONE_SCALE_LOG2));
+        uint32_t gt = 0, tc = 0, oc = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long hand0 = (long long)tile * VS_NH;
+            for (int t = 0; t < VS_NT; ++t, ++gt) {
+                const int vtx = t * VS_M + vl;
+                const bool valid = vtx < NV;
+                const float4 tm = vs_tmpl[vtx];
+                int tipslot = -1;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) if (vtx == c_vs_tip_vert[i]) tipslot = c_vs_tip_slot[i];
+                const uint32_t vp_addr = tmem + lane_addr + (gt & 1) * VS_VP_COLS;
+                vs_wait(&S.vp_full[gt & 1], (gt >> 1) & 1);
+                tc_fence_after();
+                if (v_posed_t != nullptr) {
+                    // rest-pose scratch for the skinning backward: v_posed_t[group][3 pos + p][32 hands], this warp's 32 hands
+                    const long long group = (long long)tile * 2 + half;
+                    const int pos3 = __float_as_int(tm.w);
+                    const bool live = valid && pos3 >= 0 && group * 32 < B;
+#pragma unroll 1
+                    for (int p = 0; p < 3; ++p) {
+                        uint32_t r[32];
+                        tmem_ld32_nowait(vp_addr + p * VS_NH + half * 32, r);
+                        tmem_ld_wait();
+                        if (live) {
+                            const float tp = p == 0 ? tm.x : (p == 1 ? tm.y : tm.z);
+                            float4* dst = reinterpret_cast<float4*>(v_posed_t + ((size_t)group * SK_NCOORD + pos3 + p) * 32);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                __stcs(dst + i, make_float4(fmaf(__uint_as_float(r[4 * i]), osv, tp), fmaf(__uint_as_float(r[4 * i + 1]), osv, tp),
+                                                            fmaf(__uint_as_float(r[4 * i + 2]), osv, tp), fmaf(__uint_as_float(r[4 * i + 3]), osv, tp)));
+                        }
+                    }
+                }
+                for (int ch = 0; ch < VS_NCH; ++ch, ++tc, ++oc) {
+                    const uint32_t ts = tc & 1;
+                    vs_wait(&S.t_full[ts], (tc >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t T[24], X[2], Y[2], Z[2];
+                    const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + ts * VS_TN + half * 24;
+                    tmem_ld16_nowait(t_addr, T);
+                    tmem_ld8_nowait(t_addr + 16, T + 16);
+                    const uint32_t x_addr = vp_addr + ch * VS_HC + half * 2;
+                    tmem_ld2_nowait(x_addr, X);
+                    tmem_ld2_nowait(x_addr + VS_NH, Y);
+                    tmem_ld2_nowait(x_addr + 2 * VS_NH, Z);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[ts]));
+                    const uint32_t ob = oc % VS_OSTAGES;
+                    vs_wait(&S.out_empty[ob], ((oc / VS_OSTAGES) & 1) ^ 1);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int hl = half * 2 + hh;
+                        const float x = fmaf(__uint_as_float(X[hh]), osv, tm.x);
+                        const float y = fmaf(__uint_as_float(Y[hh]), osv, tm.y);
+                        const float z = fmaf(__uint_as_float(Z[hh]), osv, tm.z);
+                        float o[3];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const float* Ti = reinterpret_cast<const float*>(T) + hh * 12 + 4 * i;
+                            o[i] = ost * fmaf(Ti[0], x, fmaf(Ti[1], y, fmaf(Ti[2], z, Ti[3])));
+                        }
+                        if (dbg != nullptr && tile == 0 && t == 0 && ch == 0) {
+                            float* dd = dbg + ((size_t)hl * VS_M + vl) * 16;
+#pragma unroll
+                            for (int i = 0; i < 12; ++i) dd[i] = ost * __uint_as_float(T[hh * 12 + i]);
+                            dd[12] = x; dd[13] = y; dd[14] = z; dd[15] = 0.f;
+                        }
+                        if (valid) {
+                            const int d = vs_d(hl);
+                            float* row = S.out[ob][hl] + vs_shift(t, hl) + 3 * vl;
+                            row[0] = o[0]; row[1] = o[1]; row[2] = o[2];
+                            if (t + 1 < VS_NT && vl >= VS_M - 2) {
+                                // the last d floats of this tile's piece open the next tile's piece
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    const int j = 3 * vl + i - (3 * VS_M - d);
+                                    if (j >= 0) S.carry[(gt + 1) & 1][ch * VS_HC + hl][j] = o[i];
+                                }
+                            }
+                            if (tipslot >= 0) {
+                                const long long hand = hand0 + ch * VS_HC + hl;
+                                if (hand < B) {
+                                    float* jo = joints + (size_t)hand * (NOUTJ * 3) + tipslot * 3;
+                                    jo[0] = o[0]; jo[1] = o[1]; jo[2] = o[2];
+                                }
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&S.out_full[ob]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&S.vp_empty[gt & 1]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, VS_TMEM_COLS);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host side
+size_t vskin_blob_bytes() { return vs_blob_layout().total; }
+
+void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, const int32_t* sk_perm, int basis_scale_log2,
+                void* host_section) {
+    const VsBlobLayout L = vs_blob_layout();
+    unsigned char* out = reinterpret_cast<unsigned char*>(host_section);
+    memset(out, 0, L.total);
+    const float sb = ldexpf(1.f, basis_scale_log2);
+    // blend basis as the A operand: rows = vertices of the tile, one image per coordinate plane
+    __half* bdst = reinterpret_cast<__half*>(out + L.basis);
+    for (int t = 0; t < VS_NT; ++t)
+        for (int p = 0; p < 3; ++p)
+            for (int c = 0; c < TC_K_CHUNKS; ++c)
+                for (int r = 0; r < VS_M; ++r)
+                    for (int kk = 0; kk < TC_K_CHUNK; ++kk) {
+                        const int v = t * VS_M + r, k = c * TC_K_CHUNK + kk;
+                        const float x = (v < NV && k < TC_K_REAL) ? basis[(size_t)k * NVC + v * 3 + p] * sb : 0.f;
+                        const __half hi = __float2half_rn(x);
+                        const __half lo = __float2half_rn(x - __half2float(hi));
+                        const size_t stage = (size_t)(t * 3 + p) * TC_K_CHUNKS + c;
+                        const size_t in = (((size_t)(r >> 3) * (TC_K_CHUNK / 8) + (kk >> 3)) * 8 + (r & 7)) * 8 + (kk & 7);
+                        bdst[stage * (VS_A_STAGE_BYTES / 2) + in] = hi;
+                        bdst[stage * (VS_A_STAGE_BYTES / 2) + (VS_A_STAGE_BYTES / 4) + in] = lo;
+                    }
+    // dense skinning weights W[vertex][bone] in three fp16 splits, K-major (K = bone)
+    std::vector<float> dense((size_t)NV * NJ, 0.f);
+    for (int v = 0; v < NV; ++v)
+        for (int s = 0; s < MAX_INFL; ++s) {
+            const float w = skin_w[v * MAX_INFL + s];
+            const int b = skin_b[v * MAX_INFL + s];
+            if (w != 0.f && b >= 0 && b < NJ) dense[(size_t)v * NJ + b] += w;
+        }
+    __half* wdst = reinterpret_cast<__half*>(out + L.w);
+    const float sw = (float)(1 << VS_W_SCALE_LOG2);
+    for (int t = 0; t < VS_NT; ++t)
+        for (int r = 0; r < VS_M; ++r)
+            for (int k = 0; k < NJ; ++k) {
+                const int v = t * VS_M + r;
+                float x = v < NV ? dense[(size_t)v * NJ + k] * sw : 0.f;
+                const size_t in = (((size_t)(r >> 3) * 2 + (k >> 3)) * 8 + (r & 7)) * 8 + (k & 7);
+                for (int s = 0; s < VS_W_SPLITS; ++s) {
+                    const __half h = __float2half_rn(x);
+                    x -= __half2float(h);
+                    wdst[((size_t)t * VS_W_SPLITS + s) * (VS_M * NJ) + in] = h;
+                }
+            }
+    // v_template per vertex + the vertex' row in the block-order rest-pose scratch
+    float* tm = reinterpret_cast<float*>(out + L.tmpl);
+    std::vector<int> pos_of(NV, -1);
+    for (int p = 0; p < SK_NPOS; ++p) if (sk_perm[p] >= 0 && sk_perm[p] < NV) pos_of[sk_perm[p]] = p;
+    for (int v = 0; v < VS_NT * VS_M; ++v) {
+        int pos3 = -1;
+        for (int c = 0; c < 3; ++c) tm[v * 4 + c] = v < NV ? basis[(size_t)FEAT_ONE * NVC + v * 3 + c] : 0.f;
+        if (v < NV && pos_of[v] >= 0) pos3 = pos_of[v] * 3;
+        memcpy(&tm[v * 4 + 3], &pos3, sizeof(int));
+    }
+}
+
+int launch_vskin_forward(const void* blob, const unsigned char* featp, const unsigned char* bone16, int B, int mode,
+                         float* verts, float* joints, float* v_posed_t, float* dbg, int variant, cudaStream_t s) {
+    if (B <= 0) return 0;
+    static SmemAttrOnce once;
+    const size_t smem = sizeof(VsShared) + 128;
+    if (int arc = ensure_dyn_smem(once, vskin_forward_kernel, smem)) return arc;
+    const BlobLayout L = blob_layout();
+    const unsigned char* tc = blob_ptr<unsigned char>(blob, L.total);
+    const unsigned char* vs = tc + blend_tc_blob_bytes();
+    const VsBlobLayout V = vs_blob_layout();
+    const int ntiles = (B + VS_NH - 1) / VS_NH;
+    int t_products = (variant >> 4) & 7;
+    if (t_products == 0) t_products = 4;
+    vskin_forward_kernel<<<ntiles < NUM_SMS ? ntiles : NUM_SMS, VS_THREADS, smem, s>>>(
+        reinterpret_cast<const TcBlobHeader*>(tc), vs + V.basis, vs + V.w, reinterpret_cast<const float4*>(vs + V.tmpl), featp, bone16,
+        B, ntiles, mode == MB_MODE_F16X3 ? 3 : 1, t_products, verts, joints, v_posed_t, dbg, variant);
+    return cuda_rc();
+}
+
+}  // namespace mb

@@ -39,7 +39,7 @@ class _ManoFunction(torch.autograd.Function):
 
     @staticmethod
     @_cabi.on_tensor_device
-    def forward(ctx, rot, coeffs, betas, layer, want_verts):
+    def forward(ctx, rot, coeffs, betas, transl, scale, layer, want_verts):
         lib = _cabi.lib()
         B = rot.shape[0]
         dev = rot.device
@@ -47,12 +47,17 @@ class _ManoFunction(torch.autograd.Function):
         joints = torch.empty((B, 21, 3), dtype=torch.float32, device=dev)
         stream = _cabi.stream_handle(dev)
         ws = None
+        # no gradient will be asked for (torch.no_grad(), or no input requires grad): the forward keeps no scratch
+        need_bwd = any(ctx.needs_input_grad[:3])
         if want_verts:
             verts = torch.empty((B, 778, 3), dtype=torch.float32, device=dev)
             nbytes = lib.mb_mano_workspace_bytes(B, layer._mode)
             ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+            fwd_mode = layer._mode | layer._fwd_flags
+            if not (need_bwd and layer.keep_workspace):
+                fwd_mode |= _cabi.FWD_INFERENCE
             _cabi.check(lib.mb_mano_forward(layer._blob.data_ptr(), nc, rot.data_ptr(), coeffs.data_ptr(),
-                                            betas.data_ptr(), B, layer._mode, verts.data_ptr(), joints.data_ptr(),
+                                            betas.data_ptr(), B, fwd_mode, verts.data_ptr(), joints.data_ptr(),
                                             ws.data_ptr(), ws.numel(), stream), "mb_mano_forward")
         else:
             verts = None
@@ -60,12 +65,24 @@ class _ManoFunction(torch.autograd.Function):
                                             betas.data_ptr(), B, layer._mode, None, joints.data_ptr(),
                                             None, 0, stream), "mb_mano_forward(joints only)")
         ctx.layer = layer
-        ctx.ws = ws if (layer.keep_workspace and want_verts) else None
+        ctx.ws = ws if (layer.keep_workspace and want_verts and need_bwd) else None
         ctx.ws_valid = ctx.ws is not None
-        ctx.save_for_backward(rot, coeffs, betas)
+        ctx.affine = transl is not None or scale is not None
+        if ctx.affine:
+            # p' = scale * p + transl per hand, in place on the outputs (csrc/affine.cu)
+            _cabi.check(lib.mb_affine_forward(_cabi.ptr(verts), joints.data_ptr(), _cabi.ptr(scale), _cabi.ptr(transl), B, stream),
+                        "mb_affine_forward")
         ctx.set_materialize_grads(False)
         if want_verts:
+            if ctx.affine and any(ctx.needs_input_grad[:5]):
+                ctx.save_for_backward(rot, coeffs, betas, transl, scale, verts, joints)
+            else:
+                ctx.save_for_backward(rot, coeffs, betas, transl, scale)
             return verts, joints
+        if ctx.affine and any(ctx.needs_input_grad[:5]):
+            ctx.save_for_backward(rot, coeffs, betas, transl, scale, None, joints)
+        else:
+            ctx.save_for_backward(rot, coeffs, betas, transl, scale)
         placeholder = joints.new_empty((0,))
         ctx.mark_non_differentiable(placeholder)
         return placeholder, joints
@@ -73,7 +90,9 @@ class _ManoFunction(torch.autograd.Function):
     @staticmethod
     @_cabi.on_tensor_device
     def backward(ctx, g_verts, g_joints):
-        rot, coeffs, betas = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        rot, coeffs, betas, transl, scale = saved[:5]
+        verts_out, joints_out = (saved[5], saved[6]) if len(saved) > 5 else (None, None)
         layer = ctx.layer
         lib = _cabi.lib()
         B = rot.shape[0]
@@ -111,7 +130,17 @@ class _ManoFunction(torch.autograd.Function):
                         "mb_mano_backward")
             if not ctx.ws_valid:
                 ctx.ws = None                 # consumed: let the caching allocator reuse it (stream-ordered)
-        return g_rot, g_coeffs, g_betas, None, None
+        g_transl = g_scale = None
+        if ctx.affine:
+            if transl is not None and ctx.needs_input_grad[3]:
+                g_transl = torch.empty_like(transl)
+            if scale is not None and ctx.needs_input_grad[4]:
+                g_scale = torch.empty_like(scale)
+            _cabi.check(lib.mb_affine_backward(_cabi.ptr(g_verts), g_joints.data_ptr(), _cabi.ptr(verts_out), _cabi.ptr(joints_out),
+                                               _cabi.ptr(scale), _cabi.ptr(transl), B, nc, _cabi.ptr(g_scale), _cabi.ptr(g_transl),
+                                               g_rot.data_ptr(), g_coeffs.data_ptr(), g_betas.data_ptr(), stream),
+                        "mb_affine_backward")
+        return g_rot, g_coeffs, g_betas, g_transl, g_scale, None, None
 
 
 BLOB_SUFFIX = ".mb20.npz"
@@ -126,11 +155,13 @@ class ManoLayer(nn.Module):
     numpy arrays with the pkl's keys, e.g. ``assets.synthetic_mano()``) instead
     of a pkl path; ``mode`` in {"fp32", "f16x3", "f16"} selects the blend-shape
     contraction precision; ``keep_workspace`` trades 12 KB/hand of retained
-    memory for not recomputing the forward in the backward.
+    memory for not recomputing the forward in the backward; ``fused_forward=False``
+    forces the separate blend-contraction and skinning kernels where the fused
+    lane = vertex kernel would run (batches of 8 192 hands and more).
     """
 
     def __init__(self, device, MANO_RIGHT_pkl=None, bases_num=10, pose_num=6, *, model=None, mode="f16x3",
-                 keep_workspace=True):
+                 keep_workspace=True, fused_forward=True):
         super().__init__()
         self.device = device
         self.bases_num = bases_num
@@ -142,6 +173,7 @@ class ManoLayer(nn.Module):
         self._mode = _cabi.MODES[mode]      # model property bits (mb_mano_model_flags) are OR-ed in below
         self.mode = mode
         self.keep_workspace = bool(keep_workspace)
+        self._fwd_flags = 0 if fused_forward else _cabi.FWD_UNFUSED
 
         if model is None:
             if MANO_RIGHT_pkl is None:
@@ -231,9 +263,12 @@ class ManoLayer(nn.Module):
             self._upload(dev)
         return self._dev
 
-    def rot_pose_beta_to_mesh(self, rots, poses, betas, joints_only=False):
+    def rot_pose_beta_to_mesh(self, rots, poses, betas, joints_only=False, transl=None, scale=None):
         """MANOLayer.py:122-208.  ``joints_only=True`` (extension) skips the 778-vertex
-        contraction and returns ``(None, joint)`` — the only output the heads use."""
+        contraction and returns ``(None, joint)`` — the only output the heads use.
+        ``transl[B,3]`` / ``scale[B]`` or ``[B,1]`` (extensions, default None = the reference's
+        behaviour): every vertex and joint of hand b becomes ``scale[b] * p + transl[b]``,
+        differentiable in both (the post-ops of resnet50MANO.py:77-81 folded into the layer)."""
         dev = self._require_device()
         if self.bases_num != 10:
             raise RuntimeError("bases_num must be 10 (the reference's view at MANOLayer.py:131 fails otherwise)")
@@ -244,9 +279,17 @@ class ManoLayer(nn.Module):
         if rots.shape != (B, 3) or poses.shape != (B, self.pose_num) or betas.shape != (B, 10):
             raise RuntimeError(f"expected rots[B,3], poses[B,{self.pose_num}], betas[B,10]; got "
                                f"{tuple(rots.shape)}, {tuple(poses.shape)}, {tuple(betas.shape)}")
-        verts, joints = _ManoFunction.apply(rots, poses, betas, self, not joints_only)
+        if transl is not None:
+            transl = _as_f32_cuda(transl, "transl", dev)
+            if transl.shape != (B, 3):
+                raise RuntimeError(f"expected transl[B,3], got {tuple(transl.shape)}")
+        if scale is not None:
+            scale = _as_f32_cuda(scale, "scale", dev)
+            if scale.numel() != B:
+                raise RuntimeError(f"expected scale[B] or [B,1], got {tuple(scale.shape)}")
+        verts, joints = _ManoFunction.apply(rots, poses, betas, transl, scale, self, not joints_only)
         return (None if joints_only else verts), joints
 
-    def forward(self, root_angles, other_angles, betas):
-        """MANOLayer.py:238-240."""
-        return self.rot_pose_beta_to_mesh(root_angles, other_angles, betas)
+    def forward(self, root_angles, other_angles, betas, *, transl=None, scale=None):
+        """MANOLayer.py:238-240; ``transl`` / ``scale`` are keyword-only extensions (see rot_pose_beta_to_mesh)."""
+        return self.rot_pose_beta_to_mesh(root_angles, other_angles, betas, transl=transl, scale=scale)

@@ -53,6 +53,14 @@ extern "C" {
  * It lets large batches run the one-thread-per-hand pose kernels; mb_mano_model_flags computes it. */
 #define MB_MODEL_CHAINS_5X3 0x100
 
+/* Forward options, OR-ed into `mode` of mb_mano_forward:
+ * MB_FWD_INFERENCE: no backward will follow — the forward keeps no rest-pose scratch in the workspace (a later
+ *                   mb_mano_backward must then be called WITHOUT MB_BWD_WORKSPACE_VALID and recomputes it);
+ * MB_FWD_UNFUSED  : run the separate blend-contraction and skinning kernels even where the fused kernel applies
+ *                   (measurement / cross-checking). */
+#define MB_FWD_INFERENCE 0x200
+#define MB_FWD_UNFUSED   0x400
+
 /* mb_mano_backward flags */
 #define MB_BWD_WORKSPACE_VALID 1  /* workspace still holds the forward's intermediates for these inputs */
 
@@ -104,6 +112,27 @@ MB_API int mb_mano_forward(const void* blob, int nc,
                     const float* rot, const float* coeffs, const float* betas, int B, int mode,
                     float* verts, float* joints,
                     void* workspace, size_t workspace_bytes, mb_stream_t stream);
+/* Diagnostics of the fused lane = vertex forward (csrc/vskin.cu; needs MB_MODEL_CHAINS_5X3 and a tensor-core mode, any B):
+ * the same outputs as mb_mano_forward through that kernel, plus — dbg (nullable, device float[4][128][16]) — the blended
+ * 3x4 transforms (12) and rest positions (3) of vertices 0..127 of hands 0..3 as the epilogue sees them.  variant: bit 0
+ * swaps the leading / stride fields of the MN-major operand descriptor, bits 4-6 = number of split products of the
+ * transform contraction (0 = default 4). */
+MB_API int mb_mano_forward_debug(const void* blob, int nc,
+                    const float* rot, const float* coeffs, const float* betas, int B, int mode,
+                    float* verts, float* joints, void* workspace, size_t workspace_bytes,
+                    float* dbg, int variant, mb_stream_t stream);
+
+/* Optional per-hand scale and translation of the layer's outputs — the `transl=` / `scale=` keyword extension of
+ * ManoLayer.forward (the reference's layer has none, MANOLayer.py:238; its callers apply the equivalent post-ops on
+ * the outputs: resnet50MANO.py:77-81, Resnet50MANO3DHandPose.py:35-60):  p' = scale[h] * p + transl[h], in place, for
+ * verts[B][778][3] (nullable) and joints[B][21][3]; scale[B] / transl[B][3] may each be NULL. */
+MB_API int mb_affine_forward(float* verts, float* joints, const float* scale, const float* transl, int B, mb_stream_t stream);
+/* Its backward, to be called AFTER mb_mano_backward was run on the same upstream gradients: g_transl[h] = sum of the
+ * hand's g, g_scale[h] = sum <g, (p' - transl) / scale> from the transformed outputs, and — the MANO backward being
+ * linear in g — the parameter gradients g_rot / g_coeffs / g_betas are multiplied by scale[h] in place. */
+MB_API int mb_affine_backward(const float* g_verts, const float* g_joints, const float* verts_out, const float* joints_out,
+                       const float* scale, const float* transl, int B, int nc, float* g_scale, float* g_transl,
+                       float* g_rot, float* g_coeffs, float* g_betas, mb_stream_t stream);
 
 /* Replaces the autograd tape of MANOLayer.py:122-208.
  *   g_verts[B][778][3] (NULL = zero: the heads' joints-only case), g_joints[B][21][3]
@@ -269,8 +298,8 @@ MB_API int mb_adam_step(float* param, const float* grad, float* exp_avg, float* 
  * mb_profile_enable(1): bracket every stage launch with CUDA events on its stream;
  * mb_profile_collect: synchronise on those events, write the summed milliseconds and launch
  * counts per stage (MB_N_STAGES entries each) and reset.  Stage order: pose_fwd, blend_fwd,
- * lbs_fwd, lbs_bwd, blend_bwd, pose_bwd, joints_only_fwd, joints_only_bwd, fk_fwd, fk_bwd. */
-#define MB_N_STAGES 10
+ * lbs_fwd, lbs_bwd, blend_bwd, pose_bwd, joints_only_fwd, joints_only_bwd, fk_fwd, fk_bwd, fused_fwd. */
+#define MB_N_STAGES 11
 MB_API long long mb_launch_count(void);
 MB_API void      mb_profile_enable(int on);
 MB_API int       mb_profile_collect(double* ms, long long* counts);

@@ -48,6 +48,28 @@ def mano_case(pkl, nc, B, seed, scale_pose=np.pi):
                 gj_rot=n(jo[0]), gj_pose=n(jo[1]), gj_beta=n(jo[2]))
 
 
+def mano_affine_case(pkl, nc, B, seed):
+    """The reference layer followed by the callers' post-ops (resnet50MANO.py:77-81: scale * x3d, + trans), with a
+    3-D translation: p' = scale * p + transl on vertices and joints, and the reference's autograd for all five inputs."""
+    layer = ref.ManoLayer("cpu", pkl, pose_num=nc)
+    g = torch.Generator().manual_seed(seed)
+    rot = ((torch.rand(B, 3, generator=g) - .5) * 2 * np.pi).requires_grad_()
+    pose = ((torch.rand(B, nc, generator=g) - .5) * 2).requires_grad_()
+    beta = (torch.rand(B, 10, generator=g) - .5).requires_grad_()
+    transl = (torch.randn(B, 3, generator=g) * .1 + torch.tensor([0, 0, .6])).requires_grad_()
+    scale = (torch.rand(B, generator=g) + .5).requires_grad_()
+    v, j = layer(rot, pose, beta)
+    v = scale.unsqueeze(1).unsqueeze(2) * v + transl.unsqueeze(1)
+    j = scale.unsqueeze(1).unsqueeze(2) * j + transl.unsqueeze(1)
+    gv = torch.randn(v.shape, generator=g)
+    gj = torch.randn(j.shape, generator=g)
+    ((v * gv).sum() + (j * gj).sum()).backward()
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(rot=n(rot), pose=n(pose), beta=n(beta), transl=n(transl), scale=n(scale), verts=n(v), joints=n(j),
+                g_verts=n(gv), g_joints=n(gj), g_rot=n(rot.grad), g_pose=n(pose.grad), g_beta=n(beta.grad),
+                g_transl=n(transl.grad), g_scale=n(scale.grad))
+
+
 def fk_case(B, seed, switched):
     ref.config.joint_order_switched = switched
     fk = ref.ForwardKinematics("cpu")
@@ -218,6 +240,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, "mano_synth_nc45.npz"), **mano_case(pkl, 45, 4, 1234))
         np.savez_compressed(os.path.join(HERE, "mano_synth_nc10.npz"), **mano_case(pkl, 10, 4, 1234))
         np.savez_compressed(os.path.join(HERE, "mano_synth_nc6.npz"), **mano_case(pkl, 6, 3, 99, scale_pose=4.0))
+        np.savez_compressed(os.path.join(HERE, "mano_affine_nc10.npz"), **mano_affine_case(pkl, 10, 5, 77))
     np.savez_compressed(os.path.join(HERE, "fk_switched.npz"), **fk_case(8, 1234, True))
     np.savez_compressed(os.path.join(HERE, "fk_unswitched.npz"), **fk_case(8, 4321, False))
     np.savez_compressed(os.path.join(HERE, "reduce_vis80.npz"), **reduce_case(16, 5, .8))

@@ -86,6 +86,35 @@ def test_mano_matches_reference_golden(pkg, synth_model, cuda_device, name, nc, 
     torch.cuda.synchronize()
 
 
+def test_mano_transl_scale_keywords_match_reference_golden(pkg, synth_model, cuda_device):
+    """``ManoLayer.forward(..., transl=, scale=)`` (keyword-only extension; north_star "global rotation and translation
+    in") against the reference layer followed by its callers' post-ops (resnet50MANO.py:77-81) with the reference's
+    autograd for all five inputs — full layer and the joints-only path; the default call is unchanged."""
+    import torch
+
+    g = load_golden("mano_affine_nc10.npz")
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=10)
+    rot, pose, beta, transl, scale = to_dev(cuda_device, g["rot"], g["pose"], g["beta"], g["transl"], g["scale"], grad=True)
+    gv, gj = to_dev(cuda_device, g["g_verts"], g["g_joints"])
+    v, j = layer(rot, pose, beta, transl=transl, scale=scale)
+    assert np.abs(v.detach().cpu().numpy() - g["verts"]).max() < 3e-7        # coordinates ~0.7 m: 1 ulp = 6e-8
+    assert np.abs(j.detach().cpu().numpy() - g["joints"]).max() < 3e-7
+    ((v * gv).sum() + (j * gj).sum()).backward()
+    for t, key in ((rot, "g_rot"), (pose, "g_pose"), (beta, "g_beta"), (transl, "g_transl"), (scale, "g_scale")):
+        assert rel(t.grad.cpu().numpy(), g[key]) < GRAD_TOL, key
+    # joints only, translation only
+    for t in (rot, pose, beta, transl, scale):
+        t.grad = None
+    _, j2 = layer.rot_pose_beta_to_mesh(rot, pose, beta, joints_only=True, transl=transl)
+    want = (g["joints"] - g["transl"][:, None]) / g["scale"][:, None, None] + g["transl"][:, None]
+    assert np.abs(j2.detach().cpu().numpy() - want).max() < 3e-7
+    (j2 * gj).sum().backward()
+    assert rel(transl.grad.cpu().numpy(), g["g_joints"].sum(1)) < 1e-5 and scale.grad is None
+    # positional signature untouched
+    v0, j0 = layer(rot.detach(), pose.detach(), beta.detach())
+    assert np.abs(v0.cpu().numpy() * g["scale"][:, None, None] + g["transl"][:, None] - g["verts"]).max() < 3e-7
+
+
 @pytest.mark.parametrize("mode", ACCURATE_MODES)
 @pytest.mark.parametrize("B,nc", [(1, 45), (2, 45), (7, 10), (129, 45), (1000, 45), (1344, 45), (2720, 10), (4096, 10), (4133, 45), (5000, 6), (8192, 10), (9001, 45),
                                   (20001, 45), (40001, 45), (77777, 10)])
