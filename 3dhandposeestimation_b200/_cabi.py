@@ -65,6 +65,7 @@ SIGNATURES = {
     "mb_regulariser_backward": (_i, [_p, _ll, _p, _ll, _f, _p, _p, _p, _p, _p]),
     "mb_hand_mask_loss": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mb_mano_fit_step": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _f, _f, _f, _f, _i, _i, _p]),
+    "mb_fit_finalize": (_i, [_p, _p, _i, _p, _p, _p]),
     "mb_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
     "mb_launch_count": (_ll, []),
     "mb_profile_enable": (None, [_i]),

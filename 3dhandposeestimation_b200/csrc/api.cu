@@ -361,9 +361,17 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
         if ((rc = launch_sgemm(rows, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s))) return rc;
     } else {
         unsigned char* dvp = reinterpret_cast<unsigned char*>(ws + W.dvp);
-        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, lh ? 1 : 0, dparts, s))) return rc; }
-        StageTimer t(ST_BLEND_BWD, s);        // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
-        if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, lh ? 1 : 0, dfeat_parts, dfeat_stride, s))) return rc;
+        if (lh && !(model_flags & MB_FWD_UNFUSED)) {
+            // large batches: the per-bone sums (role 1) ...
+            { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, nullptr, dbone, 1, dparts, s))) return rc; }
+            // ... and dv_posed feeding the tcgen05 gradient contraction from shared memory (no dv_posed tiles in HBM)
+            StageTimer t(ST_BLEND_BWD, s);
+            if ((rc = launch_skin_backward_dv_gemm(blob, bone_t, g_verts, g_joints, B, dfeat, s))) return rc;
+        } else {
+            { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, lh ? 1 : 0, dparts, s))) return rc; }
+            StageTimer t(ST_BLEND_BWD, s);        // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
+            if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, lh ? 1 : 0, dfeat_parts, dfeat_stride, s))) return rc;
+        }
     }
     StageTimer t(ST_POSE_BWD, s);
     if (lh) return launch_pose_backward_lh(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);

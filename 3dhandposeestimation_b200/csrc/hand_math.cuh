@@ -84,28 +84,50 @@ HD void sincos_acc(float a, float* s, float* c) {
 
 // Axis-angle -> rotation.  Reference: ManoLayer.rodrigues, MANOLayer.py:82-112
 // R = I + sin(t) S(n) + (1 - cos t) S(n)^2, n = r / t; Taylor form below 1e-30 (:102-110).
+// Evaluated as R = I + a S(r) + b (r r^T - t^2 I), a = sin t / t, b = (1 - cos t) / t^2 — the same matrix — with the
+// angle in DOUBLE: rounding t = |r| to fp32 before sin / cos costs 1 ulp of the ANGLE (3e-7 rad at t = 5), which was the
+// largest error of the whole layer against the fp64 arbiter (profiles/r2: blended transforms off by 6.7e-7, verts
+// by 1.3e-7 m).  t^2 is exact in double, 1 / t comes from the fp32 rsqrt refined by two Newton steps, sin / cos from the
+// fp32 sincosf of the rounded angle plus the first-order term of the rounding residue; the entries are rounded to fp32
+// once.  ~30 double FMAs per call (B200 runs them at half the fp32 rate), no double sqrt / divide.
 HD M3 rodrigues(const V3& r) {
-    float t2 = fmaf(r.x, r.x, fmaf(r.y, r.y, r.z * r.z));
-    float t = sqrtf(t2);
+    const double x = r.x, y = r.y, z = r.z;
+    const double t2 = x * x + (y * y + z * z);
     M3 R;
-    if (t < 1e-30f) {
-        float a = 1.f - t2 / 6.f, b = 0.5f - t2 / 24.f;
+    if (t2 < 1e-60) {
+        const float f2 = (float)t2;
+        const float a = 1.f - f2 / 6.f, b = 0.5f - f2 / 24.f;
         // S(r)^2 = r r^T - t2 I
-        R.m[0] = 1.f + b * (r.x * r.x - t2); R.m[1] = -a * r.z + b * r.x * r.y;   R.m[2] = a * r.y + b * r.x * r.z;
-        R.m[3] = a * r.z + b * r.x * r.y;    R.m[4] = 1.f + b * (r.y * r.y - t2); R.m[5] = -a * r.x + b * r.y * r.z;
-        R.m[6] = -a * r.y + b * r.x * r.z;   R.m[7] = a * r.x + b * r.y * r.z;    R.m[8] = 1.f + b * (r.z * r.z - t2);
+        R.m[0] = 1.f + b * (r.x * r.x - f2); R.m[1] = -a * r.z + b * r.x * r.y;   R.m[2] = a * r.y + b * r.x * r.z;
+        R.m[3] = a * r.z + b * r.x * r.y;    R.m[4] = 1.f + b * (r.y * r.y - f2); R.m[5] = -a * r.x + b * r.y * r.z;
+        R.m[6] = -a * r.y + b * r.x * r.z;   R.m[7] = a * r.x + b * r.y * r.z;    R.m[8] = 1.f + b * (r.z * r.z - f2);
         return R;
     }
-    float inv = 1.f / t;
-    float nx = r.x * inv, ny = r.y * inv, nz = r.z * inv;
-    float s, c;
-    sincos_acc(t, &s, &c);
-    float k = 1.f - c;
-    // S(n)^2 = n n^T - |n|^2 I ; |n|^2 is 1 up to rounding — keep the reference's form (S@S)
-    float nn = fmaf(nx, nx, fmaf(ny, ny, nz * nz));
-    R.m[0] = 1.f + k * (nx * nx - nn); R.m[1] = -s * nz + k * nx * ny;    R.m[2] = s * ny + k * nx * nz;
-    R.m[3] = s * nz + k * nx * ny;     R.m[4] = 1.f + k * (ny * ny - nn); R.m[5] = -s * nx + k * ny * nz;
-    R.m[6] = -s * ny + k * nx * nz;    R.m[7] = s * nx + k * ny * nz;     R.m[8] = 1.f + k * (nz * nz - nn);
+    // 1 / t: fp32 estimate (t2 is rescaled into fp32's range: axis-angles below 1e-19 would underflow t2) + 2 Newton steps
+    double inv;
+    {
+        const float f2 = (float)t2;
+#ifdef __CUDA_ARCH__
+        float y0 = f2 > 1e-30f ? rsqrtf(f2) : 1e15f * rsqrtf((float)(t2 * 1e30));
+#else
+        float y0 = f2 > 1e-30f ? 1.f / sqrtf(f2) : 1e15f / sqrtf((float)(t2 * 1e30));
+#endif
+        inv = (double)y0;
+        inv = inv * (1.5 - 0.5 * t2 * inv * inv);
+        inv = inv * (1.5 - 0.5 * t2 * inv * inv);
+    }
+    const double t = t2 * inv;
+    const float th = (float)t;
+    const float tl = (float)(t - (double)th);
+    float sf, cf;
+    sincos_acc(th, &sf, &cf);
+    const double sd = (double)sf + (double)tl * (double)cf;      // sin(th + tl), cos(th + tl) to first order in tl (|tl| < 3e-7)
+    const double cd = (double)cf - (double)tl * (double)sf;
+    const double a = sd * inv, b = (1.0 - cd) * (inv * inv);
+    const double bxy = b * x * y, bxz = b * x * z, byz = b * y * z;
+    R.m[0] = (float)(1.0 + b * (x * x - t2)); R.m[1] = (float)(bxy - a * z);           R.m[2] = (float)(bxz + a * y);
+    R.m[3] = (float)(bxy + a * z);            R.m[4] = (float)(1.0 + b * (y * y - t2)); R.m[5] = (float)(byz - a * x);
+    R.m[6] = (float)(bxz - a * y);            R.m[7] = (float)(byz + a * x);           R.m[8] = (float)(1.0 + b * (z * z - t2));
     return R;
 }
 

@@ -167,6 +167,19 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
+// End of a fused fitting iteration (fitting.py), after the caller all-reduced the kernel's partials
+// {sum vis |d|^2, sum theta_new^2, sum beta_new^2}: the loss of the iteration just done — L2 term over the global
+// visible count + the regulariser of the parameters the iteration STARTED from (globals) — then the norms of the
+// updated parameters become the next iteration's globals.  One thread: replaces ~10 tiny elementwise launches.
+__global__ void fit_finalize_kernel(double* __restrict__ globals, const double* __restrict__ partials, int regularize,
+                                    double* __restrict__ out4, double* __restrict__ loss) {
+    const double n = globals[0], t = regularize ? globals[1] : 0.0, b = regularize ? globals[2] : 0.0;
+    out4[0] = partials[0]; out4[1] = n; out4[2] = t; out4[3] = b;
+    loss[0] = (n > 0.0 ? partials[0] / n : 0.0) + (sqrt(t) + 10.0 * sqrt(b)) / 100.0;
+    globals[1] = partials[1];
+    globals[2] = partials[2];
+}
+
 inline unsigned red_grid(long long n) {
     long long blocks = (n + RED_THREADS - 1) / RED_THREADS;
     long long cap = (long long)NUM_SMS * 8;
@@ -253,6 +266,13 @@ extern "C" int mb_hand_mask_loss(const float* pred_uv, const float* gt_uv, const
         if (rc) return rc;
     }
     hand_mask_finalize_kernel<<<1, 1, 0, s>>>(accum, out);
+    return cuda_rc();
+}
+
+extern "C" int mb_fit_finalize(double* globals, const double* partials, int regularize, double* out4, double* loss,
+                               mb_stream_t stream) {
+    if (!globals || !partials || !out4 || !loss) return MB_E_NULL;
+    fit_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(globals, partials, regularize, out4, loss);
     return cuda_rc();
 }
 

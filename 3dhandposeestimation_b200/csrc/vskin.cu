@@ -13,7 +13,7 @@
 //   T[v][(h, e)]  = sum_k W[v][k] A[h][k][e]          N = 4 hands x 12 elements, K = 16 bones, fp16 3-way split, 4 products
 // Both land in TMEM with lane = vertex; the epilogue thread of vertex v reads its rest position (3 columns) and its
 // blended 3x4 transform (12 columns) of a hand, does 12 FMAs, and the warp's 32 consecutive vertices leave through a
-// shared-memory row as ONE contiguous, sector-aligned 1 536-byte bulk store per (hand, vertex tile) of
+// shared-memory row as ONE contiguous, sector-aligned 1 536-byte piece per (hand, vertex tile) of
 // verts[B][778][3] in its natural layout — no transposition, no v_posed_t round trip.
 //
 // Roles (384 threads, 1 CTA per SM, persistent over 64-hand tiles):
@@ -21,7 +21,7 @@
 //   warp 1   MMA issuer (one thread): blend products of vertex tile t+1 interleaved with the transform chunks of tile t
 //   warp 2   TMEM allocation; producer of the per-hand-tile operands (feature rows 40 KB, bone operand 72 KB) and of
 //            the weight tiles (12 KB per vertex tile, double buffered)
-//   warp 3   store warp: bulk stores shared -> global, row heads / tails that cannot be 16-byte aligned
+//   warp 3   store warp: result rows shared -> global as 16-byte vectors, row heads / tails as plain stores
 //   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices), warp / 8 = which two hands of a chunk
 // TMEM (512 columns): two rest-position stages of 3 x 64 columns, two transform stages of 48 columns.
 #include <cuda_fp16.h>
@@ -225,7 +225,10 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
             }
         }
     } else if (warp == 3) {
-        // ===== store warp =====
+        // ===== store warp: result rows shared -> global as 16-byte vectors (every piece starts on a 32-byte boundary) =====
+        // [profiles/r2: as bulk (TMA) stores with a 3-deep ring the kernel ran at the latency of cp.async.bulk.wait_group.read —
+        // ~1 900 clk per 4-hand chunk, tensor pipe 15 % busy; a plain LDS.128 -> STG.128 copy frees the row as soon as it is in
+        // registers]
         uint32_t oc = 0, gt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long hand0 = (long long)tile * VS_NH;
@@ -233,16 +236,35 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 for (int ch = 0; ch < VS_NCH; ++ch, ++oc) {
                     const uint32_t ob = oc % VS_OSTAGES;
                     vs_wait(&S.out_full[ob], (oc / VS_OSTAGES) & 1);
-                    // carried floats of the previous vertex tile go in front of the results (generic writes, made visible to
-                    // the bulk-copy engine by the proxy fence below)
-                    if (t >= 1 && lane < 4 * 8) {
+                    // carried floats of the previous vertex tile go in front of the results
+                    if (t >= 1) {
                         const int hl = lane >> 3, i = lane & 7;
                         if (i < vs_d(hl)) S.out[ob][hl][i] = S.carry[gt & 1][ch * VS_HC + hl][i];
                     }
-                    fence_proxy_async();
                     __syncwarp();
-                    if (t == 0 || t == VS_NT - 1) {
-                        // row heads (tile 0) and the short last tile: plain stores
+                    if (t >= 1 && t < VS_NT - 1) {
+                        // 4 rows x 1536 B = 4 x 96 float4: three per lane per row, all loads first
+                        float4 v[VS_HC][3];
+#pragma unroll
+                        for (int hl = 0; hl < VS_HC; ++hl) {
+                            const float4* src = reinterpret_cast<const float4*>(&S.out[ob][hl][0]);
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) v[hl][k] = src[lane + 32 * k];
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&S.out_empty[ob]));        // the rows are in registers
+#pragma unroll
+                        for (int hl = 0; hl < VS_HC; ++hl) {
+                            const long long hand = hand0 + ch * VS_HC + hl;
+                            if (hand < B) {
+                                float4* dst = reinterpret_cast<float4*>(verts + (size_t)hand * NVC + 3 * VS_M * t - vs_d(hl));
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) __stcs(dst + lane + 32 * k, v[hl][k]);
+                            }
+                        }
+                    } else {
+                        // tile 0: the row's first floats up to its first 32-byte boundary are plain stores, the rest vectors;
+                        // the short last tile (10 vertices + carry): plain stores
                         for (int hl = 0; hl < VS_HC; ++hl) {
                             const long long hand = hand0 + ch * VS_HC + hl;
                             if (hand >= B) break;
@@ -252,34 +274,21 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                             if (t == 0) {
                                 const int a = (8 - d) & 7, sh = vs_shift(0, hl);
                                 if (lane < a) grow[lane] = row[sh + lane];
+                                const float4* src = reinterpret_cast<const float4*>(row + sh + a);
+                                float4* dst = reinterpret_cast<float4*>(grow + a);
+                                const int n16 = (3 * VS_M - d - a) / 4;                 // 94 or 96
+                                for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
                             } else {
                                 const int n = NVC - (VS_NT - 1) * 3 * VS_M + d;          // 30 + d floats
                                 for (int i = lane; i < n; i += 32) grow[(VS_NT - 1) * 3 * VS_M - d + i] = row[i];
                             }
                         }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&S.out_empty[ob]));
                     }
-                    if (lane < VS_HC) {
-                        const int hl = lane;
-                        const long long hand = hand0 + ch * VS_HC + hl;
-                        if (hand < B && t < VS_NT - 1) {
-                            const int d = vs_d(hl);
-                            float* grow = verts + (size_t)hand * NVC;
-                            if (t == 0) {
-                                const int a = (8 - d) & 7, sh = vs_shift(0, hl);
-                                bulk_s2g(grow + a, smem_u32(&S.out[ob][hl][sh + a]), (uint32_t)(3 * VS_M - d - a) * 4u);
-                            } else {
-                                bulk_s2g(grow + 3 * VS_M * t - d, smem_u32(&S.out[ob][hl][0]), 3 * VS_M * 4u);
-                            }
-                        }
-                        bulk_commit();
-                        bulk_wait_read<1>();                                   // the previous chunk's rows have been read
-                    }
-                    __syncwarp();
-                    if (oc > 0 && lane == 0) mbar_arrive(smem_u32(&S.out_empty[(oc - 1) % VS_OSTAGES]));
                 }
             }
         }
-        if (lane < VS_HC) bulk_wait_all<0>();
     } else {
         // ===== epilogue: thread = vertex =====
         const int q = warp & 3, half = (warp - 4) >> 2;
@@ -377,7 +386,6 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                             }
                         }
                     }
-                    fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&S.out_full[ob]));
                 }

@@ -40,6 +40,8 @@ def reduce_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
     """All-reduce (sum) the float64[4] objective partials over the ranks (no-op without a process group)."""
     import torch.distributed as dist
 
+    if isinstance(group, str):          # "local": this rank's objective only — no collective (measurement / single-rank use)
+        return partials
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
     return partials
@@ -123,19 +125,16 @@ class ManoFitter:
                                          self.exp_avg_sq.data_ptr(), tgt.data_ptr(), vis.data_ptr(), self.B, self.layer._mode,
                                          self.globals.data_ptr(), self.kernel_partials.data_ptr(), self.lr, self.b1, self.b2,
                                          self.eps, self.steps, int(self.regularize), stream), "mb_mano_fit_step")
-        # the one collective of the iteration: {L2 sum of this iteration, norms of the updated parameters}
+        # the one collective of the iteration: {L2 sum of this iteration, norms of the updated parameters} (24 bytes) ...
         reduce_partials(self.kernel_partials, self.group)
-        p = self.partials                                     # [S, N, sum theta^2, sum beta^2] of the iteration just done
-        p[0] = self.kernel_partials[0]
-        p[1] = self.globals[0]
-        if self.regularize:
-            p[2:4] = self.globals[1:3]
-        else:
-            p[2:4] = 0
-        self.loss, _, _ = objective_from_partials(p)
-        self.globals[1:3] = self.kernel_partials[1:3]
+        # ... and one single-thread launch: the loss of the iteration just done into self.loss, [S, N, sum theta^2,
+        # sum beta^2] into self.partials, the updated norms into next iteration's globals — no torch op on the path
+        _cabi.check(lib.mb_fit_finalize(self.globals.data_ptr(), self.kernel_partials.data_ptr(), int(self.regularize),
+                                        self.partials.data_ptr(), self.loss.data_ptr(), stream), "mb_fit_finalize")
+        self._param_version = self.params._version
         return self.loss
 
+    @_cabi.on_tensor_device
     def step(self, target_joints: torch.Tensor, keypoint_vis: torch.Tensor) -> torch.Tensor:
         """One Adam iteration; returns the (global) loss as a 0-dim device tensor (no host sync)."""
         lib = _cabi.lib()

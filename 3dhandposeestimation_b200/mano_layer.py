@@ -125,7 +125,7 @@ class _ManoFunction(torch.autograd.Function):
                 ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
             _cabi.check(lib.mb_mano_backward(layer._blob.data_ptr(), nc, rot.data_ptr(), coeffs.data_ptr(),
                                              betas.data_ptr(), g_verts.data_ptr(), g_joints.data_ptr(), B,
-                                             layer._mode, flags, g_rot.data_ptr(), g_coeffs.data_ptr(),
+                                             layer._mode | layer._fwd_flags, flags, g_rot.data_ptr(), g_coeffs.data_ptr(),
                                              g_betas.data_ptr(), ws.data_ptr(), ws.numel(), stream),
                         "mb_mano_backward")
             if not ctx.ws_valid:

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """bench.py — MANO hands/sec fwd+bwd on N B200s (one process per GPU), the headline metric of
 BASELINE.json, with the roofline of the dominant kernel, an end-to-end (host buffers) number
-and the CPU baseline (the numpy oracle port of the reference) timed on the box's host cores.
+and the CPU baseline — the reference's own PyTorch ManoLayer (oracle/_ref, staged by
+oracle/make_ref.py) forward + autograd backward on the box's host cores, with the numpy port beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--hands H] [--mode fp32|f16x3|f16]
-    python bench.py --impl reference ...     # the reference's CPU algorithm (oracle port)
+    python bench.py --impl reference ...     # the reference's own CPU path (PyTorch; numpy port when it is not staged)
     torchrun --nproc-per-node N bench.py --gpus N ...
 
 Workload (config.workload): BASELINE configs[3] scaled to fwd+bwd — full 45-D axis-angle MANO
@@ -41,17 +42,25 @@ BYTES_LBS = 19692                                               # stand-alone LB
 # dv_posed tiles (bf16 hi+mid, 4 B per coordinate) 9408 + per-bone sums 768 out
 BYTES_LBS_BWD = 9336 + 60 + 9408 + 768 + 9408 + 768             # 29748
 FLOP_BLEND = 2 * 145 * 2334                                     # 676860 per hand per contraction
+FLOP_SKIN_T = 2 * 778 * 16 * 12                                 # 298752 per hand: T_v = sum_k w_vk A_k as a dense product (vskin.cu)
+# the fused lane = vertex forward kernel (vskin.cu): feature tiles 640 + bone operand 1152 in, verts 9336 + tips 60 out;
+# a training forward also leaves the rest-pose scratch of the skinning backward (9408)
+BYTES_FUSED_FWD = 640 + 1152 + 9336 + 60                        # 11188
+BYTES_FUSED_FWD_TRAIN = BYTES_FUSED_FWD + 9408                  # 20596
 STAGE_KERNEL = {"pose_fwd": "pose_forward_lh_kernel", "blend_fwd": "blend_tc_forward_mres_kernel", "lbs_fwd": "skin_forward_kernel",
+                "fused_fwd": "vskin_forward_kernel",
                 "lbs_bwd": "skin_backward_kernel", "blend_bwd": "blend_tc_backward_kernel", "pose_bwd": "pose_backward_lh_kernel"}
 
 
 def ncu_traffic_per_hand():
-    """DRAM bytes per hand per kernel from the committed `ncu --set full` capture (profiles/r1/traffic_final.json)."""
-    path = os.path.join(ROOT, "profiles", "r1", "traffic_final.json")
-    if not os.path.isfile(path):
-        return {}
-    d = json.load(open(path))["kernels"]
-    return {k: (v["dram_read_bytes"] + v["dram_write_bytes"]) / v["hands"] for k, v in d.items()}
+    """DRAM bytes per hand per kernel from the committed `ncu --set full` captures (profiles/r2 overrides profiles/r1)."""
+    out = {}
+    for rnd in ("r1", "r2"):
+        path = os.path.join(ROOT, "profiles", rnd, "traffic_final.json")
+        if os.path.isfile(path):
+            d = json.load(open(path))["kernels"]
+            out.update({k: ((v["dram_read_bytes"] + v["dram_write_bytes"]) / v["hands"], rnd) for k, v in d.items()})
+    return out
 
 
 def load_peaks():
@@ -138,42 +147,114 @@ def synth_inputs(H, seed):
     return rot, pose, beta
 
 
-def cpu_baseline(model, kept=None, budget_s=12.0, chunk=256):
-    """The oracle (numpy port of the reference's algorithm, fp32) fwd+bwd on the host cores:
-    repeated `chunk`-hand batches of the same synthetic workload for about `budget_s` seconds.  `kept`: four hands of
-    the GPU arm's last step (inputs, outputs, gradients) — checked against the fp64 oracle here, reported as `parity`."""
+def reference_layer(assets, model):
+    """The UNMODIFIED reference's ManoLayer (network/sub_modules/MANOLayer.py) on CPU, constructed on `model` written as a
+    pickle its own constructor opens — from /root/reference or its travelling copy oracle/_ref.  None when neither is there."""
+    try:
+        from oracle import ref_import
+
+        if not ref_import.available():
+            return None
+        import tempfile
+
+        import torch
+
+        ref = ref_import.load()
+        torch.set_num_threads(os.cpu_count() or 1)
+        with tempfile.TemporaryDirectory() as td:
+            pkl = os.path.join(td, "model.pkl")
+            assets.write_reference_style_pkl(model, pkl)
+            return ref.ManoLayer("cpu", pkl, pose_num=45)
+    except Exception as exc:                                   # the baseline must never take the GPU arm down
+        sys.stderr.write(f"reference ManoLayer unavailable: {exc!r}\n")
+        return None
+
+
+def reference_fwd_bwd(layer, rot, pose, beta, gv, gj):
+    import torch
+
+    t = [torch.from_numpy(a).requires_grad_() for a in (rot, pose, beta)]
+    v, j = layer(*t)
+    ((v * torch.from_numpy(gv)).sum() + (j * torch.from_numpy(gj)).sum()).backward()
+    return v, j, t
+
+
+def parity_check(model, kept):
+    """fp64 oracle on the fixed subsample of the GPU arm's last timed step (8 192 hands): forward on
+    all of it, gradients on its first 512 hands.  The one place the product arm runs oracle/ — as the checker."""
     import numpy as np
     from oracle import mano_oracle
 
-    parity = None
-    if kept is not None:
-        ov, oj = mano_oracle.mano_forward(model, kept["rot"], kept["pose"], kept["beta"])
-        og = mano_oracle.mano_backward(model, kept["rot"], kept["pose"], kept["beta"], kept["gv"], kept["gj"])
-        parity = {"verts_max_abs_err_m": float(np.abs(kept["verts"] - ov).max()),
-                  "joints_max_abs_err_m": float(np.abs(kept["joints"] - oj).max()),
-                  "grad_rel_err": max(float(np.abs(kept[k] - w).max() / np.abs(w).max())
-                                      for k, w in zip(("g_rot", "g_pose", "g_beta"), og))}
+    n = kept["rot"].shape[0]
+    ev, ej = [], []
+    for s0 in range(0, n, 1024):
+        sl = slice(s0, s0 + 1024)
+        ov, oj = mano_oracle.mano_forward(model, kept["rot"][sl], kept["pose"][sl], kept["beta"][sl])
+        ev.append(np.abs(kept["verts"][sl] - ov).max(axis=(1, 2)))
+        ej.append(np.abs(kept["joints"][sl] - oj).max(axis=(1, 2)))
+    ev, ej = np.concatenate(ev), np.concatenate(ej)
+    ng = min(n, 512)
+    og = mano_oracle.mano_backward(model, kept["rot"][:ng], kept["pose"][:ng], kept["beta"][:ng], kept["gv"][:ng], kept["gj"][:ng])
+    return {"hands": int(n), "verts_max_abs_err_m": float(ev.max()), "verts_p999_abs_err_m": float(np.quantile(ev, 0.999)),
+            "joints_max_abs_err_m": float(ej.max()), "joints_p999_abs_err_m": float(np.quantile(ej, 0.999)),
+            "grad_hands": int(ng),
+            "grad_rel_err": max(float(np.abs(kept[k][:ng] - w).max() / np.abs(w).max())
+                                for k, w in zip(("g_rot", "g_pose", "g_beta"), og)),
+            "arbiter": "fp64 numpy oracle (oracle/mano_oracle.py), per-hand max over vertices"}
+
+
+def cpu_baseline(assets, model, budget_s=12.0, chunk=512):
+    """The reference's own PyTorch CPU path (BASELINE.md 3 protocol: forward + autograd backward, <= 1 024-hand chunks,
+    torch.set_num_threads(cpu_count)) on the workload's synthetic no-PCA model for about `budget_s` seconds, with the
+    numpy port (oracle/mano_oracle.py, fp32) timed beside it.  kind = "reference" unless the reference is not staged."""
+    import numpy as np
+    from oracle import mano_oracle
 
     rot, pose, beta = synth_inputs(chunk, 4242)
     rs = np.random.RandomState(1)
     gv = rs.randn(chunk, 778, 3).astype(np.float32)
     gj = rs.randn(chunk, 21, 3).astype(np.float32)
-    mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)          # warm-up
-    done, t0 = 0, time.perf_counter()
-    while True:
-        mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)      # forward + backward
-        done += chunk
-        dt = time.perf_counter() - t0
-        if dt >= budget_s:
-            break
-    return {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{done} hands in {chunk}-hand batches, numpy fp32 oracle fwd+bwd, {dt:.1f} s"}, parity
+
+    def timed(fn, budget):
+        fn()                                                   # warm-up
+        done, t0 = 0, time.perf_counter()
+        while True:
+            fn()
+            done += chunk
+            dt = time.perf_counter() - t0
+            if dt >= budget:
+                return done / dt, done, dt
+
+    port, pdone, pdt = timed(lambda: mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32), budget_s * 0.4)
+    layer = reference_layer(assets, model)
+    if layer is None:
+        return {"value": port, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": f"{pdone} hands in {chunk}-hand batches, numpy fp32 oracle fwd+bwd, {pdt:.1f} s (reference not staged)"}
+    val, done, dt = timed(lambda: reference_fwd_bwd(layer, rot, pose, beta, gv, gj), budget_s)
+    # config 1 of BASELINE.json: the reference forward at batch 64
+    import torch
+
+    r64 = [torch.from_numpy(a[:64]) for a in (rot, pose, beta)]
+    with torch.no_grad():
+        layer(*r64)
+        best = min(_timeit(lambda: layer(*r64)) for _ in range(5))
+    return {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+            "sample": f"{done} hands in {chunk}-hand batches, the reference's PyTorch ManoLayer forward + autograd backward "
+                      f"(fp32, {os.cpu_count()} threads), {dt:.1f} s",
+            "config1_forward_b64": {"hands_per_s": 64 / best, "ms": best * 1e3},
+            "port_value": port, "port_note": "numpy fp32 port of the same algorithm (BLAS matmuls instead of repeat + bmm)"}
+
+
+def _timeit(fn):
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
 
 
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm for this path.  The reference is
-    Python and cannot travel to the GPU box, so this times its numpy port (oracle/) on the host
-    cores; each step is a bounded sample (args.ref_hands hands) of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path — its PyTorch ManoLayer forward + autograd
+    backward from the staged copy oracle/_ref (the numpy port only when that is absent) — on the host cores; each step is
+    a bounded sample (args.ref_hands hands) of the workload."""
     if rank != 0:
         return
     import numpy as np
@@ -186,11 +267,18 @@ def run_reference_arm(args, rank, world):
     rs = np.random.RandomState(1)
     gv = rs.randn(H, 778, 3).astype(np.float32)
     gj = rs.randn(H, 21, 3).astype(np.float32)
+    layer = reference_layer(assets, model)
+    if layer is not None:
+        kind, what = "reference", "the reference's PyTorch ManoLayer forward + autograd backward (fp32)"
+        fn = lambda: reference_fwd_bwd(layer, rot, pose, beta, gv, gj)
+    else:
+        kind, what = "port", "numpy fp32 oracle fwd+bwd (reference not staged)"
+        fn = lambda: mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)
     for _ in range(args.warmup):
-        mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)
+        fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        mano_oracle.mano_backward(model, rot, pose, beta, gv, gj, dtype=np.float32)
+        fn()
     dt = time.perf_counter() - t0
     value = H * args.steps / dt
     line = {
@@ -198,8 +286,8 @@ def run_reference_arm(args, rank, world):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample_hands_per_step": H, "device": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{H} hands per step x {args.steps} steps, numpy fp32 oracle fwd+bwd"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                         "sample": f"{H} hands per step x {args.steps} steps, {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -403,6 +491,137 @@ def run_secondary(args, pkg, layer, dev, rank, world, dist):
             "roofline": roof, "mpjpe_mm": float(outs[0]["mp"]), "l2": float(outs[0]["l2"]), "data": "synthetic"}
 
 
+def bind_numa_local(gpu_index):
+    """Pin this process (and therefore the pinned host buffers it first-touches) to the CPU cores of the GPU's NUMA node:
+    with 8 ranks on one box, round 1's e2e arm scaled at 0.66 with every rank on the same cores.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:                       # 00000000:xx:yy.z -> 0000:xx:yy.z
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        return {"numa_node": node, "cpus": len(use)}
+    except Exception:
+        return None
+
+
+def run_extras(args, pkg, layer45, dev, rank, world, dist, set0):
+    """The other BASELINE configs, short, for the contract line: config 2 (the Resnet50MANO3DHandPose head workload:
+    B = 4096 and the reference's own batch_size = 200, config.py:79; joints only as the heads consume it, and with verts),
+    config 3 (FK fwd + L2 + bwd + MPJPE at 65 536 samples: C-ABI graph and the nn.Module API) and config 5 (fused Adam
+    fitting iterations with the NCCL all-reduce inside the timed loop, and with it disabled)."""
+    import numpy as np
+    import torch
+
+    cabi = pkg._cabi
+    lib = cabi.lib()
+    P = lambda t: t.data_ptr()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / n
+
+    out = {}
+    # ---- config 2: head workload, pose_num = config.mano_pose_num = 10, value ranges of resnet50MANO.py:73-75 ----
+    layer10 = pkg.ManoLayer(dev, model=pkg.assets.synthetic_mano(), pose_num=10, mode=args.mode)
+    c2 = {}
+    for B in (4096, 200):
+        nsets = 16
+        rs = np.random.RandomState(7 + B)
+        sets = []
+        for _ in range(nsets):
+            sig = lambda *sh: torch.from_numpy(rs.rand(*sh).astype(np.float32)).to(dev)
+            sets.append(dict(rot=(sig(B, 3) - .5) * 2 * np.pi, pose=(sig(B, 10) - .5) * 4, beta=(sig(B, 10) - .5) * .1,
+                             joints=torch.empty(B, 21, 3, device=dev), verts=torch.empty(B, 778, 3, device=dev),
+                             gj=torch.randn(B, 21, 3, device=dev), gv=torch.randn(B, 778, 3, device=dev),
+                             g=[torch.empty(B, n, device=dev) for n in (3, 10, 10)]))
+        ws = torch.empty(max(lib.mb_mano_workspace_bytes(B, layer10._mode), 16), dtype=torch.uint8, device=dev)
+        it = [0]
+
+        def head_step():
+            s = sets[it[0] % nsets]
+            it[0] += 1
+            cabi.check(lib.mb_mano_forward(P(layer10._blob), 10, P(s["rot"]), P(s["pose"]), P(s["beta"]), B, layer10._mode, None,
+                                           P(s["joints"]), None, 0, st), "fwd")
+            cabi.check(lib.mb_mano_backward(P(layer10._blob), 10, P(s["rot"]), P(s["pose"]), P(s["beta"]), None, P(s["gj"]), B,
+                                            layer10._mode, 0, P(s["g"][0]), P(s["g"][1]), P(s["g"][2]), None, 0, st), "bwd")
+
+        def full_step():
+            s = sets[it[0] % nsets]
+            it[0] += 1
+            cabi.check(lib.mb_mano_forward(P(layer10._blob), 10, P(s["rot"]), P(s["pose"]), P(s["beta"]), B, layer10._mode,
+                                           P(s["verts"]), P(s["joints"]), P(ws), ws.numel(), st), "fwd")
+            cabi.check(lib.mb_mano_backward(P(layer10._blob), 10, P(s["rot"]), P(s["pose"]), P(s["beta"]), P(s["gv"]), P(s["gj"]), B,
+                                            layer10._mode, cabi.BWD_WORKSPACE_VALID, P(s["g"][0]), P(s["g"][1]), P(s["g"][2]),
+                                            P(ws), ws.numel(), st), "bwd")
+
+        ms_h = timed(head_step, 64)
+        ms_f = timed(full_step, 64)
+        c2[f"B{B}"] = {"joints_only_fwd+bwd_ms": ms_h, "joints_only_hands_per_s": world * B / (ms_h * 1e-3),
+                       "verts_fwd+bwd_ms": ms_f, "verts_hands_per_s": world * B / (ms_f * 1e-3)}
+        del sets, ws
+    c2["note"] = "C ABI, 16 rotating buffer sets, pose_num 10, head value ranges; joints only = what the heads consume (resnet50MANO.py:76,87)"
+    out["config2_head"] = c2
+
+    # ---- config 3: FK ----
+    import copy
+
+    a3 = copy.copy(args)
+    a3.workload, a3.hands, a3.steps = "fk", 1 << 20, max(8, min(args.steps, 20))
+    fk = run_secondary(a3, pkg, layer45, dev, rank, world, dist)
+    out["config3_fk"] = {"samples": 65536, "c_abi_graph_ms_per_step": fk["ms_per_step"], "c_abi_graph_samples_per_s": fk["value"],
+                         "module_api_ms_per_step": fk["module_api"]["ms_per_step"], "module_api_samples_per_s": fk["module_api"]["value"],
+                         "roofline": fk["roofline"], "mpjpe_mm": fk["mpjpe_mm"]}
+
+    # ---- config 5: fitting iterations, with and without the collective ----
+    H = args.hands
+    with torch.no_grad():
+        _, tgt = layer45.rot_pose_beta_to_mesh(set0["rot"], set0["pose"], set0["beta"], joints_only=True)
+        tgt = tgt + 1e-3 * torch.randn_like(tgt)
+    vis = (torch.rand(H, 21, 1, device=dev) < 0.8).float()
+    res = {}
+    for name, group in (("allreduce", None), ("local", "local")):
+        fitter = pkg.fitting.ManoFitter(layer45, H, group=group)
+        fitter.step(tgt, vis)
+        n_it = max(10, min(args.steps, 30))
+        ms = timed(lambda: fitter.step(tgt, vis), n_it)
+        res[name] = {"ms_per_iteration": ms, "hand_iterations_per_s": world * H / (ms * 1e-3), "loss": float(fitter.loss)}
+        del fitter
+    res["collective"] = f"NCCL all-reduce of 3 doubles per iteration over {world} ranks" if world > 1 else "single rank: no collective is issued"
+    res["hands_per_gpu"] = H
+    out["config5_fit"] = res
+    return out
+
+
 def workload_name(args):
     return f"mano_full45_noPCA_fwd+bwd_{args.hands}_hands_per_gpu"
 
@@ -421,6 +640,7 @@ def main():
     ap.add_argument("--rotate", type=int, default=1, help="number of distinct buffer sets cycled through (small --hands)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 2 / 3 / 5 side measurements of the default line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -534,43 +754,118 @@ def main():
         s["share"] = s["ms"] / tot_stage_ms
     traffic = ncu_traffic_per_hand()
 
-    def hbm_roofline(stage, bytes_per_hand):
-        ms = stages[stage]["ms"]
+    def hbm_roofline(stage, bytes_per_hand, ms=None):
+        ms = stages[stage]["ms"] if ms is None else ms
         gbs = bytes_per_hand * H / (ms * 1e-3) / 1e9
         kern = STAGE_KERNEL[stage]
+        tr = traffic.get(kern)
         return {"kernel": kern, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": gbs / peaks["hbm_gbs"], "traffic": traffic[kern] * H if kern in traffic else None,
-                "traffic_source": "ncu dram__bytes_read+write per hand (profiles/r1/traffic_final.json) x hands" if kern in traffic else None,
+                "frac": gbs / peaks["hbm_gbs"], "traffic": tr[0] * H if tr else None,
+                "traffic_source": f"ncu dram__bytes_read+write per hand (profiles/{tr[1]}/traffic_final.json) x hands" if tr else None,
                 "peak_source": peaks["source"], "algorithmic_bytes_per_hand": bytes_per_hand, "avg_launch_ms": ms,
-                "share_of_step": stages[stage]["share"]}
+                "share_of_step": stages[stage]["share"] if stage in stages else None}
 
+    stage_bytes = {"lbs_bwd": BYTES_LBS_BWD, "lbs_fwd": BYTES_LBS, "fused_fwd": BYTES_FUSED_FWD_TRAIN}
     dominant = max(stages, key=lambda k: stages[k]["ms"])
-    lbs_fwd_roof = hbm_roofline("lbs_fwd", BYTES_LBS)
-    lbs_bwd_roof = hbm_roofline("lbs_bwd", BYTES_LBS_BWD)
-    # `roofline` is the dominant kernel of the step (the skinning backward); the north star's named
-    # "LBS GB/s" figure — the skinning forward — is reported next to it
-    roofline = dict(lbs_bwd_roof if dominant == "lbs_bwd" else lbs_fwd_roof, dominant_stage=dominant)
-    blend_ms = stages["blend_fwd"]["ms"]
-    blend_tflops = FLOP_BLEND * H / (blend_ms * 1e-3) / 1e12
-    blend_kernel = "blend_tc_forward_mres_kernel" if (H + 127) // 128 >= 64 else "blend_tc_forward_kernel"
-    blend_roof = {"kernel": blend_kernel, "bound": "tensor", "achieved": blend_tflops, "peak": peaks["bf16_tflops_sustained"],
-                  "unit": "TFLOP/s", "frac": blend_tflops / peaks["bf16_tflops_sustained"],
-                  "algorithmic_flop_per_hand": FLOP_BLEND, "avg_launch_ms": blend_ms, "mode": args.mode,
-                  "hbm_write_gbs": 4 * 2352 * H / (blend_ms * 1e-3) / 1e9,
-                  "note": "3 fp16 products per algorithmic FLOP are executed (ncu: tensor pipe 56 % busy); the kernel writes 9.4 KB of "
-                          "v_posed_t per hand and sits 1.2x above its HBM-write floor (the single-product mode reaches it)"}
+    roof_stage = dominant if dominant in stage_bytes else max(stage_bytes.keys() & stages.keys(), key=lambda k: stages[k]["ms"])
+    # `roofline` is the dominant kernel of the step; the north star's named "LBS GB/s" figure — the skinning forward,
+    # now fused with the blend contraction — is reported next to it from the forward-only pass below
+    roofline = dict(hbm_roofline(roof_stage, stage_bytes[roof_stage]), dominant_stage=dominant)
     step_gbs = (BYTES_FWD + BYTES_BWD) * H / (ms_per_step * 1e-3) / 1e9
 
-    # ---- parity spot check: four hands of the last timed step are kept (numpy) for the CPU-baseline leg, the one
-    # place this script runs oracle/ in the product arm — as the checker of those four hands and as the timed baseline
+    # ---- forward only (north_star: >= 1e8 hands/s forward on 8 GPUs, LBS >= 70 % of the HBM roofline) -------------
+    fwd_mode = mode | cabi.FWD_INFERENCE
+
+    def fwd_step(i):
+        s = sets[i % nsets]
+        cabi.check(lib.mb_mano_forward(blob, 45, s["rot"].data_ptr(), s["pose"].data_ptr(), s["beta"].data_ptr(), H, fwd_mode,
+                                       s["verts"].data_ptr(), s["joints"].data_ptr(), ws.data_ptr(), ws_bytes, stream), "fwd")
+
+    for i in range(3):
+        fwd_step(i)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        fwd_step(i)
+    e1.record()
+    sync_all()
+    ms_fwd = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    lib.mb_profile_enable(1)
+    cabi.profile_collect()
+    for i in range(args.steps):
+        fwd_step(i)
+    torch.cuda.synchronize(dev)
+    fprof = cabi.profile_collect()
+    lib.mb_profile_enable(0)
+    fstages = {k: v[0] / v[1] for k, v in fprof.items()}
+    forward_only = {"value": world * H / (ms_fwd * 1e-3), "unit": "hands/s", "ms_per_step": ms_fwd, "steps": args.steps,
+                    "stages_ms": fstages, "hbm_algorithmic_gbs": BYTES_FWD * H / (ms_fwd * 1e-3) / 1e9,
+                    "hbm_frac": BYTES_FWD * H / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "algorithmic_bytes_per_hand": BYTES_FWD,
+                    "note": "mb_mano_forward with MB_FWD_INFERENCE (no rest-pose scratch kept): verts[H,778,3] + joints[H,21,3]"}
+    if "fused_fwd" in fstages and not args.no_extras:
+        # A/B: the same forward through the separate blend-contraction + skinning kernels (MB_FWD_UNFUSED)
+        um = fwd_mode | cabi.FWD_UNFUSED
+
+        def ufwd_step(i):
+            s = sets[i % nsets]
+            cabi.check(lib.mb_mano_forward(blob, 45, s["rot"].data_ptr(), s["pose"].data_ptr(), s["beta"].data_ptr(), H, um,
+                                           s["verts"].data_ptr(), s["joints"].data_ptr(), ws.data_ptr(), ws_bytes, stream), "fwd")
+
+        for i in range(2):
+            ufwd_step(i)
+        sync_all()
+        lib.mb_profile_enable(1)
+        cabi.profile_collect()
+        e0.record()
+        for i in range(5):
+            ufwd_step(i)
+        e1.record()
+        sync_all()
+        uprof = cabi.profile_collect()
+        lib.mb_profile_enable(0)
+        forward_only["unfused_ab"] = {"ms_per_step": e0.elapsed_time(e1) / 5, "stages_ms": {k: v[0] / v[1] for k, v in uprof.items()},
+                                      "note": "same launch with MB_FWD_UNFUSED: pose -> blend GEMM (writes v_posed_t) -> lane = hand skinning"}
+    if "fused_fwd" in fstages:
+        fms = fstages["fused_fwd"]
+        lbs_fwd_roof = hbm_roofline("fused_fwd", BYTES_FUSED_FWD, ms=fms)
+        lbs_fwd_roof["note"] = ("fused blend + skinning forward (vskin.cu), inference launch: feature tiles 640 + bone operand 1152 B in, "
+                                "verts 9336 + fingertip joints 60 B out per hand")
+        tfl = (FLOP_BLEND + FLOP_SKIN_T) * H / (fms * 1e-3) / 1e12
+        blend_roof = {"kernel": "vskin_forward_kernel", "bound": "tensor", "achieved": tfl, "peak": peaks["bf16_tflops_sustained"],
+                      "unit": "TFLOP/s", "frac": tfl / peaks["bf16_tflops_sustained"],
+                      "algorithmic_flop_per_hand": FLOP_BLEND + FLOP_SKIN_T, "avg_launch_ms": fms, "mode": args.mode,
+                      "note": "algorithmic FLOP of the blend contraction (676 860) + the dense weight blend T = W A (298 752); executed: "
+                              "x3 fp16 products for the blend, x4 for the transforms, on 896 padded vertex rows"}
+    else:
+        lbs_fwd_roof = hbm_roofline("lbs_fwd", BYTES_LBS, ms=fstages.get("lbs_fwd"))
+        bms = fstages["blend_fwd"]
+        tfl = FLOP_BLEND * H / (bms * 1e-3) / 1e12
+        blend_roof = {"kernel": "blend_tc_forward_mres_kernel" if (H + 127) // 128 >= 64 else "blend_tc_forward_kernel", "bound": "tensor",
+                      "achieved": tfl, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tfl / peaks["bf16_tflops_sustained"],
+                      "algorithmic_flop_per_hand": FLOP_BLEND, "avg_launch_ms": bms, "mode": args.mode}
+
+    # ---- parity: a fixed 8 192-hand subsample of the last timed step, checked in fp64 below ----
     parity = None
     cpu = None
     kept = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        step(args.steps - 1)                                   # the forward-only pass overwrote verts / joints: redo the last step
+        torch.cuda.synchronize(dev)
         s = sets[(args.steps - 1) % nsets]
-        idx = np.array([0, 1, H // 2, H - 1]) if H >= 4 else np.arange(H)
+        nk = min(H, 8192)
+        idx = np.unique(np.linspace(0, H - 1, nk).astype(np.int64))
         tidx = torch.from_numpy(idx).to(dev)
         kept = {k: s[k][tidx].cpu().numpy() for k in ("rot", "pose", "beta", "gv", "gj", "verts", "joints", "g_rot", "g_pose", "g_beta")}
+
+    # ---- the other BASELINE configs, short, in the same line (every rank takes part: config 5 has the collective) ----
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras = run_extras(args, pkg, layer, dev, rank, world, dist, sets[0])
+        except Exception as exc:                               # never lose the contract line to an extra
+            extras = {"error": repr(exc)}
+
     # ---- end to end through the public nn.Module API with host buffers ------------------
     e2e = None
     if not args.no_e2e:
@@ -582,46 +877,48 @@ def main():
             st.clear()
         sets.clear()
         torch.cuda.empty_cache()
-        if os.environ.get("MANO_B200_BENCH_DEBUG"):
-            sys.stderr.write(f"before e2e: allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB\n")
-        h_in = [torch.from_numpy(a).pin_memory() for a in synth_inputs(H, 555 + rank)]
-        h_out2 = [[torch.empty(H, n, dtype=torch.float32).pin_memory() for n in (3, 45, 10)] for _ in range(2)]
-        h_loss2 = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-
-        # The step is pipelined the way a host-fed training loop would be: the batch is cut into chunks,
-        # each chunk's host->device copy, ManoLayer forward, autograd backward and device->host copy
-        # run on one of two CUDA streams, so the PCIe copies of one chunk overlap the kernels of another
-        # (measured: 4 chunks on 2 streams 50.0 M hands/s, 8 on 3 46.0 M — a third stream only makes the
-        # chunks' kernels compete for the SMs) —
-        # across step boundaries too (a loader that prefetches the next batch): consecutive steps are ordered
-        # per stream only and write their results to alternating pinned buffers; every step still copies all
-        # of its inputs in and all of its gradients out inside the timed region.
+        bind_numa_local(local_rank)                           # pinned buffers are first-touched on the GPU's NUMA node
+        # ONE pinned buffer each way per step, laid out chunk by chunk as [rot | pose | beta] blocks so that a chunk is one
+        # contiguous host range: one H2D and one D2H copy per chunk (round 1 issued three each, from three arrays)
         n_chunks = int(os.environ.get("MANO_B200_E2E_CHUNKS", "4")) if H >= 8 * 4096 else 1
         Hc = (H + n_chunks - 1) // n_chunks
+        rot_h, pose_h, beta_h = synth_inputs(H, 555 + rank)
+        h_in = torch.empty(H * 58, dtype=torch.float32).pin_memory()
+        bounds = []
+        off = 0
+        for c in range(n_chunks):
+            a, b = c * Hc, min(H, (c + 1) * Hc)
+            n = b - a
+            blk = h_in[off:off + n * 58]
+            blk[:n * 3].copy_(torch.from_numpy(rot_h[a:b]).reshape(-1))
+            blk[n * 3:n * 48].copy_(torch.from_numpy(pose_h[a:b]).reshape(-1))
+            blk[n * 48:].copy_(torch.from_numpy(beta_h[a:b]).reshape(-1))
+            bounds.append((a, b, off))
+            off += n * 58
+        h_out2 = [torch.empty(H * 58, dtype=torch.float32).pin_memory() for _ in range(2)]
+        h_loss2 = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
         side = [torch.cuda.Stream(device=dev) for _ in range(min(int(os.environ.get("MANO_B200_E2E_STREAMS", "2")), n_chunks))]
-
         step_no = [0]
 
         def e2e_step():
             h_out, h_loss = h_out2[step_no[0] & 1], h_loss2[step_no[0] & 1]
             step_no[0] += 1
-            for c in range(n_chunks):
+            for c, (a, b, o) in enumerate(bounds):
                 st = side[c % len(side)]
+                n = b - a
                 with torch.cuda.stream(st):
-                    sl = slice(c * Hc, min(H, (c + 1) * Hc))
-                    d = [t[sl].to(dev, non_blocking=True).requires_grad_() for t in h_in]
+                    flat = h_in[o:o + n * 58].to(dev, non_blocking=True)
+                    d = [flat[:n * 3].view(n, 3).requires_grad_(), flat[n * 3:n * 48].view(n, 45).requires_grad_(),
+                         flat[n * 48:].view(n, 10).requires_grad_()]
                     verts, joints = layer(*d)
-                    torch.autograd.backward([verts, joints], [gv_keep[sl], gj_keep[sl]])
-                    for dst, src in zip(h_out, d):
-                        dst[sl].copy_(src.grad, non_blocking=True)
+                    torch.autograd.backward([verts, joints], [gv_keep[a:b], gj_keep[a:b]])
+                    g = torch.cat([x.grad.reshape(-1) for x in d])           # 232 B per hand of gradients, one D2H copy
+                    h_out[o:o + n * 58].copy_(g, non_blocking=True)
                     if c == 0:
                         h_loss.copy_(joints[0, 0, :1], non_blocking=True)
-                    for t in (verts, joints, gv_keep, gj_keep):
+                    for t in (verts, joints, gv_keep, gj_keep, g, flat):
                         t.record_stream(st)
-                    del verts, joints, d
-            if os.environ.get("MANO_B200_BENCH_DEBUG"):
-                sys.stderr.write(f"e2e step: allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB, "
-                                 f"reserved {torch.cuda.memory_reserved(dev) / 2**30:.1f} GiB\n")
+                    del verts, joints, d, g, flat
 
         def join_side():
             main = torch.cuda.current_stream(dev)
@@ -643,11 +940,14 @@ def main():
         ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
         e2e = {"value": world * H / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * 58 * 4,
                "d2h_bytes_per_step": H * 58 * 4 + 4, "ms_per_step": ms_e2e, "steps": n_e2e,
-               "api": "ManoLayer.forward + autograd backward; pinned host params in, pinned host grads out; "
-                      f"{n_chunks} chunks over {len(side)} CUDA streams, steps pipelined per stream (alternating pinned result buffers)"}
+               "api": "ManoLayer.forward + autograd backward; ONE pinned host buffer in (rot | pose | beta per chunk) and one out "
+                      f"(58 gradient floats per hand); {n_chunks} chunks over {len(side)} CUDA streams, one H2D + one D2H copy per chunk, "
+                      "steps pipelined per stream (alternating pinned result buffers); verts / joints and their upstream gradients "
+                      "stay on the device (the step's result that crosses PCIe is the parameter gradient)"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, parity = cpu_baseline(model, kept)
+        parity = parity_check(model, kept)
+        cpu = cpu_baseline(pkg.assets, model)
 
     if world > 1:
         dist.barrier()
@@ -672,9 +972,11 @@ def main():
         "step_hbm": {"algorithmic_gbs": step_gbs, "frac_of_peak": step_gbs / peaks["hbm_gbs"],
                      "algorithmic_bytes_per_hand": BYTES_FWD + BYTES_BWD},
         "stages_ms": stages,
+        "forward_only": forward_only,
         "parity": parity,
         "cpu_baseline": cpu,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
 
 

@@ -57,7 +57,8 @@ extern "C" {
  * MB_FWD_INFERENCE: no backward will follow — the forward keeps no rest-pose scratch in the workspace (a later
  *                   mb_mano_backward must then be called WITHOUT MB_BWD_WORKSPACE_VALID and recomputes it);
  * MB_FWD_UNFUSED  : run the separate blend-contraction and skinning kernels even where the fused kernel applies
- *                   (measurement / cross-checking). */
+ *                   (measurement / cross-checking); in mb_mano_backward's `mode`: the separate skinning-backward and
+ *                   gradient-contraction kernels with the dv_posed tiles in HBM. */
 #define MB_FWD_INFERENCE 0x200
 #define MB_FWD_UNFUSED   0x400
 
@@ -290,6 +291,12 @@ MB_API int mb_mano_fit_step(const void* blob, int nc, float* params, float* exp_
                      const float* target_joints, const float* keypoint_vis, int B, int mode, const double* globals,
                      double* partials, float lr, float beta1, float beta2, float eps, int step, int regularize,
                      mb_stream_t stream);
+/* Closes a fused iteration once the caller has all-reduced `partials` (mb_mano_fit_step's output): writes
+ * out4 = {sum vis |d|^2, N_vis, sum theta^2, sum beta^2} and loss = out4[0] / N_vis + (sqrt(out4[2]) + 10 sqrt(out4[3])) / 100
+ * for the iteration just done (norms of the parameters it started from; zero when regularize == 0), then moves the
+ * updated parameters' norms partials[1..2] into globals[1..2] for the next iteration.  All pointers device doubles. */
+MB_API int mb_fit_finalize(double* globals, const double* partials, int regularize, double* out4, double* loss,
+                    mb_stream_t stream);
 MB_API int mb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                  float lr, float beta1, float beta2, float eps, int step, mb_stream_t stream);
 

@@ -114,6 +114,12 @@ def test_fused_forward_through_the_layer(pkg, synth_model, cuda_device, B, nc):
     for x, want in zip(tg, og):
         got = x.grad.cpu().numpy()[sub]
         assert float(np.abs(got - want).max() / np.abs(want).max()) < 1e-4
+    # the separate skinning-backward + gradient-contraction kernels (dv_posed tiles through HBM) agree
+    tu = [x.clone().requires_grad_() for x in t]
+    v3, j3 = unfused(*tu)
+    ((v3 * torch.from_numpy(gv).to(cuda_device)).sum() + (j3 * torch.from_numpy(gj).to(cuda_device)).sum()).backward()
+    for a, b in zip(tg, tu):
+        assert float((a.grad - b.grad).abs().max() / b.grad.abs().max()) < 1e-4
 
 
 def test_fused_forward_is_batch_position_independent(pkg, synth_model, cuda_device):
