@@ -235,7 +235,7 @@ static int pose_and_blend_forward(const void* blob, int nc, const float* rot, co
     unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
     {
         StageTimer t(ST_POSE_FWD, s);
-        rc = use_lane_hand(model_flags, mode, B) ? launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, nullptr, joints, s)
+        rc = use_lane_hand(model_flags, mode, B) ? launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s)
                                                  : launch_pose_forward(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s);
         if (rc) return rc;
     }
@@ -254,12 +254,11 @@ static int fused_forward(const void* blob, int nc, const float* rot, const float
                          cudaStream_t s) {
     float* bone_t = reinterpret_cast<float*>(ws + W.bone_t);
     unsigned char* featp = reinterpret_cast<unsigned char*>(ws + W.featp);
-    unsigned char* bone16 = reinterpret_cast<unsigned char*>(ws + W.bone16);
     float* v_posed_t = (model_flags & MB_FWD_INFERENCE) ? nullptr : reinterpret_cast<float*>(ws + W.v_posed_t);
     int rc;
-    { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, bone16, joints, s))) return rc; }
+    { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s))) return rc; }
     StageTimer t(ST_FUSED_FWD, s);
-    return launch_vskin_forward(blob, featp, bone16, B, mode, verts, joints, v_posed_t, dbg, variant, s);
+    return launch_vskin_forward(blob, featp, bone_t, B, mode, verts, joints, v_posed_t, dbg, variant, s);
 }
 
 extern "C" int mb_mano_forward_debug(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
@@ -361,17 +360,9 @@ extern "C" int mb_mano_backward(const void* blob, int nc, const float* rot, cons
         if ((rc = launch_sgemm(rows, VP_PITCH, blob_ptr<float>(blob, L.basis_t), FEAT_K, dfeat, FEAT_K, B, FEAT_K, NVC, s))) return rc;
     } else {
         unsigned char* dvp = reinterpret_cast<unsigned char*>(ws + W.dvp);
-        if (lh && !(model_flags & MB_FWD_UNFUSED)) {
-            // large batches: the per-bone sums (role 1) ...
-            { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, nullptr, dbone, 1, dparts, s))) return rc; }
-            // ... and dv_posed feeding the tcgen05 gradient contraction from shared memory (no dv_posed tiles in HBM)
-            StageTimer t(ST_BLEND_BWD, s);
-            if ((rc = launch_skin_backward_dv_gemm(blob, bone_t, g_verts, g_joints, B, dfeat, s))) return rc;
-        } else {
-            { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, lh ? 1 : 0, dparts, s))) return rc; }
-            StageTimer t(ST_BLEND_BWD, s);        // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
-            if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, lh ? 1 : 0, dfeat_parts, dfeat_stride, s))) return rc;
-        }
+        { StageTimer t(ST_LBS_BWD, s); if ((rc = launch_skin_backward(blob, v_posed_t, bone_t, g_verts, g_joints, B, nullptr, dvp, dbone, lh ? 1 : 0, dparts, s))) return rc; }
+        StageTimer t(ST_BLEND_BWD, s);        // bf16 hi/mid x3 on tcgen05 in both tensor-core modes
+        if ((rc = launch_blend_tc_backward(blob, dvp, dfeat, B, lh ? 1 : 0, dfeat_parts, dfeat_stride, s))) return rc;
     }
     StageTimer t(ST_POSE_BWD, s);
     if (lh) return launch_pose_backward_lh(blob, nc, rot, coeffs, betas, dfeat, dbone, g_joints, B, g_rot, g_coeffs, g_betas, s);

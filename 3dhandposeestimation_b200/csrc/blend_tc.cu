@@ -507,8 +507,7 @@ blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsig
 
 // ---------------------------------------------------------------- host side
 static size_t tc_fwd_bytes() { return align256(sizeof(TcBlobHeader)) + align256((size_t)TC_N_TILES * TC_B_TILE_BYTES); }
-size_t blend_tc_bw48_offset() { return tc_fwd_bytes() + align256(TCB_B_BYTES); }
-size_t blend_tc_blob_bytes() { return blend_tc_bw48_offset() + align256(TCB48_BYTES); }
+size_t blend_tc_blob_bytes() { return tc_fwd_bytes() + align256(TCB_B_BYTES); }
 
 // basis [FEAT_K][2334] fp32 -> per n-tile, per K chunk, {hi, lo} blocks in the UMMA canonical
 // K-major layout [row-group][k-group][8 rows][8 halves]; pre-scaled by a power of two.  Columns are in
@@ -553,19 +552,6 @@ void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob
                 const size_t in = (((size_t)(r >> 3) * (TC_K_CHUNK / 8) + (kk >> 3)) * 8 + (r & 7)) * 8 + (kk & 7);
                 bw[((size_t)kc * 2 + 0) * (TC_B_BLOCK_BYTES / 2) + in] = hi;
                 bw[((size_t)kc * 2 + 1) * (TC_B_BLOCK_BYTES / 2) + in] = mid;
-            }
-    // ... and chunked by 16-vertex segment (K = 48): [49][split 2][row-group 20][k-group 6][8 rows][8 bf16]
-    __nv_bfloat16* b48 = reinterpret_cast<__nv_bfloat16*>(out + blend_tc_bw48_offset());
-    for (int seg = 0; seg < SK_NSEG; ++seg)
-        for (int r = 0; r < TC_N; ++r)
-            for (int kk = 0; kk < TCB48_K; ++kk) {
-                const int k = coord_map[seg * TCB48_K + kk];
-                const float x = (r < TC_K_REAL && k >= 0) ? basis[(size_t)r * NVC + k] : 0.f;
-                const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-                const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
-                const size_t in = (((size_t)(r >> 3) * (TCB48_K / 8) + (kk >> 3)) * 8 + (r & 7)) * 8 + (kk & 7);
-                b48[((size_t)seg * 2 + 0) * (TCB48_BLOCK_BYTES / 2) + in] = hi;
-                b48[((size_t)seg * 2 + 1) * (TCB48_BLOCK_BYTES / 2) + in] = mid;
             }
 }
 

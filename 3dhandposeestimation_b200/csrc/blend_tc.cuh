@@ -55,13 +55,6 @@ constexpr size_t TCB_B_BYTES = (size_t)TCB_K_CHUNKS * TCB_B_CHUNK_BYTES;
 
 inline size_t tc_dvp_bytes(long long B) { return (size_t)((B + TC_M - 1) / TC_M) * TCB_A_TILE_BYTES; }
 
-// the same B operand chunked by 16-vertex SEGMENT (K = 48 = 3 MMA steps) for the skinning backward that feeds the
-// contraction from shared memory (skin.cu, skin_backward_dv_gemm_kernel): [49 segments][hi, mid][160 rows x 48], 15 KB blocks
-constexpr int TCB48_K = 48;
-constexpr int TCB48_BLOCK_BYTES = TC_N * TCB48_K * 2;
-constexpr size_t TCB48_BYTES = (size_t)SK_NSEG * 2 * TCB48_BLOCK_BYTES;
-size_t blend_tc_bw48_offset();            // byte offset of that image inside the tensor-core blob section
-
 size_t blend_tc_blob_bytes();
 void blend_tc_pack(const float* basis, const int32_t* coord_map, void* host_blob_tc);
 

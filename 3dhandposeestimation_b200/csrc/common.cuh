@@ -40,8 +40,6 @@ constexpr int SK_NCOORD = SK_NPOS * 3;                     // 2352 coordinates p
 constexpr int SK_MAX_ENT = 512;                            // (block, bone) pairs supported
 constexpr int SK_SLOTS = 6;                                // bone transforms a warp keeps resident in shared memory
 constexpr int SK_MAX_CMD = 256;                            // slot (re)load commands per sweep
-constexpr int VS_NH = 64;                                  // hands per tile of the fused lane = vertex forward (vskin.cu)
-constexpr int VS_BONE_TILE_BYTES = 16 * 3 * 1536;          // its bone operand per hand tile: 16 chunks x 3 fp16 splits x (48 x 16 halves)
 constexpr int SK_TMPL_PAD = 2400;                          // v_template in block order, padded to the GEMM's 15 x 160 columns
 
 // Device blob layout (byte offsets, every section 256-byte aligned).
@@ -125,7 +123,6 @@ struct WorkLayout {
     // tensor-core modes
     size_t featp;     // fp16 hi/lo feature tiles: ceil(B/128) * 80 KB
     size_t dvp;       // bf16 hi/mid dv_posed tiles of the tcgen05 backward: ceil(B/128) * 74 * 16 KB
-    size_t bone16;    // fp16 x3 bone operand of the fused lane = vertex forward: ceil(B/64) * 72 KB
     // fp32 anchor mode
     size_t feat;      // float [B][FEAT_K]
     size_t rows;      // float [B][VP_PITCH]       sgemm output (v_posed) / input (dv_posed), original vertex order
@@ -173,7 +170,7 @@ __host__ __device__ inline WorkLayout work_layout(long long B, int mode) {
     W.dparts = o;                                              // split backward sweeps: per-unit bone sums
     const int spu = skin_segments_per_unit((long long)G, SKB_SWEEPERS);
     if (spu < SK_NSEG) o = align256(o + sizeof(float) * G * skin_units_per_group(spu) * NJ * BONE_F * 32);
-    W.featp = W.dvp = W.bone16 = W.feat = W.rows = W.dv_t = o;
+    W.featp = W.dvp = W.feat = W.rows = W.dv_t = o;
     if (mode == MB_MODE_FP32) {
         W.feat = o;  o = align256(o + sizeof(float) * B * FEAT_K);
         W.rows = o;  o = align256(o + sizeof(float) * B * VP_PITCH);
@@ -181,7 +178,6 @@ __host__ __device__ inline WorkLayout work_layout(long long B, int mode) {
     } else {
         W.featp = o; o = align256(o + T * 81920);
         W.dvp = o;   o = align256(o + T * (74 * 16384));
-        W.bone16 = o; o = align256(o + (size_t)((B + VS_NH - 1) / VS_NH) * VS_BONE_TILE_BYTES);
     }
     W.total = o;
     return W;
@@ -198,9 +194,8 @@ __host__ __device__ inline const T* blob_ptr(const void* blob, size_t off) {
 int launch_pose_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                         int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s);
 // one-thread-per-hand variants (mano_pose_lh.cu): MANO tree only; dfeat_t [G][160][32], dbone_t [G][192][32] hand-minor
-// bone16 (nullable): fp16 x3 bone operand of the fused lane = vertex forward (vskin.cuh)
 int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                           int B, float* feat, unsigned char* featp, float* bone_t, unsigned char* bone16, float* joints, cudaStream_t s);
+                           int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s);
 int launch_pose_backward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
                             const float* dfeat_t, const float* dbone_t, const float* g_joints, int B,
                             float* g_rot, float* g_coeffs, float* g_betas, cudaStream_t s);

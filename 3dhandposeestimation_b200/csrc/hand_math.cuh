@@ -89,18 +89,43 @@ HD void sincos_acc(float a, float* s, float* c) {
 // largest error of the whole layer against the fp64 arbiter (profiles/r2: blended transforms off by 6.7e-7, verts
 // by 1.3e-7 m).  t^2 is exact in double, 1 / t comes from the fp32 rsqrt refined by two Newton steps, sin / cos from the
 // fp32 sincosf of the rounded angle plus the first-order term of the rounding residue; the entries are rounded to fp32
-// once.  ~30 double FMAs per call (B200 runs them at half the fp32 rate), no double sqrt / divide.
-HD M3 rodrigues(const V3& r) {
+// once.  ~30 double FMAs per call (B200 runs them at half the fp32 rate), no double sqrt / divide.  rodrigues_d keeps
+// the entries in double for the large-batch forward chain (mano_pose_lh.cu), whose four chained products would
+// otherwise add another ~5e-7 to the blended transforms.
+struct M3d { double m[9]; };  // row-major 3x3 in double: the forward chain of the large-batch pose kernel
+struct V3d { double x, y, z; };
+HD M3d m3d_mul(const M3d& a, const M3d& b) {
+    M3d r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r.m[i*3+j] = fma(a.m[i*3+0], b.m[0*3+j], fma(a.m[i*3+1], b.m[1*3+j], a.m[i*3+2] * b.m[2*3+j]));
+    return r;
+}
+HD V3d m3d_vec(const M3d& a, const V3d& v) {
+    V3d r;
+    r.x = fma(a.m[0], v.x, fma(a.m[1], v.y, a.m[2] * v.z));
+    r.y = fma(a.m[3], v.x, fma(a.m[4], v.y, a.m[5] * v.z));
+    r.z = fma(a.m[6], v.x, fma(a.m[7], v.y, a.m[8] * v.z));
+    return r;
+}
+HD V3d v3d(const V3& v) { V3d r; r.x = v.x; r.y = v.y; r.z = v.z; return r; }
+HD V3d v3d_add(const V3d& a, const V3d& b) { V3d r; r.x = a.x + b.x; r.y = a.y + b.y; r.z = a.z + b.z; return r; }
+HD V3d v3d_sub(const V3d& a, const V3d& b) { V3d r; r.x = a.x - b.x; r.y = a.y - b.y; r.z = a.z - b.z; return r; }
+HD M3 m3_from(const M3d& a) { M3 r; for (int i = 0; i < 9; ++i) r.m[i] = (float)a.m[i]; return r; }
+HD V3 v3_from(const V3d& a) { return v3((float)a.x, (float)a.y, (float)a.z); }
+
+HD M3d rodrigues_d(const V3& r) {
     const double x = r.x, y = r.y, z = r.z;
     const double t2 = x * x + (y * y + z * z);
-    M3 R;
+    M3d R;
     if (t2 < 1e-60) {
-        const float f2 = (float)t2;
-        const float a = 1.f - f2 / 6.f, b = 0.5f - f2 / 24.f;
+        const double a = 1.0 - t2 / 6.0, b = 0.5 - t2 / 24.0;
         // S(r)^2 = r r^T - t2 I
-        R.m[0] = 1.f + b * (r.x * r.x - f2); R.m[1] = -a * r.z + b * r.x * r.y;   R.m[2] = a * r.y + b * r.x * r.z;
-        R.m[3] = a * r.z + b * r.x * r.y;    R.m[4] = 1.f + b * (r.y * r.y - f2); R.m[5] = -a * r.x + b * r.y * r.z;
-        R.m[6] = -a * r.y + b * r.x * r.z;   R.m[7] = a * r.x + b * r.y * r.z;    R.m[8] = 1.f + b * (r.z * r.z - f2);
+        R.m[0] = 1.0 + b * (x * x - t2); R.m[1] = -a * z + b * x * y;     R.m[2] = a * y + b * x * z;
+        R.m[3] = a * z + b * x * y;      R.m[4] = 1.0 + b * (y * y - t2); R.m[5] = -a * x + b * y * z;
+        R.m[6] = -a * y + b * x * z;     R.m[7] = a * x + b * y * z;      R.m[8] = 1.0 + b * (z * z - t2);
         return R;
     }
     // 1 / t: fp32 estimate (t2 is rescaled into fp32's range: axis-angles below 1e-19 would underflow t2) + 2 Newton steps
@@ -125,11 +150,12 @@ HD M3 rodrigues(const V3& r) {
     const double cd = (double)cf - (double)tl * (double)sf;
     const double a = sd * inv, b = (1.0 - cd) * (inv * inv);
     const double bxy = b * x * y, bxz = b * x * z, byz = b * y * z;
-    R.m[0] = (float)(1.0 + b * (x * x - t2)); R.m[1] = (float)(bxy - a * z);           R.m[2] = (float)(bxz + a * y);
-    R.m[3] = (float)(bxy + a * z);            R.m[4] = (float)(1.0 + b * (y * y - t2)); R.m[5] = (float)(byz - a * x);
-    R.m[6] = (float)(bxz - a * y);            R.m[7] = (float)(byz + a * x);           R.m[8] = (float)(1.0 + b * (z * z - t2));
+    R.m[0] = 1.0 + b * (x * x - t2); R.m[1] = bxy - a * z;            R.m[2] = bxz + a * y;
+    R.m[3] = bxy + a * z;            R.m[4] = 1.0 + b * (y * y - t2); R.m[5] = byz - a * x;
+    R.m[6] = bxz - a * y;            R.m[7] = byz + a * x;            R.m[8] = 1.0 + b * (z * z - t2);
     return R;
 }
+HD M3 rodrigues(const V3& r) { return m3_from(rodrigues_d(r)); }
 
 // d<dR, rodrigues(r)>/dr.  SURVEY Appendix A.2 step 6.  R = I + a S + b S^2 with
 // a = sin t / t, b = (1 - cos t)/t^2 (S = skew(r)); analytic limits for small t where

@@ -17,7 +17,6 @@
 #include <cuda_fp16.h>
 #include "hand_math.cuh"
 #include "blend_tc.cuh"
-#include "vskin.cuh"
 #include "ptx.cuh"
 
 namespace mb {
@@ -175,22 +174,21 @@ __device__ __forceinline__ void lh_theta(const LhConsts& C, const float* s_coef,
 }
 
 // bone transform with the global rotation folded in: A' = [Rq Rg | Rq (tg - Rg J)]  -> bone_t[group][k][lane][12]
-// ... and, when bone16 is given, into the fp16 x3 MMA operand of the fused lane = vertex forward (vskin.cuh)
-__device__ __forceinline__ void emit_bone(float* __restrict__ bt, unsigned char* __restrict__ bone16, long long hand, int k,
-                                          const M3& Rq, const M3& Rg, const V3& tg, const V3& J) {
-    const M3 Rp = m3_mul(Rq, Rg);
-    const V3 tp = m3_vec(Rq, v3_sub(tg, m3_vec(Rg, J)));
+// (the forward chain runs in double and is rounded to fp32 here, once)
+__device__ __forceinline__ void emit_bone(float* __restrict__ bt, int k, const M3d& Rq, const M3d& Rg, const V3d& tg, const V3d& J) {
+    const M3 Rp = m3_from(m3d_mul(Rq, Rg));
+    const V3 tp = v3_from(m3d_vec(Rq, v3d_sub(tg, m3d_vec(Rg, J))));
     float4* o = reinterpret_cast<float4*>(bt + k * (BONE_F * 32));      // bone_t[group][k][lane][12]
     o[0] = make_float4(Rp.m[0], Rp.m[1], Rp.m[2], tp.x);
     o[1] = make_float4(Rp.m[3], Rp.m[4], Rp.m[5], tp.y);
     o[2] = make_float4(Rp.m[6], Rp.m[7], Rp.m[8], tp.z);
-    if (bone16 != nullptr) {
-        const float A[BONE_F] = {Rp.m[0], Rp.m[1], Rp.m[2], tp.x, Rp.m[3], Rp.m[4], Rp.m[5], tp.y, Rp.m[6], Rp.m[7], Rp.m[8], tp.z};
-        vs_emit_bone16(bone16, hand, k, A);
-    }
 }
 __device__ __forceinline__ void emit_joint(float* __restrict__ jrow, int slot, const M3& Rq, const V3& tg) {
     const V3 j = m3_vec(Rq, tg);
+    jrow[slot * 3] = j.x; jrow[slot * 3 + 1] = j.y; jrow[slot * 3 + 2] = j.z;
+}
+__device__ __forceinline__ void emit_joint(float* __restrict__ jrow, int slot, const M3d& Rq, const V3d& tg) {
+    const V3 j = v3_from(m3d_vec(Rq, tg));
     jrow[slot * 3] = j.x; jrow[slot * 3 + 1] = j.y; jrow[slot * 3 + 2] = j.z;
 }
 
@@ -198,7 +196,7 @@ __global__ void __launch_bounds__(LH_WARPS * 32)
 pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __restrict__ rot,
                        const float* __restrict__ coeffs, const float* __restrict__ betas, int B,
                        float* __restrict__ feat, unsigned char* __restrict__ featp, float* __restrict__ bone_t,
-                       unsigned char* __restrict__ bone16, float* __restrict__ joints) {
+                       float* __restrict__ joints) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LhConsts& C = *reinterpret_cast<LhConsts*>(smem_raw);
     lh_stage_constants(C, blob, nc);
@@ -229,7 +227,7 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
         float beta[NB];
 #pragma unroll
         for (int s = 0; s < NB; ++s) beta[s] = s_beta[r * NB + s];
-        const M3 Rq = rodrigues(v3(s_rot[r * 3], s_rot[r * 3 + 1], s_rot[r * 3 + 2]));
+        const M3d Rq = rodrigues_d(v3(s_rot[r * 3], s_rot[r * 3 + 1], s_rot[r * 3 + 2]));
         // theta needs this lane's coefficients: copy them out of the row-major staging first
         // (the theta rows alias nothing below float 32*NAA + 32*NB + 96 = 1856 < THETA_ROW * BP)
         lh_theta(C, s_coef + r * nc, nc, bl);
@@ -238,29 +236,29 @@ pose_forward_lh_kernel(const void* __restrict__ blob, int nc, const float* __res
         float* bt = bone_t + (size_t)g * (NJ * BONE_F * 32) + lane * BONE_F;
         float* jrow = joints + hand * (NOUTJ * 3);
         // ---- wrist: constant root rotation [pi, 0, 0] (:76, :128)
-        const M3 R0 = rodrigues(v3(3.14159274101257324f, 0.f, 0.f));
-        const V3 J0 = rest_joint(C, 0, beta);
-        if (live) { emit_bone(bt, bone16, hand, 0, Rq, R0, J0, J0); emit_joint(jrow, 0, Rq, J0); }
+        const M3d R0 = rodrigues_d(v3(3.14159274101257324f, 0.f, 0.f));
+        const V3d J0 = v3d(rest_joint(C, 0, beta));
+        if (live) { emit_bone(bt, 0, Rq, R0, J0, J0); emit_joint(jrow, 0, Rq, J0); }
 #pragma unroll
         for (int s = 0; s < NB; ++s) bl[s * BP] = beta[s];
         bl[FEAT_ONE * BP] = 1.f; bl[(FEAT_ONE + 1) * BP] = 0.f; bl[(FEAT_ONE + 2) * BP] = 0.f;
         // ---- five chains of three joints
 #pragma unroll 1
         for (int f = 0; f < 5; ++f) {
-            M3 Rgp = R0;
-            V3 tgp = J0, Jp = J0;
+            M3d Rgp = R0;
+            V3d tgp = J0, Jp = J0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const int k = 1 + 3 * f + i;
                 const float* th = bl + (THETA_ROW + 3 * (k - 1)) * BP;
-                const M3 R = rodrigues(v3(th[0], th[BP], th[2 * BP]));
+                const M3d R = rodrigues_d(v3(th[0], th[BP], th[2 * BP]));
                 float* fr = bl + (NB + 9 * (k - 1)) * BP;
 #pragma unroll
-                for (int e = 0; e < 9; ++e) fr[e * BP] = R.m[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
-                const V3 J = rest_joint(C, k, beta);
-                const M3 Rg = m3_mul(Rgp, R);
-                const V3 tg = v3_add(tgp, m3_vec(Rgp, v3_sub(J, Jp)));
-                if (live) { emit_bone(bt, bone16, hand, k, Rq, Rg, tg, J); emit_joint(jrow, 1 + 4 * f + i, Rq, tg); }
+                for (int e = 0; e < 9; ++e) fr[e * BP] = (float)(R.m[e] - ((e == 0 || e == 4 || e == 8) ? 1.0 : 0.0));
+                const V3d J = v3d(rest_joint(C, k, beta));
+                const M3d Rg = m3d_mul(Rgp, R);
+                const V3d tg = v3d_add(tgp, m3d_vec(Rgp, v3d_sub(J, Jp)));
+                if (live) { emit_bone(bt, k, Rq, Rg, tg, J); emit_joint(jrow, 1 + 4 * f + i, Rq, tg); }
                 Rgp = Rg; tgp = tg; Jp = J;
             }
         }
@@ -819,10 +817,10 @@ inline int lh_grid(int B) {
 }  // namespace
 
 int launch_pose_forward_lh(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
-                           int B, float* feat, unsigned char* featp, float* bone_t, unsigned char* bone16, float* joints, cudaStream_t s) {
+                           int B, float* feat, unsigned char* featp, float* bone_t, float* joints, cudaStream_t s) {
     static SmemAttrOnce once;
     if (int arc = ensure_dyn_smem(once, pose_forward_lh_kernel, LH_SMEM)) return arc;
-    pose_forward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, B, feat, featp, bone_t, bone16, joints);
+    pose_forward_lh_kernel<<<lh_grid(B), LH_WARPS * 32, LH_SMEM, s>>>(blob, nc, rot, coeffs, betas, B, feat, featp, bone_t, joints);
     return cuda_rc();
 }
 

@@ -61,6 +61,30 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     return p;
 }
 
+// ---- thread-block clusters: rank / size of this CTA's cluster, cluster-wide barrier, multicast bulk copy ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one L2 read, delivered to the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier (same
+// offset) receives the byte count
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask,
+                                                   uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+                 "[%0], [%1], %2, [%3], %4, %5;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask), "l"(policy) : "memory");
+}
+
+// one lane of the (converged) warp, chosen by the hardware: code under it is single-threaded AND the compiler knows it, so
+// bulk-copy / MMA operands stay in uniform registers without a per-instruction vote ("waterfall") loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- asynchronous global -> shared copies by the threads themselves (cp.async, LDGSTS) ----------------------------
 // A staging loop `tile[i] = src[i]` is one dependent global-load round trip per element and thread; with the few
 // warps per SM of the one-thread-per-hand kernels that chain was up to 40 % of their time.  cp.async requests are

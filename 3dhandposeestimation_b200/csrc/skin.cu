@@ -33,7 +33,6 @@
 #include "blend_tc.cuh"
 #include "skin.cuh"
 #include "ptx.cuh"
-#include "tc_ptx.cuh"
 
 namespace mb {
 namespace {
@@ -141,14 +140,6 @@ __device__ __forceinline__ void load_voff(const SkinProg& P, int blk, int (&o)[S
 // latency (there is no L1 to speak of — shared memory takes the whole carve-out) never reaches the
 // register scoreboard.  [round-1 ncu: with register prefetch one entry ahead half of all stall
 // samples were long-scoreboard waits on the first use of a bone or coordinate]
-// one lane of the (converged) warp, chosen by the hardware: lets ptxas keep the bulk-copy operands in
-// uniform registers without a vote loop
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 // A wait that cannot hang the GPU: a broken schedule / pipeline traps after ~2 s instead of spinning forever.
 __device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -569,8 +560,7 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                      const float* __restrict__ bone_t, const float* __restrict__ g_verts,
                      const float* __restrict__ g_joints, int B,
                      float* __restrict__ dv_t, unsigned char* __restrict__ dvp, float* __restrict__ dbone,
-                     int dbone_hand_minor, float* __restrict__ dparts, int spu, int dv_off) {
-    // dv_off: dv_posed is produced elsewhere (skin_backward_dv_gemm_kernel) — role 0 only helps loading the gradient tiles
+                     int dbone_hand_minor, float* __restrict__ dparts, int spu) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -591,7 +581,7 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
     const int u0 = blockIdx.x + pair * gridDim.x, ustep = gridDim.x * SKB_PAIRS;
     const L2Policies pol = make_policies();
     CacheState CS = {0, 0, 0u, 0u};
-    if (!SPLIT && role == 0 && !dv_off && u0 < nunits) cache_prologue(W.bones, CS, P, bone_t + (size_t)u0 * GROUP_BONE_FLOATS, pol.keep);
+    if (!SPLIT && role == 0 && u0 < nunits) cache_prologue(W.bones, CS, P, bone_t + (size_t)u0 * GROUP_BONE_FLOATS, pol.keep);
     const size_t next_off = (size_t)ustep * GROUP_BONE_FLOATS;
 
     for (int u = u0; u < nunits; u += ustep) {
@@ -601,7 +591,7 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
         const float* vb = v_posed_t + (size_t)g * GROUP_V_FLOATS + lane;
         const float* bgrp = bone_t + (size_t)g * GROUP_BONE_FLOATS;
         const bool has_next = !SPLIT && u + ustep < nunits;
-        if (role == 0 && !dv_off) {
+        if (role == 0) {
             if (SPLIT) cache_begin_part(W.bones, CS, P, seg0, bgrp, pol.keep);
             else cache_begin_group(CS, P);
         }
@@ -733,10 +723,8 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
             }
             if (seg + 1 < seg1) prefetch_g(seg + 1);
             if (role == 0) {
-                if (!dv_off) {
-                    dv_block(2 * seg);
-                    dv_block(2 * seg + 1);
-                }
+                dv_block(2 * seg);
+                dv_block(2 * seg + 1);
             } else {
                 load_xpairs(vbk, vb + (size_t)(2 * seg + 1) * XBLK_FLOATS, pol.stream);
                 da_block(2 * seg, va);
@@ -746,7 +734,7 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
         }
         if (SPLIT) {
             if (role == 0) {
-                if (!dv_off) cache_drain(W.bones, CS);
+                cache_drain(W.bones, CS);
             } else {
                 __syncwarp();
                 int touched = 0;
@@ -776,254 +764,6 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
             __syncwarp();
         }
     }
-}
-
-// ----------------------------------------------------------------- backward, large batches: dv_posed -> tensor core in the same CTA
-// Round-1 ncu (profiles/r1): the skinning backward wrote dv_posed as bf16 hi+mid tiles (9.4 KB per hand) that a second
-// kernel read back for the gradient contraction dfeat = dv_posed . basis^T — 18.8 KB of HBM traffic per hand for a
-// tensor that lives ~a millisecond.  Here a CTA owns 128 hands (4 hand groups = the 128 TMEM lanes): four warps run
-// the dv_posed half of the backward (role 0 above, one hand group each) and write their K-groups — a lane owns a
-// tile row, 8 consecutive K values are 16 bytes — straight into the A-operand stage in SHARED memory; one thread
-// issues the tcgen05 products against the basis stream (bf16 hi + mid, 3 products, as blend_tc.cu's backward) with the
-// fp32 accumulator [128 hands x 160 features] resident in TMEM across all 49 segments; four more warps drain it as
-// dfeat_t[group][160][32].  K is chunked by 16-vertex SEGMENT (48 coordinates = 3 MMA K steps), which is the unit the
-// skinning sweep produces.  The per-bone sums (role 1) stay in skin_backward_kernel, launched with its role 0 idle.
-constexpr int DVG_THREADS = 384;                   // w0 basis producer, w1 MMA, w2 TMEM alloc, w3 idle, w4-7 dv_posed, w8-11 accumulator drain
-constexpr int DVG_K = SEG_F;                       // 48 coordinates per stage
-constexpr int DVG_KG = DVG_K / 8;                  // 6 K-groups (core matrices) per 8-row group
-constexpr int DVG_A_SPLIT_BYTES = 128 * DVG_K * 2; // 12 KB: one bf16 split of 128 hands x 48
-constexpr int DVG_A_STAGE_BYTES = 2 * DVG_A_SPLIT_BYTES;
-constexpr int DVG_B_SPLIT_BYTES = TC_N * DVG_K * 2;   // 15 KB: 160 features x 48
-constexpr int DVG_B_STAGE_BYTES = 2 * DVG_B_SPLIT_BYTES;
-constexpr int DVG_ASTAGES = 2, DVG_BSTAGES = 2, DVG_ACC = 2;
-constexpr uint32_t DVG_SBO = DVG_KG * 128;         // 768 B between 8-row groups
-constexpr uint32_t DVG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // bf16 x bf16 -> f32
-struct alignas(128) DvgWarpShared {
-    BoneCache bones;
-    alignas(16) float tile[TILE_FLOATS];
-};
-struct alignas(128) DvgShared {
-    alignas(128) unsigned char a[DVG_ASTAGES][DVG_A_STAGE_BYTES];
-    alignas(128) unsigned char b[DVG_BSTAGES][DVG_B_STAGE_BYTES];
-    DvgWarpShared w[4];
-    alignas(8) unsigned long long a_full[DVG_ASTAGES], a_empty[DVG_ASTAGES], b_full[DVG_BSTAGES], b_empty[DVG_BSTAGES];
-    unsigned long long acc_full[DVG_ACC], acc_empty[DVG_ACC];
-    uint32_t tmem_base;
-};
-constexpr size_t DVG_SMEM = PROG_BYTES + sizeof(DvgShared) + 128;
-
-__global__ void __launch_bounds__(DVG_THREADS, 1)
-skin_backward_dv_gemm_kernel(const void* __restrict__ blob, const unsigned char* __restrict__ basis_bw48,
-                             const float* __restrict__ bone_t, const float* __restrict__ g_verts,
-                             const float* __restrict__ g_joints, int B, int m_tiles, float* __restrict__ dfeat_t) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
-    DvgShared& S = *reinterpret_cast<DvgShared*>((reinterpret_cast<uintptr_t>(smem_raw + PROG_BYTES) + 127) & ~uintptr_t(127));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < DVG_ASTAGES; ++s) { mbar_init(smem_u32(&S.a_full[s]), 4); mbar_init(smem_u32(&S.a_empty[s]), 1); }
-        for (int s = 0; s < DVG_BSTAGES; ++s) { mbar_init(smem_u32(&S.b_full[s]), 1); mbar_init(smem_u32(&S.b_empty[s]), 1); }
-        for (int s = 0; s < DVG_ACC; ++s) { mbar_init(smem_u32(&S.acc_full[s]), 1); mbar_init(smem_u32(&S.acc_empty[s]), 4); }
-        fence_barrier_init();
-    }
-    if (warp >= 4 && warp < 8 && lane == 0) { S.w[warp - 4].bones.init(); fence_barrier_init(); }
-    stage_prog(P, blob);
-    if (warp == 2) tmem_alloc(smem_u32(&S.tmem_base), 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = S.tmem_base;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== basis producer: the same 49-stage stream for every hand tile (L2 hits) =====
-            const uint64_t keep = l2_policy_evict_last();
-            uint32_t st = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x)
-                for (int seg = 0; seg < SK_NSEG; ++seg) {
-                    mbar_wait_or_trap(smem_u32(&S.b_empty[st]), ph ^ 1);
-                    mbar_expect_tx(smem_u32(&S.b_full[st]), DVG_B_STAGE_BYTES);
-                    bulk_g2s_hint(smem_u32(S.b[st]), basis_bw48 + (size_t)seg * DVG_B_STAGE_BYTES, DVG_B_STAGE_BYTES, smem_u32(&S.b_full[st]), keep);
-                    if (++st == DVG_BSTAGES) { st = 0; ph ^= 1; }
-                }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
-            const uint64_t a_base = umma_desc(smem_u32(S.a[0]), TC_LBO, DVG_SBO);
-            const uint64_t b_base = umma_desc(smem_u32(S.b[0]), TC_LBO, DVG_SBO);
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-                mbar_wait_or_trap(smem_u32(&S.acc_empty[acc]), accph ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem + acc * TC_N;
-                for (int seg = 0; seg < SK_NSEG; ++seg) {
-                    mbar_wait_or_trap(smem_u32(&S.a_full[as]), aph);
-                    mbar_wait_or_trap(smem_u32(&S.b_full[bs]), bph);
-                    tc_fence_after();
-                    const uint64_t a_st = a_base + (uint64_t)((as * DVG_A_STAGE_BYTES) >> 4);
-                    const uint64_t b_st = b_base + (uint64_t)((bs * DVG_B_STAGE_BYTES) >> 4);
-#pragma unroll
-                    for (int j = 0; j < DVG_K / 16; ++j) {
-                        const uint64_t a_hi = a_st + (uint64_t)((j * 2 * (int)TC_LBO) >> 4), a_mid = a_hi + (uint64_t)(DVG_A_SPLIT_BYTES >> 4);
-                        const uint64_t b_hi = b_st + (uint64_t)((j * 2 * (int)TC_LBO) >> 4), b_mid = b_hi + (uint64_t)(DVG_B_SPLIT_BYTES >> 4);
-                        umma_f16(d, a_hi, b_hi, DVG_IDESC, (seg | j) ? 1u : 0u);
-                        umma_f16(d, a_mid, b_hi, DVG_IDESC, 1);
-                        umma_f16(d, a_hi, b_mid, DVG_IDESC, 1);
-                    }
-                    tc_commit(smem_u32(&S.a_empty[as]));
-                    tc_commit(smem_u32(&S.b_empty[bs]));
-                    if (++as == DVG_ASTAGES) { as = 0; aph ^= 1; }
-                    if (++bs == DVG_BSTAGES) { bs = 0; bph ^= 1; }
-                }
-                tc_commit(smem_u32(&S.acc_full[acc]));
-                if (++acc == DVG_ACC) { acc = 0; accph ^= 1; }
-            }
-        }
-    } else if (warp >= 8) {
-        // ===== accumulator drain: TMEM lane quarter = hand group -> dfeat_t[group][160][32], coalesced 128-byte rows =====
-        const int q = warp & 3;
-        uint32_t acc = 0, accph = 0;
-        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-            mbar_wait_or_trap(smem_u32(&S.acc_full[acc]), accph);
-            tc_fence_after();
-            const long long group = (long long)tile * 4 + q;
-            const bool live = group * 32 < B;
-#pragma unroll 1
-            for (int j = 0; j < TC_N / 32; ++j) {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * TC_N + j * 32, v);
-                if (j == TC_N / 32 - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty[acc]));
-                }
-                if (live) {
-                    float* dst = dfeat_t + ((size_t)group * TC_N + j * 32) * 32 + lane;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) dst[c * 32] = v[c];
-                }
-            }
-            if (++acc == DVG_ACC) { acc = 0; accph ^= 1; }
-        }
-    } else if (warp >= 4) {
-        // ===== dv_posed of one hand group per warp (role 0 of skin_backward_kernel), K-groups into the A stage =====
-        const int q = warp - 4;
-        DvgWarpShared& W = S.w[q];
-        float* tl = W.tile + lane;
-        const RowMap rm(lane);
-        float* tsd = W.tile + rm.tile_base();
-        const L2Policies pol = make_policies();
-        CacheState CS = {0, 0, 0u, 0u};
-        const int g0 = blockIdx.x * 4 + q;
-        const int ngroups = (B + 31) >> 5;
-        if (g0 < ngroups) cache_prologue(W.bones, CS, P, bone_t + (size_t)g0 * GROUP_BONE_FLOATS, pol.keep);
-        const size_t next_off = (size_t)gridDim.x * 4 * GROUP_BONE_FLOATS;
-        uint32_t as = 0, aph = 0;
-        const int rg = q * 4 + (lane >> 3), r = lane & 7;                     // this lane's row of the 128-hand tile
-        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-            const int g = tile * 4 + q;
-            const bool group_live = g < ngroups;
-            const int nh = group_live ? ((B - g * 32) < 32 ? (B - g * 32) : 32) : 0;
-            const float* bgrp = bone_t + (size_t)g * GROUP_BONE_FLOATS;
-            const bool has_next = g + (int)gridDim.x * 4 < ngroups;
-            if (group_live) cache_begin_group(CS, P);
-            const float* grow = g_verts + (size_t)g * 32 * NVC + rm.row_base();
-            float2 pre[8][3];                                                  // the whole segment's row pieces, one segment ahead
-            auto prefetch_g = [&](int seg) {
-                const int nf = (seg == SK_NSEG - 1) ? (NV - seg * SK_SEG) * 3 : SEG_F;
-                const float* src = grow + seg * SEG_F;
-#pragma unroll
-                for (int rb = 0; rb < 8; ++rb)
-#pragma unroll
-                    for (int qb = 0; qb < 3; ++qb) {
-                        const bool ok = (rb * 4 + rm.r < nh) && (qb * 16 + 2 * rm.p < nf);
-                        pre[rb][qb] = ok ? ld_stream2(src + (size_t)rb * 4 * NVC + qb * 16, pol.stream) : make_float2(0.f, 0.f);
-                    }
-            };
-            prefetch_g(0);
-            for (int seg = 0; seg < SK_NSEG; ++seg) {
-                __syncwarp();                                                  // every lane is done with the previous tile
-#pragma unroll
-                for (int rb = 0; rb < 8; ++rb)
-#pragma unroll
-                    for (int qb = 0; qb < 3; ++qb) {
-                        tsd[(qb * 16) * TP + rb * 4] = pre[rb][qb].x;
-                        tsd[(qb * 16 + 1) * TP + rb * 4] = pre[rb][qb].y;
-                    }
-                __syncwarp();
-                bool has_tip = false;
-#pragma unroll
-                for (int t = 0; t < N_TIP; ++t) has_tip |= (c_tip_vert[t] / SK_SEG == seg);
-                if (has_tip) {
-                    if (lane < nh) {
-#pragma unroll
-                        for (int t = 0; t < N_TIP; ++t)
-                            if (c_tip_vert[t] / SK_SEG == seg) {
-                                float* tv = tl + (c_tip_vert[t] % SK_SEG) * (3 * TP);
-                                const float* gj = g_joints + ((size_t)g * 32 + lane) * (NOUTJ * 3) + c_tip_slot[t] * 3;
-                                tv[0] += gj[0]; tv[TP] += gj[1]; tv[2 * TP] += gj[2];
-                            }
-                    }
-                    __syncwarp();
-                }
-                if (seg + 1 < SK_NSEG) prefetch_g(seg + 1);
-                // the stage's previous occupant has been consumed by the tensor core
-                mbar_wait_or_trap(smem_u32(&S.a_empty[as]), aph ^ 1);
-                unsigned char* arow = S.a[as] + ((size_t)(rg * DVG_KG) * 8 + r) * 16;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int blk = 2 * seg + half;
-                    float2 G[3][4], DV[3][4];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) DV[c][m] = make_float2(0.f, 0.f);
-                    if (group_live) {
-                        gather_block(P, tl, blk, G);
-                        const int e1 = P.blk_ptr[blk + 1];
-#pragma unroll 1
-                        for (int e = P.blk_ptr[blk]; e < e1; ++e) {
-                            float A[11], w[SK_BV];
-                            load_w(P, e, w);
-                            const float4* sl = cache_entry(W.bones, CS, P.ent_code[e], lane);
-                            const float4 a0 = sl[0], a1 = sl[1], a2 = sl[2];
-                            A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
-                            A[8] = a2.x; A[9] = a2.y; A[10] = a2.z;
-                            cache_after_entry(W.bones, CS, P, e, bgrp, has_next, next_off, pol.keep);
-                            dv_entry2(A, w, G, DV);
-                        }
-                    }
-                    float dv[SK_BC];                                           // block order: dv[3 j + c]
-#pragma unroll
-                    for (int m = 0; m < 4; ++m)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) { dv[6 * m + c] = DV[c][m].x; dv[6 * m + 3 + c] = DV[c][m].y; }
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        uint32_t hi[4], mid[4];
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const float a = dv[t * 8 + 2 * p], b = dv[t * 8 + 2 * p + 1];
-                            hi[p] = pack_bf16x2(a, b);
-                            const float ah = __uint_as_float(hi[p] << 16), bh = __uint_as_float(hi[p] & 0xffff0000u);
-                            mid[p] = pack_bf16x2(a - ah, b - bh);
-                        }
-                        unsigned char* d = arow + (half * 3 + t) * 128;        // K-group (half * 3 + t) of this row
-                        *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(d + DVG_A_SPLIT_BYTES) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-                    }
-                }
-                fence_proxy_async();                                           // generic-proxy writes -> visible to the tensor core's reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&S.a_full[as]));
-                if (++as == DVG_ASTAGES) { as = 0; aph ^= 1; }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 // split backward sweeps: dbone[g] = sum over the group's units (ascending, touched bones only) of dparts.
@@ -1361,23 +1101,10 @@ int launch_skin_forward(const void* blob, const float* v_posed_t, const float* b
     return cuda_rc();
 }
 
-int launch_skin_backward_dv_gemm(const void* blob, const float* bone_t, const float* g_verts, const float* g_joints, int B,
-                                 float* dfeat_t, cudaStream_t s) {
-    if (B <= 0) return 0;
-    static SmemAttrOnce once;
-    if (int arc = ensure_dyn_smem(once, skin_backward_dv_gemm_kernel, DVG_SMEM)) return arc;
-    const unsigned char* tc = blob_ptr<unsigned char>(blob, blob_layout().total);
-    const int m_tiles = (B + TC_M - 1) / TC_M;
-    skin_backward_dv_gemm_kernel<<<m_tiles < NUM_SMS ? m_tiles : NUM_SMS, DVG_THREADS, DVG_SMEM, s>>>(
-        blob, tc + blend_tc_bw48_offset(), bone_t, g_verts, g_joints, B, m_tiles, dfeat_t);
-    return cuda_rc();
-}
-
 int launch_skin_backward(const void* blob, const float* v_posed_t, const float* bone_t, const float* g_verts,
                          const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, int dbone_hand_minor,
                          float* dparts, cudaStream_t s) {
     if (B <= 0) return 0;
-    const int dv_off = (dv_t == nullptr && dvp == nullptr) ? 1 : 0;      // dv_posed comes from launch_skin_backward_dv_gemm
     static SmemAttrOnce once_a, once_b;
     if (int arc = ensure_dyn_smem(once_a, skin_backward_kernel<false>, SKB_SMEM)) return arc;
     if (int arc = ensure_dyn_smem(once_b, skin_backward_kernel<true>, SKB_SMEM)) return arc;
@@ -1387,13 +1114,13 @@ int launch_skin_backward(const void* blob, const float* v_posed_t, const float* 
         if (dparts == nullptr) return MB_E_NULL;
         const int nunits = ngroups * skin_units_per_group(spu);
         skin_backward_kernel<true><<<nunits < NUM_SMS ? nunits : NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(
-            blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp, dbone, dbone_hand_minor, dparts, spu, dv_off);
+            blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp, dbone, dbone_hand_minor, dparts, spu);
         int rc = cuda_rc();
         if (rc) return rc;
         dbone_reduce_kernel<<<ngroups * NJ, BONE_F * 32, 0, s>>>(blob, dparts, B, spu, dbone, dbone_hand_minor);
     } else {
         skin_backward_kernel<false><<<NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp,
-                                                                          dbone, dbone_hand_minor, nullptr, SK_NSEG, dv_off);
+                                                                          dbone, dbone_hand_minor, nullptr, SK_NSEG);
     }
     return cuda_rc();
 }

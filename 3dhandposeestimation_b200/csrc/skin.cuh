@@ -20,10 +20,6 @@ int launch_skin_forward(const void* blob, const float* v_posed_t, const float* b
 int launch_skin_backward(const void* blob, const float* v_posed_t, const float* bone_t, const float* g_verts,
                          const float* g_joints, int B, float* dv_t, unsigned char* dvp, float* dbone, int dbone_hand_minor,
                          float* dparts, cudaStream_t s);
-// Large batches: dv_posed of 128 hands per CTA goes straight into the A-operand stage of the tcgen05 gradient contraction in
-// shared memory; dfeat_t[groups][160][32] hand-minor.  launch_skin_backward is then called with dv_t == dvp == NULL (role 1 only).
-int launch_skin_backward_dv_gemm(const void* blob, const float* bone_t, const float* g_verts, const float* g_joints, int B,
-                                 float* dfeat_t, cudaStream_t s);
 // layout conversions used by the fp32 anchor mode and the stand-alone mb_lbs_forward
 int launch_rows_to_t(const void* blob, const float* rows, int pitch, int B, float* t, cudaStream_t s);
 int launch_t_to_rows(const void* blob, const float* t, int pitch, int B, float* rows, cudaStream_t s);

@@ -16,16 +16,19 @@
 // shared-memory row as ONE contiguous, sector-aligned 1 536-byte piece per (hand, vertex tile) of
 // verts[B][778][3] in its natural layout — no transposition, no v_posed_t round trip.
 //
-// Roles (384 threads, 1 CTA per SM, persistent over 64-hand tiles):
+// Roles (512 threads, 1 CTA per SM, persistent over 64-hand tiles):
 //   warp 0   basis producer: (tile, plane, K chunk) stages of 16 KB, always L2 hits, 4-stage ring
-//   warp 1   MMA issuer (one thread): blend products of vertex tile t+1 interleaved with the transform chunks of tile t
-//   warp 2   TMEM allocation; producer of the per-hand-tile operands (feature rows 40 KB, bone operand 72 KB) and of
-//            the weight tiles (12 KB per vertex tile, double buffered)
-//   warp 3   store warp: result rows shared -> global as 16-byte vectors, row heads / tails as plain stores
-//   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices), warp / 8 = which two hands of a chunk
-// TMEM (512 columns): two rest-position stages of 3 x 64 columns, two transform stages of 48 columns.
+//   warp 1   MMA issuer (one thread): per vertex tile the 90 blend products, then 16 transform chunks of 4 hands
+//   warp 2   TMEM allocation; producer of the hand tile's feature rows (40 KB) and of the weight tiles (12 KB per
+//            vertex tile, double buffered)
+//   warp 3   converts the hand tile's fp32 bone transforms (48 KB, straight from the pose stage's bone_t) into the
+//            transform products' fp16 x3 B operand in shared memory (72 KB)
+//   warps 12-15  store warps, one per slot of the result-row ring
+//   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices); warps 4-7 take the even chunks, 8-11 the odd ones
+// TMEM (512 columns): one rest-position stage of 3 x 64 columns, six transform stages of 48 columns.
 #include <cuda_fp16.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <vector>
 #include "common.cuh"
@@ -37,14 +40,15 @@
 namespace mb {
 namespace {
 
-constexpr int VS_THREADS = 384;
+constexpr int VS_THREADS = 512;                   // 16 warps: see the role list above
 constexpr int VS_EPI_WARPS = 8;
 constexpr int VS_ASTAGES = 4;
-constexpr int VS_OSTAGES = 3;
+constexpr int VS_OSTAGES = 4;                     // result-row ring: two chunks per epilogue warp set
 constexpr int VS_ROW = 392;                        // floats per staging row: up to 6 carried floats + 384 + slack
 constexpr uint32_t VS_TMEM_COLS = 512;
-constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns per rest-position stage
-constexpr uint32_t VS_T_COL0 = 2 * VS_VP_COLS;     // 384: first transform column
+constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns: the rest positions of a (vertex tile, hand tile), one stage
+constexpr uint32_t VS_T_COL0 = VS_VP_COLS;         // 192: first transform column
+constexpr int VS_TSTAGES = 6;                      // transform stages of 48 columns (three per epilogue warp set): 480 columns in all
 // instruction descriptors: f16 x f16 -> f32, M = 128
 constexpr uint32_t VS_IDESC_BLEND = (1u << 4) | ((uint32_t)(VS_NH >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);                // A, B K-major
 constexpr uint32_t VS_IDESC_T = (1u << 4) | (1u << 16) | ((uint32_t)(VS_TN >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);       // B MN-major
@@ -62,8 +66,8 @@ struct VsShared {
     alignas(8) unsigned long long a_full[VS_ASTAGES], a_empty[VS_ASTAGES];
     unsigned long long w_full[2], w_empty[2];
     unsigned long long feat_full, feat_empty, bones_full, bones_empty;
-    unsigned long long vp_full[2], vp_empty[2];
-    unsigned long long t_full[2], t_empty[2];
+    unsigned long long vp_full, vp_empty;
+    unsigned long long t_full[VS_TSTAGES], t_empty[VS_TSTAGES];
     unsigned long long out_full[VS_OSTAGES], out_empty[VS_OSTAGES];
     uint32_t tmem_base;
 };
@@ -89,153 +93,243 @@ __device__ __forceinline__ int vs_shift(int t, int hl) { return t == 0 ? ((hl & 
 __global__ void __launch_bounds__(VS_THREADS, 1)
 vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ vs_basis,
                      const unsigned char* __restrict__ vs_w, const float4* __restrict__ vs_tmpl,
-                     const unsigned char* __restrict__ featp, const unsigned char* __restrict__ bone16,
+                     const unsigned char* __restrict__ featp, const float* __restrict__ bone_t,
                      int B, int ntiles, int blend_products, int t_products,
                      float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ v_posed_t,
                      float* __restrict__ dbg, int variant) {
     extern __shared__ unsigned char smem_raw[];
     VsShared& S = *reinterpret_cast<VsShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Thread-block cluster (1, 2 or 4 CTAs): the CTAs of a cluster walk DIFFERENT hand tiles in lockstep and share one
+    // basis stream — each loads 1 / csize of every stage and multicasts it to all of them.  [profiles/r2: unicast, the
+    // basis stream alone (1.68 MB per 64-hand tile = 26 KB per hand, every SM reading the same L2 lines) ran the kernel
+    // at ~15 B/clk/SM: 6.7 ms per 2^20 hands with every MMA, store and FMA removed]
+    const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+    const int nclusters = (int)(gridDim.x / csize), cluster_id = (int)(blockIdx.x / csize);
+    const int nrounds = (ntiles + (int)csize - 1) / (int)csize;         // a round = one hand tile per CTA of the cluster
+    // a CTA whose tile of the last round does not exist runs the round on tile `ntiles - 1`'s operands and stores nothing
+#define VS_FOR_EACH_TILE for (int rnd = cluster_id, tile = rnd * (int)csize + (int)crank; rnd < nrounds; rnd += nclusters, tile = rnd * (int)csize + (int)crank)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < VS_ASTAGES; ++s) { mbar_init(smem_u32(&S.a_full[s]), 1); mbar_init(smem_u32(&S.a_empty[s]), 1); }
+        for (int s = 0; s < VS_ASTAGES; ++s) { mbar_init(smem_u32(&S.a_full[s]), 1); mbar_init(smem_u32(&S.a_empty[s]), csize); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&S.w_full[s]), 1); mbar_init(smem_u32(&S.w_empty[s]), 1);
-            mbar_init(smem_u32(&S.vp_full[s]), 1); mbar_init(smem_u32(&S.vp_empty[s]), VS_EPI_WARPS);
-            mbar_init(smem_u32(&S.t_full[s]), 1); mbar_init(smem_u32(&S.t_empty[s]), VS_EPI_WARPS);
         }
+        mbar_init(smem_u32(&S.vp_full), 1); mbar_init(smem_u32(&S.vp_empty), VS_EPI_WARPS);
+        for (int s = 0; s < VS_TSTAGES; ++s) { mbar_init(smem_u32(&S.t_full[s]), 1); mbar_init(smem_u32(&S.t_empty[s]), VS_EPI_WARPS / 2); }
         mbar_init(smem_u32(&S.feat_full), 1); mbar_init(smem_u32(&S.feat_empty), 1);
         mbar_init(smem_u32(&S.bones_full), 1); mbar_init(smem_u32(&S.bones_empty), 1);
-        for (int s = 0; s < VS_OSTAGES; ++s) { mbar_init(smem_u32(&S.out_full[s]), VS_EPI_WARPS); mbar_init(smem_u32(&S.out_empty[s]), 1); }
+        for (int s = 0; s < VS_OSTAGES; ++s) { mbar_init(smem_u32(&S.out_full[s]), VS_EPI_WARPS / 2); mbar_init(smem_u32(&S.out_empty[s]), 1); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(&S.tmem_base), VS_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                              // every CTA's barriers exist before a peer signals them
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== basis producer: the same 105-stage stream for every hand tile, kept in L2 =====
             const uint64_t keep = l2_policy_evict_last();
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const uint32_t slice = VS_A_STAGE_BYTES / csize;           // this CTA's share of every stage
+            VS_FOR_EACH_TILE {
+                (void)tile;
+                if (variant & 0x8000) continue;                        // experiment: no basis stream
                 for (int i = 0; i < VS_NT * VS_STAGES_PER_TILE; ++i) {
-                    vs_wait(&S.a_empty[stage], phase ^ 1);
+                    vs_wait(&S.a_empty[stage], phase ^ 1);             // every CTA of the cluster has consumed the slot
                     mbar_expect_tx(smem_u32(&S.a_full[stage]), VS_A_STAGE_BYTES);
-                    bulk_g2s_hint(smem_u32(S.a[stage]), vs_basis + (size_t)i * VS_A_STAGE_BYTES, VS_A_STAGE_BYTES,
-                                  smem_u32(&S.a_full[stage]), keep);
+                    if (csize == 1)
+                        bulk_g2s_hint(smem_u32(S.a[stage]), vs_basis + (size_t)i * VS_A_STAGE_BYTES, VS_A_STAGE_BYTES,
+                                      smem_u32(&S.a_full[stage]), keep);
+                    else
+                        bulk_g2s_multicast(smem_u32(S.a[stage]) + crank * slice, vs_basis + (size_t)i * VS_A_STAGE_BYTES + crank * slice, slice,
+                                           smem_u32(&S.a_full[stage]), cmask, keep);
                     if (++stage == VS_ASTAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== per-hand-tile operands (features, bones) and the weight tiles =====
             const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
             uint32_t it = 0, gw = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            VS_FOR_EACH_TILE {
+                const int ltile = tile < ntiles ? tile : ntiles - 1;
                 vs_wait(&S.feat_empty, (it & 1) ^ 1);
                 mbar_expect_tx(smem_u32(&S.feat_full), TC_K_CHUNKS * 2 * 4096);
-                const unsigned char* fsrc = featp + (size_t)(tile >> 1) * TC_A_TILE_BYTES + (size_t)(tile & 1) * 4096;
+                const unsigned char* fsrc = featp + (size_t)(ltile >> 1) * TC_A_TILE_BYTES + (size_t)(ltile & 1) * 4096;
                 for (int c = 0; c < TC_K_CHUNKS; ++c)
                     for (int sp = 0; sp < 2; ++sp)
                         bulk_g2s_hint(smem_u32(S.feat[c][sp]), fsrc + (size_t)c * TC_A_STAGE_BYTES + (size_t)sp * TC_A_BLOCK_BYTES, 4096,
                                       smem_u32(&S.feat_full), once);
-                vs_wait(&S.bones_empty, (it & 1) ^ 1);
-                mbar_expect_tx(smem_u32(&S.bones_full), VS_BONE_TILE_BYTES);
-                const unsigned char* bsrc = bone16 + (size_t)tile * VS_BONE_TILE_BYTES;
-                for (int q = 0; q < 4; ++q)
-                    bulk_g2s_hint(smem_u32(&S.bones[0][0][0]) + q * (VS_BONE_TILE_BYTES / 4), bsrc + (size_t)q * (VS_BONE_TILE_BYTES / 4),
-                                  VS_BONE_TILE_BYTES / 4, smem_u32(&S.bones_full), once);
                 for (int t = 0; t < VS_NT; ++t, ++gw) {
                     vs_wait(&S.w_empty[gw & 1], ((gw >> 1) & 1) ^ 1);
                     mbar_expect_tx(smem_u32(&S.w_full[gw & 1]), VS_W_TILE_BYTES);
                     bulk_g2s_hint(smem_u32(S.w[gw & 1]), vs_w + (size_t)t * VS_W_TILE_BYTES, VS_W_TILE_BYTES, smem_u32(&S.w_full[gw & 1]), keep);
                 }
+                ++it;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== MMA issuer =====
-            uint32_t a_stage = 0, a_phase = 0, gt = 0, tc = 0, it = 0;
-            const uint64_t a_base = umma_desc(smem_u32(S.a[0]), TC_LBO, TC_SBO);
-            const uint64_t f_base = umma_desc(smem_u32(S.feat[0][0]), TC_LBO, TC_SBO);
-            // weights: K-major, K = 16 bones = 2 core matrices 128 B apart, 8-row groups 256 B apart
-            const uint64_t w_base = umma_desc(smem_u32(S.w[0]), 128, 256);
+            // [profiles/r2: issued by `lane == 0` the compiler wrapped every tcgen05.mma in a divergence "waterfall" (ELECT /
+            // R2UR.BROADCAST / BRA.U.ANY) and rebuilt 64-bit descriptors per instruction — ~350 scalar instructions per
+            // 4-hand chunk at IPC ~0.25: the issuing THREAD, not the tensor pipe (14 % busy), paced the kernel at ~1 500 clk
+            // per chunk.  Now: elect.sync, 32-bit descriptor halves (only the low word changes), the chunk loop unrolled so
+            // that plane / K-chunk / accumulate flags are constants.]
+            uint32_t a_stage = 0, a_phase = 0, gt = 0, it = 0;
+            // K-major operands: LBO 128 B (between the K core matrices of one MMA), SBO between 8-row groups
+            const uint32_t hi_k512 = desc_hi(TC_SBO), hi_k256 = desc_hi(256);
+            const uint32_t a_lo0 = desc_lo(smem_u32(S.a[0]), TC_LBO), f_lo0 = desc_lo(smem_u32(S.feat[0][0]), TC_LBO);
+            const uint32_t w_lo0 = desc_lo(smem_u32(S.w[0]), 128);
             // bones: MN-major, n-groups 256 B apart (SBO), k-groups 128 B apart (LBO); variant 1 swaps the two fields
-            const uint64_t b_base = (variant & 1) ? umma_desc(smem_u32(&S.bones[0][0][0]), 256, 128)
-                                                  : umma_desc(smem_u32(&S.bones[0][0][0]), 128, 256);
-            // one (plane, K chunk) stage of the blend products of vertex-tile counter g
-            auto blend_stage = [&](uint32_t g, int k) {
-                const int p = k / TC_K_CHUNKS, c = k - p * TC_K_CHUNKS;
-                if (k == 0) { vs_wait(&S.vp_empty[g & 1], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
+            const uint32_t b_lo0 = desc_lo(smem_u32(&S.bones[0][0][0]), (variant & 1) ? 256 : 128);
+            const uint32_t hi_b = desc_hi((variant & 1) ? 128 : 256);
+            // one (plane p, K chunk c) stage of the blend products
+            auto blend_stage = [&](int p, int c) {
+                if (variant & 0x8000) return;                           // experiment: no basis stream
                 vs_wait(&S.a_full[a_stage], a_phase);
                 tc_fence_after();
-                const uint32_t d = tmem + (g & 1) * VS_VP_COLS + p * VS_NH;
-                const uint64_t a_st = a_base + (uint64_t)((a_stage * VS_A_STAGE_BYTES) >> 4);
+                const uint32_t d = tmem + p * VS_NH;
+                const uint32_t a_st = a_lo0 + ((a_stage * VS_A_STAGE_BYTES) >> 4);
+                const uint32_t f_st = f_lo0 + ((c * 2 * 4096) >> 4);
 #pragma unroll
                 for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
-                    const uint64_t a_hi = a_st + (uint64_t)((j * 2 * (int)TC_LBO) >> 4);
-                    const uint64_t a_lo = a_hi + (uint64_t)((VS_A_STAGE_BYTES / 2) >> 4);
-                    const uint64_t b_hi = f_base + (uint64_t)((c * 2 * 4096 + j * 2 * (int)TC_LBO) >> 4);
-                    const uint64_t b_lo = b_hi + (uint64_t)(4096 >> 4);
-                    umma_f16(d, a_hi, b_hi, VS_IDESC_BLEND, (c | j) ? 1u : 0u);
+                    const uint32_t a_hi = a_st + ((j * 2 * (int)TC_LBO) >> 4), a_lo = a_hi + ((VS_A_STAGE_BYTES / 2) >> 4);
+                    const uint32_t b_hi = f_st + ((j * 2 * (int)TC_LBO) >> 4), b_lo = b_hi + (4096 >> 4);
+                    if (variant & 0x400) continue;                                  // experiment: no blend products
+                    if (c == 0 && j == 0) umma_f16_lohi<false>(d, a_hi, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
+                    else umma_f16_lohi<true>(d, a_hi, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
                     if (blend_products == 3) {
-                        umma_f16(d, a_lo, b_hi, VS_IDESC_BLEND, 1);
-                        umma_f16(d, a_hi, b_lo, VS_IDESC_BLEND, 1);
+                        umma_f16_lohi<true>(d, a_lo, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
+                        umma_f16_lohi<true>(d, a_hi, hi_k512, b_lo, hi_k512, VS_IDESC_BLEND);
                     }
                 }
-                tc_commit(smem_u32(&S.a_empty[a_stage]));
+                if (csize == 1) tc_commit(smem_u32(&S.a_empty[a_stage]));
+                else tc_commit_multicast(smem_u32(&S.a_empty[a_stage]), cmask);      // every producer of the cluster refills this slot
                 if (++a_stage == VS_ASTAGES) { a_stage = 0; a_phase ^= 1; }
-                if (k == VS_STAGES_PER_TILE - 1) tc_commit(smem_u32(&S.vp_full[g & 1]));
             };
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            uint32_t ts = 0, tph = 0;                                   // transform stage ring: chunk counter mod 6, its phase
+            VS_FOR_EACH_TILE {
+                (void)tile;
                 vs_wait(&S.feat_full, it & 1);
                 tc_fence_after();
-                for (int k = 0; k < VS_STAGES_PER_TILE; ++k) blend_stage(gt, k);
-                vs_wait(&S.bones_full, it & 1);
-                tc_fence_after();
+#pragma unroll 1
                 for (int t = 0; t < VS_NT; ++t, ++gt) {
+                    // ---- rest positions of vertex tile t: 3 planes x 5 K chunks into the one vp stage, once the epilogue has
+                    // drained the previous tile's
+                    vs_wait(&S.vp_empty, (gt & 1) ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < VS_STAGES_PER_TILE; ++k) blend_stage(k / TC_K_CHUNKS, k % TC_K_CHUNKS);
+                    tc_commit(smem_u32(&S.vp_full));
+                    if (t == VS_NT - 1) tc_commit(smem_u32(&S.feat_empty));
+                    if (t == 0) { vs_wait(&S.bones_full, it & 1); tc_fence_after(); }
                     vs_wait(&S.w_full[gt & 1], (gt >> 1) & 1);
                     tc_fence_after();
-                    const uint64_t w1 = w_base + (uint64_t)(((gt & 1) * VS_W_TILE_BYTES) >> 4);
-                    const uint64_t w2 = w1 + (uint64_t)(4096 >> 4), w3 = w2 + (uint64_t)(4096 >> 4);
-                    for (int ch = 0; ch < VS_NCH; ++ch, ++tc) {
-                        const uint32_t ts = tc & 1;
-                        vs_wait(&S.t_empty[ts], ((tc >> 1) & 1) ^ 1);
+                    const uint32_t w1 = w_lo0 + (((gt & 1) * VS_W_TILE_BYTES) >> 4), w2 = w1 + (4096 >> 4);
+                    // ---- blended transforms, 4 hands per chunk, up to six chunks ahead of the epilogue
+#pragma unroll 1
+                    for (int ch = 0; ch < VS_NCH; ++ch) {
+                        vs_wait(&S.t_empty[ts], tph ^ 1);
                         tc_fence_after();
                         const uint32_t d = tmem + VS_T_COL0 + ts * VS_TN;
-                        const uint64_t a1 = b_base + (uint64_t)((ch * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES) >> 4);
-                        const uint64_t a2 = a1 + (uint64_t)(VS_BONE_CHUNK_BYTES >> 4), a3 = a2 + (uint64_t)(VS_BONE_CHUNK_BYTES >> 4);
-                        umma_f16(d, w1, a1, VS_IDESC_T, 0);
-                        if (t_products >= 3) { umma_f16(d, w1, a2, VS_IDESC_T, 1); umma_f16(d, w2, a1, VS_IDESC_T, 1); }
-                        if (t_products >= 4) umma_f16(d, w1, a3, VS_IDESC_T, 1);
-                        if (t_products >= 5) umma_f16(d, w2, a2, VS_IDESC_T, 1);
-                        if (t_products >= 6) umma_f16(d, w3, a1, VS_IDESC_T, 1);
+                        const uint32_t a1 = b_lo0 + ((ch * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES) >> 4);
+                        const uint32_t a2 = a1 + (VS_BONE_CHUNK_BYTES >> 4), a3 = a2 + (VS_BONE_CHUNK_BYTES >> 4);
+                        // smallest products first, w1 a1 last: the tensor core TRUNCATES its fp32 accumulator at the running
+                        // sum's magnitude on every MMA; with the corrections accumulated among themselves first, only the
+                        // last addition rounds at full magnitude
+                        if (!(variant & 0x800)) {                       // 0x800: experiment, no transform products
+                            if (t_products >= 4) {
+                                umma_f16_lohi<false>(d, w1, hi_k256, a3, hi_b, VS_IDESC_T);
+                                if (t_products >= 5) umma_f16_lohi<true>(d, w2, hi_k256, a2, hi_b, VS_IDESC_T);
+                                umma_f16_lohi<true>(d, w1, hi_k256, a2, hi_b, VS_IDESC_T);
+                                umma_f16_lohi<true>(d, w2, hi_k256, a1, hi_b, VS_IDESC_T);
+                                umma_f16_lohi<true>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
+                            } else if (t_products == 3) {
+                                umma_f16_lohi<false>(d, w1, hi_k256, a2, hi_b, VS_IDESC_T);
+                                umma_f16_lohi<true>(d, w2, hi_k256, a1, hi_b, VS_IDESC_T);
+                                umma_f16_lohi<true>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
+                            } else {
+                                umma_f16_lohi<false>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
+                            }
+                        }
                         tc_commit(smem_u32(&S.t_full[ts]));
-                        // the next vertex tile's blend products, one stage per chunk (15 stages over 16 chunks)
-                        if (t + 1 < VS_NT && ch < VS_STAGES_PER_TILE) blend_stage(gt + 1, ch);
+                        if (++ts == VS_TSTAGES) { ts = 0; tph ^= 1; }
                     }
                     tc_commit(smem_u32(&S.w_empty[gt & 1]));
-                    if (t == VS_NT - 2) tc_commit(smem_u32(&S.feat_empty));        // blend products of the last vertex tile are issued
                 }
                 tc_commit(smem_u32(&S.bones_empty));
+                ++it;
             }
         }
     } else if (warp == 3) {
-        // ===== store warp: result rows shared -> global as 16-byte vectors (every piece starts on a 32-byte boundary) =====
-        // [profiles/r2: as bulk (TMA) stores with a 3-deep ring the kernel ran at the latency of cp.async.bulk.wait_group.read —
-        // ~1 900 clk per 4-hand chunk, tensor pipe 15 % busy; a plain LDS.128 -> STG.128 copy frees the row as soon as it is in
-        // registers]
-        uint32_t oc = 0, gt = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ===== bone operand: fp32 transforms bone_t[group][bone][hand % 32][12] -> fp16 x3 MN-major core matrices =====
+        // The 12 elements of 4 consecutive hands of one bone are 48 contiguous floats = one K row (k = bone) of a chunk's
+        // B operand, n = (hand % 4) * 12 + element: a lane converts 8 of them (one 16-byte n-group) into the three splits
+        // a = a1 + a2 + a3 of 2^4 a.  [profiles/r2: written by the pose kernel as 96 scattered 16 / 8-byte stores per
+        // hand it cost that kernel +1.6 ms per 2^20 hands and 2.3 KB per hand of HBM traffic]
+        const long long ngroups = ((long long)B + 31) >> 5;
+        uint32_t it = 0;
+        VS_FOR_EACH_TILE {
+            vs_wait(&S.bones_empty, (it & 1) ^ 1);
+#pragma unroll 1
+            for (int ch = 0; ch < VS_NCH; ++ch) {
+                const long long group = (long long)tile * 2 + (ch >> 3);
+                const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + 48 * (ch & 7);
+                float4 v[3][2];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {                          // 96 (bone, n-group) items per chunk: three per lane
+                    const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
+                    const float4* p = reinterpret_cast<const float4*>(src0 + (size_t)k * (BONE_F * 32) + 8 * g);
+                    if (group < ngroups) { v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); }
+                    else { v[r][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[r][1] = v[r][0]; }
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
+                    float x[8] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w, v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] *= (float)(1 << VS_BONE_SCALE_LOG2);
+                    unsigned char* dst = &S.bones[ch][0][0] + g * 256 + (k >> 3) * 128 + (k & 7) * 16;
+#pragma unroll
+                    for (int sp = 0; sp < VS_BONE_SPLITS; ++sp) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __half lo = __float2half_rn(x[2 * e]), hi = __float2half_rn(x[2 * e + 1]);
+                            x[2 * e] -= __half2float(lo);
+                            x[2 * e + 1] -= __half2float(hi);
+                            pk[e] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+                        }
+                        *reinterpret_cast<uint4*>(dst + sp * VS_BONE_CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+            fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.bones_full));
+            ++it;
+        }
+    } else if (warp >= 12) {
+        // ===== store warps: result rows shared -> global as 16-byte vectors (every piece starts on a 32-byte boundary) =====
+        // [profiles/r2: as bulk (TMA) stores the kernel ran at the latency of cp.async.bulk.wait_group.read; as ONE warp copying
+        // every chunk in order the warp's own ~350 clk per chunk (wake-up, LDS, arrive — serial) capped the kernel: removing the
+        // ring took 0.74 of 1.83 ms off the skeleton.  Now four warps, each owning one slot of the ring: chunk oc -> warp oc % 4.]
+        const int sw = warp - 12;
+        uint32_t gt = 0;
+        VS_FOR_EACH_TILE {
             const long long hand0 = (long long)tile * VS_NH;
             for (int t = 0; t < VS_NT; ++t, ++gt) {
-                for (int ch = 0; ch < VS_NCH; ++ch, ++oc) {
-                    const uint32_t ob = oc % VS_OSTAGES;
-                    vs_wait(&S.out_full[ob], (oc / VS_OSTAGES) & 1);
+                for (int ch = sw; ch < VS_NCH; ch += VS_OSTAGES) {
+                    const uint32_t ob = sw;                               // chunk counter gt * 16 + ch = sw (mod 4)
+                    if (variant & 0x2000) continue;                     // experiment: no result ring
+                    vs_wait(&S.out_full[ob], (ch >> 2) & 1);            // the slot's use count = 4 gt + ch / 4
                     // carried floats of the previous vertex tile go in front of the results
                     if (t >= 1) {
                         const int hl = lane >> 3, i = lane & 7;
@@ -256,7 +350,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
 #pragma unroll
                         for (int hl = 0; hl < VS_HC; ++hl) {
                             const long long hand = hand0 + ch * VS_HC + hl;
-                            if (hand < B) {
+                            if (hand < B && !(variant & 0x100)) {                     // 0x100: experiment, no global stores
                                 float4* dst = reinterpret_cast<float4*>(verts + (size_t)hand * NVC + 3 * VS_M * t - vs_d(hl));
 #pragma unroll
                                 for (int k = 0; k < 3; ++k) __stcs(dst + lane + 32 * k, v[hl][k]);
@@ -289,15 +383,19 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 }
             }
         }
-    } else {
-        // ===== epilogue: thread = vertex =====
-        const int q = warp & 3, half = (warp - 4) >> 2;
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = vertex; warps 4-7 take the even chunks of a tile, warps 8-11 the odd ones =====
+        // [profiles/r2: with all eight warps on every chunk (two hands each) a chunk took ~1 500 clk — three mbarrier round
+        // trips, five TMEM loads and their wait per 2 hands of work, serial in every warp — and the tensor pipe sat at 14 %.
+        // Now a warp does all four hands of every other chunk: half the synchronisation per hand, and the other set's
+        // round hides it.]
+        const int q = warp & 3, set = (warp - 4) >> 2;
         const int vl = q * 32 + lane;                                  // vertex inside the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const float osv = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
         const float ost = exp2f(-(float)(VS_W_SCALE_LOG2 + VS_BONE_SCALE_LOG2));
-        uint32_t gt = 0, tc = 0, oc = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t gt = 0, ts = set, tph = 0;                            // this set's next chunk: transform stage (chunk counter mod 6), phase
+        VS_FOR_EACH_TILE {
             const long long hand0 = (long long)tile * VS_NH;
             for (int t = 0; t < VS_NT; ++t, ++gt) {
                 const int vtx = t * VS_M + vl;
@@ -306,18 +404,19 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 int tipslot = -1;
 #pragma unroll
                 for (int i = 0; i < 5; ++i) if (vtx == c_vs_tip_vert[i]) tipslot = c_vs_tip_slot[i];
-                const uint32_t vp_addr = tmem + lane_addr + (gt & 1) * VS_VP_COLS;
-                vs_wait(&S.vp_full[gt & 1], (gt >> 1) & 1);
+                const bool carries = valid && t + 1 < VS_NT && vl >= VS_M - 2;
+                const uint32_t vp_addr = tmem + lane_addr;
+                vs_wait(&S.vp_full, gt & 1);
                 tc_fence_after();
                 if (v_posed_t != nullptr) {
                     // rest-pose scratch for the skinning backward: v_posed_t[group][3 pos + p][32 hands], this warp's 32 hands
-                    const long long group = (long long)tile * 2 + half;
+                    const long long group = (long long)tile * 2 + set;
                     const int pos3 = __float_as_int(tm.w);
                     const bool live = valid && pos3 >= 0 && group * 32 < B;
 #pragma unroll 1
                     for (int p = 0; p < 3; ++p) {
                         uint32_t r[32];
-                        tmem_ld32_nowait(vp_addr + p * VS_NH + half * 32, r);
+                        tmem_ld32_nowait(vp_addr + p * VS_NH + set * 32, r);
                         tmem_ld_wait();
                         if (live) {
                             const float tp = p == 0 ? tm.x : (p == 1 ? tm.y : tm.z);
@@ -329,60 +428,72 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                         }
                     }
                 }
-                for (int ch = 0; ch < VS_NCH; ++ch, ++tc, ++oc) {
-                    const uint32_t ts = tc & 1;
-                    vs_wait(&S.t_full[ts], (tc >> 1) & 1);
+#pragma unroll 1
+                for (int ch = set; ch < VS_NCH; ch += 2) {
+                    vs_wait(&S.t_full[ts], tph);
                     tc_fence_after();
-                    uint32_t T[24], X[2], Y[2], Z[2];
-                    const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + ts * VS_TN + half * 24;
-                    tmem_ld16_nowait(t_addr, T);
-                    tmem_ld8_nowait(t_addr + 16, T + 16);
-                    const uint32_t x_addr = vp_addr + ch * VS_HC + half * 2;
-                    tmem_ld2_nowait(x_addr, X);
-                    tmem_ld2_nowait(x_addr + VS_NH, Y);
-                    tmem_ld2_nowait(x_addr + 2 * VS_NH, Z);
-                    tmem_ld_wait();
+                    const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + ts * VS_TN;
+                    uint32_t T[VS_TN], X[VS_HC], Y[VS_HC], Z[VS_HC];
+                    const uint32_t x_addr = vp_addr + ch * VS_HC;
+                    if (!(variant & 0x1000)) {                          // 0x1000: experiment, no TMEM loads
+                        tmem_ld32_nowait(t_addr, T);
+                        tmem_ld16_nowait(t_addr + 32, T + 32);
+                        tmem_ld4_nowait(x_addr, X);
+                        tmem_ld4_nowait(x_addr + VS_NH, Y);
+                        tmem_ld4_nowait(x_addr + 2 * VS_NH, Z);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VS_TN; ++i) T[i] = i;
+#pragma unroll
+                        for (int i = 0; i < VS_HC; ++i) X[i] = Y[i] = Z[i] = i;
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[ts]));
+                    ts += 2;
+                    if (ts >= VS_TSTAGES) { ts -= VS_TSTAGES; tph ^= 1; }
+                    // result rows of chunk oc = (chunks so far) -> ring slot; the set's slots alternate {set, set + 2}
+                    const uint32_t oc = gt * VS_NCH + ch;
                     const uint32_t ob = oc % VS_OSTAGES;
+                    if (variant & 0x2000) continue;                     // 0x2000: experiment, no result ring
                     vs_wait(&S.out_empty[ob], ((oc / VS_OSTAGES) & 1) ^ 1);
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int hl = half * 2 + hh;
-                        const float x = fmaf(__uint_as_float(X[hh]), osv, tm.x);
-                        const float y = fmaf(__uint_as_float(Y[hh]), osv, tm.y);
-                        const float z = fmaf(__uint_as_float(Z[hh]), osv, tm.z);
+                    for (int hl = 0; hl < VS_HC; ++hl) {
+                        if (variant & 0x200) break;                                 // 0x200: experiment, handshakes only
+                        const float x = fmaf(__uint_as_float(X[hl]), osv, tm.x);
+                        const float y = fmaf(__uint_as_float(Y[hl]), osv, tm.y);
+                        const float z = fmaf(__uint_as_float(Z[hl]), osv, tm.z);
                         float o[3];
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
-                            const float* Ti = reinterpret_cast<const float*>(T) + hh * 12 + 4 * i;
+                            const float* Ti = reinterpret_cast<const float*>(T) + hl * 12 + 4 * i;
                             o[i] = ost * fmaf(Ti[0], x, fmaf(Ti[1], y, fmaf(Ti[2], z, Ti[3])));
                         }
                         if (dbg != nullptr && tile == 0 && t == 0 && ch == 0) {
                             float* dd = dbg + ((size_t)hl * VS_M + vl) * 16;
 #pragma unroll
-                            for (int i = 0; i < 12; ++i) dd[i] = ost * __uint_as_float(T[hh * 12 + i]);
+                            for (int i = 0; i < 12; ++i) dd[i] = ost * __uint_as_float(T[hl * 12 + i]);
                             dd[12] = x; dd[13] = y; dd[14] = z; dd[15] = 0.f;
                         }
                         if (valid) {
-                            const int d = vs_d(hl);
                             float* row = S.out[ob][hl] + vs_shift(t, hl) + 3 * vl;
                             row[0] = o[0]; row[1] = o[1]; row[2] = o[2];
-                            if (t + 1 < VS_NT && vl >= VS_M - 2) {
-                                // the last d floats of this tile's piece open the next tile's piece
+                        }
+                        if (carries) {
+                            // the last d floats of this tile's piece open the next tile's piece
+                            const int d = vs_d(hl);
 #pragma unroll
-                                for (int i = 0; i < 3; ++i) {
-                                    const int j = 3 * vl + i - (3 * VS_M - d);
-                                    if (j >= 0) S.carry[(gt + 1) & 1][ch * VS_HC + hl][j] = o[i];
-                                }
+                            for (int i = 0; i < 3; ++i) {
+                                const int j = 3 * vl + i - (3 * VS_M - d);
+                                if (j >= 0) S.carry[(gt + 1) & 1][ch * VS_HC + hl][j] = o[i];
                             }
-                            if (tipslot >= 0) {
-                                const long long hand = hand0 + ch * VS_HC + hl;
-                                if (hand < B) {
-                                    float* jo = joints + (size_t)hand * (NOUTJ * 3) + tipslot * 3;
-                                    jo[0] = o[0]; jo[1] = o[1]; jo[2] = o[2];
-                                }
+                        }
+                        if (tipslot >= 0 && valid) {
+                            const long long hand = hand0 + ch * VS_HC + hl;
+                            if (hand < B) {
+                                float* jo = joints + (size_t)hand * (NOUTJ * 3) + tipslot * 3;
+                                jo[0] = o[0]; jo[1] = o[1]; jo[2] = o[2];
                             }
                         }
                     }
@@ -391,12 +502,14 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&S.vp_empty[gt & 1]));
+                if (lane == 0) mbar_arrive(smem_u32(&S.vp_empty));
             }
         }
     }
+#undef VS_FOR_EACH_TILE
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                              // no CTA leaves while a peer may still signal its barriers
     if (warp == 2) tmem_dealloc(tmem, VS_TMEM_COLS);
 }
 
@@ -461,7 +574,7 @@ void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, 
     }
 }
 
-int launch_vskin_forward(const void* blob, const unsigned char* featp, const unsigned char* bone16, int B, int mode,
+int launch_vskin_forward(const void* blob, const unsigned char* featp, const float* bone_t, int B, int mode,
                          float* verts, float* joints, float* v_posed_t, float* dbg, int variant, cudaStream_t s) {
     if (B <= 0) return 0;
     static SmemAttrOnce once;
@@ -472,11 +585,39 @@ int launch_vskin_forward(const void* blob, const unsigned char* featp, const uns
     const unsigned char* vs = tc + blend_tc_blob_bytes();
     const VsBlobLayout V = vs_blob_layout();
     const int ntiles = (B + VS_NH - 1) / VS_NH;
+    if (const char* ev = getenv("MANO_B200_VSKIN_VARIANT")) variant |= (int)strtol(ev, nullptr, 0);   // experiments (profiles/r2)
     int t_products = (variant >> 4) & 7;
     if (t_products == 0) t_products = 4;
-    vskin_forward_kernel<<<ntiles < NUM_SMS ? ntiles : NUM_SMS, VS_THREADS, smem, s>>>(
-        reinterpret_cast<const TcBlobHeader*>(tc), vs + V.basis, vs + V.w, reinterpret_cast<const float4*>(vs + V.tmpl), featp, bone16,
-        B, ntiles, mode == MB_MODE_F16X3 ? 3 : 1, t_products, verts, joints, v_posed_t, dbg, variant);
+    // cluster size 1, 2 (default) or 4: the CTAs of a cluster share one multicast basis stream
+    int csize = 2;
+    if (const char* ev = getenv("MANO_B200_VSKIN_CLUSTER")) csize = atoi(ev);
+    if (csize != 1 && csize != 2 && csize != 4) csize = 2;
+    while (csize > 1 && ntiles < csize) csize >>= 1;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(VS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = NUM_SMS / csize;
+    if (csize > 1) {                                                   // clusters that can be co-resident (GPC sizes strand a few SMs at 4)
+        cfg.gridDim = dim3(NUM_SMS / csize * csize);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, vskin_forward_kernel, &cfg) == cudaSuccess && n > 0 && n < max_clusters) max_clusters = n;
+    }
+    const int rounds = (ntiles + csize - 1) / csize;
+    cfg.gridDim = dim3((unsigned)((rounds < max_clusters ? rounds : max_clusters) * csize));
+    const TcBlobHeader* hdr = reinterpret_cast<const TcBlobHeader*>(tc);
+    const unsigned char* basis_p = vs + V.basis;
+    const unsigned char* w_p = vs + V.w;
+    const float4* tmpl_p = reinterpret_cast<const float4*>(vs + V.tmpl);
+    const int bp = mode == MB_MODE_F16X3 ? 3 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, vskin_forward_kernel, hdr, basis_p, w_p, tmpl_p, featp, bone_t, B, ntiles, bp, t_products,
+                                       verts, joints, v_posed_t, dbg, variant);
+    if (e != cudaSuccess) return (int)e;
     return cuda_rc();
 }
 
