@@ -18,14 +18,14 @@
 //
 // Roles (512 threads, 1 CTA per SM, persistent over 64-hand tiles):
 //   warp 0   basis producer: (tile, plane, K chunk) stages of 16 KB, always L2 hits, 4-stage ring
-//   warp 1   MMA issuer (one thread): per vertex tile the 90 blend products, then 16 transform chunks of 4 hands
+//   warp 1   MMA issuer (one thread): blend products of vertex tile t+1 interleaved with the transform chunks of tile t
 //   warp 2   TMEM allocation; producer of the hand tile's feature rows (40 KB) and of the weight tiles (12 KB per
 //            vertex tile, double buffered)
 //   warp 3   converts the hand tile's fp32 bone transforms (48 KB, straight from the pose stage's bone_t) into the
 //            transform products' fp16 x3 B operand in shared memory (72 KB)
 //   warps 12-15  store warps, one per slot of the result-row ring
 //   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices); warps 4-7 take the even chunks, 8-11 the odd ones
-// TMEM (512 columns): one rest-position stage of 3 x 64 columns, six transform stages of 48 columns.
+// TMEM (512 columns): two rest-position stages of 3 x 64 columns, two transform stages of 48 columns.
 #include <cuda_fp16.h>
 #include <string.h>
 #include <stdlib.h>
@@ -46,9 +46,9 @@ constexpr int VS_ASTAGES = 4;
 constexpr int VS_OSTAGES = 4;                     // result-row ring: two chunks per epilogue warp set
 constexpr int VS_ROW = 392;                        // floats per staging row: up to 6 carried floats + 384 + slack
 constexpr uint32_t VS_TMEM_COLS = 512;
-constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns: the rest positions of a (vertex tile, hand tile), one stage
-constexpr uint32_t VS_T_COL0 = VS_VP_COLS;         // 192: first transform column
-constexpr int VS_TSTAGES = 6;                      // transform stages of 48 columns (three per epilogue warp set): 480 columns in all
+constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns per rest-position stage (two stages)
+constexpr uint32_t VS_T_COL0 = 2 * VS_VP_COLS;     // 384: first transform column
+constexpr int VS_TSTAGES = 2;                      // transform stages of 48 columns, one per epilogue warp set: 480 columns in all
 // instruction descriptors: f16 x f16 -> f32, M = 128
 constexpr uint32_t VS_IDESC_BLEND = (1u << 4) | ((uint32_t)(VS_NH >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);                // A, B K-major
 constexpr uint32_t VS_IDESC_T = (1u << 4) | (1u << 16) | ((uint32_t)(VS_TN >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);       // B MN-major
@@ -66,7 +66,7 @@ struct VsShared {
     alignas(8) unsigned long long a_full[VS_ASTAGES], a_empty[VS_ASTAGES];
     unsigned long long w_full[2], w_empty[2];
     unsigned long long feat_full, feat_empty, bones_full, bones_empty;
-    unsigned long long vp_full, vp_empty;
+    unsigned long long vp_full[2], vp_empty[2];
     unsigned long long t_full[VS_TSTAGES], t_empty[VS_TSTAGES];
     unsigned long long out_full[VS_OSTAGES], out_empty[VS_OSTAGES];
     uint32_t tmem_base;
@@ -116,7 +116,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&S.w_full[s]), 1); mbar_init(smem_u32(&S.w_empty[s]), 1);
         }
-        mbar_init(smem_u32(&S.vp_full), 1); mbar_init(smem_u32(&S.vp_empty), VS_EPI_WARPS);
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&S.vp_full[s]), 1); mbar_init(smem_u32(&S.vp_empty[s]), VS_EPI_WARPS); }
         for (int s = 0; s < VS_TSTAGES; ++s) { mbar_init(smem_u32(&S.t_full[s]), 1); mbar_init(smem_u32(&S.t_empty[s]), VS_EPI_WARPS / 2); }
         mbar_init(smem_u32(&S.feat_full), 1); mbar_init(smem_u32(&S.feat_empty), 1);
         mbar_init(smem_u32(&S.bones_full), 1); mbar_init(smem_u32(&S.bones_empty), 1);
@@ -190,12 +190,16 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
             // bones: MN-major, n-groups 256 B apart (SBO), k-groups 128 B apart (LBO); variant 1 swaps the two fields
             const uint32_t b_lo0 = desc_lo(smem_u32(&S.bones[0][0][0]), (variant & 1) ? 256 : 128);
             const uint32_t hi_b = desc_hi((variant & 1) ? 128 : 256);
-            // one (plane p, K chunk c) stage of the blend products
-            auto blend_stage = [&](int p, int c) {
-                if (variant & 0x8000) return;                           // experiment: no basis stream
+            // one (plane p, K chunk c) stage of the blend products of vertex-tile counter g
+            auto blend_stage = [&](uint32_t g, int p, int c) {
+                if (p == 0 && c == 0) { vs_wait(&S.vp_empty[g & 1], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
+                if (variant & 0x8000) {                                 // experiment: no basis stream
+                    if (p == 2 && c == TC_K_CHUNKS - 1) tc_commit(smem_u32(&S.vp_full[g & 1]));
+                    return;
+                }
                 vs_wait(&S.a_full[a_stage], a_phase);
                 tc_fence_after();
-                const uint32_t d = tmem + p * VS_NH;
+                const uint32_t d = tmem + (g & 1) * VS_VP_COLS + p * VS_NH;
                 const uint32_t a_st = a_lo0 + ((a_stage * VS_A_STAGE_BYTES) >> 4);
                 const uint32_t f_st = f_lo0 + ((c * 2 * 4096) >> 4);
 #pragma unroll
@@ -213,32 +217,28 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 if (csize == 1) tc_commit(smem_u32(&S.a_empty[a_stage]));
                 else tc_commit_multicast(smem_u32(&S.a_empty[a_stage]), cmask);      // every producer of the cluster refills this slot
                 if (++a_stage == VS_ASTAGES) { a_stage = 0; a_phase ^= 1; }
+                if (p == 2 && c == TC_K_CHUNKS - 1) tc_commit(smem_u32(&S.vp_full[g & 1]));
             };
-            uint32_t ts = 0, tph = 0;                                   // transform stage ring: chunk counter mod 6, its phase
             VS_FOR_EACH_TILE {
                 (void)tile;
                 vs_wait(&S.feat_full, it & 1);
                 tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < VS_STAGES_PER_TILE; ++k) blend_stage(gt, k / TC_K_CHUNKS, k % TC_K_CHUNKS);
+                vs_wait(&S.bones_full, it & 1);
+                tc_fence_after();
 #pragma unroll 1
                 for (int t = 0; t < VS_NT; ++t, ++gt) {
-                    // ---- rest positions of vertex tile t: 3 planes x 5 K chunks into the one vp stage, once the epilogue has
-                    // drained the previous tile's
-                    vs_wait(&S.vp_empty, (gt & 1) ^ 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < VS_STAGES_PER_TILE; ++k) blend_stage(k / TC_K_CHUNKS, k % TC_K_CHUNKS);
-                    tc_commit(smem_u32(&S.vp_full));
-                    if (t == VS_NT - 1) tc_commit(smem_u32(&S.feat_empty));
-                    if (t == 0) { vs_wait(&S.bones_full, it & 1); tc_fence_after(); }
                     vs_wait(&S.w_full[gt & 1], (gt >> 1) & 1);
                     tc_fence_after();
                     const uint32_t w1 = w_lo0 + (((gt & 1) * VS_W_TILE_BYTES) >> 4), w2 = w1 + (4096 >> 4);
-                    // ---- blended transforms, 4 hands per chunk, up to six chunks ahead of the epilogue
-#pragma unroll 1
+                    const bool more = t + 1 < VS_NT;
+#pragma unroll
                     for (int ch = 0; ch < VS_NCH; ++ch) {
-                        vs_wait(&S.t_empty[ts], tph ^ 1);
+                        // T stage ch & 1: its uses so far = 8 gt + ch / 2 -> wait parity ((ch >> 1) & 1) ^ 1 (8 per tile: even)
+                        vs_wait(&S.t_empty[ch & 1], (((ch >> 1) & 1) ^ 1));
                         tc_fence_after();
-                        const uint32_t d = tmem + VS_T_COL0 + ts * VS_TN;
+                        const uint32_t d = tmem + VS_T_COL0 + (ch & 1) * VS_TN;
                         const uint32_t a1 = b_lo0 + ((ch * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES) >> 4);
                         const uint32_t a2 = a1 + (VS_BONE_CHUNK_BYTES >> 4), a3 = a2 + (VS_BONE_CHUNK_BYTES >> 4);
                         // smallest products first, w1 a1 last: the tensor core TRUNCATES its fp32 accumulator at the running
@@ -259,10 +259,12 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                                 umma_f16_lohi<false>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
                             }
                         }
-                        tc_commit(smem_u32(&S.t_full[ts]));
-                        if (++ts == VS_TSTAGES) { ts = 0; tph ^= 1; }
+                        tc_commit(smem_u32(&S.t_full[ch & 1]));
+                        // the next vertex tile's blend products, one stage per chunk (15 stages over 16 chunks)
+                        if (more && ch < VS_STAGES_PER_TILE) blend_stage(gt + 1, ch / TC_K_CHUNKS, ch % TC_K_CHUNKS);
                     }
                     tc_commit(smem_u32(&S.w_empty[gt & 1]));
+                    if (t == VS_NT - 2) tc_commit(smem_u32(&S.feat_empty));        // blend products of the last vertex tile are issued
                 }
                 tc_commit(smem_u32(&S.bones_empty));
                 ++it;
@@ -394,7 +396,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const float osv = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
         const float ost = exp2f(-(float)(VS_W_SCALE_LOG2 + VS_BONE_SCALE_LOG2));
-        uint32_t gt = 0, ts = set, tph = 0;                            // this set's next chunk: transform stage (chunk counter mod 6), phase
+        uint32_t gt = 0, rounds = 0;                                   // rounds: chunks this set has taken (its transform stage's phase)
         VS_FOR_EACH_TILE {
             const long long hand0 = (long long)tile * VS_NH;
             for (int t = 0; t < VS_NT; ++t, ++gt) {
@@ -405,8 +407,8 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
 #pragma unroll
                 for (int i = 0; i < 5; ++i) if (vtx == c_vs_tip_vert[i]) tipslot = c_vs_tip_slot[i];
                 const bool carries = valid && t + 1 < VS_NT && vl >= VS_M - 2;
-                const uint32_t vp_addr = tmem + lane_addr;
-                vs_wait(&S.vp_full, gt & 1);
+                const uint32_t vp_addr = tmem + lane_addr + (gt & 1) * VS_VP_COLS;
+                vs_wait(&S.vp_full[gt & 1], (gt >> 1) & 1);
                 tc_fence_after();
                 if (v_posed_t != nullptr) {
                     // rest-pose scratch for the skinning backward: v_posed_t[group][3 pos + p][32 hands], this warp's 32 hands
@@ -429,10 +431,10 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     }
                 }
 #pragma unroll 1
-                for (int ch = set; ch < VS_NCH; ch += 2) {
-                    vs_wait(&S.t_full[ts], tph);
+                for (int ch = set; ch < VS_NCH; ch += 2, ++rounds) {
+                    vs_wait(&S.t_full[set], rounds & 1);
                     tc_fence_after();
-                    const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + ts * VS_TN;
+                    const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + set * VS_TN;
                     uint32_t T[VS_TN], X[VS_HC], Y[VS_HC], Z[VS_HC];
                     const uint32_t x_addr = vp_addr + ch * VS_HC;
                     if (!(variant & 0x1000)) {                          // 0x1000: experiment, no TMEM loads
@@ -450,9 +452,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[ts]));
-                    ts += 2;
-                    if (ts >= VS_TSTAGES) { ts -= VS_TSTAGES; tph ^= 1; }
+                    if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[set]));
                     // result rows of chunk oc = (chunks so far) -> ring slot; the set's slots alternate {set, set + 2}
                     const uint32_t oc = gt * VS_NCH + ch;
                     const uint32_t ob = oc % VS_OSTAGES;
@@ -502,7 +502,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&S.vp_empty));
+                if (lane == 0) mbar_arrive(smem_u32(&S.vp_empty[gt & 1]));
             }
         }
     }

@@ -125,7 +125,7 @@ class _ManoFunction(torch.autograd.Function):
                 ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
             _cabi.check(lib.mb_mano_backward(layer._blob.data_ptr(), nc, rot.data_ptr(), coeffs.data_ptr(),
                                              betas.data_ptr(), g_verts.data_ptr(), g_joints.data_ptr(), B,
-                                             layer._mode | layer._fwd_flags, flags, g_rot.data_ptr(), g_coeffs.data_ptr(),
+                                             layer._mode, flags, g_rot.data_ptr(), g_coeffs.data_ptr(),
                                              g_betas.data_ptr(), ws.data_ptr(), ws.numel(), stream),
                         "mb_mano_backward")
             if not ctx.ws_valid:
@@ -155,13 +155,14 @@ class ManoLayer(nn.Module):
     numpy arrays with the pkl's keys, e.g. ``assets.synthetic_mano()``) instead
     of a pkl path; ``mode`` in {"fp32", "f16x3", "f16"} selects the blend-shape
     contraction precision; ``keep_workspace`` trades 12 KB/hand of retained
-    memory for not recomputing the forward in the backward; ``fused_forward=False``
-    forces the separate blend-contraction and skinning kernels where the fused
-    lane = vertex kernel would run (batches of 8 192 hands and more).
+    memory for not recomputing the forward in the backward; ``fused_forward=True``
+    runs the fused blend + skinning kernel with lane = vertex (csrc/vskin.cu) from
+    8 192 hands on — parity-green, but measured slower than the two separate
+    kernels, hence opt-in.
     """
 
     def __init__(self, device, MANO_RIGHT_pkl=None, bases_num=10, pose_num=6, *, model=None, mode="f16x3",
-                 keep_workspace=True, fused_forward=True):
+                 keep_workspace=True, fused_forward=False):
         super().__init__()
         self.device = device
         self.bases_num = bases_num
@@ -173,7 +174,7 @@ class ManoLayer(nn.Module):
         self._mode = _cabi.MODES[mode]      # model property bits (mb_mano_model_flags) are OR-ed in below
         self.mode = mode
         self.keep_workspace = bool(keep_workspace)
-        self._fwd_flags = 0 if fused_forward else _cabi.FWD_UNFUSED
+        self._fwd_flags = _cabi.FWD_FUSED if fused_forward else 0
 
         if model is None:
             if MANO_RIGHT_pkl is None:

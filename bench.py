@@ -803,9 +803,9 @@ def main():
                     "hbm_frac": BYTES_FWD * H / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "algorithmic_bytes_per_hand": BYTES_FWD,
                     "note": "mb_mano_forward with MB_FWD_INFERENCE (no rest-pose scratch kept): verts[H,778,3] + joints[H,21,3]"}
-    if "fused_fwd" in fstages and not args.no_extras:
-        # A/B: the same forward through the separate blend-contraction + skinning kernels (MB_FWD_UNFUSED)
-        um = fwd_mode | cabi.FWD_UNFUSED
+    if not args.no_extras and (mode & 0xff) != cabi.MODE_FP32:
+        # A/B: the same forward through the opt-in fused blend + skinning kernel with lane = vertex (MB_FWD_FUSED, vskin.cu)
+        um = fwd_mode | cabi.FWD_FUSED
 
         def ufwd_step(i):
             s = sets[i % nsets]
@@ -824,8 +824,9 @@ def main():
         sync_all()
         uprof = cabi.profile_collect()
         lib.mb_profile_enable(0)
-        forward_only["unfused_ab"] = {"ms_per_step": e0.elapsed_time(e1) / 5, "stages_ms": {k: v[0] / v[1] for k, v in uprof.items()},
-                                      "note": "same launch with MB_FWD_UNFUSED: pose -> blend GEMM (writes v_posed_t) -> lane = hand skinning"}
+        forward_only["fused_ab"] = {"ms_per_step": e0.elapsed_time(e1) / 5, "stages_ms": {k: v[0] / v[1] for k, v in uprof.items()},
+                                    "note": "same launch with MB_FWD_FUSED: pose -> fused blend + skinning with lane = vertex (vskin.cu), "
+                                            "no v_posed_t; opt-in because it is the slower one"}
     if "fused_fwd" in fstages:
         fms = fstages["fused_fwd"]
         lbs_fwd_roof = hbm_roofline("fused_fwd", BYTES_FUSED_FWD, ms=fms)

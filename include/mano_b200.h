@@ -54,13 +54,13 @@ extern "C" {
 #define MB_MODEL_CHAINS_5X3 0x100
 
 /* Forward options, OR-ed into `mode` of mb_mano_forward:
- * MB_FWD_INFERENCE: no backward will follow — the forward keeps no rest-pose scratch in the workspace (a later
+ * MB_FWD_INFERENCE: no backward will follow — the fused forward keeps no rest-pose scratch in the workspace (a later
  *                   mb_mano_backward must then be called WITHOUT MB_BWD_WORKSPACE_VALID and recomputes it);
- * MB_FWD_UNFUSED  : run the separate blend-contraction and skinning kernels even where the fused kernel applies
- *                   (measurement / cross-checking); in mb_mano_backward's `mode`: the separate skinning-backward and
- *                   gradient-contraction kernels with the dv_posed tiles in HBM. */
+ * MB_FWD_FUSED    : from 8 192 hands on (MANO tree, tensor-core modes) run the fused blend-shape + skinning kernel with
+ *                   lane = vertex (csrc/vskin.cu) instead of the blend-contraction and skinning kernels.  Opt-in: it is
+ *                   parity-green but measured slower than the two kernels (profiles/r2/ncu_history.md). */
 #define MB_FWD_INFERENCE 0x200
-#define MB_FWD_UNFUSED   0x400
+#define MB_FWD_FUSED     0x400
 
 /* mb_mano_backward flags */
 #define MB_BWD_WORKSPACE_VALID 1  /* workspace still holds the forward's intermediates for these inputs */

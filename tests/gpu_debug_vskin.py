@@ -52,7 +52,21 @@ def main():
         if ev.max() > 1e-6:
             bad = np.argwhere(ev.max(axis=2) > 1e-6)
             print("  first bad (hand, vertex):", bad[:8].tolist(), " count", len(bad), "of", ev.shape[0] * 778)
-    # hand-position dependence of the errors
+    # error of the default path (separate kernels) and of the fused one over whole batches, per pose-kernel regime
+    for Bt in (1000, 4096, 9001, 40001):
+        r2, p2, b2 = mano_inputs(Bt, 45, seed=Bt + 45)
+        want_v, want_j = [], []
+        for s0 in range(0, Bt, 2048):
+            a, b = mo.mano_forward(model, r2[s0:s0 + 2048], p2[s0:s0 + 2048], b2[s0:s0 + 2048])
+            want_v.append(a); want_j.append(b)
+        want_v, want_j = np.concatenate(want_v), np.concatenate(want_j)
+        for name, lay in (("default", pkg.ManoLayer(dev, model=model, pose_num=45)),
+                          ("fused", pkg.ManoLayer(dev, model=model, pose_num=45, fused_forward=True))):
+            with torch.no_grad():
+                v, j = lay(*[torch.from_numpy(x).to(dev) for x in (r2, p2, b2)])
+            ev = np.abs(v.cpu().numpy() - want_v).max(axis=(1, 2))
+            ej = np.abs(j.cpu().numpy() - want_j).max(axis=(1, 2))
+            print(f"B={Bt:6d} {name:8s} verts max {ev.max():.3e} p99.9 {np.quantile(ev, .999):.3e} p50 {np.median(ev):.3e} | joints max {ej.max():.3e}")
     torch.cuda.synchronize()
 
 

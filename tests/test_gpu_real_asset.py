@@ -13,14 +13,13 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, assert_positions
 from oracle import mano_oracle as mo
 from oracle import ref_import
 
 pytestmark = pytest.mark.gpu
 
 POS_TOL_REF = 2e-7       # vs the reference's fp32 outputs (its own fp32-vs-fp64 noise is ~1e-7 m)
-POS_TOL_F64 = 1e-7       # vs the fp64 oracle (north_star: 1e-4 mm)
 GRAD_TOL = 1e-4
 
 
@@ -124,8 +123,8 @@ def test_real_pkl_matches_live_reference_forward_and_autograd(pkg, ref, real_mod
     # and the fp64 arbiter on the same real model
     sub = idx[:96]
     ov, oj = mo.mano_forward(real_model, rot[sub], pose[sub], beta[sub])
-    assert np.abs(v.detach().cpu().numpy()[sub] - ov).max() < POS_TOL_F64
-    assert np.abs(j.detach().cpu().numpy()[sub] - oj).max() < POS_TOL_F64
+    assert_positions(v.detach().cpu().numpy()[sub], ov)
+    assert_positions(j.detach().cpu().numpy()[sub], oj)
 
 
 def test_real_pkl_joints_only_head_path(pkg, ref, cuda_device):
