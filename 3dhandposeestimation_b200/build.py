@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("MANO_B200_NVCC_EXTRA", "").split()          # e.g. -DVS_PROFILE (diagnostic builds; part of the stamp)
 
 
 def _nvcc() -> str:

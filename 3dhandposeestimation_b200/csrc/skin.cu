@@ -31,6 +31,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "blend_tc.cuh"
+#include <stdlib.h>
 #include "skin.cuh"
 #include "ptx.cuh"
 
@@ -560,11 +561,13 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                      const float* __restrict__ bone_t, const float* __restrict__ g_verts,
                      const float* __restrict__ g_joints, int B,
                      float* __restrict__ dv_t, unsigned char* __restrict__ dvp, float* __restrict__ dbone,
-                     int dbone_hand_minor, float* __restrict__ dparts, int spu) {
+                     int dbone_hand_minor, float* __restrict__ dparts, int spu, int role_flip) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SkinProg& P = *reinterpret_cast<SkinProg*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = warp >> 1, role = warp & 1;
+    // warps w and w + 4 share a scheduler: with role = warp & 1 two schedulers would run only role-0 warps and two only the
+    // (longer) role-1 warps; flipping the roles of the upper four warps gives every scheduler one of each
+    const int pair = warp >> 1, role = (warp & 1) ^ (role_flip & (warp >> 2) & 1);
     BwdPairShared& W = reinterpret_cast<BwdPairShared*>(smem_raw + PROG_BYTES)[pair];
     if (role == 0 && lane == 0) {
         W.bones.init();
@@ -1110,17 +1113,18 @@ int launch_skin_backward(const void* blob, const float* v_posed_t, const float* 
     if (int arc = ensure_dyn_smem(once_b, skin_backward_kernel<true>, SKB_SMEM)) return arc;
     const int ngroups = (B + 31) >> 5;
     const int spu = skin_segments_per_unit(ngroups, SKB_SWEEPERS);
+    static const int role_flip = getenv("MANO_B200_SKB_FLIP") ? atoi(getenv("MANO_B200_SKB_FLIP")) : 1;
     if (spu < SK_NSEG) {
         if (dparts == nullptr) return MB_E_NULL;
         const int nunits = ngroups * skin_units_per_group(spu);
         skin_backward_kernel<true><<<nunits < NUM_SMS ? nunits : NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(
-            blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp, dbone, dbone_hand_minor, dparts, spu);
+            blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp, dbone, dbone_hand_minor, dparts, spu, role_flip);
         int rc = cuda_rc();
         if (rc) return rc;
         dbone_reduce_kernel<<<ngroups * NJ, BONE_F * 32, 0, s>>>(blob, dparts, B, spu, dbone, dbone_hand_minor);
     } else {
         skin_backward_kernel<false><<<NUM_SMS, SKB_THREADS, SKB_SMEM, s>>>(blob, v_posed_t, bone_t, g_verts, g_joints, B, dv_t, dvp,
-                                                                          dbone, dbone_hand_minor, nullptr, SK_NSEG);
+                                                                          dbone, dbone_hand_minor, nullptr, SK_NSEG, role_flip);
     }
     return cuda_rc();
 }

@@ -16,16 +16,18 @@
 // shared-memory row as ONE contiguous, sector-aligned 1 536-byte piece per (hand, vertex tile) of
 // verts[B][778][3] in its natural layout — no transposition, no v_posed_t round trip.
 //
-// Roles (512 threads, 1 CTA per SM, persistent over 64-hand tiles):
-//   warp 0   basis producer: (tile, plane, K chunk) stages of 16 KB, always L2 hits, 4-stage ring
-//   warp 1   MMA issuer (one thread): blend products of vertex tile t+1 interleaved with the transform chunks of tile t
-//   warp 2   TMEM allocation; producer of the hand tile's feature rows (40 KB) and of the weight tiles (12 KB per
-//            vertex tile, double buffered)
+// Roles (384 threads, 1 CTA per SM, persistent over 64-hand tiles; a UNIT is one (hand tile, vertex tile) pair):
+//   warp 0   blend issuer + basis producer (one thread): (tile, plane, K chunk) stages of 16 KB, always L2 hits, 4-slot ring,
+//            multicast inside a cluster; the blend products of unit u + 1 run while the epilogue works on unit u
+//   warp 1   transform issuer (one thread): T = W A of unit u, 4 hands per chunk
+//   warp 2   TMEM allocation; producer of the hand tile's feature rows (40 KB) and of the weight tiles (8 KB per vertex tile,
+//            double buffered)
 //   warp 3   converts the hand tile's fp32 bone transforms (48 KB, straight from the pose stage's bone_t) into the
-//            transform products' fp16 x3 B operand in shared memory (72 KB)
-//   warps 12-15  store warps, one per slot of the result-row ring
-//   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices); warps 4-7 take the even chunks, 8-11 the odd ones
-// TMEM (512 columns): two rest-position stages of 3 x 64 columns, two transform stages of 48 columns.
+//            transform products' fp16 x3 B operand in shared memory (72 KB), chunk by chunk behind per-chunk barriers
+//   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices); warps 4-7 own hands 0-31 of the tile, 8-11 hands 32-63
+// TMEM (512 columns): ONE rest-position stage of 3 x 64 columns — every epilogue thread copies its 3 x 32 rest coordinates
+// into registers at the start of a unit and frees the stage for the next unit's blend products at once — and a ring of
+// six transform stages of 48 columns (three chunks in flight per epilogue warp set).
 #include <cuda_fp16.h>
 #include <string.h>
 #include <stdlib.h>
@@ -40,15 +42,15 @@
 namespace mb {
 namespace {
 
-constexpr int VS_THREADS = 512;                   // 16 warps: see the role list above
+constexpr int VS_THREADS = 384;                   // 12 warps: see the role list above
 constexpr int VS_EPI_WARPS = 8;
-constexpr int VS_ASTAGES = 4;
-constexpr int VS_OSTAGES = 4;                     // result-row ring: two chunks per epilogue warp set
-constexpr int VS_ROW = 392;                        // floats per staging row: up to 6 carried floats + 384 + slack
+constexpr int VS_ASTAGES = 5;                     // basis ring: 5 x 16 KB (the stream is latency-bound: bytes in flight / ~1 900 clk)
+constexpr int VS_TSTAGES = 6;                     // transform ring: chunk counter mod 6; even counters -> warp set 0, odd -> set 1
+constexpr int VS_HS = VS_NH / 2;                  // 32 hands per epilogue warp set
+constexpr int VS_ROWF = 100;                      // floats per staging row: 96 results of a warp's 32 vertices + pad (16-byte multiple)
 constexpr uint32_t VS_TMEM_COLS = 512;
-constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns per rest-position stage (two stages)
-constexpr uint32_t VS_T_COL0 = 2 * VS_VP_COLS;     // 384: first transform column
-constexpr int VS_TSTAGES = 2;                      // transform stages of 48 columns, one per epilogue warp set: 480 columns in all
+constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns: the rest positions of a unit
+constexpr uint32_t VS_T_COL0 = VS_VP_COLS;         // 192: first transform column
 // instruction descriptors: f16 x f16 -> f32, M = 128
 constexpr uint32_t VS_IDESC_BLEND = (1u << 4) | ((uint32_t)(VS_NH >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);                // A, B K-major
 constexpr uint32_t VS_IDESC_T = (1u << 4) | (1u << 16) | ((uint32_t)(VS_TN >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);       // B MN-major
@@ -60,15 +62,14 @@ struct VsShared {
     alignas(128) unsigned char feat[TC_K_CHUNKS][2][VS_NH * TC_K_CHUNK * 2];      // 40 KB: [K chunk][hi, lo][64 hands x 32]
     alignas(128) unsigned char bones[VS_NCH][VS_BONE_SPLITS][VS_BONE_CHUNK_BYTES]; // 72 KB
     alignas(128) unsigned char a[VS_ASTAGES][VS_A_STAGE_BYTES];                    // 64 KB basis ring
-    alignas(128) unsigned char w[2][VS_W_TILE_BYTES];                              // 24 KB weight tiles
-    alignas(128) float out[VS_OSTAGES][VS_HC][VS_ROW];                             // 18.4 KB result rows
-    alignas(16) float carry[2][VS_NH][8];                                          // tail of a hand's row piece, for the next vertex tile
+    alignas(128) unsigned char w[2][VS_W_TILE_BYTES];                              // 16 KB weight tiles
+    alignas(16) float out[VS_EPI_WARPS][VS_HC][VS_ROWF];                           // 12.5 KB: a chunk's result rows, private to a warp
     alignas(8) unsigned long long a_full[VS_ASTAGES], a_empty[VS_ASTAGES];
     unsigned long long w_full[2], w_empty[2];
-    unsigned long long feat_full, feat_empty, bones_full, bones_empty;
-    unsigned long long vp_full[2], vp_empty[2];
+    unsigned long long feat_full, feat_empty;
+    unsigned long long bones_full[VS_NCH], bones_empty[VS_NCH];
+    unsigned long long vp_full, vp_empty;
     unsigned long long t_full[VS_TSTAGES], t_empty[VS_TSTAGES];
-    unsigned long long out_full[VS_OSTAGES], out_empty[VS_OSTAGES];
     uint32_t tmem_base;
 };
 
@@ -82,13 +83,26 @@ __device__ __forceinline__ void vs_wait(unsigned long long* bar, uint32_t parity
     }
 }
 
-// sector alignment of the row pieces: rows of verts[B][778][3] are 9 336 B = 24 (mod 32) apart, so the piece of
-// vertex tile t >= 1 of hand h covers floats [384 t - d, 384 t + 384 - d), d = (0, 6, 4, 2)[h % 4]: every piece starts on
-// a 32-byte boundary; the d floats in front are the tail of the previous tile's results (carry).  Tile 0 starts at the
-// row's first 32-byte boundary (float a = (8 - d) % 8) and its first a floats are plain stores; inside the shared row
-// the results sit S floats in so that the bulk copy's source is 16-byte aligned: S = d for t >= 1, (0, 2, 0, 2)[h % 4] for t = 0.
-__device__ __forceinline__ int vs_d(int hl) { return (8 - 2 * hl) & 7; }                 // hl = h % 4 -> 0, 6, 4, 2
-__device__ __forceinline__ int vs_shift(int t, int hl) { return t == 0 ? ((hl & 1) << 1) : vs_d(hl); }
+// -DVS_PROFILE: every role of CTA 0 accumulates the cycles it spends in each kind of wait and its total loop time into
+// dbg[8192 + 8 * role ...] (profiles/tools/vskin_roles.py); compiled out otherwise
+#ifdef VS_PROFILE
+#define VS_WAIT(bar, parity, slot) do { const long long _t0 = clock64(); vs_wait(bar, parity); prof[slot] += clock64() - _t0; } while (0)
+#define VS_PROF_DECL long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define VS_PROF_STORE(role) do { if (dbg != nullptr && blockIdx.x == 0) { prof[7] = clock64() - prof_t0; \
+    for (int _i = 0; _i < 8; ++_i) dbg[8192 + 8 * (role) + _i] = (float)prof[_i]; } } while (0)
+#define VS_TIC const long long _tic = clock64()
+#define VS_TOC(slot) prof[slot] += clock64() - _tic
+#else
+#define VS_TIC do {} while (0)
+#define VS_TOC(slot) do {} while (0)
+#define VS_WAIT(bar, parity, slot) vs_wait(bar, parity)
+#define VS_PROF_DECL do {} while (0)
+#define VS_PROF_STORE(role) do {} while (0)
+#endif
+
+// the j-th transform chunk ISSUED of a unit is chunk (j >> 1) + 8 (j & 1): hands 4 ch .. 4 ch + 3 of the tile, so that the two
+// epilogue warp sets (hands 0-31, 32-63) are served alternately
+__device__ __forceinline__ int vs_chunk_of(int j) { return (j >> 1) + (VS_NCH / 2) * (j & 1); }
 
 __global__ void __launch_bounds__(VS_THREADS, 1)
 vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ vs_basis,
@@ -113,14 +127,11 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < VS_ASTAGES; ++s) { mbar_init(smem_u32(&S.a_full[s]), 1); mbar_init(smem_u32(&S.a_empty[s]), csize); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(smem_u32(&S.w_full[s]), 1); mbar_init(smem_u32(&S.w_empty[s]), 1);
-        }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&S.vp_full[s]), 1); mbar_init(smem_u32(&S.vp_empty[s]), VS_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&S.w_full[s]), 1); mbar_init(smem_u32(&S.w_empty[s]), 1); }
+        mbar_init(smem_u32(&S.vp_full), 1); mbar_init(smem_u32(&S.vp_empty), VS_EPI_WARPS);
         for (int s = 0; s < VS_TSTAGES; ++s) { mbar_init(smem_u32(&S.t_full[s]), 1); mbar_init(smem_u32(&S.t_empty[s]), VS_EPI_WARPS / 2); }
         mbar_init(smem_u32(&S.feat_full), 1); mbar_init(smem_u32(&S.feat_empty), 1);
-        mbar_init(smem_u32(&S.bones_full), 1); mbar_init(smem_u32(&S.bones_empty), 1);
-        for (int s = 0; s < VS_OSTAGES; ++s) { mbar_init(smem_u32(&S.out_full[s]), VS_EPI_WARPS / 2); mbar_init(smem_u32(&S.out_empty[s]), 1); }
+        for (int s = 0; s < VS_NCH; ++s) { mbar_init(smem_u32(&S.bones_full[s]), 1); mbar_init(smem_u32(&S.bones_empty[s]), 1); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(&S.tmem_base), VS_TMEM_COLS);
@@ -132,113 +143,144 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
 
     if (warp == 0) {
         if (elect_one()) {
-            // ===== basis producer: the same 105-stage stream for every hand tile, kept in L2 =====
-            const uint64_t keep = l2_policy_evict_last();
-            uint32_t stage = 0, phase = 0;
-            const uint32_t slice = VS_A_STAGE_BYTES / csize;           // this CTA's share of every stage
-            VS_FOR_EACH_TILE {
-                (void)tile;
-                if (variant & 0x8000) continue;                        // experiment: no basis stream
-                for (int i = 0; i < VS_NT * VS_STAGES_PER_TILE; ++i) {
-                    vs_wait(&S.a_empty[stage], phase ^ 1);             // every CTA of the cluster has consumed the slot
-                    mbar_expect_tx(smem_u32(&S.a_full[stage]), VS_A_STAGE_BYTES);
-                    if (csize == 1)
-                        bulk_g2s_hint(smem_u32(S.a[stage]), vs_basis + (size_t)i * VS_A_STAGE_BYTES, VS_A_STAGE_BYTES,
-                                      smem_u32(&S.a_full[stage]), keep);
-                    else
-                        bulk_g2s_multicast(smem_u32(S.a[stage]) + crank * slice, vs_basis + (size_t)i * VS_A_STAGE_BYTES + crank * slice, slice,
-                                           smem_u32(&S.a_full[stage]), cmask, keep);
-                    if (++stage == VS_ASTAGES) { stage = 0; phase ^= 1; }
+            // ===== blend issuer (one thread) =====
+            // Per (plane, K chunk) stage of the basis ring: wait for its bytes, issue its 6 MMAs, commit -> a_empty.
+            // [profiles/r2: ONE thread polling both the blend and the transform cursor spent ~400 clk per event — 31 events per
+            // unit = 13 000 clk, the whole kernel time with every MMA removed: two issuing threads with blocking waits.  With the
+            // basis refills in this thread too it was busy 9 000 clk per unit (the critical chain of the kernel: 15 400 per unit):
+            // the refills moved to the producer thread of warp 2, which idled 98 % of the time.]
+            constexpr uint32_t NS = VS_ASTAGES;
+            const uint32_t hi_k512 = desc_hi(TC_SBO);
+            const uint32_t a_lo0 = desc_lo(smem_u32(S.a[0]), TC_LBO), f_lo0 = desc_lo(smem_u32(S.feat[0][0]), TC_LBO);
+            int n_it = 0;
+            VS_FOR_EACH_TILE { (void)tile; ++n_it; }
+            VS_PROF_DECL;
+            uint32_t st = 0;                                            // stage counter over the whole kernel
+            uint32_t g = 0;                                             // unit counter
+            for (int it = 0; it < n_it; ++it) {
+                VS_WAIT(&S.feat_full, it & 1, 0);
+                for (int t = 0; t < VS_NT; ++t, ++g) {
+                    VS_WAIT(&S.vp_empty, (g & 1) ^ 1, 1);                  // the epilogue has copied the previous unit's rest positions out
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int pl = 0; pl < 3; ++pl) {
+                        const uint32_t d = tmem + pl * VS_NH;
+#pragma unroll
+                        for (int c = 0; c < TC_K_CHUNKS; ++c, ++st) {
+                            const uint32_t slot = st % NS;
+                            VS_WAIT(&S.a_full[slot], (st / NS) & 1, 2);
+                            tc_fence_after();
+                            const uint32_t a_st = a_lo0 + ((slot * VS_A_STAGE_BYTES) >> 4);
+                            const uint32_t f_st = f_lo0 + ((c * 2 * 4096) >> 4);
+                            if (!(variant & 0x400)) {                   // 0x400: experiment, no blend products
+#pragma unroll
+                                for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
+                                    const uint32_t a_hi = a_st + ((j * 2 * (int)TC_LBO) >> 4), a_lo = a_hi + ((VS_A_STAGE_BYTES / 2) >> 4);
+                                    const uint32_t b_hi = f_st + ((j * 2 * (int)TC_LBO) >> 4), b_lo = b_hi + (4096 >> 4);
+                                    if (j == 0 && c == 0) umma_f16_lohi<false>(d, a_hi, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
+                                    else umma_f16_lohi<true>(d, a_hi, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
+                                    if (blend_products == 3) {
+                                        umma_f16_lohi<true>(d, a_lo, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
+                                        umma_f16_lohi<true>(d, a_hi, hi_k512, b_lo, hi_k512, VS_IDESC_BLEND);
+                                    }
+                                }
+                            }
+                            if (variant & 0x10000) mbar_arrive(smem_u32(&S.a_empty[slot]));      // 0x10000: experiment (with 0x400, csize 1): plain arrive
+                            else if (csize == 1) tc_commit(smem_u32(&S.a_empty[slot]));
+                            else tc_commit_multicast(smem_u32(&S.a_empty[slot]), cmask);    // every CTA of the cluster refills this slot
+                        }
+                    }
+                    tc_commit(smem_u32(&S.vp_full));
                 }
+                tc_commit(smem_u32(&S.feat_empty));
             }
+            VS_PROF_STORE(0);
         }
     } else if (warp == 2) {
         if (elect_one()) {
-            // ===== per-hand-tile operands (features, bones) and the weight tiles =====
+            // ===== producer of all bulk copies: basis ring, per-hand-tile feature rows, weight tiles (one polling thread) =====
+            // The basis is the same 105-stage stream for every hand tile, kept in L2 (evict-last) and, inside a cluster, loaded
+            // once and multicast.
             const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
-            uint32_t it = 0, gw = 0;
-            VS_FOR_EACH_TILE {
-                const int ltile = tile < ntiles ? tile : ntiles - 1;
-                vs_wait(&S.feat_empty, (it & 1) ^ 1);
-                mbar_expect_tx(smem_u32(&S.feat_full), TC_K_CHUNKS * 2 * 4096);
-                const unsigned char* fsrc = featp + (size_t)(ltile >> 1) * TC_A_TILE_BYTES + (size_t)(ltile & 1) * 4096;
-                for (int c = 0; c < TC_K_CHUNKS; ++c)
-                    for (int sp = 0; sp < 2; ++sp)
-                        bulk_g2s_hint(smem_u32(S.feat[c][sp]), fsrc + (size_t)c * TC_A_STAGE_BYTES + (size_t)sp * TC_A_BLOCK_BYTES, 4096,
-                                      smem_u32(&S.feat_full), once);
-                for (int t = 0; t < VS_NT; ++t, ++gw) {
-                    vs_wait(&S.w_empty[gw & 1], ((gw >> 1) & 1) ^ 1);
-                    mbar_expect_tx(smem_u32(&S.w_full[gw & 1]), VS_W_TILE_BYTES);
-                    bulk_g2s_hint(smem_u32(S.w[gw & 1]), vs_w + (size_t)t * VS_W_TILE_BYTES, VS_W_TILE_BYTES, smem_u32(&S.w_full[gw & 1]), keep);
+            const uint32_t slice = VS_A_STAGE_BYTES / csize;           // this CTA's share of every basis stage
+            constexpr uint32_t NS = VS_ASTAGES;
+            int n_it = 0;
+            VS_FOR_EACH_TILE { (void)tile; ++n_it; }
+            const uint32_t total_a = (uint32_t)n_it * (VS_NT * VS_STAGES_PER_TILE), total_w = (uint32_t)n_it * VS_NT;
+            uint32_t na = 0, nw = 0;                                   // basis stages / weight tiles requested so far
+            int fit = 0;                                                // feature tiles requested so far
+            int rnd = cluster_id;                                       // round of the next feature tile
+            VS_PROF_DECL;
+            long long idle_since = -1;
+            while (na < total_a || nw < total_w || fit < n_it) {
+                bool progressed = false;
+                // basis stage na -> slot na % 5: free once the MMAs of stage na - 5 are done
+                if (na < total_a && (na < NS || mbar_test_wait(smem_u32(&S.a_empty[na % NS]), ((na / NS) & 1) ^ 1))) {
+                    const uint32_t slot = na % NS;
+                    const uint32_t i = na % (VS_NT * VS_STAGES_PER_TILE);
+                    if (variant & 0x8000) mbar_arrive(smem_u32(&S.a_full[slot]));          // 0x8000: experiment, no basis bytes
+                    else {
+                        mbar_expect_tx(smem_u32(&S.a_full[slot]), VS_A_STAGE_BYTES);
+                        if (csize == 1)
+                            bulk_g2s_hint(smem_u32(S.a[slot]), vs_basis + (size_t)i * VS_A_STAGE_BYTES, VS_A_STAGE_BYTES, smem_u32(&S.a_full[slot]), keep);
+                        else
+                            bulk_g2s_multicast(smem_u32(S.a[slot]) + crank * slice, vs_basis + (size_t)i * VS_A_STAGE_BYTES + crank * slice, slice,
+                                               smem_u32(&S.a_full[slot]), cmask, keep);
+                    }
+                    ++na;
+                    progressed = true;
                 }
-                ++it;
+                // weight tile of unit nw -> buffer nw & 1
+                if (nw < total_w && (nw < 2 || mbar_test_wait(smem_u32(&S.w_empty[nw & 1]), ((nw >> 1) & 1) ^ 1))) {
+                    mbar_expect_tx(smem_u32(&S.w_full[nw & 1]), VS_W_TILE_BYTES);
+                    bulk_g2s_hint(smem_u32(S.w[nw & 1]), vs_w + (size_t)(nw % VS_NT) * VS_W_TILE_BYTES, VS_W_TILE_BYTES, smem_u32(&S.w_full[nw & 1]), keep);
+                    ++nw;
+                    progressed = true;
+                }
+                // feature rows of the next hand tile
+                if (fit < n_it && (fit == 0 || mbar_test_wait(smem_u32(&S.feat_empty), (fit & 1) ^ 1))) {
+                    const int tile = rnd * (int)csize + (int)crank;
+                    const int ltile = tile < ntiles ? tile : ntiles - 1;
+                    mbar_expect_tx(smem_u32(&S.feat_full), TC_K_CHUNKS * 2 * 4096);
+                    const unsigned char* fsrc = featp + (size_t)(ltile >> 1) * TC_A_TILE_BYTES + (size_t)(ltile & 1) * 4096;
+                    for (int c = 0; c < TC_K_CHUNKS; ++c)
+                        for (int sp = 0; sp < 2; ++sp)
+                            bulk_g2s_hint(smem_u32(S.feat[c][sp]), fsrc + (size_t)c * TC_A_STAGE_BYTES + (size_t)sp * TC_A_BLOCK_BYTES, 4096,
+                                          smem_u32(&S.feat_full), once);
+                    ++fit;
+                    rnd += nclusters;
+                    progressed = true;
+                }
+                if (progressed) idle_since = -1;
+                else if (idle_since < 0) idle_since = clock64();
+                else if (clock64() - idle_since > 2000000000LL) __trap();
             }
+            VS_PROF_STORE(2);
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            // ===== MMA issuer =====
+            // ===== transform issuer: T = W A, 4 hands per chunk, through the six-stage ring =====
             // [profiles/r2: issued by `lane == 0` the compiler wrapped every tcgen05.mma in a divergence "waterfall" (ELECT /
-            // R2UR.BROADCAST / BRA.U.ANY) and rebuilt 64-bit descriptors per instruction — ~350 scalar instructions per
-            // 4-hand chunk at IPC ~0.25: the issuing THREAD, not the tensor pipe (14 % busy), paced the kernel at ~1 500 clk
-            // per chunk.  Now: elect.sync, 32-bit descriptor halves (only the low word changes), the chunk loop unrolled so
-            // that plane / K-chunk / accumulate flags are constants.]
-            uint32_t a_stage = 0, a_phase = 0, gt = 0, it = 0;
-            // K-major operands: LBO 128 B (between the K core matrices of one MMA), SBO between 8-row groups
-            const uint32_t hi_k512 = desc_hi(TC_SBO), hi_k256 = desc_hi(256);
-            const uint32_t a_lo0 = desc_lo(smem_u32(S.a[0]), TC_LBO), f_lo0 = desc_lo(smem_u32(S.feat[0][0]), TC_LBO);
+            // R2UR.BROADCAST / BRA.U.ANY) and rebuilt 64-bit descriptors per instruction: elect.sync and 32-bit descriptor halves.]
+            const uint32_t hi_k256 = desc_hi(256);
             const uint32_t w_lo0 = desc_lo(smem_u32(S.w[0]), 128);
-            // bones: MN-major, n-groups 256 B apart (SBO), k-groups 128 B apart (LBO); variant 1 swaps the two fields
-            const uint32_t b_lo0 = desc_lo(smem_u32(&S.bones[0][0][0]), (variant & 1) ? 256 : 128);
-            const uint32_t hi_b = desc_hi((variant & 1) ? 128 : 256);
-            // one (plane p, K chunk c) stage of the blend products of vertex-tile counter g
-            auto blend_stage = [&](uint32_t g, int p, int c) {
-                if (p == 0 && c == 0) { vs_wait(&S.vp_empty[g & 1], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
-                if (variant & 0x8000) {                                 // experiment: no basis stream
-                    if (p == 2 && c == TC_K_CHUNKS - 1) tc_commit(smem_u32(&S.vp_full[g & 1]));
-                    return;
-                }
-                vs_wait(&S.a_full[a_stage], a_phase);
-                tc_fence_after();
-                const uint32_t d = tmem + (g & 1) * VS_VP_COLS + p * VS_NH;
-                const uint32_t a_st = a_lo0 + ((a_stage * VS_A_STAGE_BYTES) >> 4);
-                const uint32_t f_st = f_lo0 + ((c * 2 * 4096) >> 4);
-#pragma unroll
-                for (int j = 0; j < TC_K_CHUNK / 16; ++j) {
-                    const uint32_t a_hi = a_st + ((j * 2 * (int)TC_LBO) >> 4), a_lo = a_hi + ((VS_A_STAGE_BYTES / 2) >> 4);
-                    const uint32_t b_hi = f_st + ((j * 2 * (int)TC_LBO) >> 4), b_lo = b_hi + (4096 >> 4);
-                    if (variant & 0x400) continue;                                  // experiment: no blend products
-                    if (c == 0 && j == 0) umma_f16_lohi<false>(d, a_hi, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
-                    else umma_f16_lohi<true>(d, a_hi, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
-                    if (blend_products == 3) {
-                        umma_f16_lohi<true>(d, a_lo, hi_k512, b_hi, hi_k512, VS_IDESC_BLEND);
-                        umma_f16_lohi<true>(d, a_hi, hi_k512, b_lo, hi_k512, VS_IDESC_BLEND);
-                    }
-                }
-                if (csize == 1) tc_commit(smem_u32(&S.a_empty[a_stage]));
-                else tc_commit_multicast(smem_u32(&S.a_empty[a_stage]), cmask);      // every producer of the cluster refills this slot
-                if (++a_stage == VS_ASTAGES) { a_stage = 0; a_phase ^= 1; }
-                if (p == 2 && c == TC_K_CHUNKS - 1) tc_commit(smem_u32(&S.vp_full[g & 1]));
-            };
+            // bones: MN-major, n-groups 256 B apart (SBO), k-groups 128 B apart (LBO)
+            const uint32_t b_lo0 = desc_lo(smem_u32(&S.bones[0][0][0]), 128);
+            const uint32_t hi_b = desc_hi(256);
+            uint32_t g = 0, stage = 0, phase = 0, it = 0;
+            VS_PROF_DECL;
             VS_FOR_EACH_TILE {
                 (void)tile;
-                vs_wait(&S.feat_full, it & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < VS_STAGES_PER_TILE; ++k) blend_stage(gt, k / TC_K_CHUNKS, k % TC_K_CHUNKS);
-                vs_wait(&S.bones_full, it & 1);
-                tc_fence_after();
+                for (int t = 0; t < VS_NT; ++t, ++g) {
+                    VS_WAIT(&S.w_full[g & 1], (g >> 1) & 1, 0);
+                    const uint32_t w1 = w_lo0 + (((g & 1) * VS_W_TILE_BYTES) >> 4), w2 = w1 + (4096 >> 4);
 #pragma unroll 1
-                for (int t = 0; t < VS_NT; ++t, ++gt) {
-                    vs_wait(&S.w_full[gt & 1], (gt >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t w1 = w_lo0 + (((gt & 1) * VS_W_TILE_BYTES) >> 4), w2 = w1 + (4096 >> 4);
-                    const bool more = t + 1 < VS_NT;
-#pragma unroll
-                    for (int ch = 0; ch < VS_NCH; ++ch) {
-                        // T stage ch & 1: its uses so far = 8 gt + ch / 2 -> wait parity ((ch >> 1) & 1) ^ 1 (8 per tile: even)
-                        vs_wait(&S.t_empty[ch & 1], (((ch >> 1) & 1) ^ 1));
+                    for (int j = 0; j < VS_NCH; ++j) {
+                        const int ch = vs_chunk_of(j);
+                        if (t == 0) VS_WAIT(&S.bones_full[ch], it & 1, 1);            // the tile's first unit waits for the converted bones
+                        VS_WAIT(&S.t_empty[stage], phase ^ 1, 2);
                         tc_fence_after();
-                        const uint32_t d = tmem + VS_T_COL0 + (ch & 1) * VS_TN;
+                        const uint32_t d = tmem + VS_T_COL0 + stage * VS_TN;
                         const uint32_t a1 = b_lo0 + ((ch * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES) >> 4);
                         const uint32_t a2 = a1 + (VS_BONE_CHUNK_BYTES >> 4), a3 = a2 + (VS_BONE_CHUNK_BYTES >> 4);
                         // smallest products first, w1 a1 last: the tensor core TRUNCATES its fp32 accumulator at the running
@@ -259,39 +301,47 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                                 umma_f16_lohi<false>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
                             }
                         }
-                        tc_commit(smem_u32(&S.t_full[ch & 1]));
-                        // the next vertex tile's blend products, one stage per chunk (15 stages over 16 chunks)
-                        if (more && ch < VS_STAGES_PER_TILE) blend_stage(gt + 1, ch / TC_K_CHUNKS, ch % TC_K_CHUNKS);
+                        if (variant & 0x20000) mbar_arrive(smem_u32(&S.t_full[stage]));          // 0x20000: experiment (with 0x800): plain arrive
+                        else tc_commit(smem_u32(&S.t_full[stage]));
+                        if (t == VS_NT - 1) tc_commit(smem_u32(&S.bones_empty[ch]));        // the tile's last use of the chunk's bones
+                        if (++stage == VS_TSTAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(smem_u32(&S.w_empty[gt & 1]));
-                    if (t == VS_NT - 2) tc_commit(smem_u32(&S.feat_empty));        // blend products of the last vertex tile are issued
+                    tc_commit(smem_u32(&S.w_empty[g & 1]));
                 }
-                tc_commit(smem_u32(&S.bones_empty));
                 ++it;
             }
+            VS_PROF_STORE(1);
         }
     } else if (warp == 3) {
         // ===== bone operand: fp32 transforms bone_t[group][bone][hand % 32][12] -> fp16 x3 MN-major core matrices =====
         // The 12 elements of 4 consecutive hands of one bone are 48 contiguous floats = one K row (k = bone) of a chunk's
         // B operand, n = (hand % 4) * 12 + element: a lane converts 8 of them (one 16-byte n-group) into the three splits
         // a = a1 + a2 + a3 of 2^4 a.  [profiles/r2: written by the pose kernel as 96 scattered 16 / 8-byte stores per
-        // hand it cost that kernel +1.6 ms per 2^20 hands and 2.3 KB per hand of HBM traffic]
+        // hand it cost that kernel +1.6 ms per 2^20 hands and 2.3 KB per hand of HBM traffic.]  Chunks are handed over one by
+        // one (the previous tile's last unit frees them one by one), in the order the scheduler issues them, and the loads
+        // of the next chunk are in flight while this one is converted.
         const long long ngroups = ((long long)B + 31) >> 5;
         uint32_t it = 0;
-        VS_FOR_EACH_TILE {
-            vs_wait(&S.bones_empty, (it & 1) ^ 1);
-#pragma unroll 1
-            for (int ch = 0; ch < VS_NCH; ++ch) {
-                const long long group = (long long)tile * 2 + (ch >> 3);
-                const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + 48 * (ch & 7);
-                float4 v[3][2];
+        VS_PROF_DECL;
+        auto load_chunk = [&](int tile, int ch, float4 (&v)[3][2]) {
+            const long long group = (long long)tile * 2 + (ch >> 3);
+            const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + 48 * (ch & 7);
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {                          // 96 (bone, n-group) items per chunk: three per lane
-                    const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
-                    const float4* p = reinterpret_cast<const float4*>(src0 + (size_t)k * (BONE_F * 32) + 8 * g);
-                    if (group < ngroups) { v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); }
-                    else { v[r][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[r][1] = v[r][0]; }
-                }
+            for (int r = 0; r < 3; ++r) {                              // 96 (bone, n-group) items per chunk: three per lane
+                const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
+                const float4* p = reinterpret_cast<const float4*>(src0 + (size_t)k * (BONE_F * 32) + 8 * g);
+                if (group < ngroups) { v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); }
+                else { v[r][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[r][1] = v[r][0]; }
+            }
+        };
+        VS_FOR_EACH_TILE {
+            float4 v[3][2], vn[3][2];
+            load_chunk(tile, vs_chunk_of(0), v);
+#pragma unroll 1
+            for (int j = 0; j < VS_NCH; ++j) {
+                const int ch = vs_chunk_of(j);
+                if (j + 1 < VS_NCH) load_chunk(tile, vs_chunk_of(j + 1), vn);
+                VS_WAIT(&S.bones_empty[ch], (it & 1) ^ 1, 0);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
@@ -312,185 +362,119 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                         *reinterpret_cast<uint4*>(dst + sp * VS_BONE_CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
+                fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&S.bones_full[ch]));
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { v[r][0] = vn[r][0]; v[r][1] = vn[r][1]; }
             }
-            fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core's reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&S.bones_full));
             ++it;
         }
-    } else if (warp >= 12) {
-        // ===== store warps: result rows shared -> global as 16-byte vectors (every piece starts on a 32-byte boundary) =====
-        // [profiles/r2: as bulk (TMA) stores the kernel ran at the latency of cp.async.bulk.wait_group.read; as ONE warp copying
-        // every chunk in order the warp's own ~350 clk per chunk (wake-up, LDS, arrive — serial) capped the kernel: removing the
-        // ring took 0.74 of 1.83 ms off the skeleton.  Now four warps, each owning one slot of the ring: chunk oc -> warp oc % 4.]
-        const int sw = warp - 12;
-        uint32_t gt = 0;
-        VS_FOR_EACH_TILE {
-            const long long hand0 = (long long)tile * VS_NH;
-            for (int t = 0; t < VS_NT; ++t, ++gt) {
-                for (int ch = sw; ch < VS_NCH; ch += VS_OSTAGES) {
-                    const uint32_t ob = sw;                               // chunk counter gt * 16 + ch = sw (mod 4)
-                    if (variant & 0x2000) continue;                     // experiment: no result ring
-                    vs_wait(&S.out_full[ob], (ch >> 2) & 1);            // the slot's use count = 4 gt + ch / 4
-                    // carried floats of the previous vertex tile go in front of the results
-                    if (t >= 1) {
-                        const int hl = lane >> 3, i = lane & 7;
-                        if (i < vs_d(hl)) S.out[ob][hl][i] = S.carry[gt & 1][ch * VS_HC + hl][i];
-                    }
-                    __syncwarp();
-                    if (t >= 1 && t < VS_NT - 1) {
-                        // 4 rows x 1536 B = 4 x 96 float4: three per lane per row, all loads first
-                        float4 v[VS_HC][3];
-#pragma unroll
-                        for (int hl = 0; hl < VS_HC; ++hl) {
-                            const float4* src = reinterpret_cast<const float4*>(&S.out[ob][hl][0]);
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) v[hl][k] = src[lane + 32 * k];
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&S.out_empty[ob]));        // the rows are in registers
-#pragma unroll
-                        for (int hl = 0; hl < VS_HC; ++hl) {
-                            const long long hand = hand0 + ch * VS_HC + hl;
-                            if (hand < B && !(variant & 0x100)) {                     // 0x100: experiment, no global stores
-                                float4* dst = reinterpret_cast<float4*>(verts + (size_t)hand * NVC + 3 * VS_M * t - vs_d(hl));
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) __stcs(dst + lane + 32 * k, v[hl][k]);
-                            }
-                        }
-                    } else {
-                        // tile 0: the row's first floats up to its first 32-byte boundary are plain stores, the rest vectors;
-                        // the short last tile (10 vertices + carry): plain stores
-                        for (int hl = 0; hl < VS_HC; ++hl) {
-                            const long long hand = hand0 + ch * VS_HC + hl;
-                            if (hand >= B) break;
-                            const int d = vs_d(hl);
-                            float* grow = verts + (size_t)hand * NVC;
-                            const float* row = S.out[ob][hl];
-                            if (t == 0) {
-                                const int a = (8 - d) & 7, sh = vs_shift(0, hl);
-                                if (lane < a) grow[lane] = row[sh + lane];
-                                const float4* src = reinterpret_cast<const float4*>(row + sh + a);
-                                float4* dst = reinterpret_cast<float4*>(grow + a);
-                                const int n16 = (3 * VS_M - d - a) / 4;                 // 94 or 96
-                                for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
-                            } else {
-                                const int n = NVC - (VS_NT - 1) * 3 * VS_M + d;          // 30 + d floats
-                                for (int i = lane; i < n; i += 32) grow[(VS_NT - 1) * 3 * VS_M - d + i] = row[i];
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&S.out_empty[ob]));
-                    }
-                }
-            }
-        }
+        if (lane == 0) VS_PROF_STORE(3);
     } else if (warp >= 4) {
-        // ===== epilogue: thread = vertex; warps 4-7 take the even chunks of a tile, warps 8-11 the odd ones =====
-        // [profiles/r2: with all eight warps on every chunk (two hands each) a chunk took ~1 500 clk — three mbarrier round
-        // trips, five TMEM loads and their wait per 2 hands of work, serial in every warp — and the tensor pipe sat at 14 %.
-        // Now a warp does all four hands of every other chunk: half the synchronisation per hand, and the other set's
-        // round hides it.]
+        // ===== epilogue: thread = vertex; the warp set owns 32 hands of the tile, whose rest coordinates it keeps in registers =====
+        // [profiles/r2: (a) two rest-position stages + two transform stages in TMEM: a warp set had ONE chunk in flight, and the
+        // scheduler -> tensor pipe -> epilogue -> scheduler round trip (~1 000 clk) was exposed on every chunk; (b) the result rows
+        // went through a 4-slot ring to four store warps: +300 clk per chunk of handshakes.  Now the rest positions leave TMEM at
+        // once (96 registers), which buys six transform stages, and a warp stores its own 384-byte runs.]
         const int q = warp & 3, set = (warp - 4) >> 2;
         const int vl = q * 32 + lane;                                  // vertex inside the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const float osv = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
         const float ost = exp2f(-(float)(VS_W_SCALE_LOG2 + VS_BONE_SCALE_LOG2));
-        uint32_t gt = 0, rounds = 0;                                   // rounds: chunks this set has taken (its transform stage's phase)
+        float* stg = &S.out[warp - 4][0][0];
+        uint32_t g = 0;                                                // unit counter
+        uint32_t tcnt = set;                                           // this set's next chunk counter (issue order, all units)
+        VS_PROF_DECL;
         VS_FOR_EACH_TILE {
-            const long long hand0 = (long long)tile * VS_NH;
-            for (int t = 0; t < VS_NT; ++t, ++gt) {
+            const long long hand0 = (long long)tile * VS_NH + set * VS_HS;
+            for (int t = 0; t < VS_NT; ++t, ++g) {
                 const int vtx = t * VS_M + vl;
                 const bool valid = vtx < NV;
                 const float4 tm = vs_tmpl[vtx];
                 int tipslot = -1;
 #pragma unroll
                 for (int i = 0; i < 5; ++i) if (vtx == c_vs_tip_vert[i]) tipslot = c_vs_tip_slot[i];
-                const bool carries = valid && t + 1 < VS_NT && vl >= VS_M - 2;
-                const uint32_t vp_addr = tmem + lane_addr + (gt & 1) * VS_VP_COLS;
-                vs_wait(&S.vp_full[gt & 1], (gt >> 1) & 1);
-                tc_fence_after();
+                // ---- rest positions of this thread's vertex for the set's 32 hands: TMEM -> registers, stage released
+                float X[VS_HS], Y[VS_HS], Z[VS_HS];
+                {
+                    uint32_t rx[VS_HS], ry[VS_HS], rz[VS_HS];
+                    VS_WAIT(&S.vp_full, g & 1, 0);
+                    tc_fence_after();
+                    VS_TIC;
+                    const uint32_t vp_addr = tmem + lane_addr + set * VS_HS;
+                    tmem_ld32_nowait(vp_addr, rx);
+                    tmem_ld32_nowait(vp_addr + VS_NH, ry);
+                    tmem_ld32_nowait(vp_addr + 2 * VS_NH, rz);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&S.vp_empty));
+#pragma unroll
+                    for (int i = 0; i < VS_HS; ++i) {
+                        X[i] = fmaf(__uint_as_float(rx[i]), osv, tm.x);
+                        Y[i] = fmaf(__uint_as_float(ry[i]), osv, tm.y);
+                        Z[i] = fmaf(__uint_as_float(rz[i]), osv, tm.z);
+                    }
+                    VS_TOC(5);
+                }
                 if (v_posed_t != nullptr) {
-                    // rest-pose scratch for the skinning backward: v_posed_t[group][3 pos + p][32 hands], this warp's 32 hands
+                    // rest-pose scratch for the skinning backward: v_posed_t[group][3 pos + p][32 hands], this set's 32 hands
                     const long long group = (long long)tile * 2 + set;
                     const int pos3 = __float_as_int(tm.w);
-                    const bool live = valid && pos3 >= 0 && group * 32 < B;
-#pragma unroll 1
-                    for (int p = 0; p < 3; ++p) {
-                        uint32_t r[32];
-                        tmem_ld32_nowait(vp_addr + p * VS_NH + set * 32, r);
-                        tmem_ld_wait();
-                        if (live) {
-                            const float tp = p == 0 ? tm.x : (p == 1 ? tm.y : tm.z);
-                            float4* dst = reinterpret_cast<float4*>(v_posed_t + ((size_t)group * SK_NCOORD + pos3 + p) * 32);
+                    if (valid && pos3 >= 0 && group * 32 < B) {
+                        float4* dst = reinterpret_cast<float4*>(v_posed_t + ((size_t)group * SK_NCOORD + pos3) * 32);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                __stcs(dst + i, make_float4(fmaf(__uint_as_float(r[4 * i]), osv, tp), fmaf(__uint_as_float(r[4 * i + 1]), osv, tp),
-                                                            fmaf(__uint_as_float(r[4 * i + 2]), osv, tp), fmaf(__uint_as_float(r[4 * i + 3]), osv, tp)));
+                        for (int i = 0; i < 8; ++i) {
+                            __stcs(dst + i, make_float4(X[4 * i], X[4 * i + 1], X[4 * i + 2], X[4 * i + 3]));
+                            __stcs(dst + 8 + i, make_float4(Y[4 * i], Y[4 * i + 1], Y[4 * i + 2], Y[4 * i + 3]));
+                            __stcs(dst + 16 + i, make_float4(Z[4 * i], Z[4 * i + 1], Z[4 * i + 2], Z[4 * i + 3]));
                         }
                     }
                 }
-#pragma unroll 1
-                for (int ch = set; ch < VS_NCH; ch += 2, ++rounds) {
-                    vs_wait(&S.t_full[set], rounds & 1);
+                // this warp's run of a hand's row: floats [3 (128 t + 32 q), + 96) of verts[hand]; 16-byte aligned for even hands
+                const int nfl = min(96, max(0, (NV - (t * VS_M + q * 32)) * 3));           // 96, or 30 / 0 in the last tile
+                float* run0 = verts + (size_t)hand0 * NVC + 3 * (t * VS_M + q * 32);
+#pragma unroll
+                for (int c8 = 0; c8 < VS_NCH / 2; ++c8, tcnt += 2) {
+                    const uint32_t stage = tcnt % VS_TSTAGES, use = tcnt / VS_TSTAGES;
+                    VS_WAIT(&S.t_full[stage], use & 1, 1);
                     tc_fence_after();
-                    const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + set * VS_TN;
-                    uint32_t T[VS_TN], X[VS_HC], Y[VS_HC], Z[VS_HC];
-                    const uint32_t x_addr = vp_addr + ch * VS_HC;
-                    if (!(variant & 0x1000)) {                          // 0x1000: experiment, no TMEM loads
-                        tmem_ld32_nowait(t_addr, T);
-                        tmem_ld16_nowait(t_addr + 32, T + 32);
-                        tmem_ld4_nowait(x_addr, X);
-                        tmem_ld4_nowait(x_addr + VS_NH, Y);
-                        tmem_ld4_nowait(x_addr + 2 * VS_NH, Z);
-                        tmem_ld_wait();
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < VS_TN; ++i) T[i] = i;
-#pragma unroll
-                        for (int i = 0; i < VS_HC; ++i) X[i] = Y[i] = Z[i] = i;
-                    }
+                    VS_TIC;
+                    const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + stage * VS_TN;
+                    uint32_t T[VS_TN];
+                    tmem_ld32_nowait(t_addr, T);
+                    tmem_ld16_nowait(t_addr + 32, T + 32);
+                    tmem_ld_wait();
                     tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[set]));
-                    // result rows of chunk oc = (chunks so far) -> ring slot; the set's slots alternate {set, set + 2}
-                    const uint32_t oc = gt * VS_NCH + ch;
-                    const uint32_t ob = oc % VS_OSTAGES;
-                    if (variant & 0x2000) continue;                     // 0x2000: experiment, no result ring
-                    vs_wait(&S.out_empty[ob], ((oc / VS_OSTAGES) & 1) ^ 1);
+                    __syncwarp();                                      // also: every lane is done reading the previous chunk's rows
+                    if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[stage]));
+                    VS_TOC(2);
+                    if (variant & 0x200) continue;                     // 0x200: experiment, handshakes only
+                    long long _tic2 = 0;
+#ifdef VS_PROFILE
+                    _tic2 = clock64();
+#endif
 #pragma unroll
                     for (int hl = 0; hl < VS_HC; ++hl) {
-                        if (variant & 0x200) break;                                 // 0x200: experiment, handshakes only
-                        const float x = fmaf(__uint_as_float(X[hl]), osv, tm.x);
-                        const float y = fmaf(__uint_as_float(Y[hl]), osv, tm.y);
-                        const float z = fmaf(__uint_as_float(Z[hl]), osv, tm.z);
+                        const int hi = c8 * VS_HC + hl;                // hand inside the set
+                        const float x = X[hi], y = Y[hi], z = Z[hi];
                         float o[3];
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
                             const float* Ti = reinterpret_cast<const float*>(T) + hl * 12 + 4 * i;
                             o[i] = ost * fmaf(Ti[0], x, fmaf(Ti[1], y, fmaf(Ti[2], z, Ti[3])));
                         }
-                        if (dbg != nullptr && tile == 0 && t == 0 && ch == 0) {
+                        if (dbg != nullptr && tile == 0 && t == 0 && set == 0 && c8 == 0) {
                             float* dd = dbg + ((size_t)hl * VS_M + vl) * 16;
 #pragma unroll
                             for (int i = 0; i < 12; ++i) dd[i] = ost * __uint_as_float(T[hl * 12 + i]);
                             dd[12] = x; dd[13] = y; dd[14] = z; dd[15] = 0.f;
                         }
-                        if (valid) {
-                            float* row = S.out[ob][hl] + vs_shift(t, hl) + 3 * vl;
-                            row[0] = o[0]; row[1] = o[1]; row[2] = o[2];
-                        }
-                        if (carries) {
-                            // the last d floats of this tile's piece open the next tile's piece
-                            const int d = vs_d(hl);
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const int j = 3 * vl + i - (3 * VS_M - d);
-                                if (j >= 0) S.carry[(gt + 1) & 1][ch * VS_HC + hl][j] = o[i];
-                            }
-                        }
+                        float* row = stg + hl * VS_ROWF + 3 * lane;
+                        row[0] = o[0]; row[1] = o[1]; row[2] = o[2];
                         if (tipslot >= 0 && valid) {
-                            const long long hand = hand0 + ch * VS_HC + hl;
+                            const long long hand = hand0 + hi;
                             if (hand < B) {
                                 float* jo = joints + (size_t)hand * (NOUTJ * 3) + tipslot * 3;
                                 jo[0] = o[0]; jo[1] = o[1]; jo[2] = o[2];
@@ -498,13 +482,42 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&S.out_full[ob]));
+#ifdef VS_PROFILE
+                    prof[3] += clock64() - _tic2; _tic2 = clock64();
+#endif
+                    if (variant & 0x100) continue;                     // 0x100: experiment, no global stores
+                    // ---- the four rows leave as this warp's own contiguous runs (neighbouring warps / tiles complete the
+                    // 32-byte sectors at the ends of a run in L2)
+#pragma unroll
+                    for (int hl = 0; hl < VS_HC; ++hl) {
+                        const long long hand = hand0 + c8 * VS_HC + hl;
+                        if (hand >= B) break;
+                        float* dst = run0 + (size_t)(c8 * VS_HC + hl) * NVC;
+                        const float* row = stg + hl * VS_ROWF;
+                        if ((variant & 2) && nfl == 96 && (t | q) != 0) {          // 2: TIMING experiment (wrong bytes): sector-aligned runs
+                            dst -= (8 - 2 * hl) & 7;
+                            if (lane < 24) __stcs(reinterpret_cast<float4*>(dst) + lane, reinterpret_cast<const float4*>(row)[lane]);
+                            continue;
+                        }
+                        if (nfl == 96) {
+                            if ((hl & 1) == 0) {                       // even hand: 16-byte aligned run, 24 vectors
+                                if (lane < 24) __stcs(reinterpret_cast<float4*>(dst) + lane, reinterpret_cast<const float4*>(row)[lane]);
+                            } else {                                   // odd hand: 8-byte aligned, 48 pairs
+                                __stcs(reinterpret_cast<float2*>(dst) + lane, reinterpret_cast<const float2*>(row)[lane]);
+                                if (lane < 16) __stcs(reinterpret_cast<float2*>(dst) + 32 + lane, reinterpret_cast<const float2*>(row)[32 + lane]);
+                            }
+                        } else {
+                            for (int i = lane; i < nfl; i += 32) dst[i] = row[i];
+                        }
+                    }
+#ifdef VS_PROFILE
+                    prof[4] += clock64() - _tic2;
+#endif
+                    (void)_tic2;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&S.vp_empty[gt & 1]));
             }
         }
+        if (lane == 0) VS_PROF_STORE(warp);
     }
 #undef VS_FOR_EACH_TILE
     tc_fence_before();
@@ -577,6 +590,7 @@ void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, 
 int launch_vskin_forward(const void* blob, const unsigned char* featp, const float* bone_t, int B, int mode,
                          float* verts, float* joints, float* v_posed_t, float* dbg, int variant, cudaStream_t s) {
     if (B <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(verts) & 15) != 0) return MB_E_ALIGN;           // a warp stores its runs as 16-byte vectors
     static SmemAttrOnce once;
     const size_t smem = sizeof(VsShared) + 128;
     if (int arc = ensure_dyn_smem(once, vskin_forward_kernel, smem)) return arc;

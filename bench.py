@@ -513,7 +513,17 @@ def bind_numa_local(gpu_index):
         allowed = os.sched_getaffinity(0)
         use = (cpus & allowed) or allowed
         os.sched_setaffinity(0, use)
-        return {"numa_node": node, "cpus": len(use)}
+        # ... and ask for this process's new pages on that node even when the container's cpuset holds none of its cores
+        # (set_mempolicy(MPOL_PREFERRED); x86-64 syscall 238, best effort)
+        mem = None
+        try:
+            import ctypes
+
+            mask = ctypes.c_ulong(1 << node)
+            mem = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+        except Exception:
+            pass
+        return {"numa_node": node, "cpus": len(use), "node_cpus_in_cpuset": len(cpus & allowed), "set_mempolicy_rc": mem}
     except Exception:
         return None
 
@@ -878,7 +888,7 @@ def main():
             st.clear()
         sets.clear()
         torch.cuda.empty_cache()
-        bind_numa_local(local_rank)                           # pinned buffers are first-touched on the GPU's NUMA node
+        numa = bind_numa_local(local_rank)                    # pinned buffers are first-touched on the GPU's NUMA node
         # ONE pinned buffer each way per step, laid out chunk by chunk as [rot | pose | beta] blocks so that a chunk is one
         # contiguous host range: one H2D and one D2H copy per chunk (round 1 issued three each, from three arrays)
         n_chunks = int(os.environ.get("MANO_B200_E2E_CHUNKS", "4")) if H >= 8 * 4096 else 1
@@ -939,8 +949,38 @@ def main():
         e1.record()
         sync_all()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+
+        # the host side alone: the same pinned ranges over the same streams, no kernels — what the box's PCIe / host memory
+        # path allows with `world` ranks copying at once (the ceiling of the e2e arm when it is below `value`)
+        d_flat = torch.empty(H * 58, dtype=torch.float32, device=dev)
+
+        def copy_step():
+            for c, (a, b, o) in enumerate(bounds):
+                n = b - a
+                with torch.cuda.stream(side[c % len(side)]):
+                    d_flat[o:o + n * 58].copy_(h_in[o:o + n * 58], non_blocking=True)
+                    h_out2[0][o:o + n * 58].copy_(d_flat[o:o + n * 58], non_blocking=True)
+
+        copy_step()
+        join_side()
+        sync_all()
+        e0.record()
+        for _ in range(5):
+            copy_step()
+        join_side()
+        e1.record()
+        sync_all()
+        ms_copy = max_over_ranks(e0.elapsed_time(e1)) / 5
+        numa_all = [numa]
+        if world > 1:
+            numa_all = [None] * world
+            dist.all_gather_object(numa_all, numa)
         e2e = {"value": world * H / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * 58 * 4,
                "d2h_bytes_per_step": H * 58 * 4 + 4, "ms_per_step": ms_e2e, "steps": n_e2e,
+               "copy_only": {"ms_per_step": ms_copy, "gb_per_s_per_gpu_each_way": H * 58 * 4 / (ms_copy * 1e-3) / 1e9,
+                             "note": "the same H2D + D2H copies with no kernels, all ranks at once (max over ranks): the host-side "
+                                     "ceiling of this arm"},
+               "numa": numa_all,
                "api": "ManoLayer.forward + autograd backward; ONE pinned host buffer in (rot | pose | beta per chunk) and one out "
                       f"(58 gradient floats per hand); {n_chunks} chunks over {len(side)} CUDA streams, one H2D + one D2H copy per chunk, "
                       "steps pipelined per stream (alternating pinned result buffers); verts / joints and their upstream gradients "
