@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 blend_tc_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ basis_tc,
                         const float* __restrict__ tmpl, const unsigned char* __restrict__ featp,
                         float* __restrict__ v_posed_t, int B, int m_tiles, int products) {
-    extern __shared__ unsigned char smem_raw[];
-    TcShared& S = *reinterpret_cast<TcShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // declared with its alignment and used WITHOUT integer arithmetic on the address: rounding the pointer up through uintptr_t
+    // made the compiler lose the shared address space — every access became a generic LD / ST [profiles/r2]
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
     const float out_scale = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -206,8 +208,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 blend_tc_forward_mres_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ basis_tc,
                              const float* __restrict__ tmpl, const unsigned char* __restrict__ featp,
                              float* __restrict__ v_posed_t, int B, int m_tiles, int products) {
-    extern __shared__ unsigned char smem_raw[];
-    TcSharedM& S = *reinterpret_cast<TcSharedM*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // declared with its alignment and used WITHOUT integer arithmetic on the address: rounding the pointer up through uintptr_t
+    // made the compiler lose the shared address space — every access became a generic LD / ST [profiles/r2]
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSharedM& S = *reinterpret_cast<TcSharedM*>(smem_raw);
     const float out_scale = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -367,8 +371,10 @@ struct TcBwdShared {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 blend_tc_backward_kernel(const unsigned char* __restrict__ basis_bw, const unsigned char* __restrict__ dvp,
                          float* __restrict__ dfeat, int B, int m_tiles, int hand_minor, int ksplit, size_t part_stride) {
-    extern __shared__ unsigned char smem_raw[];
-    TcBwdShared& S = *reinterpret_cast<TcBwdShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // declared with its alignment and used WITHOUT integer arithmetic on the address: rounding the pointer up through uintptr_t
+    // made the compiler lose the shared address space — every access became a generic LD / ST [profiles/r2]
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcBwdShared& S = *reinterpret_cast<TcBwdShared*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work item w = (pass p = w / ksplit, K range w % ksplit): small batches cut the K loop so that every SM has a
     // range; range r accumulates chunks [74 r / ksplit, 74 (r + 1) / ksplit) into its own dfeat copy

@@ -47,7 +47,6 @@ constexpr int VS_EPI_WARPS = 8;
 constexpr int VS_ASTAGES = 5;                     // basis ring: 5 x 16 KB (the stream is latency-bound: bytes in flight / ~1 900 clk)
 constexpr int VS_TSTAGES = 6;                     // transform ring: chunk counter mod 6; even counters -> warp set 0, odd -> set 1
 constexpr int VS_HS = VS_NH / 2;                  // 32 hands per epilogue warp set
-constexpr int VS_ROWF = 100;                      // floats per staging row: 96 results of a warp's 32 vertices + pad (16-byte multiple)
 constexpr uint32_t VS_TMEM_COLS = 512;
 constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns: the rest positions of a unit
 constexpr uint32_t VS_T_COL0 = VS_VP_COLS;         // 192: first transform column
@@ -63,7 +62,6 @@ struct VsShared {
     alignas(128) unsigned char bones[VS_NCH][VS_BONE_SPLITS][VS_BONE_CHUNK_BYTES]; // 72 KB
     alignas(128) unsigned char a[VS_ASTAGES][VS_A_STAGE_BYTES];                    // 64 KB basis ring
     alignas(128) unsigned char w[2][VS_W_TILE_BYTES];                              // 16 KB weight tiles
-    alignas(16) float out[VS_EPI_WARPS][VS_HC][VS_ROWF];                           // 12.5 KB: a chunk's result rows, private to a warp
     alignas(8) unsigned long long a_full[VS_ASTAGES], a_empty[VS_ASTAGES];
     unsigned long long w_full[2], w_empty[2];
     unsigned long long feat_full, feat_empty;
@@ -111,6 +109,9 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                      int B, int ntiles, int blend_products, int t_products,
                      float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ v_posed_t,
                      float* __restrict__ dbg, int variant) {
+    // [profiles/r2: rounding the base up through uintptr_t hides the shared address space from the compiler — every access of
+    // this kernel is a generic LD / ST.  Declared `__align__(1024)` and used directly (LDS / STS, as blend_tc.cu now does) this
+    // kernel measured SLOWER (1.78 against 1.63 ms per 262 144 hands, twice), so the generic form stays here.]
     extern __shared__ unsigned char smem_raw[];
     VsShared& S = *reinterpret_cast<VsShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,13 +377,12 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
         // [profiles/r2: (a) two rest-position stages + two transform stages in TMEM: a warp set had ONE chunk in flight, and the
         // scheduler -> tensor pipe -> epilogue -> scheduler round trip (~1 000 clk) was exposed on every chunk; (b) the result rows
         // went through a 4-slot ring to four store warps: +300 clk per chunk of handshakes.  Now the rest positions leave TMEM at
-        // once (96 registers), which buys six transform stages, and a warp stores its own 384-byte runs.]
+        // once (96 registers), which buys six transform stages, and a thread stores its own results.]
         const int q = warp & 3, set = (warp - 4) >> 2;
         const int vl = q * 32 + lane;                                  // vertex inside the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const float osv = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
         const float ost = exp2f(-(float)(VS_W_SCALE_LOG2 + VS_BONE_SCALE_LOG2));
-        float* stg = &S.out[warp - 4][0][0];
         uint32_t g = 0;                                                // unit counter
         uint32_t tcnt = set;                                           // this set's next chunk counter (issue order, all units)
         VS_PROF_DECL;
@@ -447,7 +447,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     tmem_ld16_nowait(t_addr + 32, T + 32);
                     tmem_ld_wait();
                     tc_fence_before();
-                    __syncwarp();                                      // also: every lane is done reading the previous chunk's rows
+                    __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[stage]));
                     VS_TOC(2);
                     if (variant & 0x200) continue;                     // 0x200: experiment, handshakes only
@@ -471,8 +471,18 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                             for (int i = 0; i < 12; ++i) dd[i] = ost * __uint_as_float(T[hl * 12 + i]);
                             dd[12] = x; dd[13] = y; dd[14] = z; dd[15] = 0.f;
                         }
-                        float* row = stg + hl * VS_ROWF + 3 * lane;
-                        row[0] = o[0]; row[1] = o[1]; row[2] = o[2];
+                        // results leave straight from the registers: 3 x 4-byte stores per hand, a warp instruction covering a
+                        // 384-byte run at a 12-byte lane stride — the three of them complete every 32-byte sector back to back
+                        // in L2.  [profiles/r2: staged through shared memory into 16-byte vector stores (3 STS + LDS.128 + STG.128
+                        // per hand, 57 M of the kernel's 170 M shared-memory wavefronts) the kernel took 1.63 instead of 1.53 ms
+                        // per 262 144 hands: the shared-memory pipe, 75 % busy, is what the MMAs' operand reads wait for.]
+                        {
+                            const long long hand = hand0 + hi;
+                            if (hand < B && 3 * lane < nfl && !(variant & 0x100)) {      // 0x100: experiment, no global stores
+                                float* dst = run0 + (size_t)hi * NVC + 3 * lane;
+                                __stcs(dst, o[0]); __stcs(dst + 1, o[1]); __stcs(dst + 2, o[2]);
+                            }
+                        }
                         if (tipslot >= 0 && valid) {
                             const long long hand = hand0 + hi;
                             if (hand < B) {
@@ -481,37 +491,8 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                             }
                         }
                     }
-                    __syncwarp();
 #ifdef VS_PROFILE
-                    prof[3] += clock64() - _tic2; _tic2 = clock64();
-#endif
-                    if (variant & 0x100) continue;                     // 0x100: experiment, no global stores
-                    // ---- the four rows leave as this warp's own contiguous runs (neighbouring warps / tiles complete the
-                    // 32-byte sectors at the ends of a run in L2)
-#pragma unroll
-                    for (int hl = 0; hl < VS_HC; ++hl) {
-                        const long long hand = hand0 + c8 * VS_HC + hl;
-                        if (hand >= B) break;
-                        float* dst = run0 + (size_t)(c8 * VS_HC + hl) * NVC;
-                        const float* row = stg + hl * VS_ROWF;
-                        if ((variant & 2) && nfl == 96 && (t | q) != 0) {          // 2: TIMING experiment (wrong bytes): sector-aligned runs
-                            dst -= (8 - 2 * hl) & 7;
-                            if (lane < 24) __stcs(reinterpret_cast<float4*>(dst) + lane, reinterpret_cast<const float4*>(row)[lane]);
-                            continue;
-                        }
-                        if (nfl == 96) {
-                            if ((hl & 1) == 0) {                       // even hand: 16-byte aligned run, 24 vectors
-                                if (lane < 24) __stcs(reinterpret_cast<float4*>(dst) + lane, reinterpret_cast<const float4*>(row)[lane]);
-                            } else {                                   // odd hand: 8-byte aligned, 48 pairs
-                                __stcs(reinterpret_cast<float2*>(dst) + lane, reinterpret_cast<const float2*>(row)[lane]);
-                                if (lane < 16) __stcs(reinterpret_cast<float2*>(dst) + 32 + lane, reinterpret_cast<const float2*>(row)[32 + lane]);
-                            }
-                        } else {
-                            for (int i = lane; i < nfl; i += 32) dst[i] = row[i];
-                        }
-                    }
-#ifdef VS_PROFILE
-                    prof[4] += clock64() - _tic2;
+                    prof[3] += clock64() - _tic2;
 #endif
                     (void)_tic2;
                 }
@@ -590,7 +571,6 @@ void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, 
 int launch_vskin_forward(const void* blob, const unsigned char* featp, const float* bone_t, int B, int mode,
                          float* verts, float* joints, float* v_posed_t, float* dbg, int variant, cudaStream_t s) {
     if (B <= 0) return 0;
-    if ((reinterpret_cast<uintptr_t>(verts) & 15) != 0) return MB_E_ALIGN;           // a warp stores its runs as 16-byte vectors
     static SmemAttrOnce once;
     const size_t smem = sizeof(VsShared) + 128;
     if (int arc = ensure_dyn_smem(once, vskin_forward_kernel, smem)) return arc;
