@@ -258,7 +258,10 @@ static int fused_forward(const void* blob, int nc, const float* rot, const float
     int rc;
     { StageTimer t(ST_POSE_FWD, s); if ((rc = launch_pose_forward_lh(blob, nc, rot, coeffs, betas, B, nullptr, featp, bone_t, joints, s))) return rc; }
     StageTimer t(ST_FUSED_FWD, s);
-    return launch_vskin_forward(blob, featp, bone_t, B, mode, verts, joints, v_posed_t, dbg, variant, s);
+    // the bone operand images (1 152 B per hand) live in the backward's dv_posed tile region, which no forward kernel uses
+    static_assert(VS_BONE_TILE_BYTES / VS_NH <= 74 * 16384 / 128, "bone operand images must fit the dv_posed tile region");
+    unsigned char* bones_op = reinterpret_cast<unsigned char*>(ws + W.dvp);
+    return launch_vskin_forward(blob, featp, bone_t, bones_op, B, mode, verts, joints, v_posed_t, dbg, variant, s);
 }
 
 extern "C" int mb_mano_forward_debug(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,

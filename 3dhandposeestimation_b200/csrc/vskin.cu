@@ -17,13 +17,13 @@
 // verts[B][778][3] in its natural layout — no transposition, no v_posed_t round trip.
 //
 // Roles (384 threads, 1 CTA per SM, persistent over 64-hand tiles; a UNIT is one (hand tile, vertex tile) pair):
-//   warp 0   blend issuer + basis producer (one thread): (tile, plane, K chunk) stages of 16 KB, always L2 hits, 4-slot ring,
-//            multicast inside a cluster; the blend products of unit u + 1 run while the epilogue works on unit u
+//   warp 0   blend issuer (one thread): the blend products of unit u + 1 run while the epilogue works on unit u
 //   warp 1   transform issuer (one thread): T = W A of unit u, 4 hands per chunk
-//   warp 2   TMEM allocation; producer of the hand tile's feature rows (40 KB) and of the weight tiles (8 KB per vertex tile,
-//            double buffered)
-//   warp 3   converts the hand tile's fp32 bone transforms (48 KB, straight from the pose stage's bone_t) into the
-//            transform products' fp16 x3 B operand in shared memory (72 KB), chunk by chunk behind per-chunk barriers
+//   warp 2   TMEM allocation; basis producer (one thread): (tile, plane, K chunk) stages of 16 KB, always L2 hits, multicast
+//            inside a cluster
+//   warp 3   producer of the slower streams (one polling thread): the hand tile's feature rows (40 KB), the weight tiles (8 KB per
+//            vertex tile, double buffered) and the transform products' fp16 x3 bone operand (72 KB per hand tile, written by
+//            vs_bones_operand_kernel from the pose stage's fp32 transforms), chunk by chunk behind per-chunk barriers
 //   warps 4-11  epilogue: warp % 4 = TMEM lane quarter (32 vertices); warps 4-7 own hands 0-31 of the tile, 8-11 hands 32-63
 // TMEM (512 columns): ONE rest-position stage of 3 x 64 columns — every epilogue thread copies its 3 x 32 rest coordinates
 // into registers at the start of a unit and frees the stage for the next unit's blend products at once — and a ring of
@@ -44,7 +44,7 @@ namespace {
 
 constexpr int VS_THREADS = 384;                   // 12 warps: see the role list above
 constexpr int VS_EPI_WARPS = 8;
-constexpr int VS_ASTAGES = 5;                     // basis ring: 5 x 16 KB (the stream is latency-bound: bytes in flight / ~1 900 clk)
+constexpr int VS_ASTAGES = 6;                     // basis ring: 6 x 16 KB (the stream is latency-bound: bytes in flight over ~2 000 clk)
 constexpr int VS_TSTAGES = 6;                     // transform ring: chunk counter mod 6; even counters -> warp set 0, odd -> set 1
 constexpr int VS_HS = VS_NH / 2;                  // 32 hands per epilogue warp set
 constexpr uint32_t VS_TMEM_COLS = 512;
@@ -102,10 +102,52 @@ __device__ __forceinline__ void vs_wait(unsigned long long* bar, uint32_t parity
 // epilogue warp sets (hands 0-31, 32-63) are served alternately
 __device__ __forceinline__ int vs_chunk_of(int j) { return (j >> 1) + (VS_NCH / 2) * (j & 1); }
 
+// ---- bone operand images: fp32 transforms bone_t[group][bone][hand % 32][12] -> fp16 x3 MN-major core matrices, per 4-hand chunk
+// [hand tile][chunk 16][split 3][1536 B: 6 n-groups x 2 k-groups x 8 k x 8 n].  The 12 elements of 4 consecutive hands of one bone
+// are 48 contiguous floats = one K row (k = bone) of a chunk's B operand, n = (hand % 4) * 12 + element: a lane converts 8 of
+// them (one 16-byte n-group) into the three splits a = a1 + a2 + a3 of 2^4 a; one warp per chunk.
+__global__ void __launch_bounds__(256)
+vs_bones_operand_kernel(const float* __restrict__ bone_t, int B, long long nchunks, unsigned char* __restrict__ bones_op) {
+    const int lane = threadIdx.x & 31;
+    const long long ngroups = ((long long)B + 31) >> 5;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long cidx = warp0; cidx < nchunks; cidx += nwarps) {
+        const long long group = cidx >> 3;                              // 8 chunks of 4 hands per 32-hand group
+        const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + 48 * (int)(cidx & 7);
+        unsigned char* out = bones_op + (size_t)cidx * (VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {                                  // 96 (bone, n-group) items per chunk: three per lane
+            const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (group < ngroups) {
+                const float4* p = reinterpret_cast<const float4*>(src0 + (size_t)k * (BONE_F * 32) + 8 * g);
+                v0 = __ldcs(p); v1 = __ldcs(p + 1);
+            }
+            float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] *= (float)(1 << VS_BONE_SCALE_LOG2);
+            unsigned char* dst = out + g * 256 + (k >> 3) * 128 + (k & 7) * 16;
+#pragma unroll
+            for (int sp = 0; sp < VS_BONE_SPLITS; ++sp) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const __half2 h = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+                    const float2 f = __half22float2(h);
+                    x[2 * e] -= f.x;
+                    x[2 * e + 1] -= f.y;
+                    pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(dst + sp * VS_BONE_CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(VS_THREADS, 1)
 vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* __restrict__ vs_basis,
                      const unsigned char* __restrict__ vs_w, const float4* __restrict__ vs_tmpl,
-                     const unsigned char* __restrict__ featp, const float* __restrict__ bone_t,
+                     const unsigned char* __restrict__ featp, const unsigned char* __restrict__ bones_op,
                      int B, int ntiles, int blend_products, int t_products,
                      float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ v_posed_t,
                      float* __restrict__ dbg, int variant) {
@@ -199,62 +241,31 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
         }
     } else if (warp == 2) {
         if (elect_one()) {
-            // ===== producer of all bulk copies: basis ring, per-hand-tile feature rows, weight tiles (one polling thread) =====
+            // ===== basis producer (one thread, blocking waits: this stream is the one the blend issuer waits for) =====
             // The basis is the same 105-stage stream for every hand tile, kept in L2 (evict-last) and, inside a cluster, loaded
             // once and multicast.
-            const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
+            const uint64_t keep = l2_policy_evict_last();
             const uint32_t slice = VS_A_STAGE_BYTES / csize;           // this CTA's share of every basis stage
             constexpr uint32_t NS = VS_ASTAGES;
             int n_it = 0;
             VS_FOR_EACH_TILE { (void)tile; ++n_it; }
-            const uint32_t total_a = (uint32_t)n_it * (VS_NT * VS_STAGES_PER_TILE), total_w = (uint32_t)n_it * VS_NT;
-            uint32_t na = 0, nw = 0;                                   // basis stages / weight tiles requested so far
-            int fit = 0;                                                // feature tiles requested so far
-            int rnd = cluster_id;                                       // round of the next feature tile
+            const uint32_t total_a = (uint32_t)n_it * (VS_NT * VS_STAGES_PER_TILE);
             VS_PROF_DECL;
-            long long idle_since = -1;
-            while (na < total_a || nw < total_w || fit < n_it) {
-                bool progressed = false;
-                // basis stage na -> slot na % 5: free once the MMAs of stage na - 5 are done
-                if (na < total_a && (na < NS || mbar_test_wait(smem_u32(&S.a_empty[na % NS]), ((na / NS) & 1) ^ 1))) {
-                    const uint32_t slot = na % NS;
-                    const uint32_t i = na % (VS_NT * VS_STAGES_PER_TILE);
-                    if (variant & 0x8000) mbar_arrive(smem_u32(&S.a_full[slot]));          // 0x8000: experiment, no basis bytes
-                    else {
-                        mbar_expect_tx(smem_u32(&S.a_full[slot]), VS_A_STAGE_BYTES);
-                        if (csize == 1)
-                            bulk_g2s_hint(smem_u32(S.a[slot]), vs_basis + (size_t)i * VS_A_STAGE_BYTES, VS_A_STAGE_BYTES, smem_u32(&S.a_full[slot]), keep);
-                        else
-                            bulk_g2s_multicast(smem_u32(S.a[slot]) + crank * slice, vs_basis + (size_t)i * VS_A_STAGE_BYTES + crank * slice, slice,
-                                               smem_u32(&S.a_full[slot]), cmask, keep);
-                    }
-                    ++na;
-                    progressed = true;
+            uint32_t i = 0;                                             // stage inside the 105-stage stream
+            for (uint32_t na = 0; na < total_a; ++na) {
+                const uint32_t slot = na % NS;
+                // stage na -> slot na % NS: free once the MMAs of stage na - NS are done
+                if (na >= NS) VS_WAIT(&S.a_empty[slot], ((na / NS) & 1) ^ 1, 0);
+                if (variant & 0x8000) mbar_arrive(smem_u32(&S.a_full[slot]));              // 0x8000: experiment, no basis bytes
+                else {
+                    mbar_expect_tx(smem_u32(&S.a_full[slot]), VS_A_STAGE_BYTES);
+                    if (csize == 1)
+                        bulk_g2s_hint(smem_u32(S.a[slot]), vs_basis + (size_t)i * VS_A_STAGE_BYTES, VS_A_STAGE_BYTES, smem_u32(&S.a_full[slot]), keep);
+                    else
+                        bulk_g2s_multicast(smem_u32(S.a[slot]) + crank * slice, vs_basis + (size_t)i * VS_A_STAGE_BYTES + crank * slice, slice,
+                                           smem_u32(&S.a_full[slot]), cmask, keep);
                 }
-                // weight tile of unit nw -> buffer nw & 1
-                if (nw < total_w && (nw < 2 || mbar_test_wait(smem_u32(&S.w_empty[nw & 1]), ((nw >> 1) & 1) ^ 1))) {
-                    mbar_expect_tx(smem_u32(&S.w_full[nw & 1]), VS_W_TILE_BYTES);
-                    bulk_g2s_hint(smem_u32(S.w[nw & 1]), vs_w + (size_t)(nw % VS_NT) * VS_W_TILE_BYTES, VS_W_TILE_BYTES, smem_u32(&S.w_full[nw & 1]), keep);
-                    ++nw;
-                    progressed = true;
-                }
-                // feature rows of the next hand tile
-                if (fit < n_it && (fit == 0 || mbar_test_wait(smem_u32(&S.feat_empty), (fit & 1) ^ 1))) {
-                    const int tile = rnd * (int)csize + (int)crank;
-                    const int ltile = tile < ntiles ? tile : ntiles - 1;
-                    mbar_expect_tx(smem_u32(&S.feat_full), TC_K_CHUNKS * 2 * 4096);
-                    const unsigned char* fsrc = featp + (size_t)(ltile >> 1) * TC_A_TILE_BYTES + (size_t)(ltile & 1) * 4096;
-                    for (int c = 0; c < TC_K_CHUNKS; ++c)
-                        for (int sp = 0; sp < 2; ++sp)
-                            bulk_g2s_hint(smem_u32(S.feat[c][sp]), fsrc + (size_t)c * TC_A_STAGE_BYTES + (size_t)sp * TC_A_BLOCK_BYTES, 4096,
-                                          smem_u32(&S.feat_full), once);
-                    ++fit;
-                    rnd += nclusters;
-                    progressed = true;
-                }
-                if (progressed) idle_since = -1;
-                else if (idle_since < 0) idle_since = clock64();
-                else if (clock64() - idle_since > 2000000000LL) __trap();
+                if (++i == VS_NT * VS_STAGES_PER_TILE) i = 0;
             }
             VS_PROF_STORE(2);
         }
@@ -314,64 +325,65 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
             VS_PROF_STORE(1);
         }
     } else if (warp == 3) {
-        // ===== bone operand: fp32 transforms bone_t[group][bone][hand % 32][12] -> fp16 x3 MN-major core matrices =====
-        // The 12 elements of 4 consecutive hands of one bone are 48 contiguous floats = one K row (k = bone) of a chunk's
-        // B operand, n = (hand % 4) * 12 + element: a lane converts 8 of them (one 16-byte n-group) into the three splits
-        // a = a1 + a2 + a3 of 2^4 a.  [profiles/r2: written by the pose kernel as 96 scattered 16 / 8-byte stores per
-        // hand it cost that kernel +1.6 ms per 2^20 hands and 2.3 KB per hand of HBM traffic.]  Chunks are handed over one by
-        // one (the previous tile's last unit frees them one by one), in the order the scheduler issues them, and the loads
-        // of the next chunk are in flight while this one is converted.
-        const long long ngroups = ((long long)B + 31) >> 5;
-        uint32_t it = 0;
-        VS_PROF_DECL;
-        auto load_chunk = [&](int tile, int ch, float4 (&v)[3][2]) {
-            const long long group = (long long)tile * 2 + (ch >> 3);
-            const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + 48 * (ch & 7);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {                              // 96 (bone, n-group) items per chunk: three per lane
-                const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
-                const float4* p = reinterpret_cast<const float4*>(src0 + (size_t)k * (BONE_F * 32) + 8 * g);
-                if (group < ngroups) { v[r][0] = __ldg(p); v[r][1] = __ldg(p + 1); }
-                else { v[r][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[r][1] = v[r][0]; }
-            }
-        };
-        VS_FOR_EACH_TILE {
-            float4 v[3][2], vn[3][2];
-            load_chunk(tile, vs_chunk_of(0), v);
-#pragma unroll 1
-            for (int j = 0; j < VS_NCH; ++j) {
-                const int ch = vs_chunk_of(j);
-                if (j + 1 < VS_NCH) load_chunk(tile, vs_chunk_of(j + 1), vn);
-                VS_WAIT(&S.bones_empty[ch], (it & 1) ^ 1, 0);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
-                    float x[8] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w, v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] *= (float)(1 << VS_BONE_SCALE_LOG2);
-                    unsigned char* dst = &S.bones[ch][0][0] + g * 256 + (k >> 3) * 128 + (k & 7) * 16;
-#pragma unroll
-                    for (int sp = 0; sp < VS_BONE_SPLITS; ++sp) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __half lo = __float2half_rn(x[2 * e]), hi = __float2half_rn(x[2 * e + 1]);
-                            x[2 * e] -= __half2float(lo);
-                            x[2 * e + 1] -= __half2float(hi);
-                            pk[e] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
-                        }
-                        *reinterpret_cast<uint4*>(dst + sp * VS_BONE_CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (elect_one()) {
+            // ===== producer of the slower streams (one polling thread): feature rows of a hand tile, weight tiles, bone operand =====
+            // Bone operand: the chunk's three fp16 splits (4.5 KB, written by vs_bones_operand_kernel) as one bulk copy; chunks are
+            // handed over one by one (the previous tile's last unit frees them one by one), in the order the transform issuer
+            // takes them.  [profiles/r2: converted HERE from the pose stage's fp32 transforms by this warp alone, a chunk took
+            // 2 500 clk (fp32 <-> fp16 conversions run at a quarter of the fp32 rate) and the first unit of every hand tile waited
+            // for all sixteen: 40 000 of a tile's 97 000 clk.]
+            const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
+            int n_it = 0;
+            VS_FOR_EACH_TILE { (void)tile; ++n_it; }
+            const uint32_t total_w = (uint32_t)n_it * VS_NT, total_b = (uint32_t)n_it * VS_NCH;
+            uint32_t nw = 0, nb = 0;                                   // weight tiles / bone chunks requested so far
+            int fit = 0, rnd_f = cluster_id, rnd_b = cluster_id;        // feature tiles requested; rounds of the next feature / bone tile
+            VS_PROF_DECL;
+            long long idle_since = -1;
+            while (nw < total_w || nb < total_b || fit < n_it) {
+                bool progressed = false;
+                // bone chunk nb: tile iteration nb / 16, issue index nb % 16
+                if (nb < total_b) {
+                    const uint32_t bit = nb / VS_NCH;
+                    const int ch = vs_chunk_of((int)(nb % VS_NCH));
+                    if (bit == 0 || mbar_test_wait(smem_u32(&S.bones_empty[ch]), (bit & 1) ^ 1)) {
+                        const int tile = rnd_b * (int)csize + (int)crank;
+                        const int ltile = tile < ntiles ? tile : ntiles - 1;
+                        mbar_expect_tx(smem_u32(&S.bones_full[ch]), VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES);
+                        bulk_g2s_hint(smem_u32(&S.bones[ch][0][0]),
+                                      bones_op + (size_t)ltile * VS_BONE_TILE_BYTES + (size_t)ch * (VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES),
+                                      VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES, smem_u32(&S.bones_full[ch]), once);
+                        if (++nb % VS_NCH == 0) rnd_b += nclusters;
+                        progressed = true;
                     }
                 }
-                fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core's reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&S.bones_full[ch]));
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { v[r][0] = vn[r][0]; v[r][1] = vn[r][1]; }
+                // weight tile of unit nw -> buffer nw & 1
+                if (nw < total_w && (nw < 2 || mbar_test_wait(smem_u32(&S.w_empty[nw & 1]), ((nw >> 1) & 1) ^ 1))) {
+                    mbar_expect_tx(smem_u32(&S.w_full[nw & 1]), VS_W_TILE_BYTES);
+                    bulk_g2s_hint(smem_u32(S.w[nw & 1]), vs_w + (size_t)(nw % VS_NT) * VS_W_TILE_BYTES, VS_W_TILE_BYTES, smem_u32(&S.w_full[nw & 1]), keep);
+                    ++nw;
+                    progressed = true;
+                }
+                // feature rows of the next hand tile
+                if (fit < n_it && (fit == 0 || mbar_test_wait(smem_u32(&S.feat_empty), (fit & 1) ^ 1))) {
+                    const int tile = rnd_f * (int)csize + (int)crank;
+                    const int ltile = tile < ntiles ? tile : ntiles - 1;
+                    mbar_expect_tx(smem_u32(&S.feat_full), TC_K_CHUNKS * 2 * 4096);
+                    const unsigned char* fsrc = featp + (size_t)(ltile >> 1) * TC_A_TILE_BYTES + (size_t)(ltile & 1) * 4096;
+                    for (int c = 0; c < TC_K_CHUNKS; ++c)
+                        for (int sp = 0; sp < 2; ++sp)
+                            bulk_g2s_hint(smem_u32(S.feat[c][sp]), fsrc + (size_t)c * TC_A_STAGE_BYTES + (size_t)sp * TC_A_BLOCK_BYTES, 4096,
+                                          smem_u32(&S.feat_full), once);
+                    ++fit;
+                    rnd_f += nclusters;
+                    progressed = true;
+                }
+                if (progressed) idle_since = -1;
+                else if (idle_since < 0) idle_since = clock64();
+                else if (clock64() - idle_since > 2000000000LL) __trap();
             }
-            ++it;
+            VS_PROF_STORE(3);
         }
-        if (lane == 0) VS_PROF_STORE(3);
     } else if (warp >= 4) {
         // ===== epilogue: thread = vertex; the warp set owns 32 hands of the tile, whose rest coordinates it keeps in registers =====
         // [profiles/r2: (a) two rest-position stages + two transform stages in TMEM: a warp set had ONE chunk in flight, and the
@@ -568,7 +580,7 @@ void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, 
     }
 }
 
-int launch_vskin_forward(const void* blob, const unsigned char* featp, const float* bone_t, int B, int mode,
+int launch_vskin_forward(const void* blob, const unsigned char* featp, const float* bone_t, unsigned char* bones_op, int B, int mode,
                          float* verts, float* joints, float* v_posed_t, float* dbg, int variant, cudaStream_t s) {
     if (B <= 0) return 0;
     static SmemAttrOnce once;
@@ -609,7 +621,15 @@ int launch_vskin_forward(const void* blob, const unsigned char* featp, const flo
     const unsigned char* w_p = vs + V.w;
     const float4* tmpl_p = reinterpret_cast<const float4*>(vs + V.tmpl);
     const int bp = mode == MB_MODE_F16X3 ? 3 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, vskin_forward_kernel, hdr, basis_p, w_p, tmpl_p, featp, bone_t, B, ntiles, bp, t_products,
+    {
+        // the transform products' B operand: every 4-hand chunk of every hand tile (chunks past the batch are zero)
+        const long long nchunks = (long long)ntiles * VS_NCH;
+        const long long blocks = (nchunks + 7) / 8;
+        vs_bones_operand_kernel<<<(unsigned)(blocks < 8 * NUM_SMS ? blocks : 8 * NUM_SMS), 256, 0, s>>>(bone_t, B, nchunks, bones_op);
+        if (int rc = cuda_rc()) return rc;
+    }
+    const unsigned char* bones_op_c = bones_op;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, vskin_forward_kernel, hdr, basis_p, w_p, tmpl_p, featp, bones_op_c, B, ntiles, bp, t_products,
                                        verts, joints, v_posed_t, dbg, variant);
     if (e != cudaSuccess) return (int)e;
     return cuda_rc();

@@ -19,7 +19,7 @@ constexpr int VS_W_SPLITS = 2;
 constexpr int VS_W_TILE_BYTES = VS_W_SPLITS * VS_M * NJ * 2;     // 8 KB: two fp16 splits of W[128 vertices][16 bones]
 constexpr int VS_BONE_SPLITS = 3;
 constexpr int VS_BONE_CHUNK_BYTES = VS_TN * NJ * 2;              // 1536 B: one split of one chunk, MN-major [6 n-groups][2 k-groups][8 k][8 n]
-constexpr int VS_BONE_TILE_BYTES = VS_NCH * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES;   // 73 728 B per 64 hands (shared memory only)
+constexpr int VS_BONE_TILE_BYTES = VS_NCH * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES;   // 73 728 B per 64 hands
 constexpr int VS_W_SCALE_LOG2 = 8;                 // skinning weights (<= 1) are pre-scaled by 2^8 before the fp16 split
 constexpr int VS_BONE_SCALE_LOG2 = 4;              // bone transforms (|R| <= 1, |t| < ~1 m) by 2^4: fp16 overflow only beyond 4 km
 constexpr int VS_MIN_HANDS = 8192;                 // the fused forward is used from here on (one-thread-per-hand pose kernels)
@@ -46,8 +46,10 @@ size_t vskin_blob_bytes();
 void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, const int32_t* sk_perm, int basis_scale_log2,
                 void* host_section);
 // verts[B][778][3], fingertip joints; v_posed_t (nullable): the rest-pose scratch of the skinning backward, hand-minor block order
-// bone_t: the pose stage's fp32 transforms [groups][16][32][12]; the kernel converts them into its MMA operand itself
-int launch_vskin_forward(const void* blob, const unsigned char* featp, const float* bone_t, int B, int mode,
+// bone_t: the pose stage's fp32 transforms [groups][16][32][12]; bones_op: scratch of vskin_bones_op_bytes(B) for their fp16 x3
+// operand images (written by a conversion kernel launched first on the same stream)
+inline size_t vskin_bones_op_bytes(long long B) { return (size_t)((B + VS_NH - 1) / VS_NH) * VS_BONE_TILE_BYTES; }
+int launch_vskin_forward(const void* blob, const unsigned char* featp, const float* bone_t, unsigned char* bones_op, int B, int mode,
                          float* verts, float* joints, float* v_posed_t, float* dbg, int variant, cudaStream_t s);
 
 }  // namespace mb
