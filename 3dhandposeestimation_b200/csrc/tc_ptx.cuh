@@ -50,6 +50,28 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, ui
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
                      :: "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
 }
+// The same with the A operand in TENSOR MEMORY (lane = row of A, 8 columns = 16 K values as fp16 pairs): no shared-memory
+// read for A at all.
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+                     "mov.b64 db, {%2, %3};\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+                     :: "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+                     "mov.b64 db, {%2, %3};\n\tsetp.ne.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+                     :: "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+}
+// tcgen05.st, shape 32x32b: lane i of the warp writes 8 consecutive columns of TMEM lane (32 * (warp % 4) + i)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "

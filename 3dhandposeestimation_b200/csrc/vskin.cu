@@ -44,12 +44,14 @@ namespace {
 
 constexpr int VS_THREADS = 384;                   // 12 warps: see the role list above
 constexpr int VS_EPI_WARPS = 8;
-constexpr int VS_ASTAGES = 6;                     // basis ring: 6 x 16 KB (the stream is latency-bound: bytes in flight over ~2 000 clk)
+constexpr int VS_ASTAGES = 5;                     // basis ring: 5 x 16 KB (6 measured the same)
 constexpr int VS_TSTAGES = 6;                     // transform ring: chunk counter mod 6; even counters -> warp set 0, odd -> set 1
 constexpr int VS_HS = VS_NH / 2;                  // 32 hands per epilogue warp set
 constexpr uint32_t VS_TMEM_COLS = 512;
 constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns: the rest positions of a unit
 constexpr uint32_t VS_T_COL0 = VS_VP_COLS;         // 192: first transform column
+constexpr uint32_t VS_W_COL0 = VS_T_COL0 + VS_TSTAGES * VS_TN;     // 480: the weight tiles (A operand of the transform products), two buffers of
+constexpr uint32_t VS_W_COLS = VS_W_SPLITS * NJ / 2;               //      16 columns: [split][8 columns = 16 bones as fp16 pairs], lane = vertex
 // instruction descriptors: f16 x f16 -> f32, M = 128
 constexpr uint32_t VS_IDESC_BLEND = (1u << 4) | ((uint32_t)(VS_NH >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);                // A, B K-major
 constexpr uint32_t VS_IDESC_T = (1u << 4) | (1u << 16) | ((uint32_t)(VS_TN >> 3) << 17) | ((uint32_t)(VS_M >> 4) << 24);       // B MN-major
@@ -61,7 +63,6 @@ struct VsShared {
     alignas(128) unsigned char feat[TC_K_CHUNKS][2][VS_NH * TC_K_CHUNK * 2];      // 40 KB: [K chunk][hi, lo][64 hands x 32]
     alignas(128) unsigned char bones[VS_NCH][VS_BONE_SPLITS][VS_BONE_CHUNK_BYTES]; // 72 KB
     alignas(128) unsigned char a[VS_ASTAGES][VS_A_STAGE_BYTES];                    // 64 KB basis ring
-    alignas(128) unsigned char w[2][VS_W_TILE_BYTES];                              // 16 KB weight tiles
     alignas(8) unsigned long long a_full[VS_ASTAGES], a_empty[VS_ASTAGES];
     unsigned long long w_full[2], w_empty[2];
     unsigned long long feat_full, feat_empty;
@@ -170,7 +171,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < VS_ASTAGES; ++s) { mbar_init(smem_u32(&S.a_full[s]), 1); mbar_init(smem_u32(&S.a_empty[s]), csize); }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&S.w_full[s]), 1); mbar_init(smem_u32(&S.w_empty[s]), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&S.w_full[s]), VS_EPI_WARPS); mbar_init(smem_u32(&S.w_empty[s]), 1); }
         mbar_init(smem_u32(&S.vp_full), 1); mbar_init(smem_u32(&S.vp_empty), VS_EPI_WARPS);
         for (int s = 0; s < VS_TSTAGES; ++s) { mbar_init(smem_u32(&S.t_full[s]), 1); mbar_init(smem_u32(&S.t_empty[s]), VS_EPI_WARPS / 2); }
         mbar_init(smem_u32(&S.feat_full), 1); mbar_init(smem_u32(&S.feat_empty), 1);
@@ -274,8 +275,6 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
             // ===== transform issuer: T = W A, 4 hands per chunk, through the six-stage ring =====
             // [profiles/r2: issued by `lane == 0` the compiler wrapped every tcgen05.mma in a divergence "waterfall" (ELECT /
             // R2UR.BROADCAST / BRA.U.ANY) and rebuilt 64-bit descriptors per instruction: elect.sync and 32-bit descriptor halves.]
-            const uint32_t hi_k256 = desc_hi(256);
-            const uint32_t w_lo0 = desc_lo(smem_u32(S.w[0]), 128);
             // bones: MN-major, n-groups 256 B apart (SBO), k-groups 128 B apart (LBO)
             const uint32_t b_lo0 = desc_lo(smem_u32(&S.bones[0][0][0]), 128);
             const uint32_t hi_b = desc_hi(256);
@@ -285,7 +284,8 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 (void)tile;
                 for (int t = 0; t < VS_NT; ++t, ++g) {
                     VS_WAIT(&S.w_full[g & 1], (g >> 1) & 1, 0);
-                    const uint32_t w1 = w_lo0 + (((g & 1) * VS_W_TILE_BYTES) >> 4), w2 = w1 + (4096 >> 4);
+                    // the unit's weight tile sits in TMEM (written by the epilogue warps): buffer g & 1, splits 8 columns apart
+                    const uint32_t w1 = tmem + VS_W_COL0 + (g & 1) * VS_W_COLS, w2 = w1 + NJ / 2;
 #pragma unroll 1
                     for (int j = 0; j < VS_NCH; ++j) {
                         const int ch = vs_chunk_of(j);
@@ -300,17 +300,17 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                         // last addition rounds at full magnitude
                         if (!(variant & 0x800)) {                       // 0x800: experiment, no transform products
                             if (t_products >= 4) {
-                                umma_f16_lohi<false>(d, w1, hi_k256, a3, hi_b, VS_IDESC_T);
-                                if (t_products >= 5) umma_f16_lohi<true>(d, w2, hi_k256, a2, hi_b, VS_IDESC_T);
-                                umma_f16_lohi<true>(d, w1, hi_k256, a2, hi_b, VS_IDESC_T);
-                                umma_f16_lohi<true>(d, w2, hi_k256, a1, hi_b, VS_IDESC_T);
-                                umma_f16_lohi<true>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
+                                umma_f16_ts<false>(d, w1, a3, hi_b, VS_IDESC_T);
+                                if (t_products >= 5) umma_f16_ts<true>(d, w2, a2, hi_b, VS_IDESC_T);
+                                umma_f16_ts<true>(d, w1, a2, hi_b, VS_IDESC_T);
+                                umma_f16_ts<true>(d, w2, a1, hi_b, VS_IDESC_T);
+                                umma_f16_ts<true>(d, w1, a1, hi_b, VS_IDESC_T);
                             } else if (t_products == 3) {
-                                umma_f16_lohi<false>(d, w1, hi_k256, a2, hi_b, VS_IDESC_T);
-                                umma_f16_lohi<true>(d, w2, hi_k256, a1, hi_b, VS_IDESC_T);
-                                umma_f16_lohi<true>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
+                                umma_f16_ts<false>(d, w1, a2, hi_b, VS_IDESC_T);
+                                umma_f16_ts<true>(d, w2, a1, hi_b, VS_IDESC_T);
+                                umma_f16_ts<true>(d, w1, a1, hi_b, VS_IDESC_T);
                             } else {
-                                umma_f16_lohi<false>(d, w1, hi_k256, a1, hi_b, VS_IDESC_T);
+                                umma_f16_ts<false>(d, w1, a1, hi_b, VS_IDESC_T);
                             }
                         }
                         if (variant & 0x20000) mbar_arrive(smem_u32(&S.t_full[stage]));          // 0x20000: experiment (with 0x800): plain arrive
@@ -318,7 +318,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                         if (t == VS_NT - 1) tc_commit(smem_u32(&S.bones_empty[ch]));        // the tile's last use of the chunk's bones
                         if (++stage == VS_TSTAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(smem_u32(&S.w_empty[g & 1]));
+                    tc_commit(smem_u32(&S.w_empty[g & 1]));                 // the unit's products are done with its weight tile
                 }
                 ++it;
             }
@@ -332,15 +332,15 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
             // takes them.  [profiles/r2: converted HERE from the pose stage's fp32 transforms by this warp alone, a chunk took
             // 2 500 clk (fp32 <-> fp16 conversions run at a quarter of the fp32 rate) and the first unit of every hand tile waited
             // for all sixteen: 40 000 of a tile's 97 000 clk.]
-            const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
+            const uint64_t once = l2_policy_evict_first();
             int n_it = 0;
             VS_FOR_EACH_TILE { (void)tile; ++n_it; }
-            const uint32_t total_w = (uint32_t)n_it * VS_NT, total_b = (uint32_t)n_it * VS_NCH;
-            uint32_t nw = 0, nb = 0;                                   // weight tiles / bone chunks requested so far
+            const uint32_t total_b = (uint32_t)n_it * VS_NCH;
+            uint32_t nb = 0;                                           // bone chunks requested so far
             int fit = 0, rnd_f = cluster_id, rnd_b = cluster_id;        // feature tiles requested; rounds of the next feature / bone tile
             VS_PROF_DECL;
             long long idle_since = -1;
-            while (nw < total_w || nb < total_b || fit < n_it) {
+            while (nb < total_b || fit < n_it) {
                 bool progressed = false;
                 // bone chunk nb: tile iteration nb / 16, issue index nb % 16
                 if (nb < total_b) {
@@ -356,13 +356,6 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                         if (++nb % VS_NCH == 0) rnd_b += nclusters;
                         progressed = true;
                     }
-                }
-                // weight tile of unit nw -> buffer nw & 1
-                if (nw < total_w && (nw < 2 || mbar_test_wait(smem_u32(&S.w_empty[nw & 1]), ((nw >> 1) & 1) ^ 1))) {
-                    mbar_expect_tx(smem_u32(&S.w_full[nw & 1]), VS_W_TILE_BYTES);
-                    bulk_g2s_hint(smem_u32(S.w[nw & 1]), vs_w + (size_t)(nw % VS_NT) * VS_W_TILE_BYTES, VS_W_TILE_BYTES, smem_u32(&S.w_full[nw & 1]), keep);
-                    ++nw;
-                    progressed = true;
                 }
                 // feature rows of the next hand tile
                 if (fit < n_it && (fit == 0 || mbar_test_wait(smem_u32(&S.feat_empty), (fit & 1) ^ 1))) {
@@ -396,6 +389,27 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
         const float osv = exp2f(-(float)(hdr->basis_scale_log2 + hdr->feat_scale_log2));
         const float ost = exp2f(-(float)(VS_W_SCALE_LOG2 + VS_BONE_SCALE_LOG2));
         uint32_t g = 0;                                                // unit counter
+        int n_units = 0;
+        VS_FOR_EACH_TILE { (void)tile; n_units += VS_NT; }
+        // The weight tile of a unit (A operand of its transform products) lives in TENSOR MEMORY, lane = vertex: every epilogue
+        // thread stores its own vertex' 16 weights of one fp16 split (set 0: hi, set 1: lo; 8 columns) one unit ahead.
+        // [profiles/r2: as a shared-memory operand the 4 KB tile was re-read by each of the 64 products of a unit — 256 KB of the
+        // 890 KB per unit that the shared-memory pipe (75 % busy) serves to the tensor core.]
+        auto w_row_load = [&](int vt, uint4 (&wr)[2]) {
+            const uint4* p = reinterpret_cast<const uint4*>(vs_w + ((size_t)(vt * VS_M + vl) * VS_W_SPLITS + set) * (NJ * 2));
+            wr[0] = __ldg(p); wr[1] = __ldg(p + 1);
+        };
+        auto w_row_store = [&](uint32_t unit, const uint4 (&wr)[2]) {
+            if (unit >= 2) vs_wait(&S.w_empty[unit & 1], ((unit >> 1) & 1) ^ 1);   // the products of unit - 2 are done with the buffer
+            tc_fence_after();
+            const uint32_t r[8] = {wr[0].x, wr[0].y, wr[0].z, wr[0].w, wr[1].x, wr[1].y, wr[1].z, wr[1].w};
+            tmem_st8(tmem + lane_addr + VS_W_COL0 + (unit & 1) * VS_W_COLS + set * (NJ / 2), r);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.w_full[unit & 1]));
+        };
+        if (n_units > 0) { uint4 wr[2]; w_row_load(0, wr); w_row_store(0, wr); }
         uint32_t tcnt = set;                                           // this set's next chunk counter (issue order, all units)
         VS_PROF_DECL;
         VS_FOR_EACH_TILE {
@@ -404,6 +418,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 const int vtx = t * VS_M + vl;
                 const bool valid = vtx < NV;
                 const float4 tm = vs_tmpl[vtx];
+                const bool has_next = (int)g + 1 < n_units;
                 int tipslot = -1;
 #pragma unroll
                 for (int i = 0; i < 5; ++i) if (vtx == c_vs_tip_vert[i]) tipslot = c_vs_tip_slot[i];
@@ -430,6 +445,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     }
                     VS_TOC(5);
                 }
+                if (has_next) { uint4 wnext[2]; w_row_load(t + 1 < VS_NT ? t + 1 : 0, wnext); w_row_store(g + 1, wnext); }
                 if (v_posed_t != nullptr) {
                     // rest-pose scratch for the skinning backward: v_posed_t[group][3 pos + p][32 hands], this set's 32 hands
                     const long long group = (long long)tile * 2 + set;
@@ -546,7 +562,7 @@ void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, 
                         bdst[stage * (VS_A_STAGE_BYTES / 2) + in] = hi;
                         bdst[stage * (VS_A_STAGE_BYTES / 2) + (VS_A_STAGE_BYTES / 4) + in] = lo;
                     }
-    // dense skinning weights W[vertex][bone] in three fp16 splits, K-major (K = bone)
+    // dense skinning weights W[vertex][bone] as two fp16 splits, one 32-byte row per (vertex, split)
     std::vector<float> dense((size_t)NV * NJ, 0.f);
     for (int v = 0; v < NV; ++v)
         for (int s = 0; s < MAX_INFL; ++s) {
@@ -556,18 +572,15 @@ void vskin_pack(const float* basis, const float* skin_w, const int32_t* skin_b, 
         }
     __half* wdst = reinterpret_cast<__half*>(out + L.w);
     const float sw = (float)(1 << VS_W_SCALE_LOG2);
-    for (int t = 0; t < VS_NT; ++t)
-        for (int r = 0; r < VS_M; ++r)
-            for (int k = 0; k < NJ; ++k) {
-                const int v = t * VS_M + r;
-                float x = v < NV ? dense[(size_t)v * NJ + k] * sw : 0.f;
-                const size_t in = (((size_t)(r >> 3) * 2 + (k >> 3)) * 8 + (r & 7)) * 8 + (k & 7);
-                for (int s = 0; s < VS_W_SPLITS; ++s) {
-                    const __half h = __float2half_rn(x);
-                    x -= __half2float(h);
-                    wdst[((size_t)t * VS_W_SPLITS + s) * (VS_M * NJ) + in] = h;
-                }
+    for (int v = 0; v < VS_NT * VS_M; ++v)
+        for (int k = 0; k < NJ; ++k) {
+            float x = v < NV ? dense[(size_t)v * NJ + k] * sw : 0.f;
+            for (int s = 0; s < VS_W_SPLITS; ++s) {
+                const __half h = __float2half_rn(x);
+                x -= __half2float(h);
+                wdst[((size_t)v * VS_W_SPLITS + s) * NJ + k] = h;        // row of vertex v, split s: 16 bones, K = bone
             }
+        }
     // v_template per vertex + the vertex' row in the block-order rest-pose scratch
     float* tm = reinterpret_cast<float*>(out + L.tmpl);
     std::vector<int> pos_of(NV, -1);

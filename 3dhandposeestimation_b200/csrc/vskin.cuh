@@ -27,7 +27,7 @@ constexpr int VS_MIN_HANDS = 8192;                 // the fused forward is used 
 // extra constant-blob section behind the blend_tc images
 struct VsBlobLayout {
     size_t basis;       // fp16 hi/lo A-operand images of the blend basis: [7 tiles][3 planes][5 K chunks][2][8 KB], K-major
-    size_t w;           // fp16 x2 A-operand images of the skinning weights: [7 tiles][2 splits][4 KB], K-major (K = bone)
+    size_t w;           // fp16 x2 rows of the dense skinning weights: [896 vertices][2 splits][16 bones] (the kernel stores them into TMEM)
     size_t tmpl;        // float4 [896]: v_template x, y, z of the vertex; .w = bits of int: 3 * block-order position (v_posed_t row) or -1
     size_t total;
 };

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MB_ABI_VERSION 3
+#define MB_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MB_API __attribute__((visibility("default")))

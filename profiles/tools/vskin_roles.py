@@ -42,8 +42,8 @@ torch.cuda.synchronize()
 p = dbg[8192:].cpu().numpy().reshape(16, 8)
 names = {0: ("blend issuer", ["feat_full", "vp_empty", "a_full", "a_empty"]),
          1: ("transform issuer", ["w_full", "bones_full", "t_empty"]),
-         2: ("feature/weight producer", ["feat_empty", "w_empty"]),
-         3: ("bone converter", ["bones_empty"]),
+         2: ("basis producer", ["a_empty"]),
+         3: ("slow-stream producer (polling)", []),
          4: ("epilogue set 0 q0", ["vp_full", "t_full", "T load+release", "fma+sts", "row stores", "vp load"]),
          8: ("epilogue set 1 q0", ["vp_full", "t_full", "T load+release", "fma+sts", "row stores", "vp load"])}
 ntiles = (H + 63) // 64

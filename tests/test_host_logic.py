@@ -20,7 +20,7 @@ def test_library_exports_every_header_symbol(pkg):
     assert set(declared) == set(pkg._cabi.SIGNATURES), "ctypes table and header disagree"
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mb_abi_version() == 3
+    assert lib.mb_abi_version() == 4
     assert b"NULL" in lib.mb_error_string(-1)
 
 
