@@ -20,6 +20,7 @@ BWD_WORKSPACE_VALID = 1
 MODEL_CHAINS_5X3 = 0x100
 FWD_INFERENCE = 0x200
 FWD_FUSED = 0x400
+FWD_UNFUSED = 0x800
 REDUCE_MPJPE_MM, REDUCE_L2 = 0, 1
 VIS_F32, VIS_U8 = 0, 1
 

@@ -6,6 +6,7 @@ using namespace mb;
 
 #include "blend_tc.cuh"
 #include "skin.cuh"
+#include <stdlib.h>
 #include "vskin.cuh"
 
 // ---------------------------------------------------------------- bookkeeping
@@ -206,7 +207,7 @@ extern "C" size_t mb_mano_workspace_bytes(int B, int mode) {
 static int check_common(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas, int B, int mode,
                         const void* workspace, size_t workspace_bytes) {
     if (B < 0 || nc < 1 || nc > NAA) return MB_E_RANGE;
-    if (mode & ~(0xff | MB_MODEL_CHAINS_5X3 | MB_FWD_INFERENCE | MB_FWD_FUSED)) return MB_E_RANGE;
+    if (mode & ~(0xff | MB_MODEL_CHAINS_5X3 | MB_FWD_INFERENCE | MB_FWD_FUSED | MB_FWD_UNFUSED)) return MB_E_RANGE;
     mode &= 0xff;
     if (mode != MB_MODE_FP32 && mode != MB_MODE_F16X3 && mode != MB_MODE_F16) return MB_E_RANGE;
     if (B == 0) return 0;
@@ -243,9 +244,13 @@ static int pose_and_blend_forward(const void* blob, int nc, const float* rot, co
     return launch_blend_tc_forward(blob, featp, v_posed_t, B, mode, s);
 }
 
-// the fused lane = vertex forward (vskin.cu; opt-in) serves the batches of the one-thread-per-hand pose kernels
+// the fused lane = vertex forward (vskin.cu) serves the batches of the one-thread-per-hand pose kernels; MB_FWD_FUSED /
+// MB_FWD_UNFUSED force a choice
 static inline bool use_fused_forward(int model_flags, int mode, int B) {
-    return use_lane_hand(model_flags, mode, B) && (model_flags & MB_FWD_FUSED);
+    if (!use_lane_hand(model_flags, mode, B) || (model_flags & MB_FWD_UNFUSED)) return false;
+    if (model_flags & MB_FWD_FUSED) return true;
+    static const int train_fused = getenv("MANO_B200_FUSED_TRAIN") ? atoi(getenv("MANO_B200_FUSED_TRAIN")) : 0;
+    return (model_flags & MB_FWD_INFERENCE) || train_fused;
 }
 
 // pose stage -> fused blend + skinning: verts, fingertip joints; v_posed_t only when a backward will want the workspace

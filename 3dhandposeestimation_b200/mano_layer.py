@@ -155,14 +155,14 @@ class ManoLayer(nn.Module):
     numpy arrays with the pkl's keys, e.g. ``assets.synthetic_mano()``) instead
     of a pkl path; ``mode`` in {"fp32", "f16x3", "f16"} selects the blend-shape
     contraction precision; ``keep_workspace`` trades 12 KB/hand of retained
-    memory for not recomputing the forward in the backward; ``fused_forward=True``
-    runs the fused blend + skinning kernel with lane = vertex (csrc/vskin.cu) from
-    8 192 hands on — parity-green, but measured slower than the two separate
-    kernels, hence opt-in.
+    memory for not recomputing the forward in the backward; ``fused_forward`` forces
+    (True) or forbids (False) the fused blend + skinning kernel with lane = vertex
+    (csrc/vskin.cu) from 8 192 hands on — by default the library picks the measured
+    faster of the two forward implementations.
     """
 
     def __init__(self, device, MANO_RIGHT_pkl=None, bases_num=10, pose_num=6, *, model=None, mode="f16x3",
-                 keep_workspace=True, fused_forward=False):
+                 keep_workspace=True, fused_forward=None):
         super().__init__()
         self.device = device
         self.bases_num = bases_num
@@ -174,7 +174,7 @@ class ManoLayer(nn.Module):
         self._mode = _cabi.MODES[mode]      # model property bits (mb_mano_model_flags) are OR-ed in below
         self.mode = mode
         self.keep_workspace = bool(keep_workspace)
-        self._fwd_flags = _cabi.FWD_FUSED if fused_forward else 0
+        self._fwd_flags = 0 if fused_forward is None else (_cabi.FWD_FUSED if fused_forward else _cabi.FWD_UNFUSED)
 
         if model is None:
             if MANO_RIGHT_pkl is None:

@@ -45,8 +45,8 @@ FLOP_BLEND = 2 * 145 * 2334                                     # 676860 per han
 FLOP_SKIN_T = 2 * 778 * 16 * 12                                 # 298752 per hand: T_v = sum_k w_vk A_k as a dense product (vskin.cu)
 # the fused lane = vertex forward kernel (vskin.cu): feature tiles 640 + bone operand 1152 in, verts 9336 + tips 60 out;
 # a training forward also leaves the rest-pose scratch of the skinning backward (9408)
-BYTES_FUSED_FWD = 640 + 1152 + 9336 + 60                        # 11188
-BYTES_FUSED_FWD_TRAIN = BYTES_FUSED_FWD + 9408                  # 20596
+BYTES_FUSED_FWD = 640 + 768 + 9336 + 60                         # 10804: feature tiles + fp32 bone transforms in, verts + tips out
+BYTES_FUSED_FWD_TRAIN = BYTES_FUSED_FWD + 9408                  # 20212
 STAGE_KERNEL = {"pose_fwd": "pose_forward_lh_kernel", "blend_fwd": "blend_tc_forward_mres_kernel", "lbs_fwd": "skin_forward_kernel",
                 "fused_fwd": "vskin_forward_kernel",
                 "lbs_bwd": "skin_backward_kernel", "blend_bwd": "blend_tc_backward_kernel", "pose_bwd": "pose_backward_lh_kernel"}
@@ -814,8 +814,10 @@ def main():
                     "algorithmic_bytes_per_hand": BYTES_FWD,
                     "note": "mb_mano_forward with MB_FWD_INFERENCE (no rest-pose scratch kept): verts[H,778,3] + joints[H,21,3]"}
     if not args.no_extras and (mode & 0xff) != cabi.MODE_FP32:
-        # A/B: the same forward through the opt-in fused blend + skinning kernel with lane = vertex (MB_FWD_FUSED, vskin.cu)
-        um = fwd_mode | cabi.FWD_FUSED
+        # A/B: the same forward through the OTHER implementation (the library's default from 8 192 hands on is the fused blend +
+        # skinning kernel with lane = vertex, vskin.cu; MB_FWD_UNFUSED runs the blend-contraction + lane = hand skinning kernels)
+        other_is_unfused = "fused_fwd" in fstages
+        um = fwd_mode | (cabi.FWD_UNFUSED if other_is_unfused else cabi.FWD_FUSED)
 
         def ufwd_step(i):
             s = sets[i % nsets]
@@ -834,13 +836,14 @@ def main():
         sync_all()
         uprof = cabi.profile_collect()
         lib.mb_profile_enable(0)
-        forward_only["fused_ab"] = {"ms_per_step": e0.elapsed_time(e1) / 5, "stages_ms": {k: v[0] / v[1] for k, v in uprof.items()},
-                                    "note": "same launch with MB_FWD_FUSED: pose -> fused blend + skinning with lane = vertex (vskin.cu), "
-                                            "no v_posed_t; opt-in because it is the slower one"}
+        forward_only["unfused_ab" if other_is_unfused else "fused_ab"] = {
+            "ms_per_step": e0.elapsed_time(e1) / 5, "stages_ms": {k: v[0] / v[1] for k, v in uprof.items()},
+            "note": ("same launch with MB_FWD_UNFUSED: pose -> blend GEMM (writes v_posed_t) -> lane = hand skinning" if other_is_unfused else
+                     "same launch with MB_FWD_FUSED: pose -> fused blend + skinning with lane = vertex (vskin.cu), no v_posed_t")}
     if "fused_fwd" in fstages:
         fms = fstages["fused_fwd"]
         lbs_fwd_roof = hbm_roofline("fused_fwd", BYTES_FUSED_FWD, ms=fms)
-        lbs_fwd_roof["note"] = ("fused blend + skinning forward (vskin.cu), inference launch: feature tiles 640 + bone operand 1152 B in, "
+        lbs_fwd_roof["note"] = ("fused blend + skinning forward (vskin.cu + its bone-operand pre-pass), inference launch: feature tiles 640 + bone transforms 768 B in, "
                                 "verts 9336 + fingertip joints 60 B out per hand")
         tfl = (FLOP_BLEND + FLOP_SKIN_T) * H / (fms * 1e-3) / 1e12
         blend_roof = {"kernel": "vskin_forward_kernel", "bound": "tensor", "achieved": tfl, "peak": peaks["bf16_tflops_sustained"],

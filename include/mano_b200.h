@@ -56,11 +56,14 @@ extern "C" {
 /* Forward options, OR-ed into `mode` of mb_mano_forward:
  * MB_FWD_INFERENCE: no backward will follow — the fused forward keeps no rest-pose scratch in the workspace (a later
  *                   mb_mano_backward must then be called WITHOUT MB_BWD_WORKSPACE_VALID and recomputes it);
- * MB_FWD_FUSED    : from 8 192 hands on (MANO tree, tensor-core modes) run the fused blend-shape + skinning kernel with
- *                   lane = vertex (csrc/vskin.cu) instead of the blend-contraction and skinning kernels.  Opt-in: it is
- *                   parity-green but measured slower than the two kernels (profiles/r2/ncu_history.md). */
+ * MB_FWD_FUSED / MB_FWD_UNFUSED: from 8 192 hands on (MANO tree, tensor-core modes) the forward has two implementations —
+ *                   the fused blend-shape + skinning kernel with lane = vertex (csrc/vskin.cu: both contractions on the
+ *                   tensor core, no rest-pose round trip through HBM) and the blend-contraction + lane = hand skinning
+ *                   kernels.  Without either bit the library picks the measured faster one (the fused kernel); the bits force one
+ *                   (measurement / cross-checking). */
 #define MB_FWD_INFERENCE 0x200
 #define MB_FWD_FUSED     0x400
+#define MB_FWD_UNFUSED   0x800
 
 /* mb_mano_backward flags */
 #define MB_BWD_WORKSPACE_VALID 1  /* workspace still holds the forward's intermediates for these inputs */
