@@ -291,7 +291,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_secondary(args, pkg, layer, dev, rank, world, dist):
@@ -636,7 +636,27 @@ def workload_name(args):
     return f"mano_full45_noPCA_fwd+bwd_{args.hands}_hands_per_gpu"
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON record: everything else a library prints there (NCCL's version banner,
+    torchrun's notices in a child) is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout for emit()."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -692,7 +712,7 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            emit(line)
         return
 
     nsets = max(1, args.rotate)
@@ -782,6 +802,34 @@ def main():
     # now fused with the blend contraction — is reported next to it from the forward-only pass below
     roofline = dict(hbm_roofline(roof_stage, stage_bytes[roof_stage]), dominant_stage=dominant)
     step_gbs = (BYTES_FWD + BYTES_BWD) * H / (ms_per_step * 1e-3) / 1e9
+
+    # ---- strong scaling (BASELINE config 4 as written: 2^20 hands sharded over the GPUs) beside the weak-scaling line -----
+    strong = None
+    if world > 1:
+        Hs = H // world
+        ws_s = lib.mb_mano_workspace_bytes(Hs, mode)
+
+        def strong_step(i):
+            s = sets[i % nsets]
+            cabi.check(lib.mb_mano_forward(blob, 45, s["rot"].data_ptr(), s["pose"].data_ptr(), s["beta"].data_ptr(), Hs, mode,
+                                           s["verts"].data_ptr(), s["joints"].data_ptr(), ws.data_ptr(), ws_s, stream), "fwd")
+            cabi.check(lib.mb_mano_backward(blob, 45, s["rot"].data_ptr(), s["pose"].data_ptr(), s["beta"].data_ptr(),
+                                            s["gv"].data_ptr(), s["gj"].data_ptr(), Hs, mode, cabi.BWD_WORKSPACE_VALID,
+                                            s["g_rot"].data_ptr(), s["g_pose"].data_ptr(), s["g_beta"].data_ptr(),
+                                            ws.data_ptr(), ws_s, stream), "bwd")
+
+        for i in range(3):
+            strong_step(i)
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            strong_step(i)
+        e1.record()
+        sync_all()
+        ms_s = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        strong = {"hands_total": Hs * world, "hands_per_gpu": Hs, "ms_per_step": ms_s, "value": Hs * world / (ms_s * 1e-3), "unit": UNIT,
+                  "note": "the same forward + backward with the batch of ONE GPU's weak-scaling step sharded over all ranks "
+                          "(max over ranks, no collective); at this size a rank's slice no longer exceeds L2 by much"}
 
     # ---- forward only (north_star: >= 1e8 hands/s forward on 8 GPUs, LBS >= 70 % of the HBM roofline) -------------
     fwd_mode = mode | cabi.FWD_INFERENCE
@@ -1017,11 +1065,12 @@ def main():
                      "algorithmic_bytes_per_hand": BYTES_FWD + BYTES_BWD},
         "stages_ms": stages,
         "forward_only": forward_only,
+        "strong_scaling": strong,
         "parity": parity,
         "cpu_baseline": cpu,
     }
     line.update(extras)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
