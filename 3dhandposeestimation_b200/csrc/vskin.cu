@@ -45,7 +45,8 @@ namespace {
 constexpr int VS_THREADS = 384;                   // 12 warps: see the role list above
 constexpr int VS_EPI_WARPS = 8;
 constexpr int VS_ASTAGES = 5;                     // basis ring: 5 x 16 KB (6 measured the same)
-constexpr int VS_TSTAGES = 6;                     // transform ring: chunk counter mod 6; even counters -> warp set 0, odd -> set 1
+constexpr int VS_TSTAGES = 3;                     // transform ring of 8-hand chunks: chunk counter mod 3; even counters -> warp set 0, odd -> set 1
+constexpr int VS_HH = 4;                          // hands per epilogue register load of a chunk (48 columns)
 constexpr int VS_HS = VS_NH / 2;                  // 32 hands per epilogue warp set
 constexpr uint32_t VS_TMEM_COLS = 512;
 constexpr uint32_t VS_VP_COLS = 3 * VS_NH;         // 192 columns: the rest positions of a unit
@@ -103,9 +104,9 @@ __device__ __forceinline__ void vs_wait(unsigned long long* bar, uint32_t parity
 // epilogue warp sets (hands 0-31, 32-63) are served alternately
 __device__ __forceinline__ int vs_chunk_of(int j) { return (j >> 1) + (VS_NCH / 2) * (j & 1); }
 
-// ---- bone operand images: fp32 transforms bone_t[group][bone][hand % 32][12] -> fp16 x3 MN-major core matrices, per 4-hand chunk
-// [hand tile][chunk 16][split 3][1536 B: 6 n-groups x 2 k-groups x 8 k x 8 n].  The 12 elements of 4 consecutive hands of one bone
-// are 48 contiguous floats = one K row (k = bone) of a chunk's B operand, n = (hand % 4) * 12 + element: a lane converts 8 of
+// ---- bone operand images: fp32 transforms bone_t[group][bone][hand % 32][12] -> fp16 x3 MN-major core matrices, per 8-hand chunk
+// [hand tile][chunk 8][split 3][3072 B: 12 n-groups x 2 k-groups x 8 k x 8 n].  The 12 elements of 8 consecutive hands of one bone
+// are 96 contiguous floats = one K row (k = bone) of a chunk's B operand, n = (hand % 8) * 12 + element: a lane converts 8 of
 // them (one 16-byte n-group) into the three splits a = a1 + a2 + a3 of 2^4 a; one warp per chunk.
 __global__ void __launch_bounds__(256)
 vs_bones_operand_kernel(const float* __restrict__ bone_t, int B, long long nchunks, unsigned char* __restrict__ bones_op) {
@@ -113,12 +114,12 @@ vs_bones_operand_kernel(const float* __restrict__ bone_t, int B, long long nchun
     const long long ngroups = ((long long)B + 31) >> 5;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long cidx = warp0; cidx < nchunks; cidx += nwarps) {
-        const long long group = cidx >> 3;                              // 8 chunks of 4 hands per 32-hand group
-        const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + 48 * (int)(cidx & 7);
+        const long long group = cidx / (32 / VS_HC);                    // 4 chunks of 8 hands per 32-hand group
+        const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + VS_TN * (int)(cidx % (32 / VS_HC));
         unsigned char* out = bones_op + (size_t)cidx * (VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {                                  // 96 (bone, n-group) items per chunk: three per lane
-            const int i = lane + 32 * r, k = i / 6, g = i - 6 * k;
+        for (int r = 0; r < NJ * (VS_TN / 8) / 32; ++r) {              // 192 (bone, n-group) items per chunk: six per lane
+            const int i = lane + 32 * r, k = i / (VS_TN / 8), g = i - (VS_TN / 8) * k;
             float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
             if (group < ngroups) {
                 const float4* p = reinterpret_cast<const float4*>(src0 + (size_t)k * (BONE_F * 32) + 8 * g);
@@ -468,15 +469,19 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     const uint32_t stage = tcnt % VS_TSTAGES, use = tcnt / VS_TSTAGES;
                     VS_WAIT(&S.t_full[stage], use & 1, 1);
                     tc_fence_after();
-                    VS_TIC;
                     const uint32_t t_addr = tmem + lane_addr + VS_T_COL0 + stage * VS_TN;
-                    uint32_t T[VS_TN];
-                    tmem_ld32_nowait(t_addr, T);
-                    tmem_ld16_nowait(t_addr + 32, T + 32);
+#pragma unroll
+                  for (int half = 0; half < VS_HC / VS_HH; ++half) {   // the chunk's 96 columns in two register loads of 4 hands
+                    VS_TIC;
+                    uint32_t T[VS_HH * BONE_F];
+                    tmem_ld32_nowait(t_addr + half * (VS_HH * BONE_F), T);
+                    tmem_ld16_nowait(t_addr + half * (VS_HH * BONE_F) + 32, T + 32);
                     tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[stage]));
+                    if (half == VS_HC / VS_HH - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&S.t_empty[stage]));
+                    }
                     VS_TOC(2);
                     if (variant & 0x200) continue;                     // 0x200: experiment, handshakes only
                     long long _tic2 = 0;
@@ -484,8 +489,8 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     _tic2 = clock64();
 #endif
 #pragma unroll
-                    for (int hl = 0; hl < VS_HC; ++hl) {
-                        const int hi = c8 * VS_HC + hl;                // hand inside the set
+                    for (int hl = 0; hl < VS_HH; ++hl) {
+                        const int hi = c8 * VS_HC + half * VS_HH + hl; // hand inside the set
                         const float x = X[hi], y = Y[hi], z = Z[hi];
                         float o[3];
 #pragma unroll
@@ -493,7 +498,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                             const float* Ti = reinterpret_cast<const float*>(T) + hl * 12 + 4 * i;
                             o[i] = ost * fmaf(Ti[0], x, fmaf(Ti[1], y, fmaf(Ti[2], z, Ti[3])));
                         }
-                        if (dbg != nullptr && tile == 0 && t == 0 && set == 0 && c8 == 0) {
+                        if (dbg != nullptr && tile == 0 && t == 0 && set == 0 && c8 == 0 && half == 0) {
                             float* dd = dbg + ((size_t)hl * VS_M + vl) * 16;
 #pragma unroll
                             for (int i = 0; i < 12; ++i) dd[i] = ost * __uint_as_float(T[hl * 12 + i]);
@@ -523,6 +528,7 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     prof[3] += clock64() - _tic2;
 #endif
                     (void)_tic2;
+                  }
                 }
             }
         }

@@ -10,15 +10,15 @@ namespace mb {
 constexpr int VS_M = 128;                          // vertices per tile = TMEM lanes = MMA M
 constexpr int VS_NT = (NV + VS_M - 1) / VS_M;      // 7 vertex tiles (the last one holds 10 vertices)
 constexpr int VS_NH = 64;                          // hands per hand tile = MMA N of the blend products
-constexpr int VS_HC = 4;                           // hands per transform chunk
-constexpr int VS_NCH = VS_NH / VS_HC;              // 16 chunks per hand tile
-constexpr int VS_TN = VS_HC * BONE_F;              // 48 = MMA N of the transform products: (hand, 3x4 element)
+constexpr int VS_HC = 8;                           // hands per transform chunk
+constexpr int VS_NCH = VS_NH / VS_HC;              // 8 chunks per hand tile
+constexpr int VS_TN = VS_HC * BONE_F;              // 96 = MMA N of the transform products: (hand, 3x4 element)
 constexpr int VS_A_STAGE_BYTES = 2 * VS_M * TC_K_CHUNK * 2;      // 16 KB: hi + lo of one (tile, plane, K chunk)
 constexpr int VS_STAGES_PER_TILE = 3 * TC_K_CHUNKS;              // 15: (plane, K chunk)
 constexpr int VS_W_SPLITS = 2;
 constexpr int VS_W_TILE_BYTES = VS_W_SPLITS * VS_M * NJ * 2;     // 8 KB: two fp16 splits of W[128 vertices][16 bones]
 constexpr int VS_BONE_SPLITS = 3;
-constexpr int VS_BONE_CHUNK_BYTES = VS_TN * NJ * 2;              // 1536 B: one split of one chunk, MN-major [6 n-groups][2 k-groups][8 k][8 n]
+constexpr int VS_BONE_CHUNK_BYTES = VS_TN * NJ * 2;              // 3072 B: one split of one chunk, MN-major [12 n-groups][2 k-groups][8 k][8 n]
 constexpr int VS_BONE_TILE_BYTES = VS_NCH * VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES;   // 73 728 B per 64 hands
 constexpr int VS_W_SCALE_LOG2 = 8;                 // skinning weights (<= 1) are pre-scaled by 2^8 before the fp16 split
 constexpr int VS_BONE_SCALE_LOG2 = 4;              // bone transforms (|R| <= 1, |t| < ~1 m) by 2^4: fp16 overflow only beyond 4 km

@@ -58,7 +58,7 @@ def run(flags, n=10):
 
 
 out = {"hands": H}
-ms, st = run(cabi.FWD_INFERENCE)
+ms, st = run(cabi.FWD_INFERENCE | cabi.FWD_UNFUSED)
 ref = verts.clone()
 out["separate"] = {"ms": ms, "stages": st}
 print("separate kernels", round(ms, 4), st, flush=True)
