@@ -5,20 +5,20 @@
 // fingertip vertices become joints 4,8,12,16,20) and :188,:204-205 (global rotation — already
 // folded into the bone transforms by the pose stage, so it costs nothing here).
 //
-// Round-1 ncu of the previous lane=hand kernel (bones in shared memory, one vertex at a time):
-// l1tex data pipe 76 % busy, 1 321 shared-memory wavefronts per hand — three 16-byte bone rows per
-// (vertex, bone) pair per lane.  This version keeps the bone transform in REGISTERS and amortises
-// it over a block of 8 vertices:
+// Round-1 ncu of the first lane = hand kernel (bones in shared memory, one vertex at a time): l1tex data pipe 76 % busy,
+// 1 321 shared-memory wavefronts per hand — three 16-byte bone rows per (vertex, bone) pair per lane.  This version keeps the
+// bone transform in REGISTERS and amortises it over a block of 8 vertices (DESIGN.md 3.3 has the measured path):
 //   * a warp owns 32 hands (lane = hand) and sweeps all vertices on its own — no block barriers;
-//   * the rest-pose vertices arrive hand-minor (v_posed_t[group][coord][32], written that way by the
-//     blend GEMM's epilogue), so a coordinate of 32 hands is one coalesced 128-byte load and a block
-//     of 8 vertices is 24 registers per lane;
-//   * the host-built skin program lists, per block, its distinct bones and a dense 8-vector of
-//     weights per bone; a bone transform is fetched (12 coalesced loads from the hand-minor bone_t,
-//     L1/L2 hits) once per (block, bone) — 359 times per sweep for MANO instead of 2 028;
-//   * zero weights are skipped by a WARP-UNIFORM branch (weights are shared-memory broadcasts);
-//   * results are transposed through a 12 KB per-warp tile (XOR-swizzled, conflict-free both ways)
-//     and leave as 384-byte row pieces of verts[B][778][3] (8-byte vectors: rows are 8-byte aligned).
+//   * the rest-pose vertices arrive hand-minor (v_posed_t[group][coord][32], written that way by the blend GEMM's
+//     epilogue) through a 2-slot bulk-copy (TMA engine) ring: a block of 8 vertices of a hand group is 3 KB contiguous and
+//     becomes 12 packed register pairs per lane;
+//   * the host-built skin program (skin_pack) lists, per block, its distinct bones with a dense 8-vector of weights per bone
+//     (443 entries synthetic / 386 MANO); every entry updates all 8 vertices DENSE with packed fp32 FFMA2 (48 per entry) —
+//     at 59 % density the branches of a skip-if-zero form cost as many issue slots as the zeros;
+//   * bone transforms of the hand group are resident in six 1.5 KB shared-memory slots per warp, (re)loaded by bulk copies
+//     on a static Belady schedule computed on the host (89 / 65 copies per sweep instead of one per entry);
+//   * results are transposed through a 7.4 KB per-warp tile per 16-vertex segment and leave as one contiguous,
+//     sector-aligned run per row of verts[B][778][3] (the row pitch is 24 mod 32 bytes: per-row windows with carry slots).
 //
 // Backward:  dv_posed_v = sum_k w_vk R'_k^T g_v  and
 // dA'_k = sum_v w_vk g_v (x) [v_posed_v ; 1].  Two warps share a hand group and a g_verts tile:
