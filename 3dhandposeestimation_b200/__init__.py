@@ -16,8 +16,9 @@ from .criterions import L2Loss, MPJPE, compute_hand_mask_loss, compute_regulariz
 from .fk_layer import ForwardKinematics, batch_project_xyz_to_uv, mano_joints_to_rhd_uv, match_mano_to_RHD  # noqa: F401
 from .keypoint_trafo import bone_rel_trafo, bone_rel_trafo_inv, canonical_trafo, flip_right_hand, mirror_left_hand  # noqa: F401
 from .mano_layer import ManoLayer  # noqa: F401
+from .head_loss import ManoHeadLoss  # noqa: F401
 from .viewpoint import _get_rot_mat, viewpoint_transform  # noqa: F401
 
-__all__ = ["ManoLayer", "ForwardKinematics", "batch_project_xyz_to_uv", "match_mano_to_RHD", "mano_joints_to_rhd_uv",
+__all__ = ["ManoLayer", "ManoHeadLoss", "ForwardKinematics", "batch_project_xyz_to_uv", "match_mano_to_RHD", "mano_joints_to_rhd_uv",
            "bone_rel_trafo", "bone_rel_trafo_inv", "canonical_trafo", "flip_right_hand", "mirror_left_hand", "_get_rot_mat", "viewpoint_transform", "MPJPE", "L2Loss",
            "compute_regularization_loss", "compute_hand_mask_loss", "install_into_reference", "ManoB200Error", "assets", "load_library"]

@@ -22,6 +22,7 @@ FWD_INFERENCE = 0x200
 FWD_FUSED = 0x400
 FWD_UNFUSED = 0x800
 REDUCE_MPJPE_MM, REDUCE_L2 = 0, 1
+HEAD_XYZ, HEAD_UV, HEAD_REG, HEAD_MATCH = 1, 2, 4, 8
 VIS_F32, VIS_U8 = 0, 1
 
 _p = C.c_void_p
@@ -64,6 +65,10 @@ SIGNATURES = {
     "mb_masked_l2_backward": (_i, [_p, _p, _p, _i, _ll, _i, _p, _p, _p, _p]),
     "mb_regulariser_forward": (_i, [_p, _ll, _p, _ll, _f, _p, _p, _p]),
     "mb_regulariser_backward": (_i, [_p, _ll, _p, _ll, _f, _p, _p, _p, _p, _p]),
+    "mb_mano_head_loss_workspace_bytes": (_sz, [_i]),
+    "mb_mano_head_loss_forward": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _sz, _p]),
+    "mb_mano_head_loss_backward": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p,
+                                        _p, _p, _p, _sz, _p]),
     "mb_hand_mask_loss": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mb_mano_fit_step": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _f, _f, _f, _f, _i, _i, _p]),
     "mb_fit_finalize": (_i, [_p, _p, _i, _p, _p, _p]),

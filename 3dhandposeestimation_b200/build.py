@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmano_b200.so")
-SOURCES = ["api.cu", "mano_pose.cu", "mano_pose_lh.cu", "sgemm.cu", "blend_tc.cu", "vskin.cu", "skin.cu", "fk.cu", "joint_epilogue.cu", "hand_trafo.cu", "viewpoint.cu", "reduce.cu", "affine.cu"]
+SOURCES = ["api.cu", "mano_pose.cu", "mano_pose_lh.cu", "sgemm.cu", "blend_tc.cu", "vskin.cu", "skin.cu", "fk.cu", "joint_epilogue.cu", "hand_trafo.cu", "viewpoint.cu", "reduce.cu", "affine.cu", "head_loss.cu"]
 HEADERS = ["common.cuh", "hand_math.cuh", "fk_math.cuh", "blend_tc.cuh", "vskin.cuh", "tc_ptx.cuh", "skin.cuh", "ptx.cuh", os.path.join("..", "..", "include", "mano_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

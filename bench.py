@@ -596,10 +596,49 @@ def run_extras(args, pkg, layer45, dev, rank, world, dist, set0):
 
         ms_h = timed(head_step, 64)
         ms_f = timed(full_step, 64)
+        # the heads' whole tail in one call per direction (mb_mano_head_loss_*: parameters -> joints -> match_mano_to_RHD ->
+        # projection -> L2 xyz + L2 uv + regulariser, and back), per launch sequence and replayed as ONE captured CUDA graph
+        hws = torch.empty(max(lib.mb_mano_head_loss_workspace_bytes(B), 16), dtype=torch.uint8, device=dev)
+        hK = torch.tensor([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1.]], device=dev).repeat(B, 1, 1).contiguous()
+        hL = torch.rand(B, device=dev) * .05 + .02
+        hroot = torch.randn(B, 3, device=dev) * .05 + torch.tensor([0, 0, .6], device=dev)
+        hgx, hgu = torch.randn(B, 21, 3, device=dev) * .05 + hroot[:, None, :], torch.rand(B, 21, 2, device=dev) * 320
+        hvis = (torch.rand(B, 21, device=dev) < .8).float()
+        hxyz, huv = torch.empty(B, 21, 3, device=dev), torch.empty(B, 21, 2, device=dev)
+        hloss, hgl = torch.empty(3, device=dev), torch.ones(3, device=dev)
+        hflags = cabi.HEAD_XYZ | cabi.HEAD_UV | cabi.HEAD_REG | cabi.HEAD_MATCH
+
+        def head_loss_step(stream=st):
+            s = sets[it[0] % nsets]
+            it[0] += 1
+            a = (P(layer10._blob), 10, P(s["rot"]), P(s["pose"]), P(s["beta"]), None, None, P(hL), P(hroot), P(hK), P(hgx), P(hgu),
+                 P(hvis), B, layer10._mode, hflags, 0, 10.0)
+            cabi.check(lib.mb_mano_head_loss_forward(*a, P(hxyz), P(huv), P(hloss), P(hws), hws.numel(), stream), "head fwd")
+            cabi.check(lib.mb_mano_head_loss_backward(*a, P(hxyz), P(huv), P(hgl), P(s["g"][0]), P(s["g"][1]), P(s["g"][2]), None, None,
+                                                      P(hws), hws.numel(), stream), "head bwd")
+
+        ms_hl = timed(head_loss_step, 64)
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):
+            it[0] = 0
+            head_loss_step(cap.cuda_stream)                    # warm-up on the capture stream
+            cap.synchronize()
+            with torch.cuda.graph(graph, stream=cap):
+                for _ in range(nsets):
+                    head_loss_step(cap.cuda_stream)
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        ms_hg = timed(graph.replay, 8) / nsets
         c2[f"B{B}"] = {"joints_only_fwd+bwd_ms": ms_h, "joints_only_hands_per_s": world * B / (ms_h * 1e-3),
-                       "verts_fwd+bwd_ms": ms_f, "verts_hands_per_s": world * B / (ms_f * 1e-3)}
-        del sets, ws
-    c2["note"] = "C ABI, 16 rotating buffer sets, pose_num 10, head value ranges; joints only = what the heads consume (resnet50MANO.py:76,87)"
+                       "verts_fwd+bwd_ms": ms_f, "verts_hands_per_s": world * B / (ms_f * 1e-3),
+                       "head_loss_fwd+bwd_ms": ms_hl, "head_loss_graph_fwd+bwd_ms": ms_hg,
+                       "head_loss_hands_per_s": world * B / (ms_hg * 1e-3)}
+        del sets, ws, graph
+    c2["note"] = ("C ABI, 16 rotating buffer sets, pose_num 10, head value ranges; joints only = what the heads consume "
+                  "(resnet50MANO.py:76,87); head_loss = the heads' whole tail, one call per direction (parameters -> joints -> "
+                  "match_mano_to_RHD -> projection -> L2 xyz + L2 uv + regulariser and its backward), `graph` = 16 steps replayed as one "
+                  "captured CUDA graph")
     out["config2_head"] = c2
 
     # ---- config 3: FK ----

@@ -277,6 +277,42 @@ MB_API int mb_regulariser_backward(const float* theta, long long n_theta, const 
 MB_API int mb_hand_mask_loss(const float* pred_uv, const float* gt_uv, const void* hand_mask, int mask_kind, int B, int N,
                       int H, int W, double* accum, float* out, mb_stream_t stream);
 
+/* ------------------------------------------------- the MANO heads' tail in one call ---
+ * MANO parameters -> 21 joints (joints-only kernels) [-> scale * p + transl, resnet50MANO.py:77-81]
+ * [-> match_mano_to_RHD, Resnet50MANO3DHandPose.py:35-60] -> batch_project_xyz_to_uv (:71-73) ->
+ * L2Loss on xyz and on uv (criterions/loss.py:10-25, :83-87) + compute_regularization_loss (:113-117), as the
+ * training loop combines them (trainval.py:328-358).  One call enqueues the kernels of every piece back to back on
+ * `stream` (no host round trip, capturable in a CUDA graph); `flags` selects the terms:
+ *   MB_HEAD_XYZ / MB_HEAD_UV / MB_HEAD_REG  which of losses[0..2] = {loss_xyz, loss_uv, loss_regularization} are
+ *                                           computed (the others are 0);  MB_HEAD_MATCH  apply match_mano_to_RHD
+ *                                           (swap_order as in mb_joint_epilogue_forward), else xyz = the joints.
+ * transl[B][3] / scale[B] may be NULL; index_root_bone_length[B] / kp_coord_xyz_root[B][3] are needed with
+ * MB_HEAD_MATCH only; keypoint_vis[B][21] fp32 (non-zero = visible); gt_xyz[B][21][3], gt_uv[B][21][2].
+ * Outputs: joint_xyz21[B][21][3], uv21[B][21][2] (what the head returns), losses (device float[3]).
+ * The workspace (mb_mano_head_loss_workspace_bytes) and the two outputs must reach the backward untouched.
+ * Backward: g_losses = device float[3], the upstream gradients of the three terms -> g_rot[B][3], g_coeffs[B][nc],
+ * g_betas[B][10] and (each nullable) g_transl[B][3], g_scale[B]. */
+#define MB_HEAD_XYZ   1
+#define MB_HEAD_UV    2
+#define MB_HEAD_REG   4
+#define MB_HEAD_MATCH 8
+MB_API size_t mb_mano_head_loss_workspace_bytes(int B);
+MB_API int mb_mano_head_loss_forward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                              const float* transl, const float* scale,
+                              const float* index_root_bone_length, const float* kp_coord_xyz_root, const float* K,
+                              const float* gt_xyz, const float* gt_uv, const float* keypoint_vis,
+                              int B, int mode, int flags, int swap_order, float alpha_beta,
+                              float* joint_xyz21, float* uv21, float* losses,
+                              void* workspace, size_t workspace_bytes, mb_stream_t stream);
+MB_API int mb_mano_head_loss_backward(const void* blob, int nc, const float* rot, const float* coeffs, const float* betas,
+                               const float* transl, const float* scale,
+                               const float* index_root_bone_length, const float* kp_coord_xyz_root, const float* K,
+                               const float* gt_xyz, const float* gt_uv, const float* keypoint_vis,
+                               int B, int mode, int flags, int swap_order, float alpha_beta,
+                               const float* joint_xyz21, const float* uv21, const float* g_losses,
+                               float* g_rot, float* g_coeffs, float* g_betas, float* g_transl, float* g_scale,
+                               void* workspace, size_t workspace_bytes, mb_stream_t stream);
+
 /* ----------------------------------------------------------- fitting loop ---
  * One Adam update on a flat fp32 parameter array (torch.optim.Adam semantics, no
  * weight decay, no amsgrad): used by the batched MANO fitting loop (BASELINE config 5). */

@@ -170,6 +170,45 @@ def match_case(B, seed, switched):
                 g_uv=n(gu), g_joints=n(j.grad), g_scale=n(L.grad), g_root=n(root.grad), switched=np.array(switched))
 
 
+def head_loss_case(pkl, nc, B, seed, match, switched=True):
+    """The MANO heads' tail end to end through the unmodified reference: ManoLayer -> scale * joints + transl
+    (resnet50MANO.py:77-81) -> [match_mano_to_RHD, Resnet50MANO3DHandPose.py:35-60] -> batch_project_xyz_to_uv (:73) ->
+    LossCalculation(xyz, uv, regularisation) (criterions/loss.py:62-153), weighted sum, autograd to every input."""
+    from criterions.loss import LossCalculation
+    from network.Resnet50MANO3DHandPose import Resnet50MANO3DHandPose
+    ref.config.joint_order_switched = switched
+    layer = ref.ManoLayer("cpu", pkl, pose_num=nc)
+    g = torch.Generator().manual_seed(seed)
+    rot = ((torch.rand(B, 3, generator=g) - .5) * 2).requires_grad_()
+    pose = ((torch.rand(B, nc, generator=g) - .5) * 2).requires_grad_()
+    beta = (torch.rand(B, 10, generator=g) - .5).requires_grad_()
+    transl = (torch.randn(B, 3, generator=g) * .05 + torch.tensor([0, 0, .6])).requires_grad_()
+    scale = (torch.rand(B, generator=g) * .4 + .8).requires_grad_()
+    L = torch.rand(B, 1, generator=g) * .05 + .02
+    root = torch.randn(B, 3, generator=g) * .05 + torch.tensor([0, 0, .6])
+    K = torch.tensor([[282.9, 0, 160], [0, 282.9, 160], [0, 0, 1.]]).repeat(B, 1, 1)
+    vis = (torch.rand(B, 21, 1, generator=g) < .8).float()
+    _, j = layer(rot, pose, beta)
+    j = scale.unsqueeze(1).unsqueeze(2) * j + transl.unsqueeze(1)
+    if match:
+        _, xyz = Resnet50MANO3DHandPose.match_mano_to_RHD(None, j.clone(), L, root)
+    else:
+        xyz = j
+    uv = ref.batch_project_xyz_to_uv(xyz, K)
+    gt_xyz = xyz.detach() + torch.randn(B, 21, 3, generator=g) * .05     # offsets well above the fp32 noise of the chain
+    gt_uv = uv.detach() + torch.randn(B, 21, 2, generator=g) * 20.0
+    crit = LossCalculation("cpu", comp_xyz_loss=True, comp_uv_loss=True, comp_regularization_loss=True)
+    loss_xyz, loss_uv, _, _, loss_reg = crit(xyz, gt_xyz, uv, gt_uv, vis, theta=pose, beta=beta)
+    w = torch.tensor([1.0, 1e-4, 0.5])
+    (w[0] * loss_xyz + w[1] * loss_uv + w[2] * loss_reg).backward()
+    ref.config.joint_order_switched = True
+    n = lambda t: t.detach().contiguous().numpy()
+    return dict(rot=n(rot), pose=n(pose), beta=n(beta), transl=n(transl), scale=n(scale), L=n(L), root=n(root), K=n(K), vis=n(vis),
+                gt_xyz=n(gt_xyz), gt_uv=n(gt_uv), xyz=n(xyz), uv=n(uv), losses=np.array([loss_xyz.item(), loss_uv.item(), loss_reg.item()]),
+                weights=n(w), g_rot=n(rot.grad), g_pose=n(pose.grad), g_beta=n(beta.grad), g_transl=n(transl.grad),
+                g_scale=n(scale.grad), match=np.array(match), switched=np.array(switched))
+
+
 def trafo_case(B, seed):
     """bone_rel_trafo / bone_rel_trafo_inv / canonical_trafo / flip_right_hand on hand-like keypoints
     (root-relative, normalised: joint 0 at the origin, bones ~0.3-1 long)."""
@@ -237,6 +276,10 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         pkl = os.path.join(td, "synthetic_mano.pkl")
         assets.write_reference_style_pkl(model, pkl)
+        np.savez_compressed(os.path.join(HERE, "head_loss_match.npz"), **head_loss_case(pkl, 10, 7, 91, True, switched=False))
+        np.savez_compressed(os.path.join(HERE, "head_loss_plain.npz"), **head_loss_case(pkl, 45, 6, 92, False))
+        if len(sys.argv) > 1 and sys.argv[1] == "head_loss":       # only the fixtures added in round 2
+            return
         np.savez_compressed(os.path.join(HERE, "mano_synth_nc45.npz"), **mano_case(pkl, 45, 4, 1234))
         np.savez_compressed(os.path.join(HERE, "mano_synth_nc10.npz"), **mano_case(pkl, 10, 4, 1234))
         np.savez_compressed(os.path.join(HERE, "mano_synth_nc6.npz"), **mano_case(pkl, 6, 3, 99, scale_pose=4.0))

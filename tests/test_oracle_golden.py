@@ -183,3 +183,22 @@ def test_fp32_port_noise_floor(synth_model):
     worst, q = float(err.max()), float(np.quantile(err, 0.9999))
     assert 4e-8 < worst < 1.5e-7, worst
     assert q < 1e-7, q
+
+
+@pytest.mark.parametrize("name", ["head_loss_match.npz", "head_loss_plain.npz"])
+def test_head_loss_oracle_matches_reference_golden(synth_model, name):
+    """The heads' tail (ManoLayer -> scale / transl -> [match_mano_to_RHD] -> projection -> L2 xyz + L2 uv + regulariser)
+    composed from the oracle pieces against the unmodified reference's losses and autograd gradients."""
+    from oracle import head_oracle as ho
+
+    g = load_golden(name)
+    r = ho.head_loss(synth_model, g["rot"], g["pose"], g["beta"], g["transl"], g["scale"], g["L"], g["root"], g["K"], g["gt_xyz"],
+                     g["gt_uv"], g["vis"], bool(g["match"]), switched=bool(g["switched"]))
+    # match_mano_to_RHD divides by ||joint 12 - root||: the reference's fp32 noise is relative to the normalised coordinates
+    assert rel(r["xyz"], g["xyz"]) < 2e-5
+    assert np.abs(r["uv"] - g["uv"]).max() < 2e-2
+    assert np.abs(r["losses"] / g["losses"] - 1).max() < 2e-4
+    scale_ref = max(np.abs(g["g_rot"]).max(), np.abs(g["g_pose"]).max())
+    for got, key in zip(r["grads"](g["weights"]), ("g_rot", "g_pose", "g_beta", "g_transl", "g_scale")):
+        # with match_mano_to_RHD the losses do not depend on transl / scale: both gradients are ~0 (fp32 noise in the reference)
+        assert np.abs(got - g[key]).max() < 1e-3 * max(np.abs(g[key]).max(), 0.05 * scale_ref), key
