@@ -59,7 +59,8 @@ def ncu_traffic_per_hand():
         path = os.path.join(ROOT, "profiles", rnd, "traffic_final.json")
         if os.path.isfile(path):
             d = json.load(open(path))["kernels"]
-            out.update({k: ((v["dram_read_bytes"] + v["dram_write_bytes"]) / v["hands"], rnd) for k, v in d.items()})
+            out.update({k: ((v["dram_read_bytes"] + v["dram_write_bytes"]) / v["hands"], rnd,
+                            {x: round(y, 1) for x, y in v.items() if x.endswith("_pct")}) for k, v in d.items()})
     return out
 
 
@@ -832,7 +833,9 @@ def main():
                 "frac": gbs / peaks["hbm_gbs"], "traffic": tr[0] * H if tr else None,
                 "traffic_source": f"ncu dram__bytes_read+write per hand (profiles/{tr[1]}/traffic_final.json) x hands" if tr else None,
                 "peak_source": peaks["source"], "algorithmic_bytes_per_hand": bytes_per_hand, "avg_launch_ms": ms,
-                "share_of_step": stages[stage]["share"] if stage in stages else None}
+                "share_of_step": stages[stage]["share"] if stage in stages else None,
+                # utilisation of the units that can bound the kernel, from the committed ncu capture (percent of peak)
+                "ncu_unit_utilisation_pct": tr[2] if tr else None}
 
     stage_bytes = {"lbs_bwd": BYTES_LBS_BWD, "lbs_fwd": BYTES_LBS, "fused_fwd": BYTES_FUSED_FWD_TRAIN}
     dominant = max(stages, key=lambda k: stages[k]["ms"])
@@ -931,7 +934,10 @@ def main():
         fms = fstages["fused_fwd"]
         lbs_fwd_roof = hbm_roofline("fused_fwd", BYTES_FUSED_FWD, ms=fms)
         lbs_fwd_roof["note"] = ("fused blend + skinning forward (vskin.cu + its bone-operand pre-pass), inference launch: feature tiles 640 + bone transforms 768 B in, "
-                                "verts 9336 + fingertip joints 60 B out per hand")
+                                "verts 9336 + fingertip joints 60 B out per hand.  The fused kernel is NOT HBM-bound (that is the point of fusing): its "
+                                "bound is the SM's L1 / shared-memory data pipe — tensor-core operand reads + the result stores, together ~88 % busy in the "
+                                "ncu capture (ncu_unit_utilisation_pct: l1_data_pipe_tensor_operand + l1_data_pipe_lsu); the HBM-bound figure of the unfused "
+                                "skinning kernel is in forward_only.unfused_ab")
         tfl = (FLOP_BLEND + FLOP_SKIN_T) * H / (fms * 1e-3) / 1e12
         blend_roof = {"kernel": "vskin_forward_kernel", "bound": "tensor", "achieved": tfl, "peak": peaks["bf16_tflops_sustained"],
                       "unit": "TFLOP/s", "frac": tfl / peaks["bf16_tflops_sustained"],

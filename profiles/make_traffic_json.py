@@ -20,6 +20,18 @@ for r in rows[2:]:
     out[name] = {"time_ms": f("gpu__time_duration.sum"), "dram_read_bytes": f("dram__bytes_read.sum"),
                  "dram_write_bytes": f("dram__bytes_write.sum"), "hands": hands, "lts_sectors": f("lts__t_sectors.sum"),
                  "warp_inst": f("smsp__inst_executed.sum")}
+    # utilisation of the units that can bound a kernel (percent of peak), when the capture has them
+    for key, metric in (("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                        ("tensor_pipe_pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                        ("issue_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        ("l1_data_pipe_tensor_operand_pct", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                        ("l1_data_pipe_lsu_pct", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+                        ("l2_pct", "lts__t_sectors.sum.pct_of_peak_sustained_elapsed")):
+        if metric in h:
+            try:
+                out[name][key] = float(r[h.index(metric)])
+            except ValueError:
+                pass
 json.dump({"source": sys.argv[2] if len(sys.argv) > 2 else "", "units": {"dram_*": "bytes per launch", "time_ms": "cold-cache serialised ncu time"},
            "kernels": out}, sys.stdout, indent=1)
 print()
