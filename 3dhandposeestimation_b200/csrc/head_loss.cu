@@ -5,11 +5,14 @@
 // network/Resnet50MANO3DHandPose.py:35-60 (match_mano_to_RHD), :71-73 (batch_project_xyz_to_uv),
 // criterions/loss.py:10-25 (L2Loss), :83-87 (xyz / uv losses), :113-117 (regulariser), trainval.py:328-358.
 //
-// The two entry points enqueue the kernels that already implement each piece (and are pinned to the reference
-// piece by piece) back to back on the caller's stream: no host round trip, no torch op and no allocation between
-// them — at the heads' batch sizes (config.py:79: 200) the path is launch-latency-bound, and one ctypes call that
-// can be captured in a CUDA graph replaces ~10 autograd nodes.  All scratch lives in a caller-provided workspace
-// that must stay untouched between the forward and its backward.
+// The two entry points enqueue, back to back on the caller's stream, the kernels that already implement the geometric
+// pieces (joints-only MANO forward / backward, scale + translation, joint epilogue — each pinned to the reference on
+// its own) and three small kernels of this file for the loss terms: all three reductions + their finalisation in one
+// launch, both L2 gradients in one, the regulariser's gradient accumulated into the pose / shape gradients in one.
+// No host round trip, no torch op and no allocation in between — at the heads' batch sizes (config.py:79: 200) the
+// path is launch-latency-bound, and one ctypes call that can be captured in a CUDA graph replaces ~10 autograd
+// nodes.  Forward: 3-4 launches + one 64-byte memset; backward: 4-5 launches.  All scratch lives in a caller-provided
+// workspace that must stay untouched between the forward and its backward.
 #include "common.cuh"
 
 using namespace mb;
@@ -22,6 +25,104 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 __global__ void zero_kernel(float* __restrict__ dst, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = 0.f;
 }
+constexpr int HL_THREADS = 256;
+
+// All three loss terms in ONE launch: fp64 block sums -> atomics into accum[0..5] = {S_xyz, N_xyz, S_uv, N_uv, sum theta^2,
+// sum beta^2}; the block that finishes last (ticket in accum[6]) writes losses[0..2].  The same arithmetic as
+// masked_reduce_kernel / sumsq2_kernel + their finalisers (reduce.cu), which remain the stand-alone drop-ins.
+__global__ void __launch_bounds__(HL_THREADS)
+head_reduce_kernel(const float* __restrict__ xyz, const float* __restrict__ gt_xyz, const float* __restrict__ uv,
+                   const float* __restrict__ gt_uv, const float* __restrict__ vis, long long nj,
+                   const float* __restrict__ theta, long long n_theta, const float* __restrict__ beta, long long n_beta,
+                   int flags, float alpha_beta, double* __restrict__ accum, float* __restrict__ losses) {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (flags & (MB_HEAD_XYZ | MB_HEAD_UV))
+        for (long long i = i0; i < nj; i += stride)
+            if (vis[i] != 0.f) {
+                if (flags & MB_HEAD_XYZ) {
+                    const float a = xyz[i * 3] - gt_xyz[i * 3], b = xyz[i * 3 + 1] - gt_xyz[i * 3 + 1], c = xyz[i * 3 + 2] - gt_xyz[i * 3 + 2];
+                    v[0] += (double)(a * a + b * b + c * c);       // same order as the reference's sum(dim=2)
+                    v[1] += 1.0;
+                }
+                if (flags & MB_HEAD_UV) {
+                    const float a = uv[i * 2] - gt_uv[i * 2], b = uv[i * 2 + 1] - gt_uv[i * 2 + 1];
+                    v[2] += (double)(a * a + b * b);
+                    v[3] += 1.0;
+                }
+            }
+    if (flags & MB_HEAD_REG) {
+        for (long long i = i0; i < n_theta; i += stride) { const float x = theta[i]; v[4] += (double)x * x; }
+        for (long long i = i0; i < n_beta; i += stride) { const float x = beta[i]; v[5] += (double)x * x; }
+    }
+    __shared__ double sh[HL_THREADS / 32][6];
+    __shared__ bool last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[warp][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; ++k) {
+            double x = 0.0;
+            for (int w = 0; w < HL_THREADS / 32; ++w) x += sh[w][k];
+            if (x != 0.0) atomicAdd(&accum[k], x);
+        }
+        __threadfence();
+        last = atomicAdd(reinterpret_cast<unsigned long long*>(&accum[6]), 1ULL) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const volatile double* a = accum;
+        losses[0] = (flags & MB_HEAD_XYZ) && a[1] > 0.0 ? (float)(a[0] / a[1]) : 0.f;
+        losses[1] = (flags & MB_HEAD_UV) && a[3] > 0.0 ? (float)(a[2] / a[3]) : 0.f;
+        losses[2] = (flags & MB_HEAD_REG) ? (sqrtf((float)a[4]) + alpha_beta * sqrtf((float)a[5])) / 100.f : 0.f;
+    }
+}
+
+// d(loss_xyz) / d(xyz) and d(loss_uv) / d(uv) in one launch (masked_l2_backward_kernel twice)
+__global__ void __launch_bounds__(HL_THREADS)
+head_l2_backward_kernel(const float* __restrict__ xyz, const float* __restrict__ gt_xyz, const float* __restrict__ uv,
+                        const float* __restrict__ gt_uv, const float* __restrict__ vis, long long nj, int flags,
+                        const double* __restrict__ accum, const float* __restrict__ g_losses, float* __restrict__ g_xyz,
+                        float* __restrict__ g_uv) {
+    const float sx = (flags & MB_HEAD_XYZ) && accum[1] > 0.0 ? (float)(2.0 * (double)g_losses[0] / accum[1]) : 0.f;
+    const float su = (flags & MB_HEAD_UV) && accum[3] > 0.0 ? (float)(2.0 * (double)g_losses[1] / accum[3]) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nj; i += (long long)gridDim.x * blockDim.x) {
+        const bool m = vis[i] != 0.f;
+        if (flags & MB_HEAD_XYZ) {
+            const float k = m ? sx : 0.f;
+            for (int c = 0; c < 3; ++c) g_xyz[i * 3 + c] = k * (xyz[i * 3 + c] - gt_xyz[i * 3 + c]);
+        }
+        if (flags & MB_HEAD_UV) {
+            const float k = m ? su : 0.f;
+            for (int c = 0; c < 2; ++c) g_uv[i * 2 + c] = k * (uv[i * 2 + c] - gt_uv[i * 2 + c]);
+        }
+    }
+}
+
+// the regulariser's gradient ADDED to the pose / shape gradients: g_theta += g theta / (100 ||theta||),
+// g_beta += g alpha beta / (100 ||beta||), 0 at a zero norm (regulariser_backward_kernel + two accumulations)
+__global__ void __launch_bounds__(HL_THREADS)
+head_reg_backward_add_kernel(const float* __restrict__ theta, long long n_theta, const float* __restrict__ beta, long long n_beta,
+                             float alpha_beta, const double* __restrict__ accum, const float* __restrict__ g_losses,
+                             float* __restrict__ g_theta, float* __restrict__ g_beta) {
+    const float nt = sqrtf((float)accum[4]), nb = sqrtf((float)accum[5]), g = g_losses[2];
+    const float kt = nt > 0.f ? g / (100.f * nt) : 0.f, kb = nb > 0.f ? g * alpha_beta / (100.f * nb) : 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = i0; i < n_theta; i += stride) g_theta[i] += kt * theta[i];
+    for (long long i = i0; i < n_beta; i += stride) g_beta[i] += kb * beta[i];
+}
+unsigned hl_grid(long long n) {
+    const long long b = (n + HL_THREADS - 1) / HL_THREADS;
+    return (unsigned)(b < 1 ? 1 : (b < NUM_SMS * 4 ? b : NUM_SMS * 4));
+}
+
 int launch_add(float* dst, const float* src, long long n, cudaStream_t s) {
     const long long b = (n + 255) / 256;
     add_inplace_kernel<<<(unsigned)(b < NUM_SMS * 8 ? b : NUM_SMS * 8), 256, 0, s>>>(dst, src, n);
@@ -38,9 +139,7 @@ struct HeadWs {
     size_t g_xyz;       // float [B][21][3]
     size_t g_uv;        // float [B][21][2]
     size_t g_joints;    // float [B][21][3]
-    size_t g_theta;     // float [B][45]
-    size_t g_beta;      // float [B][10]
-    size_t accum;       // double [6]: {sum, count} of the xyz loss, of the uv loss, {sum theta^2, sum beta^2}
+    size_t accum;       // double [8]: {sum, count} of the xyz loss, of the uv loss, {sum theta^2, sum beta^2}, block ticket
     size_t total;
 };
 HeadWs head_ws(long long B) {
@@ -50,9 +149,7 @@ HeadWs head_ws(long long B) {
     W.g_xyz = o;    o = align256(o + sizeof(float) * B * 63);
     W.g_uv = o;     o = align256(o + sizeof(float) * B * 42);
     W.g_joints = o; o = align256(o + sizeof(float) * B * 63);
-    W.g_theta = o;  o = align256(o + sizeof(float) * B * NAA);
-    W.g_beta = o;   o = align256(o + sizeof(float) * B * 10);
-    W.accum = o;    o = align256(o + sizeof(double) * 6);
+    W.accum = o;    o = align256(o + sizeof(double) * 8);
     W.total = o;
     return W;
 }
@@ -94,17 +191,12 @@ extern "C" int mb_mano_head_loss_forward(const void* blob, int nc, const float* 
     } else {
         if ((rc = mb_project_uv_forward(joints, K, B, 21, uv21, stream))) return rc;
     }
-    // 3. the three loss terms, each a device scalar (terms not asked for are 0)
-    if ((rc = launch_zero(losses, 3, s))) return rc;
-    if (flags & MB_HEAD_XYZ)
-        if ((rc = mb_masked_joint_reduce(joint_xyz21, gt_xyz, keypoint_vis, MB_VIS_F32, (long long)B * 21, 3, MB_REDUCE_L2, accum,
-                                         losses, stream))) return rc;
-    if (flags & MB_HEAD_UV)
-        if ((rc = mb_masked_joint_reduce(uv21, gt_uv, keypoint_vis, MB_VIS_F32, (long long)B * 21, 2, MB_REDUCE_L2, accum + 2,
-                                         losses + 1, stream))) return rc;
-    if (flags & MB_HEAD_REG)
-        if ((rc = mb_regulariser_forward(coeffs, (long long)B * nc, betas, (long long)B * 10, alpha_beta, accum + 4, losses + 2,
-                                         stream))) return rc;
+    // 3. the three loss terms in one launch, each a device scalar (terms not asked for are 0)
+    if (cudaError_t e = cudaMemsetAsync(accum, 0, 8 * sizeof(double), s)) return (int)e;
+    const long long nj = (long long)B * 21, nt = (long long)B * nc, nb = (long long)B * 10;
+    head_reduce_kernel<<<hl_grid(nj > nt ? nj : nt), HL_THREADS, 0, s>>>(joint_xyz21, gt_xyz, uv21, gt_uv, keypoint_vis, nj, coeffs, nt, betas,
+                                                                         nb, flags, alpha_beta, accum, losses);
+    if ((rc = cuda_rc())) return rc;
     return 0;
 }
 
@@ -133,12 +225,11 @@ extern "C" int mb_mano_head_loss_backward(const void* blob, int nc, const float*
     int rc;
     // 1. d(loss terms) / d(xyz), d(uv), scaled by the upstream gradients of the terms
     const bool has_xyz = (flags & MB_HEAD_XYZ) != 0, has_uv = (flags & MB_HEAD_UV) != 0;
-    if (has_xyz)
-        if ((rc = mb_masked_l2_backward(joint_xyz21, gt_xyz, keypoint_vis, MB_VIS_F32, (long long)B * 21, 3, accum, g_losses,
-                                        g_xyz, stream))) return rc;
-    if (has_uv)
-        if ((rc = mb_masked_l2_backward(uv21, gt_uv, keypoint_vis, MB_VIS_F32, (long long)B * 21, 2, accum + 2, g_losses + 1,
-                                        g_uv, stream))) return rc;
+    if (has_xyz || has_uv) {
+        head_l2_backward_kernel<<<hl_grid((long long)B * 21), HL_THREADS, 0, s>>>(joint_xyz21, gt_xyz, uv21, gt_uv, keypoint_vis, (long long)B * 21,
+                                                                                  flags, accum, g_losses, g_xyz, g_uv);
+        if ((rc = cuda_rc())) return rc;
+    }
     // 2. back through the projection (and match_mano_to_RHD) to the MANO joints
     if (match) {
         if ((rc = mb_joint_epilogue_backward(joints, index_root_bone_length, kp_coord_xyz_root, K, nullptr, has_xyz ? g_xyz : nullptr,
@@ -161,12 +252,9 @@ extern "C" int mb_mano_head_loss_backward(const void* blob, int nc, const float*
                                      g_betas, stream))) return rc;
     // 4. the regulariser's gradient joins the pose / shape gradients
     if (flags & MB_HEAD_REG) {
-        float* g_theta = reinterpret_cast<float*>(ws + W.g_theta);
-        float* g_beta = reinterpret_cast<float*>(ws + W.g_beta);
-        if ((rc = mb_regulariser_backward(coeffs, (long long)B * nc, betas, (long long)B * 10, alpha_beta, accum + 4, g_losses + 2,
-                                          g_theta, g_beta, stream))) return rc;
-        if ((rc = launch_add(g_coeffs, g_theta, (long long)B * nc, s))) return rc;
-        if ((rc = launch_add(g_betas, g_beta, (long long)B * 10, s))) return rc;
+        const long long nt = (long long)B * nc, nb = (long long)B * 10;
+        head_reg_backward_add_kernel<<<hl_grid(nt), HL_THREADS, 0, s>>>(coeffs, nt, betas, nb, alpha_beta, accum, g_losses, g_coeffs, g_betas);
+        if ((rc = cuda_rc())) return rc;
     }
     return 0;
 }
