@@ -117,15 +117,22 @@ vs_bones_operand_kernel(const float* __restrict__ bone_t, int B, long long nchun
         const long long group = cidx / (32 / VS_HC);                    // 4 chunks of 8 hands per 32-hand group
         const float* src0 = bone_t + (size_t)group * (NJ * BONE_F * 32) + VS_TN * (int)(cidx % (32 / VS_HC));
         unsigned char* out = bones_op + (size_t)cidx * (VS_BONE_SPLITS * VS_BONE_CHUNK_BYTES);
+        constexpr int NR = NJ * (VS_TN / 8) / 32;                       // 192 (bone, n-group) items per chunk: six per lane
+        float4 v[NR][2];
 #pragma unroll
-        for (int r = 0; r < NJ * (VS_TN / 8) / 32; ++r) {              // 192 (bone, n-group) items per chunk: six per lane
+        for (int r = 0; r < NR; ++r) {                                  // all twelve loads of the lane in flight before the first conversion
             const int i = lane + 32 * r, k = i / (VS_TN / 8), g = i - (VS_TN / 8) * k;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            v[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[r][1] = v[r][0];
             if (group < ngroups) {
                 const float4* p = reinterpret_cast<const float4*>(src0 + (size_t)k * (BONE_F * 32) + 8 * g);
-                v0 = __ldcs(p); v1 = __ldcs(p + 1);
+                v[r][0] = __ldcs(p); v[r][1] = __ldcs(p + 1);
             }
-            float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int i = lane + 32 * r, k = i / (VS_TN / 8), g = i - (VS_TN / 8) * k;
+            float x[8] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w, v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] *= (float)(1 << VS_BONE_SCALE_LOG2);
             unsigned char* dst = out + g * 256 + (k >> 3) * 128 + (k & 7) * 16;
@@ -140,7 +147,7 @@ vs_bones_operand_kernel(const float* __restrict__ bone_t, int B, long long nchun
                     x[2 * e + 1] -= f.y;
                     pk[e] = *reinterpret_cast<const uint32_t*>(&h);
                 }
-                *reinterpret_cast<uint4*>(dst + sp * VS_BONE_CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                __stcs(reinterpret_cast<uint4*>(dst + sp * VS_BONE_CHUNK_BYTES), make_uint4(pk[0], pk[1], pk[2], pk[3]));
             }
         }
     }
