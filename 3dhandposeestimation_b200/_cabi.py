@@ -50,6 +50,9 @@ SIGNATURES = {
     "mb_lbs_forward": (_i, [_p, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "mb_fk_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "mb_fk_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "mb_fk_loss_workspace_bytes": (_sz, [_i]),
+    "mb_fk_loss_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "mb_fk_loss_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "mb_project_uv_forward": (_i, [_p, _p, _i, _i, _p, _p]),
     "mb_project_uv_backward": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "mb_joint_epilogue_forward": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
@@ -154,7 +157,7 @@ def on_tensor_device(fn):
                 if isinstance(a, torch.Tensor) and a.is_cuda:
                     dev = a.device
                     break
-        if dev is None:
+        if dev is None or dev.index == torch.cuda.current_device():          # the common case: no context switch to pay for
             return fn(*args, **kwargs)
         with torch.cuda.device(dev):
             return fn(*args, **kwargs)
@@ -168,6 +171,14 @@ def ptr(t):
 
 
 def stream_handle(device=None):
+    """Raw cudaStream_t of torch's current stream on ``device`` (the private fast accessor where this torch has it: the
+    public ``torch.cuda.current_stream`` builds a Stream object, ~12 us per call — measured 1 200 calls in 15 ms)."""
     import torch
 
-    return torch.cuda.current_stream(device).cuda_stream
+    try:
+        idx = device.index if isinstance(device, torch.device) else device
+        if idx is None:
+            idx = torch.cuda.current_device()
+        return torch._C._cuda_getCurrentRawStream(idx)
+    except (AttributeError, TypeError):
+        return torch.cuda.current_stream(device).cuda_stream

@@ -244,13 +244,11 @@ static int pose_and_blend_forward(const void* blob, int nc, const float* rot, co
     return launch_blend_tc_forward(blob, featp, v_posed_t, B, mode, s);
 }
 
-// the fused lane = vertex forward (vskin.cu) serves the batches of the one-thread-per-hand pose kernels; MB_FWD_FUSED /
-// MB_FWD_UNFUSED force a choice
+// the fused lane = vertex forward (vskin.cu) serves the batches of the one-thread-per-hand pose kernels — inference launches
+// (5.0 against 7.7 ms per 2^20 hands) and, writing the rest-pose scratch for the backward, training launches (6.9 against 7.5);
+// MB_FWD_UNFUSED selects the two separate kernels (MB_FWD_FUSED is accepted and redundant)
 static inline bool use_fused_forward(int model_flags, int mode, int B) {
-    if (!use_lane_hand(model_flags, mode, B) || (model_flags & MB_FWD_UNFUSED)) return false;
-    if (model_flags & MB_FWD_FUSED) return true;
-    static const int train_fused = getenv("MANO_B200_FUSED_TRAIN") ? atoi(getenv("MANO_B200_FUSED_TRAIN")) : 0;
-    return (model_flags & MB_FWD_INFERENCE) || train_fused;
+    return use_lane_hand(model_flags, mode, B) && !(model_flags & MB_FWD_UNFUSED);
 }
 
 // pose stage -> fused blend + skinning: verts, fingertip joints; v_posed_t only when a backward will want the workspace

@@ -160,15 +160,40 @@ HD V3 fk_angle_grad(int kind, const FkSC& q, const M3& dR) {
     return g;
 }
 
+// keypoint o of a sample leaves: xyz / uv rows of the sample.  LOSS (the fused FK + L2Loss forward, mb_fk_loss_forward): the
+// rows hold the GROUND TRUTH on entry — the squared distances of a visible joint (criterions/loss.py:10-25: fp32 sum over the
+// coordinates, as masked_reduce_kernel forms it from the stored outputs) join the thread's fp64 sums acc = {S_xyz, S_uv}
+// before the keypoint overwrites its slot.
+template <bool LOSS>
+HD void fk_emit(int o, float X, float Y, float Z, float u, float v, float* xyz, float* uv, unsigned vismask, bool has_xyz, bool has_uv,
+                double* acc) {
+    if (LOSS) {
+        if ((vismask >> o) & 1u) {
+            if (has_xyz) {
+                const float a = X - xyz[o * 3], b = Y - xyz[o * 3 + 1], c = Z - xyz[o * 3 + 2];
+                acc[0] += (double)(a * a + b * b + c * c);
+            }
+            if (has_uv) {
+                const float a = u - uv[o * 2], b = v - uv[o * 2 + 1];
+                acc[1] += (double)(a * a + b * b);
+            }
+        }
+    }
+    xyz[o * 3] = X; xyz[o * 3 + 1] = Y; xyz[o * 3 + 2] = Z;
+    uv[o * 2] = u; uv[o * 2 + 1] = v;
+}
+
 // One sample forward.  xyz[63], uv[42] may be strided (element stride 1, caller gives row base).
+// LOSS: see fk_emit; vismask bit o = joint o (output order) is visible.
+template <bool LOSS = false>
 HD void fk_forward_sample(const float* ra, const float* oa, const float* bl, const float* K, float s,
-                          const float* root, int swap, float* xyz, float* uv) {
+                          const float* root, int swap, float* xyz, float* uv, unsigned vismask = 0u, bool has_xyz = false,
+                          bool has_uv = false, double* acc = nullptr) {
     const M3 Rroot = euler_xyz(ra[0], ra[1], ra[2]);
     {
-        xyz[0] = root[0]; xyz[1] = root[1]; xyz[2] = root[2];      // wrist: p = 0
-        float u, v;
+        float u, v;                                                 // wrist: p = 0
         project_point(K, root[0], root[1], root[2], u, v);
-        uv[0] = u; uv[1] = v;
+        fk_emit<LOSS>(0, root[0], root[1], root[2], u, v, xyz, uv, vismask, has_xyz, has_uv, acc);
     }
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
@@ -189,10 +214,9 @@ HD void fk_forward_sample(const float* ra, const float* oa, const float* bl, con
             P = v3(fmaf(L, Rg.m[2], P.x), fmaf(L, Rg.m[5], P.y), fmaf(L, Rg.m[8], P.z));
             const int o = fk_out_slot(1 + 4 * f + seg, swap);
             const float X = fmaf(P.x, s, root[0]), Y = fmaf(P.y, s, root[1]), Z = fmaf(P.z, s, root[2]);
-            xyz[o * 3] = X; xyz[o * 3 + 1] = Y; xyz[o * 3 + 2] = Z;
             float u, v;
             project_point(K, X, Y, Z, u, v);
-            uv[o * 2] = u; uv[o * 2 + 1] = v;
+            fk_emit<LOSS>(o, X, Y, Z, u, v, xyz, uv, vismask, has_xyz, has_uv, acc);
             Rpar = Rg;
         }
     }
@@ -200,9 +224,15 @@ HD void fk_forward_sample(const float* ra, const float* oa, const float* bl, con
 
 // One sample backward.  g_xyz / g_uv may be NULL.
 // g_ra[3], g_oa[23], g_bl[20] are overwritten.
+// LOSS = true (the fused FK + L2Loss backward, mb_fk_loss_backward): g_xyz / g_uv point at the GROUND TRUTH rows instead and
+// the upstream gradients of the two masked-mean L2 terms (criterions/loss.py:10-25) are formed on the spot from the recomputed
+// keypoints — d/dxyz = kx [visible] (xyz - gt), d/duv = ku [visible] (uv - gt), kx = 2 g_loss_xyz / N_visible, bit o of vismask =
+// joint o (output order) is visible — the same
+// floats masked_l2_backward_kernel writes from the forward's stored outputs (the forward sweep here recomputes them bit for bit).
+template <bool LOSS = false>
 HD void fk_backward_sample(const float* ra, const float* oa, const float* bl, const float* K, float s,
                            const float* root, int swap, const float* g_xyz, const float* g_uv,
-                           float* g_ra, float* g_oa, float* g_bl) {
+                           float* g_ra, float* g_oa, float* g_bl, unsigned vismask = 0u, float kx = 0.f, float ku = 0.f) {
     const M3 Rroot = euler_xyz(ra[0], ra[1], ra[2]);
     M3 dRroot = m3_zero();
     for (int i = 0; i < FK_OA; ++i) g_oa[i] = 0.f;
@@ -230,10 +260,25 @@ HD void fk_backward_sample(const float* ra, const float* oa, const float* bl, co
                 P = v3(fmaf(L, Rg[seg].m[2], P.x), fmaf(L, Rg[seg].m[5], P.y), fmaf(L, Rg[seg].m[8], P.z));
                 const int o = fk_out_slot(1 + 4 * f + seg, swap);
                 V3 dx = v3(0.f, 0.f, 0.f);
-                if (g_xyz) dx = v3(g_xyz[o * 3], g_xyz[o * 3 + 1], g_xyz[o * 3 + 2]);
-                if (g_uv) {
+                if (LOSS) {
                     const float X = fmaf(P.x, s, root[0]), Y = fmaf(P.y, s, root[1]), Z = fmaf(P.z, s, root[2]);
-                    dx = v3_add(dx, project_point_bwd(K, X, Y, Z, g_uv[o * 2], g_uv[o * 2 + 1]));
+                    const bool m = ((vismask >> o) & 1u) != 0u;
+                    if (g_xyz) {
+                        const float k = m ? kx : 0.f;
+                        dx = v3(k * (X - g_xyz[o * 3]), k * (Y - g_xyz[o * 3 + 1]), k * (Z - g_xyz[o * 3 + 2]));
+                    }
+                    if (g_uv) {
+                        const float k = m ? ku : 0.f;
+                        float u, v;
+                        project_point(K, X, Y, Z, u, v);
+                        dx = v3_add(dx, project_point_bwd(K, X, Y, Z, k * (u - g_uv[o * 2]), k * (v - g_uv[o * 2 + 1])));
+                    }
+                } else {
+                    if (g_xyz) dx = v3(g_xyz[o * 3], g_xyz[o * 3 + 1], g_xyz[o * 3 + 2]);
+                    if (g_uv) {
+                        const float X = fmaf(P.x, s, root[0]), Y = fmaf(P.y, s, root[1]), Z = fmaf(P.z, s, root[2]);
+                        dx = v3_add(dx, project_point_bwd(K, X, Y, Z, g_uv[o * 2], g_uv[o * 2 + 1]));
+                    }
                 }
                 dP[seg] = v3(dx.x * s, dx.y * s, dx.z * s);
                 Rpar = Rg[seg];

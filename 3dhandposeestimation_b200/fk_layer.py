@@ -105,6 +105,110 @@ class ForwardKinematics(nn.Module):
         return kp_coord_xyz21_rel_normed * index_root_bone_length.unsqueeze(-1) + kp_coord_xyz_root.unsqueeze(1)
 
 
+class _FKLossFunction(torch.autograd.Function):
+    """losses[2], xyz, uv = f(root_angles, other_angles, bone_lengths | K, scale, root, gt_xyz, gt_uv, vis); xyz / uv carry no
+    gradient (they are what the head returns; the two loss terms are differentiated here)."""
+
+    @staticmethod
+    @_cabi.on_tensor_device
+    def forward(ctx, root_angles, other_angles, bone_lengths, K, scale, root, gt_xyz, gt_uv, vis, swap, flags):
+        lib = _cabi.lib()
+        B = root_angles.shape[0]
+        dev = root_angles.device
+        xyz = torch.empty((B, 21, 3), dtype=torch.float32, device=dev)
+        uv = torch.empty((B, 21, 2), dtype=torch.float32, device=dev)
+        losses = torch.empty((2,), dtype=torch.float32, device=dev)
+        ws = torch.empty((8,), dtype=torch.float64, device=dev)
+        p = _cabi.ptr
+        _cabi.check(lib.mb_fk_loss_forward(root_angles.data_ptr(), other_angles.data_ptr(), bone_lengths.data_ptr(), K.data_ptr(),
+                                           scale.data_ptr(), root.data_ptr(), p(gt_xyz), p(gt_uv), p(vis), B, int(swap), flags,
+                                           xyz.data_ptr(), uv.data_ptr(), losses.data_ptr(), ws.data_ptr(), 64,
+                                           _cabi.stream_handle(dev)), "mb_fk_loss_forward")
+        ctx.save_for_backward(root_angles, other_angles, bone_lengths, K, scale, root, gt_xyz, gt_uv, vis, ws)
+        ctx.swap, ctx.flags = int(swap), flags
+        ctx.mark_non_differentiable(xyz, uv)
+        return losses, xyz, uv
+
+    @staticmethod
+    @_cabi.on_tensor_device
+    def backward(ctx, g_losses, _g_xyz, _g_uv):
+        root_angles, other_angles, bone_lengths, K, scale, root, gt_xyz, gt_uv, vis, ws = ctx.saved_tensors
+        lib = _cabi.lib()
+        B = root_angles.shape[0]
+        dev = root_angles.device
+        g_losses = g_losses.to(torch.float32).contiguous()
+        g_ra, g_oa, g_bl = torch.empty_like(root_angles), torch.empty_like(other_angles), torch.empty_like(bone_lengths)
+        p = _cabi.ptr
+        _cabi.check(lib.mb_fk_loss_backward(root_angles.data_ptr(), other_angles.data_ptr(), bone_lengths.data_ptr(), K.data_ptr(),
+                                            scale.data_ptr(), root.data_ptr(), p(gt_xyz), p(gt_uv), p(vis), B, ctx.swap, ctx.flags,
+                                            g_losses.data_ptr(), g_ra.data_ptr(), g_oa.data_ptr(), g_bl.data_ptr(), ws.data_ptr(), 64,
+                                            _cabi.stream_handle(dev)), "mb_fk_loss_backward")
+        return (g_ra, g_oa, g_bl) + (None,) * 8
+
+
+class ForwardKinematicsLoss(nn.Module):
+    """The FK heads' training tail as one call per direction: ``ForwardKinematics.forward``
+    (forwardKinematicsLayer.py:147-330) followed by ``LossCalculation``'s ``compute_3d_coord_loss`` /
+    ``compute_uv_coord_loss`` (criterions/loss.py:83-87 -> ``L2Loss``, :10-25) on its outputs, the way
+    network/TwoDimHandPoseWithFK.py + trainval.py:328-358 chain them.  ``comp_xyz_loss`` / ``comp_uv_loss`` are
+    ``LossCalculation``'s flags (loss.py:63).
+
+    ``forward(root_angles, other_angles, bone_lengths, camera_intrinsic_matrix, index_root_bone_length, kp_coord_xyz_root,
+    gt_xyz, gt_uv, keypoint_vis)`` returns ``(loss_xyz, loss_uv, xyz, uv)`` — 0-dim loss tensors (``None`` for a term that is
+    switched off, as ``LossCalculation.forward`` returns) and the layer's outputs, through which no gradient flows
+    (differentiate the terms).  One kernel each way: the reductions run inside the FK kernel, the L2 gradients are formed
+    inside the FK backward kernel.  At the reference's sizes the separate drop-ins (``ForwardKinematics`` + ``L2Loss`` x2)
+    cost 3 autograd nodes and 7 launches per step and are bound by that overhead, not by the GPU."""
+
+    def __init__(self, device="cpu", comp_xyz_loss=True, comp_uv_loss=True, joint_order_switched=None):
+        super().__init__()
+        self.device = device
+        self.comp_xyz_loss, self.comp_uv_loss = bool(comp_xyz_loss), bool(comp_uv_loss)
+        self.joint_order_switched = joint_order_switched
+
+    def forward(self, root_angles, other_angles, bone_lengths, camera_intrinsic_matrix, index_root_bone_length,
+                kp_coord_xyz_root, gt_xyz, gt_uv, keypoint_vis):
+        if not isinstance(root_angles, torch.Tensor) or root_angles.device.type != "cuda":
+            raise _cabi.ManoB200Error("ForwardKinematicsLoss only runs on CUDA tensors (sm_100a); there is no CPU fallback")
+        dev = root_angles.device
+        ra = _as_f32_cuda(root_angles, "root_angles", dev)
+        oa = _as_f32_cuda(other_angles, "other_angles", dev)
+        bl = _as_f32_cuda(bone_lengths, "bone_lengths", dev)
+        K = _as_f32_cuda(camera_intrinsic_matrix, "camera_intrinsic_matrix", dev)
+        sc = _as_f32_cuda(index_root_bone_length, "index_root_bone_length", dev)
+        root = _as_f32_cuda(kp_coord_xyz_root, "kp_coord_xyz_root", dev)
+        B = ra.shape[0]
+        if (ra.shape != (B, 3) or oa.shape != (B, 23) or bl.shape != (B, 20) or K.shape != (B, 3, 3)
+                or sc.numel() != B or root.shape != (B, 3)):
+            raise RuntimeError("expected root_angles[B,3], other_angles[B,23], bone_lengths[B,20], K[B,3,3], "
+                               "index_root_bone_length[B,1], kp_coord_xyz_root[B,3]")
+        flags, vis = 0, None
+        if self.comp_xyz_loss or self.comp_uv_loss:
+            vis = _as_f32_cuda(keypoint_vis, "keypoint_vis", dev)
+            if vis.numel() != B * 21:
+                raise RuntimeError("expected keypoint_vis[B,21,1]")
+            vis = vis.reshape(B, 21)
+        if self.comp_xyz_loss:
+            flags |= _cabi.HEAD_XYZ
+            gt_xyz = _as_f32_cuda(gt_xyz, "gt_xyz", dev)
+            if gt_xyz.shape != (B, 21, 3):
+                raise RuntimeError("expected gt_xyz[B,21,3]")
+        else:
+            gt_xyz = None
+        if self.comp_uv_loss:
+            flags |= _cabi.HEAD_UV
+            gt_uv = _as_f32_cuda(gt_uv, "gt_uv", dev)
+            if gt_uv.shape != (B, 21, 2):
+                raise RuntimeError("expected gt_uv[B,21,2]")
+        else:
+            gt_uv = None
+        switched = self.joint_order_switched
+        if switched is None:
+            switched = _reference_joint_order_switched()
+        losses, xyz, uv = _FKLossFunction.apply(ra, oa, bl, K, sc.reshape(B), root, gt_xyz, gt_uv, vis, not switched, flags)
+        return (losses[0] if self.comp_xyz_loss else None, losses[1] if self.comp_uv_loss else None, xyz, uv)
+
+
 class _ProjectFunction(torch.autograd.Function):
     @staticmethod
     @_cabi.on_tensor_device

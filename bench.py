@@ -475,6 +475,49 @@ def run_secondary(args, pkg, layer, dev, rank, world, dist):
         raw_step(i, torch.cuda.current_stream(dev).cuda_stream)
     prof = cabi.profile_collect()
     lib.mb_profile_enable(0)
+    # The same training step with the two L2Loss terms INSIDE the FK kernels (mb_fk_loss_forward / _backward: one launch + one
+    # 64-byte memset per direction) — through the C ABI as one graph over the rotating sets, and through the ForwardKinematicsLoss
+    # module (one autograd node instead of three)
+    gt_uvs = [torch.rand(B, 21, 2, device=dev) * 320 for _ in range(nsets)]
+    louts = [dict(losses=torch.zeros(2, device=dev), ws=torch.zeros(8, dtype=torch.float64, device=dev)) for _ in range(nsets)]
+    g_l = torch.tensor([1.0, 1e-3], device=dev)
+    both = cabi.HEAD_XYZ | cabi.HEAD_UV
+
+    def loss_step(i, stream):
+        t, gt, vis = sets[i]
+        o, lo = outs[i], louts[i]
+        ra, oa, bl, K, sc, root = t
+        cabi.check(lib.mb_fk_loss_forward(P(ra), P(oa), P(bl), P(K), P(sc), P(root), P(gt), P(gt_uvs[i]), P(vis), B, 0, both, P(o["xyz"]),
+                                          P(o["uv"]), P(lo["losses"]), P(lo["ws"]), 64, stream), "fk_loss_forward")
+        cabi.check(lib.mb_fk_loss_backward(P(ra), P(oa), P(bl), P(K), P(sc), P(root), P(gt), P(gt_uvs[i]), P(vis), B, 0, both, P(g_l),
+                                           P(o["g"][0]), P(o["g"][1]), P(o["g"][2]), P(lo["ws"]), 64, stream), "fk_loss_backward")
+
+    with torch.cuda.stream(side):
+        for i in range(nsets):
+            loss_step(i, side.cuda_stream)
+    side.synchronize()
+    lgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(lgraph, stream=side):
+        for i in range(nsets):
+            loss_step(i, torch.cuda.current_stream(dev).cuda_stream)
+    ms_loss_graph = timed(lgraph.replay, max(3, args.steps // 4)) / nsets
+    crit = pkg.ForwardKinematicsLoss(dev)
+
+    def loss_module_step():
+        t, gt, vis = sets[it[0] % nsets]
+        gu = gt_uvs[it[0] % nsets]
+        it[0] += 1
+        lx, lu, _, _ = crit(*t, gt, gu, vis)
+        (lx + 1e-3 * lu).backward()
+        for x in t[:3]:
+            x.grad = None
+
+    ms_loss_module = timed(loss_module_step, args.steps)
+    fk_loss = {"c_abi_graph_ms_per_step": ms_loss_graph, "c_abi_graph_samples_per_s": world * B / (ms_loss_graph * 1e-3),
+               "module_api_ms_per_step": ms_loss_module, "module_api_samples_per_s": world * B / (ms_loss_module * 1e-3),
+               "loss_xyz": float(louts[0]["losses"][0]), "loss_uv": float(louts[0]["losses"][1]),
+               "note": "FK forward + L2Loss(xyz) + L2Loss(uv) and back: mb_fk_loss_forward / _backward (one kernel + one 64-byte "
+                       "memset per direction); module = ForwardKinematicsLoss + (loss_xyz + 1e-3 loss_uv).backward()"}
     peaks = load_peaks()
     roof = {}
     for stage, kern, nbytes in (("fk_fwd", "fk_forward_kernel", 656), ("fk_bwd", "fk_backward_kernel", 840 + 252)):
@@ -489,6 +532,7 @@ def run_secondary(args, pkg, layer, dev, rank, world, dist):
                        "api": "C ABI, the rotating sets captured in one CUDA graph (7 kernels + 2 memsets per step)"},
             "module_api": {"value": world * B / (ms * 1e-3), "ms_per_step": ms,
                            "note": "ForwardKinematics + MPJPE nn.Modules with torch autograd: launch- and Python-bound at this size"},
+            "fk_loss": fk_loss,
             "roofline": roof, "mpjpe_mm": float(outs[0]["mp"]), "l2": float(outs[0]["l2"]), "data": "synthetic"}
 
 
@@ -650,6 +694,7 @@ def run_extras(args, pkg, layer45, dev, rank, world, dist, set0):
     fk = run_secondary(a3, pkg, layer45, dev, rank, world, dist)
     out["config3_fk"] = {"samples": 65536, "c_abi_graph_ms_per_step": fk["ms_per_step"], "c_abi_graph_samples_per_s": fk["value"],
                          "module_api_ms_per_step": fk["module_api"]["ms_per_step"], "module_api_samples_per_s": fk["module_api"]["value"],
+                         "fk_loss": fk["fk_loss"],
                          "roofline": fk["roofline"], "mpjpe_mm": fk["mpjpe_mm"]}
 
     # ---- config 5: fitting iterations, with and without the collective ----
@@ -710,6 +755,7 @@ def main():
     ap.add_argument("--rotate", type=int, default=1, help="number of distinct buffer sets cycled through (small --hands)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="A/B: the two separate forward kernels (MB_FWD_UNFUSED) instead of the fused one")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 2 / 3 / 5 side measurements of the default line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -742,8 +788,8 @@ def main():
     torch.cuda.set_device(dev)
     H = args.hands
     model = no_pca_model(pkg.assets)
-    layer = pkg.ManoLayer(dev, model=model, pose_num=45, mode=args.mode)
-    mode = layer._mode
+    layer = pkg.ManoLayer(dev, model=model, pose_num=45, mode=args.mode, fused_forward=False if args.unfused else None)
+    mode = layer._mode | layer._fwd_flags
     stream = cabi.stream_handle(dev)
 
     if args.workload != "mano":
@@ -907,7 +953,7 @@ def main():
         # A/B: the same forward through the OTHER implementation (the library's default from 8 192 hands on is the fused blend +
         # skinning kernel with lane = vertex, vskin.cu; MB_FWD_UNFUSED runs the blend-contraction + lane = hand skinning kernels)
         other_is_unfused = "fused_fwd" in fstages
-        um = fwd_mode | (cabi.FWD_UNFUSED if other_is_unfused else cabi.FWD_FUSED)
+        um = (fwd_mode & ~(cabi.FWD_FUSED | cabi.FWD_UNFUSED)) | (cabi.FWD_UNFUSED if other_is_unfused else cabi.FWD_FUSED)
 
         def ufwd_step(i):
             s = sets[i % nsets]
@@ -1004,29 +1050,50 @@ def main():
             off += n * 58
         h_out2 = [torch.empty(H * 58, dtype=torch.float32).pin_memory() for _ in range(2)]
         h_loss2 = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-        side = [torch.cuda.Stream(device=dev) for _ in range(min(int(os.environ.get("MANO_B200_E2E_STREAMS", "2")), n_chunks))]
+        # Three streams: host -> device copies, kernels, device -> host copies.  Every kernel of the step runs on ONE compute
+        # stream, back to back as in the device-resident loop; the copies of the neighbouring chunks hide behind them (events
+        # order a chunk's copy-in -> compute -> copy-out; device staging buffers alternate per step).  [round 2: two
+        # symmetric streams, each doing copy + kernels + copy, let kernels of different chunks compete for the SMs — the
+        # one-CTA-per-SM kernels serialise anyway — and measured 20.5 - 22.7 ms per step depending on how they interleaved]
+        st_in, st_cmp, st_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        side = [st_in, st_cmp, st_out]
+        d_in2 = [[torch.empty((b - a) * 58, dtype=torch.float32, device=dev) for (a, b, _) in bounds] for _ in range(2)]
+        free_ev = [[None] * n_chunks for _ in range(2)]
         step_no = [0]
 
         def e2e_step(copy_grads=True):
-            h_out, h_loss = h_out2[step_no[0] & 1], h_loss2[step_no[0] & 1]
+            par = step_no[0] & 1
+            h_out, h_loss = h_out2[par], h_loss2[par]
             step_no[0] += 1
             for c, (a, b, o) in enumerate(bounds):
-                st = side[c % len(side)]
                 n = b - a
-                with torch.cuda.stream(st):
-                    flat = h_in[o:o + n * 58].to(dev, non_blocking=True)
+                flat = d_in2[par][c]
+                with torch.cuda.stream(st_in):
+                    if free_ev[par][c] is not None:
+                        st_in.wait_event(free_ev[par][c])                    # the step before last is done with this buffer
+                    flat.copy_(h_in[o:o + n * 58], non_blocking=True)
+                    ev_in = st_in.record_event()
+                with torch.cuda.stream(st_cmp):
+                    st_cmp.wait_event(ev_in)
                     d = [flat[:n * 3].view(n, 3).requires_grad_(), flat[n * 3:n * 48].view(n, 45).requires_grad_(),
                          flat[n * 48:].view(n, 10).requires_grad_()]
                     verts, joints = layer(*d)
                     torch.autograd.backward([verts, joints], [gv_keep[a:b], gj_keep[a:b]])
                     g = torch.cat([x.grad.reshape(-1) for x in d])           # 232 B per hand of gradients, one D2H copy
+                    loss = joints[0, 0, :1] if c == 0 else None
+                    ev_done = st_cmp.record_event()
+                    free_ev[par][c] = ev_done
+                with torch.cuda.stream(st_out):
+                    st_out.wait_event(ev_done)
                     if copy_grads:
                         h_out[o:o + n * 58].copy_(g, non_blocking=True)
-                    if c == 0:
-                        h_loss.copy_(joints[0, 0, :1], non_blocking=True)
-                    for t in (verts, joints, gv_keep, gj_keep, g, flat):
-                        t.record_stream(st)
-                    del verts, joints, d, g, flat
+                    if loss is not None:
+                        h_loss.copy_(loss, non_blocking=True)
+                    g.record_stream(st_out)
+                    joints.record_stream(st_out)
+                for t in (gv_keep, gj_keep):
+                    t.record_stream(st_cmp)
+                del verts, joints, d, g, flat, loss
 
         def join_side():
             main = torch.cuda.current_stream(dev)
@@ -1068,8 +1135,11 @@ def main():
         def copy_step():
             for c, (a, b, o) in enumerate(bounds):
                 n = b - a
-                with torch.cuda.stream(side[c % len(side)]):
+                with torch.cuda.stream(st_in):
                     d_flat[o:o + n * 58].copy_(h_in[o:o + n * 58], non_blocking=True)
+                    ev = st_in.record_event()
+                with torch.cuda.stream(st_out):
+                    st_out.wait_event(ev)
                     h_out2[0][o:o + n * 58].copy_(d_flat[o:o + n * 58], non_blocking=True)
 
         copy_step()
@@ -1095,8 +1165,9 @@ def main():
                                      "ceiling of this arm"},
                "numa": numa_all,
                "api": "ManoLayer.forward + autograd backward; ONE pinned host buffer in (rot | pose | beta per chunk) and one out "
-                      f"(58 gradient floats per hand); {n_chunks} chunks over {len(side)} CUDA streams, one H2D + one D2H copy per chunk, "
-                      "steps pipelined per stream (alternating pinned result buffers); verts / joints and their upstream gradients "
+                      f"(58 gradient floats per hand); {n_chunks} chunks, one H2D + one D2H copy per chunk on a copy-in and a copy-out "
+                      "stream around ONE compute stream (events per chunk; device staging and pinned result buffers alternate per "
+                      "step, so consecutive steps overlap); verts / joints and their upstream gradients "
                       "stay on the device (the step's result that crosses PCIe is the parameter gradient)"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

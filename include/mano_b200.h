@@ -58,9 +58,10 @@ extern "C" {
  *                   mb_mano_backward must then be called WITHOUT MB_BWD_WORKSPACE_VALID and recomputes it);
  * MB_FWD_FUSED / MB_FWD_UNFUSED: from 8 192 hands on (MANO tree, tensor-core modes) the forward has two implementations —
  *                   the fused blend-shape + skinning kernel with lane = vertex (csrc/vskin.cu: both contractions on the
- *                   tensor core, no rest-pose round trip through HBM) and the blend-contraction + lane = hand skinning
- *                   kernels.  Without either bit the library picks the measured faster one (the fused kernel); the bits force one
- *                   (measurement / cross-checking). */
+ *                   tensor core, rest positions never leave the SM; with a backward to follow it also writes the rest-pose
+ *                   scratch) and the blend-contraction + lane = hand skinning kernels.  The fused kernel is the default (the
+ *                   measured faster one in both kinds of launch); MB_FWD_UNFUSED selects the two kernels (measurement /
+ *                   cross-checking), MB_FWD_FUSED is accepted for symmetry. */
 #define MB_FWD_INFERENCE 0x200
 #define MB_FWD_FUSED     0x400
 #define MB_FWD_UNFUSED   0x800
@@ -181,6 +182,29 @@ MB_API int mb_fk_backward(const float* root_angles, const float* other_angles, c
                    const float* K, const float* index_root_bone_length, const float* kp_coord_xyz_root,
                    const float* g_xyz, const float* g_uv, int B, int swap_order,
                    float* g_root_angles, float* g_other_angles, float* g_bone_lengths, mb_stream_t stream);
+
+/* The FK heads' training tail in one launch per direction: ForwardKinematics.forward (as mb_fk_forward) followed by
+ * LossCalculation.compute_3d_coord_loss / compute_uv_coord_loss (criterions/loss.py:83-87 -> L2Loss, :10-25) on its two
+ * outputs, as network/TwoDimHandPoseWithFK.py / ThreeDimHandPose.py + trainval.py:328-358 combine them.
+ *   gt_xyz[B][21][3], gt_uv[B][21][2], keypoint_vis[B][21] (fp32, non-zero = visible); flags = MB_HEAD_XYZ | MB_HEAD_UV
+ *   selects the terms (declared with the MANO heads' tail below); a term that is off is 0 and its ground truth may be NULL.
+ * Forward: xyz[B][21][3], uv[B][21][2] (what the head returns) and losses = device float[2] = {loss_xyz, loss_uv}; the
+ * reductions run inside the FK kernel (fp32 per-joint sums of squares, fp64 above), the last warp divides.
+ * Backward: g_losses = device float[2], the upstream gradients of the two terms; the gradients w.r.t. xyz / uv are formed
+ * inside the FK backward kernel from the recomputed keypoints and never stored.  The workspace
+ * (mb_fk_loss_workspace_bytes: sums, visible-joint counts, ticket) must reach the backward untouched.
+ * Same results as mb_fk_forward -> mb_masked_joint_reduce x2 and mb_masked_l2_backward x2 -> mb_fk_backward. */
+MB_API size_t mb_fk_loss_workspace_bytes(int B);
+MB_API int mb_fk_loss_forward(const float* root_angles, const float* other_angles, const float* bone_lengths,
+                       const float* K, const float* index_root_bone_length, const float* kp_coord_xyz_root,
+                       const float* gt_xyz, const float* gt_uv, const float* keypoint_vis, int B, int swap_order,
+                       int flags, float* xyz, float* uv, float* losses, void* workspace, size_t workspace_bytes,
+                       mb_stream_t stream);
+MB_API int mb_fk_loss_backward(const float* root_angles, const float* other_angles, const float* bone_lengths,
+                        const float* K, const float* index_root_bone_length, const float* kp_coord_xyz_root,
+                        const float* gt_xyz, const float* gt_uv, const float* keypoint_vis, int B, int swap_order,
+                        int flags, const float* g_losses, float* g_root_angles, float* g_other_angles,
+                        float* g_bone_lengths, const void* workspace, size_t workspace_bytes, mb_stream_t stream);
 
 /* Replaces batch_project_xyz_to_uv (utils/coordinate_trans.py:29-73) for xyz[B][N][3]:
  * p = K xyz; p_z == 0 -> 1e-10; uv = p_xy / p_z. */

@@ -398,6 +398,94 @@ def test_fk_matches_oracle_config3(pkg, cuda_device, B):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("B,skip", [(97, 1), (1 << 18, 0), (100003, 3)])
+def test_fk_bulk_copy_and_per_element_paths_agree(pkg, cuda_device, B, skip):
+    """fk.cu moves whole 32-sample tiles with bulk copies when every pointer is 16-byte aligned and falls back to per-element
+    loops otherwise (row-offset views: rows of 3 / 23 / 9 / 1 floats are not 16-byte multiples) and for the last partial tile.
+    Both paths run the same per-sample code: bit-identical results, several tiles per persistent warp at the large sizes."""
+    import torch
+
+    args = fk_inputs(B + skip, seed=11 + B)
+    fk = pkg.ForwardKinematics(cuda_device, joint_order_switched=False)
+    full = to_dev(cuda_device, *args)
+    rs = np.random.RandomState(5)
+    gx, gu = to_dev(cuda_device, rs.randn(B + skip, 21, 3).astype(np.float32), (rs.randn(B + skip, 21, 2) * 1e-3).astype(np.float32))
+
+    def run(ts, gxs, gus):
+        leaves = [x.detach().requires_grad_() for x in ts[:3]]
+        xyz, uv, _ = fk(*leaves, *ts[3:])
+        ((xyz * gxs).sum() + (uv * gus).sum()).backward()
+        return [xyz.detach(), uv.detach()] + [x.grad for x in leaves]
+
+    # (a) views that start `skip` rows in: unaligned when skip is odd -> per-element path for every tile
+    view = run([x[skip:] for x in full], gx[skip:], gu[skip:])
+    # (b) fresh, aligned copies of the same rows -> bulk path for the full tiles
+    copy = run([x[skip:].clone() for x in full], gx[skip:].clone(), gu[skip:].clone())
+    for a, b in zip(view, copy):
+        assert torch.equal(a, b)
+    n = min(B, 4096)
+    sub = [a[skip:skip + n] for a in args]
+    oxyz, ouv = fo.fk_forward(*sub, joint_order_switched=False)
+    assert np.abs(copy[0][:n].cpu().numpy() - oxyz).max() < POS_TOL_FK
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("B,switched,terms", [(1, True, (1, 1)), (200, True, (1, 1)), (333, False, (1, 1)), (65536, True, (1, 1)),
+                                              (77, True, (1, 0)), (77, False, (0, 1)), (64, True, (0, 0))])
+def test_fk_loss_one_call_matches_oracle_and_the_separate_dropins(pkg, cuda_device, B, switched, terms):
+    """ForwardKinematicsLoss (mb_fk_loss_forward / _backward: FK + both L2Loss terms, one kernel per direction) against the fp64
+    oracle composition fk_forward -> l2loss (+ backward) and against ForwardKinematics + L2Loss x2 through autograd."""
+    import torch
+
+    args = fk_inputs(B, seed=3 * B + 1)
+    rs = np.random.RandomState(B)
+    oxyz, ouv = fo.fk_forward(*args, joint_order_switched=switched)
+    gt_xyz = (oxyz + rs.randn(B, 21, 3) * .02).astype(np.float32)
+    gt_uv = (ouv + rs.randn(B, 21, 2) * 3.).astype(np.float32)
+    vis = (rs.rand(B, 21, 1) < .8).astype(np.float32)
+    if B == 1:
+        vis[:] = 1.
+    wx, wu = 0.7, 1e-3                                          # weights of the two terms in the total (upstream gradients)
+    use_xyz, use_uv = terms
+    crit = pkg.ForwardKinematicsLoss(cuda_device, comp_xyz_loss=bool(use_xyz), comp_uv_loss=bool(use_uv), joint_order_switched=switched)
+    t = to_dev(cuda_device, *args[:3], grad=True) + to_dev(cuda_device, *args[3:])
+    tg = to_dev(cuda_device, gt_xyz, gt_uv, vis)
+    lx, lu, xyz, uv = crit(*t, *tg)
+    assert (lx is None) == (not use_xyz) and (lu is None) == (not use_uv)
+    assert not xyz.requires_grad and not uv.requires_grad
+    assert np.abs(xyz.cpu().numpy() - oxyz).max() < POS_TOL_FK
+    assert np.abs(uv.cpu().numpy() - ouv).max() < 1e-3
+    # oracle losses on the kernel's own fp32 outputs (the reduction), then the full fp64 chain for the gradients
+    if use_xyz:
+        want = fo.l2loss(xyz.cpu().numpy(), gt_xyz, vis)
+        assert abs(float(lx) - want) <= 1e-5 * abs(want) + 1e-12
+    if use_uv:
+        want = fo.l2loss(uv.cpu().numpy(), gt_uv, vis)
+        assert abs(float(lu) - want) <= 1e-5 * abs(want) + 1e-12
+    if not (use_xyz or use_uv):
+        return
+    total = (wx * lx if use_xyz else 0.) + (wu * lu if use_uv else 0.)
+    total.backward()
+    g_xyz = wx * fo.l2loss_backward(oxyz, gt_xyz, vis) if use_xyz else None
+    g_uv = wu * fo.l2loss_backward(ouv, gt_uv, vis) if use_uv else None
+    want = fo.fk_backward(*args, g_xyz, g_uv, joint_order_switched=switched)
+    got = [x.grad.clone() for x in t[:3]]
+    for g, w in zip(got, want):
+        assert rel(g.cpu().numpy(), w) < GRAD_TOL
+    # the separate drop-ins through autograd: same kernels' arithmetic, so agreement to fp32 rounding of the loss scalars
+    for x in t[:3]:
+        x.grad = None
+    fk, l2 = pkg.ForwardKinematics(cuda_device, joint_order_switched=switched), pkg.L2Loss()
+    xyz2, uv2, _ = fk(*t)
+    assert torch.equal(xyz2.detach(), xyz) and torch.equal(uv2.detach(), uv)
+    total2 = (wx * l2(xyz2, tg[0], tg[2]) if use_xyz else 0.) + (wu * l2(uv2, tg[1], tg[2]) if use_uv else 0.)
+    total2.backward()
+    assert abs(float(total2) - float(total)) <= 2e-6 * abs(float(total))
+    for g, x in zip(got, t[:3]):
+        assert rel(g.cpu().numpy(), x.grad.cpu().numpy()) < 1e-5
+    torch.cuda.synchronize()
+
+
 def test_fk_hand_typed_kat(pkg, cuda_device):
     """KAT-FK-0."""
     import torch
