@@ -11,7 +11,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmano_b200.so")
+# MANO_B200_LIB selects another build of the same library (A/B timing of kernel variants: profiles/tools)
+LIB_PATH = os.environ.get("MANO_B200_LIB") or os.path.join(_HERE, "libmano_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mano_b200.h")
 
 MODE_FP32, MODE_F16X3, MODE_F16 = 0, 1, 2

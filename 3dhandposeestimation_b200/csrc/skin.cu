@@ -568,6 +568,9 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
     // warps w and w + 4 share a scheduler: with role = warp & 1 two schedulers would run only role-0 warps and two only the
     // (longer) role-1 warps; flipping the roles of the upper four warps gives every scheduler one of each
     const int pair = warp >> 1, role = (warp & 1) ^ (role_flip & (warp >> 2) & 1);
+    // timing experiments (MANO_B200_SKB_EXP, profiles/tools/skb_exp.sh; the results are WRONG with any bit set): 1 / 2 = role 0 /
+    // role 1 skips its arithmetic, 4 = no gradient-tile stores, 8 / 16 = role 1 / role 0 only takes part in the tile hand-over
+    const int exp = role_flip >> 8;
     BwdPairShared& W = reinterpret_cast<BwdPairShared*>(smem_raw + PROG_BYTES)[pair];
     if (role == 0 && lane == 0) {
         W.bones.init();
@@ -655,13 +658,14 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
                     A[8] = a2.x; A[9] = a2.y; A[10] = a2.z;
                     cache_after_entry(W.bones, CS, P, e, bgrp, has_next, next_off, pol.keep);
                 }
-                dv_entry2(A, w, G, DV);
+                if (!(exp & 1)) dv_entry2(A, w, G, DV);
             }
             float dv[SK_BC];                                    // block order: dv[3j + c]
 #pragma unroll
             for (int m = 0; m < 4; ++m)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { dv[6 * m + c] = DV[c][m].x; dv[6 * m + 3 + c] = DV[c][m].y; }
+            if (exp & 4) return;
             if (dvp != nullptr) {
                 // A operand of the tcgen05 gradient contraction: bf16 hi + mid, UMMA canonical K-major
                 // blocks; a lane owns a tile row, so 8 consecutive K values are one 16-byte group and
@@ -693,7 +697,8 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
         auto da_block = [&](int blk, const float2 (&V)[3][4]) {
             float2 G[3][4];
             gather_block(P, tl, blk, G);
-            skin_block_da(P, blk, W.dacc + lane, G, V);
+            if (!(exp & 2)) skin_block_da(P, blk, W.dacc + lane, G, V);
+            else if (G[0][0].x + V[0][0].x == 123.456f) W.dacc[lane] = 1.f;
         };
 
         for (int seg = seg0; seg < seg1; ++seg) {
@@ -726,8 +731,11 @@ skin_backward_kernel(const void* __restrict__ blob, const float* __restrict__ v_
             }
             if (seg + 1 < seg1) prefetch_g(seg + 1);
             if (role == 0) {
-                dv_block(2 * seg);
-                dv_block(2 * seg + 1);
+                if (!(exp & 16)) {
+                    dv_block(2 * seg);
+                    dv_block(2 * seg + 1);
+                }
+            } else if (exp & 8) {
             } else {
                 load_xpairs(vbk, vb + (size_t)(2 * seg + 1) * XBLK_FLOATS, pol.stream);
                 da_block(2 * seg, va);
@@ -1113,7 +1121,8 @@ int launch_skin_backward(const void* blob, const float* v_posed_t, const float* 
     if (int arc = ensure_dyn_smem(once_b, skin_backward_kernel<true>, SKB_SMEM)) return arc;
     const int ngroups = (B + 31) >> 5;
     const int spu = skin_segments_per_unit(ngroups, SKB_SWEEPERS);
-    static const int role_flip = getenv("MANO_B200_SKB_FLIP") ? atoi(getenv("MANO_B200_SKB_FLIP")) : 1;
+    static const int role_flip = (getenv("MANO_B200_SKB_FLIP") ? atoi(getenv("MANO_B200_SKB_FLIP")) : 1) |
+                                 ((getenv("MANO_B200_SKB_EXP") ? atoi(getenv("MANO_B200_SKB_EXP")) : 0) << 8);
     if (spu < SK_NSEG) {
         if (dparts == nullptr) return MB_E_NULL;
         const int nunits = ngroups * skin_units_per_group(spu);
