@@ -40,13 +40,18 @@
 #include "tc_ptx.cuh"
 
 namespace mb {
+// 256-bit store (sm_100): eight consecutive floats = one full 32-byte sector, streaming
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 namespace {
 
 constexpr int VS_THREADS = 384;                   // 12 warps: see the role list above
 constexpr int VS_EPI_WARPS = 8;
 constexpr int VS_ASTAGES = 5;                     // basis ring: 5 x 16 KB (6 measured the same)
 constexpr int VS_TSTAGES = 3;                     // transform ring of 8-hand chunks: chunk counter mod 3; even counters -> warp set 0, odd -> set 1
-constexpr int VS_VT_PITCH = 20;                   // floats per row of the scratch transposition tile: 16 hands + 4 (16-byte rows, conflict-free STS.128)
 constexpr int VS_HH = 4;                          // hands per epilogue register load of a chunk (48 columns)
 constexpr int VS_HS = VS_NH / 2;                  // 32 hands per epilogue warp set
 constexpr uint32_t VS_TMEM_COLS = 512;
@@ -65,7 +70,6 @@ struct VsShared {
     alignas(128) unsigned char feat[TC_K_CHUNKS][2][VS_NH * TC_K_CHUNK * 2];      // 40 KB: [K chunk][hi, lo][64 hands x 32]
     alignas(128) unsigned char bones[VS_NCH][VS_BONE_SPLITS][VS_BONE_CHUNK_BYTES]; // 72 KB
     alignas(128) unsigned char a[VS_ASTAGES][VS_A_STAGE_BYTES];                    // 64 KB basis ring
-    alignas(16) float vt[VS_EPI_WARPS][32 * VS_VT_PITCH];                          // 20 KB: per-warp transposition tile of the rest-pose scratch
     alignas(8) unsigned long long a_full[VS_ASTAGES], a_empty[VS_ASTAGES];
     unsigned long long w_full[2], w_empty[2];
     unsigned long long feat_full, feat_empty;
@@ -458,39 +462,19 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                 if (has_next) { uint4 wnext[2]; w_row_load(t + 1 < VS_NT ? t + 1 : 0, wnext); w_row_store(g + 1, wnext); }
                 if (v_posed_t != nullptr) {
                     // rest-pose scratch for the skinning backward: v_posed_t[group][3 pos + p][32 hands], this set's 32 hands = one
-                    // hand group.  A thread holds the 32 hands of ITS vertex, a line of the scratch is the 32 hands of ONE coordinate:
-                    // transposed through a per-warp tile, 16 hands at a time, with 16-byte accesses on both sides — a store instruction
-                    // covers eight 64-byte half lines.  [profiles/r2: written straight from the registers — every lane its own
-                    // 16-byte piece of 32 different lines per instruction — the scratch cost 4.4 ms per 2^20 hands; transposed with
-                    // 4-byte accesses (384 instructions per unit and thread) 3.1 ms.]
+                    // hand group.  A thread holds the 32 hands of ITS vertex and the vertex' three scratch rows are 384 contiguous
+                    // bytes: twelve 256-bit stores (sm_100: one full 32-byte sector each) straight from the registers.
+                    // [profiles/r2, scratch cost per 2^20 hands: 16-byte stores from the registers (half sectors) 4.4 ms; transposed
+                    // through a per-warp shared-memory tile with 4-byte accesses 3.1 ms, with 16-byte accesses 2.1 ms; this 1.9 ms]
                     const long long group = (long long)tile * 2 + set;
                     const int pos3 = valid ? __float_as_int(tm.w) : -1;
-                    if (group * 32 < B) {                               // warp-uniform
-                        float* tl = &S.vt[warp - 4][0];
-                        // lane -> (row inside an 8-row slab, 16-byte chunk of the 64-byte half line)
-                        float* gbase = v_posed_t + (size_t)group * SK_NCOORD * 32 + 4 * (lane & 3);
+                    if (group * 32 < B && pos3 >= 0) {
+                        float* dst = v_posed_t + ((size_t)group * SK_NCOORD + pos3) * 32;
 #pragma unroll
-                        for (int p = 0; p < 3; ++p) {
-#pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                __syncwarp();
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    const int i = hh * 16 + 4 * c;
-                                    const float4 v4 = p == 0 ? make_float4(X[i], X[i + 1], X[i + 2], X[i + 3])
-                                                    : p == 1 ? make_float4(Y[i], Y[i + 1], Y[i + 2], Y[i + 3])
-                                                             : make_float4(Z[i], Z[i + 1], Z[i + 2], Z[i + 3]);
-                                    *reinterpret_cast<float4*>(tl + lane * VS_VT_PITCH + 4 * c) = v4;
-                                }
-                                __syncwarp();
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const int r = 8 * k + (lane >> 2);                   // the vertex row of this lane quad
-                                    const int pr = __shfl_sync(0xffffffffu, pos3, r);
-                                    const float4 v4 = *reinterpret_cast<const float4*>(tl + r * VS_VT_PITCH + 4 * (lane & 3));
-                                    if (pr >= 0) __stcs(reinterpret_cast<float4*>(gbase + (size_t)(pr + p) * 32 + hh * 16), v4);
-                                }
-                            }
+                        for (int k = 0; k < 4; ++k) {
+                            st_global_v8(dst + 8 * k, &X[8 * k]);
+                            st_global_v8(dst + 32 + 8 * k, &Y[8 * k]);
+                            st_global_v8(dst + 64 + 8 * k, &Z[8 * k]);
                         }
                     }
                 }
