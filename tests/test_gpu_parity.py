@@ -861,3 +861,31 @@ def test_module_api_does_not_leak_device_memory(pkg, synth_model, cuda_device):
         one()
     torch.cuda.synchronize()
     assert torch.cuda.memory_allocated(cuda_device) - base < (1 << 20)
+
+
+def test_layers_on_a_non_current_device(pkg, synth_model):
+    """The C ABI launches on the CURRENT device; the wrappers switch to the tensors' device (a layer on
+    cuda:1 while cuda:0 is current failed every launch).  Needs two GPUs: skipped on a single-GPU box."""
+    import torch
+
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    assert torch.cuda.current_device() == 0
+    dev = torch.device("cuda", 1)
+    B, nc = 97, 45
+    rot, pose, beta = mano_inputs(B, nc, 5)
+    layer = pkg.ManoLayer(dev, model=synth_model, pose_num=nc)
+    t = to_dev(dev, rot, pose, beta, grad=True)
+    verts, joints = layer(*t)
+    (verts.sum() + joints.sum()).backward()
+    ov, oj = mo.mano_forward(synth_model, rot, pose, beta)
+    assert_positions(verts.detach().cpu().numpy(), ov)
+    og = mo.mano_backward(synth_model, rot, pose, beta, np.ones((B, 778, 3), np.float32), np.ones((B, 21, 3), np.float32))
+    for got, want in zip(t, og):
+        assert rel(got.grad.cpu().numpy(), want) < GRAD_TOL
+    args = fk_inputs(B, seed=9)
+    xyz, uv, _ = pkg.ForwardKinematics(dev)(*to_dev(dev, *args))
+    oxyz, _ = fo.fk_forward(*args)
+    assert np.abs(xyz.cpu().numpy() - oxyz).max() < POS_TOL_FK
+    assert torch.cuda.current_device() == 0
+    torch.cuda.synchronize(dev)
