@@ -106,8 +106,10 @@ class ForwardKinematics(nn.Module):
 
 
 class _FKLossFunction(torch.autograd.Function):
-    """losses[2], xyz, uv = f(root_angles, other_angles, bone_lengths | K, scale, root, gt_xyz, gt_uv, vis); xyz / uv carry no
-    gradient (they are what the head returns; the two loss terms are differentiated here)."""
+    """loss_xyz, loss_uv, xyz, uv = f(root_angles, other_angles, bone_lengths | K, scale, root, gt_xyz, gt_uv, vis); xyz / uv
+    carry no gradient (they are what the head returns; the two loss terms are differentiated here).  The terms leave as two
+    0-dim outputs of the node (not as indexed views of one tensor: two SelectBackward nodes and their zero-filled gradient
+    buffers cost more host time than the two kernels of this step)."""
 
     @staticmethod
     @_cabi.on_tensor_device
@@ -127,16 +129,18 @@ class _FKLossFunction(torch.autograd.Function):
         ctx.save_for_backward(root_angles, other_angles, bone_lengths, K, scale, root, gt_xyz, gt_uv, vis, ws)
         ctx.swap, ctx.flags = int(swap), flags
         ctx.mark_non_differentiable(xyz, uv)
-        return losses, xyz, uv
+        ctx.set_materialize_grads(False)
+        return losses[0], losses[1], xyz, uv
 
     @staticmethod
     @_cabi.on_tensor_device
-    def backward(ctx, g_losses, _g_xyz, _g_uv):
+    def backward(ctx, g_lx, g_lu, _g_xyz, _g_uv):
         root_angles, other_angles, bone_lengths, K, scale, root, gt_xyz, gt_uv, vis, ws = ctx.saved_tensors
         lib = _cabi.lib()
         B = root_angles.shape[0]
         dev = root_angles.device
-        g_losses = g_losses.to(torch.float32).contiguous()
+        zero = ws.new_zeros((), dtype=torch.float32) if g_lx is None or g_lu is None else None
+        g_losses = torch.stack([(g if g is not None else zero).to(torch.float32) for g in (g_lx, g_lu)])
         g_ra, g_oa, g_bl = torch.empty_like(root_angles), torch.empty_like(other_angles), torch.empty_like(bone_lengths)
         p = _cabi.ptr
         _cabi.check(lib.mb_fk_loss_backward(root_angles.data_ptr(), other_angles.data_ptr(), bone_lengths.data_ptr(), K.data_ptr(),
@@ -205,8 +209,8 @@ class ForwardKinematicsLoss(nn.Module):
         switched = self.joint_order_switched
         if switched is None:
             switched = _reference_joint_order_switched()
-        losses, xyz, uv = _FKLossFunction.apply(ra, oa, bl, K, sc.reshape(B), root, gt_xyz, gt_uv, vis, not switched, flags)
-        return (losses[0] if self.comp_xyz_loss else None, losses[1] if self.comp_uv_loss else None, xyz, uv)
+        lx, lu, xyz, uv = _FKLossFunction.apply(ra, oa, bl, K, sc.reshape(B), root, gt_xyz, gt_uv, vis, not switched, flags)
+        return (lx if self.comp_xyz_loss else None, lu if self.comp_uv_loss else None, xyz, uv)
 
 
 class _ProjectFunction(torch.autograd.Function):

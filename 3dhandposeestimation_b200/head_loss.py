@@ -16,8 +16,9 @@ from .mano_layer import ManoLayer, _as_f32_cuda
 
 
 class _HeadLossFunction(torch.autograd.Function):
-    """losses[3], joint_xyz21, uv21 = f(rot, coeffs, betas, transl, scale | constants); the last two outputs carry no
-    gradient (they are what the head returns for logging / metrics; the loss terms are differentiated here)."""
+    """loss_xyz, loss_uv, loss_reg, joint_xyz21, uv21 = f(rot, coeffs, betas, transl, scale | constants); the last two outputs
+    carry no gradient (they are what the head returns for logging / metrics; the loss terms are differentiated here).  The
+    terms leave as three 0-dim outputs of the node (indexing one tensor afterwards would add three SelectBackward nodes)."""
 
     @staticmethod
     @_cabi.on_tensor_device
@@ -37,16 +38,19 @@ class _HeadLossFunction(torch.autograd.Function):
         ctx.save_for_backward(rot, coeffs, betas, transl, scale, L, root, K, gt_xyz, gt_uv, vis, xyz, uv, ws)
         ctx.layer, ctx.flags, ctx.swap, ctx.alpha_beta = layer, flags, swap, alpha_beta
         ctx.mark_non_differentiable(xyz, uv)
-        return losses, xyz, uv
+        ctx.set_materialize_grads(False)
+        return losses[0], losses[1], losses[2], xyz, uv
 
     @staticmethod
     @_cabi.on_tensor_device
-    def backward(ctx, g_losses, _g_xyz, _g_uv):
+    def backward(ctx, g_l0, g_l1, g_l2, _g_xyz, _g_uv):
         rot, coeffs, betas, transl, scale, L, root, K, gt_xyz, gt_uv, vis, xyz, uv, ws = ctx.saved_tensors
         lib = _cabi.lib()
         layer = ctx.layer
         B, nc, dev = rot.shape[0], coeffs.shape[1], rot.device
-        g_losses = g_losses.to(torch.float32).contiguous()
+        gs = (g_l0, g_l1, g_l2)
+        zero = ws.new_zeros((), dtype=torch.float32) if any(g is None for g in gs) else None
+        g_losses = torch.stack([(g if g is not None else zero).to(torch.float32) for g in gs])
         g_rot, g_coeffs, g_betas = torch.empty_like(rot), torch.empty_like(coeffs), torch.empty_like(betas)
         g_transl = torch.empty_like(transl) if transl is not None and ctx.needs_input_grad[3] else None
         g_scale = torch.empty_like(scale) if scale is not None and ctx.needs_input_grad[4] else None
@@ -135,7 +139,7 @@ class ManoHeadLoss(nn.Module):
                 raise RuntimeError("expected transl[B,3]")
         if scale is not None:
             scale = _as_f32_cuda(scale, "scale", dev).reshape(B)
-        losses, xyz, uv = _HeadLossFunction.apply(rot, pose, beta, transl, scale, L, root, K, gt_xyz, gt_uv, vis, layer, flags, swap,
-                                                   self.alpha_beta)
-        return (losses[0] if self.comp_xyz_loss else None, losses[1] if self.comp_uv_loss else None,
-                losses[2] if self.comp_regularization_loss else None, xyz, uv)
+        lx, lu, lr, xyz, uv = _HeadLossFunction.apply(rot, pose, beta, transl, scale, L, root, K, gt_xyz, gt_uv, vis, layer, flags, swap,
+                                                       self.alpha_beta)
+        return (lx if self.comp_xyz_loss else None, lu if self.comp_uv_loss else None,
+                lr if self.comp_regularization_loss else None, xyz, uv)

@@ -692,7 +692,14 @@ def run_extras(args, pkg, layer45, dev, rank, world, dist, set0):
     a3 = copy.copy(args)
     a3.workload, a3.hands, a3.steps = "fk", 1 << 20, max(8, min(args.steps, 20))
     fk = run_secondary(a3, pkg, layer45, dev, rank, world, dist)
+    # the same kernels on 2^20 - 1 samples (several tiles per persistent warp, a partial last tile): their HBM rooflines
+    a3b = copy.copy(a3)
+    a3b.hands, a3b.steps = (1 << 20) - 1, 4
+    fkb = run_secondary(a3b, pkg, layer45, dev, rank, world, dist)
     out["config3_fk"] = {"samples": 65536, "c_abi_graph_ms_per_step": fk["ms_per_step"], "c_abi_graph_samples_per_s": fk["value"],
+                         "at_1048575_samples": {"c_abi_graph_ms_per_step": fkb["ms_per_step"], "roofline": fkb["roofline"],
+                                                "fk_loss_c_abi_graph_ms_per_step": fkb["fk_loss"]["c_abi_graph_ms_per_step"],
+                                                "fk_loss_c_abi_graph_samples_per_s": fkb["fk_loss"]["c_abi_graph_samples_per_s"]},
                          "module_api_ms_per_step": fk["module_api"]["ms_per_step"], "module_api_samples_per_s": fk["module_api"]["value"],
                          "fk_loss": fk["fk_loss"],
                          "roofline": fk["roofline"], "mpjpe_mm": fk["mpjpe_mm"]}
