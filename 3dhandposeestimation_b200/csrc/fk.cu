@@ -355,7 +355,8 @@ extern "C" int mb_fk_loss_forward(const float* root_angles, const float* other_a
         return MB_E_NULL;
     StageTimer t(ST_FK_FWD, s);
     const FkIn in = {root_angles, other_angles, bone_lengths, K, index_root_bone_length, kp_coord_xyz_root};
-    const int bulk_ok = aligned16({root_angles, other_angles, bone_lengths, K, index_root_bone_length, kp_coord_xyz_root, xyz, uv});
+    const int bulk_ok = aligned16({root_angles, other_angles, bone_lengths, K, index_root_bone_length, kp_coord_xyz_root, xyz, uv,
+                                   (flags & MB_HEAD_XYZ) ? gt_xyz : nullptr, (flags & MB_HEAD_UV) ? gt_uv : nullptr});
     const FkLoss lo = {(flags & MB_HEAD_XYZ) ? gt_xyz : nullptr, (flags & MB_HEAD_UV) ? gt_uv : nullptr, keypoint_vis,
                        reinterpret_cast<double*>(workspace), losses};
     if (flags & (MB_HEAD_XYZ | MB_HEAD_UV))

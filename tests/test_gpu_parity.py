@@ -427,6 +427,24 @@ def test_fk_bulk_copy_and_per_element_paths_agree(pkg, cuda_device, B, skip):
     sub = [a[skip:skip + n] for a in args]
     oxyz, ouv = fo.fk_forward(*sub, joint_order_switched=False)
     assert np.abs(copy[0][:n].cpu().numpy() - oxyz).max() < POS_TOL_FK
+    # the one-kernel loss call on the same views / copies (ground truths and visibility offset too)
+    vis = (rs.rand(B + skip, 21) < .8).astype(np.float32)
+    tv, = to_dev(cuda_device, vis)
+    crit = pkg.ForwardKinematicsLoss(cuda_device, joint_order_switched=False)
+
+    def run_loss(ts, gxs, gus, vs):
+        leaves = [x.detach().requires_grad_() for x in ts[:3]]
+        lx, lu, xyz, uv = crit(*leaves, *ts[3:], gxs, gus * 1e3, vs)
+        (lx + 1e-3 * lu).backward()
+        return [lx.detach(), lu.detach(), xyz, uv] + [x.grad for x in leaves]
+
+    lv = run_loss([x[skip:] for x in full], gx[skip:], gu[skip:], tv[skip:])
+    lc = run_loss([x[skip:].clone() for x in full], gx[skip:].clone(), gu[skip:].clone(), tv[skip:].clone())
+    for a, b in zip(lv[2:], lc[2:]):
+        assert torch.equal(a, b)
+    for a, b in zip(lv[:2], lc[:2]):                        # the same fp64 partial sums, added in a different order
+        assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b))
+    assert torch.equal(lv[2], copy[0]) and torch.equal(lv[3], copy[1])
     torch.cuda.synchronize()
 
 
