@@ -907,3 +907,104 @@ def test_layers_on_a_non_current_device(pkg, synth_model):
     assert np.abs(xyz.cpu().numpy() - oxyz).max() < POS_TOL_FK
     assert torch.cuda.current_device() == 0
     torch.cuda.synchronize(dev)
+
+
+@pytest.mark.parametrize("B,shift", [(32, 0), (33, 0), (4099, 0), (4099, 1), (70000, 0)])
+def test_fk_entry_points_write_only_their_outputs(pkg, cuda_device, B, shift):
+    """Guard bands around every output of the FK entry points (bulk-copy path: shift 0 keeps the 16-byte alignment; per-element
+    path: shift 1 float): nothing outside [0, B x width) changes.  compute-sanitizer is not available on the GPU pool."""
+    import torch
+
+    cabi = pkg._cabi
+    lib = pkg.load_library()
+    args = fk_inputs(B, seed=B + shift)
+    ins = to_dev(cuda_device, *args)
+    PAD, SENT = 64, -777.25
+
+    def guarded(width):
+        buf = torch.full((PAD + shift + B * width + PAD,), SENT, device=cuda_device)
+        return buf, buf[PAD + shift:PAD + shift + B * width]
+
+    def intact(buf, width):
+        return bool((buf[:PAD + shift] == SENT).all()) and bool((buf[PAD + shift + B * width:] == SENT).all())
+
+    P = lambda t: t.data_ptr()
+    st = cabi.stream_handle(cuda_device)
+    bx, xyz = guarded(63)
+    bu, uv = guarded(42)
+    cabi.check(lib.mb_fk_forward(*[P(t) for t in ins], B, 0, P(xyz), P(uv), st), "fk_forward")
+    assert intact(bx, 63) and intact(bu, 42)
+    assert not bool((xyz == SENT).any()) and not bool((uv == SENT).any())
+    rs = np.random.RandomState(1)
+    gx, gu, vis = to_dev(cuda_device, rs.randn(B, 21, 3).astype(np.float32), rs.randn(B, 21, 2).astype(np.float32),
+                         (rs.rand(B, 21) < .8).astype(np.float32))
+    outs = [guarded(w) for w in (3, 23, 20)]
+    cabi.check(lib.mb_fk_backward(*[P(t) for t in ins], P(gx), P(gu), B, 0, *[P(o[1]) for o in outs], st), "fk_backward")
+    for (buf, view), w in zip(outs, (3, 23, 20)):
+        assert intact(buf, w) and not bool((view == SENT).any())
+    # the one-kernel loss pair
+    bx2, xyz2 = guarded(63)
+    bu2, uv2 = guarded(42)
+    losses = torch.full((2 + 2 * PAD,), SENT, device=cuda_device)
+    ws = torch.zeros(8, dtype=torch.float64, device=cuda_device)
+    both = cabi.HEAD_XYZ | cabi.HEAD_UV
+    cabi.check(lib.mb_fk_loss_forward(*[P(t) for t in ins], P(gx), P(gu), P(vis), B, 0, both, P(xyz2), P(uv2), P(losses[PAD:]),
+                                      P(ws), 64, st), "fk_loss_forward")
+    assert intact(bx2, 63) and intact(bu2, 42) and torch.equal(xyz2, xyz) and torch.equal(uv2, uv)
+    assert bool((losses[:PAD] == SENT).all()) and bool((losses[PAD + 2:] == SENT).all()) and not bool((losses[PAD:PAD + 2] == SENT).any())
+    g_l = torch.tensor([1.0, 1e-3], device=cuda_device)
+    outs2 = [guarded(w) for w in (3, 23, 20)]
+    cabi.check(lib.mb_fk_loss_backward(*[P(t) for t in ins], P(gx), P(gu), P(vis), B, 0, both, P(g_l), *[P(o[1]) for o in outs2],
+                                       P(ws), 64, st), "fk_loss_backward")
+    for (buf, view), w in zip(outs2, (3, 23, 20)):
+        assert intact(buf, w) and not bool((view == SENT).any())
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("B,inference", [(8195, False), (8195, True), (37921, False), (100, False)])
+def test_mano_entry_points_write_only_their_outputs(pkg, synth_model, cuda_device, B, inference):
+    """Guard bands around verts / joints / the three gradients and BEHIND the declared workspace of mb_mano_forward /
+    mb_mano_backward (ragged batches: the fused forward's 64-hand tiles, its 256-bit scratch stores into 32-hand groups, the
+    lane = hand backward).  compute-sanitizer is not available on the GPU pool."""
+    import torch
+
+    cabi = pkg._cabi
+    lib = pkg.load_library()
+    nc = 45
+    layer = pkg.ManoLayer(cuda_device, model=synth_model, pose_num=nc)
+    layer._require_device()
+    rot, pose, beta = to_dev(cuda_device, *mano_inputs(B, nc, 77))
+    PAD, SENT = 4096, -777.25
+    mode = layer._mode | (cabi.FWD_INFERENCE if inference else 0)
+
+    def guarded(n):
+        buf = torch.full((PAD + n + PAD,), SENT, device=cuda_device)
+        return buf, buf[PAD:PAD + n]
+
+    def intact(buf, n):
+        return bool((buf[:PAD] == SENT).all()) and bool((buf[PAD + n:] == SENT).all())
+
+    P = lambda t: t.data_ptr()
+    st = cabi.stream_handle(cuda_device)
+    nws = lib.mb_mano_workspace_bytes(B, layer._mode)
+    wsbuf = torch.full((nws + 65536,), 0x5a, dtype=torch.uint8, device=cuda_device)
+    bv, verts = guarded(B * 778 * 3)
+    bj, joints = guarded(B * 21 * 3)
+    cabi.check(lib.mb_mano_forward(P(layer._blob), nc, P(rot), P(pose), P(beta), B, mode, P(verts), P(joints), P(wsbuf), nws, st), "fwd")
+    assert intact(bv, B * 778 * 3) and intact(bj, B * 63)
+    assert not bool((verts == SENT).any()) and not bool((joints == SENT).any())
+    assert bool((wsbuf[nws:] == 0x5a).all())
+    ov, oj = mo.mano_forward(synth_model, *[t.cpu().numpy() for t in (rot[-3:], pose[-3:], beta[-3:])])
+    assert np.abs(verts.view(B, 778, 3)[-3:].cpu().numpy() - ov).max() < POS_TOL_REF
+    if inference:
+        return
+    gv = torch.randn(B, 778, 3, device=cuda_device)
+    gj = torch.randn(B, 21, 3, device=cuda_device)
+    outs = [guarded(B * w) for w in (3, nc, 10)]
+    cabi.check(lib.mb_mano_backward(P(layer._blob), nc, P(rot), P(pose), P(beta), P(gv), P(gj), B, layer._mode, cabi.BWD_WORKSPACE_VALID,
+                                    *[P(o[1]) for o in outs], P(wsbuf), nws, st), "bwd")
+    for (buf, view), w in zip(outs, (3, nc, 10)):
+        assert intact(buf, B * w) and not bool((view == SENT).any())
+    assert bool((wsbuf[nws:] == 0x5a).all())
+    torch.cuda.synchronize()
+
