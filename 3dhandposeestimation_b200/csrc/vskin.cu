@@ -469,12 +469,16 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                     const long long group = (long long)tile * 2 + set;
                     const int pos3 = valid ? __float_as_int(tm.w) : -1;
                     if (group * 32 < B && pos3 >= 0) {
-                        float* dst = v_posed_t + ((size_t)group * SK_NCOORD + pos3) * 32;
+                        // 0x40000: experiment — every group's scratch lands on group 0's 300 KB (L2-resident: the stores' SM-side cost
+                        // without their DRAM traffic); 0x80000: experiment — no scratch stores at all
+                        float* dst = v_posed_t + ((size_t)((variant & 0x40000) ? 0 : group) * SK_NCOORD + pos3) * 32;
+                        if (!(variant & (0x80000 | 0x100000))) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            st_global_v8(dst + 8 * k, &X[8 * k]);
-                            st_global_v8(dst + 32 + 8 * k, &Y[8 * k]);
-                            st_global_v8(dst + 64 + 8 * k, &Z[8 * k]);
+                            for (int k = 0; k < 4; ++k) {
+                                st_global_v8(dst + 8 * k, &X[8 * k]);
+                                st_global_v8(dst + 32 + 8 * k, &Y[8 * k]);
+                                st_global_v8(dst + 64 + 8 * k, &Z[8 * k]);
+                            }
                         }
                     }
                 }
@@ -531,6 +535,10 @@ vskin_forward_kernel(const TcBlobHeader* __restrict__ hdr, const unsigned char* 
                             if (hand < B && 3 * lane < nfl && !(variant & 0x100)) {      // 0x100: experiment, no global stores
                                 float* dst = run0 + (size_t)hi * NVC + 3 * lane;
                                 __stcs(dst, o[0]); __stcs(dst + 1, o[1]); __stcs(dst + 2, o[2]);
+                                if ((variant & 0x100000) && v_posed_t != nullptr) {   // 0x100000: experiment, scratch in verts' layout
+                                    float* ds = v_posed_t + (size_t)hand * NVC + 3 * (t * VS_M + q * 32) + 3 * lane;
+                                    __stcs(ds, x); __stcs(ds + 1, y); __stcs(ds + 2, z);
+                                }
                             }
                         }
                         if (tipslot >= 0 && valid) {
