@@ -155,10 +155,11 @@ class ManoLayer(nn.Module):
     numpy arrays with the pkl's keys, e.g. ``assets.synthetic_mano()``) instead
     of a pkl path; ``mode`` in {"fp32", "f16x3", "f16"} selects the blend-shape
     contraction precision; ``keep_workspace`` trades 12 KB/hand of retained
-    memory for not recomputing the forward in the backward; ``fused_forward`` forces
-    (True) or forbids (False) the fused blend + skinning kernel with lane = vertex
-    (csrc/vskin.cu) from 8 192 hands on — by default the library picks the measured
-    faster of the two forward implementations.
+    memory for not recomputing the forward in the backward; ``fused_forward=False``
+    selects the two separate forward kernels (blend contraction + lane = hand skinning)
+    instead of the fused blend + skinning kernel with lane = vertex (csrc/vskin.cu) that
+    runs from 8 192 hands on by default (the measured faster one, with and without a
+    backward to follow).
     """
 
     def __init__(self, device, MANO_RIGHT_pkl=None, bases_num=10, pose_num=6, *, model=None, mode="f16x3",
