@@ -501,6 +501,15 @@ def test_fk_loss_one_call_matches_oracle_and_the_separate_dropins(pkg, cuda_devi
     assert abs(float(total2) - float(total)) <= 2e-6 * abs(float(total))
     for g, x in zip(got, t[:3]):
         assert rel(g.cpu().numpy(), x.grad.cpu().numpy()) < 1e-5
+    if use_xyz and use_uv:
+        # both terms computed, only ONE differentiated: the other term's upstream gradient is None inside the node
+        for x in t[:3]:
+            x.grad = None
+        lx3, lu3, _, _ = crit(*t, *tg)
+        lu3.backward()
+        want = fo.fk_backward(*args, None, fo.l2loss_backward(ouv, gt_uv, vis), joint_order_switched=switched)
+        for x, w in zip(t[:3], want):
+            assert rel(x.grad.cpu().numpy(), w) < GRAD_TOL
     torch.cuda.synchronize()
 
 
