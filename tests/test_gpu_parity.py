@@ -476,10 +476,10 @@ def test_fk_loss_one_call_matches_oracle_and_the_separate_dropins(pkg, cuda_devi
     # oracle losses on the kernel's own fp32 outputs (the reduction), then the full fp64 chain for the gradients
     if use_xyz:
         want = fo.l2loss(xyz.cpu().numpy(), gt_xyz, vis)
-        assert abs(float(lx) - want) <= 1e-5 * abs(want) + 1e-12
+        assert abs(float(lx.detach()) - want) <= 1e-5 * abs(want) + 1e-12
     if use_uv:
         want = fo.l2loss(uv.cpu().numpy(), gt_uv, vis)
-        assert abs(float(lu) - want) <= 1e-5 * abs(want) + 1e-12
+        assert abs(float(lu.detach()) - want) <= 1e-5 * abs(want) + 1e-12
     if not (use_xyz or use_uv):
         return
     total = (wx * lx if use_xyz else 0.) + (wu * lu if use_uv else 0.)
@@ -498,7 +498,7 @@ def test_fk_loss_one_call_matches_oracle_and_the_separate_dropins(pkg, cuda_devi
     assert torch.equal(xyz2.detach(), xyz) and torch.equal(uv2.detach(), uv)
     total2 = (wx * l2(xyz2, tg[0], tg[2]) if use_xyz else 0.) + (wu * l2(uv2, tg[1], tg[2]) if use_uv else 0.)
     total2.backward()
-    assert abs(float(total2) - float(total)) <= 2e-6 * abs(float(total))
+    assert abs(float(total2.detach()) - float(total.detach())) <= 2e-6 * abs(float(total.detach()))
     for g, x in zip(got, t[:3]):
         assert rel(g.cpu().numpy(), x.grad.cpu().numpy()) < 1e-5
     if use_xyz and use_uv:
