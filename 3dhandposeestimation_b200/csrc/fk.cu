@@ -1,8 +1,8 @@
 // fk.cu — RHD 21-joint forward-kinematics layer + pinhole projection, forward and backward.
 // One thread per sample (59 floats in, 105 out — no cross-sample data).  A warp owns 32 consecutive samples and private
 // shared-memory tiles laid out exactly like the global arrays (dense rows), so a tile moves with ONE bulk copy (TMA engine) per
-// array and direction: no per-element staging loops, no block barriers, the next tile's inputs are requested before this
-// tile's results leave.  [round 1 ncu: the cp.async / st.global staging loops of the 64-thread-block version were ~37 % of the
+// array and direction: no per-element staging loops, no block barriers; the next tile's inputs are requested as soon as this
+// tile's results have been handed to the copy engine (its stores only read the result tiles).  [round 1 ncu: the cp.async / st.global staging loops of the 64-thread-block version were ~37 % of the
 // kernel's instructions at 46 % issue utilisation and 14 % occupancy.]  Dense pitches cost a 4-way bank conflict on the 20
 // bone-length reads and a 2-way one on the 42 uv writes of a sample; every other row pitch (3, 23, 9, 1, 63) is odd.
 // The last (partial) tile of a batch and unaligned pointers take plain per-element loops.  Math in fk_math.cuh (reference
